@@ -1,0 +1,321 @@
+"""ctypes front-end of the CPU oracle (oracle/hitl_oracle.hpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (hitl_slam_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+
+
+def build(ref=True):
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    subprocess.run(["make", "-s", "-C", HERE] + ([] if ref else ["_build/liboracle.so"]), check=True)
+
+
+def _load(name):
+    path = os.path.join(HERE, "_build", name)
+    if not os.path.exists(path):
+        build()
+    return C.CDLL(path)
+
+
+class Oracle:
+    """One loaded oracle library (parity build by default, `fast=True` for the timing build)."""
+
+    def __init__(self, fast=False):
+        self.lib = lib = _load("liboracle_fast.so" if fast else "liboracle.so")
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_int]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_flatten.argtypes = [C.c_void_p, _f32p, _i32p, _i32p]
+        lib.orc_query.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
+        lib.orc_radius.restype = C.c_uint32
+        lib.orc_radius.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, _i32p, C.c_uint32]
+        lib.orc_relative_pose.argtypes = [_f64p, C.c_uint32, C.c_uint32, _f32p]
+        lib.orc_find_stf.argtypes = [C.c_void_p, _f64p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int,
+                                     C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _u64p]
+        lib.orc_get_stf.argtypes = [C.c_void_p, _u32p, _u32p, _u64p, _u32p, _u32p]
+        lib.orc_find_vo.restype = C.c_uint64
+        lib.orc_find_vo.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, C.c_float, C.c_float]
+        lib.orc_get_vo.argtypes = [C.c_void_p, _u32p, _u32p, _u32p]
+        lib.orc_world_transform.argtypes = [C.c_void_p, _f32p, _f32p]
+        lib.orc_em_inliers.restype = C.c_uint64
+        lib.orc_em_inliers.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_double, _u32p, _u32p, C.c_uint64]
+        lib.orc_em_assign.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_double, C.c_uint32, _u32p,
+                                      _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
+        lib.orc_em_run.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _i32p, _i32p, _i32p]
+        lib.orc_seg_fit.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p]
+        lib.orc_distance_to_line_segment.restype = C.c_float
+        lib.orc_distance_to_line_segment.argtypes = [_f32p, C.c_float, C.c_float]
+        lib.orc_dist_to_line_seg.restype = C.c_double
+        lib.orc_dist_to_line_seg.argtypes = [_f32p, C.c_float, C.c_float]
+        lib.orc_eval_stf.argtypes = [C.c_void_p, _f64p, C.c_uint64, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_float,
+                                     C.c_float, _f64p, C.c_void_p, C.c_int]
+        lib.orc_odometry_consts.argtypes = [_f32p, C.c_uint32, _f32p]
+        lib.orc_eval_odometry.argtypes = [_f32p, _f64p, C.c_uint32, _f64p, C.c_void_p]
+        lib.orc_human_blocks.argtypes = [_f32p, C.c_uint32, _i32p, _f32p, _i32p, _f64p]
+        lib.orc_eval_human.argtypes = [C.c_uint32, _i32p, _f64p, _f64p, _f64p, C.c_void_p]
+        lib.orc_eval_p2l_glob.argtypes = [C.c_uint32, _u32p, _u64p, _f32p, _f32p, _f32p, _u8p, C.c_float, C.c_float,
+                                          _f64p, _f64p, C.c_void_p]
+        lib.orc_eval_p2l.argtypes = [C.c_uint64, _u32p, _f32p, _f32p, _f32p, _u8p, C.c_float, C.c_float, _f64p,
+                                     _f64p, C.c_void_p]
+        lib.orc_load_pose_graph.restype = C.c_void_p
+        lib.orc_load_pose_graph.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.orc_pose_graph_get.argtypes = [C.c_void_p, _f32p, _f32p, _u32p, _f32p, _f32p]
+        lib.orc_pose_graph_free.argtypes = [C.c_void_p]
+        lib.orc_sinf.restype = C.c_float
+        lib.orc_sinf.argtypes = [C.c_float]
+        lib.orc_cosf.restype = C.c_float
+        lib.orc_cosf.argtypes = [C.c_float]
+        lib.orc_num_threads.restype = C.c_int
+
+    def num_threads(self):
+        return self.lib.orc_num_threads()
+
+    def scans(self, offsets, pts, nrm, build_trees=True):
+        return OracleScans(self, offsets, pts, nrm, build_trees)
+
+    def load_pose_graph(self, path):
+        n, m = C.c_uint64(), C.c_uint64()
+        h = self.lib.orc_load_pose_graph(path.encode(), C.byref(n), C.byref(m))
+        if not h:
+            raise IOError(path)
+        poses = np.zeros(3 * n.value, np.float32)
+        cov = np.zeros(9 * n.value, np.float32)
+        off = np.zeros(n.value + 1, np.uint32)
+        pts = np.zeros(2 * m.value, np.float32)
+        nrm = np.zeros(2 * m.value, np.float32)
+        self.lib.orc_pose_graph_get(h, poses, cov, off, pts, nrm)
+        self.lib.orc_pose_graph_free(h)
+        return dict(poses=poses.reshape(-1, 3), cov=cov.reshape(-1, 9), offsets=off, pts=pts.reshape(-1, 2),
+                    nrm=nrm.reshape(-1, 2))
+
+    def em_inliers(self, offsets, world, seg, thr=0.03):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        world = np.ascontiguousarray(world, np.float32).reshape(-1)
+        cap = len(world) // 2
+        op, oi = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        n = self.lib.orc_em_inliers(len(offsets) - 1, offsets, world, np.ascontiguousarray(seg, np.float32), thr, op, oi, cap)
+        return op[:n].copy(), oi[:n].copy()
+
+    def em_assign(self, offsets, world, segs, thr=0.03, min_obs=5):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        world = np.ascontiguousarray(world, np.float32).reshape(-1)
+        n, m = len(offsets) - 1, len(world) // 2
+        ns = np.zeros(2, np.uint32)
+        out = []
+        bufs = [(np.zeros(n, np.uint32), np.zeros(n + 1, np.uint64), np.zeros(m, np.uint32)) for _ in range(2)]
+        self.lib.orc_em_assign(n, offsets, world, np.ascontiguousarray(segs, np.float32).reshape(-1), thr, min_obs, ns,
+                               bufs[0][0], bufs[0][1], bufs[0][2], bufs[1][0], bufs[1][1], bufs[1][2])
+        for f in range(2):
+            k = int(ns[f])
+            off = bufs[f][1][:k + 1].copy()
+            out.append((bufs[f][0][:k].copy(), off, bufs[f][2][:int(off[-1])].copy()))
+        return out
+
+    def em_run(self, offsets, world, segs):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        world = np.ascontiguousarray(world, np.float32).reshape(-1)
+        n = len(offsets) - 1
+        s = np.ascontiguousarray(segs, np.float32).reshape(-1).copy()
+        ret = np.zeros(6, np.int32)
+        cor, anc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.lib.orc_em_run(n, offsets, world, s, ret, cor, anc)
+        return dict(segs=s.reshape(4, 2), corrected=cor[:ret[0]].copy(), anchor=anc[:ret[1]].copy(),
+                    backprop=(int(ret[2]), int(ret[3])), swapped=bool(ret[4]), rounds=int(ret[5]))
+
+    def seg_fit(self, p1, p2, data):
+        out = np.zeros(4, np.float32)
+        data = np.ascontiguousarray(data, np.float64).reshape(-1)
+        self.lib.orc_seg_fit(np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64), data, len(data) // 2, out)
+        return out.reshape(2, 2)
+
+    def odometry_consts(self, poses_f32):
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+        n = len(p) // 3
+        c = np.zeros(9 * (n - 1), np.float32)
+        self.lib.orc_odometry_consts(p, n, c)
+        return c.reshape(-1, 9)
+
+    def eval_odometry(self, consts, poses_f64, want_jac=True):
+        p = np.ascontiguousarray(poses_f64, np.float64).reshape(-1)
+        n = len(p) // 3
+        r = np.zeros(3 * (n - 1))
+        J = np.zeros(18 * (n - 1)) if want_jac else None
+        self.lib.orc_eval_odometry(np.ascontiguousarray(consts, np.float32).reshape(-1), p, n, r, J.ctypes.data if want_jac else None)
+        return r.reshape(-1, 3), (J.reshape(-1, 2, 3, 3) if want_jac else None)
+
+    def human_blocks(self, poses_f32, hc_i, hc_f):
+        hc_i = np.ascontiguousarray(hc_i, np.int32).reshape(-1, 3)
+        hc_f = np.ascontiguousarray(hc_f, np.float32).reshape(-1, 4)
+        n = len(hc_i)
+        bi, bd = np.zeros(2 * n, np.int32), np.zeros(4 * n)
+        self.lib.orc_human_blocks(np.ascontiguousarray(poses_f32, np.float32).reshape(-1), n, hc_i.reshape(-1), hc_f.reshape(-1), bi, bd)
+        return bi.reshape(-1, 2), bd.reshape(-1, 4)
+
+    def eval_human(self, blk_i, blk_d, poses_f64, want_jac=True):
+        n = len(blk_i)
+        r = np.zeros(3 * n)
+        J = np.zeros(9 * n) if want_jac else None
+        self.lib.orc_eval_human(n, np.ascontiguousarray(blk_i, np.int32).reshape(-1), np.ascontiguousarray(blk_d, np.float64).reshape(-1),
+                                np.ascontiguousarray(poses_f64, np.float64).reshape(-1), r, J.ctypes.data if want_jac else None)
+        return r.reshape(-1, 3), (J.reshape(-1, 3, 3) if want_jac else None)
+
+    def eval_p2l_glob(self, blk_pose, blk_off, pts, line_n, line_off, valid, std_dev, corr, poses_f64, want_jac=True):
+        nb = len(blk_pose)
+        r = np.zeros(nb)
+        J = np.zeros(3 * nb) if want_jac else None
+        self.lib.orc_eval_p2l_glob(nb, np.ascontiguousarray(blk_pose, np.uint32), np.ascontiguousarray(blk_off, np.uint64),
+                                   np.ascontiguousarray(pts, np.float32).reshape(-1), np.ascontiguousarray(line_n, np.float32).reshape(-1),
+                                   np.ascontiguousarray(line_off, np.float32), np.ascontiguousarray(valid, np.uint8), std_dev, corr,
+                                   np.ascontiguousarray(poses_f64, np.float64).reshape(-1), r, J.ctypes.data if want_jac else None)
+        return r, (J.reshape(-1, 3) if want_jac else None)
+
+    def eval_p2l(self, pose_idx, pts, line_n, line_off, valid, std_dev, corr, poses_f64, want_jac=True):
+        n = len(pose_idx)
+        r = np.zeros(n)
+        J = np.zeros(3 * n) if want_jac else None
+        self.lib.orc_eval_p2l(n, np.ascontiguousarray(pose_idx, np.uint32), np.ascontiguousarray(pts, np.float32).reshape(-1),
+                              np.ascontiguousarray(line_n, np.float32).reshape(-1), np.ascontiguousarray(line_off, np.float32),
+                              np.ascontiguousarray(valid, np.uint8), std_dev, corr,
+                              np.ascontiguousarray(poses_f64, np.float64).reshape(-1), r, J.ctypes.data if want_jac else None)
+        return r, (J.reshape(-1, 3) if want_jac else None)
+
+
+class OracleScans:
+    def __init__(self, orc, offsets, pts, nrm, build_trees=True):
+        self.orc, self.lib = orc, orc.lib
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        self.pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
+        self.nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1)
+        self.n = len(self.offsets) - 1
+        self.h = self.lib.orc_create(self.n, self.offsets, self.pts, self.nrm, int(build_trees))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def flatten(self):
+        m = int(self.offsets[-1])
+        pn, idx, dim = np.zeros(4 * m, np.float32), np.zeros(m, np.int32), np.zeros(m, np.int32)
+        self.lib.orc_flatten(self.h, pn, idx, dim)
+        return pn.reshape(-1, 4), idx, dim
+
+    def query(self, scan, q, thr, mode=0):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1)
+        n = len(q) // 2
+        d, i = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.orc_query(self.h, scan, n, q, thr, mode, d, i)
+        return d, i
+
+    def radius(self, scan, qx, qy, thr):
+        cap = int(self.offsets[scan + 1] - self.offsets[scan])
+        idx = np.zeros(max(cap, 1), np.int32)
+        n = self.lib.orc_radius(self.h, scan, qx, qy, thr, idx, cap)
+        return idx[:n].copy()
+
+    def find_stf(self, poses, min_pose=0, max_pose=None, thr=0.15, min_cos=None, cap=6, skip=1, min_corr=10,
+                 src_lo=0, src_hi=None):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        if max_pose is None:
+            max_pose = self.n - 1
+        if min_cos is None:
+            min_cos = default_min_cos()
+        if src_hi is None:
+            src_hi = 2 ** 62
+        counts = np.zeros(3, np.uint64)
+        self.lib.orc_find_stf(self.h, poses, min_pose, max_pose, thr, min_cos, cap, skip, min_corr, src_lo, src_hi, counts)
+        npairs, nm = int(counts[0]), int(counts[1])
+        pi, pj = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32)
+        off = np.zeros(npairs + 1, np.uint64)
+        k, idx = np.zeros(nm, np.uint32), np.zeros(nm, np.uint32)
+        self.lib.orc_get_stf(self.h, pi, pj, off, k, idx)
+        return dict(pair_i=pi, pair_j=pj, pair_off=off, k=k, idx=idx, n_queries=int(counts[2]))
+
+    def find_vo(self, poses, min_pose=0, max_pose=None, thr=0.15, min_cos=None):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        if max_pose is None:
+            max_pose = self.n - 1
+        if min_cos is None:
+            min_cos = default_min_cos()
+        n = self.lib.orc_find_vo(self.h, poses, min_pose, max_pose, thr, min_cos)
+        sp, sk, tk = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.lib.orc_get_vo(self.h, sp, sk, tk)
+        return sp, sk, tk
+
+    def world_transform(self, poses_f32):
+        out = np.zeros(len(self.pts), np.float32)
+        self.lib.orc_world_transform(self.h, np.ascontiguousarray(poses_f32, np.float32).reshape(-1), out)
+        return out.reshape(-1, 2)
+
+    def eval_stf(self, poses, corr, std_dev=0.05, corr_factor=1.0 / 40.0, want_jac=True, parallel=False):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        nb = len(corr["pair_i"])
+        r = np.zeros(2 * nb)
+        J = np.zeros(12 * nb) if want_jac else None
+        self.lib.orc_eval_stf(self.h, poses, nb, corr["pair_i"], corr["pair_j"], corr["pair_off"], corr["k"], corr["idx"],
+                              std_dev, corr_factor, r, J.ctypes.data if want_jac else None, int(parallel))
+        return r.reshape(-1, 2), (J.reshape(-1, 2, 2, 3) if want_jac else None)
+
+
+def default_min_cos():
+    """cos(max_stf_angle_error = deg2rad(25)) as a float (config/non_markov_localization.cfg:48,
+    JointOptimization.cpp:564); the angle option is a float, the cosine is stored to a float."""
+    ang = np.float32(np.deg2rad(25.0))
+    return float(np.float32(np.cos(np.float64(ang))))
+
+
+class RefKDTree:
+    """The reference's own KDTree<float,2> (oracle/_ref/libkdtree_ref.so), when it was built."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libkdtree_ref.so"))
+
+    def __init__(self, pts, nrm):
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libkdtree_ref.so"))
+        lib.ref_kd_create.restype = C.c_void_p
+        lib.ref_kd_create.argtypes = [C.c_uint32, _f32p, _f32p]
+        lib.ref_kd_destroy.argtypes = [C.c_void_p]
+        lib.ref_kd_flatten.argtypes = [C.c_void_p, _f32p, _i32p, _i32p]
+        lib.ref_kd_query.argtypes = [C.c_void_p, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
+        lib.ref_kd_radius.restype = C.c_uint32
+        lib.ref_kd_radius.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _i32p, C.c_uint32]
+        self.pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
+        self.nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1)
+        self.n = len(self.pts) // 2
+        self.h = lib.ref_kd_create(self.n, self.pts, self.nrm)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_kd_destroy(self.h)
+            self.h = None
+
+    def flatten(self):
+        pn, idx, dim = np.zeros(4 * self.n, np.float32), np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self.lib.ref_kd_flatten(self.h, pn, idx, dim)
+        return pn.reshape(-1, 4), idx, dim
+
+    def query(self, q, thr, mode=0):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1)
+        n = len(q) // 2
+        d, i = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.ref_kd_query(self.h, n, q, thr, mode, d, i)
+        return d, i
+
+    def radius(self, qx, qy, thr):
+        idx = np.zeros(max(self.n, 1), np.int32)
+        n = self.lib.ref_kd_radius(self.h, qx, qy, thr, idx, self.n)
+        return idx[:n].copy()
