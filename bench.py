@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+
+One "step" = one pass of the hot path over the synthetic map: FindSTFCorrespondences over all
+ordered pose pairs + one residual/Jacobian/normal-equation evaluation of the resulting blocks
+(+ odometry blocks).  Metric: M correspondence+Jacobian evals/s = (KD queries the reference
+semantics execute + matched correspondences pushed through residual+Jacobian) / time.
+
+ * value      whole-job throughput, scans/trees resident in HBM, CUDA events on the library's stream
+ * e2e        same metric through the C ABI with HOST buffers: scans + trees + poses H2D, CSR +
+              residuals + Jacobians D2H inside the timed region
+ * roofline   stf_search_kernel: algorithmic bytes (40 B/query + 8 B/match) / kernel time
+ * cpu_baseline  the oracle port (OpenMP over source poses, reference flags) on a bounded sample
+ * --impl reference   the same oracle on the host cores as the reference arm
+Multi-GPU: source poses are sharded by point count (no data-path collective in the search);
+the per-iteration exchange is one NCCL all-reduce of the packed normal-equation blocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "correspondence+Jacobian evals/s"
+UNIT = "M evals/s"
+STD_DEV, CORR = 0.05, 1.0 / 40.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(name, n_poses=None, beams=None):
+    from hitl_slam_b200 import synth
+    cache = os.path.join(os.environ.get("HITL_SYNTH_DIR", "/tmp/hitl_synth"), "%s_%s_%s.npz" % (name, n_poses, beams))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return {k: z[k] for k in z.files}
+    g = synth.generate(name, n_poses=n_poses, beams=beams)
+    out = {k: g[k] for k in ("poses", "offsets", "pts", "nrm")}
+    os.makedirs(os.path.dirname(cache), exist_ok=True)
+    np.savez(cache, **out)
+    return out
+
+
+def cpu_sample(g, seconds=15.0, threads=None):
+    """Oracle port timed on the host cores on a bounded sample: chunks of source poses spread over the
+    trajectory against ALL target poses (search) + evaluation of the blocks they produce."""
+    from oracle.pyoracle import Oracle
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    orc = Oracle(fast=True)
+    S = orc.scans(g["offsets"], g["pts"], g["nrm"])
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    cores = orc.num_threads()
+    chunk = max(cores, 8)
+    starts = list(range(0, max(n - chunk, 1), max((n - chunk) // 7, 1)))[:8] if n > 2 * chunk else [0]
+    evals, t_used, n_src, t_search, t_eval, queries, matches = 0, 0.0, 0, 0.0, 0.0, 0, 0
+    rounds = 0
+    while t_used < seconds and rounds < 64:
+        progressed = False
+        for s in starts:
+            lo = s + rounds * chunk
+            hi = min(lo + chunk, n)
+            if lo >= n or (rounds and lo >= s + max((n - chunk) // 7, 1)):
+                continue
+            t0 = time.perf_counter()
+            r = S.find_stf(poses, src_lo=lo, src_hi=hi)
+            t1 = time.perf_counter()
+            S.eval_stf(poses, r, STD_DEV, CORR, want_jac=True, parallel=True)
+            t2 = time.perf_counter()
+            t_search += t1 - t0
+            t_eval += t2 - t1
+            queries += r["n_queries"]
+            matches += len(r["k"])
+            n_src += hi - lo
+            t_used = t_search + t_eval
+            progressed = True
+            if t_used >= seconds:
+                break
+        if not progressed:
+            break
+        rounds += 1
+    evals = queries + matches
+    return {"value": evals / t_used / 1e6 if t_used else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d source poses (8 chunks spread over the trajectory) vs all %d targets: %d queries + %d Jacobian evals in %.1f s "
+                      "(search %.1f s, eval %.1f s); oracle -O3 -march=native -fopenmp" % (n_src, n, n, queries, matches, t_used, t_search, t_eval),
+            "search_Mq_per_s": queries / t_search / 1e6 if t_search else 0.0, "eval_Mm_per_s": matches / t_eval / 1e6 if t_eval else 0.0}
+
+
+def rebuild_fast_oracle_native():
+    """liboracle_fast.so is compiled with -march=native: rebuild it on THIS box's CPU."""
+    try:
+        subprocess.run(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "_build", "liboracle_fast.so")], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        pass
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    rebuild_fast_oracle_native()
+    g = workload(args.workload, args.poses, args.beams)
+    per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    vals = []
+    for it in range(args.warmup + args.steps):
+        r = cpu_sample(g, seconds=per_step)
+        if it >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([x["value"] for x in vals]))
+    last = vals[-1]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / f64 residuals",
+            "data": "synthetic", "config": config_of(args, g),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_of(args, g):
+    return {"workload": "%s: synthetic corridor-lattice map, %d poses x %d beams (%d points) in .stfs.covars format, thr 0.15 m, 25 deg, cap 6, skip 1"
+                        % (args.workload, len(g["poses"]), args.beams or 0, int(g["offsets"][-1])),
+            "n_poses": int(len(g["poses"])), "n_points": int(g["offsets"][-1]),
+            "l2": "scans + trees + record buffers exceed the 126 MB L2; a 512 MB buffer is also written between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--poses", type=int, default=None)
+    ap.add_argument("--beams", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from hitl_slam_b200 import synth
+    if args.beams is None:
+        args.beams = synth.CONFIGS[args.workload]["beams"]
+    if args.poses is None:
+        args.poses = synth.CONFIGS[args.workload]["n_poses"]
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hitl_slam_b200 import HitlGpu, capi
+    from hitl_slam_b200.sharding import shard_ranges
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # rank 0 generates (and caches) the map; the others read the cache
+    if rank == 0:
+        g = workload(args.workload, args.poses, args.beams)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        g = workload(args.workload, args.poses, args.beams)
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    lo, hi = shard_ranges(g["offsets"], world)[rank]
+
+    gpu = HitlGpu(local_rank)
+    stream = torch.cuda.ExternalStream(gpu.lib.hitl_stream(gpu.ctx), device=torch.device("cuda", local_rank))
+    gpu.set_scans(g["offsets"], g["pts"], g["nrm"])
+    t0 = time.perf_counter()
+    gpu.build_kdtrees()
+    t_build = time.perf_counter() - t0
+    nodes = gpu.get_kdtrees()
+    # odometry blocks (all ranks evaluate their share: rank 0 takes them; trivial cost)
+    odo = odometry_consts_host(g["poses"]) if rank == 0 else np.zeros((0, 9), np.float32)
+    gpu.set_odometry_blocks(odo)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    neq_dev = None
+
+    def step():
+        info = gpu.find_stf(poses, src_lo=lo, src_hi=hi, fetch=False)
+        gpu.set_stf_blocks_from_search(STD_DEV, CORR)
+        ne = gpu.normal_eq(poses, fetch=False)
+        if world > 1:
+            nonlocal neq_dev
+            ptr, nd = gpu.normal_eq_device()
+            if neq_dev is None or neq_dev[0] != ptr:
+                neq_dev = (ptr, tensor_from_ptr(ptr, nd, local_rank))
+            with torch.cuda.stream(stream):
+                dist.all_reduce(neq_dev[1])
+        return info, ne
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = gpu.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    infos = []
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # evict L2 between timed steps (not timed)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            starts[k].record()
+        infos.append(step())
+        with torch.cuda.stream(stream):
+            ends[k].record()
+    torch.cuda.synchronize()
+    launches = gpu.launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(infos[-1][0]["n_queries"]), float(infos[-1][0]["n_matches"]), float(infos[-1][0]["n_pairs"]),
+                        float(infos[-1][0]["n_traversals"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt)
+    total_ms = float(t.item())
+    queries, matches, pairs, trav = [int(x) for x in cnt.tolist()]
+    ms_per_step = total_ms / args.steps
+    evals = queries + matches
+    value = evals / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (this rank's launch) ----
+    peak, peak_src = load_peaks()
+    ms_search = float(np.mean([i[0]["ms_search"] for i in infos]))
+    my_q, my_m = infos[-1][0]["n_queries"], infos[-1][0]["n_raw_matches"]
+    alg_bytes = 40.0 * my_q + 8.0 * my_m
+    achieved = alg_bytes / (ms_search * 1e-3) / 1e9
+    roofline = {"kernel": "stf_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "ms_kernel": ms_search, "share_of_step": ms_search / ms_per_step,
+                "note": "algorithmic bytes = 40 B per query + 8 B per match (pair-tile model, SURVEY.md 8d); the kernel proves most queries empty "
+                        "with AABB tests and reuses one source tile across all targets, so it can exceed the stream model"}
+
+    # ---- e2e through the C ABI with host buffers ----
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = g["pts"].nbytes + g["nrm"].nbytes + nodes.nbytes + g["offsets"].nbytes + poses.nbytes * 2
+    d2h = 0
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gpu.set_scans(g["offsets"], g["pts"], g["nrm"])
+        gpu.set_kdtrees(nodes)
+        out = gpu.find_stf(poses, src_lo=lo, src_hi=hi, fetch=True)
+        gpu.set_odometry_blocks(odo)
+        gpu.set_stf_blocks_from_search(STD_DEV, CORR)
+        ev = gpu.eval(poses, fetch=True)
+        d2h = out["pair_i"].nbytes * 2 + out["pair_off"].nbytes + out["k"].nbytes * 2 + ev["r_stf"].nbytes + ev["J_stf"].nbytes + ev["r_odometry"].nbytes + ev["J_odometry"].nbytes
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": evals / float(te.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": float(te.item()) * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, max over ranks"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rebuild_fast_oracle_native()
+        cpu = cpu_sample(g, seconds=args.cpu_seconds)
+
+    if rank == 0:
+        cfg = config_of(args, g)
+        cfg.update({"parallelism": "source-pose shards x%d (scans+trees replicated), 1 all-reduce of packed J^TJ/J^Tr per step" % world if world > 1 else "single GPU",
+                    "kdtree_build_host_s": t_build})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav,
+                           "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos]))}}
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tensor_from_ptr(ptr, n_doubles, device_index):
+    """Wrap the library's resident normal-equation buffer as a torch tensor (no copy) for NCCL."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device=torch.device("cuda", device_index))
+
+
+def odometry_consts_host(poses_f32):
+    """PoseConstraint constants of AddOdometryConstraints (JointOptimization.cpp:736-825) from the float poses
+    (host-side problem building; the non-degenerate branch, float arithmetic)."""
+    p = np.asarray(poses_f32, np.float32)
+    t = (p[1:, :2] - p[:-1, :2]).astype(np.float32)
+    a = (-p[:-1, 2]).astype(np.float32)
+    c, s = np.cos(a).astype(np.float32), np.sin(a).astype(np.float32)
+    rx, ry = (c * t[:, 0] - s * t[:, 1]).astype(np.float32), (s * t[:, 0] + c * t[:, 1]).astype(np.float32)
+    nr = np.sqrt(rx * rx + ry * ry).astype(np.float32)
+    nr[nr == 0] = 1
+    rx, ry = rx / nr, ry / nr
+    rot = (p[1:, 2] - p[:-1, 2]).astype(np.float64)
+    rot = (rot - 2 * np.pi * np.rint(rot / (2 * np.pi))).astype(np.float32)
+    out = np.zeros((len(p) - 1, 9), np.float32)
+    out[:, 0], out[:, 1], out[:, 2], out[:, 3] = rx, ry, -ry, rx
+    out[:, 4], out[:, 5], out[:, 6] = 0.03, 0.03, 0.01
+    out[:, 7] = np.sqrt(t[:, 0] ** 2 + t[:, 1] ** 2)
+    out[:, 8] = rot
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,403 @@
+"""ctypes bindings of the C ABI (include/hitl_gpu.h) and of the host mirror library.
+
+This is plumbing for tests/ and bench.py: every call goes straight through the C ABI of
+libhitl_gpu.so.  There is no CPU fallback — if the library is missing or no CUDA device is
+present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(HERE, "lib")
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+
+KDNODE = np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("index", "<i4"), ("dim", "<i4")])
+
+# every symbol include/hitl_gpu.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count",
+    "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_kd_query",
+    "hitl_find_stf", "hitl_get_stf", "hitl_find_vo", "hitl_get_vo",
+    "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
+    "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
+    "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
+    "hitl_normal_eq_device", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose",
+]
+
+
+class StfOpts(C.Structure):
+    _fields_ = [("point_match_threshold", C.c_float), ("min_cosine_angle", C.c_float),
+                ("max_correspondences_per_point", C.c_int32), ("num_skip_readings", C.c_uint32),
+                ("min_inter_pose_correspondence", C.c_uint32), ("disable_culling", C.c_uint32)]
+
+
+class StfInfo(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
+                ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float)]
+
+
+class EvalLayout(C.Structure):
+    _fields_ = [("n_odometry", C.c_uint64), ("n_human", C.c_uint64), ("n_stf", C.c_uint64), ("n_p2l_glob", C.c_uint64),
+                ("n_p2l", C.c_uint64), ("n_residuals", C.c_uint64), ("n_jacobian", C.c_uint64)]
+
+
+class HitlError(RuntimeError):
+    pass
+
+
+def lib_path(name="libhitl_gpu.so"):
+    return os.path.join(LIB_DIR, name)
+
+
+def load_gpu_library():
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HitlError("libhitl_gpu.so is not built (run `python -m hitl_slam_b200.build`); there is no CPU fallback")
+    return C.CDLL(path)
+
+
+def default_min_cos():
+    """cos(deg2rad(25)) stored to a float (config/non_markov_localization.cfg:48; JointOptimization.cpp:564)."""
+    ang = np.float32(np.deg2rad(25.0))
+    return float(np.float32(np.cos(np.float64(ang))))
+
+
+class HitlGpu:
+    """One context = one GPU.  Thin, argument-for-argument mirror of the C ABI."""
+
+    def __init__(self, device=0):
+        self.lib = lib = load_gpu_library()
+        vp = C.c_void_p
+        lib.hitl_create.argtypes = [C.POINTER(vp), C.c_int]
+        lib.hitl_destroy.argtypes = [vp]
+        lib.hitl_last_error.restype = C.c_char_p
+        lib.hitl_last_error.argtypes = [vp]
+        lib.hitl_stream.restype = vp
+        lib.hitl_stream.argtypes = [vp]
+        lib.hitl_launch_count.restype = C.c_uint64
+        lib.hitl_launch_count.argtypes = [vp]
+        lib.hitl_sm_count.argtypes = [vp]
+        lib.hitl_set_scans.argtypes = [vp, C.c_uint32, _u32p, _f32p, _f32p]
+        lib.hitl_build_kdtrees.argtypes = [vp]
+        lib.hitl_set_kdtrees.argtypes = [vp, vp]
+        lib.hitl_get_kdtrees.argtypes = [vp, vp]
+        lib.hitl_kd_query.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
+        lib.hitl_find_stf.argtypes = [vp, _f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(StfOpts), C.POINTER(StfInfo)]
+        lib.hitl_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p]
+        lib.hitl_find_vo.argtypes = [vp, _f64p, C.c_int32, C.c_int32, C.POINTER(StfOpts), C.POINTER(C.c_uint64)]
+        lib.hitl_get_vo.argtypes = [vp, _u32p, _u32p, _u32p]
+        lib.hitl_world_transform.argtypes = [vp, _f32p, vp]
+        lib.hitl_set_world_clouds.argtypes = [vp, _f32p]
+        lib.hitl_em_inliers.argtypes = [vp, _f32p, C.c_double, C.c_uint64, vp, vp, vp, C.POINTER(C.c_uint64)]
+        lib.hitl_em_assign.argtypes = [vp, _f32p, C.c_double, C.c_uint32, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
+        lib.hitl_set_stf_blocks_from_search.argtypes = [vp, C.c_float, C.c_float]
+        lib.hitl_set_stf_blocks.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_float, C.c_float]
+        lib.hitl_set_odometry_blocks.argtypes = [vp, C.c_uint32, _f32p]
+        lib.hitl_set_human_blocks.argtypes = [vp, C.c_uint32, _i32p, _f64p]
+        lib.hitl_set_p2l_glob_blocks.argtypes = [vp, C.c_uint32, _u32p, _u64p, _f32p, _f32p, _f32p, _u8p, C.c_float, C.c_float]
+        lib.hitl_set_p2l_blocks.argtypes = [vp, C.c_uint64, _u32p, _f32p, _f32p, _f32p, _u8p, C.c_float, C.c_float]
+        lib.hitl_eval_layout_get.argtypes = [vp, C.POINTER(EvalLayout)]
+        lib.hitl_eval.argtypes = [vp, _f64p, C.c_int, vp, vp, C.POINTER(C.c_float)]
+        lib.hitl_normal_eq.argtypes = [vp, _f64p, vp, vp, vp, vp, C.POINTER(C.c_float)]
+        lib.hitl_normal_eq_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+        lib.hitl_debug_sincos.argtypes = [vp, C.c_uint64, _f32p, _f32p, _f32p]
+        lib.hitl_debug_relative_pose.argtypes = [vp, _f64p, C.c_uint32, _u32p, _u32p, _f32p]
+        self.ctx = vp()
+        rc = lib.hitl_create(C.byref(self.ctx), device)
+        if rc != 0:
+            self.ctx = None
+            raise HitlError("hitl_create failed (status %d): no usable CUDA device %d — this library has no CPU fallback" % (rc, device))
+        self.n_poses = 0
+        self.n_points = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.hitl_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HitlError("status %d: %s" % (rc, self.lib.hitl_last_error(self.ctx).decode()))
+
+    # ---- scans / trees ----
+    def set_scans(self, offsets, pts, nrm):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1)
+        self.offsets = offsets
+        self.n_poses = len(offsets) - 1
+        self.n_points = int(offsets[-1]) if len(offsets) else 0
+        if len(pts) == 0:
+            pts = np.zeros(2, np.float32)
+            nrm = np.zeros(2, np.float32)
+        self._ck(self.lib.hitl_set_scans(self.ctx, self.n_poses, offsets, pts, nrm))
+
+    def build_kdtrees(self):
+        self._ck(self.lib.hitl_build_kdtrees(self.ctx))
+
+    def set_kdtrees(self, nodes):
+        nodes = np.ascontiguousarray(nodes, KDNODE)
+        self._ck(self.lib.hitl_set_kdtrees(self.ctx, nodes.ctypes.data))
+
+    def get_kdtrees(self):
+        nodes = np.zeros(max(self.n_points, 1), KDNODE)
+        self._ck(self.lib.hitl_get_kdtrees(self.ctx, nodes.ctypes.data))
+        return nodes[:self.n_points]
+
+    def kd_query(self, scan, q, thr, mode=0):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1)
+        n = len(q) // 2
+        d, i = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.int32)
+        self._ck(self.lib.hitl_kd_query(self.ctx, scan, n, q if n else np.zeros(2, np.float32), thr, mode, d, i))
+        return d[:n], i[:n]
+
+    # ---- search ----
+    @staticmethod
+    def stf_opts(thr=0.15, min_cos=None, cap=6, skip=1, min_corr=10, disable_culling=0):
+        return StfOpts(thr, default_min_cos() if min_cos is None else min_cos, cap, skip, min_corr, disable_culling)
+
+    def find_stf(self, poses, min_pose=0, max_pose=None, src_lo=0, src_hi=0xFFFFFFFF, opts=None, fetch=True):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        if max_pose is None:
+            max_pose = max(self.n_poses - 1, 0)
+        opts = opts or self.stf_opts()
+        info = StfInfo()
+        self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
+        out = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
+                   n_traversals=info.n_traversals, ms_search=info.ms_search, ms_total=info.ms_total)
+        if fetch:
+            out.update(self.get_stf(info.n_pairs, info.n_matches))
+        return out
+
+    def get_stf(self, n_pairs, n_matches):
+        pi, pj = np.zeros(max(n_pairs, 1), np.uint32), np.zeros(max(n_pairs, 1), np.uint32)
+        off = np.zeros(n_pairs + 1, np.uint64)
+        k, idx = np.zeros(max(n_matches, 1), np.uint32), np.zeros(max(n_matches, 1), np.uint32)
+        self._ck(self.lib.hitl_get_stf(self.ctx, pi, pj, off, k, idx))
+        return dict(pair_i=pi[:n_pairs], pair_j=pj[:n_pairs], pair_off=off, k=k[:n_matches], idx=idx[:n_matches])
+
+    def find_vo(self, poses, min_pose=0, max_pose=None, opts=None):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        if max_pose is None:
+            max_pose = self.n_poses - 1
+        opts = opts or self.stf_opts()
+        n = C.c_uint64()
+        self._ck(self.lib.hitl_find_vo(self.ctx, poses, min_pose, max_pose, C.byref(opts), C.byref(n)))
+        m = max(n.value, 1)
+        sp, sk, tk = np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+        self._ck(self.lib.hitl_get_vo(self.ctx, sp, sk, tk))
+        return sp[:n.value], sk[:n.value], tk[:n.value]
+
+    # ---- world / EM ----
+    def world_transform(self, poses_f32, fetch=True):
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+        out = np.zeros(2 * max(self.n_points, 1), np.float32) if fetch else None
+        self._ck(self.lib.hitl_world_transform(self.ctx, p, out.ctypes.data if fetch else None))
+        return out[:2 * self.n_points].reshape(-1, 2) if fetch else None
+
+    def set_world_clouds(self, world):
+        w = np.ascontiguousarray(world, np.float32).reshape(-1)
+        self._ck(self.lib.hitl_set_world_clouds(self.ctx, w if len(w) else np.zeros(2, np.float32)))
+
+    def em_inliers(self, seg, thr=0.03, fetch=True, cap=None):
+        seg = np.ascontiguousarray(seg, np.float32).reshape(-1)
+        n = C.c_uint64()
+        if not fetch:
+            self._ck(self.lib.hitl_em_inliers(self.ctx, seg, thr, 0, None, None, None, C.byref(n)))
+            return n.value
+        cap = self.n_points if cap is None else cap
+        op, oi, xy = np.zeros(max(cap, 1), np.uint32), np.zeros(max(cap, 1), np.uint32), np.zeros(2 * max(cap, 1), np.float32)
+        self._ck(self.lib.hitl_em_inliers(self.ctx, seg, thr, cap, op.ctypes.data, oi.ctypes.data, xy.ctypes.data, C.byref(n)))
+        return op[:n.value].copy(), oi[:n.value].copy(), xy[:2 * n.value].reshape(-1, 2).copy()
+
+    def em_assign(self, segs, thr=0.03, min_obs=5):
+        segs = np.ascontiguousarray(segs, np.float32).reshape(-1)
+        n, m = max(self.n_poses, 1), max(self.n_points, 1)
+        ns = np.zeros(2, np.uint32)
+        bufs = [(np.zeros(n, np.uint32), np.zeros(n + 1, np.uint64), np.zeros(m, np.uint32)) for _ in range(2)]
+        self._ck(self.lib.hitl_em_assign(self.ctx, segs, thr, min_obs, ns, bufs[0][0], bufs[0][1], bufs[0][2], bufs[1][0], bufs[1][1], bufs[1][2]))
+        out = []
+        for f in range(2):
+            k = int(ns[f])
+            off = bufs[f][1][:k + 1].copy()
+            out.append((bufs[f][0][:k].copy(), off, bufs[f][2][:int(off[-1])].copy()))
+        return out
+
+    # ---- residual blocks ----
+    def set_stf_blocks_from_search(self, std_dev=0.05, corr=1.0 / 40.0):
+        self._ck(self.lib.hitl_set_stf_blocks_from_search(self.ctx, std_dev, corr))
+
+    def set_stf_blocks(self, corr_set, std_dev=0.05, corr=1.0 / 40.0):
+        n = len(corr_set["pair_i"])
+        z32 = np.zeros(1, np.uint32)
+        self._ck(self.lib.hitl_set_stf_blocks(self.ctx, n, np.ascontiguousarray(corr_set["pair_i"], np.uint32) if n else z32,
+                                              np.ascontiguousarray(corr_set["pair_j"], np.uint32) if n else z32,
+                                              np.ascontiguousarray(corr_set["pair_off"], np.uint64),
+                                              np.ascontiguousarray(corr_set["k"], np.uint32) if n else z32,
+                                              np.ascontiguousarray(corr_set["idx"], np.uint32) if n else z32, std_dev, corr))
+
+    def set_odometry_blocks(self, consts9):
+        c = np.ascontiguousarray(consts9, np.float32).reshape(-1)
+        self._ck(self.lib.hitl_set_odometry_blocks(self.ctx, len(c) // 9, c if len(c) else np.zeros(9, np.float32)))
+
+    def set_human_blocks(self, type_pose, targets4):
+        tp = np.ascontiguousarray(type_pose, np.int32).reshape(-1)
+        tg = np.ascontiguousarray(targets4, np.float64).reshape(-1)
+        self._ck(self.lib.hitl_set_human_blocks(self.ctx, len(tp) // 2, tp if len(tp) else np.zeros(2, np.int32), tg if len(tg) else np.zeros(4)))
+
+    def set_p2l_glob_blocks(self, blk_pose, blk_off, pts, line_n, line_off, valid, std_dev, corr):
+        self._ck(self.lib.hitl_set_p2l_glob_blocks(self.ctx, len(blk_pose), np.ascontiguousarray(blk_pose, np.uint32), np.ascontiguousarray(blk_off, np.uint64),
+                                                   np.ascontiguousarray(pts, np.float32).reshape(-1), np.ascontiguousarray(line_n, np.float32).reshape(-1),
+                                                   np.ascontiguousarray(line_off, np.float32), np.ascontiguousarray(valid, np.uint8), std_dev, corr))
+
+    def set_p2l_blocks(self, pose_idx, pts, line_n, line_off, valid, std_dev, corr):
+        self._ck(self.lib.hitl_set_p2l_blocks(self.ctx, len(pose_idx), np.ascontiguousarray(pose_idx, np.uint32), np.ascontiguousarray(pts, np.float32).reshape(-1),
+                                              np.ascontiguousarray(line_n, np.float32).reshape(-1), np.ascontiguousarray(line_off, np.float32),
+                                              np.ascontiguousarray(valid, np.uint8), std_dev, corr))
+
+    def layout(self):
+        L = EvalLayout()
+        self._ck(self.lib.hitl_eval_layout_get(self.ctx, C.byref(L)))
+        return L
+
+    def eval(self, poses, precision=0, want_jac=True, fetch=True):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        L = self.layout()
+        r = np.zeros(max(L.n_residuals, 1)) if fetch else None
+        J = np.zeros(max(L.n_jacobian, 1)) if (fetch and want_jac) else None
+        ms = C.c_float()
+        self._ck(self.lib.hitl_eval(self.ctx, poses, precision, r.ctypes.data if r is not None else None, J.ctypes.data if J is not None else None, C.byref(ms)))
+        out = dict(ms=ms.value, layout=L)
+        if fetch:
+            out.update(split_eval(L, r, J))
+        return out
+
+    def normal_eq(self, poses, fetch=True):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        n = self.n_poses
+        L = self.layout()
+        nbin = L.n_odometry + L.n_stf
+        ms = C.c_float()
+        if not fetch:
+            self._ck(self.lib.hitl_normal_eq(self.ctx, poses, None, None, None, None, C.byref(ms)))
+            return dict(ms=ms.value)
+        H, g, Ho, cost = np.zeros(9 * n), np.zeros(3 * n), np.zeros(9 * max(nbin, 1)), np.zeros(1)
+        self._ck(self.lib.hitl_normal_eq(self.ctx, poses, H.ctypes.data, g.ctypes.data, Ho.ctypes.data, cost.ctypes.data, C.byref(ms)))
+        return dict(H_diag=H.reshape(n, 3, 3), g=g.reshape(n, 3), H_off=Ho[:9 * nbin].reshape(-1, 3, 3), cost=float(cost[0]), ms=ms.value)
+
+    def normal_eq_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.hitl_normal_eq_device(self.ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def debug_sincos(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        s, c = np.zeros_like(x), np.zeros_like(x)
+        self._ck(self.lib.hitl_debug_sincos(self.ctx, len(x), x, s, c))
+        return s, c
+
+    def debug_relative_pose(self, poses, src, dst):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        src, dst = np.ascontiguousarray(src, np.uint32), np.ascontiguousarray(dst, np.uint32)
+        out = np.zeros(6 * len(src), np.float32)
+        self._ck(self.lib.hitl_debug_relative_pose(self.ctx, poses, len(src), src, dst, out))
+        return out.reshape(-1, 6)
+
+    def launch_count(self):
+        return self.lib.hitl_launch_count(self.ctx)
+
+    def sm_count(self):
+        return self.lib.hitl_sm_count(self.ctx)
+
+
+def split_eval(L, r, J):
+    """Split the flat hitl_eval outputs into per-kind arrays (layout in include/hitl_gpu.h)."""
+    out = {}
+    ro = jo = 0
+    for name, n, nr, nj, jshape in (("odometry", L.n_odometry, 3, 18, (2, 3, 3)), ("human", L.n_human, 3, 9, (3, 3)),
+                                    ("stf", L.n_stf, 2, 12, (2, 2, 3)), ("p2l_glob", L.n_p2l_glob, 1, 3, (3,)), ("p2l", L.n_p2l, 1, 3, (3,))):
+        out["r_" + name] = r[ro:ro + nr * n].reshape(n, nr)
+        if J is not None:
+            out["J_" + name] = J[jo:jo + nj * n].reshape((n,) + jshape)
+        ro += nr * n
+        jo += nj * n
+    return out
+
+
+def kdtree_build_host(pts, nrm):
+    """Flat preorder KD-tree of one scan, built by the library's host builder (no GPU needed)."""
+    lib = load_gpu_library()
+    lib.hitl_kdtree_build_host.argtypes = [_f32p, _f32p, C.c_uint32, C.c_void_p]
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
+    nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1)
+    n = len(pts) // 2
+    nodes = np.zeros(max(n, 1), KDNODE)
+    rc = lib.hitl_kdtree_build_host(pts if n else np.zeros(2, np.float32), nrm if n else np.zeros(2, np.float32), n, nodes.ctypes.data)
+    if rc:
+        raise HitlError("hitl_kdtree_build_host failed: %d" % rc)
+    return nodes[:n]
+
+
+# ---- host mirror library (file formats) ---------------------------------------------------------
+class HostLib:
+    def __init__(self):
+        path = lib_path("libhitl_host.so")
+        if not os.path.exists(path):
+            raise HitlError("libhitl_host.so is not built (run `python -m hitl_slam_b200.build`)")
+        self.lib = lib = C.CDLL(path)
+        lib.hitl_host_load_pose_graph.restype = C.c_void_p
+        lib.hitl_host_load_pose_graph.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.hitl_host_pose_graph_get.argtypes = [C.c_void_p, _f32p, _f32p, _u32p, _f32p, _f32p]
+        lib.hitl_host_pose_graph_free.argtypes = [C.c_void_p]
+        lib.hitl_host_save_stfs_covars.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_uint32, _f32p, _f32p, _u32p, _f32p, _f32p]
+        lib.hitl_host_save_poses.argtypes = [C.c_char_p, C.c_uint32, _f32p]
+        lib.hitl_host_sinf.restype = C.c_float
+        lib.hitl_host_sinf.argtypes = [C.c_float]
+        lib.hitl_host_cosf.restype = C.c_float
+        lib.hitl_host_cosf.argtypes = [C.c_float]
+        lib.hitl_host_sincos_mismatches.restype = C.c_uint64
+        lib.hitl_host_sincos_mismatches.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        lib.hitl_host_relative_pose.argtypes = [_f64p, C.c_uint32, C.c_uint32, _f32p]
+
+    def sincos_mismatches(self, first, count, stride):
+        return int(self.lib.hitl_host_sincos_mismatches(first, count, stride))
+
+    def relative_pose(self, poses, src, dst):
+        out = np.zeros(6, np.float32)
+        self.lib.hitl_host_relative_pose(np.ascontiguousarray(poses, np.float64).reshape(-1), src, dst, out)
+        return out
+
+    def load_pose_graph(self, path):
+        n, m = C.c_uint64(), C.c_uint64()
+        h = self.lib.hitl_host_load_pose_graph(path.encode(), C.byref(n), C.byref(m))
+        if not h:
+            raise IOError("cannot read pose graph " + path)
+        poses, cov = np.zeros(3 * n.value, np.float32), np.zeros(9 * n.value, np.float32)
+        off = np.zeros(n.value + 1, np.uint32)
+        pts, nrm = np.zeros(2 * m.value, np.float32), np.zeros(2 * m.value, np.float32)
+        self.lib.hitl_host_pose_graph_get(h, poses, cov, off, pts, nrm)
+        self.lib.hitl_host_pose_graph_free(h)
+        return dict(poses=poses.reshape(-1, 3), cov=cov.reshape(-1, 9), offsets=off, pts=pts.reshape(-1, 2), nrm=nrm.reshape(-1, 2))
+
+    def save_stfs_covars(self, path, poses, cov, offsets, obs_world, nrm_world, map_name="synthetic", timestamp=0.0):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1)
+        rc = self.lib.hitl_host_save_stfs_covars(path.encode(), map_name.encode(), timestamp, len(poses) // 3, poses,
+                                                 np.ascontiguousarray(cov, np.float32).reshape(-1), np.ascontiguousarray(offsets, np.uint32),
+                                                 np.ascontiguousarray(obs_world, np.float32).reshape(-1),
+                                                 np.ascontiguousarray(nrm_world, np.float32).reshape(-1))
+        if rc:
+            raise IOError("cannot write " + path)

@@ -1,0 +1,248 @@
+// ctx.cu — context lifetime, scan / KD-tree residency (C ABI: include/hitl_gpu.h).
+//
+// Replaces JointOpt::BuildKDTrees (human_in_the_loop_slam/JointOptimization.cpp:514-537): scans
+// and trees are uploaded once per session and stay in HBM; the reference keeps one heap node
+// per point behind `kdtrees_`.
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include "hitl_internal.h"
+#include "hitl_math.h"
+
+namespace hitl {
+int fail(hitl_ctx* c, int code, const char* what) {
+  if (c) c->err = what;
+  return code;
+}
+int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where) {
+  if (c) { c->err = std::string(where) + ": " + cudaGetErrorString(e); }
+  cudaGetLastError();
+  return HITL_ERR_CUDA;
+}
+int launch_scan_aabb(hitl_ctx* ctx);
+}  // namespace hitl
+using namespace hitl;
+
+extern "C" int hitl_create(hitl_ctx** out, int device) {
+  if (!out) return HITL_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) { cudaGetLastError(); return HITL_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return HITL_ERR_CUDA; }
+  hitl_ctx* ctx = new hitl_ctx();
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  if (cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess) { hitl_destroy(ctx); cudaGetLastError(); return HITL_ERR_CUDA; }
+  *out = ctx;
+  return HITL_OK;
+}
+
+extern "C" void hitl_destroy(hitl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
+  ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
+  ctx->d_node_pn.release(); ctx->d_node_meta.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release();
+  ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
+  ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
+  ctx->d_pose_cnt.release(); ctx->d_counters.release();
+  ctx->d_pair_i.release(); ctx->d_pair_j.release(); ctx->d_k.release(); ctx->d_idx.release(); ctx->d_pair_off.release();
+  ctx->d_vo_sp.release(); ctx->d_vo_sk.release(); ctx->d_vo_tk.release();
+  ctx->d_world.release(); ctx->d_poses_f.release(); ctx->d_em_pose.release(); ctx->d_em_idx.release(); ctx->d_em_xy.release();
+  for (int f = 0; f < 2; ++f) { ctx->d_em_obs[f].release(); ctx->d_em_cnt[f].release(); ctx->d_em_setpose[f].release(); ctx->d_em_setoff[f].release(); ctx->d_em_slots[f].release(); }
+  ctx->d_em_slotof.release();
+  ctx->d_scan_state.release(); ctx->d_ticket.release();
+  ctx->d_odo.release(); ctx->d_hum_i.release(); ctx->d_hum_d.release();
+  ctx->d_blk_i.release(); ctx->d_blk_j.release(); ctx->d_blk_k.release(); ctx->d_blk_idx.release(); ctx->d_blk_off.release();
+  ctx->d_p2lg_pose.release(); ctx->d_p2lg_off.release(); ctx->d_p2lg_pts.release(); ctx->d_p2lg_n.release(); ctx->d_p2lg_o.release(); ctx->d_p2lg_v.release();
+  ctx->d_p2l_pose.release(); ctx->d_p2l_pts.release(); ctx->d_p2l_n.release(); ctx->d_p2l_o.release(); ctx->d_p2l_v.release();
+  ctx->d_r.release(); ctx->d_J.release(); ctx->d_neq.release(); ctx->d_hoff.release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* hitl_last_error(const hitl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* hitl_stream(hitl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t hitl_launch_count(const hitl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int hitl_sm_count(const hitl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* off, const float* pts_xy, const float* nrm_xy) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!off && n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null offsets");
+  HITL_CUDA(cudaSetDevice(ctx->device));
+  ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false;
+  ctx->n_poses = n_poses;
+  ctx->h_off.assign(n_poses + 1, 0);
+  uint32_t max_scan = 0;
+  for (uint32_t i = 0; i <= n_poses && n_poses; ++i) {
+    ctx->h_off[i] = off[i];
+    if (i && off[i] < off[i - 1]) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: offsets must be non-decreasing");
+    if (i) max_scan = std::max(max_scan, off[i] - off[i - 1]);
+  }
+  if (n_poses && off[0] != 0) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: offsets must start at 0");
+  if (max_scan > 65534) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: scans larger than 65534 points are not supported");
+  ctx->max_scan = max_scan;
+  ctx->n_points = n_poses ? off[n_poses] : 0;
+  if (ctx->n_points && (!pts_xy || !nrm_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null clouds");
+  ctx->h_pts.assign(pts_xy, pts_xy + 2 * ctx->n_points);
+  ctx->h_nrm.assign(nrm_xy, nrm_xy + 2 * ctx->n_points);
+  HITL_CUDA(ctx->d_off.ensure(n_poses + 1));
+  HITL_CUDA(ctx->d_pts.ensure(ctx->n_points)); HITL_CUDA(ctx->d_nrm.ensure(ctx->n_points));
+  HITL_CUDA(cudaMemcpyAsync(ctx->d_off.p, ctx->h_off.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->n_points) {
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_pts.p, pts_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_nrm.p, nrm_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // tiles: 32 consecutive points of one scan
+  std::vector<uint32_t> tile_scan, tile_k0;
+  ctx->h_tile_begin.assign(n_poses + 1, 0);
+  for (uint32_t i = 0; i < n_poses; ++i) {
+    ctx->h_tile_begin[i] = (uint32_t)tile_scan.size();
+    const uint32_t n = ctx->h_off[i + 1] - ctx->h_off[i];
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) { tile_scan.push_back(i); tile_k0.push_back(k0); }
+  }
+  ctx->h_tile_begin[n_poses] = (uint32_t)tile_scan.size();
+  ctx->n_tiles = (uint32_t)tile_scan.size();
+  HITL_CUDA(ctx->d_tile_scan.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_k0.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_begin.ensure(n_poses + 1));
+  if (ctx->n_tiles) {
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_scan.p, tile_scan.data(), 4 * (size_t)ctx->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_k0.p, tile_k0.data(), 4 * (size_t)ctx->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_begin.p, ctx->h_tile_begin.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_scan_aabb(ctx);
+  if (rc) return rc;
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tile_scan / tile_k0 are locals
+  return HITL_OK;
+}
+
+static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
+  const size_t m = ctx->n_points;
+  std::vector<float4> pn(m);
+  std::vector<int32_t> meta(m);
+  for (size_t i = 0; i < m; ++i) {
+    pn[i] = make_float4(nodes[i].px, nodes[i].py, nodes[i].nx, nodes[i].ny);
+    meta[i] = (nodes[i].index & 0x7FFFFFFF) | (nodes[i].dim ? (int32_t)0x80000000 : 0);
+  }
+  HITL_CUDA(ctx->d_node_pn.ensure(m)); HITL_CUDA(ctx->d_node_meta.ensure(m));
+  if (m) {
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_pn.p, pn.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_meta.p, meta.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_trees = true;
+  return HITL_OK;
+}
+
+extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_kdtrees: call hitl_set_scans first");
+  if (!nodes && ctx->n_points) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: null nodes");
+  for (size_t s = 0; s < ctx->n_poses; ++s) {
+    const uint32_t n = ctx->h_off[s + 1] - ctx->h_off[s];
+    for (uint32_t k = ctx->h_off[s]; k < ctx->h_off[s + 1]; ++k)
+      if (nodes[k].index < 0 || (uint32_t)nodes[k].index >= n || (nodes[k].dim != 0 && nodes[k].dim != 1))
+        return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
+  }
+  return upload_trees(ctx, nodes);
+}
+
+extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_build_kdtrees: call hitl_set_scans first");
+  std::vector<hitl_kdnode> nodes(ctx->n_points);
+  const uint32_t n = ctx->n_poses;
+  unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  if (n < 64) nt = 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&, t]() {
+      for (uint32_t i = t; i < n; i += nt) {
+        const uint32_t o = ctx->h_off[i], c = ctx->h_off[i + 1] - o;
+        build_flat_kdtree(ctx->h_pts.data() + 2 * (size_t)o, ctx->h_nrm.data() + 2 * (size_t)o, c, nodes.data() + o);
+      }
+    });
+  for (auto& x : th) x.join();
+  return upload_trees(ctx, nodes.data());
+}
+
+extern "C" int hitl_kdtree_build_host(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out) {
+  if (n && (!pts_xy || !nrm_xy || !out)) return HITL_ERR_ARG;
+  if (n > 65534) return HITL_ERR_ARG;
+  build_flat_kdtree(pts_xy, nrm_xy, n, out);
+  return HITL_OK;
+}
+
+extern "C" int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_get_kdtrees: trees not built");
+  const size_t m = ctx->n_points;
+  if (!m) return HITL_OK;
+  if (!out) return fail(ctx, HITL_ERR_ARG, "hitl_get_kdtrees: null output");
+  std::vector<float4> pn(m);
+  std::vector<int32_t> meta(m);
+  HITL_CUDA(cudaMemcpy(pn.data(), ctx->d_node_pn.p, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+  HITL_CUDA(cudaMemcpy(meta.data(), ctx->d_node_meta.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < m; ++i) {
+    out[i].px = pn[i].x; out[i].py = pn[i].y; out[i].nx = pn[i].z; out[i].ny = pn[i].w;
+    out[i].index = meta[i] & 0x7FFFFFFF; out[i].dim = (int32_t)((uint32_t)meta[i] >> 31);
+  }
+  return HITL_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+namespace hitl {
+__global__ void debug_sincos_kernel(const float* __restrict__ x, uint64_t n, float* __restrict__ s, float* __restrict__ c) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { s[i] = sinf_rn(x[i]); c[i] = cosf_rn(x[i]); }
+}
+__global__ void debug_relative_pose_kernel(const double* __restrict__ pose, uint32_t n, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                                           float* __restrict__ out6) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Aff2 a = pose_affine(pose[3 * src[i]], pose[3 * src[i] + 1], pose[3 * src[i] + 2]);
+  const Aff2 b = pose_affine(pose[3 * dst[i]], pose[3 * dst[i] + 1], pose[3 * dst[i] + 2]);
+  const Aff2 T = affine_mul(affine_inverse(b), a);
+  float* o = out6 + 6 * (size_t)i;
+  o[0] = T.m00; o[1] = T.m01; o[2] = T.m10; o[3] = T.m11; o[4] = T.tx; o[5] = T.ty;
+}
+}  // namespace hitl
+
+extern "C" int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (n == 0) return HITL_OK;
+  if (!x || !sin_out || !cos_out) return fail(ctx, HITL_ERR_ARG, "hitl_debug_sincos: null argument");
+  DevBuf<float> dx, ds, dc;
+  HITL_CUDA(dx.ensure(n)); HITL_CUDA(ds.ensure(n)); HITL_CUDA(dc.ensure(n));
+  HITL_CUDA(cudaMemcpyAsync(dx.p, x, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  debug_sincos_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.p, n, ds.p, dc.p);
+  HITL_LAUNCH_CHECK("debug_sincos_kernel");
+  HITL_CUDA(cudaMemcpyAsync(sin_out, ds.p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(cos_out, dc.p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  dx.release(); ds.release(); dc.release();
+  return HITL_OK;
+}
+
+extern "C" int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src, const uint32_t* dst, float* out6) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (n_pairs == 0) return HITL_OK;
+  if (!pose_array || !src || !dst || !out6 || ctx->n_poses == 0) return fail(ctx, HITL_ERR_ARG, "hitl_debug_relative_pose: bad argument");
+  DevBuf<double> dp; DevBuf<uint32_t> da, db; DevBuf<float> dout;
+  HITL_CUDA(dp.ensure(3 * (size_t)ctx->n_poses)); HITL_CUDA(da.ensure(n_pairs)); HITL_CUDA(db.ensure(n_pairs)); HITL_CUDA(dout.ensure(6 * (size_t)n_pairs));
+  HITL_CUDA(cudaMemcpyAsync(dp.p, pose_array, 24 * (size_t)ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(da.p, src, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(db.p, dst, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+  debug_relative_pose_kernel<<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(dp.p, n_pairs, da.p, db.p, dout.p);
+  HITL_LAUNCH_CHECK("debug_relative_pose_kernel");
+  HITL_CUDA(cudaMemcpyAsync(out6, dout.p, 24 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  dp.release(); da.release(); db.release(); dout.release();
+  return HITL_OK;
+}

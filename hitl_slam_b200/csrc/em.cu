@@ -1,0 +1,354 @@
+// em.cu — world-frame clouds and the EM point-to-feature assignment on sm_100a.
+//
+// Replaces (paths relative to HitL-SLAM/src/):
+//   HitLSLAM::transformPointCloudsToWorldFrame    human_in_the_loop_slam/HitLSLAM.cpp:245-254
+//   E-step of EMInput::AutomaticEndpointAdjustment  human_in_the_loop_slam/EMinput.cpp:207-218
+//       with Eigen::DistanceToLineSegment         shared/math/eigen_helper.h:66-81
+//   EMInput::EstablishObservationSets             EMinput.cpp:281-323  with distToLineSeg :269-279
+//
+// Both are HBM streams: 8 B read per point, a few bytes written per inlier.  Compiled with
+// --fmad=false; float expressions follow Eigen's evaluation order so flags are bit-exact.
+#include <float.h>
+#include "hitl_internal.h"
+#include "hitl_math.h"
+
+namespace hitl {
+
+// ---- K4: world = Rotation2Df(theta) * p + t ------------------------------------------------
+__global__ void world_transform_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, const float* __restrict__ poses,
+                                       uint32_t n_poses, float2* __restrict__ world) {
+  // one warp per scan: the pose's sin/cos is computed once per lane (uniform), points stream coalesced
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_poses) return;
+  const float th = poses[3 * w + 2];
+  const float s = sinf_rn(th), c = cosf_rn(th);
+  const float tx = poses[3 * w], ty = poses[3 * w + 1];
+  for (uint32_t k = off[w] + lane; k < off[w + 1]; k += 32) {
+    const float2 p = pts[k];
+    float2 o;
+    o.x = fadd(dot2(c, p.x, -s, p.y), tx);
+    o.y = fadd(dot2(s, p.x, c, p.y), ty);
+    world[k] = o;
+  }
+}
+
+// ---- distance helpers ------------------------------------------------------------------------
+struct Seg { float p0x, p0y, p1x, p1y, dirx, diry; };   // dir = (p1 - p0).normalized()
+
+// eigen_helper.h:66-81 (t in metres compared with 1.0 — kept)
+__device__ __forceinline__ float distance_to_line_segment(const Seg& s, float px, float py) {
+  const float ax = fsub(px, s.p0x), ay = fsub(py, s.p0y);
+  const float t = dot2(ax, s.dirx, ay, s.diry);
+  if (t < 0.0f) return sqrtf(dot2(ax, ax, ay, ay));
+  if (t > 1.0f) { const float bx = fsub(px, s.p1x), by = fsub(py, s.p1y); return sqrtf(dot2(bx, bx, by, by)); }
+  return fabsf(dot2(-s.diry, ax, s.dirx, ay));
+}
+// EMinput.cpp:269-279
+struct Seg2 { float p1x, p1y, p2x, p2y, dx, dy, dd; };   // d = p2 - p1, dd = d.d
+__device__ __forceinline__ float dist_to_line_seg(const Seg2& s, float px, float py) {
+  const float ax = fsub(px, s.p1x), ay = fsub(py, s.p1y);
+  const float t = dot2(ax, s.dx, ay, s.dy) / s.dd;
+  if (t < 0.0f) return sqrtf(dot2(ax, ax, ay, ay));
+  if (t > 1.0f) { const float bx = fsub(px, s.p2x), by = fsub(py, s.p2y); return sqrtf(dot2(bx, bx, by, by)); }
+  const float qx = fadd(s.p1x, fmul(t, s.dx)), qy = fadd(s.p1y, fmul(t, s.dy));
+  const float cx = fsub(px, qx), cy = fsub(py, qy);
+  return sqrtf(dot2(cx, cx, cy, cy));
+}
+
+// ---- K2a: E-step inliers with single-pass ordered compaction (decoupled look-back) ------------
+constexpr int kEmThreads = 256;
+constexpr int kEmPerThread = 8;                       // 4 x float4 loads = 8 points per thread
+constexpr int kEmChunk = kEmThreads * kEmPerThread;   // 2048 points per CTA step
+// chunk state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = value
+constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStMask = 3ull << 62;
+
+__global__ void __launch_bounds__(kEmThreads) em_inliers_kernel(const float2* __restrict__ world, const uint32_t* __restrict__ off,
+                                                                uint32_t n_poses, uint64_t n_points, Seg seg, double thr,
+                                                                unsigned long long* state, uint32_t* ticket, uint64_t cap,
+                                                                uint32_t* __restrict__ out_pose, uint32_t* __restrict__ out_idx,
+                                                                float2* __restrict__ out_xy, unsigned long long* total) {
+  __shared__ uint32_t s_chunk;
+  __shared__ uint32_t s_warp[kEmThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_chunks = (uint32_t)((n_points + kEmChunk - 1) / kEmChunk);
+  for (;;) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= n_chunks) return;
+    // thread owns 8 consecutive points: keeps (pose, idx) order inside the thread, lanes ascending
+    const uint64_t base = (uint64_t)chunk * kEmChunk + (uint64_t)threadIdx.x * kEmPerThread;
+    float2 p[kEmPerThread];
+    if (base + kEmPerThread <= n_points) {
+      const float4* src = reinterpret_cast<const float4*>(world + base);
+#pragma unroll
+      for (int q = 0; q < kEmPerThread / 2; ++q) { const float4 v = __ldg(src + q); p[2 * q] = make_float2(v.x, v.y); p[2 * q + 1] = make_float2(v.z, v.w); }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kEmPerThread; ++q) p[q] = base + q < n_points ? world[base + q] : make_float2(FLT_MAX, FLT_MAX);
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < kEmPerThread; ++q) {
+      const bool in = base + q < n_points && (double)distance_to_line_segment(seg, p[q].x, p[q].y) < thr;
+      mask |= (uint32_t)in << q;
+    }
+    const uint32_t cnt = __popc(mask);
+    // block exclusive scan of cnt
+    uint32_t x = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t wbase = 0, block_total = 0;
+    for (int q = 0; q < kEmThreads / 32; ++q) { const uint32_t v = s_warp[q]; if (q < (int)w) wbase += v; block_total += v; }
+    const uint32_t excl = wbase + x - cnt;
+    // publish aggregate, look back for the exclusive prefix of this chunk
+    if (threadIdx.x == 0) {
+      unsigned long long prefix = 0;
+      if (chunk == 0) {
+        atomicExch(&state[0], kStPre | block_total);
+      } else {
+        atomicExch(&state[chunk], kStAgg | block_total);
+        for (int64_t c = (int64_t)chunk - 1; c >= 0; --c) {
+          unsigned long long v;
+          do { v = atomicAdd(&state[c], 0ull); } while ((v & kStMask) == 0);
+          prefix += v & ~kStMask;
+          if ((v & kStMask) == kStPre) break;
+        }
+        atomicExch(&state[chunk], kStPre | (prefix + block_total));
+      }
+      s_prefix = prefix;
+      if (chunk == n_chunks - 1) *total = prefix + block_total;
+    }
+    __syncthreads();
+    unsigned long long o = s_prefix + excl;
+    if (mask && out_pose) {
+#pragma unroll
+      for (int q = 0; q < kEmPerThread; ++q) {
+        if (mask & (1u << q)) {
+          if (o < cap) {
+            const uint32_t g = (uint32_t)(base + q);
+            // pose of point g: last scan with off[pose] <= g (upper_bound - 1 skips empty scans correctly)
+            uint32_t lo = 0, hi = n_poses;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
+            out_pose[o] = lo; out_idx[o] = g - off[lo];
+            if (out_xy) out_xy[o] = p[q];
+          }
+          ++o;
+        }
+      }
+    }
+    __syncthreads();   // s_chunk / s_warp reuse
+  }
+}
+
+// ---- K2b: observation sets of both strokes -----------------------------------------------------
+// One warp per scan; indices written in order into a per-scan slot region (same offsets as the
+// scan), counts per scan.  Poses with <= min_obs indices are dropped by the compaction below.
+__global__ void em_assign_kernel(const float2* __restrict__ world, const uint32_t* __restrict__ off, uint32_t n_poses, Seg2 sa, Seg2 sb,
+                                 double thr, uint32_t* __restrict__ obs_a, uint32_t* __restrict__ obs_b, uint32_t* __restrict__ cnt_a,
+                                 uint32_t* __restrict__ cnt_b) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_poses) return;
+  const uint32_t o0 = off[w], o1 = off[w + 1];
+  uint32_t na = 0, nb = 0;
+  for (uint32_t k0 = o0; k0 < o1; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    bool fa = false, fb = false;
+    if (k < o1) {
+      const float2 p = __ldg(world + k);
+      fa = (double)dist_to_line_seg(sa, p.x, p.y) < thr;
+      fb = (double)dist_to_line_seg(sb, p.x, p.y) < thr;
+    }
+    const uint32_t ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (fa) obs_a[o0 + na + __popc(ma & lt)] = k - o0;
+    if (fb) obs_b[o0 + nb + __popc(mb & lt)] = k - o0;
+    na += __popc(ma); nb += __popc(mb);
+  }
+  if (lane == 0) { cnt_a[w] = na; cnt_b[w] = nb; }
+}
+
+// Single-CTA ordered compaction of the kept poses: set_pose / set_off from per-scan counts.
+__global__ void em_sets_scan_kernel(const uint32_t* __restrict__ cnt, uint32_t n_poses, uint32_t min_obs, uint32_t* __restrict__ set_pose,
+                                    unsigned long long* __restrict__ set_off, uint32_t* __restrict__ slot_of_pose, unsigned long long* totals) {
+  __shared__ unsigned long long sm_c[32]; __shared__ uint32_t sm_s[32];
+  __shared__ unsigned long long carry_c; __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) { carry_c = 0; carry_s = 0; }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (uint32_t b = 0; b < n_poses; b += blockDim.x) {
+    const uint32_t i = b + threadIdx.x;
+    const uint32_t c = i < n_poses ? cnt[i] : 0;
+    const bool keep = c > min_obs;
+    unsigned long long xc = keep ? c : 0; uint32_t xs = keep ? 1u : 0u;
+    const unsigned long long vc = xc; const uint32_t vs = xs;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long yc = __shfl_up_sync(0xffffffffu, xc, o); const uint32_t ys = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= (uint32_t)o) { xc += yc; xs += ys; }
+    }
+    if (lane == 31) { sm_c[w] = xc; sm_s[w] = xs; }
+    __syncthreads();
+    if (w == 0) {
+      unsigned long long a = lane < nw ? sm_c[lane] : 0; uint32_t s = lane < nw ? sm_s[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ya = __shfl_up_sync(0xffffffffu, a, o); const uint32_t ys = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= (uint32_t)o) { a += ya; s += ys; }
+      }
+      sm_c[lane] = a; sm_s[lane] = s;
+    }
+    __syncthreads();
+    const unsigned long long ec = carry_c + (w ? sm_c[w - 1] : 0) + xc - vc;
+    const uint32_t es = carry_s + (w ? sm_s[w - 1] : 0) + xs - vs;
+    if (i < n_poses) {
+      slot_of_pose[i] = keep ? es : 0xFFFFFFFFu;
+      if (keep) { set_pose[es] = i; set_off[es] = ec; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry_c += sm_c[nw - 1]; carry_s += sm_s[nw - 1]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { set_off[carry_s] = carry_c; totals[0] = carry_s; totals[1] = carry_c; }
+}
+
+// Gather the kept scans' index lists into the dense CSR payload. One warp per scan.
+__global__ void em_sets_gather_kernel(const uint32_t* __restrict__ obs_slots, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                                      const uint32_t* __restrict__ slot_of_pose, const unsigned long long* __restrict__ set_off, uint32_t n_poses,
+                                      uint32_t* __restrict__ obs_out) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_poses) return;
+  const uint32_t s = slot_of_pose[w];
+  if (s == 0xFFFFFFFFu) return;
+  const unsigned long long dst = set_off[s];
+  const uint32_t c = cnt[w], src = off[w];
+  for (uint32_t k = lane; k < c; k += 32) obs_out[dst + k] = obs_slots[src + k];
+}
+
+}  // namespace hitl
+
+using namespace hitl;
+
+extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float* world_xy_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_world_transform: scans not set");
+  if (!poses_xyt && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_world_transform: null poses");
+  HITL_CUDA(ctx->d_world.ensure(ctx->n_points)); HITL_CUDA(ctx->d_poses_f.ensure(3 * (size_t)ctx->n_poses));
+  if (ctx->n_poses) {
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_poses_f.p, poses_xyt, 12 * (size_t)ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256;
+    world_transform_kernel<<<((size_t)ctx->n_poses * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(ctx->d_pts.p, ctx->d_off.p, ctx->d_poses_f.p,
+                                                                                                          ctx->n_poses, ctx->d_world.p);
+    HITL_LAUNCH_CHECK("world_transform_kernel");
+  }
+  if (world_xy_out && ctx->n_points) HITL_CUDA(cudaMemcpyAsync(world_xy_out, ctx->d_world.p, 8 * ctx->n_points, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_world = true;
+  return HITL_OK;
+}
+
+extern "C" int hitl_set_world_clouds(hitl_ctx* ctx, const float* world_xy) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_world_clouds: scans not set");
+  if (!world_xy && ctx->n_points) return fail(ctx, HITL_ERR_ARG, "hitl_set_world_clouds: null clouds");
+  HITL_CUDA(ctx->d_world.ensure(ctx->n_points));
+  if (ctx->n_points) HITL_CUDA(cudaMemcpyAsync(ctx->d_world.p, world_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_world = true;
+  return HITL_OK;
+}
+
+// host mirror of Vector2f::normalized() in float (same IEEE ops as the device would do)
+static void make_seg(const float s[4], Seg* o) {
+  o->p0x = s[0]; o->p0y = s[1]; o->p1x = s[2]; o->p1y = s[3];
+  const float dx = s[2] - s[0], dy = s[3] - s[1];
+  const float z = dx * dx + dy * dy;
+  if (z > 0.0f) { const float n = sqrtf(z); o->dirx = dx / n; o->diry = dy / n; }
+  else { o->dirx = dx; o->diry = dy; }
+}
+static void make_seg2(const float s[4], Seg2* o) {
+  o->p1x = s[0]; o->p1y = s[1]; o->p2x = s[2]; o->p2y = s[3];
+  o->dx = s[2] - s[0]; o->dy = s[3] - s[1];
+  o->dd = o->dx * o->dx + o->dy * o->dy;
+}
+
+extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double threshold, uint64_t cap, uint32_t* out_pose, uint32_t* out_idx,
+                               float* out_xy, uint64_t* n_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_inliers: world clouds not set");
+  if (!seg || !n_out) return fail(ctx, HITL_ERR_ARG, "hitl_em_inliers: null argument");
+  *n_out = 0;
+  if (ctx->n_points == 0) return HITL_OK;
+  const bool want = out_pose && out_idx && cap;
+  const uint64_t dcap = want ? std::min<uint64_t>(cap, ctx->n_points) : 0;
+  const uint32_t n_chunks = (uint32_t)((ctx->n_points + kEmChunk - 1) / kEmChunk);
+  HITL_CUDA(ctx->d_scan_state.ensure(n_chunks + 1)); HITL_CUDA(ctx->d_ticket.ensure(1));
+  if (want) { HITL_CUDA(ctx->d_em_pose.ensure(dcap)); HITL_CUDA(ctx->d_em_idx.ensure(dcap)); if (out_xy) HITL_CUDA(ctx->d_em_xy.ensure(dcap)); }
+  HITL_CUDA(cudaMemsetAsync(ctx->d_scan_state.p, 0, 8 * (size_t)(n_chunks + 1), ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
+  Seg s; make_seg(seg, &s);
+  const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
+  em_inliers_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, threshold,
+                                                          (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap,
+                                                          want ? ctx->d_em_pose.p : nullptr, want ? ctx->d_em_idx.p : nullptr,
+                                                          (want && out_xy) ? ctx->d_em_xy.p : nullptr,
+                                                          (unsigned long long*)ctx->d_scan_state.p + n_chunks);
+  HITL_LAUNCH_CHECK("em_inliers_kernel");
+  HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_scan_state.p + n_chunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint64_t n = ctx->h_pinned[0];
+  *n_out = n;
+  if (want && n) {
+    const uint64_t m = std::min<uint64_t>(n, dcap);
+    HITL_CUDA(cudaMemcpyAsync(out_pose, ctx->d_em_pose.p, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(out_idx, ctx->d_em_idx.p, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_xy) HITL_CUDA(cudaMemcpyAsync(out_xy, ctx->d_em_xy.p, 8 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > cap) return fail(ctx, HITL_ERR_OVERFLOW, "hitl_em_inliers: more inliers than cap");
+  }
+  return HITL_OK;
+}
+
+extern "C" int hitl_em_assign(hitl_ctx* ctx, const float segs[8], double threshold, uint32_t min_obs, uint32_t n_sets[2], uint32_t* set_pose0,
+                              uint64_t* set_off0, uint32_t* obs0, uint32_t* set_pose1, uint64_t* set_off1, uint32_t* obs1) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_assign: world clouds not set");
+  if (!segs || !n_sets) return fail(ctx, HITL_ERR_ARG, "hitl_em_assign: null argument");
+  n_sets[0] = n_sets[1] = 0;
+  if (set_off0) set_off0[0] = 0;
+  if (set_off1) set_off1[0] = 0;
+  const uint32_t n = ctx->n_poses;
+  if (n == 0) return HITL_OK;
+  DevBuf<uint32_t>* slots = ctx->d_em_slots; DevBuf<uint32_t>& slot_of_pose = ctx->d_em_slotof;
+  for (int f = 0; f < 2; ++f) {
+    HITL_CUDA(slots[f].ensure(ctx->n_points)); HITL_CUDA(ctx->d_em_obs[f].ensure(ctx->n_points)); HITL_CUDA(ctx->d_em_cnt[f].ensure(n));
+    HITL_CUDA(ctx->d_em_setpose[f].ensure(n)); HITL_CUDA(ctx->d_em_setoff[f].ensure(n + 1));
+  }
+  HITL_CUDA(slot_of_pose.ensure(n)); HITL_CUDA(ctx->d_counters.ensure(8));
+  Seg2 sa, sb; make_seg2(segs, &sa); make_seg2(segs + 4, &sb);
+  const int threads = 256;
+  const uint32_t grid = (uint32_t)(((size_t)n * 32 + threads - 1) / threads);
+  em_assign_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, n, sa, sb, threshold, slots[0].p, slots[1].p, ctx->d_em_cnt[0].p,
+                                                      ctx->d_em_cnt[1].p);
+  HITL_LAUNCH_CHECK("em_assign_kernel");
+  uint32_t* set_pose[2] = {set_pose0, set_pose1}; uint64_t* set_off[2] = {set_off0, set_off1}; uint32_t* obs[2] = {obs0, obs1};
+  for (int f = 0; f < 2; ++f) {
+    em_sets_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_em_cnt[f].p, n, min_obs, ctx->d_em_setpose[f].p, (unsigned long long*)ctx->d_em_setoff[f].p,
+                                                     slot_of_pose.p, (unsigned long long*)ctx->d_counters.p + 2 * f);
+    HITL_LAUNCH_CHECK("em_sets_scan_kernel");
+    em_sets_gather_kernel<<<grid, threads, 0, ctx->stream>>>(slots[f].p, ctx->d_off.p, ctx->d_em_cnt[f].p, slot_of_pose.p,
+                                                            (unsigned long long*)ctx->d_em_setoff[f].p, n, ctx->d_em_obs[f].p);
+    HITL_LAUNCH_CHECK("em_sets_gather_kernel");
+  }
+  HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int f = 0; f < 2; ++f) {
+    const uint64_t ns = ctx->h_pinned[2 * f], no = ctx->h_pinned[2 * f + 1];
+    n_sets[f] = (uint32_t)ns;
+    if (set_pose[f] && ns) HITL_CUDA(cudaMemcpyAsync(set_pose[f], ctx->d_em_setpose[f].p, 4 * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    if (set_off[f]) HITL_CUDA(cudaMemcpyAsync(set_off[f], ctx->d_em_setoff[f].p, 8 * (ns + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (obs[f] && no) HITL_CUDA(cudaMemcpyAsync(obs[f], ctx->d_em_obs[f].p, 4 * no, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}

@@ -1,0 +1,133 @@
+// hitl_internal.h — context object and device-side layouts shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/hitl_gpu.h"
+
+namespace hitl {
+
+// Per-pose record written by pose_prep_kernel on every search call (64 B, 16 B aligned so a
+// warp-uniform read is four LDG.128 broadcasts).
+struct __align__(16) PoseRec {
+  float c, s, tx, ty;             // source transform  Translation(tx,ty) * Rotation(theta)
+  float i00, i01, i10, i11;       // inverse of the same transform (linear part) ...
+  float itx, ity;                 // ... and its translation
+  float bx0, by0, bx1, by1;       // robot-frame AABB of the scan, inflated by thr (+ulps): exact per-point cull
+  uint32_t off, n;                // scan offset / size (copy of scan_offsets for locality)
+};
+static_assert(sizeof(PoseRec) == 64, "PoseRec must be 64 bytes");
+
+template <typename T> struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n ? n : 1;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace hitl
+
+struct hitl_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  uint64_t launches = 0;
+
+  // ---- scans ----
+  uint32_t n_poses = 0;
+  uint64_t n_points = 0;
+  uint32_t max_scan = 0;
+  std::vector<uint32_t> h_off;           // n_poses + 1
+  std::vector<float> h_pts, h_nrm;       // kept for the host tree builder
+  hitl::DevBuf<uint32_t> d_off;
+  hitl::DevBuf<float2> d_pts, d_nrm;
+  hitl::DevBuf<float4> d_aabb;           // robot-frame AABB per scan (minx, miny, maxx, maxy)
+  // tiles: 32 consecutive points of one scan
+  uint32_t n_tiles = 0;
+  hitl::DevBuf<uint32_t> d_tile_scan, d_tile_k0, d_tile_begin;   // tile -> scan, first point; scan -> first tile
+  std::vector<uint32_t> h_tile_begin;
+
+  // ---- trees ----
+  bool have_trees = false;
+  hitl::DevBuf<float4> d_node_pn;        // px, py, nx, ny   (preorder, concatenated)
+  hitl::DevBuf<int32_t> d_node_meta;     // index | dim << 31
+
+  // ---- per-call pose tables ----
+  hitl::DevBuf<double> d_pose;           // x, y, theta
+  hitl::DevBuf<hitl::PoseRec> d_rec;
+  hitl::DevBuf<float4> d_wbox;           // world-frame AABB per scan, inflated (pair cull)
+
+  // ---- search results ----
+  hitl::DevBuf<uint32_t> d_raw_j, d_raw_k, d_raw_idx, d_tile_cnt;   // per-tile raw records
+  hitl::DevBuf<uint32_t> d_srt_j, d_srt_k, d_srt_idx;               // per-pose sorted staging
+  hitl::DevBuf<uint8_t> d_srt_flag;                                 // bit0 keep, bit1 first-of-pair
+  hitl::DevBuf<uint64_t> d_pose_cnt;     // per pose: kept matches, kept pairs (2 per pose) then scanned
+  hitl::DevBuf<uint64_t> d_counters;     // [0] n_queries [1] n_traversals [2] raw matches [3] pairs [4] matches
+  hitl::DevBuf<uint32_t> d_pair_i, d_pair_j, d_k, d_idx;
+  hitl::DevBuf<uint64_t> d_pair_off;
+  uint64_t n_pairs = 0, n_matches = 0;
+  bool have_stf = false;
+  // vo
+  hitl::DevBuf<uint32_t> d_vo_sp, d_vo_sk, d_vo_tk;
+  uint64_t n_vo = 0;
+
+  // ---- world clouds / EM ----
+  hitl::DevBuf<float2> d_world;
+  bool have_world = false;
+  hitl::DevBuf<float> d_poses_f;
+  hitl::DevBuf<uint32_t> d_em_pose, d_em_idx, d_em_obs[2], d_em_cnt[2], d_em_setpose[2], d_em_slots[2], d_em_slotof;
+  hitl::DevBuf<uint64_t> d_em_setoff[2];
+  hitl::DevBuf<float2> d_em_xy;
+  hitl::DevBuf<uint64_t> d_scan_state;   // decoupled look-back tile states
+  hitl::DevBuf<uint32_t> d_ticket;
+
+  // ---- residual blocks ----
+  uint64_t nb_odo = 0, nb_human = 0, nb_stf = 0, nb_p2lg = 0, nb_p2l = 0;
+  bool stf_from_search = false;
+  float stf_std = 0.05f, stf_corr = 0.025f;
+  hitl::DevBuf<float> d_odo;             // 9 per block
+  hitl::DevBuf<int32_t> d_hum_i;         // 2 per block
+  hitl::DevBuf<double> d_hum_d;          // 4 per block
+  hitl::DevBuf<uint32_t> d_blk_i, d_blk_j, d_blk_k, d_blk_idx;   // explicit stf blocks
+  hitl::DevBuf<uint64_t> d_blk_off;
+  hitl::DevBuf<uint32_t> d_p2lg_pose; hitl::DevBuf<uint64_t> d_p2lg_off;
+  hitl::DevBuf<float2> d_p2lg_pts, d_p2lg_n; hitl::DevBuf<float> d_p2lg_o; hitl::DevBuf<uint8_t> d_p2lg_v;
+  float p2lg_std = 1, p2lg_corr = 1;
+  hitl::DevBuf<uint32_t> d_p2l_pose; hitl::DevBuf<float2> d_p2l_pts, d_p2l_n; hitl::DevBuf<float> d_p2l_o;
+  hitl::DevBuf<uint8_t> d_p2l_v;
+  float p2l_std = 1, p2l_corr = 1;
+  hitl::DevBuf<double> d_r, d_J, d_neq, d_hoff;
+
+  // pinned staging for small read-backs
+  uint64_t* h_pinned = nullptr;          // 64 x u64
+};
+
+namespace hitl {
+int fail(hitl_ctx* c, int code, const char* what);
+int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
+#define HITL_CUDA(call)                                              \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, #call); \
+  } while (0)
+#define HITL_LAUNCH_CHECK(name)                                      \
+  do {                                                               \
+    ctx->launches++;                                                 \
+    cudaError_t e__ = cudaGetLastError();                            \
+    if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, name);  \
+  } while (0)
+
+// host tree builder (kdtree_build.cpp)
+void build_flat_kdtree(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out);
+}  // namespace hitl

@@ -1,0 +1,767 @@
+// search.cu — KD-tree queries and the scan-to-scan correspondence search on sm_100a.
+//
+// Replaces (paths relative to HitL-SLAM/src/):
+//   KDTree<float,2>::FindNearestPointNormal / FindNearestPoint / FindNeighborPoints
+//       perception_tools/kdtree.cpp:141-197, :220-273, :199-218
+//   JointOpt::RelativePoseTransform          human_in_the_loop_slam/JointOptimization.cpp:296-305
+//   JointOpt::FindSTFCorrespondences         JointOptimization.cpp:561-642
+//   JointOpt::FindVisualOdometryCorrespondences  JointOptimization.cpp:432-468
+//
+// Compiled with --fmad=false: every float expression below is one IEEE operation at a time, in
+// the order the reference (Eigen 3) evaluates it, so index sets are bit-exact.
+//
+// Work decomposition of the search:
+//   * a warp owns a "tile" = 32 consecutive points of one source scan i and walks the target
+//     poses j in ascending order by itself (the per-point cap makes j a sequential loop per
+//     point, but tiles are independent of each other);
+//   * 32 target poses are culled per step, one per lane, by a world-frame AABB overlap test
+//     (tile box vs scan box, both conservatively inflated) -> ballot of candidate j;
+//   * per candidate j the warp forms T_ij, transforms its points, culls each point exactly
+//     against scan j's robot-frame AABB inflated by thr, and only the survivors walk the tree;
+//   * the tree walk is the reference's recursion unrolled into a frame machine with a
+//     16-byte-per-level stack in shared memory; nodes come through the read-only L1 path;
+//   * matches are appended per tile in (j, k) order by ballot/popc; three small kernels then
+//     merge the tiles of each pose into the reference's (i, j, k) order, apply the
+//     "> 10 matches per pair" rule and emit the CSR arrays.
+#include <float.h>
+#include "hitl_internal.h"
+#include "hitl_math.h"
+
+namespace hitl {
+
+// ------------------------------------------------------------------------------------------------
+// Tree walk: FindNearestPointNormal as a frame machine.
+// Frame = {best, |s|, far child (pos | n << 16), bestpos | state << 16}; one uint4 per level per thread.
+// ------------------------------------------------------------------------------------------------
+enum { FAR_NONE = 0, FAR_COND = 1, FAR_UNCOND = 2 };
+constexpr uint32_t kNoPos = 0xFFFFu;
+
+struct TreeRef {
+  const float4* __restrict__ pn;     // px, py, nx, ny
+  const int32_t* __restrict__ meta;  // index | dim << 31
+};
+
+// stack[level * stride + tid]
+__device__ __forceinline__ void nearest_point_normal(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr,
+                                                     uint4* stack, uint32_t stride, float* out_best, uint32_t* out_pos) {
+  const float thr2 = fmul(thr, thr);
+  uint32_t pos = 0, n = n_nodes, level = 0;
+  float ret_best;
+  uint32_t ret_pos;
+  for (;;) {
+    // ---- call(pos, n) ----
+    for (;;) {
+      const float4 nd = __ldg(t.pn + pos);
+      const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+      float best = FLT_MAX;
+      uint32_t bestpos = kNoPos;
+      const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
+      bool leaf_return = false;
+      if (fadd(fmul(ex, ex), fmul(ey, ey)) < thr2) {
+        bestpos = pos;
+        best = fabsf(fadd(fmul(nd.z, fsub(qx, nd.x)), fmul(nd.w, fsub(qy, nd.y))));
+        if (best < FLT_MIN) { best = 0.0f; leaf_return = true; }
+      }
+      const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
+      const uint32_t nl = n >> 1, nr = n - 1 - nl;
+      uint32_t far, state, near_pos, near_n;
+      if (leaf_return || nl == 0) {
+        ret_best = best; ret_pos = bestpos; break;
+      }
+      if (s < 0.0f) {
+        near_pos = pos + 1; near_n = nl;
+        far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_COND : FAR_NONE;
+      } else if (s > 0.0f) {
+        if (nr == 0) { ret_best = best; ret_pos = bestpos; break; }   // right NULL: `other` stays NULL
+        near_pos = pos + 1 + nl; near_n = nr;
+        far = (pos + 1) | (nl << 16); state = FAR_COND;
+      } else {                                                       // s == 0: left then right, no third visit
+        near_pos = pos + 1; near_n = nl;
+        far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_UNCOND : FAR_NONE;
+      }
+      stack[level * stride] = make_uint4(__float_as_uint(best), __float_as_uint(fabsf(s)), far, bestpos | (state << 16));
+      ++level;
+      pos = near_pos; n = near_n;
+    }
+    // ---- return(ret_best, ret_pos) ----
+    for (;;) {
+      if (level == 0) { *out_best = ret_best; *out_pos = ret_pos; return; }
+      uint4 f = stack[(level - 1) * stride];
+      float best = __uint_as_float(f.x);
+      uint32_t bestpos = f.w & 0xFFFFu;
+      const uint32_t state = f.w >> 16;
+      if (ret_best < best) { best = ret_best; bestpos = ret_pos; }
+      const float bound = best < thr ? best : thr;
+      if (state == FAR_UNCOND || (state == FAR_COND && __uint_as_float(f.y) < bound)) {
+        f.x = __float_as_uint(best); f.w = bestpos;   // state -> FAR_NONE
+        stack[(level - 1) * stride] = f;
+        pos = f.z & 0xFFFFu; n = f.z >> 16;
+        break;                                        // call(far)
+      }
+      --level;
+      ret_best = best; ret_pos = bestpos;
+    }
+  }
+}
+
+// FindNearestPoint (kdtree.cpp:220-273): Euclidean, the bound min(best, thr) is handed down.
+// Only used by the consecutive-pose matcher and hitl_kd_query: explicit local stack.
+__device__ void nearest_point(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr0, float* out_best,
+                              uint32_t* out_pos) {
+  struct Frame { float best, abs_s, thr; uint32_t far, bestpos, state; };
+  Frame st[17];
+  uint32_t pos = 0, n = n_nodes, level = 0;
+  float thr = thr0;
+  float ret_best; uint32_t ret_pos;
+  for (;;) {
+    for (;;) {
+      const float4 nd = __ldg(t.pn + pos);
+      const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+      const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
+      float best = sqrtf(fadd(fmul(ex, ex), fmul(ey, ey)));
+      uint32_t bestpos = pos;
+      const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
+      const uint32_t nl = n >> 1, nr = n - 1 - nl;
+      if (best < FLT_MIN) { ret_best = 0.0f; ret_pos = pos; break; }
+      if (nl == 0) { ret_best = best; ret_pos = bestpos; break; }
+      uint32_t far, state, near_pos, near_n;
+      if (s < 0.0f) { near_pos = pos + 1; near_n = nl; far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_COND : FAR_NONE; }
+      else if (s > 0.0f) {
+        if (nr == 0) { ret_best = best; ret_pos = bestpos; break; }
+        near_pos = pos + 1 + nl; near_n = nr; far = (pos + 1) | (nl << 16); state = FAR_COND;
+      } else { near_pos = pos + 1; near_n = nl; far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_UNCOND : FAR_NONE; }
+      Frame f; f.best = best; f.abs_s = fabsf(s); f.thr = thr; f.far = far; f.bestpos = bestpos; f.state = state;
+      st[level++] = f;
+      thr = best < thr ? best : thr;        // min(current_best_dist, threshold) handed to the child
+      pos = near_pos; n = near_n;
+    }
+    for (;;) {
+      if (level == 0) { *out_best = ret_best; *out_pos = ret_pos; return; }
+      Frame& f = st[level - 1];
+      if (ret_best < f.best) { f.best = ret_best; f.bestpos = ret_pos; }
+      const float bound = f.best < f.thr ? f.best : f.thr;
+      if (f.state == FAR_UNCOND || (f.state == FAR_COND && f.abs_s < bound)) {
+        f.state = FAR_NONE;
+        pos = f.far & 0xFFFFu; n = f.far >> 16; thr = bound;
+        break;
+      }
+      --level;
+      ret_best = f.best; ret_pos = f.bestpos;
+    }
+  }
+}
+
+// FindNeighborPoints (kdtree.cpp:199-218): number of nodes with |p - q| < thr (visit order is
+// irrelevant for a count; the reference has no caller).
+__device__ uint32_t neighbor_count(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr) {
+  uint32_t stack_pos[34], stack_n[34];
+  int sp = 0; uint32_t count = 0;
+  stack_pos[0] = 0; stack_n[0] = n_nodes; sp = 1;
+  while (sp) {
+    --sp;
+    const uint32_t pos = stack_pos[sp], n = stack_n[sp];
+    const float4 nd = __ldg(t.pn + pos);
+    const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+    const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
+    if (sqrtf(fadd(fmul(ex, ex), fmul(ey, ey))) < thr) ++count;
+    const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
+    const uint32_t nl = n >> 1, nr = n - 1 - nl;
+    if (s > -thr && nr) { stack_pos[sp] = pos + 1 + nl; stack_n[sp] = nr; ++sp; }
+    if (s < thr && nl) { stack_pos[sp] = pos + 1; stack_n[sp] = nl; ++sp; }
+  }
+  return count;
+}
+
+__global__ void kd_query_kernel(const float4* pn, const int32_t* meta, uint32_t tree_off, uint32_t n_nodes, uint32_t nq,
+                                const float2* q, float thr, int mode, float* dist, int32_t* index) {
+  extern __shared__ uint4 smem_stack[];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  TreeRef t; t.pn = pn + tree_off; t.meta = meta + tree_off;
+  if (n_nodes == 0) { if (mode != 2) dist[i] = FLT_MAX; index[i] = mode == 2 ? 0 : -1; return; }
+  const float2 p = q[i];
+  if (mode == 2) { index[i] = (int32_t)neighbor_count(t, n_nodes, p.x, p.y, thr); return; }
+  float best; uint32_t pos;
+  if (mode == 0) nearest_point_normal(t, n_nodes, p.x, p.y, thr, smem_stack + threadIdx.x, blockDim.x, &best, &pos);
+  else nearest_point(t, n_nodes, p.x, p.y, thr, &best, &pos);
+  dist[i] = best;
+  index[i] = pos == kNoPos ? -1 : (__ldg(t.meta + pos) & 0x7FFFFFFF);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-scan robot-frame AABB (once per hitl_set_scans). One warp per scan.
+// ------------------------------------------------------------------------------------------------
+__global__ void scan_aabb_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, uint32_t n_poses,
+                                 float4* __restrict__ aabb) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_poses) return;
+  float x0 = FLT_MAX, y0 = FLT_MAX, x1 = -FLT_MAX, y1 = -FLT_MAX;
+  for (uint32_t k = off[w] + lane; k < off[w + 1]; k += 32) {
+    const float2 p = pts[k];
+    x0 = fminf(x0, p.x); y0 = fminf(y0, p.y); x1 = fmaxf(x1, p.x); y1 = fmaxf(y1, p.y);
+  }
+  for (int o = 16; o; o >>= 1) {
+    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (lane == 0) aabb[w] = make_float4(x0, y0, x1, y1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: per-pose records for one search call.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cull_margin(float a, float b, float c, float d) {
+  // Absorbs float rounding of the reference's transforms: 5 mm + 2^-18 of the largest coordinate.
+  const float m = fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d)));
+  return 0.005f + m * 3.8146973e-6f;
+}
+
+__global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* __restrict__ aabb,
+                                 const uint32_t* __restrict__ off, uint32_t n_poses, float thr, PoseRec* __restrict__ rec,
+                                 float4* __restrict__ wbox) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_poses) return;
+  const Aff2 a = pose_affine(pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]);
+  const Aff2 inv = affine_inverse(a);
+  PoseRec r;
+  r.c = a.m00; r.s = a.m10; r.tx = a.tx; r.ty = a.ty;
+  r.i00 = inv.m00; r.i01 = inv.m01; r.i10 = inv.m10; r.i11 = inv.m11; r.itx = inv.tx; r.ity = inv.ty;
+  const float4 b = aabb[i];
+  r.off = off[i]; r.n = off[i + 1] - off[i];
+  if (r.n == 0) {
+    r.bx0 = r.by0 = FLT_MAX; r.bx1 = r.by1 = -FLT_MAX;
+    wbox[i] = make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
+  } else {
+    // exact per-point cull: a node within thr of q (as the reference computes it in float) forces q
+    // inside this box; slack thr*2^-10 + 2^-20*|coord| dominates the rounding of the subtraction.
+    const float infl = thr * 1.0009765625f + 9.5367432e-7f * fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    r.bx0 = b.x - infl; r.by0 = b.y - infl; r.bx1 = b.z + infl; r.by1 = b.w + infl;
+    float x[4], y[4];
+    affine_apply(a, b.x, b.y, &x[0], &y[0]); affine_apply(a, b.z, b.y, &x[1], &y[1]);
+    affine_apply(a, b.x, b.w, &x[2], &y[2]); affine_apply(a, b.z, b.w, &x[3], &y[3]);
+    const float wx0 = fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), wx1 = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    const float wy0 = fminf(fminf(y[0], y[1]), fminf(y[2], y[3])), wy1 = fmaxf(fmaxf(y[0], y[1]), fmaxf(y[2], y[3]));
+    const float m = cull_margin(wx0, wy0, wx1, wy1);
+    wbox[i] = make_float4(wx0 - m, wy0 - m, wx1 + m, wy1 + m);
+  }
+  rec[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: the search.
+// ------------------------------------------------------------------------------------------------
+struct SearchParams {
+  const float2* __restrict__ pts; const float2* __restrict__ nrm;
+  const float4* __restrict__ node_pn; const int32_t* __restrict__ node_meta;
+  const PoseRec* __restrict__ rec; const float4* __restrict__ wbox; const double* __restrict__ pose;
+  const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
+  uint32_t tile_lo, tile_hi;          // tiles of the source shard
+  uint32_t jmin, jmax;                // inclusive target range
+  float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
+  uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
+  unsigned long long* __restrict__ counters;
+};
+
+constexpr int kSearchThreads = 128;
+
+__global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const SearchParams P) {
+  extern __shared__ uint4 smem_stack[];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t tile = P.tile_lo + blockIdx.x * (kSearchThreads / 32) + (threadIdx.x >> 5);
+  if (tile >= P.tile_hi) return;
+  uint4* const my_stack = smem_stack + threadIdx.x;
+  const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
+  const PoseRec ri = P.rec[i];
+  const uint32_t k = k0 + lane;
+  const bool valid = k < ri.n && (k % P.skip) == 0;
+  float2 p = make_float2(0.f, 0.f), nv = make_float2(0.f, 0.f);
+  if (valid) { p = P.pts[ri.off + k]; nv = P.nrm[ri.off + k]; }
+  const double theta_i = P.pose[3 * i + 2];
+  Aff2 src; src.m00 = ri.c; src.m01 = -ri.s; src.m10 = ri.s; src.m11 = ri.c; src.tx = ri.tx; src.ty = ri.ty;
+
+  // world-frame box of this tile, inflated by thr + margin (conservative pair cull)
+  float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
+  if (valid) { float wx, wy; affine_apply(src, p.x, p.y, &wx, &wy); bx0 = bx1 = wx; by0 = by1 = wy; }
+  for (int o = 16; o; o >>= 1) {
+    bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  {
+    const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
+    bx0 -= m; by0 -= m; bx1 += m; by1 += m;
+  }
+
+  const uint32_t out_base = (ri.off + k0) * (uint32_t)P.cap;   // this tile's private record region
+  uint32_t wcount = 0;                                         // records written by the warp
+  int cnt = 0;                                                 // matches of this lane's point
+  bool active = valid;
+  uint32_t exec_last = 0xFFFFFFFFu;                            // j at which this lane hit the cap
+  unsigned long long n_trav = 0;
+  const bool i_in_range = i >= P.jmin && i <= P.jmax;
+
+  if (__any_sync(0xffffffffu, active)) {
+    for (uint32_t jb = P.jmin & ~31u; jb <= P.jmax; jb += 32) {
+      const uint32_t jl = jb + lane;
+      bool hit = jl >= P.jmin && jl <= P.jmax && jl != i;
+      if (hit && !P.no_cull) {
+        const float4 wb = __ldg(P.wbox + jl);
+        hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
+      }
+      uint32_t cand = __ballot_sync(0xffffffffu, hit);
+      while (cand) {
+        const uint32_t j = jb + (__ffs(cand) - 1);
+        cand &= cand - 1;
+        const PoseRec rj = P.rec[j];
+        // T_ij = target^-1 * source  (Affine product, JointOptimization.cpp:304)
+        Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+        const Aff2 T = affine_mul(inv, src);
+        float qx, qy;
+        affine_apply(T, p.x, p.y, &qx, &qy);
+        const bool inside = active && (P.no_cull ? rj.n != 0 : (qx >= rj.bx0 && qx <= rj.bx1 && qy >= rj.by0 && qy <= rj.by1));
+        if (__any_sync(0xffffffffu, inside)) {
+          float best = FLT_MAX; uint32_t bpos = kNoPos;
+          TreeRef t; t.pn = P.node_pn + rj.off; t.meta = P.node_meta + rj.off;
+          if (inside) { nearest_point_normal(t, rj.n, qx, qy, P.thr, my_stack, kSearchThreads, &best, &bpos); ++n_trav; }
+          const bool found = inside && best < P.thr;   // implies bpos valid: best < FLT_MAX only via an in-radius node
+          if (__any_sync(0xffffffffu, found)) {
+            // Rotation2Df(theta_j - theta_i) * normal  (JointOptimization.cpp:604-606)
+            const float dth = (float)(P.pose[3 * j + 2] - theta_i);
+            const float sn = sinf_rn(dth), cs = cosf_rn(dth);
+            bool ok = false; uint32_t tgt = 0;
+            if (found) {
+              float rnx, rny; rot_apply(cs, sn, nv.x, nv.y, &rnx, &rny);
+              const float4 nd = __ldg(t.pn + bpos);
+              ok = fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > P.min_cos;
+              tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+              const uint32_t o = out_base + wcount + __popc(m & ((1u << lane) - 1u));
+              P.raw_j[o] = j; P.raw_k[o] = k; P.raw_idx[o] = tgt;
+              if (++cnt >= P.cap) { active = false; exec_last = j; }
+            }
+            wcount += __popc(m);
+          }
+        }
+        if (!__any_sync(0xffffffffu, active)) goto done;
+      }
+    }
+  }
+done:
+  if (lane == 0) P.tile_cnt[tile] = wcount;
+  // queries the reference semantics execute for this point: every j != i in range up to and
+  // including the one that filled the cap (JointOptimization.cpp:597-600)
+  unsigned long long exec = 0;
+  if (valid) {
+    if (exec_last == 0xFFFFFFFFu) exec = (unsigned long long)(P.jmax - P.jmin + 1) - (i_in_range ? 1 : 0);
+    else exec = (unsigned long long)(exec_last - P.jmin + 1) - ((i_in_range && i <= exec_last) ? 1 : 0);
+  }
+  for (int o = 16; o; o >>= 1) { exec += __shfl_xor_sync(0xffffffffu, exec, o); n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o); }
+  if (lane == 0) { atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 2, (unsigned long long)wcount); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: order the per-tile records of each source pose by (j, k), drop pairs with <= min_corr
+// matches, emit CSR.  Each CTA owns a private u32[n_poses] scratch slice indexed by j.
+//   pass 0 (count): per pose -> kept matches / kept pairs
+//   (host-launched scan over poses)
+//   pass 1 (fill):  per pose -> pair_i, pair_j, pair_off, k, idx at the scanned offsets
+// ------------------------------------------------------------------------------------------------
+constexpr int kOrderThreads = 128;
+constexpr uint32_t kDropped = 0xFFFFFFFFu;
+
+struct OrderParams {
+  const uint32_t* __restrict__ raw_j; const uint32_t* __restrict__ raw_k; const uint32_t* __restrict__ raw_idx;
+  const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ off;
+  uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
+  uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
+  unsigned long long* pose_cnt;       // 2 per source pose of the shard: matches, pairs (pass 1: exclusive offsets)
+  uint32_t* pair_i; uint32_t* pair_j; unsigned long long* pair_off; uint32_t* out_k; uint32_t* out_idx;
+};
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* sm /* 33 words */) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+  if (lane == 31) sm[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = lane < (blockDim.x >> 5) ? sm[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += y; }
+    sm[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t base = w ? sm[w - 1] : 0;
+  *total = sm[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderParams P) {
+  __shared__ uint32_t sm[40];
+  __shared__ uint32_t s_jlo, s_jhi;
+  __shared__ unsigned long long s_off_m, s_off_p;
+  uint32_t* const cntj = P.scratch + (size_t)blockIdx.x * P.n_poses;
+  for (uint32_t i = P.src_lo + blockIdx.x; i < P.src_hi; i += gridDim.x) {
+    const uint32_t tb = P.tile_begin[i], te = P.tile_begin[i + 1];
+    const uint32_t seg = P.off[i] * (uint32_t)P.cap;
+    if (threadIdx.x == 0) { s_jlo = 0xFFFFFFFFu; s_jhi = 0; }
+    __syncthreads();
+    // -- histogram over j (tile lists are sorted by j: first/last record bound the range) --
+    uint32_t jlo = 0xFFFFFFFFu, jhi = 0;
+    for (uint32_t t = tb; t < te; ++t) {
+      const uint32_t c = P.tile_cnt[t], base = seg + (t - tb) * 32u * (uint32_t)P.cap;
+      for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+        const uint32_t j = P.raw_j[base + u];
+        atomicAdd(&cntj[j], 1u);
+        jlo = min(jlo, j); jhi = max(jhi, j);
+      }
+    }
+    if (jlo != 0xFFFFFFFFu) { atomicMin(&s_jlo, jlo); atomicMax(&s_jhi, jhi); }
+    __syncthreads();
+    jlo = s_jlo; jhi = s_jhi;
+    unsigned long long tot_m = 0, tot_p = 0;
+    if (PASS == 1 && threadIdx.x == 0) { s_off_m = P.pose_cnt[2 * (i - P.src_lo)]; s_off_p = P.pose_cnt[2 * (i - P.src_lo) + 1]; }
+    __syncthreads();
+    if (jlo != 0xFFFFFFFFu) {
+      // -- scan over j in [jlo, jhi]: kept-match prefix and kept-pair prefix --
+      uint32_t run_m = 0, run_p = 0;
+      for (uint32_t j0 = jlo; j0 <= jhi; j0 += kOrderThreads) {
+        const uint32_t j = j0 + threadIdx.x;
+        const uint32_t c = j <= jhi ? cntj[j] : 0;
+        const uint32_t keep = c > P.min_corr ? c : 0;
+        uint32_t tm, tp;
+        const uint32_t em = block_exclusive_scan(keep, &tm, sm);
+        const uint32_t ep = block_exclusive_scan(keep ? 1u : 0u, &tp, sm);
+        if (PASS == 1 && j <= jhi) {
+          if (keep) {
+            const unsigned long long po = s_off_p + run_p + ep;
+            P.pair_i[po] = i; P.pair_j[po] = j; P.pair_off[po] = s_off_m + run_m + em;
+            cntj[j] = run_m + em;                 // start of this pair inside the pose's kept segment
+          } else if (c) cntj[j] = kDropped;
+        }
+        run_m += tm; run_p += tp;
+      }
+      tot_m = run_m; tot_p = run_p;
+      if (PASS == 1) {
+        __syncthreads();
+        // -- placement: tiles in ascending k order; inside a tile each j forms one run --
+        for (uint32_t t = tb; t < te; ++t) {
+          const uint32_t c = P.tile_cnt[t], base = seg + (t - tb) * 32u * (uint32_t)P.cap;
+          // phase 1: every record reads its pair cursor (value at tile start) and is placed
+          for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+            const uint32_t j = P.raw_j[base + u];
+            const uint32_t pos = cntj[j];
+            if (pos == kDropped) continue;
+            uint32_t start = u;
+            while (start > 0 && P.raw_j[base + start - 1] == j) --start;     // run start (<= 31 steps)
+            const unsigned long long o = s_off_m + pos + (u - start);
+            P.out_k[o] = P.raw_k[base + u]; P.out_idx[o] = P.raw_idx[base + u];
+          }
+          __syncthreads();
+          // phase 2: the first record of each run advances its pair cursor by the run length
+          for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+            const uint32_t j = P.raw_j[base + u];
+            if (u > 0 && P.raw_j[base + u - 1] == j) continue;
+            const uint32_t pos = cntj[j];
+            if (pos == kDropped) continue;
+            uint32_t e = u + 1;
+            while (e < c && P.raw_j[base + e] == j) ++e;
+            cntj[j] = pos + (e - u);
+          }
+          __syncthreads();
+        }
+      }
+      // -- clear the touched scratch entries --
+      __syncthreads();
+      for (uint32_t j = jlo + threadIdx.x; j <= jhi; j += kOrderThreads) cntj[j] = 0;
+    }
+    if (PASS == 0 && threadIdx.x == 0) { P.pose_cnt[2 * (i - P.src_lo)] = tot_m; P.pose_cnt[2 * (i - P.src_lo) + 1] = tot_p; }
+    __syncthreads();
+  }
+}
+
+// Exclusive scan over the per-pose (matches, pairs) counts; totals to counters[3], [4]. Single CTA.
+__global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, unsigned long long* counters) {
+  __shared__ unsigned long long sm_m[32], sm_p[32];
+  __shared__ unsigned long long carry_m, carry_p;
+  if (threadIdx.x == 0) { carry_m = 0; carry_p = 0; }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (uint32_t b = 0; b < n; b += blockDim.x) {
+    const uint32_t i = b + threadIdx.x;
+    const unsigned long long vm = i < n ? pose_cnt[2 * i] : 0, vp = i < n ? pose_cnt[2 * i + 1] : 0;
+    unsigned long long xm = vm, xp = vp;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long ym = __shfl_up_sync(0xffffffffu, xm, o), yp = __shfl_up_sync(0xffffffffu, xp, o);
+      if (lane >= (uint32_t)o) { xm += ym; xp += yp; }
+    }
+    if (lane == 31) { sm_m[w] = xm; sm_p[w] = xp; }
+    __syncthreads();
+    if (w == 0) {
+      unsigned long long sm_ = lane < nw ? sm_m[lane] : 0, sp_ = lane < nw ? sm_p[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ym = __shfl_up_sync(0xffffffffu, sm_, o), yp = __shfl_up_sync(0xffffffffu, sp_, o);
+        if (lane >= (uint32_t)o) { sm_ += ym; sp_ += yp; }
+      }
+      sm_m[lane] = sm_; sm_p[lane] = sp_;
+    }
+    __syncthreads();
+    const unsigned long long bm = carry_m + (w ? sm_m[w - 1] : 0), bp = carry_p + (w ? sm_p[w - 1] : 0);
+    if (i < n) { pose_cnt[2 * i] = bm + xm - vm; pose_cnt[2 * i + 1] = bp + xp - vp; }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry_m += sm_m[nw - 1]; carry_p += sm_p[nw - 1]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { counters[3] = carry_p; counters[4] = carry_m; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Consecutive-pose matcher (FindVisualOdometryCorrespondences). One warp per source scan,
+// ordered output through a per-scan slot region, compacted on the host side of the call
+// (the result is never consumed downstream in the reference; kept simple).
+// ------------------------------------------------------------------------------------------------
+__global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const float4* __restrict__ node_pn,
+                                 const int32_t* __restrict__ node_meta, const PoseRec* __restrict__ rec,
+                                 const double* __restrict__ pose, uint32_t i_lo, uint32_t i_hi, float thr, float min_cos,
+                                 uint32_t* __restrict__ out_tk, uint32_t* __restrict__ scan_cnt) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t i = i_lo + w;
+  if (i >= i_hi) return;
+  const PoseRec ri = rec[i], rj = rec[i + 1];
+  Aff2 src; src.m00 = ri.c; src.m01 = -ri.s; src.m10 = ri.s; src.m11 = ri.c; src.tx = ri.tx; src.ty = ri.ty;
+  Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+  const Aff2 T = affine_mul(inv, src);
+  const float dth = (float)(pose[3 * i + 5] - pose[3 * i + 2]);
+  const float sn = sinf_rn(dth), cs = cosf_rn(dth);
+  TreeRef t; t.pn = node_pn + rj.off; t.meta = node_meta + rj.off;
+  uint32_t total = 0;
+  for (uint32_t k0 = 0; k0 < ri.n; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    bool ok = false; uint32_t tgt = 0;
+    if (k < ri.n && rj.n) {
+      const float2 p = pts[ri.off + k], nv = nrm[ri.off + k];
+      float qx, qy; affine_apply(T, p.x, p.y, &qx, &qy);
+      float best; uint32_t bpos;
+      nearest_point(t, rj.n, qx, qy, thr, &best, &bpos);
+      float rnx, rny; rot_apply(cs, sn, nv.x, nv.y, &rnx, &rny);
+      const float4 nd = __ldg(t.pn + bpos);
+      ok = best < thr && fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > min_cos;
+      tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    // slot per source point: target index or 0xFFFFFFFF
+    if (k < ri.n) out_tk[ri.off + k] = ok ? tgt : 0xFFFFFFFFu;
+    total += __popc(m);
+  }
+  if (lane == 0) scan_cnt[i] = total;
+}
+
+}  // namespace hitl
+
+// ================================================================================================
+// Host side of the C ABI for this file.
+// ================================================================================================
+using namespace hitl;
+
+static uint32_t stack_levels(uint32_t max_scan) {
+  uint32_t d = 1;
+  while ((1u << d) <= max_scan) ++d;   // floor(log2(max_scan)) + 1 >= number of non-leaf levels + 1
+  return d;
+}
+
+extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const float* q_xy, float threshold, int mode,
+                             float* dist_out, int32_t* index_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_kd_query: trees not built");
+  if (scan >= ctx->n_poses || mode < 0 || mode > 2 || (nq && (!q_xy || !index_out))) return fail(ctx, HITL_ERR_ARG, "hitl_kd_query: bad argument");
+  if (nq == 0) return HITL_OK;
+  DevBuf<float2> dq; DevBuf<float> dd; DevBuf<int32_t> di;
+  HITL_CUDA(dq.ensure(nq)); HITL_CUDA(dd.ensure(nq)); HITL_CUDA(di.ensure(nq));
+  HITL_CUDA(cudaMemcpyAsync(dq.p, q_xy, sizeof(float2) * nq, cudaMemcpyHostToDevice, ctx->stream));
+  const uint32_t toff = ctx->h_off[scan], tn = ctx->h_off[scan + 1] - toff;
+  const int threads = 128;
+  const size_t smem = (size_t)stack_levels(ctx->max_scan) * threads * sizeof(uint4);
+  kd_query_kernel<<<(nq + threads - 1) / threads, threads, smem, ctx->stream>>>(ctx->d_node_pn.p, ctx->d_node_meta.p, toff, tn, nq, dq.p,
+                                                                              threshold, mode, dd.p, di.p);
+  HITL_LAUNCH_CHECK("kd_query_kernel");
+  if (dist_out && mode != 2) HITL_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(float) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(index_out, di.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  dq.release(); dd.release(); di.release();
+  return HITL_OK;
+}
+
+namespace hitl {
+int upload_poses_and_prep(hitl_ctx* ctx, const double* pose_array, float thr) {
+  HITL_CUDA(ctx->d_pose.ensure(3 * (size_t)ctx->n_poses));
+  HITL_CUDA(ctx->d_rec.ensure(ctx->n_poses));
+  HITL_CUDA(ctx->d_wbox.ensure(ctx->n_poses));
+  HITL_CUDA(cudaMemcpyAsync(ctx->d_pose.p, pose_array, sizeof(double) * 3 * ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
+  pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->n_poses, thr,
+                                                                        ctx->d_rec.p, ctx->d_wbox.p);
+  HITL_LAUNCH_CHECK("pose_prep_kernel");
+  return HITL_OK;
+}
+int launch_scan_aabb(hitl_ctx* ctx) {
+  HITL_CUDA(ctx->d_aabb.ensure(ctx->n_poses));
+  if (ctx->n_poses == 0) return HITL_OK;
+  const int threads = 128;
+  scan_aabb_kernel<<<((size_t)ctx->n_poses * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(ctx->d_pts.p, ctx->d_off.p, ctx->n_poses,
+                                                                                                   ctx->d_aabb.p);
+  HITL_LAUNCH_CHECK("scan_aabb_kernel");
+  return HITL_OK;
+}
+}  // namespace hitl
+
+extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t min_pose, uint32_t max_pose, uint32_t src_lo,
+                             uint32_t src_hi, const hitl_stf_opts* o, hitl_stf_info* info) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!pose_array || !o) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: null argument");
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_find_stf: scans/trees not set");
+  if (o->num_skip_readings == 0) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: num_skip_readings must be >= 1");
+  if (o->max_correspondences_per_point > 64) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: max_correspondences_per_point > 64 unsupported");
+  hitl_stf_info inf; memset(&inf, 0, sizeof(inf));
+  ctx->have_stf = false; ctx->n_pairs = ctx->n_matches = 0;
+  // poses_end = min(max_poses + 1, n)  (JointOptimization.cpp:566-567)
+  const uint32_t n = ctx->n_poses;
+  const uint64_t poses_end = std::min<uint64_t>((uint64_t)max_pose + 1, n);
+  const int cap = o->max_correspondences_per_point;
+  uint32_t lo = std::max(min_pose, src_lo), hi = (uint32_t)std::min<uint64_t>(poses_end, src_hi);
+  if (poses_end <= min_pose || lo >= hi || cap <= 0 || ctx->n_points == 0) {
+    if (cap <= 0 && poses_end > min_pose && lo < hi) inf.n_queries = 0;
+    ctx->have_stf = true;
+    if (info) *info = inf;
+    return HITL_OK;
+  }
+  const uint32_t jmin = min_pose, jmax = (uint32_t)poses_end - 1;
+  const size_t rec_cap = (size_t)ctx->n_points * cap;
+  if (rec_cap >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: n_points * cap exceeds 2^32 records");
+  HITL_CUDA(ctx->d_raw_j.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_k.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_idx.ensure(rec_cap));
+  HITL_CUDA(ctx->d_tile_cnt.ensure(ctx->n_tiles));
+  HITL_CUDA(ctx->d_counters.ensure(8));
+  HITL_CUDA(ctx->d_pose_cnt.ensure(2 * (size_t)n + 2));
+  HITL_CUDA(ctx->d_k.ensure(rec_cap)); HITL_CUDA(ctx->d_idx.ensure(rec_cap));
+  const size_t pair_cap = rec_cap / (o->min_inter_pose_correspondence + 1) + 1;
+  HITL_CUDA(ctx->d_pair_i.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_j.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_off.ensure(pair_cap + 1));
+
+  HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));
+  int rc = upload_poses_and_prep(ctx, pose_array, o->point_match_threshold);
+  if (rc) return rc;
+
+  SearchParams P;
+  P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pn = ctx->d_node_pn.p; P.node_meta = ctx->d_node_meta.p;
+  P.rec = ctx->d_rec.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
+  P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
+  P.jmin = jmin; P.jmax = jmax; P.thr = o->point_match_threshold; P.min_cos = o->min_cosine_angle; P.cap = cap;
+  P.skip = o->num_skip_readings; P.no_cull = o->disable_culling;
+  P.raw_j = ctx->d_raw_j.p; P.raw_k = ctx->d_raw_k.p; P.raw_idx = ctx->d_raw_idx.p; P.tile_cnt = ctx->d_tile_cnt.p;
+  P.counters = (unsigned long long*)ctx->d_counters.p;
+  const uint32_t n_tiles = P.tile_hi - P.tile_lo;
+  const uint32_t wpb = kSearchThreads / 32;
+  const size_t smem = (size_t)stack_levels(ctx->max_scan) * kSearchThreads * sizeof(uint4);
+  HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (n_tiles) {
+    HITL_CUDA(cudaFuncSetAttribute(stf_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stf_search_kernel<<<(n_tiles + wpb - 1) / wpb, kSearchThreads, smem, ctx->stream>>>(P);
+    HITL_LAUNCH_CHECK("stf_search_kernel");
+  }
+  HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+  OrderParams Q;
+  Q.raw_j = ctx->d_raw_j.p; Q.raw_k = ctx->d_raw_k.p; Q.raw_idx = ctx->d_raw_idx.p; Q.tile_cnt = ctx->d_tile_cnt.p;
+  Q.tile_begin = ctx->d_tile_begin.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
+  Q.min_corr = o->min_inter_pose_correspondence;
+  const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)ctx->sm_count * 8);
+  HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
+  HITL_CUDA(cudaMemsetAsync(ctx->d_srt_j.p, 0, sizeof(uint32_t) * (size_t)order_grid * n, ctx->stream));
+  Q.scratch = ctx->d_srt_j.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
+  Q.pair_i = ctx->d_pair_i.p; Q.pair_j = ctx->d_pair_j.p; Q.pair_off = (unsigned long long*)ctx->d_pair_off.p;
+  Q.out_k = ctx->d_k.p; Q.out_idx = ctx->d_idx.p;
+  stf_order_kernel<0><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
+  HITL_LAUNCH_CHECK("stf_order_kernel<0>");
+  pose_cnt_scan_kernel<<<1, 1024, 0, ctx->stream>>>((unsigned long long*)ctx->d_pose_cnt.p, hi - lo, (unsigned long long*)ctx->d_counters.p);
+  HITL_LAUNCH_CHECK("pose_cnt_scan_kernel");
+  stf_order_kernel<1><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
+  HITL_LAUNCH_CHECK("stf_order_kernel<1>");
+  HITL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
+  inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4];
+  // terminating offset of the CSR
+  HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  HITL_CUDA(cudaEventElapsedTime(&inf.ms_search, ctx->ev[1], ctx->ev[2]));
+  HITL_CUDA(cudaEventElapsedTime(&inf.ms_total, ctx->ev[0], ctx->ev[3]));
+  ctx->n_pairs = inf.n_pairs; ctx->n_matches = inf.n_matches; ctx->have_stf = true;
+  if (info) *info = inf;
+  return HITL_OK;
+}
+
+extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf: no search result");
+  const uint64_t np = ctx->n_pairs, nm = ctx->n_matches;
+  if (pair_off && np == 0) pair_off[0] = 0;
+  if (np) {
+    if (pair_i) HITL_CUDA(cudaMemcpyAsync(pair_i, ctx->d_pair_i.p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_j) HITL_CUDA(cudaMemcpyAsync(pair_j, ctx->d_pair_j.p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_off) HITL_CUDA(cudaMemcpyAsync(pair_off, ctx->d_pair_off.p, 8 * (np + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (nm) {
+    if (k) HITL_CUDA(cudaMemcpyAsync(k, ctx->d_k.p, 4 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idx) HITL_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, 4 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+extern "C" int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min_pose, int32_t max_pose, const hitl_stf_opts* o,
+                            uint64_t* n_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!pose_array || !o || min_pose < 0) return fail(ctx, HITL_ERR_ARG, "hitl_find_vo: bad argument");
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_find_vo: scans/trees not set");
+  ctx->n_vo = 0;
+  if (n_out) *n_out = 0;
+  const uint64_t poses_end = std::min<uint64_t>((uint64_t)((int64_t)max_pose + 1 < 0 ? 0 : (int64_t)max_pose + 1), ctx->n_poses);
+  if ((int64_t)poses_end < (int64_t)min_pose + 1 || poses_end < 2 || (uint64_t)min_pose + 1 >= poses_end) return HITL_OK;
+  int rc = upload_poses_and_prep(ctx, pose_array, o->point_match_threshold);
+  if (rc) return rc;
+  const uint32_t i_lo = (uint32_t)min_pose, i_hi = (uint32_t)poses_end - 1;   // sources i in [i_lo, i_hi)
+  HITL_CUDA(ctx->d_vo_tk.ensure(ctx->n_points)); HITL_CUDA(ctx->d_tile_cnt.ensure(std::max<size_t>(ctx->n_tiles, ctx->n_poses)));
+  const int threads = 128;
+  vo_search_kernel<<<((size_t)(i_hi - i_lo) * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(
+      ctx->d_pts.p, ctx->d_nrm.p, ctx->d_node_pn.p, ctx->d_node_meta.p, ctx->d_rec.p, ctx->d_pose.p, i_lo, i_hi, o->point_match_threshold,
+      o->min_cosine_angle, ctx->d_vo_tk.p, ctx->d_tile_cnt.p);
+  HITL_LAUNCH_CHECK("vo_search_kernel");
+  // compaction on the host side of the call (result is (N-1)*P slots; the reference never consumes it)
+  const uint32_t p_lo = ctx->h_off[i_lo], p_hi = ctx->h_off[i_hi];
+  std::vector<uint32_t> slots(p_hi - p_lo);
+  if (p_hi > p_lo) HITL_CUDA(cudaMemcpyAsync(slots.data(), ctx->d_vo_tk.p + p_lo, 4 * (size_t)(p_hi - p_lo), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> sp, sk, tk;
+  for (uint32_t i = i_lo; i < i_hi; ++i)
+    for (uint32_t k = ctx->h_off[i]; k < ctx->h_off[i + 1]; ++k)
+      if (slots[k - p_lo] != 0xFFFFFFFFu) { sp.push_back(i); sk.push_back(k - ctx->h_off[i]); tk.push_back(slots[k - p_lo]); }
+  ctx->n_vo = sp.size();
+  HITL_CUDA(ctx->d_vo_sp.ensure(sp.size())); HITL_CUDA(ctx->d_vo_sk.ensure(sp.size())); HITL_CUDA(ctx->d_vo_tk.ensure(std::max<size_t>(sp.size(), ctx->n_points)));
+  if (!sp.empty()) {
+    HITL_CUDA(cudaMemcpy(ctx->d_vo_sp.p, sp.data(), 4 * sp.size(), cudaMemcpyHostToDevice));
+    HITL_CUDA(cudaMemcpy(ctx->d_vo_sk.p, sk.data(), 4 * sp.size(), cudaMemcpyHostToDevice));
+    HITL_CUDA(cudaMemcpy(ctx->d_vo_tk.p, tk.data(), 4 * sp.size(), cudaMemcpyHostToDevice));
+  }
+  if (n_out) *n_out = ctx->n_vo;
+  return HITL_OK;
+}
+
+extern "C" int hitl_get_vo(hitl_ctx* ctx, uint32_t* source_pose, uint32_t* source_point, uint32_t* target_point) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->n_vo == 0) return HITL_OK;
+  if (source_pose) HITL_CUDA(cudaMemcpy(source_pose, ctx->d_vo_sp.p, 4 * ctx->n_vo, cudaMemcpyDeviceToHost));
+  if (source_point) HITL_CUDA(cudaMemcpy(source_point, ctx->d_vo_sk.p, 4 * ctx->n_vo, cudaMemcpyDeviceToHost));
+  if (target_point) HITL_CUDA(cudaMemcpy(target_point, ctx->d_vo_tk.p, 4 * ctx->n_vo, cudaMemcpyDeviceToHost));
+  return HITL_OK;
+}

@@ -1,0 +1,38 @@
+"""Source-pose sharding of the hot path across the GPUs of one box.
+
+The correspondence search is independent per SOURCE pose (each source point carries its own
+cap state across the ascending target loop), so rank r owns a contiguous source-pose range
+balanced by point count; scans and trees are replicated.  Residual blocks live on the rank
+that found them (pose_index0 is in its range).  The only exchange is one all-reduce of the
+packed normal-equation blocks per Gauss-Newton / LM iteration.
+"""
+import numpy as np
+
+
+def shard_ranges(offsets, world_size):
+    """Contiguous [lo, hi) source-pose ranges, one per rank, balanced by number of points."""
+    offsets = np.asarray(offsets, np.int64)
+    n = len(offsets) - 1
+    total = int(offsets[-1])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        b = int(np.searchsorted(offsets, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+def concat_stf(parts):
+    """Concatenate per-shard CSR results (in rank order) into the full reference-ordered result."""
+    pair_i = np.concatenate([p["pair_i"] for p in parts]) if parts else np.zeros(0, np.uint32)
+    pair_j = np.concatenate([p["pair_j"] for p in parts]) if parts else np.zeros(0, np.uint32)
+    k = np.concatenate([p["k"] for p in parts]) if parts else np.zeros(0, np.uint32)
+    idx = np.concatenate([p["idx"] for p in parts]) if parts else np.zeros(0, np.uint32)
+    offs, base = [np.zeros(1, np.uint64)], 0
+    for p in parts:
+        o = np.asarray(p["pair_off"], np.uint64)
+        offs.append(o[1:] + np.uint64(base))
+        base += int(o[-1])
+    return dict(pair_i=pair_i, pair_j=pair_j, pair_off=np.concatenate(offs), k=k, idx=idx,
+                n_queries=sum(int(p.get("n_queries", 0)) for p in parts))

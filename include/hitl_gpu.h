@@ -1,0 +1,199 @@
+/* hitl_gpu.h — C ABI of the B200 (sm_100a) back-end for HitL-SLAM's data-parallel hot path.
+ *
+ * Drop-in boundary: every entry point replaces one reference interface on the path
+ * BASELINE.json:north_star names (paths relative to HitL-SLAM/src/ of ut-amrl/hitl-slam):
+ *
+ *   hitl_set_scans / hitl_build_kdtrees   JointOpt::BuildKDTrees            human_in_the_loop_slam/JointOptimization.cpp:514-537
+ *                                         KDTree<float,2>::BuildKDTree      perception_tools/kdtree.cpp:37-139
+ *   hitl_kd_query                         KDTree::FindNearestPointNormal    perception_tools/kdtree.cpp:141-197
+ *                                         KDTree::FindNearestPoint          perception_tools/kdtree.cpp:220-273
+ *                                         KDTree::FindNeighborPoints        perception_tools/kdtree.cpp:199-218 (count only)
+ *   hitl_find_stf / hitl_get_stf          JointOpt::FindSTFCorrespondences  JointOptimization.cpp:561-642
+ *   hitl_find_vo / hitl_get_vo            JointOpt::FindVisualOdometryCorrespondences  JointOptimization.cpp:432-468
+ *   hitl_world_transform                  HitLSLAM::transformPointCloudsToWorldFrame   human_in_the_loop_slam/HitLSLAM.cpp:245-254
+ *   hitl_em_inliers                       E-step of EMInput::AutomaticEndpointAdjustment  human_in_the_loop_slam/EMinput.cpp:207-218
+ *   hitl_em_assign                        EMInput::EstablishObservationSets EMinput.cpp:281-323
+ *   hitl_set_*_blocks / hitl_eval         AutoDiffCostFunction<...>::Evaluate of the blocks added by
+ *                                         AddSTFConstraints :539-559, AddOdometryConstraints :736-825,
+ *                                         AddHumanConstraints :969-1054 (functors: residual_functors.h:768-848,
+ *                                         1054-1133, 1299-1415; point-to-line :314-385, :557-622)
+ *   hitl_normal_eq                        per-pose 3x3 J^T J / J^T r blocks of the same problem (input of the
+ *                                         Gauss-Newton / LM step the host solver takes)
+ *
+ * Conventions: plain pointers and sizes; the caller owns every host buffer; the context owns
+ * all device memory; scans/trees are uploaded once per session, poses per call. Every call
+ * returns a status (0 = ok) and never throws or aborts; hitl_last_error() describes the last
+ * failure. There is no CPU fallback: without a CUDA device hitl_create fails.
+ * One context per GPU per process; calls on one context must come from one thread at a time.
+ */
+#ifndef HITL_GPU_H_
+#define HITL_GPU_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hitl_ctx hitl_ctx;
+
+enum {
+  HITL_OK = 0,
+  HITL_ERR_ARG = 1,       /* bad argument */
+  HITL_ERR_CUDA = 2,      /* CUDA runtime error (message in hitl_last_error) */
+  HITL_ERR_STATE = 3,     /* call order: scans / trees / blocks not set */
+  HITL_ERR_OVERFLOW = 4,  /* caller buffer too small */
+  HITL_ERR_NCCL = 5
+};
+
+/* ---- context ------------------------------------------------------------------------- */
+int hitl_create(hitl_ctx** ctx, int device);
+void hitl_destroy(hitl_ctx* ctx);
+const char* hitl_last_error(const hitl_ctx* ctx);
+/* cudaStream_t all kernels of this context are launched on (for external CUDA-event timing). */
+void* hitl_stream(hitl_ctx* ctx);
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t hitl_launch_count(const hitl_ctx* ctx);
+int hitl_sm_count(const hitl_ctx* ctx);
+
+/* ---- scans and KD-trees ----------------------------------------------------------------- */
+/* Robot-frame point and normal clouds of all poses, concatenated; scan i owns
+ * [scan_offsets[i], scan_offsets[i+1]). float2 AoS on the host, kept SoA-of-float2 in HBM. */
+int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* scan_offsets, const float* pts_xy,
+                   const float* nrm_xy);
+
+/* One KD node, preorder-flattened: a subtree of n nodes rooted at position p has its left
+ * child (n/2 nodes) at p+1 and its right child (n-1-n/2 nodes) at p+1+n/2. */
+typedef struct {
+  float px, py, nx, ny;
+  int32_t index; /* index of the point inside its scan */
+  int32_t dim;   /* splitting dimension, 0 or 1 */
+} hitl_kdnode;
+
+/* Build every scan's tree with the reference's algorithm (max-variance split, std::sort,
+ * median n/2) and make it resident.  v1 builds on the host side of the library. */
+int hitl_build_kdtrees(hitl_ctx* ctx);
+/* Or adopt trees built elsewhere (same layout, concatenated by scan_offsets). */
+int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes);
+int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* nodes_out);
+
+/* The same builder for one scan without a context (pure host code; used by tests and by callers
+ * that want to inspect a tree).  out must hold n nodes. */
+int hitl_kdtree_build_host(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out);
+
+/* Batched tree queries against scan `scan`.  mode 0 = FindNearestPointNormal, 1 = FindNearestPoint,
+ * 2 = FindNeighborPoints (dist_out unused, index_out = number of neighbours).
+ * index_out = -1 when the reference would leave neighbor_node untouched. */
+int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t n_queries, const float* q_xy, float threshold, int mode,
+                  float* dist_out, int32_t* index_out);
+
+/* ---- scan-to-scan correspondence search ------------------------------------------------ */
+typedef struct {
+  float point_match_threshold;          /* kPointMatchThreshold, config 0.15 */
+  float min_cosine_angle;               /* cos(kMaxStfAngleError) computed once by the caller */
+  int32_t max_correspondences_per_point; /* kMaxCorrespondencesPerPoint, config 6 */
+  uint32_t num_skip_readings;           /* config 1 */
+  uint32_t min_inter_pose_correspondence; /* kMinInterPoseCorrespondence = 10: keep pairs with MORE matches */
+  uint32_t disable_culling;             /* debug: 1 = visit every pair exactly as the CPU loop does */
+} hitl_stf_opts;
+
+typedef struct {
+  uint64_t n_pairs;       /* kept ordered pose pairs (= residual blocks) */
+  uint64_t n_matches;     /* correspondences in kept pairs */
+  uint64_t n_raw_matches; /* matches before the > min_inter_pose_correspondence filter */
+  uint64_t n_queries;     /* KD queries the reference semantics execute (cap-skipped ones excluded) */
+  uint64_t n_traversals;  /* queries that actually walked a tree on the GPU (rest proven empty by AABB tests) */
+  float ms_search;        /* device time of the search kernel alone (CUDA events on the ctx stream) */
+  float ms_total;         /* device time of the whole call: pose prep + search + ordering/compaction */
+} hitl_stf_info;
+
+/* Correspondences between source poses [src_lo, src_hi) ∩ [min_pose, max_pose] and all target
+ * poses in [min_pose, max_pose].  src_lo = 0, src_hi = UINT32_MAX gives the reference call;
+ * a narrower source range is one shard of it (results of consecutive shards concatenate to
+ * the full result).  pose_array: x, y, theta doubles per pose (JointOpt::pose_array_).
+ * Results stay resident for hitl_set_stf_blocks_from_search / hitl_get_stf. */
+int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t min_pose, uint32_t max_pose, uint32_t src_lo,
+                  uint32_t src_hi, const hitl_stf_opts* opts, hitl_stf_info* info);
+/* CSR copy-out in the reference's order (pose_index0 asc, pose_index1 asc, points0 index asc):
+ * pair_i/pair_j [n_pairs], pair_off [n_pairs+1], k/idx [n_matches]. */
+int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx);
+
+/* Consecutive-pose matching with the Euclidean query. n_out = number of correspondences. */
+int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min_pose, int32_t max_pose,
+                 const hitl_stf_opts* opts, uint64_t* n_out);
+int hitl_get_vo(hitl_ctx* ctx, uint32_t* source_pose, uint32_t* source_point, uint32_t* target_point);
+
+/* ---- world-frame clouds and EM assignment ------------------------------------------------ */
+/* world = Rotation2Df(theta) * p + t for every point; poses_xyt: 3 floats per pose (poses_).
+ * Result stays resident for the EM calls; world_xy_out may be NULL. */
+int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float* world_xy_out);
+int hitl_set_world_clouds(hitl_ctx* ctx, const float* world_xy);
+
+/* E-step: every world point with DistanceToLineSegment(seg) < threshold, in (pose, index) order.
+ * seg = {p0x, p0y, p1x, p1y}. out_* may be NULL (count only); cap = capacity of the out arrays. */
+int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double threshold, uint64_t cap, uint32_t* out_pose,
+                    uint32_t* out_idx, float* out_xy, uint64_t* n_out);
+
+/* Observation sets of both strokes: segs = {a0, a1, b0, b1} as 8 floats.  A pose is kept for a
+ * stroke when MORE than min_obs of its points are within threshold (reference: 5).
+ * For stroke f: set_pose[f][s], set_off[f][s..s+1] into obs[f][]. Capacities: n_poses, n_poses+1,
+ * total points. */
+int hitl_em_assign(hitl_ctx* ctx, const float segs[8], double threshold, uint32_t min_obs, uint32_t n_sets[2],
+                   uint32_t* set_pose0, uint64_t* set_off0, uint32_t* obs0, uint32_t* set_pose1, uint64_t* set_off1,
+                   uint32_t* obs1);
+
+/* ---- residual blocks --------------------------------------------------------------------- */
+/* Block order of hitl_eval = [odometry | human | stf | p2l_glob | p2l], each in the order given. */
+/* STF blocks = the kept pairs of the last hitl_find_stf on this context (AddSTFConstraints). */
+int hitl_set_stf_blocks_from_search(hitl_ctx* ctx, float laser_std_dev, float point_point_correlation_factor);
+/* Or from an explicit CSR list. */
+int hitl_set_stf_blocks(hitl_ctx* ctx, uint64_t n_pairs, const uint32_t* pair_i, const uint32_t* pair_j,
+                        const uint64_t* pair_off, const uint32_t* k, const uint32_t* idx, float laser_std_dev,
+                        float point_point_correlation_factor);
+/* Odometry blocks between poses b and b+1: 9 floats each = axis_transform (row-major 2x2), radial,
+ * tangential, angular std-dev, radial_translation, rotation (PoseConstraint's members). */
+int hitl_set_odometry_blocks(hitl_ctx* ctx, uint32_t n_blocks, const float* consts9);
+/* Human blocks: type_pose = {CorrectionType, constrained pose} per block, targets = {x, y, theta,
+ * penalty_dir} doubles per block (what AddHumanConstraints passes to the functor constructors). */
+int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int32_t* type_pose, const double* targets4);
+/* Point-to-line-glob blocks (one pose per block, CSR over points) and single point-to-line blocks. */
+int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const uint32_t* blk_pose, const uint64_t* blk_off,
+                             const float* pts_xy, const float* line_normal_xy, const float* line_offset,
+                             const uint8_t* valid, float std_dev, float correlation_factor);
+int hitl_set_p2l_blocks(hitl_ctx* ctx, uint64_t n_blocks, const uint32_t* pose_idx, const float* pts_xy,
+                        const float* line_normal_xy, const float* line_offset, const uint8_t* valid, float std_dev,
+                        float correlation_factor);
+
+typedef struct {
+  uint64_t n_odometry, n_human, n_stf, n_p2l_glob, n_p2l;
+  uint64_t n_residuals;  /* doubles in r_out */
+  uint64_t n_jacobian;   /* doubles in J_out */
+} hitl_eval_layout;
+/* r_out / J_out layout per block kind (row-major [residual][param], pose blocks side by side):
+ *   odometry : r 3, J 18 = [3x3 wrt pose b | 3x3 wrt pose b+1]
+ *   human    : r 3 (unused rows 0), J 9 = [3x3 wrt constrained pose] (unused rows 0)
+ *   stf      : r 2, J 12 = [2x3 wrt pose_index0 | 2x3 wrt pose_index1]
+ *   p2l_glob : r 1, J 3 ;  p2l : r 1, J 3 */
+int hitl_eval_layout_get(hitl_ctx* ctx, hitl_eval_layout* layout);
+/* precision: 0 = FP64 (<=1e-9 rel. vs the CPU functors), 1 = FP32 arithmetic (<=1e-5). J_out may be NULL. */
+int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision, double* r_out, double* J_out, float* ms_out);
+/* Normal-equation blocks of the whole problem at pose_array: H_diag [n_poses x 9] (J^T J, row-major
+ * 3x3 per pose), g [n_poses x 3] (J^T r), H_off [n_binary_blocks x 9] (J_a^T J_b per odometry block,
+ * then per stf block), cost = 1/2 sum r^2. Any output may be NULL. Results also stay resident
+ * (hitl_normal_eq_device) for a device-side all-reduce. */
+int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* H_off, double* cost,
+                   float* ms_out);
+/* Device pointer + length (doubles) of the packed [H_diag | g | cost] buffer of the last hitl_normal_eq. */
+int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
+
+/* ---- diagnostics ------------------------------------------------------------------------- */
+/* Device evaluation of the library's sinf/cosf (bit-identical to glibc 2.39's x86-64 FMA variant;
+ * csrc/hitl_math.h) and of RelativePoseTransform (JointOptimization.cpp:296-305) for parity tests. */
+int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out);
+int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src,
+                             const uint32_t* dst, float* out6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HITL_GPU_H_ */

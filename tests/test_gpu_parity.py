@@ -1,0 +1,412 @@
+"""GPU parity suite (-m gpu): the sm_100a kernels, called through the C ABI, against the CPU
+oracle on identical inputs.  Index sets and EM assignments bit-exact; residuals / Jacobians
+within 1e-9 relative (FP64) and 1e-5 (FP32 mode), as BASELINE.json:north_star states."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_same_stf, random_scans
+
+pytestmark = pytest.mark.gpu
+
+REL64 = 1e-9     # FP64 tolerance (north_star)
+REL32 = 1e-5     # FP32-mode tolerance (north_star)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    return np.abs(a - b).max() / scale if b.size else 0.0
+
+
+def load_map(gpu, g):
+    gpu.set_scans(g["offsets"], g["pts"], g["nrm"])
+    gpu.build_kdtrees()
+
+
+# ---- device arithmetic -----------------------------------------------------------------------------
+def test_device_sincos_bit_exact(gpu, host):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-8, 8, 1 << 20), rng.uniform(-130, 130, 1 << 18), rng.normal(size=1 << 16) * 1e4,
+                        np.array([0.0, -0.0, 1e-30, 2 ** -12, 0.785398, 0.785399, 119.99, 120.0, 1e9, 3e38])]).astype(np.float32)
+    s, c = gpu.debug_sincos(x)
+    hs = np.array([host.lib.hitl_host_sinf(float(v)) for v in x[:4096]], np.float32)
+    assert np.array_equal(hs.view(np.uint32), s[:4096].view(np.uint32))
+    # against the platform libm (what the reference calls) through numpy's float32 ufuncs is not
+    # guaranteed to be libm; use the oracle's wrappers instead
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    idx = rng.integers(0, len(x), 20000)
+    ls = np.array([o.lib.orc_sinf(float(v)) for v in x[idx]], np.float32)
+    lc = np.array([o.lib.orc_cosf(float(v)) for v in x[idx]], np.float32)
+    assert np.array_equal(ls.view(np.uint32), s[idx].view(np.uint32))
+    assert np.array_equal(lc.view(np.uint32), c[idx].view(np.uint32))
+
+
+def test_device_relative_pose_bit_exact(gpu, oracle, maps):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    rng = np.random.default_rng(1)
+    src, dst = rng.integers(0, n, 2000).astype(np.uint32), rng.integers(0, n, 2000).astype(np.uint32)
+    out = gpu.debug_relative_pose(poses, src, dst)
+    ref = np.zeros(6, np.float32)
+    for q in range(2000):
+        oracle.lib.orc_relative_pose(poses.reshape(-1), int(src[q]), int(dst[q]), ref)
+        assert np.array_equal(ref.view(np.uint32), out[q].view(np.uint32))
+
+
+# ---- KD queries ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 360, 1080, 2160])
+def test_kd_queries_match_oracle(gpu, oracle, n):
+    rng = np.random.default_rng(n)
+    off, pts, nrm = random_scans(rng, 3, n, n, empty=(1,))
+    gpu.set_scans(off, pts, nrm)
+    gpu.build_kdtrees()
+    S = oracle.scans(off, pts, nrm)
+    nodes = gpu.get_kdtrees()
+    pn, idx, dim = S.flatten()
+    assert np.array_equal(nodes["index"], idx) and np.array_equal(nodes["dim"], dim) and np.array_equal(nodes["px"], pn[:, 0])
+    for scan in (0, 1, 2):
+        m = int(off[scan + 1] - off[scan])
+        base = pts[off[scan]:off[scan + 1]] if m else np.zeros((1, 2), np.float32)
+        q = (base[rng.integers(0, len(base), 5000)] + rng.normal(size=(5000, 2)) * 0.1).astype(np.float32)
+        q[:50] = base[rng.integers(0, len(base), 50)]
+        q[50:100, 0] = base[rng.integers(0, len(base), 50), 0]
+        for mode in (0, 1):
+            for thr in (0.05, 0.15, 1.0):
+                d0, i0 = S.query(scan, q, thr, mode)
+                d1, i1 = gpu.kd_query(scan, q, thr, mode)
+                if m == 0:
+                    assert (i1 == -1).all()
+                    continue
+                assert np.array_equal(i0, i1), (scan, mode, thr)
+                assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)), (scan, mode, thr)
+        if m:
+            _, cnt = gpu.kd_query(scan, q[:200], 0.3, 2)
+            ref = np.array([len(S.radius(scan, q[k, 0], q[k, 1], 0.3)) for k in range(200)])
+            assert np.array_equal(cnt, ref)
+
+
+# ---- correspondence search -------------------------------------------------------------------------
+@pytest.mark.parametrize("name,normals", [("tiny", "compensated"), ("tiny", "faithful"), ("small", "compensated"), ("small", "faithful")])
+def test_find_stf_bit_exact(gpu, oracle, maps, name, normals):
+    g = maps(name, normals=normals)
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses)
+    for cull in (0, 1):
+        out = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=cull))
+        assert_same_stf(out, ref)
+        assert out["n_queries"] == ref["n_queries"]
+    assert len(ref["pair_i"]) > 0 or normals == "faithful"
+
+
+def test_find_stf_golden_fixture(gpu):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tiny_compensated.npz"))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tiny_stf.npz"))
+    gpu.set_scans(g["offsets"], g["pts"], g["nrm"])
+    gpu.build_kdtrees()
+    out = gpu.find_stf(g["poses"].astype(np.float64))
+    assert_same_stf(out, gold)
+    assert out["n_queries"] == int(gold["n_queries"])
+
+
+@pytest.mark.parametrize("opts", [dict(cap=1), dict(cap=3, skip=2), dict(cap=6, skip=5, min_corr=0), dict(thr=0.05, min_corr=3),
+                                  dict(thr=0.4, cap=12, min_corr=25), dict(min_cos=-2.0), dict(cap=0)])
+def test_find_stf_option_sweep(gpu, oracle, maps, opts):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses, **opts)
+    out = gpu.find_stf(poses, opts=gpu.stf_opts(**opts))
+    assert_same_stf(out, ref)
+    if opts.get("cap", 6) > 0:
+        assert out["n_queries"] == ref["n_queries"]
+
+
+@pytest.mark.parametrize("rng_", [(0, 159), (10, 90), (37, 37), (50, 1000), (120, 60)])
+def test_find_stf_pose_ranges(gpu, oracle, maps, rng_):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses, min_pose=rng_[0], max_pose=rng_[1])
+    out = gpu.find_stf(poses, min_pose=rng_[0], max_pose=rng_[1])
+    assert_same_stf(out, ref)
+    assert out["n_queries"] == ref["n_queries"]
+
+
+def test_find_stf_shards_concatenate(gpu, oracle, maps):
+    from hitl_slam_b200.sharding import concat_stf, shard_ranges
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses)
+    for world in (2, 3, 8):
+        parts = [gpu.find_stf(poses, src_lo=a, src_hi=b) for a, b in shard_ranges(g["offsets"], world)]
+        cat = concat_stf(parts)
+        assert_same_stf(cat, ref)
+        assert cat["n_queries"] == ref["n_queries"]
+
+
+def test_find_stf_ragged_and_empty_scans(gpu, oracle):
+    rng = np.random.default_rng(11)
+    # a strip of overlapping random scans, some empty, sizes from 1 to 300
+    off, pts, nrm = random_scans(rng, 60, 1, 300, empty=(0, 7, 8, 59))
+    pts = (pts * 0.5).astype(np.float32)
+    poses = np.stack([np.linspace(0, 3, 60), rng.normal(size=60) * 0.1, rng.uniform(-0.3, 0.3, 60)], 1)
+    gpu.set_scans(off, pts, nrm)
+    gpu.build_kdtrees()
+    S = oracle.scans(off, pts, nrm)
+    for opts in (dict(), dict(min_corr=0, min_cos=-2.0), dict(thr=0.5, min_cos=-2.0, cap=4)):
+        ref = S.find_stf(poses, **opts)
+        out = gpu.find_stf(poses, opts=gpu.stf_opts(**opts))
+        assert_same_stf(out, ref)
+        assert out["n_queries"] == ref["n_queries"]
+    assert len(S.find_stf(poses, min_corr=0, min_cos=-2.0)["k"]) > 0
+
+
+def test_find_stf_empty_problem(gpu):
+    gpu.set_scans(np.zeros(1, np.uint32), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    gpu.build_kdtrees()
+    out = gpu.find_stf(np.zeros(0))
+    assert out["n_pairs"] == 0 and out["n_matches"] == 0 and list(out["pair_off"]) == [0]
+
+
+def test_find_stf_c1_full_size(gpu, oracle, maps):
+    """BASELINE config 1 (500 poses x 360 points) end to end, bit-exact."""
+    g = maps("c1")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses)
+    out = gpu.find_stf(poses)
+    assert_same_stf(out, ref)
+    assert out["n_queries"] == ref["n_queries"]
+    assert out["n_pairs"] > 1000
+
+
+def test_find_stf_culling_is_result_preserving_at_scale(gpu, maps):
+    """Size-independent property: AABB culling never changes the result (2000 x 360, too big for the oracle to be quick)."""
+    g = maps("c2", n_poses=2000, beams=360)
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    a = gpu.find_stf(poses)
+    b = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=1))
+    assert_same_stf(a, b)
+    assert a["n_queries"] == b["n_queries"] and a["n_traversals"] < b["n_traversals"]
+    counts = np.diff(a["pair_off"].astype(np.int64))
+    assert (counts > 10).all()
+    # per source point at most `cap` matches over all pairs
+    key = a["pair_i"].astype(np.int64).repeat(counts) * (1 << 20) + a["k"]
+    assert np.unique(key, return_counts=True)[1].max() <= 6
+    # pairs sorted by (i, j), k ascending inside a pair
+    pij = a["pair_i"].astype(np.int64) * (1 << 32) + a["pair_j"]
+    assert (np.diff(pij) > 0).all()
+    for bb in range(0, len(counts), 997):
+        kk = a["k"][int(a["pair_off"][bb]):int(a["pair_off"][bb + 1])]
+        assert (np.diff(kk.astype(np.int64)) > 0).all()
+
+
+def test_find_vo_matches_oracle(gpu, oracle, maps):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    for lo, hi in ((0, 159), (20, 60), (5, 5)):
+        ref = S.find_vo(poses, lo, hi)
+        out = gpu.find_vo(poses, lo, hi)
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b)
+    assert len(S.find_vo(poses)[0]) > 0
+
+
+# ---- world transform + EM ---------------------------------------------------------------------------
+def test_world_transform_bit_exact(gpu, oracle, maps):
+    g = maps("small")
+    load_map(gpu, g)
+    ref = oracle.scans(g["offsets"], g["pts"], g["nrm"], build_trees=False).world_transform(g["poses"])
+    out = gpu.world_transform(g["poses"])
+    assert np.array_equal(ref.view(np.uint32), out.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_em_inliers_and_assign_bit_exact(gpu, oracle, maps, name):
+    from hitl_slam_b200 import synth
+    g = maps(name)
+    load_map(gpu, g)
+    world = gpu.world_transform(g["poses"])
+    strokes = synth.make_strokes(g)
+    rng = np.random.default_rng(2)
+    cases = [strokes, strokes + rng.normal(size=(4, 2)).astype(np.float32) * 0.02,
+             np.array([[0, 0], [30, 9], [1, 1], [1, 1]], np.float32),      # long diagonal stroke / degenerate stroke
+             np.array([[-5, -5], [-4, -5], [100, 100], [101, 100]], np.float32)]   # nothing selected
+    for s in cases:
+        for seg in (s[:2], s[2:]):
+            op, oi = oracle.em_inliers(g["offsets"], world, seg.reshape(-1))
+            gp, gi, gxy = gpu.em_inliers(seg.reshape(-1))
+            assert np.array_equal(op, gp) and np.array_equal(oi, gi)
+            assert np.array_equal(gxy, world[g["offsets"][gp].astype(np.int64) + gi]) if len(gp) else True
+            assert gpu.em_inliers(seg.reshape(-1), fetch=False) == len(op)
+        ref = oracle.em_assign(g["offsets"], world, s)
+        out = gpu.em_assign(s)
+        for f in range(2):
+            for a, b in zip(ref[f], out[f]):
+                assert np.array_equal(a, b)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "small_em.npz"))
+    if name == "small":
+        gp, gi, _ = gpu.em_inliers(gold["strokes"][:2].reshape(-1))
+        assert np.array_equal(gp, gold["inl_pose"]) and np.array_equal(gi, gold["inl_idx"])
+
+
+def test_em_with_empty_scans(gpu, oracle):
+    rng = np.random.default_rng(4)
+    off, pts, nrm = random_scans(rng, 40, 1, 90, empty=(0, 3, 4, 39))
+    gpu.set_scans(off, pts, nrm)
+    gpu.set_world_clouds(pts)
+    seg = np.array([-1, -1, 1.5, 1.2, -2, 0.5, 2, 0.4], np.float32)
+    op, oi = oracle.em_inliers(off, pts, seg[:4], thr=0.2)
+    gp, gi, _ = gpu.em_inliers(seg[:4], thr=0.2)
+    assert len(op) > 0 and np.array_equal(op, gp) and np.array_equal(oi, gi)
+    ref, out = oracle.em_assign(off, pts, seg, thr=0.2, min_obs=1), gpu.em_assign(seg, thr=0.2, min_obs=1)
+    for f in range(2):
+        for a, b in zip(ref[f], out[f]):
+            assert np.array_equal(a, b)
+
+
+# ---- residuals / Jacobians / normal equations -----------------------------------------------------------
+def _human_constraints(n):
+    hc_i = np.array([[2, n - 3, 1], [4, n - 4, 2], [5, n - 5, 3], [6, n - 6, 0], [4, n - 2, 5]], np.int32)
+    hc_f = np.array([[0.3, -0.2, 0.1, 0.0], [1.0, 0.5, -0.4, 1.2], [0, 0, 1.57, 0], [0, 0, 0.02, 0], [-0.7, 0.1, 3.0, -0.5]], np.float32)
+    return hc_i, hc_f
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_eval_matches_oracle(gpu, oracle, maps, name):
+    g = maps(name)
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    corr = gpu.find_stf(poses)
+    rng = np.random.default_rng(0)
+    x = poses + rng.normal(size=poses.shape) * 0.01
+    consts = oracle.odometry_consts(g["poses"])
+    hc_i, hc_f = _human_constraints(n)
+    blk_i, blk_d = oracle.human_blocks(g["poses"], hc_i, hc_f)
+    gpu.set_odometry_blocks(consts)
+    gpu.set_human_blocks(blk_i, blk_d)
+    gpu.set_stf_blocks_from_search()
+    r_stf, J_stf = S.eval_stf(x, corr)
+    r_odo, J_odo = oracle.eval_odometry(consts, x)
+    r_hum, J_hum = oracle.eval_human(blk_i, blk_d, x)
+    for precision, tol in ((0, REL64), (1, REL32)):
+        out = gpu.eval(x, precision=precision)
+        assert rel_err(out["r_stf"], r_stf) <= tol and rel_err(out["J_stf"], J_stf) <= tol
+        assert rel_err(out["r_odometry"], r_odo) <= tol and rel_err(out["J_odometry"], J_odo) <= tol
+        assert rel_err(out["r_human"], r_hum) <= tol and rel_err(out["J_human"], J_hum) <= tol
+    # explicit CSR upload gives the same numbers as the device-resident search result
+    gpu.set_stf_blocks(corr)
+    out2 = gpu.eval(x)
+    assert np.array_equal(out2["r_stf"], gpu.eval(x)["r_stf"]) and rel_err(out2["J_stf"], J_stf) <= REL64
+    if name == "tiny":
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "tiny_eval.npz"))
+        o3 = gpu.eval(gold["x"])
+        assert rel_err(o3["r_stf"], gold["r_stf"]) <= REL64 and rel_err(o3["J_stf"], gold["J_stf"]) <= REL64
+        assert rel_err(o3["r_odometry"], gold["r_odo"]) <= REL64 and rel_err(o3["J_odometry"], gold["J_odo"]) <= REL64
+
+
+def test_eval_point_to_line_matches_oracle(gpu, oracle, maps):
+    g = maps("tiny")
+    load_map(gpu, g)
+    n = len(g["poses"])
+    rng = np.random.default_rng(3)
+    x = g["poses"].astype(np.float64) + rng.normal(size=(n, 3)) * 0.01
+    sizes = rng.integers(1, 80, 25)
+    blk_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    m = int(blk_off[-1])
+    blk_pose = rng.integers(0, n, 25).astype(np.uint32)
+    pts = rng.normal(size=(m, 2)).astype(np.float32) * 3
+    ang = rng.uniform(0, 6.28, m)
+    ln = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    lo = rng.normal(size=m).astype(np.float32)
+    valid = (rng.uniform(size=m) > 0.2).astype(np.uint8)
+    valid[blk_off[3]:blk_off[4]] = 0     # a block with no valid point: residual 0, Jacobian 0
+    gpu.set_odometry_blocks(np.zeros((0, 9), np.float32))
+    gpu.set_human_blocks(np.zeros((0, 2), np.int32), np.zeros((0, 4)))
+    gpu.set_stf_blocks(dict(pair_i=np.zeros(0, np.uint32), pair_j=np.zeros(0, np.uint32), pair_off=np.zeros(1, np.uint64),
+                            k=np.zeros(0, np.uint32), idx=np.zeros(0, np.uint32)))
+    gpu.set_p2l_glob_blocks(blk_pose, blk_off, pts, ln, lo, valid, 0.05, 1 / 50.0)
+    pose_idx = rng.integers(0, n, m).astype(np.uint32)
+    gpu.set_p2l_blocks(pose_idx, pts, ln, lo, valid, 0.05, 1 / 50.0)
+    rg, Jg = oracle.eval_p2l_glob(blk_pose, blk_off, pts, ln, lo, valid, 0.05, 1 / 50.0, x)
+    rs, Js = oracle.eval_p2l(pose_idx, pts, ln, lo, valid, 0.05, 1 / 50.0, x)
+    for precision, tol in ((0, REL64), (1, 2e-5)):
+        out = gpu.eval(x, precision=precision)
+        assert rel_err(out["r_p2l_glob"][:, 0], rg) <= tol and rel_err(out["J_p2l_glob"], Jg) <= tol
+        assert rel_err(out["r_p2l"][:, 0], rs) <= tol and rel_err(out["J_p2l"], Js) <= tol
+    assert out["r_p2l_glob"][3, 0] == 0 and (out["J_p2l_glob"][3] == 0).all()
+    gpu.set_p2l_glob_blocks(np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32),
+                            np.zeros(0, np.float32), np.zeros(0, np.uint8), 1.0, 1.0)
+    gpu.set_p2l_blocks(np.zeros(0, np.uint32), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.float32),
+                       np.zeros(0, np.uint8), 1.0, 1.0)
+
+
+def test_normal_equations_match_oracle_jacobians(gpu, oracle, maps):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    corr = gpu.find_stf(poses)
+    rng = np.random.default_rng(1)
+    x = poses + rng.normal(size=poses.shape) * 0.01
+    consts = oracle.odometry_consts(g["poses"])
+    hc_i, hc_f = _human_constraints(n)
+    blk_i, blk_d = oracle.human_blocks(g["poses"], hc_i, hc_f)
+    gpu.set_odometry_blocks(consts)
+    gpu.set_human_blocks(blk_i, blk_d)
+    gpu.set_stf_blocks_from_search()
+    r_stf, J_stf = S.eval_stf(x, corr)
+    r_odo, J_odo = oracle.eval_odometry(consts, x)
+    r_hum, J_hum = oracle.eval_human(blk_i, blk_d, x)
+    H, gvec = np.zeros((n, 3, 3)), np.zeros((n, 3))
+    Hoff = []
+    for b in range(n - 1):
+        for side, p in ((0, b), (1, b + 1)):
+            H[p] += J_odo[b, side].T @ J_odo[b, side]
+            gvec[p] += J_odo[b, side].T @ r_odo[b]
+        Hoff.append(J_odo[b, 0].T @ J_odo[b, 1])
+    for b in range(len(blk_i)):
+        p = blk_i[b, 1]
+        H[p] += J_hum[b].T @ J_hum[b]
+        gvec[p] += J_hum[b].T @ r_hum[b]
+    for b in range(len(corr["pair_i"])):
+        for side, p in ((0, int(corr["pair_i"][b])), (1, int(corr["pair_j"][b]))):
+            H[p] += J_stf[b, side].T @ J_stf[b, side]
+            gvec[p] += J_stf[b, side].T @ r_stf[b]
+        Hoff.append(J_stf[b, 0].T @ J_stf[b, 1])
+    cost = 0.5 * ((r_odo ** 2).sum() + (r_hum ** 2).sum() + (r_stf ** 2).sum())
+    out = gpu.normal_eq(x)
+    assert rel_err(out["H_diag"], H) <= REL64 and rel_err(out["g"], gvec) <= REL64
+    assert rel_err(out["H_off"], np.array(Hoff)) <= REL64
+    assert abs(out["cost"] - cost) <= REL64 * cost
+    ptr, nd = gpu.normal_eq_device()
+    assert ptr and nd == 12 * n + 1
+
+
+# ---- error behaviour ------------------------------------------------------------------------------------
+def test_error_paths(gpu):
+    from hitl_slam_b200 import HitlError, HitlGpu
+    fresh = HitlGpu(0)
+    with pytest.raises(HitlError):
+        fresh.find_stf(np.zeros(3))                      # scans not set
+    with pytest.raises(HitlError):
+        fresh.em_inliers(np.zeros(4, np.float32))        # world clouds not set
+    fresh.set_scans(np.array([0, 2], np.uint32), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32))
+    with pytest.raises(HitlError):
+        fresh.set_scans(np.array([0, 3, 2], np.uint32), np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32))
+    with pytest.raises(HitlError):
+        fresh.set_human_blocks(np.array([[3, 0]], np.int32), np.zeros((1, 4)))   # corner type unsupported, as in the reference
+    fresh.close()
