@@ -321,7 +321,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav,
+                "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
                            "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos]))}}
         print(json.dumps(line))
     gpu.close()

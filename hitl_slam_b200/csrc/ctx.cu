@@ -47,7 +47,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_node_pn.release(); ctx->d_node_meta.release();
-  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
   ctx->d_pose_cnt.release(); ctx->d_counters.release();
@@ -118,6 +118,9 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_begin.p, ctx->h_tile_begin.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
   int rc = launch_scan_aabb(ctx);
   if (rc) return rc;
+  ctx->h_aabb.assign(4 * (size_t)n_poses, 0.f);
+  ctx->grid_valid = false;
+  if (n_poses) HITL_CUDA(cudaMemcpyAsync(ctx->h_aabb.data(), ctx->d_aabb.p, 16 * (size_t)n_poses, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tile_scan / tile_k0 are locals
   return HITL_OK;
 }

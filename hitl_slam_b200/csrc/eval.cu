@@ -156,9 +156,14 @@ __global__ void __launch_bounds__(128) eval_stf_kernel(const float2* __restrict_
   if (b >= n_blocks) return;
   const uint32_t i = pair_i[b], j = pair_j[b];
   const unsigned long long m0 = pair_off[b], m1 = pair_off[b + 1];
-  const T t0x = (T)pose[3 * i], t0y = (T)pose[3 * i + 1], th0 = (T)pose[3 * i + 2];
-  const T t1x = (T)pose[3 * j], t1y = (T)pose[3 * j + 1], th1 = (T)pose[3 * j + 2];
-  const T c0 = cos(th0), s0 = sin(th0), c1 = cos(th1), s1 = sin(th1);
+  // Pose trigonometry and the world-frame difference p1g - p0g are always formed in FP64: the
+  // difference cancels ~10 m coordinates down to centimetres, which FP32 cannot carry to 1e-5.
+  // Everything downstream (normals, projections, derivative sums) runs in T.
+  const double t0x = pose[3 * i], t0y = pose[3 * i + 1], t1x = pose[3 * j], t1y = pose[3 * j + 1];
+  double c0d, s0d, c1d, s1d;
+  sincos(pose[3 * i + 2], &s0d, &c0d);
+  sincos(pose[3 * j + 2], &s1d, &c1d);
+  const T c0 = (T)c0d, s0 = (T)s0d, c1 = (T)c1d, s1 = (T)s1d;
   const T cf = T(corr), sd = T(std_dev);
   const uint32_t oi = off[i], oj = off[j];
   T S0 = 0, S1 = 0, G0[6] = {0, 0, 0, 0, 0, 0}, G1[6] = {0, 0, 0, 0, 0, 0};
@@ -166,11 +171,12 @@ __global__ void __launch_bounds__(128) eval_stf_kernel(const float2* __restrict_
     const uint32_t k = kk[m], q = idx[m];
     const float2 P0 = __ldg(pts + oi + k), N0 = __ldg(nrm + oi + k), P1 = __ldg(pts + oj + q), N1 = __ldg(nrm + oj + q);
     // rotated (not translated) points and normals
-    const T r0x = c0 * T(P0.x) - s0 * T(P0.y), r0y = s0 * T(P0.x) + c0 * T(P0.y);
-    const T r1x = c1 * T(P1.x) - s1 * T(P1.y), r1y = s1 * T(P1.x) + c1 * T(P1.y);
+    const double r0xd = c0d * P0.x - s0d * P0.y, r0yd = s0d * P0.x + c0d * P0.y;
+    const double r1xd = c1d * P1.x - s1d * P1.y, r1yd = s1d * P1.x + c1d * P1.y;
+    const T r0x = (T)r0xd, r0y = (T)r0yd, r1x = (T)r1xd, r1y = (T)r1yd;
     const T n0x = c0 * T(N0.x) - s0 * T(N0.y), n0y = s0 * T(N0.x) + c0 * T(N0.y);
     const T n1x = c1 * T(N1.x) - s1 * T(N1.y), n1y = s1 * T(N1.x) + c1 * T(N1.y);
-    const T dx = (r1x + t1x) - (r0x + t0x), dy = (r1y + t1y) - (r0y + t0y);
+    const T dx = (T)((r1xd + t1x) - (r0xd + t0x)), dy = (T)((r1yd + t1y) - (r0yd + t0y));
     const T u = n0x * dx + n0y * dy, v = n1x * dx + n1y * dy;
     const T a = u * cf / sd, bb = v * cf / sd;
     S0 += a * a; S1 += bb * bb;

@@ -9,15 +9,20 @@
 
 namespace hitl {
 
-// Per-pose record written by pose_prep_kernel on every search call (64 B, 16 B aligned so a
-// warp-uniform read is four LDG.128 broadcasts).
+// Target-side per-pose record written by pose_prep_kernel on every search call (64 B, 16 B
+// aligned so a warp-uniform read is four LDG.128 broadcasts).
 struct __align__(16) PoseRec {
-  float c, s, tx, ty;             // source transform  Translation(tx,ty) * Rotation(theta)
-  float i00, i01, i10, i11;       // inverse of the same transform (linear part) ...
-  float itx, ity;                 // ... and its translation
-  float bx0, by0, bx1, by1;       // robot-frame AABB of the scan, inflated by thr (+ulps): exact per-point cull
-  uint32_t off, n;                // scan offset / size (copy of scan_offsets for locality)
+  float i00, i01, i10, i11;       // inverse of Translation(t) * Rotation(theta): linear part ...
+  float itx, ity;                 // ... and translation
+  uint32_t off, n;                // scan offset / size
+  float gx0, gy0, ginv;           // occupancy grid of the scan: origin and 1 / cell size (cell >= thr)
+  uint32_t gdim;                  // nx | ny << 16  (0 = empty scan)
+  uint32_t goff;                  // first word of the scan's bitmap
+  float c, s;                     // cos / sin of the pose angle
+  uint32_t pad;
 };
+// Per-scan occupancy grid descriptor (host-built from the scan AABBs for a given threshold).
+struct GridRec { float gx0, gy0, ginv; uint32_t gdim, goff; };
 static_assert(sizeof(PoseRec) == 64, "PoseRec must be 64 bytes");
 
 template <typename T> struct DevBuf {
@@ -67,6 +72,13 @@ struct hitl_ctx {
   hitl::DevBuf<double> d_pose;           // x, y, theta
   hitl::DevBuf<hitl::PoseRec> d_rec;
   hitl::DevBuf<float4> d_wbox;           // world-frame AABB per scan, inflated (pair cull)
+  hitl::DevBuf<float4> d_src;            // source-side transform per pose: cos, sin, tx, ty
+  // occupancy bitmaps (exact "no point of scan j within thr of q" test), rebuilt when thr or the scans change
+  std::vector<float> h_aabb;             // 4 per scan
+  hitl::DevBuf<hitl::GridRec> d_grid;
+  hitl::DevBuf<uint32_t> d_occ;
+  bool grid_valid = false;
+  float grid_thr = 0.f;
 
   // ---- search results ----
   hitl::DevBuf<uint32_t> d_raw_j, d_raw_k, d_raw_idx, d_tile_cnt;   // per-tile raw records

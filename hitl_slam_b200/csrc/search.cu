@@ -24,6 +24,9 @@
 //     merge the tiles of each pose into the reference's (i, j, k) order, apply the
 //     "> 10 matches per pair" rule and emit the CSR arrays.
 #include <float.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
 #include "hitl_internal.h"
 #include "hitl_math.h"
 
@@ -79,6 +82,11 @@ __device__ __forceinline__ void nearest_point_normal(const TreeRef t, uint32_t n
         near_pos = pos + 1; near_n = nl;
         far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_UNCOND : FAR_NONE;
       }
+      // The far side is entered only if |s| < min(best, thr) <= thr: when |s| >= thr it never is.
+      if (state == FAR_COND && !(fabsf(s) < thr)) state = FAR_NONE;
+      // Tail call: nothing found at this node and no far side to consider -> the near child's result
+      // is this call's result (the merge `child < FLT_MAX` would just copy it); no frame needed.
+      if (state == FAR_NONE && bestpos == kNoPos) { pos = near_pos; n = near_n; continue; }
       stack[level * stride] = make_uint4(__float_as_uint(best), __float_as_uint(fabsf(s)), far, bestpos | (state << 16));
       ++level;
       pos = near_pos; n = near_n;
@@ -217,25 +225,22 @@ __device__ __forceinline__ float cull_margin(float a, float b, float c, float d)
 }
 
 __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* __restrict__ aabb,
-                                 const uint32_t* __restrict__ off, uint32_t n_poses, float thr, PoseRec* __restrict__ rec,
-                                 float4* __restrict__ wbox) {
+                                 const uint32_t* __restrict__ off, const GridRec* __restrict__ grid, uint32_t n_poses,
+                                 PoseRec* __restrict__ rec, float4* __restrict__ src, float4* __restrict__ wbox) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_poses) return;
   const Aff2 a = pose_affine(pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]);
   const Aff2 inv = affine_inverse(a);
   PoseRec r;
-  r.c = a.m00; r.s = a.m10; r.tx = a.tx; r.ty = a.ty;
+  r.c = a.m00; r.s = a.m10; r.pad = 0;
   r.i00 = inv.m00; r.i01 = inv.m01; r.i10 = inv.m10; r.i11 = inv.m11; r.itx = inv.tx; r.ity = inv.ty;
   const float4 b = aabb[i];
   r.off = off[i]; r.n = off[i + 1] - off[i];
+  const GridRec g = grid[i];
+  r.gx0 = g.gx0; r.gy0 = g.gy0; r.ginv = g.ginv; r.gdim = g.gdim; r.goff = g.goff;
   if (r.n == 0) {
-    r.bx0 = r.by0 = FLT_MAX; r.bx1 = r.by1 = -FLT_MAX;
     wbox[i] = make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
   } else {
-    // exact per-point cull: a node within thr of q (as the reference computes it in float) forces q
-    // inside this box; slack thr*2^-10 + 2^-20*|coord| dominates the rounding of the subtraction.
-    const float infl = thr * 1.0009765625f + 9.5367432e-7f * fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
-    r.bx0 = b.x - infl; r.by0 = b.y - infl; r.bx1 = b.z + infl; r.by1 = b.w + infl;
     float x[4], y[4];
     affine_apply(a, b.x, b.y, &x[0], &y[0]); affine_apply(a, b.z, b.y, &x[1], &y[1]);
     affine_apply(a, b.x, b.w, &x[2], &y[2]); affine_apply(a, b.z, b.w, &x[3], &y[3]);
@@ -245,119 +250,262 @@ __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* 
     wbox[i] = make_float4(wx0 - m, wy0 - m, wx1 + m, wy1 + m);
   }
   rec[i] = r;
+  src[i] = make_float4(a.m00, a.m10, a.tx, a.ty);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: the search.
+// Occupancy bitmaps: scan j's grid has cell size >= thr * (1 + 2^-9) and every point marks the
+// 3x3 block of cells around its own cell.  A query q with an unmarked (or out-of-grid) cell has
+// no node with |node - q|^2 < thr^2 as the reference evaluates it in float: |qx - px| < thr puts
+// q's cell index within +-1 of p's (the 2^-9 slack dominates the rounding of the cell formula,
+// which is the same instruction sequence for points and queries).  Skipping the tree walk for
+// such a query is therefore exact: the walk would return FLT_MAX and change no state.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_cell(const float gx0, const float gy0, const float ginv, const uint32_t gdim, float x, float y,
+                                          uint32_t* cx, uint32_t* cy) {
+  const float fx = fmul(fsub(x, gx0), ginv), fy = fmul(fsub(y, gy0), ginv);
+  const float nx = (float)(gdim & 0xFFFFu), ny = (float)(gdim >> 16);
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < nx && fy < ny)) return false;
+  *cx = (uint32_t)fx; *cy = (uint32_t)fy;
+  return true;
+}
+
+__global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, const uint32_t* __restrict__ tile_scan,
+                                       const uint32_t* __restrict__ tile_k0, uint32_t n_tiles, const GridRec* __restrict__ grid,
+                                       uint32_t* __restrict__ occ) {
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const uint32_t i = tile_scan[tile], k = tile_k0[tile] + lane;
+  if (k >= off[i + 1] - off[i]) return;
+  const GridRec g = grid[i];
+  const float2 p = pts[off[i] + k];
+  uint32_t cx, cy;
+  if (!grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  const uint32_t nx = g.gdim & 0xFFFFu, ny = g.gdim >> 16;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = (int)cx + dx, y = (int)cy + dy;
+      if (x < 0 || y < 0 || x >= (int)nx || y >= (int)ny) continue;
+      const uint32_t bit = (uint32_t)y * nx + (uint32_t)x;
+      atomicOr(occ + g.goff + (bit >> 5), 1u << (bit & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: the search.  Persistent warps; each warp pulls 32-point source tiles from a global counter.
+//
+// Per tile, the ascending target loop is split in two decoupled stages so that the expensive part
+// (the tree walk) always runs with full lanes:
+//   stage 1 (cull)  for a block of 32 target poses: lane-per-pose world-box test -> candidate
+//                   mask; the candidates' records are staged in shared memory; for every candidate
+//                   each lane transforms its own point and tests the target's occupancy bitmap
+//                   (independent loads, pipelined) -> 32-bit "needs a walk" mask per lane;
+//   stage 2 (walk)  (lane, j) items are appended to a per-warp queue in (j, lane) order; whenever
+//                   32 items are queued, ALL 32 lanes take one item each (point and normal of the
+//                   owning lane come by shuffle), walk tree j and evaluate both gates; results
+//                   are committed in queue order: an item counts only while its owner's match
+//                   count is below the cap (exactly the reference's `continue`), so walking an
+//                   item speculatively past the cap is harmless and is simply dropped.
+// Committed matches are appended in queue order, so a tile's records come out sorted by (j, k).
 // ------------------------------------------------------------------------------------------------
 struct SearchParams {
   const float2* __restrict__ pts; const float2* __restrict__ nrm;
   const float4* __restrict__ node_pn; const int32_t* __restrict__ node_meta;
-  const PoseRec* __restrict__ rec; const float4* __restrict__ wbox; const double* __restrict__ pose;
+  const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
+  const uint32_t* __restrict__ occ;
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
   uint32_t tile_lo, tile_hi;          // tiles of the source shard
   uint32_t jmin, jmax;                // inclusive target range
   float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
   uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
-  unsigned long long* __restrict__ counters;
+  unsigned long long* __restrict__ counters;   // [6] = tile ticket
 };
 
 constexpr int kSearchThreads = 128;
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr uint32_t kQueueCap = 64;
+constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
+
+struct __align__(16) WarpShared {
+  uint4 rec[32][4];        // staged target records (PoseRec) of the current block of 32 target poses
+  uint32_t queue[kQueueCap];   // item = owner lane | j << 5
+  uint32_t cnt[32];        // matches per lane's point
+  uint32_t exec_last[32];  // j that filled the cap (kNotCapped otherwise)
+};
 
 __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const SearchParams P) {
-  extern __shared__ uint4 smem_stack[];
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t tile = P.tile_lo + blockIdx.x * (kSearchThreads / 32) + (threadIdx.x >> 5);
-  if (tile >= P.tile_hi) return;
-  uint4* const my_stack = smem_stack + threadIdx.x;
-  const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
-  const PoseRec ri = P.rec[i];
-  const uint32_t k = k0 + lane;
-  const bool valid = k < ri.n && (k % P.skip) == 0;
-  float2 p = make_float2(0.f, 0.f), nv = make_float2(0.f, 0.f);
-  if (valid) { p = P.pts[ri.off + k]; nv = P.nrm[ri.off + k]; }
-  const double theta_i = P.pose[3 * i + 2];
-  Aff2 src; src.m00 = ri.c; src.m01 = -ri.s; src.m10 = ri.s; src.m11 = ri.c; src.tx = ri.tx; src.ty = ri.ty;
+  __shared__ WarpShared s_warp[kSearchWarps];
+  WarpShared& W = s_warp[threadIdx.x >> 5];
+  const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  uint4 stack[17];                                             // walk frames (local memory; rarely touched)
+  unsigned long long n_trav = 0, n_cand = 0;
 
-  // world-frame box of this tile, inflated by thr + margin (conservative pair cull)
-  float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
-  if (valid) { float wx, wy; affine_apply(src, p.x, p.y, &wx, &wy); bx0 = bx1 = wx; by0 = by1 = wy; }
-  for (int o = 16; o; o >>= 1) {
-    bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-    bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-  }
-  {
-    const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
-    bx0 -= m; by0 -= m; bx1 += m; by1 += m;
-  }
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = P.tile_lo + (uint32_t)atomicAdd(P.counters + 6, 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= P.tile_hi) break;
+    const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
+    const uint32_t i_off = P.rec[i].off, i_n = P.rec[i].n;
+    const uint32_t k = k0 + lane;
+    const bool valid = k < i_n && (k % P.skip) == 0;
+    float2 p = make_float2(0.f, 0.f), nv = make_float2(0.f, 0.f);
+    if (valid) { p = P.pts[i_off + k]; nv = P.nrm[i_off + k]; }
+    const double theta_i = P.pose[3 * i + 2];
+    const float4 si = P.src[i];
+    Aff2 src; src.m00 = si.x; src.m01 = -si.y; src.m10 = si.y; src.m11 = si.x; src.tx = si.z; src.ty = si.w;
 
-  const uint32_t out_base = (ri.off + k0) * (uint32_t)P.cap;   // this tile's private record region
-  uint32_t wcount = 0;                                         // records written by the warp
-  int cnt = 0;                                                 // matches of this lane's point
-  bool active = valid;
-  uint32_t exec_last = 0xFFFFFFFFu;                            // j at which this lane hit the cap
-  unsigned long long n_trav = 0;
-  const bool i_in_range = i >= P.jmin && i <= P.jmax;
+    // world-frame box of this tile, inflated by thr + margin (conservative pair cull)
+    float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
+    if (valid) { float wx, wy; affine_apply(src, p.x, p.y, &wx, &wy); bx0 = bx1 = wx; by0 = by1 = wy; }
+    for (int o = 16; o; o >>= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    {
+      const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
+      bx0 -= m; by0 -= m; bx1 += m; by1 += m;
+    }
+    const uint32_t out_base = (i_off + k0) * (uint32_t)P.cap;   // this tile's private record region
+    uint32_t wcount = 0;                                        // records written by the warp
+    uint32_t qn = 0;                                            // queued items
+    bool active = valid;
+    W.cnt[lane] = 0; W.exec_last[lane] = kNotCapped;
+    __syncwarp();
 
-  if (__any_sync(0xffffffffu, active)) {
-    for (uint32_t jb = P.jmin & ~31u; jb <= P.jmax; jb += 32) {
-      const uint32_t jl = jb + lane;
-      bool hit = jl >= P.jmin && jl <= P.jmax && jl != i;
-      if (hit && !P.no_cull) {
-        const float4 wb = __ldg(P.wbox + jl);
-        hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
-      }
-      uint32_t cand = __ballot_sync(0xffffffffu, hit);
-      while (cand) {
-        const uint32_t j = jb + (__ffs(cand) - 1);
-        cand &= cand - 1;
+    // Walks one batch of up to 32 queued items (all lanes busy) and commits it in queue order.
+    auto drain = [&](uint32_t nitems) {
+      const bool item = lane < nitems;
+      const uint32_t it = item ? W.queue[lane] : 0u;
+      const uint32_t o = it & 31u, j = it >> 5;
+      // point / normal of the owning lane
+      const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
+      const float onx = __shfl_sync(0xffffffffu, nv.x, o), ony = __shfl_sync(0xffffffffu, nv.y, o);
+      bool ok = false; uint32_t tgt = 0;
+      const uint32_t cnt_o = W.cnt[o];
+      if (item && cnt_o < (uint32_t)P.cap) {
         const PoseRec rj = P.rec[j];
-        // T_ij = target^-1 * source  (Affine product, JointOptimization.cpp:304)
         Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
-        const Aff2 T = affine_mul(inv, src);
+        const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
         float qx, qy;
-        affine_apply(T, p.x, p.y, &qx, &qy);
-        const bool inside = active && (P.no_cull ? rj.n != 0 : (qx >= rj.bx0 && qx <= rj.bx1 && qy >= rj.by0 && qy <= rj.by1));
-        if (__any_sync(0xffffffffu, inside)) {
-          float best = FLT_MAX; uint32_t bpos = kNoPos;
-          TreeRef t; t.pn = P.node_pn + rj.off; t.meta = P.node_meta + rj.off;
-          if (inside) { nearest_point_normal(t, rj.n, qx, qy, P.thr, my_stack, kSearchThreads, &best, &bpos); ++n_trav; }
-          const bool found = inside && best < P.thr;   // implies bpos valid: best < FLT_MAX only via an in-radius node
-          if (__any_sync(0xffffffffu, found)) {
-            // Rotation2Df(theta_j - theta_i) * normal  (JointOptimization.cpp:604-606)
-            const float dth = (float)(P.pose[3 * j + 2] - theta_i);
-            const float sn = sinf_rn(dth), cs = cosf_rn(dth);
-            bool ok = false; uint32_t tgt = 0;
-            if (found) {
-              float rnx, rny; rot_apply(cs, sn, nv.x, nv.y, &rnx, &rny);
-              const float4 nd = __ldg(t.pn + bpos);
-              ok = fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > P.min_cos;
-              tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+        affine_apply(T, opx, opy, &qx, &qy);
+        TreeRef t; t.pn = P.node_pn + rj.off; t.meta = P.node_meta + rj.off;
+        float best; uint32_t bpos;
+        nearest_point_normal(t, rj.n, qx, qy, P.thr, stack, 1, &best, &bpos);
+        ++n_trav;
+        if (best < P.thr) {                                     // implies bpos valid: best < FLT_MAX only via an in-radius node
+          // Rotation2Df(theta_j - theta_i) * normal  (JointOptimization.cpp:604-606)
+          const float dth = (float)(P.pose[3 * j + 2] - theta_i);
+          const float sn = sinf_rn(dth), cs = cosf_rn(dth);
+          float rnx, rny; rot_apply(cs, sn, onx, ony, &rnx, &rny);
+          const float4 nd = __ldg(t.pn + bpos);
+          ok = fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > P.min_cos;
+          tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+        }
+      }
+      // commit in queue order: an item counts only while its owner is below the cap
+      const uint32_t same = __match_any_sync(0xffffffffu, item ? o : (32u + lane));
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+      const uint32_t earlier = __popc(same & okmask & lt);
+      const bool commit = ok && (cnt_o + earlier < (uint32_t)P.cap);
+      const uint32_t cm = __ballot_sync(0xffffffffu, commit);
+      if (commit) {
+        const uint32_t dst = out_base + wcount + __popc(cm & lt);
+        P.raw_j[dst] = j; P.raw_k[dst] = k0 + o; P.raw_idx[dst] = tgt;
+        atomicAdd(&W.cnt[o], 1u);
+        if (cnt_o + earlier + 1 == (uint32_t)P.cap) W.exec_last[o] = j;
+      }
+      wcount += __popc(cm);
+      __syncwarp();
+      // shift the remaining items to the front
+      const uint32_t rest = qn - nitems;
+      uint32_t a = 0, b = 0;
+      if (lane < rest) a = W.queue[nitems + lane];
+      if (lane + 32 < rest) b = W.queue[nitems + lane + 32];
+      __syncwarp();
+      if (lane < rest) W.queue[lane] = a;
+      if (lane + 32 < rest) W.queue[lane + 32] = b;
+      qn = rest;
+      active = valid && W.cnt[lane] < (uint32_t)P.cap;
+      __syncwarp();
+    };
+
+    if (__any_sync(0xffffffffu, active)) {
+      bool all_done = false;
+      for (uint32_t jb = P.jmin & ~31u; jb <= P.jmax && !all_done; jb += 32) {
+        // ---- stage 1: candidates of this block of 32 target poses ----
+        const uint32_t jl = jb + lane;
+        bool hit = jl >= P.jmin && jl <= P.jmax && jl != i;
+        if (hit && !P.no_cull) {
+          const float4 wb = __ldg(P.wbox + jl);
+          hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
+        }
+        const uint32_t cand = __ballot_sync(0xffffffffu, hit);
+        if (cand == 0) continue;
+        n_cand += __popc(cand);
+        if (hit) {
+          const uint4* r = reinterpret_cast<const uint4*>(P.rec + jl);
+          W.rec[lane][0] = __ldg(r); W.rec[lane][1] = __ldg(r + 1); W.rec[lane][2] = __ldg(r + 2); W.rec[lane][3] = __ldg(r + 3);
+        }
+        __syncwarp();
+        uint32_t need = 0;
+        for (uint32_t cm = cand; cm; cm &= cm - 1) {
+          const uint32_t c = __ffs(cm) - 1;
+          const uint4 r0 = W.rec[c][0], r1 = W.rec[c][1], r2 = W.rec[c][2];
+          bool in = active && r1.w != 0;                        // r1.w = n
+          if (in && !P.no_cull) {
+            Aff2 inv; inv.m00 = __uint_as_float(r0.x); inv.m01 = __uint_as_float(r0.y); inv.m10 = __uint_as_float(r0.z); inv.m11 = __uint_as_float(r0.w);
+            inv.tx = __uint_as_float(r1.x); inv.ty = __uint_as_float(r1.y);
+            const Aff2 T = affine_mul(inv, src);
+            float qx, qy;
+            affine_apply(T, p.x, p.y, &qx, &qy);
+            uint32_t cx, cy;
+            in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
+            if (in) {
+              const uint32_t goff = W.rec[c][3].x;
+              const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
+              in = (__ldg(P.occ + goff + (bit >> 5)) >> (bit & 31)) & 1u;
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-              const uint32_t o = out_base + wcount + __popc(m & ((1u << lane) - 1u));
-              P.raw_j[o] = j; P.raw_k[o] = k; P.raw_idx[o] = tgt;
-              if (++cnt >= P.cap) { active = false; exec_last = j; }
-            }
-            wcount += __popc(m);
+          }
+          need |= (uint32_t)in << c;
+        }
+        __syncwarp();
+        // ---- stage 2: queue (j, lane) items in order; walk whenever a full batch is available ----
+        for (uint32_t cm = cand; cm; cm &= cm - 1) {
+          const uint32_t c = __ffs(cm) - 1;
+          const bool want = ((need >> c) & 1u) && active;
+          const uint32_t m = __ballot_sync(0xffffffffu, want);
+          if (m == 0) continue;
+          if (want) W.queue[qn + __popc(m & lt)] = lane | ((jb + c) << 5);
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32) {
+            drain(32);
+            if (!__any_sync(0xffffffffu, active)) { all_done = true; break; }
           }
         }
-        if (!__any_sync(0xffffffffu, active)) goto done;
+      }
+      while (qn && !all_done) {
+        drain(qn < 32 ? qn : 32);
+        if (!__any_sync(0xffffffffu, active)) all_done = true;
       }
     }
+    if (lane == 0) P.tile_cnt[tile] = wcount;
+    // queries the reference semantics execute for this point: every j != i in range up to and
+    // including the one that filled the cap (JointOptimization.cpp:597-600)
+    unsigned long long exec = 0;
+    if (valid) {
+      const bool i_in_range = i >= P.jmin && i <= P.jmax;
+      const uint32_t el = W.exec_last[lane];
+      if (el == kNotCapped) exec = (unsigned long long)(P.jmax - P.jmin + 1) - (i_in_range ? 1 : 0);
+      else exec = (unsigned long long)(el - P.jmin + 1) - ((i_in_range && i <= el) ? 1 : 0);
+    }
+    for (int o = 16; o; o >>= 1) exec += __shfl_xor_sync(0xffffffffu, exec, o);
+    if (lane == 0) { atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 2, (unsigned long long)wcount); }
+    __syncwarp();
   }
-done:
-  if (lane == 0) P.tile_cnt[tile] = wcount;
-  // queries the reference semantics execute for this point: every j != i in range up to and
-  // including the one that filled the cap (JointOptimization.cpp:597-600)
-  unsigned long long exec = 0;
-  if (valid) {
-    if (exec_last == 0xFFFFFFFFu) exec = (unsigned long long)(P.jmax - P.jmin + 1) - (i_in_range ? 1 : 0);
-    else exec = (unsigned long long)(exec_last - P.jmin + 1) - ((i_in_range && i <= exec_last) ? 1 : 0);
-  }
-  for (int o = 16; o; o >>= 1) { exec += __shfl_xor_sync(0xffffffffu, exec, o); n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o); }
-  if (lane == 0) { atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 2, (unsigned long long)wcount); }
+  for (int o = 16; o; o >>= 1) n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
+  if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,14 +671,15 @@ __global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, u
 // (the result is never consumed downstream in the reference; kept simple).
 // ------------------------------------------------------------------------------------------------
 __global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const float4* __restrict__ node_pn,
-                                 const int32_t* __restrict__ node_meta, const PoseRec* __restrict__ rec,
+                                 const int32_t* __restrict__ node_meta, const PoseRec* __restrict__ rec, const float4* __restrict__ srcs,
                                  const double* __restrict__ pose, uint32_t i_lo, uint32_t i_hi, float thr, float min_cos,
                                  uint32_t* __restrict__ out_tk, uint32_t* __restrict__ scan_cnt) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t i = i_lo + w;
   if (i >= i_hi) return;
   const PoseRec ri = rec[i], rj = rec[i + 1];
-  Aff2 src; src.m00 = ri.c; src.m01 = -ri.s; src.m10 = ri.s; src.m11 = ri.c; src.tx = ri.tx; src.ty = ri.ty;
+  const float4 si = srcs[i];
+  Aff2 src; src.m00 = si.x; src.m01 = -si.y; src.m10 = si.y; src.m11 = si.x; src.tx = si.z; src.ty = si.w;
   Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
   const Aff2 T = affine_mul(inv, src);
   const float dth = (float)(pose[3 * i + 5] - pose[3 * i + 2]);
@@ -594,13 +743,52 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
 }
 
 namespace hitl {
+// (Re)build the per-scan occupancy bitmaps for threshold thr (cached until the scans or thr change).
+int ensure_occupancy(hitl_ctx* ctx, float thr) {
+  if (ctx->grid_valid && ctx->grid_thr == thr) return HITL_OK;
+  const uint32_t n = ctx->n_poses;
+  std::vector<GridRec> tab(n);
+  const float c0 = thr * (1.0f + 1.0f / 512.0f);
+  uint64_t words = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    GridRec g; g.gx0 = g.gy0 = 0.f; g.ginv = 0.f; g.gdim = 0; g.goff = 0;
+    if (ctx->h_off[i + 1] > ctx->h_off[i]) {
+      const float* b = &ctx->h_aabb[4 * (size_t)i];
+      const float ext = std::max(b[2] - b[0], b[3] - b[1]);
+      float c = std::max(c0, ext / 4000.0f);
+      if (!(c > 0.0f)) c = 1.0f;
+      g.gx0 = b[0] - 1.5f * c; g.gy0 = b[1] - 1.5f * c; g.ginv = 1.0f / c;
+      const uint32_t nx = (uint32_t)((b[2] - g.gx0) * g.ginv) + 4, ny = (uint32_t)((b[3] - g.gy0) * g.ginv) + 4;
+      g.gdim = nx | (ny << 16);
+      if (words >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "occupancy bitmaps exceed 2^32 words");
+      g.goff = (uint32_t)words;
+      words += ((uint64_t)nx * ny + 31) / 32;
+    }
+    tab[i] = g;
+  }
+  HITL_CUDA(ctx->d_grid.ensure(n)); HITL_CUDA(ctx->d_occ.ensure(words));
+  if (n) HITL_CUDA(cudaMemcpyAsync(ctx->d_grid.p, tab.data(), sizeof(GridRec) * n, cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_occ.p, 0, 4 * (words ? words : 1), ctx->stream));
+  if (ctx->n_tiles) {
+    const int threads = 128;
+    occupancy_build_kernel<<<(uint32_t)(((size_t)ctx->n_tiles * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        ctx->d_pts.p, ctx->d_off.p, ctx->d_tile_scan.p, ctx->d_tile_k0.p, ctx->n_tiles, ctx->d_grid.p, ctx->d_occ.p);
+    HITL_LAUNCH_CHECK("occupancy_build_kernel");
+  }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tab is a local
+  ctx->grid_valid = true; ctx->grid_thr = thr;
+  return HITL_OK;
+}
+
 int upload_poses_and_prep(hitl_ctx* ctx, const double* pose_array, float thr) {
+  int rc = ensure_occupancy(ctx, thr);
+  if (rc) return rc;
   HITL_CUDA(ctx->d_pose.ensure(3 * (size_t)ctx->n_poses));
-  HITL_CUDA(ctx->d_rec.ensure(ctx->n_poses));
+  HITL_CUDA(ctx->d_rec.ensure(ctx->n_poses)); HITL_CUDA(ctx->d_src.ensure(ctx->n_poses));
   HITL_CUDA(ctx->d_wbox.ensure(ctx->n_poses));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_pose.p, pose_array, sizeof(double) * 3 * ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
-  pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->n_poses, thr,
-                                                                        ctx->d_rec.p, ctx->d_wbox.p);
+  pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->d_grid.p, ctx->n_poses,
+                                                                        ctx->d_rec.p, ctx->d_src.p, ctx->d_wbox.p);
   HITL_LAUNCH_CHECK("pose_prep_kernel");
   return HITL_OK;
 }
@@ -653,7 +841,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
 
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pn = ctx->d_node_pn.p; P.node_meta = ctx->d_node_meta.p;
-  P.rec = ctx->d_rec.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
+  P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
   P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
   P.jmin = jmin; P.jmax = jmax; P.thr = o->point_match_threshold; P.min_cos = o->min_cosine_angle; P.cap = cap;
   P.skip = o->num_skip_readings; P.no_cull = o->disable_culling;
@@ -661,11 +849,14 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.counters = (unsigned long long*)ctx->d_counters.p;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
-  const size_t smem = (size_t)stack_levels(ctx->max_scan) * kSearchThreads * sizeof(uint4);
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (n_tiles) {
-    HITL_CUDA(cudaFuncSetAttribute(stf_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stf_search_kernel<<<(n_tiles + wpb - 1) / wpb, kSearchThreads, smem, ctx->stream>>>(P);
+    // persistent grid: one wave of CTAs (a multiple of the SM count), warps pull tiles from a ticket
+    int per_sm = 0;
+    HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stf_search_kernel, kSearchThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const uint32_t grid = std::min<uint32_t>((n_tiles + wpb - 1) / wpb, (uint32_t)(ctx->sm_count * per_sm));
+    stf_search_kernel<<<grid, kSearchThreads, 0, ctx->stream>>>(P);
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -690,7 +881,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
-  inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4];
+  inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5];
   // terminating offset of the CSR
   HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -734,7 +925,7 @@ extern "C" int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min
   HITL_CUDA(ctx->d_vo_tk.ensure(ctx->n_points)); HITL_CUDA(ctx->d_tile_cnt.ensure(std::max<size_t>(ctx->n_tiles, ctx->n_poses)));
   const int threads = 128;
   vo_search_kernel<<<((size_t)(i_hi - i_lo) * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(
-      ctx->d_pts.p, ctx->d_nrm.p, ctx->d_node_pn.p, ctx->d_node_meta.p, ctx->d_rec.p, ctx->d_pose.p, i_lo, i_hi, o->point_match_threshold,
+      ctx->d_pts.p, ctx->d_nrm.p, ctx->d_node_pn.p, ctx->d_node_meta.p, ctx->d_rec.p, ctx->d_src.p, ctx->d_pose.p, i_lo, i_hi, o->point_match_threshold,
       o->min_cosine_angle, ctx->d_vo_tk.p, ctx->d_tile_cnt.p);
   HITL_LAUNCH_CHECK("vo_search_kernel");
   // compaction on the host side of the call (result is (N-1)*P slots; the reference never consumes it)

@@ -102,7 +102,8 @@ typedef struct {
   uint64_t n_matches;     /* correspondences in kept pairs */
   uint64_t n_raw_matches; /* matches before the > min_inter_pose_correspondence filter */
   uint64_t n_queries;     /* KD queries the reference semantics execute (cap-skipped ones excluded) */
-  uint64_t n_traversals;  /* queries that actually walked a tree on the GPU (rest proven empty by AABB tests) */
+  uint64_t n_traversals;  /* queries that actually walked a tree on the GPU (rest proven empty by exact culling) */
+  uint64_t n_tile_pairs;  /* (32-point source tile, target pose) pairs that survived the world-frame box test */
   float ms_search;        /* device time of the search kernel alone (CUDA events on the ctx stream) */
   float ms_total;         /* device time of the whole call: pose prep + search + ordering/compaction */
 } hitl_stf_info;
@@ -175,7 +176,9 @@ typedef struct {
  *   stf      : r 2, J 12 = [2x3 wrt pose_index0 | 2x3 wrt pose_index1]
  *   p2l_glob : r 1, J 3 ;  p2l : r 1, J 3 */
 int hitl_eval_layout_get(hitl_ctx* ctx, hitl_eval_layout* layout);
-/* precision: 0 = FP64 (<=1e-9 rel. vs the CPU functors), 1 = FP32 arithmetic (<=1e-5). J_out may be NULL. */
+/* precision: 0 = FP64 (<=1e-9 rel. vs the CPU functors), 1 = FP32 mode (<=1e-5): projections and
+ * derivative sums in FP32; pose trigonometry and the cancelling world-frame point difference of
+ * the STF blocks stay FP64. J_out may be NULL. */
 int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision, double* r_out, double* J_out, float* ms_out);
 /* Normal-equation blocks of the whole problem at pose_array: H_diag [n_poses x 9] (J^T J, row-major
  * 3x3 per pose), g [n_poses x 3] (J^T r), H_off [n_binary_blocks x 9] (J_a^T J_b per odometry block,
