@@ -24,6 +24,7 @@ KDNODE = np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), (
 # every symbol include/hitl_gpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count",
+    "hitl_host_alloc", "hitl_host_free",
     "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_kd_query",
     "hitl_find_stf", "hitl_get_stf", "hitl_find_vo", "hitl_get_vo",
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
@@ -85,6 +86,9 @@ class HitlGpu:
         lib.hitl_launch_count.restype = C.c_uint64
         lib.hitl_launch_count.argtypes = [vp]
         lib.hitl_sm_count.argtypes = [vp]
+        lib.hitl_host_alloc.restype = vp
+        lib.hitl_host_alloc.argtypes = [C.c_size_t]
+        lib.hitl_host_free.argtypes = [vp]
         lib.hitl_set_scans.argtypes = [vp, C.c_uint32, _u32p, _f32p, _f32p]
         lib.hitl_build_kdtrees.argtypes = [vp]
         lib.hitl_set_kdtrees.argtypes = [vp, vp]
@@ -117,9 +121,30 @@ class HitlGpu:
             raise HitlError("hitl_create failed (status %d): no usable CUDA device %d — this library has no CPU fallback" % (rc, device))
         self.n_poses = 0
         self.n_points = 0
+        self._pinned = []
+
+    def pinned(self, shape, dtype):
+        """numpy array backed by page-locked host memory from hitl_host_alloc (freed by close())."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        ptr = self.lib.hitl_host_alloc(max(n, 1) * dtype.itemsize)
+        if not ptr:
+            raise HitlError("hitl_host_alloc failed")
+        self._pinned.append(ptr)
+        buf = (C.c_char * (max(n, 1) * dtype.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def pinned_copy(self, a):
+        a = np.asarray(a)
+        out = self.pinned(a.shape, a.dtype)
+        out[...] = a
+        return out
 
     def close(self):
         if getattr(self, "ctx", None):
+            for ptr in self._pinned:
+                self.lib.hitl_host_free(ptr)
+            self._pinned = []
             self.lib.hitl_destroy(self.ctx)
             self.ctx = None
 
@@ -170,23 +195,30 @@ class HitlGpu:
     def stf_opts(thr=0.15, min_cos=None, cap=6, skip=1, min_corr=10, disable_culling=0):
         return StfOpts(thr, default_min_cos() if min_cos is None else min_cos, cap, skip, min_corr, disable_culling)
 
-    def find_stf(self, poses, min_pose=0, max_pose=None, src_lo=0, src_hi=0xFFFFFFFF, opts=None, fetch=True):
+    def find_stf(self, poses, min_pose=0, max_pose=None, src_lo=0, src_hi=0xFFFFFFFF, opts=None, fetch=True, out=None):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
         if max_pose is None:
             max_pose = max(self.n_poses - 1, 0)
         opts = opts or self.stf_opts()
         info = StfInfo()
         self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
-        out = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
+        res = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
                    n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, ms_search=info.ms_search, ms_total=info.ms_total)
         if fetch:
-            out.update(self.get_stf(info.n_pairs, info.n_matches))
-        return out
+            res.update(self.get_stf(info.n_pairs, info.n_matches, out))
+        return res
 
-    def get_stf(self, n_pairs, n_matches):
-        pi, pj = np.zeros(max(n_pairs, 1), np.uint32), np.zeros(max(n_pairs, 1), np.uint32)
-        off = np.zeros(n_pairs + 1, np.uint64)
-        k, idx = np.zeros(max(n_matches, 1), np.uint32), np.zeros(max(n_matches, 1), np.uint32)
+    def get_stf(self, n_pairs, n_matches, out=None):
+        """out = (pair_i, pair_j, pair_off, k, idx) preallocated (e.g. pinned) arrays, or None."""
+        if out is not None:
+            pi, pj, off, k, idx = out
+            if len(pi) < n_pairs or len(off) < n_pairs + 1 or len(k) < n_matches or len(idx) < n_matches:
+                raise HitlError("get_stf: output buffers too small")
+            off = off[:n_pairs + 1]
+        else:
+            pi, pj = np.zeros(max(n_pairs, 1), np.uint32), np.zeros(max(n_pairs, 1), np.uint32)
+            off = np.zeros(n_pairs + 1, np.uint64)
+            k, idx = np.zeros(max(n_matches, 1), np.uint32), np.zeros(max(n_matches, 1), np.uint32)
         self._ck(self.lib.hitl_get_stf(self.ctx, pi, pj, off, k, idx))
         return dict(pair_i=pi[:n_pairs], pair_j=pj[:n_pairs], pair_off=off, k=k[:n_matches], idx=idx[:n_matches])
 
@@ -274,11 +306,17 @@ class HitlGpu:
         self._ck(self.lib.hitl_eval_layout_get(self.ctx, C.byref(L)))
         return L
 
-    def eval(self, poses, precision=0, want_jac=True, fetch=True):
+    def eval(self, poses, precision=0, want_jac=True, fetch=True, out=None):
+        """out = (r, J) preallocated float64 arrays (e.g. pinned) at least as large as the layout."""
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
         L = self.layout()
-        r = np.zeros(max(L.n_residuals, 1)) if fetch else None
-        J = np.zeros(max(L.n_jacobian, 1)) if (fetch and want_jac) else None
+        if out is not None:
+            if len(out[0]) < L.n_residuals or (want_jac and len(out[1]) < L.n_jacobian):
+                raise HitlError("eval: output buffers too small")
+            r, J = out[0][:max(L.n_residuals, 1)], (out[1][:max(L.n_jacobian, 1)] if want_jac else None)
+        else:
+            r = np.zeros(max(L.n_residuals, 1)) if fetch else None
+            J = np.zeros(max(L.n_jacobian, 1)) if (fetch and want_jac) else None
         ms = C.c_float()
         self._ck(self.lib.hitl_eval(self.ctx, poses, precision, r.ctypes.data if r is not None else None, J.ctypes.data if J is not None else None, C.byref(ms)))
         out = dict(ms=ms.value, layout=L)

@@ -46,7 +46,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
-  ctx->d_node_pn.release(); ctx->d_node_meta.release();
+  ctx->d_node_pn.release(); ctx->d_node_meta.release(); ctx->d_node_aos.release();
   ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
@@ -73,6 +73,15 @@ extern "C" void* hitl_stream(hitl_ctx* ctx) { return ctx ? (void*)ctx->stream : 
 extern "C" uint64_t hitl_launch_count(const hitl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int hitl_sm_count(const hitl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
+// Page-locked host buffers for the caller's pose / scan / result arrays: DMA at PCIe rate and truly
+// asynchronous copies.  Plain malloc'd buffers work everywhere too (staged by the driver).
+extern "C" void* hitl_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void hitl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* off, const float* pts_xy, const float* nrm_xy) {
   if (!ctx) return HITL_ERR_ARG;
   if (!off && n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null offsets");
@@ -91,8 +100,7 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   ctx->max_scan = max_scan;
   ctx->n_points = n_poses ? off[n_poses] : 0;
   if (ctx->n_points && (!pts_xy || !nrm_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null clouds");
-  ctx->h_pts.assign(pts_xy, pts_xy + 2 * ctx->n_points);
-  ctx->h_nrm.assign(nrm_xy, nrm_xy + 2 * ctx->n_points);
+  ctx->h_pts.clear(); ctx->h_nrm.clear();   // host copies are fetched lazily by hitl_build_kdtrees
   HITL_CUDA(ctx->d_off.ensure(n_poses + 1));
   HITL_CUDA(ctx->d_pts.ensure(ctx->n_points)); HITL_CUDA(ctx->d_nrm.ensure(ctx->n_points));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_off.p, ctx->h_off.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
@@ -102,6 +110,7 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   }
   // tiles: 32 consecutive points of one scan
   std::vector<uint32_t> tile_scan, tile_k0;
+  tile_scan.reserve(ctx->n_points / 32 + n_poses); tile_k0.reserve(ctx->n_points / 32 + n_poses);
   ctx->h_tile_begin.assign(n_poses + 1, 0);
   for (uint32_t i = 0; i < n_poses; ++i) {
     ctx->h_tile_begin[i] = (uint32_t)tile_scan.size();
@@ -125,20 +134,45 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   return HITL_OK;
 }
 
+namespace hitl {
+// AoS hitl_kdnode (24 B) -> the resident SoA layout {float4 p|n, int32 index|dim<<31}; validates
+// index / dim against the owning scan on the way (one thread per node, scan found by bisection).
+__global__ void split_nodes_kernel(const hitl_kdnode* __restrict__ nodes, const uint32_t* __restrict__ off, uint32_t n_poses, uint64_t m,
+                                   float4* __restrict__ pn, int32_t* __restrict__ meta, uint32_t* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const hitl_kdnode nd = nodes[i];
+  uint32_t lo = 0, hi = n_poses;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+  const uint32_t n = off[lo + 1] - off[lo];
+  if (nd.index < 0 || (uint32_t)nd.index >= n || (nd.dim != 0 && nd.dim != 1)) atomicOr(bad, 1u);
+  pn[i] = make_float4(nd.px, nd.py, nd.nx, nd.ny);
+  meta[i] = (nd.index & 0x7FFFFFFF) | (nd.dim ? (int32_t)0x80000000 : 0);
+}
+__global__ void merge_nodes_kernel(const float4* __restrict__ pn, const int32_t* __restrict__ meta, uint64_t m, hitl_kdnode* __restrict__ nodes) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float4 p = pn[i]; const int32_t w = meta[i];
+  hitl_kdnode nd; nd.px = p.x; nd.py = p.y; nd.nx = p.z; nd.ny = p.w; nd.index = w & 0x7FFFFFFF; nd.dim = (int32_t)((uint32_t)w >> 31);
+  nodes[i] = nd;
+}
+}  // namespace hitl
+
 static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
   const size_t m = ctx->n_points;
-  std::vector<float4> pn(m);
-  std::vector<int32_t> meta(m);
-  for (size_t i = 0; i < m; ++i) {
-    pn[i] = make_float4(nodes[i].px, nodes[i].py, nodes[i].nx, nodes[i].ny);
-    meta[i] = (nodes[i].index & 0x7FFFFFFF) | (nodes[i].dim ? (int32_t)0x80000000 : 0);
-  }
   HITL_CUDA(ctx->d_node_pn.ensure(m)); HITL_CUDA(ctx->d_node_meta.ensure(m));
+  ctx->have_trees = false;
   if (m) {
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_pn.p, pn.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_meta.p, meta.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(ctx->d_node_aos.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(1));
+    HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_aos.p, nodes, sizeof(hitl_kdnode) * m, cudaMemcpyHostToDevice, ctx->stream));
+    split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_node_pn.p,
+                                                                            ctx->d_node_meta.p, ctx->d_ticket.p);
+    HITL_LAUNCH_CHECK("split_nodes_kernel");
+    HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_ticket.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*(const uint32_t*)ctx->h_pinned) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
   }
-  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->have_trees = true;
   return HITL_OK;
 }
@@ -147,12 +181,6 @@ extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
   if (!ctx) return HITL_ERR_ARG;
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_kdtrees: call hitl_set_scans first");
   if (!nodes && ctx->n_points) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: null nodes");
-  for (size_t s = 0; s < ctx->n_poses; ++s) {
-    const uint32_t n = ctx->h_off[s + 1] - ctx->h_off[s];
-    for (uint32_t k = ctx->h_off[s]; k < ctx->h_off[s + 1]; ++k)
-      if (nodes[k].index < 0 || (uint32_t)nodes[k].index >= n || (nodes[k].dim != 0 && nodes[k].dim != 1))
-        return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
-  }
   return upload_trees(ctx, nodes);
 }
 
@@ -161,6 +189,14 @@ extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_build_kdtrees: call hitl_set_scans first");
   std::vector<hitl_kdnode> nodes(ctx->n_points);
   const uint32_t n = ctx->n_poses;
+  if (ctx->h_pts.size() != 2 * ctx->n_points) {   // the builder runs on the host: fetch the resident clouds
+    ctx->h_pts.resize(2 * ctx->n_points); ctx->h_nrm.resize(2 * ctx->n_points);
+    if (ctx->n_points) {
+      HITL_CUDA(cudaMemcpyAsync(ctx->h_pts.data(), ctx->d_pts.p, 8 * ctx->n_points, cudaMemcpyDeviceToHost, ctx->stream));
+      HITL_CUDA(cudaMemcpyAsync(ctx->h_nrm.data(), ctx->d_nrm.p, 8 * ctx->n_points, cudaMemcpyDeviceToHost, ctx->stream));
+      HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  }
   unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
   if (n < 64) nt = 1;
   std::vector<std::thread> th;
@@ -188,14 +224,11 @@ extern "C" int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* out) {
   const size_t m = ctx->n_points;
   if (!m) return HITL_OK;
   if (!out) return fail(ctx, HITL_ERR_ARG, "hitl_get_kdtrees: null output");
-  std::vector<float4> pn(m);
-  std::vector<int32_t> meta(m);
-  HITL_CUDA(cudaMemcpy(pn.data(), ctx->d_node_pn.p, sizeof(float4) * m, cudaMemcpyDeviceToHost));
-  HITL_CUDA(cudaMemcpy(meta.data(), ctx->d_node_meta.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < m; ++i) {
-    out[i].px = pn[i].x; out[i].py = pn[i].y; out[i].nx = pn[i].z; out[i].ny = pn[i].w;
-    out[i].index = meta[i] & 0x7FFFFFFF; out[i].dim = (int32_t)((uint32_t)meta[i] >> 31);
-  }
+  HITL_CUDA(ctx->d_node_aos.ensure(m));
+  merge_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pn.p, ctx->d_node_meta.p, m, ctx->d_node_aos.p);
+  HITL_LAUNCH_CHECK("merge_nodes_kernel");
+  HITL_CUDA(cudaMemcpyAsync(out, ctx->d_node_aos.p, sizeof(hitl_kdnode) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }
 

@@ -67,6 +67,7 @@ struct hitl_ctx {
   bool have_trees = false;
   hitl::DevBuf<float4> d_node_pn;        // px, py, nx, ny   (preorder, concatenated)
   hitl::DevBuf<int32_t> d_node_meta;     // index | dim << 31
+  hitl::DevBuf<hitl_kdnode> d_node_aos;  // staging for hitl_set_kdtrees / hitl_get_kdtrees (AoS <-> SoA on the device)
 
   // ---- per-call pose tables ----
   hitl::DevBuf<double> d_pose;           // x, y, theta

@@ -55,6 +55,10 @@ void* hitl_stream(hitl_ctx* ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t hitl_launch_count(const hitl_ctx* ctx);
 int hitl_sm_count(const hitl_ctx* ctx);
+/* Page-locked host memory for the caller's buffers (optional: any host pointer is accepted by every
+ * call; pinned ones move at PCIe rate).  NULL on failure. */
+void* hitl_host_alloc(size_t bytes);
+void hitl_host_free(void* p);
 
 /* ---- scans and KD-trees ----------------------------------------------------------------- */
 /* Robot-frame point and normal clouds of all poses, concatenated; scan i owns
