@@ -4,4 +4,4 @@ The product is the C-ABI library lib/libhitl_gpu.so (include/hitl_gpu.h) plus th
 mirror lib/libhitl_host.so; this Python package is only plumbing (ctypes bindings, the
 synthetic-trajectory generator, the in-tree build).  No CPU fallback exists.
 """
-from .capi import HitlGpu, HostLib, HitlError, default_min_cos, ABI_SYMBOLS, KDNODE  # noqa: F401
+from .capi import HitlGpu, HostLib, HostSession, HitlError, default_min_cos, ABI_SYMBOLS, KDNODE  # noqa: F401

@@ -439,3 +439,215 @@ class HostLib:
                                                  np.ascontiguousarray(nrm_world, np.float32).reshape(-1))
         if rc:
             raise IOError("cannot write " + path)
+
+    # ---- device-free pieces of the C++ mirror ----
+    def _bind_mirror(self):
+        lib = self.lib
+        if getattr(lib, "_mirror_bound", False):
+            return
+        vp = C.c_void_p
+        lib.hitl_host_seg_fit_em.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p]
+        lib.hitl_host_odometry_consts.argtypes = [_f32p, C.c_uint32, _f32p]
+        lib.hitl_host_human_targets.argtypes = [_f32p, C.c_uint32, C.c_uint32, _i32p, _f32p, _f64p]
+        lib.hitl_host_solver_selftest.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f64p]
+        lib.hitl_host_load_log.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, _i32p, _i32p, _i32p, _f32p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        lib.hitl_host_save_log.argtypes = [C.c_char_p, C.c_uint32, _i32p, _i32p, _i32p, _f32p]
+        lib.hitl_host_session_create.restype = vp
+        lib.hitl_host_session_create.argtypes = [vp]
+        lib.hitl_host_session_destroy.argtypes = [vp]
+        lib.hitl_host_session_error.restype = C.c_char_p
+        lib.hitl_host_session_error.argtypes = [vp]
+        lib.hitl_host_session_set_map.argtypes = [vp, C.c_uint32, _f32p, _u32p, _f32p, _f32p]
+        lib.hitl_host_session_set_poses.argtypes = [vp, _f32p]
+        lib.hitl_host_session_get_poses.argtypes = [vp, _f32p, _f64p]
+        lib.hitl_host_session_world_transform.argtypes = [vp, C.c_int]
+        lib.hitl_host_session_em_run.argtypes = [vp, C.c_int, _f32p, _i32p]
+        lib.hitl_host_session_em_poses.argtypes = [vp, _i32p, _i32p]
+        lib.hitl_host_session_add_constraints_from_em.argtypes = [vp, C.POINTER(C.c_uint32)]
+        lib.hitl_host_session_add_constraints.argtypes = [vp, C.c_uint32, _i32p, _f32p]
+        lib.hitl_host_session_clear_constraints.argtypes = [vp]
+        lib.hitl_host_session_solver_options.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.hitl_host_session_joint_opt_run.argtypes = [vp, C.c_int, _f64p]
+        lib.hitl_host_session_solve.argtypes = [vp, C.c_int, _f64p]
+        lib.hitl_host_session_copy_params.argtypes = [vp]
+        lib.hitl_host_session_find_stf.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p]
+        lib.hitl_host_session_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p]
+        lib.hitl_host_session_gradient.argtypes = [vp, C.c_uint64, _f64p, C.POINTER(C.c_uint64), _u64p]
+        lib.hitl_host_session_evaluate_block.argtypes = [vp, C.c_int, C.c_uint64, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _f64p, _f64p, _f64p, C.POINTER(C.c_uint64)]
+        lib._mirror_bound = True
+
+    def seg_fit_em(self, p1, p2, data):
+        """EMInput::SegFitEM of the C++ mirror (host only)."""
+        self._bind_mirror()
+        data = np.ascontiguousarray(data, np.float64).reshape(-1)
+        out = np.zeros(4, np.float32)
+        rc = self.lib.hitl_host_seg_fit_em(np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64), data if len(data) else np.zeros(2), len(data) // 2, out)
+        if rc:
+            raise HitlError("hitl_host_seg_fit_em failed")
+        return out.reshape(2, 2)
+
+    def odometry_consts(self, poses_f32):
+        """PoseConstraint constants as JointOpt::AddOdometryConstraints of the C++ mirror computes them."""
+        self._bind_mirror()
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+        n = len(p) // 3
+        out = np.zeros(9 * max(n - 1, 1), np.float32)
+        self.lib.hitl_host_odometry_consts(p, n, out)
+        return out[:9 * max(n - 1, 0)].reshape(-1, 9)
+
+    def human_targets(self, poses_f32, ids3, deltas4):
+        self._bind_mirror()
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+        ids3 = np.ascontiguousarray(ids3, np.int32).reshape(-1)
+        out = np.zeros(4 * (len(ids3) // 3))
+        self.lib.hitl_host_human_targets(p, len(p) // 3, len(ids3) // 3, ids3, np.ascontiguousarray(deltas4, np.float32).reshape(-1), out)
+        return out.reshape(-1, 4)
+
+    def solver_selftest(self, x0, max_iterations=200, hold_x1=False, force_cg=False):
+        self._bind_mirror()
+        x = np.ascontiguousarray(x0, np.float64).copy()
+        out = np.zeros(4)
+        self.lib.hitl_host_solver_selftest(x, max_iterations, int(hold_x1), int(force_cg), out)
+        return x, dict(initial_cost=out[0], final_cost=out[1], iterations=int(out[2]), termination=int(out[3]))
+
+    def save_log(self, path, entries):
+        """entries: list of (type, undone, [[x, y], ...]) in the reference's session-log format."""
+        self._bind_mirror()
+        types = np.array([e[0] for e in entries], np.int32)
+        undone = np.array([e[1] for e in entries], np.int32)
+        npts = np.array([len(e[2]) for e in entries], np.int32)
+        pts = np.concatenate([np.asarray(e[2], np.float32).reshape(-1, 2) for e in entries]).reshape(-1) if entries else np.zeros(2, np.float32)
+        z = np.zeros(1, np.int32)
+        if self.lib.hitl_host_save_log(path.encode(), len(entries), types if len(entries) else z, undone if len(entries) else z, npts if len(entries) else z,
+                                       np.ascontiguousarray(pts, np.float32)):
+            raise IOError("cannot write " + path)
+
+    def load_log(self, path, cap_entries=4096):
+        self._bind_mirror()
+        types, undone, npts = np.zeros(cap_entries, np.int32), np.zeros(cap_entries, np.int32), np.zeros(cap_entries, np.int32)
+        pts = np.zeros(2 * 8 * cap_entries, np.float32)
+        ne, npnt = C.c_uint32(), C.c_uint32()
+        rc = self.lib.hitl_host_load_log(path.encode(), cap_entries, 8 * cap_entries, types, undone, npts, pts, C.byref(ne), C.byref(npnt))
+        if rc:
+            raise IOError("cannot read session log %s (status %d)" % (path, rc))
+        out, o = [], 0
+        for e in range(ne.value):
+            m = int(npts[e])
+            out.append((int(types[e]), int(undone[e]), pts[2 * o:2 * (o + m)].reshape(-1, 2).copy()))
+            o += m
+        return out
+
+
+class HostSession:
+    """JointOpt + EMInput of the C++ host mirror on one GPU context (host_capi.cpp)."""
+
+    def __init__(self, gpu, host=None):
+        self.gpu = gpu
+        self.host = host or HostLib()
+        self.host._bind_mirror()
+        self.lib = self.host.lib
+        self.s = self.lib.hitl_host_session_create(gpu.ctx)
+        if not self.s:
+            raise HitlError("hitl_host_session_create failed")
+        self.n_poses = 0
+
+    def close(self):
+        if getattr(self, "s", None):
+            self.lib.hitl_host_session_destroy(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HitlError("host session: " + self.lib.hitl_host_session_error(self.s).decode())
+
+    def set_map(self, poses, offsets, pts, nrm):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1)
+        self.n_poses = len(poses) // 3
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        self.n_points = int(self.offsets[-1])
+        self._ck(self.lib.hitl_host_session_set_map(self.s, self.n_poses, poses, self.offsets, np.ascontiguousarray(pts, np.float32).reshape(-1),
+                                                    np.ascontiguousarray(nrm, np.float32).reshape(-1)))
+        self.gpu.n_poses, self.gpu.n_points, self.gpu.offsets = self.n_poses, self.n_points, self.offsets
+
+    def set_poses(self, poses):
+        self._ck(self.lib.hitl_host_session_set_poses(self.s, np.ascontiguousarray(poses, np.float32).reshape(-1)))
+
+    def poses(self):
+        p, a = np.zeros(3 * self.n_poses, np.float32), np.zeros(3 * self.n_poses)
+        self.lib.hitl_host_session_get_poses(self.s, p, a)
+        return p.reshape(-1, 3), a.reshape(-1, 3)
+
+    def world_transform(self, keep_host_copy=False):
+        self._ck(self.lib.hitl_host_session_world_transform(self.s, int(keep_host_copy)))
+
+    def em_run(self, correction_type, selected_points):
+        sel = np.ascontiguousarray(selected_points, np.float32).reshape(-1).copy()
+        info = np.zeros(6, np.int32)
+        self._ck(self.lib.hitl_host_session_em_run(self.s, int(correction_type), sel, info))
+        cor, anc = np.zeros(max(int(info[0]), 1), np.int32), np.zeros(max(int(info[1]), 1), np.int32)
+        self.lib.hitl_host_session_em_poses(self.s, cor, anc)
+        return dict(segs=sel.reshape(4, 2), corrected=cor[:info[0]].copy(), anchor=anc[:info[1]].copy(), backprop=(int(info[2]), int(info[3])),
+                    rounds=(int(info[4]), int(info[5])))
+
+    def add_constraints_from_em(self):
+        n = C.c_uint32()
+        self._ck(self.lib.hitl_host_session_add_constraints_from_em(self.s, C.byref(n)))
+        return n.value
+
+    def add_constraints(self, ids3, deltas4):
+        ids3 = np.ascontiguousarray(ids3, np.int32).reshape(-1)
+        self._ck(self.lib.hitl_host_session_add_constraints(self.s, len(ids3) // 3, ids3, np.ascontiguousarray(deltas4, np.float32).reshape(-1)))
+
+    def clear_constraints(self):
+        self.lib.hitl_host_session_clear_constraints(self.s)
+
+    def solver_options(self, which=0, max_iterations=-1, function_tolerance=-1.0, gradient_tolerance=-1.0, parameter_tolerance=-1.0, precision=-1, verbose=-1):
+        self.lib.hitl_host_session_solver_options(self.s, which, max_iterations, function_tolerance, gradient_tolerance, parameter_tolerance, precision, verbose)
+
+    @staticmethod
+    def _summary(v):
+        return dict(initial_cost=v[0], final_cost=v[1], successful_steps=int(v[2]), unsuccessful_steps=int(v[3]), termination=int(v[4]), num_hc_residuals=int(v[5]))
+
+    def joint_opt_run(self, post=False):
+        v = np.zeros(6)
+        self._ck(self.lib.hitl_host_session_joint_opt_run(self.s, int(post), v))
+        return self._summary(v)
+
+    def solve(self, mode=0):
+        v = np.zeros(6)
+        self._ck(self.lib.hitl_host_session_solve(self.s, mode, v))
+        return self._summary(v)
+
+    def copy_params(self):
+        self.lib.hitl_host_session_copy_params(self.s)
+
+    def find_stf(self, min_pose=0, max_pose=None):
+        c = np.zeros(3, np.uint64)
+        self._ck(self.lib.hitl_host_session_find_stf(self.s, min_pose, self.n_poses - 1 if max_pose is None else max_pose, c))
+        npair, nm = int(c[0]), int(c[1])
+        pi, pj, off = np.zeros(max(npair, 1), np.uint32), np.zeros(max(npair, 1), np.uint32), np.zeros(npair + 1, np.uint64)
+        k, idx = np.zeros(max(nm, 1), np.uint32), np.zeros(max(nm, 1), np.uint32)
+        self.lib.hitl_host_session_get_stf(self.s, pi, pj, off, k, idx)
+        return dict(pair_i=pi[:npair], pair_j=pj[:npair], pair_off=off, k=k[:nm], idx=idx[:nm], n_queries=int(c[2]), n_pairs=npair, n_matches=nm)
+
+    def gradient(self):
+        n, dims = C.c_uint64(), np.zeros(3, np.uint64)
+        g = np.zeros(3 * self.n_poses)
+        self.lib.hitl_host_session_gradient(self.s, len(g), g, C.byref(n), dims)
+        return g[:n.value], tuple(int(x) for x in dims)
+
+    def evaluate_block(self, block, with_stf=False, pose_array=None):
+        """One residual block through CostFunction::Evaluate, the way Ceres calls it."""
+        nres, nblk, total = C.c_int32(), C.c_int32(), C.c_uint64()
+        r, j0, j1 = np.zeros(3), np.zeros(9), np.zeros(9)
+        pa = np.ascontiguousarray(pose_array, np.float64).reshape(-1) if pose_array is not None else None
+        self._ck(self.lib.hitl_host_session_evaluate_block(self.s, int(with_stf), block, pa.ctypes.data if pa is not None else None, C.byref(nres), C.byref(nblk),
+                                                           r, j0, j1, C.byref(total)))
+        k = nres.value
+        return r[:k].copy(), j0[:3 * k].reshape(k, 3).copy(), (j1[:3 * k].reshape(k, 3).copy() if nblk.value == 2 else None), total.value

@@ -1,0 +1,76 @@
+// gpu_cost_functions.cpp — the batch behind the GPU-backed cost blocks (see gpu_cost_functions.h).
+#include "gpu_cost_functions.h"
+
+#include <string.h>
+
+namespace hitl {
+
+// doubles per block in hitl_eval's output (include/hitl_gpu.h "r_out / J_out layout")
+static const int kResPerBlock[GpuBlockEvaluator::kNumKinds] = {3, 3, 2, 1, 1};
+static const int kJacPerBlock[GpuBlockEvaluator::kNumKinds] = {18, 9, 12, 3, 3};
+
+GpuBlockEvaluator::GpuBlockEvaluator(hitl_ctx* ctx, const double* pose_array, size_t n_poses, int precision)
+    : ctx_(ctx), pose_array_(pose_array), n_poses_(n_poses), precision_(precision) {
+  memset(&layout_, 0, sizeof(layout_));
+  memset(r_off_, 0, sizeof(r_off_)); memset(j_off_, 0, sizeof(j_off_));
+}
+
+bool GpuBlockEvaluator::Refresh() {
+  if (hitl_eval_layout_get(ctx_, &layout_) != HITL_OK) { ok_ = false; error_ = "hitl_eval_layout_get failed"; return false; }
+  const uint64_t counts[kNumKinds] = {layout_.n_odometry, layout_.n_human, layout_.n_stf, layout_.n_p2l_glob, layout_.n_p2l};
+  uint64_t ro = 0, jo = 0;
+  for (int k = 0; k < kNumKinds; ++k) { r_off_[k] = ro; j_off_[k] = jo; ro += counts[k] * kResPerBlock[k]; jo += counts[k] * kJacPerBlock[k]; }
+  r_.assign(layout_.n_residuals ? layout_.n_residuals : 1, 0.0);
+  J_.assign(layout_.n_jacobian ? layout_.n_jacobian : 1, 0.0);
+  valid_ = false; ok_ = true;
+  return true;
+}
+
+bool GpuBlockEvaluator::run_batch(bool want_jac) {
+  const int rc = hitl_eval(ctx_, pose_array_, precision_, r_.data(), want_jac ? J_.data() : nullptr, &last_ms_);
+  ++batches_;
+  if (rc != HITL_OK) { ok_ = false; valid_ = false; error_ = hitl_last_error(ctx_); return false; }
+  snapshot_.assign(pose_array_, pose_array_ + 3 * n_poses_);
+  valid_ = true; have_jac_ = want_jac; ok_ = true;
+  return true;
+}
+
+void GpuBlockEvaluator::PrepareForEvaluation(bool evaluate_jacobians, bool new_evaluation_point) {
+  std::lock_guard<std::mutex> lock(mu_);
+  if (!new_evaluation_point && valid_ && (have_jac_ || !evaluate_jacobians) &&
+      memcmp(snapshot_.data(), pose_array_, sizeof(double) * 3 * n_poses_) == 0) return;   // same point, already staged
+  run_batch(evaluate_jacobians);
+}
+
+bool GpuBlockEvaluator::matches(int pose, const double* x) const {
+  return pose < 0 || !x || memcmp(&snapshot_[3 * (size_t)pose], x, 3 * sizeof(double)) == 0;
+}
+
+bool GpuBlockEvaluator::Fetch(Kind kind, uint64_t block, int pose0, const double* x0, int pose1, const double* x1, int nres, double* residuals,
+                              double* jac0, double* jac1) {
+  const bool want_jac = jac0 || jac1;
+  if (!valid_ || (want_jac && !have_jac_) || !matches(pose0, x0) || !matches(pose1, x1)) {
+    // No callback ran for this point (a solver without EvaluationCallback support, or a direct
+    // Evaluate call): the caller's pose array is the point — batch it now, once, for all blocks.
+    std::lock_guard<std::mutex> lock(mu_);
+    if (!valid_ || (want_jac && !have_jac_) || !matches(pose0, x0) || !matches(pose1, x1)) {
+      if (!run_batch(true)) return false;
+      if (!matches(pose0, x0) || !matches(pose1, x1)) {
+        ok_ = false; error_ = "GPU cost function evaluated at a point that is not in the bound pose array (solver without EvaluationCallback?)";
+        return false;
+      }
+    }
+  }
+  if (!ok_) return false;
+  const double* r = &r_[r_off_[kind] + block * kResPerBlock[kind]];
+  for (int q = 0; q < nres; ++q) residuals[q] = r[q];
+  if (want_jac) {
+    const double* J = &J_[j_off_[kind] + block * kJacPerBlock[kind]];
+    const int half = kJacPerBlock[kind] / 2;   // binary kinds: [rows x 3 wrt pose0 | rows x 3 wrt pose1]
+    if (jac0) memcpy(jac0, J, sizeof(double) * 3 * nres);
+    if (jac1) memcpy(jac1, J + half, sizeof(double) * 3 * nres);
+  }
+  return true;
+}
+
+}  // namespace hitl

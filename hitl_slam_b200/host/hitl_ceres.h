@@ -22,6 +22,7 @@ namespace hitl { namespace ceres = ::ceres; }
 #include <stddef.h>
 #include <stdint.h>
 #include <memory>
+#include <type_traits>
 #include <string>
 #include <unordered_map>
 #include <vector>

@@ -36,3 +36,25 @@ def concat_stf(parts):
         base += int(o[-1])
     return dict(pair_i=pair_i, pair_j=pair_j, pair_off=np.concatenate(offs), k=k, idx=idx,
                 n_queries=sum(int(p.get("n_queries", 0)) for p in parts))
+
+
+def gather_stf(local, group=None):
+    """All ranks: exchange the per-shard CSR results (host objects) and return the full
+    reference-ordered result.  Not on the per-iteration path — the search result normally
+    stays on the GPU that produced it; this is for callers that want the whole list on the host."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    keep = {k: local[k] for k in ("pair_i", "pair_j", "pair_off", "k", "idx")}
+    keep["n_queries"] = int(local.get("n_queries", 0))
+    dist.all_gather_object(parts, keep, group=group)
+    return concat_stf(parts)
+
+
+def allreduce_normal_equations(packed, group=None):
+    """The one collective of a Gauss-Newton / LM iteration: sum the packed per-pose blocks
+    [H_diag (N x 9) | g (N x 3) | cost] over the ranks, in place (NCCL on the device buffer
+    returned by hitl_normal_eq_device, gloo on host tensors in the CPU tests)."""
+    import torch.distributed as dist
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed

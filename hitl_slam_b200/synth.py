@@ -211,3 +211,65 @@ def make_strokes(g, kind="colinear"):
     a = [(x0, cor + 0.01), (x1, cor + 0.012)]
     b = [(x0 + 0.05, cor - 0.005), (x1 - 0.1, cor - 0.004)]
     return np.array(a + b, np.float32)
+
+
+def world_points(g):
+    """World-frame points (float64, for picking strokes only) and the pose index of every point."""
+    poses = g["poses"].astype(np.float64)
+    off = g["offsets"].astype(np.int64)
+    pid = np.repeat(np.arange(len(poses)), np.diff(off))
+    c, s = np.cos(poses[pid, 2]), np.sin(poses[pid, 2])
+    p = g["pts"].astype(np.float64)
+    return np.stack([c * p[:, 0] - s * p[:, 1] + poses[pid, 0], s * p[:, 0] + c * p[:, 1] + poses[pid, 1]], 1), pid
+
+
+def _observers(w, pid, a, b, thr=0.03, min_obs=5):
+    """Poses with more than min_obs points inside the pill around segment a-b (EstablishObservationSets, approximately)."""
+    d = b - a
+    t = np.clip(((w - a) @ d) / (d @ d), 0.0, 1.0)
+    dist = np.linalg.norm(w - (a + t[:, None] * d), axis=1)
+    ids, cnt = np.unique(pid[dist < thr], return_counts=True)
+    return ids[cnt > min_obs]
+
+
+def pick_strokes(g, min_sep=0.07, max_sep=0.6, window=2.0):
+    """Two strokes a human would draw on the displayed map to close a loop: the same physical wall as
+    it appears on a LATE visit (feature A, first stroke) and on an EARLY visit (feature B), picked where
+    odometry drift separates the two appearances by more than the EM pill and the poses observing the
+    two strokes are cleanly ordered in time.  Returns float32 [4, 2] (a0, a1, b0, b1) or raises if the
+    map has no usable revisit."""
+    cfg = g["config"]
+    cor, bw, bh = cfg["cor"], cfg["bw"], cfg["bh"]
+    w, pid = world_points(g)
+    for j in range(cfg["by"]):
+        for i in range(cfg["bx"]):
+            for ywall in (cor + j * (bh + cor), cor + j * (bh + cor) + bh):
+                wx0, wx1 = cor + i * (bw + cor) + 0.1 * bw, cor + i * (bw + cor) + 0.9 * bw
+                for x0 in np.arange(wx0, wx1 - window + 1e-9, 0.5):
+                    x1 = x0 + window
+                    sel = (np.abs(w[:, 1] - ywall) < 0.3) & (w[:, 0] > x0) & (w[:, 0] < x1)
+                    ids = np.unique(pid[sel])
+                    if len(ids) < 12:
+                        continue
+                    passes = [p for p in np.split(ids, np.where(np.diff(ids) > 25)[0] + 1) if len(p) >= 6]
+                    fits = []
+                    for p in passes:
+                        m = sel & np.isin(pid, p)
+                        fits.append(np.polyfit(w[m, 0], w[m, 1], 1) if m.sum() >= 40 else None)
+                    for late in range(len(passes) - 1, 0, -1):
+                        for early in range(late):
+                            if fits[late] is None or fits[early] is None:
+                                continue
+                            (k1, c1), (k0, c0) = fits[late], fits[early]
+                            xm = 0.5 * (x0 + x1)
+                            sep = abs((k1 * xm + c1) - (k0 * xm + c0))
+                            if not (min_sep <= sep <= max_sep):
+                                continue
+                            A = np.array([[x0, k1 * x0 + c1], [x1, k1 * x1 + c1]])
+                            B = np.array([[x0, k0 * x0 + c0], [x1, k0 * x1 + c0]])
+                            fa, fb = _observers(w, pid, A[0], A[1]), _observers(w, pid, B[0], B[1])
+                            both = np.intersect1d(fa, fb)
+                            fa, fb = np.setdiff1d(fa, both), np.setdiff1d(fb, both)
+                            if len(fa) >= 3 and len(fb) >= 3 and fa.min() > fb.max() + 5:
+                                return np.concatenate([A, B]).astype(np.float32)
+    raise RuntimeError("no revisited wall with enough drift in this map")

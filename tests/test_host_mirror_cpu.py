@@ -1,0 +1,164 @@
+"""CPU-side checks of the C++ host mirror (no GPU): the Ceres-shaped solver, SegFitEM, the float
+problem-building arithmetic, the session-log format, exported symbols, and the 2-rank sharding
+logic over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_host_library_exports_every_declared_symbol(host):
+    hdr = open(os.path.join(ROOT, "hitl_slam_b200", "host", "hitl_host.h")).read()
+    names = sorted(set(re.findall(r"\b(hitl_host_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(host.lib, n)]
+    assert not missing, missing
+
+
+def test_solver_powell_dense_cg_and_constant_block(host):
+    x0 = [3.0, -1.0, 0.0, 1.0]
+    for cg in (False, True):
+        x, s = host.solver_selftest(x0, force_cg=cg)
+        assert s["initial_cost"] == pytest.approx(107.5)
+        assert s["final_cost"] < 1e-15 and np.abs(x).max() < 1e-4 and s["termination"] == 0
+    x, s = host.solver_selftest(x0, hold_x1=True)
+    assert x[0] == 3.0                                  # SetParameterBlockConstant honoured
+    assert s["final_cost"] < s["initial_cost"]
+    # cross-check the constrained minimum with scipy
+    from scipy.optimize import least_squares
+
+    def f(v):
+        x1, (x2, x3, x4) = 3.0, v
+        return [x1 + 10 * x2, np.sqrt(5) * (x3 - x4), (x2 - 2 * x3) ** 2, np.sqrt(10) * (x1 - x4) ** 2]
+    ref = least_squares(f, x0[1:], xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    assert np.abs(x[1:] - ref.x).max() < 1e-6
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_seg_fit_em_matches_oracle(host, oracle, seed):
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0.02, 1.5)
+    n = int(rng.integers(8, 400))
+    t = rng.uniform(-0.2, 2.2, n)
+    data = np.stack([1 + t * np.cos(ang), 2 + t * np.sin(ang)], 1) + rng.normal(size=(n, 2)) * 0.01
+    p1 = np.array([1.0, 2.0]) + rng.normal(size=2) * 0.03
+    p2 = np.array([1 + 2 * np.cos(ang), 2 + 2 * np.sin(ang)]) + rng.normal(size=2) * 0.03
+    a, b = host.seg_fit_em(p1, p2, data), oracle.seg_fit(p1, p2, data)
+    assert np.abs(a - b).max() <= 1e-5                  # two LM implementations, float endpoints: tolerance-level
+    assert np.allclose((a[0] + a[1]) / 2, (p1 + p2) / 2, atol=1e-6)   # midpoint and length are kept
+    assert np.linalg.norm(a[0] - a[1]) == pytest.approx(np.linalg.norm(p1 - p2), abs=1e-5)
+
+
+def test_seg_fit_em_without_inliers_keeps_the_initial_angle(host, oracle):
+    p1, p2 = np.array([0.0, 0.0]), np.array([1.0, -1.0])   # negative slope: acos(|dx|/h) drops the sign (reference quirk)
+    a, b = host.seg_fit_em(p1, p2, np.zeros((0, 2))), oracle.seg_fit(p1, p2, np.zeros((0, 2)))
+    assert np.array_equal(a, b)
+    assert a[0, 1] > a[1, 1]                                # endpoints come back on the positive-slope diagonal
+
+
+def test_odometry_constants_bit_exact(host, oracle, maps):
+    g = maps("small")
+    poses = g["poses"].copy()
+    poses[7] = poses[6]                                   # a pair that did not move: the heading-axes branch
+    poses[7, 2] += np.float32(0.3)
+    poses[20, 2] = np.float32(3.1)
+    poses[21, 2] = np.float32(-3.1)                       # wrap-around of the measured rotation
+    assert np.array_equal(host.odometry_consts(poses), oracle.odometry_consts(poses))
+
+
+def test_human_targets_bit_exact(host, oracle, maps):
+    g = maps("small")
+    n = len(g["poses"])
+    rng = np.random.default_rng(5)
+    m = 64
+    ids = np.stack([rng.choice([2, 4, 5, 6], m), rng.integers(0, n, m), rng.integers(0, n, m)], 1).astype(np.int32)
+    deltas = rng.normal(size=(m, 4)).astype(np.float32) * 2
+    blk_i, blk_d = oracle.human_blocks(g["poses"], ids, deltas)
+    tg = host.human_targets(g["poses"], ids, deltas)
+    assert np.array_equal(blk_i[:, 0], ids[:, 0]) and np.array_equal(blk_i[:, 1], ids[:, 1])
+    assert np.array_equal(tg, blk_d)
+
+
+def test_session_log_round_trip_and_format(host, tmp_path):
+    entries = [(4, 0, [[1.23456, 2.0], [3.0, 4.00004], [5.5, 6.5], [7.25, -8.125]]),
+               (5, 1, [[0, 0], [1, 1], [2, 2], [3, 3]]),
+               (1, 0, [[9, 9], [8, 8]]),
+               (3, 0, [[i, -i] for i in range(8)]),
+               (2, 0, [[0.1, 0.2], [0.3, 0.4], [0.5, 0.6], [0.7, 0.8]])]
+    p = str(tmp_path / "session_logged.log")
+    host.save_log(p, entries)
+    text = open(p).read().split("\n")
+    assert text[0] == "5 " and text[1] == "4, 0" and text[2] == "1.2346, 2.0000"   # "%d \n", "%d, %d\n", "%.4f, %.4f\n"
+    back = host.load_log(p)
+    assert [(t, u, len(x)) for t, u, x in back] == [(4, 0, 4), (5, 1, 4), (1, 0, 2), (3, 0, 8), (2, 0, 4)]
+    assert np.allclose(back[0][2], np.round(np.array(entries[0][2]), 4), atol=1e-6)
+    with pytest.raises(IOError):
+        host.load_log(str(tmp_path / "missing.log"))
+
+
+def test_mirror_refuses_to_run_without_a_context(host):
+    host._bind_mirror()
+    assert not host.lib.hitl_host_session_create(None)     # no ctx, no session: there is no CPU implementation of the stages
+
+
+# ---- 2-rank sharding over gloo (host logic of the multi-GPU path; the oracle stands in for the GPUs) ----
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hitl_slam_b200 import synth
+from hitl_slam_b200.sharding import shard_ranges, gather_stf, allreduce_normal_equations
+from oracle.pyoracle import Oracle
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = synth.generate("tiny")
+poses = g["poses"].astype(np.float64)
+n = len(poses)
+orc = Oracle()
+S = orc.scans(g["offsets"], g["pts"], g["nrm"])
+lo, hi = shard_ranges(g["offsets"], world)[rank]
+local = S.find_stf(poses, src_lo=lo, src_hi=hi)
+full = gather_stf(local)
+x = poses + np.random.default_rng(0).normal(size=poses.shape) * 0.01
+
+def packed(corr):
+    r, J = S.eval_stf(x, corr)
+    H, gv = np.zeros((n, 3, 3)), np.zeros((n, 3))
+    for b in range(len(corr["pair_i"])):
+        for side, p in ((0, int(corr["pair_i"][b])), (1, int(corr["pair_j"][b]))):
+            H[p] += J[b, side].T @ J[b, side]
+            gv[p] += J[b, side].T @ r[b]
+    return np.concatenate([H.reshape(-1), gv.reshape(-1), [0.5 * (r ** 2).sum()]])
+
+t = torch.from_numpy(packed(local))
+allreduce_normal_equations(t)
+if rank == 0:
+    ref = S.find_stf(poses)
+    for k in ("pair_i", "pair_j", "pair_off", "k", "idx"):
+        assert np.array_equal(np.asarray(full[k]), np.asarray(ref[k])), k
+    assert full["n_queries"] == ref["n_queries"]
+    want = packed(ref)
+    assert np.abs(t.numpy() - want).max() <= 1e-9 * np.abs(want).max()
+    assert len(ref["pair_i"]) > 0 and hi > lo
+    print("SHARDING_OK", len(ref["pair_i"]), world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", HITL_SYNTH_DIR=str(tmp_path))
+    port = 29500 + (os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "SHARDING_OK" in r.stdout
