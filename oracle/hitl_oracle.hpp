@@ -3,12 +3,23 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // build, load or call anything in oracle/.  The product (hitl_slam_b200/) never does.
 //
-// PARITY STATUS: the reference (ut-amrl/hitl-slam) ships no tests, golden vectors or
-// fixtures for this path and cannot be compiled here (Eigen, Ceres, glog, ROS absent), so
-// this restatement is "parity unpinned" EXCEPT for the KD-tree: oracle/Makefile compiles the
-// reference's own perception_tools/kdtree.cpp against a minimal Eigen/glog shim
-// (oracle/shim/) into oracle/_ref/libkdtree_ref.so and tests/test_oracle_kdtree_ref.py checks
-// this file's tree build and both searches against it node for node / query for query.
+// PARITY STATUS: the reference (ut-amrl/hitl-slam) ships no tests, golden vectors or fixtures
+// for this path, and its translation units cannot be built here as a whole (Eigen, Ceres, glog,
+// ROS absent).  What CAN be compiled from the reference's own sources, where they lie, is
+// (oracle/Makefile `ref`, outputs in oracle/_ref/, never copied into this repo):
+//   * perception_tools/kdtree.cpp            against oracle/shim   -> libkdtree_ref.so
+//       pins the tree build and all three queries of this file, node for node / query for query
+//       (tests/test_cpu_oracle.py::test_oracle_tree_matches_reference_kdtree);
+//   * human_in_the_loop_slam/residual_functors.h + shared/math/eigen_helper.h (header-only code)
+//     against oracle/shim2 (Eigen 2-vector / 2x2 / Rotation2D, ceres::Jet, glog stand-ins) -> libfunctors_ref.so
+//       pins PointToPointGlob, PoseConstraint, the four human-imposed functors, both point-to-line
+//       functors (values and auto-diff Jacobians, <= 1e-12) and DistanceToLineSegment (identical
+//       inlier sets) (tests/test_oracle_functors_ref.py).
+// Still "parity unpinned" (restated from the cited lines only, nothing of the reference runs beside
+// them): the FindSTFCorrespondences / FindVisualOdometryCorrespondences loops and
+// RelativePoseTransform (JointOptimization.cpp — needs Ceres/CImg/ROS headers), EMInput's
+// distToLineSeg / EstablishObservationSets / OrderAndFilterUserInput / SegFitEM (EMinput.cpp — Ceres),
+// and the problem-building constants of AddOdometryConstraints / AddHumanConstraints.
 //
 // Every function cites the reference lines it follows (paths relative to
 // /root/reference/HitL-SLAM/src/).  Float expressions follow Eigen 3's evaluation order as

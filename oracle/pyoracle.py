@@ -319,3 +319,59 @@ class RefKDTree:
         idx = np.zeros(max(self.n, 1), np.int32)
         n = self.lib.ref_kd_radius(self.h, qx, qy, thr, idx, self.n)
         return idx[:n].copy()
+
+
+class RefFunctors:
+    """The reference's own residual functors and DistanceToLineSegment (oracle/_ref/libfunctors_ref.so:
+    residual_functors.h + eigen_helper.h compiled where they lie against oracle/shim2), when built."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libfunctors_ref.so"))
+
+    def __init__(self):
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libfunctors_ref.so"))
+        lib.ref_p2p_glob.argtypes = [C.c_uint32, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
+        lib.ref_pose_constraint.argtypes = [_f32p, _f64p, _f64p, _f64p, _f64p, _f64p]
+        lib.ref_human.restype = C.c_int
+        lib.ref_human.argtypes = [C.c_int, _f64p, _f64p, _f64p, _f64p]
+        lib.ref_p2l_glob.argtypes = [C.c_uint32, _f32p, _f32p, _f32p, _u8p, C.c_float, C.c_float, _f64p, _f64p, _f64p]
+        lib.ref_p2l.argtypes = [_f32p, _f32p, C.c_float, C.c_int, C.c_float, C.c_float, _f64p, _f64p, _f64p]
+        lib.ref_distance_to_line_segment.argtypes = [C.c_uint32, _f32p, _f32p, _f32p, _f32p]
+
+    @staticmethod
+    def _f32(a):
+        return np.ascontiguousarray(a, np.float32).reshape(-1)
+
+    def p2p_glob(self, p0, p1, n0, n1, std_dev, corr, x0, x1):
+        r, j0, j1, rp = np.zeros(2), np.zeros(6), np.zeros(6), np.zeros(2)
+        self.lib.ref_p2p_glob(len(self._f32(p0)) // 2, self._f32(p0), self._f32(p1), self._f32(n0), self._f32(n1), std_dev, corr,
+                              np.ascontiguousarray(x0, np.float64), np.ascontiguousarray(x1, np.float64), r, j0, j1, rp)
+        return r, j0.reshape(2, 3), j1.reshape(2, 3), rp
+
+    def pose_constraint(self, consts9, x0, x1):
+        r, j0, j1 = np.zeros(3), np.zeros(9), np.zeros(9)
+        self.lib.ref_pose_constraint(self._f32(consts9), np.ascontiguousarray(x0, np.float64), np.ascontiguousarray(x1, np.float64), r, j0, j1)
+        return r, j0.reshape(3, 3), j1.reshape(3, 3)
+
+    def human(self, ctype, targets4, x):
+        r, j = np.zeros(3), np.zeros(9)
+        k = self.lib.ref_human(int(ctype), np.ascontiguousarray(targets4, np.float64), np.ascontiguousarray(x, np.float64), r, j)
+        return r[:k], j[:3 * k].reshape(k, 3)
+
+    def p2l_glob(self, pts, ln, lo, valid, std_dev, corr, x):
+        r, j = np.zeros(1), np.zeros(3)
+        self.lib.ref_p2l_glob(len(self._f32(pts)) // 2, self._f32(pts), self._f32(ln), self._f32(lo), np.ascontiguousarray(valid, np.uint8), std_dev, corr,
+                              np.ascontiguousarray(x, np.float64), r, j)
+        return r[0], j
+
+    def p2l(self, pt, ln, lo, valid, std_dev, corr, x):
+        r, j = np.zeros(1), np.zeros(3)
+        self.lib.ref_p2l(self._f32(pt), self._f32(ln), float(lo), int(valid), std_dev, corr, np.ascontiguousarray(x, np.float64), r, j)
+        return r[0], j
+
+    def distance_to_line_segment(self, p0, p1, pts):
+        pts = self._f32(pts)
+        out = np.zeros(len(pts) // 2, np.float32)
+        self.lib.ref_distance_to_line_segment(len(out), self._f32(p0), self._f32(p1), pts, out)
+        return out
