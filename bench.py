@@ -79,17 +79,23 @@ def workload(name, n_poses=None, beams=None):
     cache = os.path.join(os.environ.get("HITL_SYNTH_DIR", "/tmp/hitl_synth"), "%s_%s_%s.npz" % (name, n_poses, beams))
     if os.path.exists(cache):
         z = np.load(cache)
-        return {k: z[k] for k in z.files}
+        out = {k: z[k] for k in z.files if k != "config_json"}
+        if "config_json" in z.files:
+            out["config"] = json.loads(str(z["config_json"]))
+            return out
     g = synth.generate(name, n_poses=n_poses, beams=beams)
     out = {k: g[k] for k in ("poses", "offsets", "pts", "nrm")}
     os.makedirs(os.path.dirname(cache), exist_ok=True)
-    np.savez(cache, **out)
+    np.savez(cache, config_json=np.array(json.dumps(g["config"])), **out)
+    out["config"] = g["config"]
     return out
 
 
 def cpu_sample(g, seconds=15.0, threads=None):
-    """Oracle port timed on the host cores on a bounded sample: chunks of source poses spread over the
-    trajectory against ALL target poses (search) + evaluation of the blocks they produce."""
+    """Oracle port timed on the host cores on a bounded sample of the same workload: chunks of consecutive
+    source poses, visited in a strided order so that a partial sample is spread over the whole trajectory,
+    each searched against ALL target poses (OpenMP over the chunk's source poses, as JointOptimization.cpp:575)
+    and followed by the evaluation of the blocks it produced; stops at the time budget."""
     from oracle.pyoracle import Oracle
     if threads:
         os.environ["OMP_NUM_THREADS"] = str(threads)
@@ -99,37 +105,28 @@ def cpu_sample(g, seconds=15.0, threads=None):
     n = len(poses)
     cores = orc.num_threads()
     chunk = max(cores, 8)
-    starts = list(range(0, max(n - chunk, 1), max((n - chunk) // 7, 1)))[:8] if n > 2 * chunk else [0]
-    evals, t_used, n_src, t_search, t_eval, queries, matches = 0, 0.0, 0, 0.0, 0.0, 0, 0
-    rounds = 0
-    while t_used < seconds and rounds < 64:
-        progressed = False
-        for s in starts:
-            lo = s + rounds * chunk
-            hi = min(lo + chunk, n)
-            if lo >= n or (rounds and lo >= s + max((n - chunk) // 7, 1)):
-                continue
-            t0 = time.perf_counter()
-            r = S.find_stf(poses, src_lo=lo, src_hi=hi)
-            t1 = time.perf_counter()
-            S.eval_stf(poses, r, STD_DEV, CORR, want_jac=True, parallel=True)
-            t2 = time.perf_counter()
-            t_search += t1 - t0
-            t_eval += t2 - t1
-            queries += r["n_queries"]
-            matches += len(r["k"])
-            n_src += hi - lo
-            t_used = t_search + t_eval
-            progressed = True
-            if t_used >= seconds:
-                break
-        if not progressed:
-            break
-        rounds += 1
-    evals = queries + matches
-    return {"value": evals / t_used / 1e6 if t_used else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d source poses (8 chunks spread over the trajectory) vs all %d targets: %d queries + %d Jacobian evals in %.1f s "
-                      "(search %.1f s, eval %.1f s); oracle -O3 -march=native -fopenmp" % (n_src, n, n, queries, matches, t_used, t_search, t_eval),
+    n_chunks = (n + chunk - 1) // chunk
+    stride = next(s for s in (61, 37, 17, 7, 3, 1) if n_chunks % s != 0 or s == 1)   # coprime stride -> a permutation of the chunks
+    t_search = t_eval = 0.0
+    queries = matches = n_src = done = 0
+    while done < n_chunks and t_search + t_eval < seconds:
+        c = (done * stride) % n_chunks
+        lo, hi = c * chunk, min((c + 1) * chunk, n)
+        t0 = time.perf_counter()
+        r = S.find_stf(poses, src_lo=lo, src_hi=hi)
+        t1 = time.perf_counter()
+        S.eval_stf(poses, r, STD_DEV, CORR, want_jac=True, parallel=True)
+        t2 = time.perf_counter()
+        t_search += t1 - t0
+        t_eval += t2 - t1
+        queries += r["n_queries"]
+        matches += len(r["k"])
+        n_src += hi - lo
+        done += 1
+    t_used = t_search + t_eval
+    return {"value": (queries + matches) / t_used / 1e6 if t_used else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d source poses (%d-pose chunks spread over the trajectory) vs all %d targets: %d queries + %d Jacobian evals in %.1f s "
+                      "(search %.1f s, eval %.1f s); oracle -O3 -march=native -fopenmp" % (n_src, n, chunk, n, queries, matches, t_used, t_search, t_eval),
             "search_Mq_per_s": queries / t_search / 1e6 if t_search else 0.0, "eval_Mm_per_s": matches / t_eval / 1e6 if t_eval else 0.0}
 
 
@@ -182,6 +179,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +196,7 @@ def main():
     import torch
     import torch.distributed as dist
     from hitl_slam_b200 import HitlGpu, capi
-    from hitl_slam_b200.sharding import shard_ranges
+    from hitl_slam_b200.sharding import shard_ranges, shard_ranges_by_work
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -239,8 +237,14 @@ def main():
                 dist.all_reduce(neq_dev[1])
         return info, ne
 
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
         step()
+        if world > 1 and w < 2:
+            # re-cut the source ranges at equal MEASURED work (SM cycles per source pose of the search that
+            # just ran, summed over the ranks); setup-time exchange, not on the per-step data path
+            work = torch.from_numpy(gpu.stf_work().astype(np.int64)).cuda()
+            dist.all_reduce(work)
+            lo, hi = shard_ranges_by_work(work.cpu().numpy(), world)[rank]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -283,8 +287,15 @@ def main():
     my_q, my_m = infos[-1][0]["n_queries"], infos[-1][0]["n_raw_matches"]
     alg_bytes = 40.0 * my_q + 8.0 * my_m
     achieved = alg_bytes / (ms_search * 1e-3) / 1e9
+    traffic = None
+    try:                                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["stf_search_kernel"]
+        if args.workload == "c2" and world == 1:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"kernel": "stf_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "ms_kernel": ms_search, "share_of_step": ms_search / ms_per_step,
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "ms_kernel": ms_search, "share_of_step": ms_search / ms_per_step,
                 "note": "algorithmic bytes = 40 B per query + 8 B per match (pair-tile model, SURVEY.md 8d); the kernel proves most queries empty "
                         "with AABB tests and reuses one source tile across all targets, so it can exceed the stream model"}
 
@@ -327,6 +338,14 @@ def main():
            "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
            "timing": "host wall clock around the synchronous C-ABI calls (every call ends with a stream sync), pinned host buffers, max over ranks"}
 
+    # ---- correction latency (second half of the BASELINE metric): one human correction on this map ----
+    correction = None
+    if rank == 0 and not args.no_correction:
+        try:
+            correction = correction_latency(gpu, g, cpu=(world == 1 and not args.no_cpu))
+        except Exception as e:            # the headline line must still print
+            correction = {"error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rebuild_fast_oracle_native()
@@ -334,17 +353,61 @@ def main():
 
     if rank == 0:
         cfg = config_of(args, g)
-        cfg.update({"parallelism": "source-pose shards x%d (scans+trees replicated), 1 all-reduce of packed J^TJ/J^Tr per step" % world if world > 1 else "single GPU",
+        cfg.update({"parallelism": "source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 all-reduce of packed J^TJ/J^Tr per step" % world if world > 1 else "single GPU",
                     "kdtree_build_host_s": t_build})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction,
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
                            "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos]))}}
         print(json.dumps(line))
     gpu.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def correction_latency(gpu, g, cpu=True, reps=5):
+    """One human correction (colinear, two strokes picked on a revisited wall) through the C++ host mirror:
+    world-frame clouds -> EMInput::Run (E-steps on the GPU, M-steps on the host, observation sets on the GPU,
+    ordering on the host) -> constraint targets -> problem build + one batched evaluation of every block
+    (residuals + Jacobians back on the host).  Wall clock around synchronous calls; the host LM solve is
+    reported separately (latency excludes the host linear solve)."""
+    from hitl_slam_b200 import HostSession, synth
+    strokes = synth.pick_strokes(g)
+    sess = HostSession(gpu)
+    sess.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    lat, solve, em = [], [], None
+    for it in range(reps + 1):
+        sess.clear_constraints()
+        sess.set_poses(g["poses"])
+        t0 = time.perf_counter()
+        sess.world_transform(keep_host_copy=False)
+        em = sess.em_run(4, strokes)
+        nc = sess.add_constraints_from_em()
+        sess.evaluate_block(0, with_stf=False)
+        t1 = time.perf_counter()
+        summ = sess.joint_opt_run(post=False)
+        t2 = time.perf_counter()
+        if it:                              # first pass warms allocations
+            lat.append((t1 - t0) * 1e3)
+            solve.append((t2 - t1) * 1e3)
+    out = {"ms": float(np.median(lat)), "ms_min": float(np.min(lat)), "ms_with_host_solve": float(np.median(lat) + np.median(solve)), "unit": "ms per correction",
+           "what": "world transform + EM (E-steps/assignment on GPU, M-step/ordering on host) + constraint targets + build & one batched evaluation of all odometry+human blocks",
+           "em_rounds": list(em["rounds"]), "corrected_poses": int(len(em["corrected"])), "anchor_poses": int(len(em["anchor"])), "human_blocks": int(nc),
+           "solver_steps": int(summ["successful_steps"] + summ["unsuccessful_steps"]), "n_points": int(g["offsets"][-1])}
+    sess.close()
+    if cpu:
+        from oracle.pyoracle import Oracle
+        orc = Oracle(fast=True)
+        S = orc.scans(g["offsets"], g["pts"], g["nrm"], build_trees=False)
+        t0 = time.perf_counter()
+        world = S.world_transform(g["poses"])
+        ref = orc.em_run(g["offsets"], world, strokes)
+        consts = orc.odometry_consts(g["poses"])
+        orc.eval_odometry(consts, g["poses"].astype(np.float64))
+        out["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        out["cpu_what"] = "oracle port, 1 thread as in the reference: world transform + EM (same strokes, %d rounds) + odometry block evaluation" % ref["rounds"]
+    return out
 
 
 def tensor_from_ptr(ptr, n_doubles, device_index):

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count",
     "hitl_host_alloc", "hitl_host_free",
     "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_kd_query",
-    "hitl_find_stf", "hitl_get_stf", "hitl_find_vo", "hitl_get_vo",
+    "hitl_find_stf", "hitl_get_stf", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
@@ -96,6 +96,7 @@ class HitlGpu:
         lib.hitl_kd_query.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
         lib.hitl_find_stf.argtypes = [vp, _f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(StfOpts), C.POINTER(StfInfo)]
         lib.hitl_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p]
+        lib.hitl_get_stf_work.argtypes = [vp, _u64p]
         lib.hitl_find_vo.argtypes = [vp, _f64p, C.c_int32, C.c_int32, C.POINTER(StfOpts), C.POINTER(C.c_uint64)]
         lib.hitl_get_vo.argtypes = [vp, _u32p, _u32p, _u32p]
         lib.hitl_world_transform.argtypes = [vp, _f32p, vp]
@@ -221,6 +222,12 @@ class HitlGpu:
             k, idx = np.zeros(max(n_matches, 1), np.uint32), np.zeros(max(n_matches, 1), np.uint32)
         self._ck(self.lib.hitl_get_stf(self.ctx, pi, pj, off, k, idx))
         return dict(pair_i=pi[:n_pairs], pair_j=pj[:n_pairs], pair_off=off, k=k[:n_matches], idx=idx[:n_matches])
+
+    def stf_work(self):
+        """SM cycles the last find_stf spent per source pose (shard-balancing feedback)."""
+        w = np.zeros(max(self.n_poses, 1), np.uint64)
+        self._ck(self.lib.hitl_get_stf_work(self.ctx, w))
+        return w[:self.n_poses]
 
     def find_vo(self, poses, min_pose=0, max_pose=None, opts=None):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1)

@@ -50,7 +50,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
-  ctx->d_pose_cnt.release(); ctx->d_counters.release();
+  ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();
   ctx->d_pair_i.release(); ctx->d_pair_j.release(); ctx->d_k.release(); ctx->d_idx.release(); ctx->d_pair_off.release();
   ctx->d_vo_sp.release(); ctx->d_vo_sk.release(); ctx->d_vo_tk.release();
   ctx->d_world.release(); ctx->d_poses_f.release(); ctx->d_em_pose.release(); ctx->d_em_idx.release(); ctx->d_em_xy.release();

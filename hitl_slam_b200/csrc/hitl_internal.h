@@ -86,6 +86,7 @@ struct hitl_ctx {
   hitl::DevBuf<uint32_t> d_srt_j, d_srt_k, d_srt_idx;               // per-pose sorted staging
   hitl::DevBuf<uint8_t> d_srt_flag;                                 // bit0 keep, bit1 first-of-pair
   hitl::DevBuf<uint64_t> d_pose_cnt;     // per pose: kept matches, kept pairs (2 per pose) then scanned
+  hitl::DevBuf<uint64_t> d_pose_work;    // SM cycles per source pose of the last search (shard balancing)
   hitl::DevBuf<uint64_t> d_counters;     // [0] n_queries [1] n_traversals [2] raw matches [3] pairs [4] matches
   hitl::DevBuf<uint32_t> d_pair_i, d_pair_j, d_k, d_idx;
   hitl::DevBuf<uint64_t> d_pair_off;

@@ -319,6 +319,7 @@ struct SearchParams {
   float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
   uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
   unsigned long long* __restrict__ counters;   // [6] = tile ticket
+  unsigned long long* __restrict__ pose_work;  // SM cycles spent on the tiles of each source pose (load-balancing feedback)
 };
 
 constexpr int kSearchThreads = 128;
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
     if (lane == 0) tile = P.tile_lo + (uint32_t)atomicAdd(P.counters + 6, 1ull);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= P.tile_hi) break;
+    const long long t_begin = clock64();
     const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
     const uint32_t i_off = P.rec[i].off, i_n = P.rec[i].n;
     const uint32_t k = k0 + lane;
@@ -501,7 +503,10 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
       else exec = (unsigned long long)(el - P.jmin + 1) - ((i_in_range && i <= el) ? 1 : 0);
     }
     for (int o = 16; o; o >>= 1) exec += __shfl_xor_sync(0xffffffffu, exec, o);
-    if (lane == 0) { atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 2, (unsigned long long)wcount); }
+    if (lane == 0) {
+      atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 2, (unsigned long long)wcount);
+      atomicAdd(P.pose_work + i, (unsigned long long)(clock64() - t_begin));
+    }
     __syncwarp();
   }
   for (int o = 16; o; o >>= 1) n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
@@ -830,12 +835,14 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(ctx->d_tile_cnt.ensure(ctx->n_tiles));
   HITL_CUDA(ctx->d_counters.ensure(8));
   HITL_CUDA(ctx->d_pose_cnt.ensure(2 * (size_t)n + 2));
+  HITL_CUDA(ctx->d_pose_work.ensure(n));
   HITL_CUDA(ctx->d_k.ensure(rec_cap)); HITL_CUDA(ctx->d_idx.ensure(rec_cap));
   const size_t pair_cap = rec_cap / (o->min_inter_pose_correspondence + 1) + 1;
   HITL_CUDA(ctx->d_pair_i.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_j.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_off.ensure(pair_cap + 1));
 
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_pose_work.p, 0, sizeof(uint64_t) * n, ctx->stream));
   int rc = upload_poses_and_prep(ctx, pose_array, o->point_match_threshold);
   if (rc) return rc;
 
@@ -847,6 +854,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.skip = o->num_skip_readings; P.no_cull = o->disable_culling;
   P.raw_j = ctx->d_raw_j.p; P.raw_k = ctx->d_raw_k.p; P.raw_idx = ctx->d_raw_idx.p; P.tile_cnt = ctx->d_tile_cnt.p;
   P.counters = (unsigned long long*)ctx->d_counters.p;
+  P.pose_work = (unsigned long long*)ctx->d_pose_work.p;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -906,6 +914,15 @@ extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, u
     if (k) HITL_CUDA(cudaMemcpyAsync(k, ctx->d_k.p, 4 * nm, cudaMemcpyDeviceToHost, ctx->stream));
     if (idx) HITL_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, 4 * nm, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+extern "C" int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_stf || !ctx->d_pose_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf_work: no search result");
+  if (!work_per_pose && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_get_stf_work: null output");
+  if (ctx->n_poses) HITL_CUDA(cudaMemcpyAsync(work_per_pose, ctx->d_pose_work.p, 8 * (size_t)ctx->n_poses, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }

@@ -173,11 +173,15 @@ bool dense_cholesky_solve(std::vector<double>& A, int n, std::vector<double>& b)
   return true;
 }
 
-// Small dense SPD solve used by the block-Jacobi preconditioner (in place on copies).
-bool small_solve(std::vector<double> A, int n, double* b) {
-  std::vector<double> rhs(b, b + n);
-  if (!dense_cholesky_solve(A, n, rhs)) return false;
-  memcpy(b, rhs.data(), sizeof(double) * n);
+// Inverse of a small SPD block (Cholesky based), for the block-Jacobi preconditioner.
+bool small_inverse(const std::vector<double>& A, int n, std::vector<double>* inv) {
+  inv->assign((size_t)n * n, 0.0);
+  for (int c = 0; c < n; ++c) {
+    std::vector<double> M = A, e(n, 0.0);
+    e[c] = 1.0;
+    if (!dense_cholesky_solve(M, n, e)) return false;
+    for (int r = 0; r < n; ++r) (*inv)[(size_t)r * n + c] = e[r];
+  }
   return true;
 }
 
@@ -185,13 +189,19 @@ bool pcg_solve(const BlockSparse& H, const std::vector<double>& lm_diag2, const 
   const int n = H.n;
   x->assign(n, 0.0);
   std::vector<double> r = rhs, z(n), p(n), Ap(n);
+  // block-Jacobi: (D_a + lm_a)^-1 per parameter block, factored once per linear solve
+  std::vector<std::vector<double>> Dinv(H.diag.size());
+  for (size_t a = 0; a < H.diag.size(); ++a) {
+    const int s = H.size[a], o = H.off[a];
+    std::vector<double> D = H.diag[a];
+    for (int i = 0; i < s; ++i) D[i * s + i] += lm_diag2[o + i];
+    if (!small_inverse(D, s, &Dinv[a])) return false;
+  }
   auto precond = [&](const std::vector<double>& v, std::vector<double>* out) -> bool {
-    *out = v;
     for (size_t a = 0; a < H.diag.size(); ++a) {
       const int s = H.size[a], o = H.off[a];
-      std::vector<double> D = H.diag[a];
-      for (int i = 0; i < s; ++i) D[i * s + i] += lm_diag2[o + i];
-      if (!small_solve(D, s, &(*out)[o])) return false;
+      const double* M = Dinv[a].data();
+      for (int i = 0; i < s; ++i) { double t = 0; for (int j = 0; j < s; ++j) t += M[i * s + j] * v[o + j]; (*out)[o + i] = t; }
     }
     return true;
   };

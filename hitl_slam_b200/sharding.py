@@ -23,6 +23,22 @@ def shard_ranges(offsets, world_size):
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
+def shard_ranges_by_work(work, world_size):
+    """Contiguous [lo, hi) source-pose ranges cut at equal measured work (hitl_get_stf_work summed
+    over the ranks of the previous search).  Falls back to equal pose counts when no work is known."""
+    work = np.asarray(work, np.float64)
+    n = len(work)
+    if n == 0 or work.sum() <= 0:
+        return [(n * r // world_size, n * (r + 1) // world_size) for r in range(world_size)]
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    bounds = [0]
+    for r in range(1, world_size):
+        b = int(np.searchsorted(cum, cum[-1] * r / world_size, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
 def concat_stf(parts):
     """Concatenate per-shard CSR results (in rank order) into the full reference-ordered result."""
     pair_i = np.concatenate([p["pair_i"] for p in parts]) if parts else np.zeros(0, np.uint32)

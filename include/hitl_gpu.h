@@ -123,6 +123,11 @@ int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t min_pose, ui
  * pair_i/pair_j [n_pairs], pair_off [n_pairs+1], k/idx [n_matches]. */
 int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx);
 
+/* Load-balancing feedback: SM cycles the last hitl_find_stf spent on each source pose (0 outside the
+ * searched source range).  work_per_pose holds n_poses entries.  Multi-GPU callers sum these over the
+ * ranks and cut the next call's source ranges at equal work (hitl_slam_b200/sharding.py). */
+int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose);
+
 /* Consecutive-pose matching with the Euclidean query. n_out = number of correspondences. */
 int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min_pose, int32_t max_pose,
                  const hitl_stf_opts* opts, uint64_t* n_out);

@@ -151,6 +151,19 @@ def test_find_stf_shards_concatenate(gpu, oracle, maps):
         assert cat["n_queries"] == ref["n_queries"]
 
 
+def test_find_stf_work_feedback_covers_exactly_the_searched_sources(gpu, maps):
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    gpu.find_stf(poses, src_lo=40, src_hi=100, fetch=False)
+    w = gpu.stf_work()
+    assert len(w) == len(poses) and (w[:40] == 0).all() and (w[100:] == 0).all() and (w[40:100] > 0).all()
+    from hitl_slam_b200.sharding import shard_ranges_by_work
+    gpu.find_stf(poses, fetch=False)
+    cuts = shard_ranges_by_work(gpu.stf_work(), 4)
+    assert cuts[0][0] == 0 and cuts[-1][1] == len(poses) and all(hi > lo for lo, hi in cuts)
+
+
 def test_find_stf_ragged_and_empty_scans(gpu, oracle):
     rng = np.random.default_rng(11)
     # a strip of overlapping random scans, some empty, sizes from 1 to 300

@@ -162,3 +162,15 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                         "--master-port", str(port), str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "SHARDING_OK" in r.stdout
+
+
+def test_shard_ranges_by_work():
+    from hitl_slam_b200.sharding import shard_ranges_by_work
+    work = np.array([0, 0, 10, 10, 10, 10, 0, 40, 0, 0], np.uint64)
+    r = shard_ranges_by_work(work, 2)
+    assert r[0][0] == 0 and r[-1][1] == len(work) and r[0][1] == r[1][0]
+    assert abs(int(work[r[0][0]:r[0][1]].sum()) - int(work[r[1][0]:r[1][1]].sum())) <= 40
+    r4 = shard_ranges_by_work(work, 4)
+    assert [a for a, _ in r4][0] == 0 and all(r4[i][1] == r4[i + 1][0] for i in range(3)) and r4[-1][1] == len(work)
+    assert shard_ranges_by_work(np.zeros(8), 4) == [(0, 2), (2, 4), (4, 6), (6, 8)]      # nothing measured yet: equal pose counts
+    assert shard_ranges_by_work(np.zeros(0), 2) == [(0, 0), (0, 0)]
