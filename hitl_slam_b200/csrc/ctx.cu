@@ -46,7 +46,8 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
-  ctx->d_node_pn.release(); ctx->d_node_meta.release(); ctx->d_node_aos.release();
+  ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
+  ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release();
   ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
@@ -118,6 +119,8 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
     for (uint32_t k0 = 0; k0 < n; k0 += 32) { tile_scan.push_back(i); tile_k0.push_back(k0); }
   }
   ctx->h_tile_begin[n_poses] = (uint32_t)tile_scan.size();
+  // a previous tile order stays a valid hint only if the tiling is unchanged (same scans re-uploaded)
+  if ((uint32_t)tile_scan.size() != ctx->n_tiles) { ctx->order_valid = false; ctx->iota_valid = false; }
   ctx->n_tiles = (uint32_t)tile_scan.size();
   HITL_CUDA(ctx->d_tile_scan.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_k0.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_begin.ensure(n_poses + 1));
   if (ctx->n_tiles) {
@@ -138,7 +141,7 @@ namespace hitl {
 // AoS hitl_kdnode (24 B) -> the resident SoA layout {float4 p|n, int32 index|dim<<31}; validates
 // index / dim against the owning scan on the way (one thread per node, scan found by bisection).
 __global__ void split_nodes_kernel(const hitl_kdnode* __restrict__ nodes, const uint32_t* __restrict__ off, uint32_t n_poses, uint64_t m,
-                                   float4* __restrict__ pn, int32_t* __restrict__ meta, uint32_t* __restrict__ bad) {
+                                   float4* __restrict__ pm, float2* __restrict__ nn, uint32_t* __restrict__ bad) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const hitl_kdnode nd = nodes[i];
@@ -146,28 +149,28 @@ __global__ void split_nodes_kernel(const hitl_kdnode* __restrict__ nodes, const 
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
   const uint32_t n = off[lo + 1] - off[lo];
   if (nd.index < 0 || (uint32_t)nd.index >= n || (nd.dim != 0 && nd.dim != 1)) atomicOr(bad, 1u);
-  pn[i] = make_float4(nd.px, nd.py, nd.nx, nd.ny);
-  meta[i] = (nd.index & 0x7FFFFFFF) | (nd.dim ? (int32_t)0x80000000 : 0);
+  pm[i] = make_float4(nd.px, nd.py, __uint_as_float(((uint32_t)nd.index & 0x7FFFFFFFu) | (nd.dim ? 0x80000000u : 0u)), 0.0f);
+  nn[i] = make_float2(nd.nx, nd.ny);
 }
-__global__ void merge_nodes_kernel(const float4* __restrict__ pn, const int32_t* __restrict__ meta, uint64_t m, hitl_kdnode* __restrict__ nodes) {
+__global__ void merge_nodes_kernel(const float4* __restrict__ pm, const float2* __restrict__ nn, uint64_t m, hitl_kdnode* __restrict__ nodes) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float4 p = pn[i]; const int32_t w = meta[i];
-  hitl_kdnode nd; nd.px = p.x; nd.py = p.y; nd.nx = p.z; nd.ny = p.w; nd.index = w & 0x7FFFFFFF; nd.dim = (int32_t)((uint32_t)w >> 31);
+  const float4 p = pm[i]; const float2 v = nn[i]; const uint32_t w = __float_as_uint(p.z);
+  hitl_kdnode nd; nd.px = p.x; nd.py = p.y; nd.nx = v.x; nd.ny = v.y; nd.index = (int32_t)(w & 0x7FFFFFFFu); nd.dim = (int32_t)(w >> 31);
   nodes[i] = nd;
 }
 }  // namespace hitl
 
 static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
   const size_t m = ctx->n_points;
-  HITL_CUDA(ctx->d_node_pn.ensure(m)); HITL_CUDA(ctx->d_node_meta.ensure(m));
+  HITL_CUDA(ctx->d_node_pm.ensure(m)); HITL_CUDA(ctx->d_node_nn.ensure(m));
   ctx->have_trees = false;
   if (m) {
     HITL_CUDA(ctx->d_node_aos.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(1));
     HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
     HITL_CUDA(cudaMemcpyAsync(ctx->d_node_aos.p, nodes, sizeof(hitl_kdnode) * m, cudaMemcpyHostToDevice, ctx->stream));
-    split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_node_pn.p,
-                                                                            ctx->d_node_meta.p, ctx->d_ticket.p);
+    split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_node_pm.p,
+                                                                            ctx->d_node_nn.p, ctx->d_ticket.p);
     HITL_LAUNCH_CHECK("split_nodes_kernel");
     HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_ticket.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     HITL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -225,7 +228,7 @@ extern "C" int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* out) {
   if (!m) return HITL_OK;
   if (!out) return fail(ctx, HITL_ERR_ARG, "hitl_get_kdtrees: null output");
   HITL_CUDA(ctx->d_node_aos.ensure(m));
-  merge_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pn.p, ctx->d_node_meta.p, m, ctx->d_node_aos.p);
+  merge_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pm.p, ctx->d_node_nn.p, m, ctx->d_node_aos.p);
   HITL_LAUNCH_CHECK("merge_nodes_kernel");
   HITL_CUDA(cudaMemcpyAsync(out, ctx->d_node_aos.p, sizeof(hitl_kdnode) * m, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -62,11 +62,16 @@ struct hitl_ctx {
   uint32_t n_tiles = 0;
   hitl::DevBuf<uint32_t> d_tile_scan, d_tile_k0, d_tile_begin;   // tile -> scan, first point; scan -> first tile
   std::vector<uint32_t> h_tile_begin;
+  // scheduling hint of the search: tiles sorted by the cycles the previous call spent on them
+  hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys;
+  hitl::DevBuf<uint8_t> d_sort_tmp;
+  bool order_valid = false, iota_valid = false;
+  uint32_t order_lo = 0, order_hi = 0;
 
   // ---- trees ----
   bool have_trees = false;
-  hitl::DevBuf<float4> d_node_pn;        // px, py, nx, ny   (preorder, concatenated)
-  hitl::DevBuf<int32_t> d_node_meta;     // index | dim << 31
+  hitl::DevBuf<float4> d_node_pm;        // px, py, bits(index | dim << 31), 0   (preorder, concatenated): one 16 B load per node visit
+  hitl::DevBuf<float2> d_node_nn;        // nx, ny   (read only for nodes inside the query radius)
   hitl::DevBuf<hitl_kdnode> d_node_aos;  // staging for hitl_set_kdtrees / hitl_get_kdtrees (AoS <-> SoA on the device)
 
   // ---- per-call pose tables ----

@@ -27,6 +27,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 #include "hitl_internal.h"
 #include "hitl_math.h"
 
@@ -40,9 +41,10 @@ enum { FAR_NONE = 0, FAR_COND = 1, FAR_UNCOND = 2 };
 constexpr uint32_t kNoPos = 0xFFFFu;
 
 struct TreeRef {
-  const float4* __restrict__ pn;     // px, py, nx, ny
-  const int32_t* __restrict__ meta;  // index | dim << 31
+  const float4* __restrict__ pm;     // px, py, bits(index | dim << 31), 0 : everything a node visit needs in one 16 B load
+  const float2* __restrict__ nn;     // nx, ny : read only when the node is inside the radius
 };
+__device__ __forceinline__ uint32_t node_meta(const float4& nd) { return __float_as_uint(nd.z); }
 
 // stack[level * stride + tid]
 __device__ __forceinline__ void nearest_point_normal(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr,
@@ -54,15 +56,16 @@ __device__ __forceinline__ void nearest_point_normal(const TreeRef t, uint32_t n
   for (;;) {
     // ---- call(pos, n) ----
     for (;;) {
-      const float4 nd = __ldg(t.pn + pos);
-      const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+      const float4 nd = __ldg(t.pm + pos);
+      const int dim = (int)(node_meta(nd) >> 31);
       float best = FLT_MAX;
       uint32_t bestpos = kNoPos;
       const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
       bool leaf_return = false;
       if (fadd(fmul(ex, ex), fmul(ey, ey)) < thr2) {
+        const float2 nv = __ldg(t.nn + pos);
         bestpos = pos;
-        best = fabsf(fadd(fmul(nd.z, fsub(qx, nd.x)), fmul(nd.w, fsub(qy, nd.y))));
+        best = fabsf(fadd(fmul(nv.x, fsub(qx, nd.x)), fmul(nv.y, fsub(qy, nd.y))));
         if (best < FLT_MIN) { best = 0.0f; leaf_return = true; }
       }
       const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
@@ -123,8 +126,8 @@ __device__ void nearest_point(const TreeRef t, uint32_t n_nodes, float qx, float
   float ret_best; uint32_t ret_pos;
   for (;;) {
     for (;;) {
-      const float4 nd = __ldg(t.pn + pos);
-      const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+      const float4 nd = __ldg(t.pm + pos);
+      const int dim = (int)(node_meta(nd) >> 31);
       const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
       float best = sqrtf(fadd(fmul(ex, ex), fmul(ey, ey)));
       uint32_t bestpos = pos;
@@ -168,8 +171,8 @@ __device__ uint32_t neighbor_count(const TreeRef t, uint32_t n_nodes, float qx, 
   while (sp) {
     --sp;
     const uint32_t pos = stack_pos[sp], n = stack_n[sp];
-    const float4 nd = __ldg(t.pn + pos);
-    const int dim = (int)((uint32_t)__ldg(t.meta + pos) >> 31);
+    const float4 nd = __ldg(t.pm + pos);
+    const int dim = (int)(node_meta(nd) >> 31);
     const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
     if (sqrtf(fadd(fmul(ex, ex), fmul(ey, ey))) < thr) ++count;
     const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
@@ -180,12 +183,12 @@ __device__ uint32_t neighbor_count(const TreeRef t, uint32_t n_nodes, float qx, 
   return count;
 }
 
-__global__ void kd_query_kernel(const float4* pn, const int32_t* meta, uint32_t tree_off, uint32_t n_nodes, uint32_t nq,
+__global__ void kd_query_kernel(const float4* pm, const float2* nn, uint32_t tree_off, uint32_t n_nodes, uint32_t nq,
                                 const float2* q, float thr, int mode, float* dist, int32_t* index) {
   extern __shared__ uint4 smem_stack[];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
-  TreeRef t; t.pn = pn + tree_off; t.meta = meta + tree_off;
+  TreeRef t; t.pm = pm + tree_off; t.nn = nn + tree_off;
   if (n_nodes == 0) { if (mode != 2) dist[i] = FLT_MAX; index[i] = mode == 2 ? 0 : -1; return; }
   const float2 p = q[i];
   if (mode == 2) { index[i] = (int32_t)neighbor_count(t, n_nodes, p.x, p.y, thr); return; }
@@ -193,7 +196,7 @@ __global__ void kd_query_kernel(const float4* pn, const int32_t* meta, uint32_t 
   if (mode == 0) nearest_point_normal(t, n_nodes, p.x, p.y, thr, smem_stack + threadIdx.x, blockDim.x, &best, &pos);
   else nearest_point(t, n_nodes, p.x, p.y, thr, &best, &pos);
   dist[i] = best;
-  index[i] = pos == kNoPos ? -1 : (__ldg(t.meta + pos) & 0x7FFFFFFF);
+  index[i] = pos == kNoPos ? -1 : (int32_t)(node_meta(__ldg(t.pm + pos)) & 0x7FFFFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,7 +313,7 @@ __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uin
 // ------------------------------------------------------------------------------------------------
 struct SearchParams {
   const float2* __restrict__ pts; const float2* __restrict__ nrm;
-  const float4* __restrict__ node_pn; const int32_t* __restrict__ node_meta;
+  const float4* __restrict__ node_pm; const float2* __restrict__ node_nn;
   const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
   const uint32_t* __restrict__ occ;
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
@@ -320,21 +323,24 @@ struct SearchParams {
   uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
   unsigned long long* __restrict__ counters;   // [6] = tile ticket
   unsigned long long* __restrict__ pose_work;  // SM cycles spent on the tiles of each source pose (load-balancing feedback)
+  const uint32_t* __restrict__ tile_order;     // tiles of the shard, most expensive first (from the previous call), or null
+  uint32_t* __restrict__ tile_work;            // cycles / 64 per tile of this call
 };
 
 constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kSearchMinBlocks = 12;   // 48 warps / SM: the walk is latency-bound, more resident warps hide the node loads
 constexpr uint32_t kQueueCap = 64;
 constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
 
 struct __align__(16) WarpShared {
-  uint4 rec[32][4];        // staged target records (PoseRec) of the current block of 32 target poses
+  uint4 rec[32][3];        // per candidate of the current block of 32 target poses: T_ij, scan size, occupancy grid descriptor
   uint32_t queue[kQueueCap];   // item = owner lane | j << 5
   uint32_t cnt[32];        // matches per lane's point
   uint32_t exec_last[32];  // j that filled the cap (kNotCapped otherwise)
 };
 
-__global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_kernel(const SearchParams P) {
   __shared__ WarpShared s_warp[kSearchWarps];
   WarpShared& W = s_warp[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
@@ -343,9 +349,13 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
 
   for (;;) {
     uint32_t tile = 0;
-    if (lane == 0) tile = P.tile_lo + (uint32_t)atomicAdd(P.counters + 6, 1ull);
+    if (lane == 0) {
+      const uint32_t ticket = (uint32_t)atomicAdd(P.counters + 6, 1ull);
+      // longest-processing-time-first: heavy tiles start early so the last wave is made of light ones
+      tile = ticket >= P.tile_hi - P.tile_lo ? 0xFFFFFFFFu : (P.tile_order ? __ldg(P.tile_order + ticket) : P.tile_lo + ticket);
+    }
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= P.tile_hi) break;
+    if (tile == 0xFFFFFFFFu) break;
     const long long t_begin = clock64();
     const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
     const uint32_t i_off = P.rec[i].off, i_n = P.rec[i].n;
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
         const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
         float qx, qy;
         affine_apply(T, opx, opy, &qx, &qy);
-        TreeRef t; t.pn = P.node_pn + rj.off; t.meta = P.node_meta + rj.off;
+        TreeRef t; t.pm = P.node_pm + rj.off; t.nn = P.node_nn + rj.off;
         float best; uint32_t bpos;
         nearest_point_normal(t, rj.n, qx, qy, P.thr, stack, 1, &best, &bpos);
         ++n_trav;
@@ -400,9 +410,9 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
           const float dth = (float)(P.pose[3 * j + 2] - theta_i);
           const float sn = sinf_rn(dth), cs = cosf_rn(dth);
           float rnx, rny; rot_apply(cs, sn, onx, ony, &rnx, &rny);
-          const float4 nd = __ldg(t.pn + bpos);
-          ok = fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > P.min_cos;
-          tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+          const float2 nb = __ldg(t.nn + bpos);
+          ok = fadd(fmul(nb.x, rnx), fmul(nb.y, rny)) > P.min_cos;
+          tgt = node_meta(__ldg(t.pm + bpos)) & 0x7FFFFFFFu;
         }
       }
       // commit in queue order: an item counts only while its owner is below the cap
@@ -446,27 +456,31 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
         if (cand == 0) continue;
         n_cand += __popc(cand);
         if (hit) {
-          const uint4* r = reinterpret_cast<const uint4*>(P.rec + jl);
-          W.rec[lane][0] = __ldg(r); W.rec[lane][1] = __ldg(r + 1); W.rec[lane][2] = __ldg(r + 2); W.rec[lane][3] = __ldg(r + 3);
+          // this lane's candidate: T_ij = target^-1 * source once per (tile, j), staged with the grid descriptor
+          const PoseRec rj = P.rec[jl];
+          Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+          const Aff2 T = affine_mul(inv, src);
+          W.rec[lane][0] = make_uint4(__float_as_uint(T.m00), __float_as_uint(T.m01), __float_as_uint(T.m10), __float_as_uint(T.m11));
+          W.rec[lane][1] = make_uint4(__float_as_uint(T.tx), __float_as_uint(T.ty), rj.n, rj.goff);
+          W.rec[lane][2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
         }
         __syncwarp();
         uint32_t need = 0;
         for (uint32_t cm = cand; cm; cm &= cm - 1) {
           const uint32_t c = __ffs(cm) - 1;
-          const uint4 r0 = W.rec[c][0], r1 = W.rec[c][1], r2 = W.rec[c][2];
-          bool in = active && r1.w != 0;                        // r1.w = n
+          const uint4 r0 = W.rec[c][0], r1 = W.rec[c][1];
+          bool in = active && r1.z != 0;                        // r1.z = n
           if (in && !P.no_cull) {
-            Aff2 inv; inv.m00 = __uint_as_float(r0.x); inv.m01 = __uint_as_float(r0.y); inv.m10 = __uint_as_float(r0.z); inv.m11 = __uint_as_float(r0.w);
-            inv.tx = __uint_as_float(r1.x); inv.ty = __uint_as_float(r1.y);
-            const Aff2 T = affine_mul(inv, src);
+            Aff2 T; T.m00 = __uint_as_float(r0.x); T.m01 = __uint_as_float(r0.y); T.m10 = __uint_as_float(r0.z); T.m11 = __uint_as_float(r0.w);
+            T.tx = __uint_as_float(r1.x); T.ty = __uint_as_float(r1.y);
             float qx, qy;
             affine_apply(T, p.x, p.y, &qx, &qy);
+            const uint4 r2 = W.rec[c][2];
             uint32_t cx, cy;
             in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
             if (in) {
-              const uint32_t goff = W.rec[c][3].x;
               const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
-              in = (__ldg(P.occ + goff + (bit >> 5)) >> (bit & 31)) & 1u;
+              in = (__ldg(P.occ + r1.w + (bit >> 5)) >> (bit & 31)) & 1u;
             }
           }
           need |= (uint32_t)in << c;
@@ -505,12 +519,19 @@ __global__ void __launch_bounds__(kSearchThreads) stf_search_kernel(const Search
     for (int o = 16; o; o >>= 1) exec += __shfl_xor_sync(0xffffffffu, exec, o);
     if (lane == 0) {
       atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 2, (unsigned long long)wcount);
-      atomicAdd(P.pose_work + i, (unsigned long long)(clock64() - t_begin));
+      const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
+      atomicAdd(P.pose_work + i, dt);
+      P.tile_work[tile] = (uint32_t)min(dt >> 6, 0xFFFFFFFFull);
     }
     __syncwarp();
   }
   for (int o = 16; o; o >>= 1) n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
   if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); }
+}
+
+__global__ void iota_kernel(uint32_t* out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,8 +696,8 @@ __global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, u
 // ordered output through a per-scan slot region, compacted on the host side of the call
 // (the result is never consumed downstream in the reference; kept simple).
 // ------------------------------------------------------------------------------------------------
-__global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const float4* __restrict__ node_pn,
-                                 const int32_t* __restrict__ node_meta, const PoseRec* __restrict__ rec, const float4* __restrict__ srcs,
+__global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const float4* __restrict__ node_pm,
+                                 const float2* __restrict__ node_nn, const PoseRec* __restrict__ rec, const float4* __restrict__ srcs,
                                  const double* __restrict__ pose, uint32_t i_lo, uint32_t i_hi, float thr, float min_cos,
                                  uint32_t* __restrict__ out_tk, uint32_t* __restrict__ scan_cnt) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -689,7 +710,7 @@ __global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* _
   const Aff2 T = affine_mul(inv, src);
   const float dth = (float)(pose[3 * i + 5] - pose[3 * i + 2]);
   const float sn = sinf_rn(dth), cs = cosf_rn(dth);
-  TreeRef t; t.pn = node_pn + rj.off; t.meta = node_meta + rj.off;
+  TreeRef t; t.pm = node_pm + rj.off; t.nn = node_nn + rj.off;
   uint32_t total = 0;
   for (uint32_t k0 = 0; k0 < ri.n; k0 += 32) {
     const uint32_t k = k0 + lane;
@@ -700,9 +721,9 @@ __global__ void vo_search_kernel(const float2* __restrict__ pts, const float2* _
       float best; uint32_t bpos;
       nearest_point(t, rj.n, qx, qy, thr, &best, &bpos);
       float rnx, rny; rot_apply(cs, sn, nv.x, nv.y, &rnx, &rny);
-      const float4 nd = __ldg(t.pn + bpos);
-      ok = best < thr && fadd(fmul(nd.z, rnx), fmul(nd.w, rny)) > min_cos;
-      tgt = (uint32_t)(__ldg(t.meta + bpos) & 0x7FFFFFFF);
+      const float2 nb = __ldg(t.nn + bpos);
+      ok = best < thr && fadd(fmul(nb.x, rnx), fmul(nb.y, rny)) > min_cos;
+      tgt = node_meta(__ldg(t.pm + bpos)) & 0x7FFFFFFFu;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, ok);
     // slot per source point: target index or 0xFFFFFFFF
@@ -737,7 +758,7 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
   const uint32_t toff = ctx->h_off[scan], tn = ctx->h_off[scan + 1] - toff;
   const int threads = 128;
   const size_t smem = (size_t)stack_levels(ctx->max_scan) * threads * sizeof(uint4);
-  kd_query_kernel<<<(nq + threads - 1) / threads, threads, smem, ctx->stream>>>(ctx->d_node_pn.p, ctx->d_node_meta.p, toff, tn, nq, dq.p,
+  kd_query_kernel<<<(nq + threads - 1) / threads, threads, smem, ctx->stream>>>(ctx->d_node_pm.p, ctx->d_node_nn.p, toff, tn, nq, dq.p,
                                                                               threshold, mode, dd.p, di.p);
   HITL_LAUNCH_CHECK("kd_query_kernel");
   if (dist_out && mode != 2) HITL_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(float) * nq, cudaMemcpyDeviceToHost, ctx->stream));
@@ -847,7 +868,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   if (rc) return rc;
 
   SearchParams P;
-  P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pn = ctx->d_node_pn.p; P.node_meta = ctx->d_node_meta.p;
+  P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
   P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
   P.jmin = jmin; P.jmax = jmax; P.thr = o->point_match_threshold; P.min_cos = o->min_cosine_angle; P.cap = cap;
@@ -855,6 +876,10 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.raw_j = ctx->d_raw_j.p; P.raw_k = ctx->d_raw_k.p; P.raw_idx = ctx->d_raw_idx.p; P.tile_cnt = ctx->d_tile_cnt.p;
   P.counters = (unsigned long long*)ctx->d_counters.p;
   P.pose_work = (unsigned long long*)ctx->d_pose_work.p;
+  HITL_CUDA(ctx->d_tile_work.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_order.ensure(ctx->n_tiles));
+  P.tile_work = ctx->d_tile_work.p;
+  // the order computed after the previous search of the same tile range is a pure scheduling hint
+  P.tile_order = (ctx->order_valid && ctx->order_lo == P.tile_lo && ctx->order_hi == P.tile_hi && !o->disable_culling) ? ctx->d_tile_order.p : nullptr;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -868,6 +893,23 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (n_tiles > 1 && !o->disable_culling) {
+    // next call's ticket order: this call's tiles sorted by measured cycles, descending
+    HITL_CUDA(ctx->d_tile_iota.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_keys.ensure(ctx->n_tiles));
+    if (!ctx->iota_valid) {
+      iota_kernel<<<(ctx->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_tile_iota.p, ctx->n_tiles);
+      HITL_LAUNCH_CHECK("iota_kernel");
+      ctx->iota_valid = true;
+    }
+    size_t tmp_bytes = 0;
+    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
+                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
+    HITL_CUDA(ctx->d_sort_tmp.ensure(tmp_bytes));
+    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(ctx->d_sort_tmp.p, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
+                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
+    ctx->launches += 1;
+    ctx->order_valid = true; ctx->order_lo = P.tile_lo; ctx->order_hi = P.tile_hi;
+  }
 
   OrderParams Q;
   Q.raw_j = ctx->d_raw_j.p; Q.raw_k = ctx->d_raw_k.p; Q.raw_idx = ctx->d_raw_idx.p; Q.tile_cnt = ctx->d_tile_cnt.p;
@@ -942,7 +984,7 @@ extern "C" int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min
   HITL_CUDA(ctx->d_vo_tk.ensure(ctx->n_points)); HITL_CUDA(ctx->d_tile_cnt.ensure(std::max<size_t>(ctx->n_tiles, ctx->n_poses)));
   const int threads = 128;
   vo_search_kernel<<<((size_t)(i_hi - i_lo) * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(
-      ctx->d_pts.p, ctx->d_nrm.p, ctx->d_node_pn.p, ctx->d_node_meta.p, ctx->d_rec.p, ctx->d_src.p, ctx->d_pose.p, i_lo, i_hi, o->point_match_threshold,
+      ctx->d_pts.p, ctx->d_nrm.p, ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_rec.p, ctx->d_src.p, ctx->d_pose.p, i_lo, i_hi, o->point_match_threshold,
       o->min_cosine_angle, ctx->d_vo_tk.p, ctx->d_tile_cnt.p);
   HITL_LAUNCH_CHECK("vo_search_kernel");
   // compaction on the host side of the call (result is (N-1)*P slots; the reference never consumes it)

@@ -125,7 +125,9 @@ int hitl_host_session_world_transform(void* sp, int keep_host_copy) {
   Session* s = static_cast<Session*>(sp);
   HOST_TRY(s, {
     if (keep_host_copy) {
+      s->jopt.copy_world_frame_clouds_to_host_ = true;
       s->jopt.CopyTempLaserScans();
+      s->jopt.copy_world_frame_clouds_to_host_ = false;
       s->em.local_version_point_clouds_ = s->jopt.world_frame_point_clouds_;
     } else {
       std::vector<float> p(3 * s->jopt.poses_.size());

@@ -110,6 +110,10 @@ void JointOpt::CopyTempLaserScans() {
   for (size_t i = 0; i < poses_.size(); ++i) { p[3 * i] = poses_[i].translation.x; p[3 * i + 1] = poses_[i].translation.y; p[3 * i + 2] = poses_[i].angle; }
   size_t total = 0;
   for (const PointCloudf& c : robot_frame_point_clouds_) total += c.size();
+  if (!copy_world_frame_clouds_to_host_) {   // clouds stay on the device (the EM stage reads them there)
+    check(hitl_world_transform(ctx_, p.data(), nullptr), "hitl_world_transform");
+    return;
+  }
   std::vector<float> w(2 * std::max<size_t>(total, 1));
   check(hitl_world_transform(ctx_, p.data(), w.data()), "hitl_world_transform");
   world_frame_point_clouds_.resize(robot_frame_point_clouds_.size());

@@ -51,6 +51,7 @@ class JointOpt {
   VectorMappingOptions localization_options_;
   bool enable_post_human_optimization_ = false;   // the PostHumanOptimization call is inside /* */ at :1353-1373
   int precision_ = 0;                              // 0 = FP64 blocks, 1 = FP32 mode (hitl_eval)
+  bool copy_world_frame_clouds_to_host_ = false;   // CopyTempLaserScans: also fill world_frame_point_clouds_ (nothing on the path reads it)
   bool verbose_ = false;
   ceres::Solver::Options human_solver_options_;    // defaults of SolveHumanConstraints (:1059-1063)
   ceres::Solver::Options post_solver_options_;     // SetSolverOptions (:145-162) + max_num_iterations 100

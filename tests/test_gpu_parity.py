@@ -151,6 +151,24 @@ def test_find_stf_shards_concatenate(gpu, oracle, maps):
         assert cat["n_queries"] == ref["n_queries"]
 
 
+def test_find_stf_is_independent_of_the_tile_schedule(gpu, oracle, maps):
+    """The second and later calls hand tiles out heaviest-first (order measured by the previous call);
+    results must not depend on it, also when the source range or the poses change in between."""
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    ref = S.find_stf(poses)
+    for _ in range(3):
+        assert_same_stf(gpu.find_stf(poses), ref)
+    part = gpu.find_stf(poses, src_lo=30, src_hi=90)
+    assert_same_stf(part, S.find_stf(poses, src_lo=30, src_hi=90))
+    assert_same_stf(gpu.find_stf(poses, src_lo=30, src_hi=90), part)
+    moved = poses + np.random.default_rng(4).normal(size=poses.shape) * 0.02
+    assert_same_stf(gpu.find_stf(moved), S.find_stf(moved))
+    assert_same_stf(gpu.find_stf(poses), ref)
+
+
 def test_find_stf_work_feedback_covers_exactly_the_searched_sources(gpu, maps):
     g = maps("small")
     load_map(gpu, g)
