@@ -329,7 +329,7 @@ struct SearchParams {
 
 constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
-constexpr int kSearchMinBlocks = 12;   // 48 warps / SM: the walk is latency-bound, more resident warps hide the node loads
+constexpr int kSearchMinBlocks = 16;   // 48 warps / SM: the walk is latency-bound, more resident warps hide the node loads
 constexpr uint32_t kQueueCap = 64;
 constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
 
@@ -549,6 +549,7 @@ struct OrderParams {
   const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ off;
   uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
   uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
+  uint32_t* kept;                     // gridDim.x * n_poses: kept target poses of the pose being placed (pass 1)
   unsigned long long* pose_cnt;       // 2 per source pose of the shard: matches, pairs (pass 1: exclusive offsets)
   uint32_t* pair_i; uint32_t* pair_j; unsigned long long* pair_off; uint32_t* out_k; uint32_t* out_idx;
 };
@@ -571,12 +572,27 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return base + x - v;
 }
 
+// Exclusive scan of a (matches, pairs) couple packed as matches | pairs << 40 (matches per pose < 2^40).
+__device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* total, unsigned long long* sm /* 33 words */) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long x = v;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+  if (lane == 31) sm[w] = x;
+  __syncthreads();
+  unsigned long long base = 0, tot = 0;
+  for (uint32_t q = 0; q < (blockDim.x >> 5); ++q) { const unsigned long long t = sm[q]; if (q < w) base += t; tot += t; }
+  *total = tot;
+  __syncthreads();
+  return base + x - v;
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderParams P) {
-  __shared__ uint32_t sm[40];
+  __shared__ unsigned long long sm[8];
   __shared__ uint32_t s_jlo, s_jhi;
   __shared__ unsigned long long s_off_m, s_off_p;
   uint32_t* const cntj = P.scratch + (size_t)blockIdx.x * P.n_poses;
+  uint32_t* const keptj = PASS == 1 ? P.kept + (size_t)blockIdx.x * P.n_poses : nullptr;
   for (uint32_t i = P.src_lo + blockIdx.x; i < P.src_hi; i += gridDim.x) {
     const uint32_t tb = P.tile_begin[i], te = P.tile_begin[i + 1];
     const uint32_t seg = P.off[i] * (uint32_t)P.cap;
@@ -605,46 +621,49 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
         const uint32_t j = j0 + threadIdx.x;
         const uint32_t c = j <= jhi ? cntj[j] : 0;
         const uint32_t keep = c > P.min_corr ? c : 0;
-        uint32_t tm, tp;
-        const uint32_t em = block_exclusive_scan(keep, &tm, sm);
-        const uint32_t ep = block_exclusive_scan(keep ? 1u : 0u, &tp, sm);
+        unsigned long long tot2;
+        const unsigned long long ex2 = block_exclusive_scan64((unsigned long long)keep | ((unsigned long long)(keep ? 1u : 0u) << 40), &tot2, sm);
+        const uint32_t em = (uint32_t)(ex2 & 0xFFFFFFFFFFull), ep = (uint32_t)(ex2 >> 40);
+        const uint32_t tm = (uint32_t)(tot2 & 0xFFFFFFFFFFull), tp = (uint32_t)(tot2 >> 40);
         if (PASS == 1 && j <= jhi) {
           if (keep) {
             const unsigned long long po = s_off_p + run_p + ep;
             P.pair_i[po] = i; P.pair_j[po] = j; P.pair_off[po] = s_off_m + run_m + em;
             cntj[j] = run_m + em;                 // start of this pair inside the pose's kept segment
-          } else if (c) cntj[j] = kDropped;
+            keptj[run_p + ep] = j;
+          }
         }
         run_m += tm; run_p += tp;
       }
       tot_m = run_m; tot_p = run_p;
       if (PASS == 1) {
         __syncthreads();
-        // -- placement: tiles in ascending k order; inside a tile each j forms one run --
-        for (uint32_t t = tb; t < te; ++t) {
-          const uint32_t c = P.tile_cnt[t], base = seg + (t - tb) * 32u * (uint32_t)P.cap;
-          // phase 1: every record reads its pair cursor (value at tile start) and is placed
-          for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
-            const uint32_t j = P.raw_j[base + u];
-            const uint32_t pos = cntj[j];
-            if (pos == kDropped) continue;
-            uint32_t start = u;
-            while (start > 0 && P.raw_j[base + start - 1] == j) --start;     // run start (<= 31 steps)
-            const unsigned long long o = s_off_m + pos + (u - start);
-            P.out_k[o] = P.raw_k[base + u]; P.out_idx[o] = P.raw_idx[base + u];
+        // -- placement, one warp per kept target pose j: every tile list is sorted by (j, k) and tiles are
+        //    in ascending k order, so pair (i, j) is the concatenation over tiles of each tile's run of j.
+        //    Lanes bisect "their" tile for the run, a warp scan turns run lengths into offsets. --
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const uint32_t ntile = te - tb, tile_stride = 32u * (uint32_t)P.cap;
+        for (uint32_t e = wid; e < tot_p; e += kOrderThreads / 32) {
+          const uint32_t j = keptj[e];
+          unsigned long long dst = s_off_m + cntj[j];
+          for (uint32_t t0 = 0; t0 < ntile; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            uint32_t lb = 0, len = 0, base = 0;
+            if (t < ntile) {
+              const uint32_t c = P.tile_cnt[tb + t];
+              base = seg + t * tile_stride;
+              uint32_t lo = 0, hi = c;                                   // lower_bound(j)
+              while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (P.raw_j[base + mid] < j) lo = mid + 1; else hi = mid; }
+              lb = lo;
+              while (lb + len < c && len < 32 && P.raw_j[base + lb + len] == j) ++len;   // a run holds each point at most once: <= 32 records
+            }
+            uint32_t x = len;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
+            const unsigned long long o0 = dst + (x - len);
+            for (uint32_t r = 0; r < len; ++r) { P.out_k[o0 + r] = P.raw_k[base + lb + r]; P.out_idx[o0 + r] = P.raw_idx[base + lb + r]; }
+            dst += total;
           }
-          __syncthreads();
-          // phase 2: the first record of each run advances its pair cursor by the run length
-          for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
-            const uint32_t j = P.raw_j[base + u];
-            if (u > 0 && P.raw_j[base + u - 1] == j) continue;
-            const uint32_t pos = cntj[j];
-            if (pos == kDropped) continue;
-            uint32_t e = u + 1;
-            while (e < c && P.raw_j[base + e] == j) ++e;
-            cntj[j] = pos + (e - u);
-          }
-          __syncthreads();
         }
       }
       // -- clear the touched scratch entries --
@@ -917,8 +936,9 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   Q.min_corr = o->min_inter_pose_correspondence;
   const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)ctx->sm_count * 8);
   HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
+  HITL_CUDA(ctx->d_srt_k.ensure((size_t)order_grid * n));   // reused as the kept-j lists
   HITL_CUDA(cudaMemsetAsync(ctx->d_srt_j.p, 0, sizeof(uint32_t) * (size_t)order_grid * n, ctx->stream));
-  Q.scratch = ctx->d_srt_j.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
+  Q.scratch = ctx->d_srt_j.p; Q.kept = ctx->d_srt_k.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
   Q.pair_i = ctx->d_pair_i.p; Q.pair_j = ctx->d_pair_j.p; Q.pair_off = (unsigned long long*)ctx->d_pair_off.p;
   Q.out_k = ctx->d_k.p; Q.out_idx = ctx->d_idx.p;
   stf_order_kernel<0><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
