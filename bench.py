@@ -171,7 +171,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--poses", type=int, default=None)
@@ -238,13 +238,19 @@ def main():
         return info, ne
 
     for w in range(args.warmup):
-        step()
-        if world > 1 and w < 2:
-            # re-cut the source ranges at equal MEASURED work (SM cycles per source pose of the search that
-            # just ran, summed over the ranks); setup-time exchange, not on the per-step data path
-            work = torch.from_numpy(gpu.stf_work().astype(np.int64)).cuda()
+        info_w, _ = step()
+        if world > 1 and w < min(4, args.warmup - 2):
+            # re-cut the source ranges at equal MEASURED time: SM cycles per source pose of the search that just
+            # ran, scaled so that a rank's poses add up to its kernel time, summed over the ranks.  Setup-time
+            # exchange (not on the per-step data path); the last warm-up steps run on the final ranges.
+            wk = gpu.stf_work().astype(np.float64)
+            if wk.sum() > 0:
+                wk *= info_w["ms_search"] / wk.sum()
+            work = torch.from_numpy(wk).cuda()
             dist.all_reduce(work)
             lo, hi = shard_ranges_by_work(work.cpu().numpy(), world)[rank]
+        if os.environ.get("HITL_BENCH_DEBUG"):
+            sys.stderr.write("[rank %d] warmup %d: ms_search %.3f ms_total %.3f tiles %d -> %d, next range [%d, %d)\n" % (rank, w, info_w["ms_search"], info_w["ms_total"], info_w["n_tiles"], info_w["n_tiles_next"], lo, hi))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -277,6 +283,14 @@ def main():
         dist.all_reduce(cnt)
     total_ms = float(t.item())
     queries, matches, pairs, trav = [int(x) for x in cnt.tolist()]
+    # per-rank view of the last timed step (diagnosis of shard balance): search kernel ms, whole find_stf ms, tiles
+    mine = torch.tensor([infos[-1][0]["ms_search"], infos[-1][0]["ms_total"], float(infos[-1][0]["n_tiles"]), float(hi - lo)], dtype=torch.float64, device="cuda")
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [[round(float(x), 3) for x in r.tolist()] for r in per_rank]
     ms_per_step = total_ms / args.steps
     evals = queries + matches
     value = evals / (ms_per_step * 1e-3) / 1e6
@@ -359,7 +373,8 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction,
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
-                           "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos]))}}
+                           "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
+                           "per_rank_[ms_search,ms_find_stf,tiles,source_poses]": per_rank}}
         print(json.dumps(line))
     gpu.close()
     if world > 1:

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose",
+    "hitl_normal_eq_device", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
 ]
 
 
@@ -42,7 +42,8 @@ class StfOpts(C.Structure):
 
 class StfInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
-                ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float)]
+                ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float),
+                ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
 
 
 class EvalLayout(C.Structure):
@@ -113,6 +114,8 @@ class HitlGpu:
         lib.hitl_eval.argtypes = [vp, _f64p, C.c_int, vp, vp, C.POINTER(C.c_float)]
         lib.hitl_normal_eq.argtypes = [vp, _f64p, vp, vp, vp, vp, C.POINTER(C.c_float)]
         lib.hitl_normal_eq_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+        lib.hitl_debug_tile_work.argtypes = [vp, C.c_uint32, _u32p, C.POINTER(C.c_uint32)]
+        lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int]
         lib.hitl_debug_sincos.argtypes = [vp, C.c_uint64, _f32p, _f32p, _f32p]
         lib.hitl_debug_relative_pose.argtypes = [vp, _f64p, C.c_uint32, _u32p, _u32p, _f32p]
         self.ctx = vp()
@@ -204,7 +207,8 @@ class HitlGpu:
         info = StfInfo()
         self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
         res = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
-                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, ms_search=info.ms_search, ms_total=info.ms_total)
+                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, ms_search=info.ms_search, ms_total=info.ms_total,
+                   n_tiles=info.n_tiles, n_tiles_next=info.n_tiles_next)
         if fetch:
             res.update(self.get_stf(info.n_pairs, info.n_matches, out))
         return res
@@ -348,6 +352,16 @@ class HitlGpu:
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self.lib.hitl_normal_eq_device(self.ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def debug_tile_work(self):
+        n = C.c_uint32()
+        self._ck(self.lib.hitl_debug_tile_work(self.ctx, 0, np.zeros(1, np.uint32), C.byref(n)))
+        w = np.zeros(max(n.value, 1), np.uint32)
+        self._ck(self.lib.hitl_debug_tile_work(self.ctx, n.value, w, C.byref(n)))
+        return w[:n.value].astype(np.uint64) * 64
+
+    def debug_set_tiling(self, max_len=32, adaptive=True):
+        self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive)))
 
     def debug_sincos(self, x):
         x = np.ascontiguousarray(x, np.float32)

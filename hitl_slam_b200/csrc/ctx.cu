@@ -20,6 +20,72 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where) {
   return HITL_ERR_CUDA;
 }
 int launch_scan_aabb(hitl_ctx* ctx);
+
+// Uploads the host tile tables (h_tile_scan, h_tile_kl = k0 | len << 16, h_tile_begin).
+int upload_tiling(hitl_ctx* ctx) {
+  const uint32_t nt = (uint32_t)ctx->h_tile_scan.size();
+  ctx->n_tiles = nt;
+  // per-tile cost estimates (0 = never searched) and the identity permutation the scheduler sorts by them
+  HITL_CUDA(ctx->d_tile_work.ensure(nt)); HITL_CUDA(ctx->d_tile_order.ensure(nt)); HITL_CUDA(ctx->d_tile_iota.ensure(nt)); HITL_CUDA(ctx->d_tile_keys.ensure(nt));
+  if (nt) {
+    HITL_CUDA(cudaMemsetAsync(ctx->d_tile_work.p, 0, 4 * (size_t)nt, ctx->stream));
+    std::vector<uint32_t> iota(nt);
+    for (uint32_t t = 0; t < nt; ++t) iota[t] = t;
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_iota.p, iota.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  HITL_CUDA(ctx->d_tile_scan.ensure(nt)); HITL_CUDA(ctx->d_tile_k0.ensure(nt)); HITL_CUDA(ctx->d_tile_begin.ensure(ctx->n_poses + 1));
+  if (nt) {
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_scan.p, ctx->h_tile_scan.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_k0.p, ctx->h_tile_kl.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_begin.p, ctx->h_tile_begin.data(), 4 * (size_t)(ctx->n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+// Uniform tiling: every scan cut into tiles of at most max_len points.
+int build_tiling(hitl_ctx* ctx, uint32_t max_len) {
+  if (max_len < 1) max_len = 1;
+  if (max_len > 32) max_len = 32;
+  const uint32_t n_poses = ctx->n_poses;
+  ctx->h_tile_scan.clear(); ctx->h_tile_kl.clear();
+  ctx->h_tile_scan.reserve(ctx->n_points / max_len + n_poses); ctx->h_tile_kl.reserve(ctx->n_points / max_len + n_poses);
+  ctx->h_tile_begin.assign(n_poses + 1, 0);
+  for (uint32_t i = 0; i < n_poses; ++i) {
+    ctx->h_tile_begin[i] = (uint32_t)ctx->h_tile_scan.size();
+    const uint32_t n = ctx->h_off[i + 1] - ctx->h_off[i];
+    for (uint32_t k0 = 0; k0 < n; k0 += max_len) { ctx->h_tile_scan.push_back(i); ctx->h_tile_kl.push_back(k0 | (std::min(max_len, n - k0) << 16)); }
+  }
+  ctx->h_tile_begin[n_poses] = (uint32_t)ctx->h_tile_scan.size();
+  ctx->tiling_splits = 0;
+  return upload_tiling(ctx);
+}
+
+// Splits every tile whose measured work (cycles / 64, h_work indexed by tile id, tiles in [lo, hi)) exceeds
+// `limit` into 2, 4 or 8 equal parts (never below 4 points).  Returns the number of tiles that were split.
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, uint32_t lo, uint32_t hi, uint64_t limit, std::vector<uint32_t>* est) {
+  std::vector<uint32_t> scan, kl;
+  est->clear(); est->reserve(ctx->h_tile_scan.size() + 1024);
+  scan.reserve(ctx->h_tile_scan.size() + 1024); kl.reserve(ctx->h_tile_scan.size() + 1024);
+  std::vector<uint32_t> begin(ctx->n_poses + 1, 0);
+  uint32_t n_split = 0, pose = 0;
+  for (uint32_t t = 0; t < (uint32_t)ctx->h_tile_scan.size(); ++t) {
+    const uint32_t i = ctx->h_tile_scan[t], k0 = ctx->h_tile_kl[t] & 0xFFFFu, len = ctx->h_tile_kl[t] >> 16;
+    while (pose <= i) begin[pose++] = (uint32_t)scan.size();
+    uint32_t parts = 1;
+    if (t >= lo && t < hi && h_work[t - lo] > limit) {
+      while (parts < 8 && len / (parts * 2) >= 4 && (uint64_t)h_work[t - lo] > limit * parts) parts *= 2;
+    }
+    if (parts > 1) ++n_split;
+    const uint32_t step = (len + parts - 1) / parts;
+    const uint32_t w = (t >= lo && t < hi) ? h_work[t - lo] / parts : 0;   // children inherit an equal share of the measured work
+    for (uint32_t a = 0; a < len; a += step) { scan.push_back(i); kl.push_back((k0 + a) | (std::min(step, len - a) << 16)); est->push_back(w); }
+  }
+  while (pose <= ctx->n_poses) begin[pose++] = (uint32_t)scan.size();
+  if (n_split) { ctx->h_tile_scan.swap(scan); ctx->h_tile_kl.swap(kl); ctx->h_tile_begin.swap(begin); ctx->tiling_splits += n_split; }
+  return n_split;
+}
 }  // namespace hitl
 using namespace hitl;
 
@@ -62,7 +128,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_blk_i.release(); ctx->d_blk_j.release(); ctx->d_blk_k.release(); ctx->d_blk_idx.release(); ctx->d_blk_off.release();
   ctx->d_p2lg_pose.release(); ctx->d_p2lg_off.release(); ctx->d_p2lg_pts.release(); ctx->d_p2lg_n.release(); ctx->d_p2lg_o.release(); ctx->d_p2lg_v.release();
   ctx->d_p2l_pose.release(); ctx->d_p2l_pts.release(); ctx->d_p2l_n.release(); ctx->d_p2l_o.release(); ctx->d_p2l_v.release();
-  ctx->d_r.release(); ctx->d_J.release(); ctx->d_neq.release(); ctx->d_hoff.release();
+  ctx->d_r.release(); ctx->d_J.release(); ctx->d_neq.release(); ctx->d_hoff.release(); ctx->d_trig.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -88,6 +154,9 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   if (!off && n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null offsets");
   HITL_CUDA(cudaSetDevice(ctx->device));
   ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false;
+  // Same scan partition as before (a re-upload of the same map): tiling and schedule hints stay valid.
+  const bool same_partition = ctx->n_poses == n_poses && n_poses > 0 && ctx->h_off.size() == (size_t)n_poses + 1 &&
+                              memcmp(ctx->h_off.data(), off, sizeof(uint32_t) * ((size_t)n_poses + 1)) == 0 && !ctx->h_tile_scan.empty();
   ctx->n_poses = n_poses;
   ctx->h_off.assign(n_poses + 1, 0);
   uint32_t max_scan = 0;
@@ -109,31 +178,15 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
     HITL_CUDA(cudaMemcpyAsync(ctx->d_pts.p, pts_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
     HITL_CUDA(cudaMemcpyAsync(ctx->d_nrm.p, nrm_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
   }
-  // tiles: 32 consecutive points of one scan
-  std::vector<uint32_t> tile_scan, tile_k0;
-  tile_scan.reserve(ctx->n_points / 32 + n_poses); tile_k0.reserve(ctx->n_points / 32 + n_poses);
-  ctx->h_tile_begin.assign(n_poses + 1, 0);
-  for (uint32_t i = 0; i < n_poses; ++i) {
-    ctx->h_tile_begin[i] = (uint32_t)tile_scan.size();
-    const uint32_t n = ctx->h_off[i + 1] - ctx->h_off[i];
-    for (uint32_t k0 = 0; k0 < n; k0 += 32) { tile_scan.push_back(i); tile_k0.push_back(k0); }
-  }
-  ctx->h_tile_begin[n_poses] = (uint32_t)tile_scan.size();
-  // a previous tile order stays a valid hint only if the tiling is unchanged (same scans re-uploaded)
-  if ((uint32_t)tile_scan.size() != ctx->n_tiles) { ctx->order_valid = false; ctx->iota_valid = false; }
-  ctx->n_tiles = (uint32_t)tile_scan.size();
-  HITL_CUDA(ctx->d_tile_scan.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_k0.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_begin.ensure(n_poses + 1));
-  if (ctx->n_tiles) {
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_scan.p, tile_scan.data(), 4 * (size_t)ctx->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_k0.p, tile_k0.data(), 4 * (size_t)ctx->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_begin.p, ctx->h_tile_begin.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = launch_scan_aabb(ctx);
+  // tiles: up to 32 consecutive points of one scan (the unit of work of the search; heavy tiles are split later)
+  int rc = same_partition ? HITL_OK : hitl::build_tiling(ctx, 32);
+  if (rc) return rc;
+  rc = launch_scan_aabb(ctx);
   if (rc) return rc;
   ctx->h_aabb.assign(4 * (size_t)n_poses, 0.f);
   ctx->grid_valid = false;
   if (n_poses) HITL_CUDA(cudaMemcpyAsync(ctx->h_aabb.data(), ctx->d_aabb.p, 16 * (size_t)n_poses, cudaMemcpyDeviceToHost, ctx->stream));
-  HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tile_scan / tile_k0 are locals
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }
 

@@ -141,81 +141,151 @@ __global__ void eval_human_kernel(const int32_t* __restrict__ type_pose, const d
   if (want_neq) accumulate_cost(neq, cost);
 }
 
+// ---- per-pose trigonometry, once per evaluation point ---------------------------------------------
+// (c, s, x, y) per pose: every STF block needs both of its poses' sin/cos; computing them per block
+// costs more FP64 instructions than the block's own matches (~90 on average).
+__global__ void pose_trig_kernel(const double* __restrict__ pose, uint32_t n_poses, double2* __restrict__ trig) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_poses) return;
+  double s, c;
+  sincos(pose[3 * i + 2], &s, &c);
+  trig[2 * i] = make_double2(c, s);
+  trig[2 * i + 1] = make_double2(pose[3 * i], pose[3 * i + 1]);
+}
+
 // ---- STF blocks: one warp per block ----------------------------------------------------------
 // r0 = sqrt(S0 / M), S0 = sum a_m^2, a_m = (n0g . (p1g - p0g)) * cf / sd      (likewise r1 with n1g)
 // dr0/dx = (sum a_m da_m/dx) / (M r0); r = 0 with zero Jacobian when the sum is exactly 0.
 template <typename T>
-__global__ void __launch_bounds__(128) eval_stf_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const uint32_t* __restrict__ off,
-                                                       const uint32_t* __restrict__ pair_i, const uint32_t* __restrict__ pair_j,
-                                                       const unsigned long long* __restrict__ pair_off, const uint32_t* __restrict__ kk,
-                                                       const uint32_t* __restrict__ idx, const double* __restrict__ pose, uint64_t n_blocks,
-                                                       float std_dev, float corr, double* __restrict__ r_out, double* __restrict__ J_out, NeqOut neq,
-                                                       int want_neq, size_t off_slot0) {
+struct StfAccum {
+  T S0, S1, G0[6], G1[6];
+};
+
+template <typename T>
+__device__ __forceinline__ void stf_accumulate(StfAccum<T>& A, const float2 P0, const float2 N0, const float2 P1, const float2 N1, const double c0d, const double s0d,
+                                               const double c1d, const double s1d, const double tdx, const double tdy, const T w) {
+  // Pose trigonometry and the world-frame difference p1g - p0g are always formed in FP64: the
+  // difference cancels ~10 m coordinates down to centimetres, which FP32 cannot carry to 1e-5.
+  // Everything downstream (normals, projections, derivative sums) runs in T.
+  const T c0 = (T)c0d, s0 = (T)s0d, c1 = (T)c1d, s1 = (T)s1d;
+  const double r0xd = c0d * P0.x - s0d * P0.y, r0yd = s0d * P0.x + c0d * P0.y;   // rotated (not translated) points
+  const double r1xd = c1d * P1.x - s1d * P1.y, r1yd = s1d * P1.x + c1d * P1.y;
+  const T r0x = (T)r0xd, r0y = (T)r0yd, r1x = (T)r1xd, r1y = (T)r1yd;
+  const T n0x = c0 * T(N0.x) - s0 * T(N0.y), n0y = s0 * T(N0.x) + c0 * T(N0.y);
+  const T n1x = c1 * T(N1.x) - s1 * T(N1.y), n1y = s1 * T(N1.x) + c1 * T(N1.y);
+  const T dx = (T)((r1xd - r0xd) + tdx), dy = (T)((r1yd - r0yd) + tdy);
+  const T u = n0x * dx + n0y * dy, v = n1x * dx + n1y * dy;
+  const T a = u * w, bb = v * w;
+  A.S0 += a * a; A.S1 += bb * bb;
+  // perp(w) = (-w.y, w.x) = d/dtheta of a rotated vector
+  // du/dth0 = perp(n0g).d - n0g.perp(r0) ; du/dth1 = n0g.perp(r1)
+  const T du_t0 = (-n0y * dx + n0x * dy) - (n0x * (-r0y) + n0y * r0x);
+  const T du_t1 = n0x * (-r1y) + n0y * r1x;
+  // dv/dth0 = -n1g.perp(r0) ; dv/dth1 = perp(n1g).d + n1g.perp(r1)
+  const T dv_t0 = -(n1x * (-r0y) + n1y * r0x);
+  const T dv_t1 = (-n1y * dx + n1x * dy) + (n1x * (-r1y) + n1y * r1x);
+  const T aw = a * w, bw = bb * w;
+  A.G0[0] += aw * (-n0x); A.G0[1] += aw * (-n0y); A.G0[2] += aw * du_t0; A.G0[3] += aw * n0x; A.G0[4] += aw * n0y; A.G0[5] += aw * du_t1;
+  A.G1[0] += bw * (-n1x); A.G1[1] += bw * (-n1y); A.G1[2] += bw * dv_t0; A.G1[3] += bw * n1x; A.G1[4] += bw * n1y; A.G1[5] += bw * dv_t1;
+}
+
+constexpr int kStfThreads = 256;
+#ifndef HITL_STF_MINBLOCKS
+#define HITL_STF_MINBLOCKS 4   // 64 registers, 32 warps / SM: measured 0.53 / 0.42 / 0.41 ms at 2 / 3 / 4 on B200 (profiles/eval_variants.py)
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(kStfThreads, HITL_STF_MINBLOCKS) eval_stf_kernel(const float2* __restrict__ pts, const float2* __restrict__ nrm, const uint32_t* __restrict__ off,
+                                                               const uint32_t* __restrict__ pair_i, const uint32_t* __restrict__ pair_j,
+                                                               const unsigned long long* __restrict__ pair_off, const uint32_t* __restrict__ kk,
+                                                               const uint32_t* __restrict__ idx, const double2* __restrict__ trig, uint64_t n_blocks,
+                                                               float std_dev, float corr, double* __restrict__ r_out, double* __restrict__ J_out, NeqOut neq,
+                                                               int want_neq, size_t off_slot0) {
   const uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (b >= n_blocks) return;
   const uint32_t i = pair_i[b], j = pair_j[b];
   const unsigned long long m0 = pair_off[b], m1 = pair_off[b + 1];
-  // Pose trigonometry and the world-frame difference p1g - p0g are always formed in FP64: the
-  // difference cancels ~10 m coordinates down to centimetres, which FP32 cannot carry to 1e-5.
-  // Everything downstream (normals, projections, derivative sums) runs in T.
-  const double t0x = pose[3 * i], t0y = pose[3 * i + 1], t1x = pose[3 * j], t1y = pose[3 * j + 1];
-  double c0d, s0d, c1d, s1d;
-  sincos(pose[3 * i + 2], &s0d, &c0d);
-  sincos(pose[3 * j + 2], &s1d, &c1d);
-  const T c0 = (T)c0d, s0 = (T)s0d, c1 = (T)c1d, s1 = (T)s1d;
-  const T cf = T(corr), sd = T(std_dev);
-  const uint32_t oi = off[i], oj = off[j];
-  T S0 = 0, S1 = 0, G0[6] = {0, 0, 0, 0, 0, 0}, G1[6] = {0, 0, 0, 0, 0, 0};
-  for (unsigned long long m = m0 + lane; m < m1; m += 32) {
-    const uint32_t k = kk[m], q = idx[m];
-    const float2 P0 = __ldg(pts + oi + k), N0 = __ldg(nrm + oi + k), P1 = __ldg(pts + oj + q), N1 = __ldg(nrm + oj + q);
-    // rotated (not translated) points and normals
-    const double r0xd = c0d * P0.x - s0d * P0.y, r0yd = s0d * P0.x + c0d * P0.y;
-    const double r1xd = c1d * P1.x - s1d * P1.y, r1yd = s1d * P1.x + c1d * P1.y;
-    const T r0x = (T)r0xd, r0y = (T)r0yd, r1x = (T)r1xd, r1y = (T)r1yd;
-    const T n0x = c0 * T(N0.x) - s0 * T(N0.y), n0y = s0 * T(N0.x) + c0 * T(N0.y);
-    const T n1x = c1 * T(N1.x) - s1 * T(N1.y), n1y = s1 * T(N1.x) + c1 * T(N1.y);
-    const T dx = (T)((r1xd + t1x) - (r0xd + t0x)), dy = (T)((r1yd + t1y) - (r0yd + t0y));
-    const T u = n0x * dx + n0y * dy, v = n1x * dx + n1y * dy;
-    const T a = u * cf / sd, bb = v * cf / sd;
-    S0 += a * a; S1 += bb * bb;
-    // perp(w) = (-w.y, w.x) = d/dtheta of a rotated vector
-    // du/dth0 = perp(n0g).d - n0g.perp(r0) ; du/dth1 = n0g.perp(r1)
-    const T du_t0 = (-n0y * dx + n0x * dy) - (n0x * (-r0y) + n0y * r0x);
-    const T du_t1 = n0x * (-r1y) + n0y * r1x;
-    // dv/dth0 = -n1g.perp(r0) ; dv/dth1 = perp(n1g).d + n1g.perp(r1)
-    const T dv_t0 = -(n1x * (-r0y) + n1y * r0x);
-    const T dv_t1 = (-n1y * dx + n1x * dy) + (n1x * (-r1y) + n1y * r1x);
-    const T w = cf / sd;
-    const T aw = a * w, bw = bb * w;
-    G0[0] += aw * (-n0x); G0[1] += aw * (-n0y); G0[2] += aw * du_t0; G0[3] += aw * n0x; G0[4] += aw * n0y; G0[5] += aw * du_t1;
-    G1[0] += bw * (-n1x); G1[1] += bw * (-n1y); G1[2] += bw * dv_t0; G1[3] += bw * n1x; G1[4] += bw * n1y; G1[5] += bw * dv_t1;
+  const double2 ti = __ldg(trig + 2 * i), xi = __ldg(trig + 2 * i + 1), tj = __ldg(trig + 2 * j), xj = __ldg(trig + 2 * j + 1);   // (cos, sin), (x, y)
+  const double tdx = xj.x - xi.x, tdy = xj.y - xi.y;
+  const T w = T(corr) / T(std_dev);
+  const float2* __restrict__ pi = pts + off[i]; const float2* __restrict__ ni = nrm + off[i];
+  const float2* __restrict__ pj = pts + off[j]; const float2* __restrict__ nj = nrm + off[j];
+  StfAccum<T> A;
+  A.S0 = 0; A.S1 = 0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) { A.G0[q] = 0; A.G1[q] = 0; }
+  unsigned long long m = m0 + lane;
+  // two matches per lane and iteration: all eight gathers are issued before the first use
+  for (; m + 32 < m1; m += 64) {
+    const uint32_t ka = __ldg(kk + m), qa = __ldg(idx + m), kb = __ldg(kk + m + 32), qb = __ldg(idx + m + 32);
+    const float2 P0a = __ldg(pi + ka), N0a = __ldg(ni + ka), P1a = __ldg(pj + qa), N1a = __ldg(nj + qa);
+    const float2 P0b = __ldg(pi + kb), N0b = __ldg(ni + kb), P1b = __ldg(pj + qb), N1b = __ldg(nj + qb);
+    stf_accumulate<T>(A, P0a, N0a, P1a, N1a, ti.x, ti.y, tj.x, tj.y, tdx, tdy, w);
+    stf_accumulate<T>(A, P0b, N0b, P1b, N1b, ti.x, ti.y, tj.x, tj.y, tdx, tdy, w);
+  }
+  if (m < m1) {
+    const uint32_t ka = __ldg(kk + m), qa = __ldg(idx + m);
+    stf_accumulate<T>(A, __ldg(pi + ka), __ldg(ni + ka), __ldg(pj + qa), __ldg(nj + qa), ti.x, ti.y, tj.x, tj.y, tdx, tdy, w);
   }
   // fixed-order butterfly: every lane ends with the same sums
   for (int o = 16; o; o >>= 1) {
-    S0 += __shfl_xor_sync(0xffffffffu, S0, o); S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+    A.S0 += __shfl_xor_sync(0xffffffffu, A.S0, o); A.S1 += __shfl_xor_sync(0xffffffffu, A.S1, o);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) { G0[q] += __shfl_xor_sync(0xffffffffu, G0[q], o); G1[q] += __shfl_xor_sync(0xffffffffu, G1[q], o); }
+    for (int q = 0; q < 6; ++q) { A.G0[q] += __shfl_xor_sync(0xffffffffu, A.G0[q], o); A.G1[q] += __shfl_xor_sync(0xffffffffu, A.G1[q], o); }
   }
-  if (lane == 0) {
-    const T M = (T)(double)(m1 - m0);
-    double r[2], Ji[6], Jj[6];
-    T r0 = 0, r1 = 0, k0 = 0, k1 = 0;
-    if (S0 != T(0)) { r0 = sqrt(S0 / M); k0 = T(1) / (M * r0); }
-    if (S1 != T(0)) { r1 = sqrt(S1 / M); k1 = T(1) / (M * r1); }
-    r[0] = (double)r0; r[1] = (double)r1;
+  // every lane holds the block's sums: lanes share the epilogue (lane q < 12 owns Jacobian entry q)
+  const T M = (T)(double)(m1 - m0);
+  T r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  if (A.S0 != T(0)) { r0 = sqrt(A.S0 / M); k0 = T(1) / (M * r0); }
+  if (A.S1 != T(0)) { r1 = sqrt(A.S1 / M); k1 = T(1) / (M * r1); }
+  double r[2], Ji[6], Jj[6];
+  r[0] = (double)r0; r[1] = (double)r1;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      Ji[q] = (double)(G0[q] * k0); Ji[3 + q] = (double)(G1[q] * k1);
-      Jj[q] = (double)(G0[3 + q] * k0); Jj[3 + q] = (double)(G1[3 + q] * k1);
-    }
-    if (r_out) { r_out[2 * b] = r[0]; r_out[2 * b + 1] = r[1]; }
-    if (J_out) { double* J = J_out + 12 * b;
+  for (int q = 0; q < 3; ++q) {
+    Ji[q] = (double)(A.G0[q] * k0); Ji[3 + q] = (double)(A.G1[q] * k1);
+    Jj[q] = (double)(A.G0[3 + q] * k0); Jj[3 + q] = (double)(A.G1[3 + q] * k1);
+  }
+  if (lane == 0 && r_out) { r_out[2 * b] = r[0]; r_out[2 * b + 1] = r[1]; }
+  if (J_out && lane < 12) {
+    double v = 0;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) { J[q] = Ji[q]; J[6 + q] = Jj[q]; } }
-    if (want_neq) {
-      accumulate_binary<2>(neq, off_slot0 + b, i, j, r, Ji, Jj);
+    for (int q = 0; q < 6; ++q) { if (lane == (uint32_t)q) v = Ji[q]; if (lane == (uint32_t)(6 + q)) v = Jj[q]; }
+    J_out[12 * b + lane] = v;                                       // one coalesced 96 B store per block
+  }
+  if (want_neq) {
+    // lanes 0..8: H_ii entry, 9..17: H_jj entry, 18..20: g_i, 21..23: g_j, 24: cost; H_off by lanes 0..8 as plain stores
+    const uint32_t e = lane < 9 ? lane : lane < 18 ? lane - 9 : 0, a3 = e / 3, b3 = e % 3;
+    if (lane < 18) {
+      const double* Jx = lane < 9 ? Ji : Jj;
+      double h = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double ja = 0, jb = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { if (a3 == (uint32_t)c) ja = Jx[3 * q + c]; if (b3 == (uint32_t)c) jb = Jx[3 * q + c]; }
+        h += ja * jb;
+      }
+      atomicAdd(neq.H_diag + 9 * (size_t)(lane < 9 ? i : j) + e, h);
+      if (lane < 9 && neq.H_off) {
+        double ho = 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          double ja = 0, jb = 0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { if (a3 == (uint32_t)c) ja = Ji[3 * q + c]; if (b3 == (uint32_t)c) jb = Jj[3 * q + c]; }
+          ho += ja * jb;
+        }
+        neq.H_off[9 * (off_slot0 + b) + e] = ho;
+      }
+    } else if (lane < 24) {
+      const uint32_t c3 = (lane - 18) % 3;
+      const double* Jx = lane < 21 ? Ji : Jj;
+      double gq = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) if (c3 == (uint32_t)c) gq = Jx[c] * r[0] + Jx[3 + c] * r[1];
+      atomicAdd(neq.g + 3 * (size_t)(lane < 21 ? i : j) + c3, gq);
+    } else if (lane == 24) {
       const double c = 0.5 * (r[0] * r[0] + r[1] * r[1]);
       if (c != 0.0) atomicAdd(neq.cost, c);
     }
@@ -410,9 +480,12 @@ static int launch_all(hitl_ctx* ctx, double* d_r, double* d_J, const NeqOut& neq
   if (ctx->nb_stf) {
     const bool fs = ctx->stf_from_search;
     const uint64_t nb = ctx->nb_stf;
-    eval_stf_kernel<T><<<(uint32_t)((nb * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+    HITL_CUDA(ctx->d_trig.ensure(2 * (size_t)ctx->n_poses));
+    pose_trig_kernel<<<(ctx->n_poses + 255) / 256, 256, 0, ctx->stream>>>(pose, ctx->n_poses, ctx->d_trig.p);
+    HITL_LAUNCH_CHECK("pose_trig_kernel");
+    eval_stf_kernel<T><<<(uint32_t)((nb * 32 + kStfThreads - 1) / kStfThreads), kStfThreads, 0, ctx->stream>>>(
         ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, fs ? ctx->d_pair_i.p : ctx->d_blk_i.p, fs ? ctx->d_pair_j.p : ctx->d_blk_j.p,
-        (const unsigned long long*)(fs ? ctx->d_pair_off.p : ctx->d_blk_off.p), fs ? ctx->d_k.p : ctx->d_blk_k.p, fs ? ctx->d_idx.p : ctx->d_blk_idx.p, pose, nb,
+        (const unsigned long long*)(fs ? ctx->d_pair_off.p : ctx->d_blk_off.p), fs ? ctx->d_k.p : ctx->d_blk_k.p, fs ? ctx->d_idx.p : ctx->d_blk_idx.p, ctx->d_trig.p, nb,
         ctx->stf_std, ctx->stf_corr, d_r ? d_r + ro : nullptr, d_J ? d_J + jo : nullptr, neq, want_neq, (size_t)ctx->nb_odo);
     HITL_LAUNCH_CHECK("eval_stf_kernel");
   }

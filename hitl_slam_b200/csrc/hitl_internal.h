@@ -58,15 +58,16 @@ struct hitl_ctx {
   hitl::DevBuf<uint32_t> d_off;
   hitl::DevBuf<float2> d_pts, d_nrm;
   hitl::DevBuf<float4> d_aabb;           // robot-frame AABB per scan (minx, miny, maxx, maxy)
-  // tiles: 32 consecutive points of one scan
+  // tiles: up to 32 consecutive points of one scan
   uint32_t n_tiles = 0;
-  hitl::DevBuf<uint32_t> d_tile_scan, d_tile_k0, d_tile_begin;   // tile -> scan, first point; scan -> first tile
-  std::vector<uint32_t> h_tile_begin;
+  hitl::DevBuf<uint32_t> d_tile_scan, d_tile_k0, d_tile_begin;   // tile -> scan, first point | length << 16; scan -> first tile
+  std::vector<uint32_t> h_tile_scan, h_tile_kl, h_tile_begin;    // host mirrors of the three tables
+  uint32_t tiling_splits = 0;                                    // heavy tiles split so far (adaptive tiling)
+  uint32_t split_rounds = 0, split_lo = 0, split_hi = 0;         // split rounds done for the source range [split_lo, split_hi)
+  int adaptive_tiling = 1;
   // scheduling hint of the search: tiles sorted by the cycles the previous call spent on them
   hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys;
   hitl::DevBuf<uint8_t> d_sort_tmp;
-  bool order_valid = false, iota_valid = false;
-  uint32_t order_lo = 0, order_hi = 0;
 
   // ---- trees ----
   bool have_trees = false;
@@ -127,6 +128,7 @@ struct hitl_ctx {
   hitl::DevBuf<uint8_t> d_p2l_v;
   float p2l_std = 1, p2l_corr = 1;
   hitl::DevBuf<double> d_r, d_J, d_neq, d_hoff;
+  hitl::DevBuf<double2> d_trig;          // per pose (cos, sin), (x, y) of the current evaluation point
 
   // pinned staging for small read-backs
   uint64_t* h_pinned = nullptr;          // 64 x u64
@@ -147,6 +149,9 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
     if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, name);  \
   } while (0)
 
+int build_tiling(hitl_ctx* ctx, uint32_t max_len);
+int upload_tiling(hitl_ctx* ctx);
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, uint32_t lo, uint32_t hi, uint64_t limit, std::vector<uint32_t>* est);
 // host tree builder (kdtree_build.cpp)
 void build_flat_kdtree(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out);
 }  // namespace hitl

@@ -278,8 +278,8 @@ __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uin
                                        uint32_t* __restrict__ occ) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
-  const uint32_t i = tile_scan[tile], k = tile_k0[tile] + lane;
-  if (k >= off[i + 1] - off[i]) return;
+  const uint32_t i = tile_scan[tile], kl = tile_k0[tile], k = (kl & 0xFFFFu) + lane;
+  if (lane >= (kl >> 16) || k >= off[i + 1] - off[i]) return;
   const GridRec g = grid[i];
   const float2 p = pts[off[i] + k];
   uint32_t cx, cy;
@@ -357,10 +357,10 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile == 0xFFFFFFFFu) break;
     const long long t_begin = clock64();
-    const uint32_t i = P.tile_scan[tile], k0 = P.tile_k0[tile];
+    const uint32_t i = P.tile_scan[tile], kl = P.tile_k0[tile], k0 = kl & 0xFFFFu;
     const uint32_t i_off = P.rec[i].off, i_n = P.rec[i].n;
     const uint32_t k = k0 + lane;
-    const bool valid = k < i_n && (k % P.skip) == 0;
+    const bool valid = lane < (kl >> 16) && k < i_n && (k % P.skip) == 0;
     float2 p = make_float2(0.f, 0.f), nv = make_float2(0.f, 0.f);
     if (valid) { p = P.pts[i_off + k]; nv = P.nrm[i_off + k]; }
     const double theta_i = P.pose[3 * i + 2];
@@ -522,16 +522,13 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
       const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
       atomicAdd(P.pose_work + i, dt);
       P.tile_work[tile] = (uint32_t)min(dt >> 6, 0xFFFFFFFFull);
+      atomicAdd(P.counters + 7, dt >> 6);
+      atomicMax(P.counters + 8, dt >> 6);
     }
     __syncwarp();
   }
   for (int o = 16; o; o >>= 1) n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
   if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); }
-}
-
-__global__ void iota_kernel(uint32_t* out, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -546,7 +543,7 @@ constexpr uint32_t kDropped = 0xFFFFFFFFu;
 
 struct OrderParams {
   const uint32_t* __restrict__ raw_j; const uint32_t* __restrict__ raw_k; const uint32_t* __restrict__ raw_idx;
-  const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ off;
+  const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ tile_k0; const uint32_t* __restrict__ off;
   uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
   uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
   uint32_t* kept;                     // gridDim.x * n_poses: kept target poses of the pose being placed (pass 1)
@@ -601,7 +598,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
     // -- histogram over j (tile lists are sorted by j: first/last record bound the range) --
     uint32_t jlo = 0xFFFFFFFFu, jhi = 0;
     for (uint32_t t = tb; t < te; ++t) {
-      const uint32_t c = P.tile_cnt[t], base = seg + (t - tb) * 32u * (uint32_t)P.cap;
+      const uint32_t c = P.tile_cnt[t], base = seg + (P.tile_k0[t] & 0xFFFFu) * (uint32_t)P.cap;
       for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
         const uint32_t j = P.raw_j[base + u];
         atomicAdd(&cntj[j], 1u);
@@ -642,7 +639,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
         //    in ascending k order, so pair (i, j) is the concatenation over tiles of each tile's run of j.
         //    Lanes bisect "their" tile for the run, a warp scan turns run lengths into offsets. --
         const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const uint32_t ntile = te - tb, tile_stride = 32u * (uint32_t)P.cap;
+        const uint32_t ntile = te - tb;
         for (uint32_t e = wid; e < tot_p; e += kOrderThreads / 32) {
           const uint32_t j = keptj[e];
           unsigned long long dst = s_off_m + cntj[j];
@@ -651,7 +648,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
             uint32_t lb = 0, len = 0, base = 0;
             if (t < ntile) {
               const uint32_t c = P.tile_cnt[tb + t];
-              base = seg + t * tile_stride;
+              base = seg + (P.tile_k0[tb + t] & 0xFFFFu) * (uint32_t)P.cap;
               uint32_t lo = 0, hi = c;                                   // lower_bound(j)
               while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (P.raw_j[base + mid] < j) lo = mid + 1; else hi = mid; }
               lb = lo;
@@ -873,7 +870,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   if (rec_cap >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: n_points * cap exceeds 2^32 records");
   HITL_CUDA(ctx->d_raw_j.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_k.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_idx.ensure(rec_cap));
   HITL_CUDA(ctx->d_tile_cnt.ensure(ctx->n_tiles));
-  HITL_CUDA(ctx->d_counters.ensure(8));
+  HITL_CUDA(ctx->d_counters.ensure(16));
   HITL_CUDA(ctx->d_pose_cnt.ensure(2 * (size_t)n + 2));
   HITL_CUDA(ctx->d_pose_work.ensure(n));
   HITL_CUDA(ctx->d_k.ensure(rec_cap)); HITL_CUDA(ctx->d_idx.ensure(rec_cap));
@@ -881,7 +878,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(ctx->d_pair_i.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_j.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_off.ensure(pair_cap + 1));
 
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  HITL_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(uint64_t), ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_pose_work.p, 0, sizeof(uint64_t) * n, ctx->stream));
   int rc = upload_poses_and_prep(ctx, pose_array, o->point_match_threshold);
   if (rc) return rc;
@@ -895,12 +892,22 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.raw_j = ctx->d_raw_j.p; P.raw_k = ctx->d_raw_k.p; P.raw_idx = ctx->d_raw_idx.p; P.tile_cnt = ctx->d_tile_cnt.p;
   P.counters = (unsigned long long*)ctx->d_counters.p;
   P.pose_work = (unsigned long long*)ctx->d_pose_work.p;
-  HITL_CUDA(ctx->d_tile_work.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_order.ensure(ctx->n_tiles));
   P.tile_work = ctx->d_tile_work.p;
-  // the order computed after the previous search of the same tile range is a pure scheduling hint
-  P.tile_order = (ctx->order_valid && ctx->order_lo == P.tile_lo && ctx->order_hi == P.tile_hi && !o->disable_culling) ? ctx->d_tile_order.p : nullptr;
+  P.tile_order = nullptr;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
+  if (n_tiles > 1 && !o->disable_culling) {
+    // Heaviest-first ticket order from the latest per-tile cost estimates (measured by the previous search,
+    // inherited by the children of split tiles, 0 for tiles never searched): a scheduling hint only.
+    size_t tmp_bytes = 0;
+    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
+                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
+    HITL_CUDA(ctx->d_sort_tmp.ensure(tmp_bytes));
+    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(ctx->d_sort_tmp.p, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
+                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
+    ctx->launches += 1;
+    P.tile_order = ctx->d_tile_order.p;
+  }
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (n_tiles) {
     // persistent grid: one wave of CTAs (a multiple of the SM count), warps pull tiles from a ticket
@@ -912,27 +919,10 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (n_tiles > 1 && !o->disable_culling) {
-    // next call's ticket order: this call's tiles sorted by measured cycles, descending
-    HITL_CUDA(ctx->d_tile_iota.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_keys.ensure(ctx->n_tiles));
-    if (!ctx->iota_valid) {
-      iota_kernel<<<(ctx->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_tile_iota.p, ctx->n_tiles);
-      HITL_LAUNCH_CHECK("iota_kernel");
-      ctx->iota_valid = true;
-    }
-    size_t tmp_bytes = 0;
-    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
-                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
-    HITL_CUDA(ctx->d_sort_tmp.ensure(tmp_bytes));
-    HITL_CUDA(cub::DeviceRadixSort::SortPairsDescending(ctx->d_sort_tmp.p, tmp_bytes, ctx->d_tile_work.p + P.tile_lo, ctx->d_tile_keys.p, ctx->d_tile_iota.p + P.tile_lo,
-                                                        ctx->d_tile_order.p, (int)n_tiles, 0, 32, ctx->stream));
-    ctx->launches += 1;
-    ctx->order_valid = true; ctx->order_lo = P.tile_lo; ctx->order_hi = P.tile_hi;
-  }
 
   OrderParams Q;
   Q.raw_j = ctx->d_raw_j.p; Q.raw_k = ctx->d_raw_k.p; Q.raw_idx = ctx->d_raw_idx.p; Q.tile_cnt = ctx->d_tile_cnt.p;
-  Q.tile_begin = ctx->d_tile_begin.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
+  Q.tile_begin = ctx->d_tile_begin.p; Q.tile_k0 = ctx->d_tile_k0.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
   Q.min_corr = o->min_inter_pose_correspondence;
   const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)ctx->sm_count * 8);
   HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
@@ -948,18 +938,51 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   stf_order_kernel<1><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<1>");
   HITL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-  HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
   inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5];
+  const uint64_t work_sum = ctx->h_pinned[7];
   // terminating offset of the CSR
   HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_search, ctx->ev[1], ctx->ev[2]));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_total, ctx->ev[0], ctx->ev[3]));
   ctx->n_pairs = inf.n_pairs; ctx->n_matches = inf.n_matches; ctx->have_stf = true;
+  inf.n_tiles = n_tiles; inf.n_tiles_next = n_tiles;
   if (info) *info = inf;
+  // Adaptive tiling for the NEXT call: a tile is a sequential loop over the target poses, so the heaviest
+  // tile bounds the kernel from below; when it exceeds its fair share of this shard by far (small maps,
+  // shards of a multi-GPU run) it is split into shorter tiles.  Scheduling only: results do not depend on it.
+  if (ctx->adaptive_tiling && n_tiles > 1 && !o->disable_culling) {
+    const uint64_t slots = (uint64_t)ctx->sm_count * 64;
+    const uint64_t fair = work_sum / slots + 1;                              // cycles/64 per resident warp if perfectly packed
+    const uint64_t limit = std::max<uint64_t>(fair / 2, 4096);               // never split tiles cheaper than ~0.13 ms
+    const uint64_t h_max = ctx->h_pinned[8];                                 // heaviest tile of this call
+    if (ctx->split_lo != lo || ctx->split_hi != hi) { ctx->split_lo = lo; ctx->split_hi = hi; ctx->split_rounds = 0; }
+    if (h_max > 2 * limit && ctx->split_rounds < 3) {
+      ++ctx->split_rounds;
+      std::vector<uint32_t> h_work(n_tiles), est;
+      HITL_CUDA(cudaMemcpy(h_work.data(), ctx->d_tile_work.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+      if (split_heavy_tiles(ctx, h_work, P.tile_lo, P.tile_hi, limit, &est)) {
+        rc = upload_tiling(ctx);
+        if (rc) return rc;
+        const uint32_t new_lo = ctx->h_tile_begin[lo], new_hi = ctx->h_tile_begin[hi], nn = new_hi - new_lo;
+        if (info) info->n_tiles_next = nn;
+        // the heaviest-first schedule survives the re-tiling: children inherit their parent's share of the work
+        HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_work.p, est.data(), 4 * (size_t)ctx->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
+        HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // est is a local
+      }
+    }
+  }
   return HITL_OK;
+}
+
+extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_debug_set_tiling: scans not set");
+  ctx->adaptive_tiling = adaptive;
+  return build_tiling(ctx, max_len);
 }
 
 extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx) {
@@ -985,6 +1008,16 @@ extern "C" int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose) {
   if (!ctx->have_stf || !ctx->d_pose_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf_work: no search result");
   if (!work_per_pose && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_get_stf_work: null output");
   if (ctx->n_poses) HITL_CUDA(cudaMemcpyAsync(work_per_pose, ctx->d_pose_work.p, 8 * (size_t)ctx->n_poses, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+extern "C" int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32_t* n_tiles_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_stf || !ctx->d_tile_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_debug_tile_work: no search result");
+  if (n_tiles_out) *n_tiles_out = ctx->n_tiles;
+  const uint32_t n = std::min(cap, ctx->n_tiles);
+  if (n && work_out) HITL_CUDA(cudaMemcpyAsync(work_out, ctx->d_tile_work.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }

@@ -110,6 +110,8 @@ typedef struct {
   uint64_t n_tile_pairs;  /* (32-point source tile, target pose) pairs that survived the world-frame box test */
   float ms_search;        /* device time of the search kernel alone (CUDA events on the ctx stream) */
   float ms_total;         /* device time of the whole call: pose prep + search + ordering/compaction */
+  uint32_t n_tiles;       /* work units (runs of <= 32 source points) the search kernel scheduled in this call */
+  uint32_t n_tiles_next;  /* ... and after the adaptive split of heavy tiles that this call's measurements triggered */
 } hitl_stf_info;
 
 /* Correspondences between source poses [src_lo, src_hi) ∩ [min_pose, max_pose] and all target
@@ -201,6 +203,12 @@ int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
 /* ---- diagnostics ------------------------------------------------------------------------- */
 /* Device evaluation of the library's sinf/cosf (bit-identical to glibc 2.39's x86-64 FMA variant;
  * csrc/hitl_math.h) and of RelativePoseTransform (JointOptimization.cpp:296-305) for parity tests. */
+/* SM cycles / 64 the last hitl_find_stf spent on each 32-point tile (tiles outside the searched range keep
+ * stale values); profiling aid for the tile scheduler. */
+int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32_t* n_tiles_out);
+/* Re-cuts every scan into tiles of at most max_len (1..32) points and switches the automatic splitting of
+ * heavy tiles on or off.  The tiling is a scheduling choice; parity tests use this to prove it. */
+int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive);
 int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out);
 int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src,
                              const uint32_t* dst, float* out6);

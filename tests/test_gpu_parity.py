@@ -169,6 +169,41 @@ def test_find_stf_is_independent_of_the_tile_schedule(gpu, oracle, maps):
     assert_same_stf(gpu.find_stf(poses), ref)
 
 
+@pytest.mark.parametrize("max_len", [32, 7, 4, 1])
+def test_find_stf_is_independent_of_the_tiling(gpu, oracle, maps, max_len):
+    """Tiles (the unit of work of the search) may be any partition of a scan into runs of <= 32 points."""
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    ref = S.find_stf(poses)
+    try:
+        gpu.debug_set_tiling(max_len, adaptive=False)
+        out = gpu.find_stf(poses)
+        assert_same_stf(out, ref)
+        assert out["n_queries"] == ref["n_queries"]
+        assert_same_stf(gpu.find_stf(poses, src_lo=20, src_hi=77), S.find_stf(poses, src_lo=20, src_hi=77))
+    finally:
+        gpu.debug_set_tiling(32, adaptive=True)
+
+
+def test_find_stf_adaptive_tile_splitting_keeps_results(gpu, oracle, maps):
+    """Heavy tiles are split after a search that was dominated by them (here: forced by a tiny shard);
+    later searches over any range still return the reference's lists."""
+    g = maps("c1")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    ref = S.find_stf(poses, src_lo=100, src_hi=140)
+    for _ in range(4):                                   # each call may split further
+        assert_same_stf(gpu.find_stf(poses, src_lo=100, src_hi=140), ref)
+    full = S.find_stf(poses)
+    for _ in range(2):
+        out = gpu.find_stf(poses)
+        assert_same_stf(out, full)
+        assert out["n_queries"] == full["n_queries"]
+
+
 def test_find_stf_work_feedback_covers_exactly_the_searched_sources(gpu, maps):
     g = maps("small")
     load_map(gpu, g)
