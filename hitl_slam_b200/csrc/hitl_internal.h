@@ -19,10 +19,12 @@ struct __align__(16) PoseRec {
   uint32_t gdim;                  // nx | ny << 16  (0 = empty scan)
   uint32_t goff;                  // first word of the scan's bitmap
   float c, s;                     // cos / sin of the pose angle
-  uint32_t pad;
+  uint32_t foff;                  // first word of the scan's FINE bitmap (kFineCells x kFineCells cells per coarse cell), kNoFine = none
 };
+constexpr uint32_t kNoFine = 0xFFFFFFFFu;
+constexpr int kFineCells = 4;     // fine cell = coarse cell / 4  (power of two: the fine 1/cell is exact)
 // Per-scan occupancy grid descriptor (host-built from the scan AABBs for a given threshold).
-struct GridRec { float gx0, gy0, ginv; uint32_t gdim, goff; };
+struct GridRec { float gx0, gy0, ginv; uint32_t gdim, goff, foff; };
 static_assert(sizeof(PoseRec) == 64, "PoseRec must be 64 bytes");
 
 template <typename T> struct DevBuf {
@@ -84,7 +86,9 @@ struct hitl_ctx {
   std::vector<float> h_aabb;             // 4 per scan
   hitl::DevBuf<hitl::GridRec> d_grid;
   hitl::DevBuf<uint32_t> d_occ;
+  hitl::DevBuf<uint32_t> d_occ_fine;     // second level: cell = thr / 4, consulted only for points that pass the coarse level
   bool grid_valid = false;
+  int fine_occupancy = 1;                // second-level bitmaps on (hitl_debug_set_fine_occupancy)
   float grid_thr = 0.f;
 
   // ---- search results ----

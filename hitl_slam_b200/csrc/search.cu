@@ -235,12 +235,12 @@ __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* 
   const Aff2 a = pose_affine(pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]);
   const Aff2 inv = affine_inverse(a);
   PoseRec r;
-  r.c = a.m00; r.s = a.m10; r.pad = 0;
+  r.c = a.m00; r.s = a.m10;
   r.i00 = inv.m00; r.i01 = inv.m01; r.i10 = inv.m10; r.i11 = inv.m11; r.itx = inv.tx; r.ity = inv.ty;
   const float4 b = aabb[i];
   r.off = off[i]; r.n = off[i + 1] - off[i];
   const GridRec g = grid[i];
-  r.gx0 = g.gx0; r.gy0 = g.gy0; r.ginv = g.ginv; r.gdim = g.gdim; r.goff = g.goff;
+  r.gx0 = g.gx0; r.gy0 = g.gy0; r.ginv = g.ginv; r.gdim = g.gdim; r.goff = g.goff; r.foff = g.foff;
   if (r.n == 0) {
     wbox[i] = make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
   } else {
@@ -264,13 +264,27 @@ __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* 
 // which is the same instruction sequence for points and queries).  Skipping the tree walk for
 // such a query is therefore exact: the walk would return FLT_MAX and change no state.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool grid_cell(const float gx0, const float gy0, const float ginv, const uint32_t gdim, float x, float y,
-                                          uint32_t* cx, uint32_t* cy) {
+__device__ __forceinline__ bool grid_cell_dims(const float gx0, const float gy0, const float ginv, const uint32_t nxi, const uint32_t nyi, float x,
+                                               float y, uint32_t* cx, uint32_t* cy) {
   const float fx = fmul(fsub(x, gx0), ginv), fy = fmul(fsub(y, gy0), ginv);
-  const float nx = (float)(gdim & 0xFFFFu), ny = (float)(gdim >> 16);
+  const float nx = (float)nxi, ny = (float)nyi;
   if (!(fx >= 0.0f && fy >= 0.0f && fx < nx && fy < ny)) return false;
   *cx = (uint32_t)fx; *cy = (uint32_t)fy;
   return true;
+}
+__device__ __forceinline__ bool grid_cell(const float gx0, const float gy0, const float ginv, const uint32_t gdim, float x, float y,
+                                          uint32_t* cx, uint32_t* cy) {
+  return grid_cell_dims(gx0, gy0, ginv, gdim & 0xFFFFu, gdim >> 16, x, y, cx, cy);
+}
+// Second level: the same grid with kFineCells x kFineCells cells per coarse cell (same origin; 1/cell scaled by a power
+// of two, so exact).  thr = kFineCells * cell / (1 + 2^-9): |qx - px| < thr puts q's fine cell index within
+// +-kFineCells of p's (the 2^-9 slack, 0.0078 fine cells, dominates the rounding of the cell formula, < 1e-3 cells up to
+// 16k cells per axis), and when |dx| = kFineCells the real |qx - px| exceeds (kFineCells - 1) cells, which caps |dy| at
+// kFineCells - 1.  Every point marks that footprint (9 x 9 cells minus the four corners); a query with an unmarked fine
+// cell has no in-radius node, exactly as for the coarse level.
+__device__ __forceinline__ bool fine_cell(const float gx0, const float gy0, const float ginv, const uint32_t gdim, float x, float y,
+                                          uint32_t* cx, uint32_t* cy) {
+  return grid_cell_dims(gx0, gy0, fmul(ginv, (float)kFineCells), (gdim & 0xFFFFu) * kFineCells, (gdim >> 16) * kFineCells, x, y, cx, cy);
 }
 
 __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, const uint32_t* __restrict__ tile_scan,
@@ -294,6 +308,33 @@ __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uin
     }
 }
 
+__global__ void occupancy_fine_build_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, const uint32_t* __restrict__ tile_scan,
+                                            const uint32_t* __restrict__ tile_k0, uint32_t n_tiles, const GridRec* __restrict__ grid,
+                                            uint32_t* __restrict__ occ) {
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const uint32_t i = tile_scan[tile], kl = tile_k0[tile], k = (kl & 0xFFFFu) + lane;
+  if (lane >= (kl >> 16) || k >= off[i + 1] - off[i]) return;
+  const GridRec g = grid[i];
+  if (g.foff == kNoFine) return;
+  const float2 p = pts[off[i] + k];
+  uint32_t cx, cy;
+  if (!fine_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  const int nx = (int)((g.gdim & 0xFFFFu) * kFineCells), ny = (int)((g.gdim >> 16) * kFineCells);
+  for (int dy = -kFineCells; dy <= kFineCells; ++dy) {
+    const int y = (int)cy + dy;
+    if (y < 0 || y >= ny) continue;
+    const int r = (dy == -kFineCells || dy == kFineCells) ? kFineCells - 1 : kFineCells;
+    const int xa = max((int)cx - r, 0), xb = min((int)cx + r, nx - 1);
+    if (xa > xb) continue;
+    const uint64_t b0 = (uint64_t)y * (uint32_t)nx + (uint32_t)xa, b1 = b0 + (uint32_t)(xb - xa);
+    const uint64_t w0 = b0 >> 5, w1 = b1 >> 5;                                  // a row of <= 9 bits spans at most two words
+    const uint32_t lo_mask = 0xFFFFFFFFu << (b0 & 31), hi_mask = 0xFFFFFFFFu >> (31 - (b1 & 31));
+    if (w0 == w1) atomicOr(occ + g.foff + w0, lo_mask & hi_mask);
+    else { atomicOr(occ + g.foff + w0, lo_mask); atomicOr(occ + g.foff + w1, hi_mask); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: the search.  Persistent warps; each warp pulls 32-point source tiles from a global counter.
 //
@@ -315,7 +356,7 @@ struct SearchParams {
   const float2* __restrict__ pts; const float2* __restrict__ nrm;
   const float4* __restrict__ node_pm; const float2* __restrict__ node_nn;
   const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
-  const uint32_t* __restrict__ occ;
+  const uint32_t* __restrict__ occ; const uint32_t* __restrict__ occ_fine;
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
   uint32_t tile_lo, tile_hi;          // tiles of the source shard
   uint32_t jmin, jmax;                // inclusive target range
@@ -335,7 +376,9 @@ constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
 
 struct __align__(16) WarpShared {
   uint4 rec[32][3];        // per candidate of the current block of 32 target poses: T_ij, scan size, occupancy grid descriptor
-  uint32_t queue[kQueueCap];   // item = owner lane | j << 5
+  uint32_t queue[kQueueCap];   // stage A: items that passed the coarse occupancy level; item = owner lane | j << 5
+  uint32_t wq[kQueueCap];      // stage B: items that also passed the fine level, with their query point in frame j
+  float wqx[kQueueCap], wqy[kQueueCap];
   uint32_t cnt[32];        // matches per lane's point
   uint32_t exec_last[32];  // j that filled the cap (kNotCapped otherwise)
 };
@@ -380,30 +423,64 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
     }
     const uint32_t out_base = (i_off + k0) * (uint32_t)P.cap;   // this tile's private record region
     uint32_t wcount = 0;                                        // records written by the warp
-    uint32_t qn = 0;                                            // queued items
+    uint32_t qn = 0, qw = 0;                                    // queued items: stage A (coarse-passed), stage B (to walk)
     bool active = valid;
     W.cnt[lane] = 0; W.exec_last[lane] = kNotCapped;
     __syncwarp();
 
-    // Walks one batch of up to 32 queued items (all lanes busy) and commits it in queue order.
-    auto drain = [&](uint32_t nitems) {
+    // Stage A -> B: all lanes take one coarse-passed item each, form T_ij and the query point in frame j and test the
+    // FINE occupancy level; survivors are appended to the walk queue in the same (j, lane) order.
+    auto filter = [&](uint32_t nitems) {
       const bool item = lane < nitems;
       const uint32_t it = item ? W.queue[lane] : 0u;
       const uint32_t o = it & 31u, j = it >> 5;
-      // point / normal of the owning lane
       const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
+      bool pass = false; float qx = 0.f, qy = 0.f;
+      if (item && W.cnt[o] < (uint32_t)P.cap) {
+        const PoseRec rj = P.rec[j];
+        Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+        const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
+        affine_apply(T, opx, opy, &qx, &qy);
+        pass = true;
+        if (!P.no_cull && rj.foff != kNoFine) {
+          uint32_t cx, cy;
+          pass = fine_cell(rj.gx0, rj.gy0, rj.ginv, rj.gdim, qx, qy, &cx, &cy);
+          if (pass) {
+            const uint64_t bit = (uint64_t)cy * ((rj.gdim & 0xFFFFu) * kFineCells) + cx;
+            pass = (__ldg(P.occ_fine + rj.foff + (bit >> 5)) >> (bit & 31)) & 1u;
+          }
+        }
+      }
+      const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+      if (pass) { const uint32_t slot = qw + __popc(pm & lt); W.wq[slot] = it; W.wqx[slot] = qx; W.wqy[slot] = qy; }
+      qw += __popc(pm);
+      // shift the remaining stage-A items to the front
+      const uint32_t rest = qn - nitems;
+      uint32_t a = 0, b = 0;
+      if (lane < rest) a = W.queue[nitems + lane];
+      if (lane + 32 < rest) b = W.queue[nitems + lane + 32];
+      __syncwarp();
+      if (lane < rest) W.queue[lane] = a;
+      if (lane + 32 < rest) W.queue[lane + 32] = b;
+      qn = rest;
+      __syncwarp();
+    };
+
+    // Walks one batch of up to 32 stage-B items (all lanes busy) and commits it in queue order.
+    auto drain = [&](uint32_t nitems) {
+      const bool item = lane < nitems;
+      const uint32_t it = item ? W.wq[lane] : 0u;
+      const float qx = item ? W.wqx[lane] : 0.f, qy = item ? W.wqy[lane] : 0.f;
+      const uint32_t o = it & 31u, j = it >> 5;
+      // normal of the owning lane
       const float onx = __shfl_sync(0xffffffffu, nv.x, o), ony = __shfl_sync(0xffffffffu, nv.y, o);
       bool ok = false; uint32_t tgt = 0;
       const uint32_t cnt_o = W.cnt[o];
       if (item && cnt_o < (uint32_t)P.cap) {
-        const PoseRec rj = P.rec[j];
-        Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
-        const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
-        float qx, qy;
-        affine_apply(T, opx, opy, &qx, &qy);
-        TreeRef t; t.pm = P.node_pm + rj.off; t.nn = P.node_nn + rj.off;
+        const uint2 on = *reinterpret_cast<const uint2*>(&P.rec[j].off);   // scan offset, size
+        TreeRef t; t.pm = P.node_pm + on.x; t.nn = P.node_nn + on.x;
         float best; uint32_t bpos;
-        nearest_point_normal(t, rj.n, qx, qy, P.thr, stack, 1, &best, &bpos);
+        nearest_point_normal(t, on.y, qx, qy, P.thr, stack, 1, &best, &bpos);
         ++n_trav;
         if (best < P.thr) {                                     // implies bpos valid: best < FLT_MAX only via an in-radius node
           // Rotation2Df(theta_j - theta_i) * normal  (JointOptimization.cpp:604-606)
@@ -430,14 +507,12 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
       wcount += __popc(cm);
       __syncwarp();
       // shift the remaining items to the front
-      const uint32_t rest = qn - nitems;
-      uint32_t a = 0, b = 0;
-      if (lane < rest) a = W.queue[nitems + lane];
-      if (lane + 32 < rest) b = W.queue[nitems + lane + 32];
+      const uint32_t rest = qw - nitems;
+      uint32_t a = 0; float ax = 0.f, ay = 0.f;
+      if (lane < rest) { a = W.wq[nitems + lane]; ax = W.wqx[nitems + lane]; ay = W.wqy[nitems + lane]; }
       __syncwarp();
-      if (lane < rest) W.queue[lane] = a;
-      if (lane + 32 < rest) W.queue[lane + 32] = b;
-      qn = rest;
+      if (lane < rest) { W.wq[lane] = a; W.wqx[lane] = ax; W.wqy[lane] = ay; }
+      qw = rest;
       active = valid && W.cnt[lane] < (uint32_t)P.cap;
       __syncwarp();
     };
@@ -496,13 +571,17 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
           qn += __popc(m);
           __syncwarp();
           if (qn >= 32) {
-            drain(32);
-            if (!__any_sync(0xffffffffu, active)) { all_done = true; break; }
+            filter(32);
+            if (qw >= 32) {
+              drain(32);
+              if (!__any_sync(0xffffffffu, active)) { all_done = true; break; }
+            }
           }
         }
       }
-      while (qn && !all_done) {
-        drain(qn < 32 ? qn : 32);
+      while ((qn || qw) && !all_done) {
+        if (qn && qw < 32) { filter(qn < 32 ? qn : 32); if ((qn && qw < 32) || qw == 0) continue; }
+        drain(qw < 32 ? qw : 32);
         if (!__any_sync(0xffffffffu, active)) all_done = true;
       }
     }
@@ -790,10 +869,11 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
   if (ctx->grid_valid && ctx->grid_thr == thr) return HITL_OK;
   const uint32_t n = ctx->n_poses;
   std::vector<GridRec> tab(n);
+  std::vector<uint64_t> fine_words(n, 0);
   const float c0 = thr * (1.0f + 1.0f / 512.0f);
   uint64_t words = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    GridRec g; g.gx0 = g.gy0 = 0.f; g.ginv = 0.f; g.gdim = 0; g.goff = 0;
+    GridRec g; g.gx0 = g.gy0 = 0.f; g.ginv = 0.f; g.gdim = 0; g.goff = 0; g.foff = kNoFine;
     if (ctx->h_off[i + 1] > ctx->h_off[i]) {
       const float* b = &ctx->h_aabb[4 * (size_t)i];
       const float ext = std::max(b[2] - b[0], b[3] - b[1]);
@@ -805,17 +885,35 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
       if (words >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "occupancy bitmaps exceed 2^32 words");
       g.goff = (uint32_t)words;
       words += ((uint64_t)nx * ny + 31) / 32;
+      g.foff = 0;
+      fine_words[i] = ((uint64_t)nx * kFineCells * ny * kFineCells + 31) / 32;
     }
     tab[i] = g;
   }
-  HITL_CUDA(ctx->d_grid.ensure(n)); HITL_CUDA(ctx->d_occ.ensure(words));
+  // second level (cell / kFineCells): offsets in words; dropped as a whole when it would not fit 32-bit word offsets
+  uint64_t fwords = 0;
+  for (uint32_t i = 0; i < n; ++i) fwords += fine_words[i];
+  const bool fine = ctx->fine_occupancy && fwords < 0xFFFFFFFFull;
+  fwords = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    tab[i].foff = (fine && fine_words[i]) ? (uint32_t)fwords : kNoFine;
+    if (fine) fwords += fine_words[i];
+  }
+  HITL_CUDA(ctx->d_grid.ensure(n)); HITL_CUDA(ctx->d_occ.ensure(words)); HITL_CUDA(ctx->d_occ_fine.ensure(fwords));
   if (n) HITL_CUDA(cudaMemcpyAsync(ctx->d_grid.p, tab.data(), sizeof(GridRec) * n, cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_occ.p, 0, 4 * (words ? words : 1), ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_occ_fine.p, 0, 4 * (fwords ? fwords : 1), ctx->stream));
   if (ctx->n_tiles) {
     const int threads = 128;
-    occupancy_build_kernel<<<(uint32_t)(((size_t)ctx->n_tiles * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
+    const uint32_t blocks = (uint32_t)(((size_t)ctx->n_tiles * 32 + threads - 1) / threads);
+    occupancy_build_kernel<<<blocks, threads, 0, ctx->stream>>>(
         ctx->d_pts.p, ctx->d_off.p, ctx->d_tile_scan.p, ctx->d_tile_k0.p, ctx->n_tiles, ctx->d_grid.p, ctx->d_occ.p);
     HITL_LAUNCH_CHECK("occupancy_build_kernel");
+    if (fine && fwords) {
+      occupancy_fine_build_kernel<<<blocks, threads, 0, ctx->stream>>>(
+          ctx->d_pts.p, ctx->d_off.p, ctx->d_tile_scan.p, ctx->d_tile_k0.p, ctx->n_tiles, ctx->d_grid.p, ctx->d_occ_fine.p);
+      HITL_LAUNCH_CHECK("occupancy_fine_build_kernel");
+    }
   }
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tab is a local
   ctx->grid_valid = true; ctx->grid_thr = thr;
@@ -885,7 +983,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
 
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
-  P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
+  P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
   P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
   P.jmin = jmin; P.jmax = jmax; P.thr = o->point_match_threshold; P.min_cos = o->min_cosine_angle; P.cap = cap;
   P.skip = o->num_skip_readings; P.no_cull = o->disable_culling;
@@ -983,6 +1081,12 @@ extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adapti
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_debug_set_tiling: scans not set");
   ctx->adaptive_tiling = adaptive;
   return build_tiling(ctx, max_len);
+}
+
+extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->fine_occupancy != (on ? 1 : 0)) { ctx->fine_occupancy = on ? 1 : 0; ctx->grid_valid = false; }
+  return HITL_OK;
 }
 
 extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx) {

@@ -209,6 +209,9 @@ int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32
 /* Re-cuts every scan into tiles of at most max_len (1..32) points and switches the automatic splitting of
  * heavy tiles on or off.  The tiling is a scheduling choice; parity tests use this to prove it. */
 int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive);
+/* Switches the second (fine, cell = threshold / 4) level of the occupancy cull on or off; the bitmaps are rebuilt by the
+ * next search.  Culling is result-preserving; parity tests compare both settings and disable_culling = 1. */
+int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
 int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out);
 int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src,
                              const uint32_t* dst, float* out6);

@@ -97,10 +97,12 @@ def test_find_stf_bit_exact(gpu, oracle, maps, name, normals):
     load_map(gpu, g)
     poses = g["poses"].astype(np.float64)
     ref = oracle.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(poses)
-    for cull in (0, 1):
+    for cull, fine in ((0, True), (0, False), (1, True)):
+        gpu.debug_set_fine_occupancy(fine)
         out = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=cull))
         assert_same_stf(out, ref)
         assert out["n_queries"] == ref["n_queries"]
+    gpu.debug_set_fine_occupancy(True)
     assert len(ref["pair_i"]) > 0 or normals == "faithful"
 
 
@@ -262,6 +264,12 @@ def test_find_stf_culling_is_result_preserving_at_scale(gpu, maps):
     b = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=1))
     assert_same_stf(a, b)
     assert a["n_queries"] == b["n_queries"] and a["n_traversals"] < b["n_traversals"]
+    # the second (fine) occupancy level only removes walks that would find nothing
+    gpu.debug_set_fine_occupancy(False)
+    c = gpu.find_stf(poses)
+    gpu.debug_set_fine_occupancy(True)
+    assert_same_stf(a, c)
+    assert a["n_queries"] == c["n_queries"] and a["n_traversals"] < c["n_traversals"] < b["n_traversals"]
     counts = np.diff(a["pair_off"].astype(np.int64))
     assert (counts > 10).all()
     # per source point at most `cap` matches over all pairs
