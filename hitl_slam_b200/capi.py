@@ -44,7 +44,7 @@ class StfOpts(C.Structure):
 class StfInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
                 ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float),
-                ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
+                ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
 
 
 class EvalLayout(C.Structure):
@@ -209,7 +209,7 @@ class HitlGpu:
         info = StfInfo()
         self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
         res = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
-                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, ms_search=info.ms_search, ms_total=info.ms_total,
+                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, n_coarse_pass=info.n_coarse_pass, n_in_radius=info.n_in_radius, ms_search=info.ms_search, ms_total=info.ms_total,
                    n_tiles=info.n_tiles, n_tiles_next=info.n_tiles_next)
         if fetch:
             res.update(self.get_stf(info.n_pairs, info.n_matches, out))

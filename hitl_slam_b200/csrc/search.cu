@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   uint4 stack[17];                                             // walk frames (local memory; rarely touched)
   unsigned long long n_trav = 0, n_cand = 0;
+  uint32_t n_coarse = 0, n_inrad = 0;                          // per-thread diagnostics (flushed per kernel)
 
   for (;;) {
     uint32_t tile = 0;
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
       const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
       bool pass = false; float qx = 0.f, qy = 0.f;
       if (item && W.cnt[o] < (uint32_t)P.cap) {
+        ++n_coarse;
         const PoseRec rj = P.rec[j];
         Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
         const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
         nearest_point_normal(t, on.y, qx, qy, P.thr, stack, 1, &best, &bpos);
         ++n_trav;
         if (best < P.thr) {                                     // implies bpos valid: best < FLT_MAX only via an in-radius node
+          ++n_inrad;
           // Rotation2Df(theta_j - theta_i) * normal  (JointOptimization.cpp:604-606)
           const float dth = (float)(P.pose[3 * j + 2] - theta_i);
           const float sn = sinf_rn(dth), cs = cosf_rn(dth);
@@ -530,6 +533,40 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
         const uint32_t cand = __ballot_sync(0xffffffffu, hit);
         if (cand == 0) continue;
         n_cand += __popc(cand);
+        const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+        uint32_t need = 0, todo = cand;
+        if (!P.no_cull && __popc(act_mask) * 5u < __popc(cand) * 9u) {
+          // ---- stage 1, sparse form: few points of the tile are still below the cap (stragglers keep a tile alive
+          // through all the targets), so the loop runs over the active POINTS with one candidate target per lane:
+          // each lane keeps its own T_ij and tests the owner's point against its own target's coarse bitmap. ----
+          Aff2 T; uint32_t goff = 0, gdim = 0; float gx0 = 0.f, gy0 = 0.f, ginv = 0.f;
+          bool live = false;
+          if (hit) {
+            const PoseRec rj = P.rec[jl];
+            Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+            T = affine_mul(inv, src);
+            goff = rj.goff; gdim = rj.gdim; gx0 = rj.gx0; gy0 = rj.gy0; ginv = rj.ginv;
+            live = rj.n != 0;
+          }
+          for (uint32_t am = act_mask; am; am &= am - 1) {
+            const uint32_t o = __ffs(am) - 1;
+            const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
+            bool in = live;
+            if (in) {
+              float qx, qy;
+              affine_apply(T, opx, opy, &qx, &qy);
+              uint32_t cx, cy;
+              in = grid_cell(gx0, gy0, ginv, gdim, qx, qy, &cx, &cy);
+              if (in) {
+                const uint32_t bit = cy * (gdim & 0xFFFFu) + cx;
+                in = (__ldg(P.occ + goff + (bit >> 5)) >> (bit & 31)) & 1u;
+              }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, in);     // bit c = target jb + c passes for owner o
+            if (lane == o) need = m;
+          }
+          todo = __reduce_or_sync(0xffffffffu, need);
+        } else {
         if (hit) {
           // this lane's candidate: T_ij = target^-1 * source once per (tile, j), staged with the grid descriptor
           const PoseRec rj = P.rec[jl];
@@ -540,7 +577,6 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
           W.rec[lane][2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
         }
         __syncwarp();
-        uint32_t need = 0;
         for (uint32_t cm = cand; cm; cm &= cm - 1) {
           const uint32_t c = __ffs(cm) - 1;
           const uint4 r0 = W.rec[c][0], r1 = W.rec[c][1];
@@ -561,8 +597,9 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
           need |= (uint32_t)in << c;
         }
         __syncwarp();
+        }
         // ---- stage 2: queue (j, lane) items in order; walk whenever a full batch is available ----
-        for (uint32_t cm = cand; cm; cm &= cm - 1) {
+        for (uint32_t cm = todo; cm; cm &= cm - 1) {
           const uint32_t c = __ffs(cm) - 1;
           const bool want = ((need >> c) & 1u) && active;
           const uint32_t m = __ballot_sync(0xffffffffu, want);
@@ -606,8 +643,12 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
     }
     __syncwarp();
   }
-  for (int o = 16; o; o >>= 1) n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
-  if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); }
+  unsigned long long n_co = n_coarse, n_ir = n_inrad;
+  for (int o = 16; o; o >>= 1) {
+    n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
+    n_co += __shfl_xor_sync(0xffffffffu, n_co, o); n_ir += __shfl_xor_sync(0xffffffffu, n_ir, o);
+  }
+  if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); atomicAdd(P.counters + 9, n_co); atomicAdd(P.counters + 10, n_ir); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1039,7 +1080,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
-  inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5];
+  inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5]; inf.n_coarse_pass = ctx->h_pinned[9]; inf.n_in_radius = ctx->h_pinned[10];
   const uint64_t work_sum = ctx->h_pinned[7];
   // terminating offset of the CSR
   HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));

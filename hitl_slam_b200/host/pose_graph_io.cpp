@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <thread>
 #include <vector>
 #include "hitl_host.h"
 #include "hitl_math.h"
@@ -25,28 +26,42 @@ struct Graph {
   double timestamp = 0;
 };
 
-void flush_scan(Graph* g, std::vector<float>* pc, std::vector<float>* nc) {
-  const size_t n = g->poses.size() / 3 - 1;
-  const float th = -g->poses[3 * n + 2];
-  const float s = hitl::sinf_rn(th), c = hitl::cosf_rn(th);
-  const float lx = -g->poses[3 * n], ly = -g->poses[3 * n + 1];
-  for (size_t i = 0; i < pc->size() / 2; ++i) {
-    float ox, oy;
-    hitl::rot_apply(c, s, (*pc)[2 * i] + lx, (*pc)[2 * i + 1] + ly, &ox, &oy);
-    g->pts.push_back(ox); g->pts.push_back(oy);
-    hitl::rot_apply(c, s, (*nc)[2 * i] + lx, (*nc)[2 * i + 1] + ly, &ox, &oy);
-    g->nrm.push_back(ox); g->nrm.push_back(oy);
+// Decimal -> float, correctly rounded like strtof / fscanf("%f").  Fast path (Clinger): a plain decimal
+// with at most 7 significant digits' worth of mantissa (< 2^24) and at most 10 fractional digits is the
+// quotient of two exactly representable floats, and one IEEE division rounds it correctly.  Everything
+// else (exponents, long mantissas, inf/nan, hex) goes to strtof.
+inline float parse_float(const char* s, const char** end) {
+  static const float kPow10[11] = {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+  const char* p = s;
+  while (*p == ' ' || *p == '\t') ++p;
+  // a number must start here: strtof would otherwise skip line breaks and read the NEXT line's first field
+  if (!((*p >= '0' && *p <= '9') || *p == '-' || *p == '+' || *p == '.' || *p == 'i' || *p == 'I' || *p == 'n' || *p == 'N')) { *end = s; return 0.f; }
+  const char* q = p;
+  bool neg = false;
+  if (*q == '-') { neg = true; ++q; } else if (*q == '+') ++q;
+  uint32_t m = 0; int digits = 0, frac = 0; bool ok = true;
+  while (*q >= '0' && *q <= '9') { m = m * 10 + (uint32_t)(*q - '0'); ++q; if (++digits > 8) ok = false; }
+  if (*q == '.') {
+    ++q;
+    while (*q >= '0' && *q <= '9') { m = m * 10 + (uint32_t)(*q - '0'); ++q; ++frac; if (++digits > 8) ok = false; }
   }
-  g->off.push_back((uint32_t)(g->pts.size() / 2));
-  pc->clear(); nc->clear();
+  if (digits == 0 || !ok || frac > 10 || m >= (1u << 24) || *q == 'e' || *q == 'E' || *q == 'x' || *q == 'X' || *q == 'n' || *q == 'i') {
+    char* e;
+    const float v = strtof(s, &e);
+    *end = e;
+    return v;
+  }
+  *end = q;
+  const float v = (float)m / kPow10[frac];
+  return neg ? -v : v;
 }
 
 // Parses the 16 comma-separated floats of one line; returns the number parsed.
 int parse_line(const char* s, float* v) {
   int n = 0;
   while (n < 16) {
-    char* end;
-    v[n] = strtof(s, &end);
+    const char* end;
+    v[n] = parse_float(s, &end);
     if (end == s) break;
     ++n;
     s = end;
@@ -55,38 +70,133 @@ int parse_line(const char* s, float* v) {
   }
   return n;
 }
+
+// One worker's share of the file: the scans it saw (pose, covariance, first point), world-frame points and normals.
+struct Piece {
+  std::vector<float> poses, cov, pw, nw;   // 3 / 9 per scan, 2 per point (world frame, as stored in the file)
+  std::vector<uint64_t> first;             // first point of each scan inside pw / nw
+  bool stopped = false;                    // hit a malformed line: everything after it is ignored
+};
+
+void parse_piece(const char* b, const char* e, Piece* out) {
+  float v[16];
+  while (b < e) {
+    const char* nl = (const char*)memchr(b, '\n', (size_t)(e - b));
+    const char* le = nl ? nl : e;
+    if (parse_line(b, v) != 16) { out->stopped = true; return; }   // the reference's fscanf loop stops at the first malformed line
+    const size_t n = out->poses.size() / 3;
+    if (n == 0 || v[0] != out->poses[3 * n - 3] || v[1] != out->poses[3 * n - 2] || v[2] != out->poses[3 * n - 1]) {
+      out->poses.insert(out->poses.end(), v, v + 3);
+      out->cov.insert(out->cov.end(), v + 7, v + 16);
+      out->first.push_back(out->pw.size() / 2);
+    }
+    out->pw.push_back(v[3]); out->pw.push_back(v[4]); out->nw.push_back(v[5]); out->nw.push_back(v[6]);
+    b = le + 1;
+  }
+}
+
+unsigned io_threads() {
+  const char* env = getenv("HITL_IO_THREADS");
+  unsigned t = env ? (unsigned)atoi(env) : std::thread::hardware_concurrency();
+  return t < 1 ? 1 : (t > 64 ? 64 : t);
+}
 }  // namespace
 
 extern "C" {
 
+// Whole file in memory, split at line boundaries into one piece per thread, parsed in parallel; pieces are stitched
+// in order (a scan that straddles a boundary is merged: same pose on both sides), then every scan is converted to
+// the robot frame in parallel.  Result is identical to the sequential getline loop.
 void* hitl_host_load_pose_graph(const char* path, uint64_t* n_poses, uint64_t* n_points) {
-  FILE* f = fopen(path, "r");
+  FILE* f = fopen(path, "rb");
   if (!f) return NULL;
-  Graph* g = new Graph();
-  char* line = NULL; size_t cap = 0;
-  bool ok = getline(&line, &cap, f) > 0;
-  if (ok) { g->map_name = line; while (!g->map_name.empty() && (g->map_name.back() == '\n' || g->map_name.back() == '\r')) g->map_name.pop_back(); }
-  ok = ok && getline(&line, &cap, f) > 0;
-  if (ok) g->timestamp = strtod(line, NULL);
-  if (!ok) { free(line); fclose(f); delete g; return NULL; }
-  std::vector<float> pc, nc;
-  float v[16];
-  g->off.push_back(0);
-  while (getline(&line, &cap, f) > 0) {
-    if (parse_line(line, v) != 16) break;   // the reference's fscanf loop stops at the first malformed line
-    const size_t n = g->poses.size() / 3;
-    const bool first = n == 0;
-    const bool changed = !first && (v[0] != g->poses[3 * n - 3] || v[1] != g->poses[3 * n - 2] || v[2] != g->poses[3 * n - 1]);
-    if (changed) flush_scan(g, &pc, &nc);
-    if (first || changed) {
-      g->poses.insert(g->poses.end(), v, v + 3);
-      g->cov.insert(g->cov.end(), v + 7, v + 16);
-    }
-    pc.push_back(v[3]); pc.push_back(v[4]); nc.push_back(v[5]); nc.push_back(v[6]);
+  std::string data;
+  {
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); return NULL; }
+    data.resize((size_t)sz);
+    if (sz && fread(&data[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return NULL; }
+    fclose(f);
   }
-  if (!pc.empty()) flush_scan(g, &pc, &nc);
-  free(line); fclose(f);
-  *n_poses = g->poses.size() / 3; *n_points = g->pts.size() / 2;
+  const char* b = data.c_str();
+  const char* e = b + data.size();
+  const char* l1 = (const char*)memchr(b, '\n', (size_t)(e - b));
+  if (!l1) return NULL;
+  const char* l2 = (const char*)memchr(l1 + 1, '\n', (size_t)(e - l1 - 1));
+  if (!l2) { if (l1 + 1 >= e) return NULL; l2 = e - 1; }
+  Graph* g = new Graph();
+  g->map_name.assign(b, l1);
+  while (!g->map_name.empty() && g->map_name.back() == '\r') g->map_name.pop_back();
+  g->timestamp = strtod(l1 + 1, NULL);
+  const char* body = l2 + 1 <= e ? l2 + 1 : e;
+  const unsigned nt = (size_t)(e - body) < (1u << 20) ? 1u : io_threads();
+  std::vector<const char*> cut(nt + 1);
+  cut[0] = body; cut[nt] = e;
+  for (unsigned t = 1; t < nt; ++t) {
+    const char* c = body + (size_t)(e - body) * t / nt;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    const char* nl = c < e ? (const char*)memchr(c, '\n', (size_t)(e - c)) : NULL;
+    cut[t] = nl ? nl + 1 : e;
+  }
+  std::vector<Piece> pieces(nt);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(parse_piece, cut[t], cut[t + 1], &pieces[t]);
+    parse_piece(cut[0], cut[1], &pieces[0]);
+    for (auto& x : th) x.join();
+  }
+  // stitch: scan list (pose, cov, point range in the concatenated world arrays)
+  std::vector<uint64_t> scan_begin;   // first point of each scan in the global numbering
+  std::vector<uint64_t> base(nt + 1, 0);
+  for (unsigned t = 0; t < nt; ++t) {
+    const Piece& P = pieces[t];
+    base[t + 1] = base[t] + P.pw.size() / 2;
+    for (size_t k = 0; k < P.first.size(); ++k) {
+      const size_t n = g->poses.size() / 3;
+      const bool same = k == 0 && n > 0 && P.poses[0] == g->poses[3 * n - 3] && P.poses[1] == g->poses[3 * n - 2] && P.poses[2] == g->poses[3 * n - 1];
+      if (same) continue;            // continuation of the scan the previous piece ended with
+      g->poses.insert(g->poses.end(), P.poses.begin() + 3 * k, P.poses.begin() + 3 * k + 3);
+      g->cov.insert(g->cov.end(), P.cov.begin() + 9 * k, P.cov.begin() + 9 * k + 9);
+      scan_begin.push_back(base[t] + P.first[k]);
+    }
+    if (P.stopped) { for (unsigned u = t + 1; u <= nt; ++u) base[u] = base[t + 1]; pieces.resize(t + 1); break; }
+  }
+  const unsigned np = (unsigned)pieces.size();
+  const uint64_t total = base[np];
+  const size_t ns = scan_begin.size();
+  g->pts.resize(2 * total); g->nrm.resize(2 * total);
+  g->off.resize(ns + 1);
+  for (size_t i = 0; i < ns; ++i) g->off[i] = (uint32_t)scan_begin[i];
+  g->off[ns] = (uint32_t)total;
+  // robot-frame conversion, one contiguous range of scans per thread
+  auto convert = [&](size_t s_lo, size_t s_hi) {
+    unsigned t = 0;
+    for (size_t i = s_lo; i < s_hi; ++i) {
+      const float th = -g->poses[3 * i + 2];
+      const float sn = hitl::sinf_rn(th), cs = hitl::cosf_rn(th);
+      const float lx = -g->poses[3 * i], ly = -g->poses[3 * i + 1];
+      for (uint64_t k = g->off[i]; k < g->off[i + 1]; ++k) {
+        while (k >= base[t + 1]) ++t;
+        const Piece& P = pieces[t];
+        const size_t q = (size_t)(k - base[t]);
+        float ox, oy;
+        hitl::rot_apply(cs, sn, P.pw[2 * q] + lx, P.pw[2 * q + 1] + ly, &ox, &oy);
+        g->pts[2 * k] = ox; g->pts[2 * k + 1] = oy;
+        hitl::rot_apply(cs, sn, P.nw[2 * q] + lx, P.nw[2 * q + 1] + ly, &ox, &oy);
+        g->nrm[2 * k] = ox; g->nrm[2 * k + 1] = oy;
+      }
+    }
+  };
+  {
+    const unsigned ct = ns < 64 ? 1u : nt;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < ct; ++t) th.emplace_back(convert, ns * t / ct, ns * (t + 1) / ct);
+    convert(0, ns / ct);
+    for (auto& x : th) x.join();
+  }
+  *n_poses = ns; *n_points = total;
   return g;
 }
 
@@ -103,18 +213,43 @@ void hitl_host_pose_graph_free(void* h) { delete static_cast<Graph*>(h); }
 // One line per point; obs/normals are WORLD frame as the format requires (README.md:119-137).
 int hitl_host_save_stfs_covars(const char* path, const char* map_name, double timestamp, uint32_t n_poses, const float* poses_xyt, const float* cov9,
                                const uint32_t* off, const float* obs_world_xy, const float* nrm_world_xy) {
-  FILE* f = fopen(path, "w");
+  FILE* f = fopen(path, "wb");
   if (!f) return 1;
-  std::vector<char> buf(1 << 22);
-  setvbuf(f, buf.data(), _IOFBF, buf.size());
   fprintf(f, "%s\n", map_name);
   fprintf(f, "%lf\n", timestamp);
-  for (uint32_t i = 0; i < n_poses; ++i) {
-    const float* p = poses_xyt + 3 * i; const float* c = cov9 + 9 * i;
-    for (uint32_t k = off[i]; k < off[i + 1]; ++k)
-      fprintf(f, "%.4f,%.4f,%.4f,%.4f,%.4f, %.4f,%.4f,%f, %f, %f, %f, %f, %f, %f, %f, %f\n", p[0], p[1], p[2], obs_world_xy[2 * k], obs_world_xy[2 * k + 1],
-              nrm_world_xy[2 * k], nrm_world_xy[2 * k + 1], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]);
+  // Scans are formatted in parallel (contiguous pose ranges balanced by point count), then written in order.  The
+  // pose prefix and covariance suffix of a line repeat for every point of a scan and are formatted once per scan.
+  const unsigned nt = off[n_poses] < (1u << 16) ? 1u : io_threads();
+  std::vector<uint32_t> cut(nt + 1, n_poses);
+  cut[0] = 0;
+  for (unsigned t = 1, i = 0; t < nt; ++t) {
+    const uint64_t want = (uint64_t)off[n_poses] * t / nt;
+    while (i < n_poses && off[i] < want) ++i;
+    cut[t] = i;
   }
+  std::vector<std::string> out(nt);
+  auto format = [&](unsigned t) {
+    std::string& o = out[t];
+    o.reserve((size_t)(off[cut[t + 1]] - off[cut[t]]) * 150 + 64);
+    char head[128], tail[256], mid[160];
+    for (uint32_t i = cut[t]; i < cut[t + 1]; ++i) {
+      const float* p = poses_xyt + 3 * i; const float* c = cov9 + 9 * i;
+      const int nh = snprintf(head, sizeof(head), "%.4f,%.4f,%.4f,", p[0], p[1], p[2]);
+      const int ntl = snprintf(tail, sizeof(tail), "%f, %f, %f, %f, %f, %f, %f, %f, %f\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8]);
+      for (uint32_t k = off[i]; k < off[i + 1]; ++k) {
+        const int nm = snprintf(mid, sizeof(mid), "%.4f,%.4f, %.4f,%.4f,", obs_world_xy[2 * k], obs_world_xy[2 * k + 1], nrm_world_xy[2 * k], nrm_world_xy[2 * k + 1]);
+        o.append(head, (size_t)nh); o.append(mid, (size_t)nm); o.append(tail, (size_t)ntl);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(format, t);
+    format(0);
+    for (auto& x : th) x.join();
+  }
+  for (unsigned t = 0; t < nt; ++t)
+    if (!out[t].empty() && fwrite(out[t].data(), 1, out[t].size(), f) != out[t].size()) { fclose(f); return 2; }
   const int rc = ferror(f) ? 2 : 0;
   fclose(f);
   return rc;

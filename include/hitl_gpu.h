@@ -110,6 +110,8 @@ typedef struct {
   uint64_t n_tile_pairs;  /* (32-point source tile, target pose) pairs that survived the world-frame box test */
   float ms_search;        /* device time of the search kernel alone (CUDA events on the ctx stream) */
   float ms_total;         /* device time of the whole call: pose prep + search + ordering/compaction */
+  uint64_t n_coarse_pass; /* (point, target) items that passed the coarse occupancy level (candidates of the fine level) */
+  uint64_t n_in_radius;   /* tree walks that found a node inside the radius (the rest proved "no neighbour" the slow way) */
   uint32_t n_tiles;       /* work units (runs of <= 32 source points) the search kernel scheduled in this call */
   uint32_t n_tiles_next;  /* ... and after the adaptive split of heavy tiles that this call's measurements triggered */
 } hitl_stf_info;

@@ -101,6 +101,57 @@ def test_session_log_round_trip_and_format(host, tmp_path):
         host.load_log(str(tmp_path / "missing.log"))
 
 
+def test_stfs_covars_io_threads_and_fast_parser(host, tmp_path, monkeypatch):
+    """The parallel reader / writer (HitLSLAM_main.cpp:192-300, vector_mapping_main.cpp:1855-1928 mirrors) give the
+    same bytes and the same arrays as the single-threaded path; the Clinger fast path equals strtof (= fscanf %f);
+    a malformed line stops the load where the reference's fscanf loop would."""
+    rng = np.random.default_rng(7)
+    n = 300
+    poses = (rng.normal(size=(n, 3)) * 20).astype(np.float32)
+    cov = np.abs(rng.normal(size=(n, 9)) * 1e-4).astype(np.float32)
+    cnt = rng.integers(0, 900, n)
+    cnt[5] = 0
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
+    obs = (rng.normal(size=(off[-1], 2)) * 25).astype(np.float32)
+    nrm = rng.normal(size=(off[-1], 2)).astype(np.float32)
+    obs[::11] = 0
+    obs[3] = [123456.7, -0.00004]           # rounds to 8 digits / to zero at 4 decimals
+    obs[4] = [1.6777216e7, 3.3554432e7]     # mantissa >= 2^24: strtof path
+    paths = {}
+    for tag, threads in (("mt", "8"), ("st", "1")):
+        monkeypatch.setenv("HITL_IO_THREADS", threads)
+        paths[tag] = str(tmp_path / (tag + ".stfs.covars"))
+        host.save_stfs_covars(paths[tag], poses, cov, off, obs, nrm, map_name="io", timestamp=12.5)
+    a, b = open(paths["mt"], "rb").read(), open(paths["st"], "rb").read()
+    assert a == b and len(a) > (1 << 20)
+    text = a.decode().split("\n")
+    assert text[0] == "io" and float(text[1]) == 12.5
+    # python's float() is correctly rounded like strtof: check the parsed world-frame values through a pose with theta = 0
+    loads = {}
+    for tag, threads in (("mt", "8"), ("st", "1")):
+        monkeypatch.setenv("HITL_IO_THREADS", threads)
+        loads[tag] = host.load_pose_graph(paths["mt"])
+    for k in ("poses", "offsets", "pts", "nrm"):
+        assert np.array_equal(np.asarray(loads["mt"][k]).view(np.uint32), np.asarray(loads["st"][k]).view(np.uint32)), k
+    g = loads["mt"]
+    want_poses = np.array([[np.float32(x) for x in line.split(",")[:3]] for line in text[2:-1]], np.float32)
+    change = np.ones(len(want_poses), bool)
+    change[1:] = (want_poses[1:] != want_poses[:-1]).any(1)
+    assert np.array_equal(g["poses"], want_poses[change])
+    assert int(g["offsets"][-1]) == len(want_poses)
+    # malformed line in the middle: everything from it on is ignored, in both modes
+    lines = text[:]
+    cutline = 2 + len(want_poses) // 2
+    lines[cutline] = "oops"
+    bad = str(tmp_path / "bad.stfs.covars")
+    open(bad, "w").write("\n".join(lines))
+    for threads in ("8", "1"):
+        monkeypatch.setenv("HITL_IO_THREADS", threads)
+        gb = host.load_pose_graph(bad)
+        assert int(gb["offsets"][-1]) == cutline - 2
+        assert np.array_equal(gb["pts"], g["pts"][:cutline - 2])
+
+
 def test_mirror_refuses_to_run_without_a_context(host):
     host._bind_mirror()
     assert not host.lib.hitl_host_session_create(None)     # no ctx, no session: there is no CPU implementation of the stages
