@@ -35,9 +35,17 @@ namespace hitl {
 
 // ------------------------------------------------------------------------------------------------
 // Tree walk: FindNearestPointNormal as a frame machine.
-// Frame = {best, |s|, far child (pos | n << 16), bestpos | state << 16}; one uint4 per level per thread.
+// The recursion's pending work lives on a stack of 8-byte entries, at most two per level:
+//   gate entry {gate, far child (pos | n << 16)}   far.n >= 1, so the second word is >= 0x10000
+//   best entry {best, bestpos}                     bestpos <= 0xFFFF
+// `gate` folds the reference's three far-side cases into one compare at return time, `gate < min(best, thr)`:
+//   |s|   far side is entered only if |s| < min(best, thr)   (pushed only when |s| < thr, else it never can be)
+//   -inf  s == 0: left, then right unconditionally
+//   (no entry)  no far side: missing child, or |s| >= thr
+// A node in the radius pushes its own distance as a best entry ABOVE its gate entry: on the way back the child's result
+// is first merged with it (the node wins ties, as `child < best` in the reference), the merged value bounds the gate,
+// and when the far side is entered the merged value is parked as a best entry so that it wins ties over the far result.
 // ------------------------------------------------------------------------------------------------
-enum { FAR_NONE = 0, FAR_COND = 1, FAR_UNCOND = 2 };
 constexpr uint32_t kNoPos = 0xFFFFu;
 
 struct TreeRef {
@@ -48,73 +56,66 @@ __device__ __forceinline__ uint32_t node_meta(const float4& nd) { return __float
 
 // stack[level * stride + tid]
 __device__ __forceinline__ void nearest_point_normal(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr,
-                                                     uint4* stack, uint32_t stride, float* out_best, uint32_t* out_pos) {
+                                                     uint2* stack, uint32_t stride, float* out_best, uint32_t* out_pos) {
   const float thr2 = fmul(thr, thr);
-  uint32_t pos = 0, n = n_nodes, level = 0;
+  const float kNegInf = __int_as_float(0xff800000);
+  uint32_t pos = 0, n = n_nodes, sp = 0;
   float ret_best;
   uint32_t ret_pos;
   for (;;) {
     // ---- call(pos, n) ----
     for (;;) {
       const float4 nd = __ldg(t.pm + pos);
-      const int dim = (int)(node_meta(nd) >> 31);
       float best = FLT_MAX;
       uint32_t bestpos = kNoPos;
-      const float ex = fsub(nd.x, qx), ey = fsub(nd.y, qy);
-      bool leaf_return = false;
-      if (fadd(fmul(ex, ex), fmul(ey, ey)) < thr2) {
+      // (node - q)^2 == (q - node)^2 bit for bit, so one pair of differences serves the radius test, the normal
+      // distance and the splitting-plane offset s
+      const float dx = fsub(qx, nd.x), dy = fsub(qy, nd.y);
+      bool exact = false;
+      if (fadd(fmul(dx, dx), fmul(dy, dy)) < thr2) {
         const float2 nv = __ldg(t.nn + pos);
         bestpos = pos;
-        best = fabsf(fadd(fmul(nv.x, fsub(qx, nd.x)), fmul(nv.y, fsub(qy, nd.y))));
-        if (best < FLT_MIN) { best = 0.0f; leaf_return = true; }
+        best = fabsf(fadd(fmul(nv.x, dx), fmul(nv.y, dy)));
+        if (best < FLT_MIN) { best = 0.0f; exact = true; }
       }
-      const float s = dim ? fsub(qy, nd.y) : fsub(qx, nd.x);
+      const float s = (node_meta(nd) >> 31) ? dy : dx;
       const uint32_t nl = n >> 1, nr = n - 1 - nl;
-      uint32_t far, state, near_pos, near_n;
-      if (leaf_return || nl == 0) {
-        ret_best = best; ret_pos = bestpos; break;
+      const bool go_right = s > 0.0f;
+      const uint32_t near_n = go_right ? nr : nl, far_n = go_right ? nl : nr;
+      // leaf (nl == 0 implies nr == 0), exact hit, or s > 0 with no right child (`other` stays NULL): the call returns its own node
+      if (exact || near_n == 0) { ret_best = best; ret_pos = bestpos; break; }
+      const uint32_t lpos = pos + 1, rpos = lpos + nl;
+      const float as = fabsf(s);
+      const bool both = !go_right && !(s < 0.0f);                   // s == 0: no third visit, both children in order
+      if (far_n != 0 && (both || as < thr)) {
+        stack[sp * stride] = make_uint2(__float_as_uint(both ? kNegInf : as), (go_right ? lpos : rpos) | (far_n << 16));
+        ++sp;
       }
-      if (s < 0.0f) {
-        near_pos = pos + 1; near_n = nl;
-        far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_COND : FAR_NONE;
-      } else if (s > 0.0f) {
-        if (nr == 0) { ret_best = best; ret_pos = bestpos; break; }   // right NULL: `other` stays NULL
-        near_pos = pos + 1 + nl; near_n = nr;
-        far = (pos + 1) | (nl << 16); state = FAR_COND;
-      } else {                                                       // s == 0: left then right, no third visit
-        near_pos = pos + 1; near_n = nl;
-        far = (pos + 1 + nl) | (nr << 16); state = nr ? FAR_UNCOND : FAR_NONE;
-      }
-      // The far side is entered only if |s| < min(best, thr) <= thr: when |s| >= thr it never is.
-      if (state == FAR_COND && !(fabsf(s) < thr)) state = FAR_NONE;
-      // Tail call: nothing found at this node and no far side to consider -> the near child's result
-      // is this call's result (the merge `child < FLT_MAX` would just copy it); no frame needed.
-      if (state == FAR_NONE && bestpos == kNoPos) { pos = near_pos; n = near_n; continue; }
-      stack[level * stride] = make_uint4(__float_as_uint(best), __float_as_uint(fabsf(s)), far, bestpos | (state << 16));
-      ++level;
-      pos = near_pos; n = near_n;
+      if (bestpos != kNoPos) { stack[sp * stride] = make_uint2(__float_as_uint(best), bestpos); ++sp; }
+      // (neither pushed = tail call: the near child's result is this call's result)
+      pos = go_right ? rpos : lpos; n = near_n;
     }
     // ---- return(ret_best, ret_pos) ----
     for (;;) {
-      if (level == 0) { *out_best = ret_best; *out_pos = ret_pos; return; }
-      uint4 f = stack[(level - 1) * stride];
-      float best = __uint_as_float(f.x);
-      uint32_t bestpos = f.w & 0xFFFFu;
-      const uint32_t state = f.w >> 16;
-      if (ret_best < best) { best = ret_best; bestpos = ret_pos; }
-      const float bound = best < thr ? best : thr;
-      if (state == FAR_UNCOND || (state == FAR_COND && __uint_as_float(f.y) < bound)) {
-        f.x = __float_as_uint(best); f.w = bestpos;   // state -> FAR_NONE
-        stack[(level - 1) * stride] = f;
-        pos = f.z & 0xFFFFu; n = f.z >> 16;
-        break;                                        // call(far)
+      if (sp == 0) { *out_best = ret_best; *out_pos = ret_pos; return; }
+      --sp;
+      const uint2 e = stack[sp * stride];
+      if (e.y < 0x10000u) {                            // best entry: wins ties over what came back from below
+        if (!(ret_best < __uint_as_float(e.x))) { ret_best = __uint_as_float(e.x); ret_pos = e.y; }
+        continue;
       }
-      --level;
-      ret_best = best; ret_pos = bestpos;
+      const float bound = ret_best < thr ? ret_best : thr;
+      if (__uint_as_float(e.x) < bound) {              // call(far); the merged result so far waits as a best entry
+        stack[sp * stride] = make_uint2(__float_as_uint(ret_best), ret_pos);
+        ++sp;
+        pos = e.y & 0xFFFFu; n = e.y >> 16;
+        break;
+      }
     }
   }
 }
 
+enum { FAR_NONE = 0, FAR_COND = 1, FAR_UNCOND = 2 };
 // FindNearestPoint (kdtree.cpp:220-273): Euclidean, the bound min(best, thr) is handed down.
 // Only used by the consecutive-pose matcher and hitl_kd_query: explicit local stack.
 __device__ void nearest_point(const TreeRef t, uint32_t n_nodes, float qx, float qy, float thr0, float* out_best,
@@ -185,7 +186,7 @@ __device__ uint32_t neighbor_count(const TreeRef t, uint32_t n_nodes, float qx, 
 
 __global__ void kd_query_kernel(const float4* pm, const float2* nn, uint32_t tree_off, uint32_t n_nodes, uint32_t nq,
                                 const float2* q, float thr, int mode, float* dist, int32_t* index) {
-  extern __shared__ uint4 smem_stack[];
+  extern __shared__ uint2 smem_stack[];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   TreeRef t; t.pm = pm + tree_off; t.nn = nn + tree_off;
@@ -377,17 +378,17 @@ constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
 struct __align__(16) WarpShared {
   uint4 rec[32][3];        // per candidate of the current block of 32 target poses: T_ij, scan size, occupancy grid descriptor
   uint32_t queue[kQueueCap];   // stage A: items that passed the coarse occupancy level; item = owner lane | j << 5
-  uint32_t wq[kQueueCap];      // stage B: items that also passed the fine level, with their query point in frame j
-  float wqx[kQueueCap], wqy[kQueueCap];
+  uint32_t wq[kQueueCap];      // stage B: items that also passed the fine level
   uint32_t cnt[32];        // matches per lane's point
   uint32_t exec_last[32];  // j that filled the cap (kNotCapped otherwise)
 };
 
-__global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_kernel(const SearchParams P) {
+template <int MINB>
+__global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const SearchParams P) {
   __shared__ WarpShared s_warp[kSearchWarps];
   WarpShared& W = s_warp[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
-  uint4 stack[17];                                             // walk frames (local memory; rarely touched)
+  uint2 stack[34];                                             // walk entries (local memory, 8 B each, at most 2 per tree level)
   unsigned long long n_trav = 0, n_cand = 0;
   uint32_t n_coarse = 0, n_inrad = 0;                          // per-thread diagnostics (flushed per kernel)
 
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
         }
       }
       const uint32_t pm = __ballot_sync(0xffffffffu, pass);
-      if (pass) { const uint32_t slot = qw + __popc(pm & lt); W.wq[slot] = it; W.wqx[slot] = qx; W.wqy[slot] = qy; }
+      if (pass) W.wq[qw + __popc(pm & lt)] = it;
       qw += __popc(pm);
       // shift the remaining stage-A items to the front
       const uint32_t rest = qn - nitems;
@@ -472,17 +473,23 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
     auto drain = [&](uint32_t nitems) {
       const bool item = lane < nitems;
       const uint32_t it = item ? W.wq[lane] : 0u;
-      const float qx = item ? W.wqx[lane] : 0.f, qy = item ? W.wqy[lane] : 0.f;
       const uint32_t o = it & 31u, j = it >> 5;
-      // normal of the owning lane
+      // point / normal of the owning lane
+      const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
       const float onx = __shfl_sync(0xffffffffu, nv.x, o), ony = __shfl_sync(0xffffffffu, nv.y, o);
       bool ok = false; uint32_t tgt = 0;
       const uint32_t cnt_o = W.cnt[o];
       if (item && cnt_o < (uint32_t)P.cap) {
-        const uint2 on = *reinterpret_cast<const uint2*>(&P.rec[j].off);   // scan offset, size
-        TreeRef t; t.pm = P.node_pm + on.x; t.nn = P.node_nn + on.x;
+        const float4 ra = *reinterpret_cast<const float4*>(&P.rec[j].i00);
+        const float4 rb = *reinterpret_cast<const float4*>(&P.rec[j].itx);   // itx, ity, scan offset, size
+        Aff2 inv; inv.m00 = ra.x; inv.m01 = ra.y; inv.m10 = ra.z; inv.m11 = ra.w; inv.tx = rb.x; inv.ty = rb.y;
+        const Aff2 T = affine_mul(inv, src);                    // T_ij = target^-1 * source (JointOptimization.cpp:304)
+        float qx, qy;
+        affine_apply(T, opx, opy, &qx, &qy);
+        const uint32_t toff = __float_as_uint(rb.z), tn = __float_as_uint(rb.w);
+        TreeRef t; t.pm = P.node_pm + toff; t.nn = P.node_nn + toff;
         float best; uint32_t bpos;
-        nearest_point_normal(t, on.y, qx, qy, P.thr, stack, 1, &best, &bpos);
+        nearest_point_normal(t, tn, qx, qy, P.thr, stack, 1, &best, &bpos);
         ++n_trav;
         if (best < P.thr) {                                     // implies bpos valid: best < FLT_MAX only via an in-radius node
           ++n_inrad;
@@ -511,10 +518,10 @@ __global__ void __launch_bounds__(kSearchThreads, kSearchMinBlocks) stf_search_k
       __syncwarp();
       // shift the remaining items to the front
       const uint32_t rest = qw - nitems;
-      uint32_t a = 0; float ax = 0.f, ay = 0.f;
-      if (lane < rest) { a = W.wq[nitems + lane]; ax = W.wqx[nitems + lane]; ay = W.wqy[nitems + lane]; }
+      uint32_t a = 0;
+      if (lane < rest) a = W.wq[nitems + lane];
       __syncwarp();
-      if (lane < rest) { W.wq[lane] = a; W.wqx[lane] = ax; W.wqy[lane] = ay; }
+      if (lane < rest) W.wq[lane] = a;
       qw = rest;
       active = valid && W.cnt[lane] < (uint32_t)P.cap;
       __syncwarp();
@@ -893,7 +900,7 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
   HITL_CUDA(cudaMemcpyAsync(dq.p, q_xy, sizeof(float2) * nq, cudaMemcpyHostToDevice, ctx->stream));
   const uint32_t toff = ctx->h_off[scan], tn = ctx->h_off[scan + 1] - toff;
   const int threads = 128;
-  const size_t smem = (size_t)stack_levels(ctx->max_scan) * threads * sizeof(uint4);
+  const size_t smem = (size_t)stack_levels(ctx->max_scan) * 2 * threads * sizeof(uint2);
   kd_query_kernel<<<(nq + threads - 1) / threads, threads, smem, ctx->stream>>>(ctx->d_node_pm.p, ctx->d_node_nn.p, toff, tn, nq, dq.p,
                                                                               threshold, mode, dd.p, di.p);
   HITL_LAUNCH_CHECK("kd_query_kernel");
@@ -1051,10 +1058,11 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   if (n_tiles) {
     // persistent grid: one wave of CTAs (a multiple of the SM count), warps pull tiles from a ticket
     int per_sm = 0;
-    HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stf_search_kernel, kSearchThreads, 0));
+    void (*kernel)(const SearchParams) = ctx->search_variant == 1 ? stf_search_kernel<12> : (ctx->search_variant == 2 ? stf_search_kernel<10> : stf_search_kernel<kSearchMinBlocks>);
+    HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSearchThreads, 0));
     if (per_sm < 1) per_sm = 1;
     const uint32_t grid = std::min<uint32_t>((n_tiles + wpb - 1) / wpb, (uint32_t)(ctx->sm_count * per_sm));
-    stf_search_kernel<<<grid, kSearchThreads, 0, ctx->stream>>>(P);
+    kernel<<<grid, kSearchThreads, 0, ctx->stream>>>(P);
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1122,6 +1130,12 @@ extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adapti
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_debug_set_tiling: scans not set");
   ctx->adaptive_tiling = adaptive;
   return build_tiling(ctx, max_len);
+}
+
+extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 2) return HITL_ERR_ARG;
+  ctx->search_variant = variant;
+  return HITL_OK;
 }
 
 extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {

@@ -1,13 +1,19 @@
-import sys, numpy as np, json
+"""Cull / walk diagnostics of the search kernel on one workload (default c2): counters and kernel time per setting.
+usage: python profiles/diag_cull.py [workload] [poses] [beams]"""
+import sys, numpy as np
 sys.path.insert(0, '.')
 import bench
-from hitl_slam_b200 import HitlGpu
-g = bench.workload("c2", 5000, 720)
+from hitl_slam_b200 import HitlGpu, synth
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+n_poses = int(sys.argv[2]) if len(sys.argv) > 2 else synth.CONFIGS[name]["n_poses"]
+beams = int(sys.argv[3]) if len(sys.argv) > 3 else synth.CONFIGS[name]["beams"]
+g = bench.workload(name, n_poses, beams)
 gpu = HitlGpu(0)
 gpu.set_scans(g["offsets"], g["pts"], g["nrm"]); gpu.build_kdtrees()
 poses = g["poses"].astype(np.float64)
-for fine in (True, False):
+for variant, fine in ((0, True), (1, True), (2, True), (0, False)):
+    gpu.debug_set_search_variant(variant)
     gpu.debug_set_fine_occupancy(fine)
-    for _ in range(3):
+    for _ in range(4):
         r = gpu.find_stf(poses, fetch=False)
-    print(fine, {k: (int(v) if not isinstance(v, float) else round(v, 3)) for k, v in r.items() if k.startswith("n_") or k.startswith("ms_")})
+    print("variant", variant, "fine", fine, {k: (int(v) if not isinstance(v, float) else round(v, 3)) for k, v in r.items() if k.startswith("n_") or k.startswith("ms_")})
