@@ -118,7 +118,7 @@ class HitlGpu:
         lib.hitl_debug_tile_work.argtypes = [vp, C.c_uint32, _u32p, C.POINTER(C.c_uint32)]
         lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int]
         lib.hitl_debug_set_fine_occupancy.argtypes = [vp, C.c_int]
-        lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int]
+        lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int, C.c_int]
         lib.hitl_debug_sincos.argtypes = [vp, C.c_uint64, _f32p, _f32p, _f32p]
         lib.hitl_debug_relative_pose.argtypes = [vp, _f64p, C.c_uint32, _u32p, _u32p, _f32p]
         self.ctx = vp()
@@ -366,8 +366,8 @@ class HitlGpu:
     def debug_set_tiling(self, max_len=32, adaptive=True):
         self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive)))
 
-    def debug_set_search_variant(self, variant=0):
-        self._ck(self.lib.hitl_debug_set_search_variant(self.ctx, int(variant)))
+    def debug_set_search_variant(self, variant=0, smem_carveout_pct=-1):
+        self._ck(self.lib.hitl_debug_set_search_variant(self.ctx, int(variant), int(smem_carveout_pct)))
 
     def debug_set_fine_occupancy(self, on=True):
         self._ck(self.lib.hitl_debug_set_fine_occupancy(self.ctx, int(on)))

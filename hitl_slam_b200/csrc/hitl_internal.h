@@ -67,6 +67,7 @@ struct hitl_ctx {
   uint32_t tiling_splits = 0;                                    // heavy tiles split so far (adaptive tiling)
   uint32_t split_rounds = 0, split_lo = 0, split_hi = 0;         // split rounds done for the source range [split_lo, split_hi)
   int adaptive_tiling = 1;
+  int search_carveout = -1;              // preferred shared-memory carve-out in percent (-1: driver default)
   int search_variant = 0;                // 0: 16 CTAs/SM (32 regs), 1: 12 CTAs/SM (40 regs), 2: 10 CTAs/SM (hitl_debug_set_search_variant)
   // scheduling hint of the search: tiles sorted by the cycles the previous call spent on them
   hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys;

@@ -376,7 +376,7 @@ constexpr uint32_t kQueueCap = 64;
 constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
 
 struct __align__(16) WarpShared {
-  uint4 rec[32][3];        // per candidate of the current block of 32 target poses: T_ij, scan size, occupancy grid descriptor
+  uint4 rec[16][3];        // per candidate of the current half block of 16 target poses: T_ij, scan size, occupancy grid descriptor
   uint32_t queue[kQueueCap];   // stage A: items that passed the coarse occupancy level; item = owner lane | j << 5
   uint32_t wq[kQueueCap];      // stage B: items that also passed the fine level
   uint32_t cnt[32];        // matches per lane's point
@@ -574,36 +574,42 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
           }
           todo = __reduce_or_sync(0xffffffffu, need);
         } else {
-        if (hit) {
-          // this lane's candidate: T_ij = target^-1 * source once per (tile, j), staged with the grid descriptor
-          const PoseRec rj = P.rec[jl];
-          Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
-          const Aff2 T = affine_mul(inv, src);
-          W.rec[lane][0] = make_uint4(__float_as_uint(T.m00), __float_as_uint(T.m01), __float_as_uint(T.m10), __float_as_uint(T.m11));
-          W.rec[lane][1] = make_uint4(__float_as_uint(T.tx), __float_as_uint(T.ty), rj.n, rj.goff);
-          W.rec[lane][2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
-        }
-        __syncwarp();
-        for (uint32_t cm = cand; cm; cm &= cm - 1) {
-          const uint32_t c = __ffs(cm) - 1;
-          const uint4 r0 = W.rec[c][0], r1 = W.rec[c][1];
-          bool in = active && r1.z != 0;                        // r1.z = n
-          if (in && !P.no_cull) {
-            Aff2 T; T.m00 = __uint_as_float(r0.x); T.m01 = __uint_as_float(r0.y); T.m10 = __uint_as_float(r0.z); T.m11 = __uint_as_float(r0.w);
-            T.tx = __uint_as_float(r1.x); T.ty = __uint_as_float(r1.y);
-            float qx, qy;
-            affine_apply(T, p.x, p.y, &qx, &qy);
-            const uint4 r2 = W.rec[c][2];
-            uint32_t cx, cy;
-            in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
-            if (in) {
-              const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
-              in = (__ldg(P.occ + r1.w + (bit >> 5)) >> (bit & 31)) & 1u;
-            }
+        // dense form: the candidates' T_ij and grid descriptors are staged in shared memory, 16 targets at a time
+        for (uint32_t half = 0; half < 2; ++half) {
+          const uint32_t hm = cand & (0xFFFFu << (16 * half));
+          if (hm == 0) continue;
+          if (hit && (lane >> 4) == half) {
+            // this lane's candidate: T_ij = target^-1 * source once per (tile, j)
+            const PoseRec rj = P.rec[jl];
+            Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+            const Aff2 T = affine_mul(inv, src);
+            uint4* const r = W.rec[lane & 15];
+            r[0] = make_uint4(__float_as_uint(T.m00), __float_as_uint(T.m01), __float_as_uint(T.m10), __float_as_uint(T.m11));
+            r[1] = make_uint4(__float_as_uint(T.tx), __float_as_uint(T.ty), rj.n, rj.goff);
+            r[2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
           }
-          need |= (uint32_t)in << c;
+          __syncwarp();
+          for (uint32_t cm = hm; cm; cm &= cm - 1) {
+            const uint32_t c = __ffs(cm) - 1;
+            const uint4 r0 = W.rec[c & 15][0], r1 = W.rec[c & 15][1];
+            bool in = active && r1.z != 0;                        // r1.z = n
+            if (in && !P.no_cull) {
+              Aff2 T; T.m00 = __uint_as_float(r0.x); T.m01 = __uint_as_float(r0.y); T.m10 = __uint_as_float(r0.z); T.m11 = __uint_as_float(r0.w);
+              T.tx = __uint_as_float(r1.x); T.ty = __uint_as_float(r1.y);
+              float qx, qy;
+              affine_apply(T, p.x, p.y, &qx, &qy);
+              const uint4 r2 = W.rec[c & 15][2];
+              uint32_t cx, cy;
+              in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
+              if (in) {
+                const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
+                in = (__ldg(P.occ + r1.w + (bit >> 5)) >> (bit & 31)) & 1u;
+              }
+            }
+            need |= (uint32_t)in << c;
+          }
+          __syncwarp();
         }
-        __syncwarp();
         }
         // ---- stage 2: queue (j, lane) items in order; walk whenever a full batch is available ----
         for (uint32_t cm = todo; cm; cm &= cm - 1) {
@@ -1059,6 +1065,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     // persistent grid: one wave of CTAs (a multiple of the SM count), warps pull tiles from a ticket
     int per_sm = 0;
     void (*kernel)(const SearchParams) = ctx->search_variant == 1 ? stf_search_kernel<12> : (ctx->search_variant == 2 ? stf_search_kernel<10> : stf_search_kernel<kSearchMinBlocks>);
+    if (ctx->search_carveout >= 0) HITL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->search_carveout));
     HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSearchThreads, 0));
     if (per_sm < 1) per_sm = 1;
     const uint32_t grid = std::min<uint32_t>((n_tiles + wpb - 1) / wpb, (uint32_t)(ctx->sm_count * per_sm));
@@ -1132,9 +1139,10 @@ extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adapti
   return build_tiling(ctx, max_len);
 }
 
-extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 2) return HITL_ERR_ARG;
+extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int smem_carveout_pct) {
+  if (!ctx || variant < 0 || variant > 2 || smem_carveout_pct > 100) return HITL_ERR_ARG;
   ctx->search_variant = variant;
+  ctx->search_carveout = smem_carveout_pct;
   return HITL_OK;
 }
 

@@ -214,8 +214,9 @@ int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive);
 /* Switches the second (fine, cell = threshold / 4) level of the occupancy cull on or off; the bitmaps are rebuilt by the
  * next search.  Culling is result-preserving; parity tests compare both settings and disable_culling = 1. */
 int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
-/* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48). */
-int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant);
+/* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48);
+ * smem_carveout_pct = preferred shared-memory carve-out of the unified L1 (percent, -1 = driver default). */
+int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int smem_carveout_pct);
 int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out);
 int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src,
                              const uint32_t* dst, float* out6);

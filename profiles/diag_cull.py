@@ -11,9 +11,9 @@ g = bench.workload(name, n_poses, beams)
 gpu = HitlGpu(0)
 gpu.set_scans(g["offsets"], g["pts"], g["nrm"]); gpu.build_kdtrees()
 poses = g["poses"].astype(np.float64)
-for variant, fine in ((0, True), (1, True), (2, True), (0, False)):
-    gpu.debug_set_search_variant(variant)
+for variant, carve, fine in ((0, -1, True), (0, 50, True), (0, 30, True), (1, -1, True), (0, -1, False)):
+    gpu.debug_set_search_variant(variant, carve)
     gpu.debug_set_fine_occupancy(fine)
     for _ in range(4):
         r = gpu.find_stf(poses, fetch=False)
-    print("variant", variant, "fine", fine, {k: (int(v) if not isinstance(v, float) else round(v, 3)) for k, v in r.items() if k.startswith("n_") or k.startswith("ms_")})
+    print("variant", variant, "carveout", carve, "fine", fine, {k: (int(v) if not isinstance(v, float) else round(v, 3)) for k, v in r.items() if k.startswith("n_") or k.startswith("ms_")})
