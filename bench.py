@@ -171,12 +171,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--poses", type=int, default=None)
     ap.add_argument("--beams", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--balance-passes", type=int, default=4, help="multi-GPU setup: searches used to cut the source ranges at equal measured work")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
@@ -193,6 +194,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries exactly one JSON line
     import torch
     import torch.distributed as dist
     from hitl_slam_b200 import HitlGpu, capi
@@ -237,20 +239,24 @@ def main():
                 dist.all_reduce(neq_dev[1])
         return info, ne
 
+    if world > 1:
+        # Setup (not a step): cut the source ranges at equal MEASURED work.  Every search reports the SM cycles it spent on
+        # each source pose; summed over the ranks this is a partition-independent cost per pose (all GPUs are alike), so
+        # the ranges are re-cut at equal cycle sums and the estimate is refined over a few passes.
+        est = None
+        for p in range(args.balance_passes):
+            info_b = gpu.find_stf(poses, src_lo=lo, src_hi=hi, fetch=False)
+            work = torch.from_numpy(gpu.stf_work().astype(np.float64)).cuda()
+            dist.all_reduce(work)
+            wk = work.cpu().numpy()
+            est = wk if est is None else 0.5 * (est + wk)
+            if os.environ.get("HITL_BENCH_DEBUG"):
+                sys.stderr.write("[rank %d] balance %d: [%d, %d) ms_search %.3f ms_total %.3f tiles %d -> %d\n" % (rank, p, lo, hi, info_b["ms_search"], info_b["ms_total"], info_b["n_tiles"], info_b["n_tiles_next"]))
+            lo, hi = shard_ranges_by_work(est, world)[rank]
     for w in range(args.warmup):
         info_w, _ = step()
-        if world > 1 and w < min(4, args.warmup - 2):
-            # re-cut the source ranges at equal MEASURED time: SM cycles per source pose of the search that just
-            # ran, scaled so that a rank's poses add up to its kernel time, summed over the ranks.  Setup-time
-            # exchange (not on the per-step data path); the last warm-up steps run on the final ranges.
-            wk = gpu.stf_work().astype(np.float64)
-            if wk.sum() > 0:
-                wk *= info_w["ms_search"] / wk.sum()
-            work = torch.from_numpy(wk).cuda()
-            dist.all_reduce(work)
-            lo, hi = shard_ranges_by_work(work.cpu().numpy(), world)[rank]
         if os.environ.get("HITL_BENCH_DEBUG"):
-            sys.stderr.write("[rank %d] warmup %d: ms_search %.3f ms_total %.3f tiles %d -> %d, next range [%d, %d)\n" % (rank, w, info_w["ms_search"], info_w["ms_total"], info_w["n_tiles"], info_w["n_tiles_next"], lo, hi))
+            sys.stderr.write("[rank %d] warmup %d: ms_search %.3f ms_total %.3f tiles %d -> %d, range [%d, %d)\n" % (rank, w, info_w["ms_search"], info_w["ms_total"], info_w["n_tiles"], info_w["n_tiles_next"], lo, hi))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

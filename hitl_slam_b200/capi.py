@@ -44,7 +44,7 @@ class StfOpts(C.Structure):
 class StfInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
                 ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float),
-                ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
+                ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("sum_tile_cycles", C.c_uint64), ("max_tile_cycles", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
 
 
 class EvalLayout(C.Structure):
@@ -116,7 +116,7 @@ class HitlGpu:
         lib.hitl_normal_eq.argtypes = [vp, _f64p, vp, vp, vp, vp, C.POINTER(C.c_float)]
         lib.hitl_normal_eq_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         lib.hitl_debug_tile_work.argtypes = [vp, C.c_uint32, _u32p, C.POINTER(C.c_uint32)]
-        lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int]
+        lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int, C.c_uint32]
         lib.hitl_debug_set_fine_occupancy.argtypes = [vp, C.c_int]
         lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int, C.c_int]
         lib.hitl_debug_sincos.argtypes = [vp, C.c_uint64, _f32p, _f32p, _f32p]
@@ -210,7 +210,7 @@ class HitlGpu:
         info = StfInfo()
         self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
         res = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
-                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, n_coarse_pass=info.n_coarse_pass, n_in_radius=info.n_in_radius, ms_search=info.ms_search, ms_total=info.ms_total,
+                   n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, n_coarse_pass=info.n_coarse_pass, n_in_radius=info.n_in_radius, sum_tile_cycles=info.sum_tile_cycles, max_tile_cycles=info.max_tile_cycles, ms_search=info.ms_search, ms_total=info.ms_total,
                    n_tiles=info.n_tiles, n_tiles_next=info.n_tiles_next)
         if fetch:
             res.update(self.get_stf(info.n_pairs, info.n_matches, out))
@@ -363,8 +363,8 @@ class HitlGpu:
         self._ck(self.lib.hitl_debug_tile_work(self.ctx, n.value, w, C.byref(n)))
         return w[:n.value].astype(np.uint64) * 64
 
-    def debug_set_tiling(self, max_len=32, adaptive=True):
-        self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive)))
+    def debug_set_tiling(self, max_len=32, adaptive=True, target_parts=1):
+        self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive), int(target_parts)))
 
     def debug_set_search_variant(self, variant=0, smem_carveout_pct=-1):
         self._ck(self.lib.hitl_debug_set_search_variant(self.ctx, int(variant), int(smem_carveout_pct)))

@@ -25,26 +25,44 @@ int launch_scan_aabb(hitl_ctx* ctx);
 int upload_tiling(hitl_ctx* ctx) {
   const uint32_t nt = (uint32_t)ctx->h_tile_scan.size();
   ctx->n_tiles = nt;
+  // record slots and target-axis groups: unit 0 of a group (and every unsplit tile) writes at its points' own slots
+  ctx->h_tile_slot.resize(nt);
+  std::vector<uint2> groups;
+  uint64_t extra = 0;
+  for (uint32_t t = 0; t < nt;) {
+    uint32_t e = t + 1;
+    const bool split = ctx->h_tile_jlo[t] != 0 || ctx->h_tile_jhi[t] != kFullRange;
+    if (split) while (e < nt && ctx->h_tile_scan[e] == ctx->h_tile_scan[t] && ctx->h_tile_kl[e] == ctx->h_tile_kl[t] && ctx->h_tile_jlo[e] == ctx->h_tile_jhi[e - 1] + 1) ++e;
+    const uint32_t len = ctx->h_tile_kl[t] >> 16;
+    ctx->h_tile_slot[t] = ctx->h_off[ctx->h_tile_scan[t]] + (ctx->h_tile_kl[t] & 0xFFFFu);
+    for (uint32_t u = t + 1; u < e; ++u) { ctx->h_tile_slot[u] = (uint32_t)(ctx->n_points + extra); extra += len; }
+    if (e - t > 1) groups.push_back(make_uint2(t, e - t));
+    t = e;
+  }
+  ctx->n_slots = ctx->n_points + extra;
+  ctx->n_groups = (uint32_t)groups.size();
   // per-tile cost estimates (0 = never searched) and the identity permutation the scheduler sorts by them
   HITL_CUDA(ctx->d_tile_work.ensure(nt)); HITL_CUDA(ctx->d_tile_order.ensure(nt)); HITL_CUDA(ctx->d_tile_iota.ensure(nt)); HITL_CUDA(ctx->d_tile_keys.ensure(nt));
+  HITL_CUDA(ctx->d_tile_scan.ensure(nt)); HITL_CUDA(ctx->d_tile_k0.ensure(nt)); HITL_CUDA(ctx->d_tile_begin.ensure(ctx->n_poses + 1));
+  HITL_CUDA(ctx->d_tile_j.ensure(nt)); HITL_CUDA(ctx->d_tile_slot.ensure(nt)); HITL_CUDA(ctx->d_groups.ensure(groups.size()));
+  std::vector<uint32_t> iota(nt);
+  std::vector<uint2> tj(nt);
+  for (uint32_t t = 0; t < nt; ++t) { iota[t] = t; tj[t] = make_uint2(ctx->h_tile_jlo[t], ctx->h_tile_jhi[t]); }
   if (nt) {
     HITL_CUDA(cudaMemsetAsync(ctx->d_tile_work.p, 0, 4 * (size_t)nt, ctx->stream));
-    std::vector<uint32_t> iota(nt);
-    for (uint32_t t = 0; t < nt; ++t) iota[t] = t;
     HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_iota.p, iota.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
-    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  HITL_CUDA(ctx->d_tile_scan.ensure(nt)); HITL_CUDA(ctx->d_tile_k0.ensure(nt)); HITL_CUDA(ctx->d_tile_begin.ensure(ctx->n_poses + 1));
-  if (nt) {
     HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_scan.p, ctx->h_tile_scan.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
     HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_k0.p, ctx->h_tile_kl.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_j.p, tj.data(), 8 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_slot.p, ctx->h_tile_slot.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (!groups.empty()) HITL_CUDA(cudaMemcpyAsync(ctx->d_groups.p, groups.data(), 8 * groups.size(), cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_begin.p, ctx->h_tile_begin.data(), 4 * (size_t)(ctx->n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
-  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // the staging vectors are locals
   return HITL_OK;
 }
 
-// Uniform tiling: every scan cut into tiles of at most max_len points.
+// Uniform tiling: every scan cut into tiles of at most max_len points, each over the full target range.
 int build_tiling(hitl_ctx* ctx, uint32_t max_len) {
   if (max_len < 1) max_len = 1;
   if (max_len > 32) max_len = 32;
@@ -58,32 +76,64 @@ int build_tiling(hitl_ctx* ctx, uint32_t max_len) {
     for (uint32_t k0 = 0; k0 < n; k0 += max_len) { ctx->h_tile_scan.push_back(i); ctx->h_tile_kl.push_back(k0 | (std::min(max_len, n - k0) << 16)); }
   }
   ctx->h_tile_begin[n_poses] = (uint32_t)ctx->h_tile_scan.size();
+  ctx->h_tile_jlo.assign(ctx->h_tile_scan.size(), 0u);
+  ctx->h_tile_jhi.assign(ctx->h_tile_scan.size(), kFullRange);
   ctx->tiling_splits = 0;
   return upload_tiling(ctx);
 }
 
-// Splits every tile whose measured work (cycles / 64, h_work indexed by tile id, tiles in [lo, hi)) exceeds
-// `limit` into 2, 4 or 8 equal parts (never below 4 points).  Returns the number of tiles that were split.
-uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, uint32_t lo, uint32_t hi, uint64_t limit, std::vector<uint32_t>* est) {
-  std::vector<uint32_t> scan, kl;
-  est->clear(); est->reserve(ctx->h_tile_scan.size() + 1024);
-  scan.reserve(ctx->h_tile_scan.size() + 1024); kl.reserve(ctx->h_tile_scan.size() + 1024);
+// Splits every tile whose measured work (cycles / 64, h_work indexed by tile id, tiles in [lo, hi)) exceeds `limit`:
+// first along the points into 2, 4 or 8 equal parts (never below 4 points), then — a tile is a sequential loop over
+// the target poses, so a few points that never reach the cap keep it alive through all of them — along the TARGET
+// axis into up to 16 consecutive ranges (never below 64 target poses) that different warps search concurrently
+// (stf_split_merge_kernel re-applies the per-point cap across the ranges).  Returns the number of tiles that were split.
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, uint32_t lo, uint32_t hi, uint64_t limit,
+                           std::vector<uint32_t>* est) {
+  std::vector<uint32_t> scan, kl, jlo, jhi;
+  const size_t cap0 = ctx->h_tile_scan.size() + 1024;
+  est->clear(); est->reserve(cap0);
+  scan.reserve(cap0); kl.reserve(cap0); jlo.reserve(cap0); jhi.reserve(cap0);
   std::vector<uint32_t> begin(ctx->n_poses + 1, 0);
   uint32_t n_split = 0, pose = 0;
+  const uint32_t last_pose = ctx->n_poses ? ctx->n_poses - 1 : 0;
   for (uint32_t t = 0; t < (uint32_t)ctx->h_tile_scan.size(); ++t) {
     const uint32_t i = ctx->h_tile_scan[t], k0 = ctx->h_tile_kl[t] & 0xFFFFu, len = ctx->h_tile_kl[t] >> 16;
+    const uint32_t a = ctx->h_tile_jlo[t], b = ctx->h_tile_jhi[t];
     while (pose <= i) begin[pose++] = (uint32_t)scan.size();
-    uint32_t parts = 1;
-    if (t >= lo && t < hi && h_work[t - lo] > limit) {
-      while (parts < 8 && len / (parts * 2) >= 4 && (uint64_t)h_work[t - lo] > limit * parts) parts *= 2;
+    const bool measured = t >= lo && t < hi;
+    const uint64_t work = measured ? h_work[t - lo] : 0;
+    uint32_t parts = 1, jparts = 1;
+    if (work > limit) {
+      const bool is_unit = a != 0 || b != kFullRange;                       // units of a group keep their points (the group must stay aligned)
+      if (!is_unit) while (parts < 8 && len / (parts * 2) >= 4 && work > limit * parts) parts *= 2;
+      // only tiles that some point kept alive to the end of the target range: a tile whose points all reach the cap
+      // would redo its whole matching phase in every range
+      if (ctx->target_splitting && h_open[t - lo] > 0 && work > limit * parts) {
+        const uint32_t ja = a, jb = std::min(b, last_pose);
+        const uint32_t span = jb >= ja ? jb - ja + 1 : 0;
+        jparts = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(16, span / 64), (work + limit * parts - 1) / (limit * parts));
+        if (jparts < 1) jparts = 1;
+      }
     }
-    if (parts > 1) ++n_split;
+    if (parts > 1 || jparts > 1) ++n_split;
     const uint32_t step = (len + parts - 1) / parts;
-    const uint32_t w = (t >= lo && t < hi) ? h_work[t - lo] / parts : 0;   // children inherit an equal share of the measured work
-    for (uint32_t a = 0; a < len; a += step) { scan.push_back(i); kl.push_back((k0 + a) | (std::min(step, len - a) << 16)); est->push_back(w); }
+    const uint32_t w = (uint32_t)(work / (parts * jparts));   // children inherit an equal share of the measured work
+    for (uint32_t p0 = 0; p0 < len; p0 += step) {
+      if (jparts == 1) { scan.push_back(i); kl.push_back((k0 + p0) | (std::min(step, len - p0) << 16)); jlo.push_back(a); jhi.push_back(b); est->push_back(w); continue; }
+      const uint32_t ja = a, jb = std::min(b, last_pose), span = jb - ja + 1;
+      for (uint32_t q = 0; q < jparts; ++q) {
+        const uint32_t qa = ja + (uint32_t)((uint64_t)span * q / jparts), qb = ja + (uint32_t)((uint64_t)span * (q + 1) / jparts) - 1;
+        scan.push_back(i); kl.push_back((k0 + p0) | (std::min(step, len - p0) << 16));
+        jlo.push_back(qa); jhi.push_back(q + 1 == jparts ? b : qb);           // the last range keeps the original (possibly open) end
+        est->push_back(w);
+      }
+    }
   }
   while (pose <= ctx->n_poses) begin[pose++] = (uint32_t)scan.size();
-  if (n_split) { ctx->h_tile_scan.swap(scan); ctx->h_tile_kl.swap(kl); ctx->h_tile_begin.swap(begin); ctx->tiling_splits += n_split; }
+  if (n_split) {
+    ctx->h_tile_scan.swap(scan); ctx->h_tile_kl.swap(kl); ctx->h_tile_begin.swap(begin); ctx->h_tile_jlo.swap(jlo); ctx->h_tile_jhi.swap(jhi);
+    ctx->tiling_splits += n_split;
+  }
   return n_split;
 }
 }  // namespace hitl
@@ -114,7 +164,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
   ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release();
-  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
   ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();

@@ -64,13 +64,23 @@ struct hitl_ctx {
   uint32_t n_tiles = 0;
   hitl::DevBuf<uint32_t> d_tile_scan, d_tile_k0, d_tile_begin;   // tile -> scan, first point | length << 16; scan -> first tile
   std::vector<uint32_t> h_tile_scan, h_tile_kl, h_tile_begin;    // host mirrors of the three tables
+  // A heavy tile may further be cut along the TARGET axis into consecutive "units" (same points, disjoint ascending
+  // target ranges [jlo, jhi], full range = [0, 0xFFFFFFFF]); every unit is a tile of its own for the scheduler.  Unit 0
+  // of a group keeps the tile's record slot (off + k0), the others get slots after the last point.
+  std::vector<uint32_t> h_tile_jlo, h_tile_jhi, h_tile_slot;
+  hitl::DevBuf<uint2> d_tile_j;                                  // (jlo, jhi)
+  hitl::DevBuf<uint32_t> d_tile_slot;                            // record region of the unit = slot * cap
+  hitl::DevBuf<uint2> d_groups;                                  // (first unit, units) of every tile that is split along the target axis
+  uint32_t n_groups = 0;
+  uint64_t n_slots = 0;                                          // n_points + extra slots of the split units
   uint32_t tiling_splits = 0;                                    // heavy tiles split so far (adaptive tiling)
   uint32_t split_rounds = 0, split_lo = 0, split_hi = 0;         // split rounds done for the source range [split_lo, split_hi)
   int adaptive_tiling = 1;
+  int target_splitting = 1;              // heavy tiles may also be cut along the target axis (hitl_debug_set_tiling)
   int search_carveout = -1;              // preferred shared-memory carve-out in percent (-1: driver default)
   int search_variant = 0;                // 0: 16 CTAs/SM (32 regs), 1: 12 CTAs/SM (40 regs), 2: 10 CTAs/SM (hitl_debug_set_search_variant)
   // scheduling hint of the search: tiles sorted by the cycles the previous call spent on them
-  hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys;
+  hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys, d_tile_open;
   hitl::DevBuf<uint8_t> d_sort_tmp;
 
   // ---- trees ----
@@ -157,7 +167,9 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
 
 int build_tiling(hitl_ctx* ctx, uint32_t max_len);
 int upload_tiling(hitl_ctx* ctx);
-uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, uint32_t lo, uint32_t hi, uint64_t limit, std::vector<uint32_t>* est);
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, uint32_t lo, uint32_t hi, uint64_t limit,
+                           std::vector<uint32_t>* est);
+constexpr uint32_t kFullRange = 0xFFFFFFFFu;
 // host tree builder (kdtree_build.cpp)
 void build_flat_kdtree(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out);
 }  // namespace hitl

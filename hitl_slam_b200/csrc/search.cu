@@ -359,6 +359,7 @@ struct SearchParams {
   const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
   const uint32_t* __restrict__ occ; const uint32_t* __restrict__ occ_fine;
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
+  const uint2* __restrict__ tile_j; const uint32_t* __restrict__ tile_slot;   // target range of the unit, record slot
   uint32_t tile_lo, tile_hi;          // tiles of the source shard
   uint32_t jmin, jmax;                // inclusive target range
   float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
@@ -367,6 +368,7 @@ struct SearchParams {
   unsigned long long* __restrict__ pose_work;  // SM cycles spent on the tiles of each source pose (load-balancing feedback)
   const uint32_t* __restrict__ tile_order;     // tiles of the shard, most expensive first (from the previous call), or null
   uint32_t* __restrict__ tile_work;            // cycles / 64 per tile of this call
+  uint32_t* __restrict__ tile_open;            // points of the tile that ended below the cap (they kept it alive through all its targets)
 };
 
 constexpr int kSearchThreads = 128;
@@ -423,7 +425,10 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
       bx0 -= m; by0 -= m; bx1 += m; by1 += m;
     }
-    const uint32_t out_base = (i_off + k0) * (uint32_t)P.cap;   // this tile's private record region
+    const uint32_t out_base = P.tile_slot[tile] * (uint32_t)P.cap;   // this unit's private record region
+    const uint2 tj = P.tile_j[tile];
+    const bool is_unit = tj.x != 0 || tj.y != kFullRange;        // one of several target ranges of a split tile
+    const uint32_t jlo = max(P.jmin, tj.x), jhi = min(P.jmax, tj.y);
     uint32_t wcount = 0;                                        // records written by the warp
     uint32_t qn = 0, qw = 0;                                    // queued items: stage A (coarse-passed), stage B (to walk)
     bool active = valid;
@@ -527,12 +532,12 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       __syncwarp();
     };
 
-    if (__any_sync(0xffffffffu, active)) {
+    if (jlo <= jhi && __any_sync(0xffffffffu, active)) {
       bool all_done = false;
-      for (uint32_t jb = P.jmin & ~31u; jb <= P.jmax && !all_done; jb += 32) {
+      for (uint32_t jb = jlo & ~31u; jb <= jhi && !all_done; jb += 32) {
         // ---- stage 1: candidates of this block of 32 target poses ----
         const uint32_t jl = jb + lane;
-        bool hit = jl >= P.jmin && jl <= P.jmax && jl != i;
+        bool hit = jl >= jlo && jl <= jhi && jl != i;
         if (hit && !P.no_cull) {
           const float4 wb = __ldg(P.wbox + jl);
           hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
@@ -635,11 +640,12 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
         if (!__any_sync(0xffffffffu, active)) all_done = true;
       }
     }
-    if (lane == 0) P.tile_cnt[tile] = wcount;
+    const uint32_t open_pts = __popc(__ballot_sync(0xffffffffu, valid && W.cnt[lane] < (uint32_t)P.cap));
+    if (lane == 0) { P.tile_cnt[tile] = wcount; P.tile_open[tile] = open_pts; }
     // queries the reference semantics execute for this point: every j != i in range up to and
     // including the one that filled the cap (JointOptimization.cpp:597-600)
     unsigned long long exec = 0;
-    if (valid) {
+    if (valid && !is_unit) {                                    // split tiles: stf_split_merge_kernel counts after re-applying the cap
       const bool i_in_range = i >= P.jmin && i <= P.jmax;
       const uint32_t el = W.exec_last[lane];
       if (el == kNotCapped) exec = (unsigned long long)(P.jmax - P.jmin + 1) - (i_in_range ? 1 : 0);
@@ -665,6 +671,74 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1b': tiles split along the target axis.  Every unit searched its own target range with a private cap state, so a
+// point may hold up to `cap` matches PER UNIT.  The reference's sequential loop keeps the first `cap` matches of a
+// point in ascending target order and stops there: concatenating the units in range order and truncating every
+// point at `cap` gives exactly that (a unit's own first `cap` contain every match that can survive).  One warp per
+// group walks its units in order, drops the surplus records in place (lists stay sorted by (j, k)), rewrites the
+// unit counts, and accounts the queries the reference semantics execute (up to the target that filled the cap).
+// ------------------------------------------------------------------------------------------------
+struct MergeParams {
+  const uint2* __restrict__ groups; uint32_t n_groups, tile_lo, tile_hi;
+  const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0; const uint32_t* __restrict__ tile_slot;
+  const uint32_t* __restrict__ off;
+  uint32_t* raw_j; uint32_t* raw_k; uint32_t* raw_idx; uint32_t* tile_cnt;
+  uint32_t jmin, jmax, skip; int cap;
+  unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(128) stf_split_merge_kernel(const MergeParams P) {
+  __shared__ uint32_t s_cnt[4][32], s_last[4][32];
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  const uint32_t g = blockIdx.x * 4 + w;
+  if (g >= P.n_groups) return;
+  const uint2 grp = P.groups[g];
+  if (grp.x < P.tile_lo || grp.x >= P.tile_hi) return;            // group of another shard
+  const uint32_t i = P.tile_scan[grp.x], kl = P.tile_k0[grp.x], k0 = kl & 0xFFFFu, len = kl >> 16;
+  s_cnt[w][lane] = 0; s_last[w][lane] = kNotCapped;
+  __syncwarp();
+  unsigned long long dropped = 0;
+  for (uint32_t u = 0; u < grp.y; ++u) {
+    const uint32_t t = grp.x + u, c = P.tile_cnt[t], base = P.tile_slot[t] * (uint32_t)P.cap;
+    uint32_t wr = 0;
+    for (uint32_t r0 = 0; r0 < c; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      const bool have = r < c;
+      uint32_t j = 0, k = 0, idx = 0;
+      if (have) { j = P.raw_j[base + r]; k = P.raw_k[base + r]; idx = P.raw_idx[base + r]; }
+      const uint32_t o = have ? k - k0 : 32u + lane;
+      const uint32_t same = __match_any_sync(0xffffffffu, o);
+      const uint32_t earlier = __popc(same & lt);
+      const uint32_t prior = have ? s_cnt[w][o] : 0u;
+      const bool keep = have && prior + earlier < (uint32_t)P.cap;
+      const uint32_t km = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) {
+        const uint32_t dst = base + wr + __popc(km & lt);           // dst <= base + r: in-place compaction
+        P.raw_j[dst] = j; P.raw_k[dst] = k; P.raw_idx[dst] = idx;
+        atomicAdd(&s_cnt[w][o], 1u);
+        if (prior + earlier + 1 == (uint32_t)P.cap) s_last[w][o] = j;
+      }
+      wr += __popc(km);
+      __syncwarp();
+    }
+    dropped += c - wr;
+    if (lane == 0) P.tile_cnt[t] = wr;
+  }
+  // queries the reference semantics execute for each point of the tile (as in the search kernel for unsplit tiles)
+  const uint32_t i_n = P.off[i + 1] - P.off[i], k = k0 + lane;
+  unsigned long long exec = 0;
+  if (lane < len && k < i_n && (k % P.skip) == 0) {
+    const bool i_in_range = i >= P.jmin && i <= P.jmax;
+    const uint32_t el = s_last[w][lane];
+    if (el == kNotCapped) exec = (unsigned long long)(P.jmax - P.jmin + 1) - (i_in_range ? 1 : 0);
+    else exec = (unsigned long long)(el - P.jmin + 1) - ((i_in_range && i <= el) ? 1 : 0);
+  }
+  for (int o = 16; o; o >>= 1) exec += __shfl_xor_sync(0xffffffffu, exec, o);
+  if (lane == 0) { atomicAdd(P.counters + 0, exec); atomicAdd(P.counters + 2, 0ull - dropped); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1c: order the per-tile records of each source pose by (j, k), drop pairs with <= min_corr
 // matches, emit CSR.  Each CTA owns a private u32[n_poses] scratch slice indexed by j.
 //   pass 0 (count): per pose -> kept matches / kept pairs
@@ -676,7 +750,7 @@ constexpr uint32_t kDropped = 0xFFFFFFFFu;
 
 struct OrderParams {
   const uint32_t* __restrict__ raw_j; const uint32_t* __restrict__ raw_k; const uint32_t* __restrict__ raw_idx;
-  const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ tile_k0; const uint32_t* __restrict__ off;
+  const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ tile_slot; const uint32_t* __restrict__ off;
   uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
   uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
   uint32_t* kept;                     // gridDim.x * n_poses: kept target poses of the pose being placed (pass 1)
@@ -725,13 +799,12 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
   uint32_t* const keptj = PASS == 1 ? P.kept + (size_t)blockIdx.x * P.n_poses : nullptr;
   for (uint32_t i = P.src_lo + blockIdx.x; i < P.src_hi; i += gridDim.x) {
     const uint32_t tb = P.tile_begin[i], te = P.tile_begin[i + 1];
-    const uint32_t seg = P.off[i] * (uint32_t)P.cap;
     if (threadIdx.x == 0) { s_jlo = 0xFFFFFFFFu; s_jhi = 0; }
     __syncthreads();
     // -- histogram over j (tile lists are sorted by j: first/last record bound the range) --
     uint32_t jlo = 0xFFFFFFFFu, jhi = 0;
     for (uint32_t t = tb; t < te; ++t) {
-      const uint32_t c = P.tile_cnt[t], base = seg + (P.tile_k0[t] & 0xFFFFu) * (uint32_t)P.cap;
+      const uint32_t c = P.tile_cnt[t], base = P.tile_slot[t] * (uint32_t)P.cap;
       for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
         const uint32_t j = P.raw_j[base + u];
         atomicAdd(&cntj[j], 1u);
@@ -781,7 +854,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
             uint32_t lb = 0, len = 0, base = 0;
             if (t < ntile) {
               const uint32_t c = P.tile_cnt[tb + t];
-              base = seg + (P.tile_k0[tb + t] & 0xFFFFu) * (uint32_t)P.cap;
+              base = P.tile_slot[tb + t] * (uint32_t)P.cap;
               uint32_t lo = 0, hi = c;                                   // lower_bound(j)
               while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (P.raw_j[base + mid] < j) lo = mid + 1; else hi = mid; }
               lb = lo;
@@ -1018,9 +1091,9 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     return HITL_OK;
   }
   const uint32_t jmin = min_pose, jmax = (uint32_t)poses_end - 1;
-  const size_t rec_cap = (size_t)ctx->n_points * cap;
-  if (rec_cap >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: n_points * cap exceeds 2^32 records");
-  HITL_CUDA(ctx->d_raw_j.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_k.ensure(rec_cap)); HITL_CUDA(ctx->d_raw_idx.ensure(rec_cap));
+  const size_t rec_cap = (size_t)ctx->n_points * cap, raw_cap = (size_t)ctx->n_slots * cap;
+  if (raw_cap >= 0xFFFFFFFFull) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: n_points * cap exceeds 2^32 records");
+  HITL_CUDA(ctx->d_raw_j.ensure(raw_cap)); HITL_CUDA(ctx->d_raw_k.ensure(raw_cap)); HITL_CUDA(ctx->d_raw_idx.ensure(raw_cap));
   HITL_CUDA(ctx->d_tile_cnt.ensure(ctx->n_tiles));
   HITL_CUDA(ctx->d_counters.ensure(16));
   HITL_CUDA(ctx->d_pose_cnt.ensure(2 * (size_t)n + 2));
@@ -1038,6 +1111,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
+  P.tile_j = ctx->d_tile_j.p; P.tile_slot = ctx->d_tile_slot.p;
   P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
   P.jmin = jmin; P.jmax = jmax; P.thr = o->point_match_threshold; P.min_cos = o->min_cosine_angle; P.cap = cap;
   P.skip = o->num_skip_readings; P.no_cull = o->disable_culling;
@@ -1045,6 +1119,8 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.counters = (unsigned long long*)ctx->d_counters.p;
   P.pose_work = (unsigned long long*)ctx->d_pose_work.p;
   P.tile_work = ctx->d_tile_work.p;
+  HITL_CUDA(ctx->d_tile_open.ensure(ctx->n_tiles));
+  P.tile_open = ctx->d_tile_open.p;
   P.tile_order = nullptr;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
@@ -1073,10 +1149,19 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (ctx->n_groups && n_tiles) {
+    MergeParams M;
+    M.groups = ctx->d_groups.p; M.n_groups = ctx->n_groups; M.tile_lo = P.tile_lo; M.tile_hi = P.tile_hi;
+    M.tile_scan = ctx->d_tile_scan.p; M.tile_k0 = ctx->d_tile_k0.p; M.tile_slot = ctx->d_tile_slot.p; M.off = ctx->d_off.p;
+    M.raw_j = ctx->d_raw_j.p; M.raw_k = ctx->d_raw_k.p; M.raw_idx = ctx->d_raw_idx.p; M.tile_cnt = ctx->d_tile_cnt.p;
+    M.jmin = jmin; M.jmax = jmax; M.skip = o->num_skip_readings; M.cap = cap; M.counters = (unsigned long long*)ctx->d_counters.p;
+    stf_split_merge_kernel<<<(ctx->n_groups + 3) / 4, 128, 0, ctx->stream>>>(M);
+    HITL_LAUNCH_CHECK("stf_split_merge_kernel");
+  }
 
   OrderParams Q;
   Q.raw_j = ctx->d_raw_j.p; Q.raw_k = ctx->d_raw_k.p; Q.raw_idx = ctx->d_raw_idx.p; Q.tile_cnt = ctx->d_tile_cnt.p;
-  Q.tile_begin = ctx->d_tile_begin.p; Q.tile_k0 = ctx->d_tile_k0.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
+  Q.tile_begin = ctx->d_tile_begin.p; Q.tile_slot = ctx->d_tile_slot.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
   Q.min_corr = o->min_inter_pose_correspondence;
   const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)ctx->sm_count * 8);
   HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
@@ -1096,6 +1181,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
   inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5]; inf.n_coarse_pass = ctx->h_pinned[9]; inf.n_in_radius = ctx->h_pinned[10];
+  inf.sum_tile_cycles = ctx->h_pinned[7] << 6; inf.max_tile_cycles = ctx->h_pinned[8] << 6;
   const uint64_t work_sum = ctx->h_pinned[7];
   // terminating offset of the CSR
   HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1114,11 +1200,12 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     const uint64_t limit = std::max<uint64_t>(fair / 2, 4096);               // never split tiles cheaper than ~0.13 ms
     const uint64_t h_max = ctx->h_pinned[8];                                 // heaviest tile of this call
     if (ctx->split_lo != lo || ctx->split_hi != hi) { ctx->split_lo = lo; ctx->split_hi = hi; ctx->split_rounds = 0; }
-    if (h_max > 2 * limit && ctx->split_rounds < 3) {
+    if (h_max > 2 * limit && ctx->split_rounds < 4) {
       ++ctx->split_rounds;
-      std::vector<uint32_t> h_work(n_tiles), est;
+      std::vector<uint32_t> h_work(n_tiles), h_open(n_tiles), est;
       HITL_CUDA(cudaMemcpy(h_work.data(), ctx->d_tile_work.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
-      if (split_heavy_tiles(ctx, h_work, P.tile_lo, P.tile_hi, limit, &est)) {
+      HITL_CUDA(cudaMemcpy(h_open.data(), ctx->d_tile_open.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+      if (split_heavy_tiles(ctx, h_work, h_open, P.tile_lo, P.tile_hi, limit, &est)) {
         rc = upload_tiling(ctx);
         if (rc) return rc;
         const uint32_t new_lo = ctx->h_tile_begin[lo], new_hi = ctx->h_tile_begin[hi], nn = new_hi - new_lo;
@@ -1132,11 +1219,30 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   return HITL_OK;
 }
 
-extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive) {
+extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_t target_parts) {
   if (!ctx) return HITL_ERR_ARG;
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_debug_set_tiling: scans not set");
-  ctx->adaptive_tiling = adaptive;
-  return build_tiling(ctx, max_len);
+  ctx->adaptive_tiling = adaptive != 0;
+  ctx->target_splitting = adaptive == 1;
+  ctx->split_rounds = 0;
+  int rc = build_tiling(ctx, max_len);
+  if (rc || target_parts <= 1 || ctx->n_poses < 2) return rc;
+  // forced uniform cut of EVERY tile into target_parts consecutive target ranges (parity tests of the cap merge)
+  const uint32_t parts = std::min(target_parts, ctx->n_poses);
+  std::vector<uint32_t> scan, kl, jlo, jhi, begin(ctx->n_poses + 1, 0);
+  uint32_t pose = 0;
+  for (uint32_t t = 0; t < (uint32_t)ctx->h_tile_scan.size(); ++t) {
+    const uint32_t i = ctx->h_tile_scan[t];
+    while (pose <= i) begin[pose++] = (uint32_t)scan.size();
+    for (uint32_t q = 0; q < parts; ++q) {
+      scan.push_back(i); kl.push_back(ctx->h_tile_kl[t]);
+      jlo.push_back((uint32_t)((uint64_t)ctx->n_poses * q / parts));
+      jhi.push_back(q + 1 == parts ? kFullRange : (uint32_t)((uint64_t)ctx->n_poses * (q + 1) / parts) - 1);
+    }
+  }
+  while (pose <= ctx->n_poses) begin[pose++] = (uint32_t)scan.size();
+  ctx->h_tile_scan.swap(scan); ctx->h_tile_kl.swap(kl); ctx->h_tile_jlo.swap(jlo); ctx->h_tile_jhi.swap(jhi); ctx->h_tile_begin.swap(begin);
+  return upload_tiling(ctx);
 }
 
 extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int smem_carveout_pct) {

@@ -112,6 +112,8 @@ typedef struct {
   float ms_total;         /* device time of the whole call: pose prep + search + ordering/compaction */
   uint64_t n_coarse_pass; /* (point, target) items that passed the coarse occupancy level (candidates of the fine level) */
   uint64_t n_in_radius;   /* tree walks that found a node inside the radius (the rest proved "no neighbour" the slow way) */
+  uint64_t sum_tile_cycles; /* SM cycles the resident warps spent inside tiles, summed over all tiles of this call */
+  uint64_t max_tile_cycles; /* ... and of the single most expensive tile: the kernel's critical path (a tile is a sequential loop) */
   uint32_t n_tiles;       /* work units (runs of <= 32 source points) the search kernel scheduled in this call */
   uint32_t n_tiles_next;  /* ... and after the adaptive split of heavy tiles that this call's measurements triggered */
 } hitl_stf_info;
@@ -208,9 +210,11 @@ int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
 /* SM cycles / 64 the last hitl_find_stf spent on each 32-point tile (tiles outside the searched range keep
  * stale values); profiling aid for the tile scheduler. */
 int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32_t* n_tiles_out);
-/* Re-cuts every scan into tiles of at most max_len (1..32) points and switches the automatic splitting of
- * heavy tiles on or off.  The tiling is a scheduling choice; parity tests use this to prove it. */
-int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive);
+/* Re-cuts every scan into tiles of at most max_len (1..32) points and sets the automatic splitting of heavy tiles:
+ * adaptive 0 = off, 1 = along the points and along the target axis, 2 = along the points only.  target_parts > 1
+ * additionally cuts EVERY tile into that many consecutive target ranges that are searched concurrently and merged
+ * under the per-point cap.  The tiling is a scheduling choice; parity tests use this to prove it. */
+int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_t target_parts);
 /* Switches the second (fine, cell = threshold / 4) level of the occupancy cull on or off; the bitmaps are rebuilt by the
  * next search.  Culling is result-preserving; parity tests compare both settings and disable_culling = 1. */
 int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);

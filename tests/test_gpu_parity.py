@@ -189,6 +189,31 @@ def test_find_stf_is_independent_of_the_tiling(gpu, oracle, maps, max_len):
         gpu.debug_set_tiling(32, adaptive=True)
 
 
+@pytest.mark.parametrize("max_len,parts", [(32, 2), (32, 5), (9, 16), (1, 3)])
+def test_find_stf_target_axis_split_reapplies_the_cap(gpu, oracle, maps, max_len, parts):
+    """A tile may be cut into consecutive TARGET ranges searched concurrently, each with a private cap state; the
+    merge keeps each point's first `cap` matches in target order, which is the reference's sequential loop."""
+    g = maps("small")
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    ref = S.find_stf(poses)
+    try:
+        gpu.debug_set_tiling(max_len, adaptive=False, target_parts=parts)
+        for cull in (0, 1):
+            out = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=cull))
+            assert_same_stf(out, ref)
+            assert out["n_queries"] == ref["n_queries"]
+        assert_same_stf(gpu.find_stf(poses, src_lo=20, src_hi=77), S.find_stf(poses, src_lo=20, src_hi=77))
+        for cap, skip, min_corr in ((2, 1, 10), (1, 3, 2), (11, 2, 0)):
+            out = gpu.find_stf(poses, min_pose=7, max_pose=140, opts=gpu.stf_opts(cap=cap, skip=skip, min_corr=min_corr))
+            want = S.find_stf(poses, min_pose=7, max_pose=140, cap=cap, skip=skip, min_corr=min_corr)
+            assert_same_stf(out, want)
+            assert out["n_queries"] == want["n_queries"]
+    finally:
+        gpu.debug_set_tiling(32, adaptive=True)
+
+
 def test_find_stf_adaptive_tile_splitting_keeps_results(gpu, oracle, maps):
     """Heavy tiles are split after a search that was dominated by them (here: forced by a tiny shard);
     later searches over any range still return the reference's lists."""
