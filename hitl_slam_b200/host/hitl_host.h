@@ -22,6 +22,7 @@ float hitl_host_sinf(float x);
 float hitl_host_cosf(float x);
 uint64_t hitl_host_sincos_mismatches(uint64_t first, uint64_t count, uint64_t stride);
 void hitl_host_relative_pose(const double* pose_array, uint32_t src, uint32_t dst, float* out6);
+uint64_t hitl_host_stdsort_mismatches(const float* keys, uint32_t n, uint32_t* out_std, uint32_t* out_restated, uint32_t* heap_sorts);
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,9 @@
 #include <thread>
 #include <vector>
 #include "hitl_host.h"
+#include <algorithm>
 #include "hitl_math.h"
+#include "stdsort_exact.h"
 
 extern "C" {
 float hitl_host_sinf(float x) { return hitl::sinf_rn(x); }
@@ -35,6 +37,21 @@ uint64_t hitl_host_sincos_mismatches(uint64_t first, uint64_t count, uint64_t st
     });
   for (auto& x : th) x.join();
   return bad.load();
+}
+
+// Sorts ids 0..n-1 by keys[id] twice: with this image's std::sort and with the restatement of libstdc++'s introsort the GPU
+// tree builder uses for segments that contain equal keys (csrc/stdsort_exact.h).  Returns the number of positions that differ.
+uint64_t hitl_host_stdsort_mismatches(const float* keys, uint32_t n, uint32_t* out_std, uint32_t* out_restated, uint32_t* heap_sorts) {
+  std::vector<uint32_t> a(n), b(n);
+  for (uint32_t i = 0; i < n; ++i) a[i] = b[i] = i;
+  std::sort(a.begin(), a.end(), [keys](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  const uint32_t hs = hitl::stdsort::sort_ids(b.data(), (int64_t)n, [keys](uint32_t id) { return keys[id]; });
+  if (heap_sorts) *heap_sorts = hs;
+  uint64_t bad = 0;
+  for (uint32_t i = 0; i < n; ++i) bad += a[i] != b[i];
+  if (out_std) memcpy(out_std, a.data(), 4 * (size_t)n);
+  if (out_restated) memcpy(out_restated, b.data(), 4 * (size_t)n);
+  return bad;
 }
 
 void hitl_host_relative_pose(const double* pose_array, uint32_t src, uint32_t dst, float* out6) {
