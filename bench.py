@@ -374,7 +374,7 @@ def main():
     if rank == 0:
         cfg = config_of(args, g)
         cfg.update({"parallelism": "source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 all-reduce of packed J^TJ/J^Tr per step" % world if world > 1 else "single GPU",
-                    "kdtree_build_host_s": t_build})
+                    "kdtree_build_device_s": t_build})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction,

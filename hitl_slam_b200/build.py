@@ -24,6 +24,7 @@ GPU_SOURCES = [
     ("ctx.cu", ["--fmad=false"]),
     ("search.cu", ["--fmad=false"]),
     ("em.cu", ["--fmad=false"]),
+    ("kdtree_gpu.cu", ["--fmad=false"]),
     ("eval.cu", []),
     ("kdtree_build.cpp", []),
 ]
@@ -47,7 +48,7 @@ def _run(cmd):
 def build_gpu(force=False, verbose=False):
     """Compile every CUDA translation unit for sm_100a and link libhitl_gpu.so."""
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("hitl_internal.h", "hitl_math.h")] + [os.path.join(HERE, "..", "include", "hitl_gpu.h")]
+    headers = [os.path.join(CSRC, h) for h in ("hitl_internal.h", "hitl_math.h", "stdsort_exact.h")] + [os.path.join(HERE, "..", "include", "hitl_gpu.h")]
     objs = []
     for name, extra in GPU_SOURCES:
         src = os.path.join(CSRC, name)

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
     "hitl_normal_eq_device", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
-    "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant",
+    "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
 
 
@@ -119,6 +119,8 @@ class HitlGpu:
         lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int, C.c_uint32]
         lib.hitl_debug_set_fine_occupancy.argtypes = [vp, C.c_int]
         lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int, C.c_int]
+        lib.hitl_debug_set_tree_builder.argtypes = [vp, C.c_int]
+        lib.hitl_debug_tree_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         lib.hitl_debug_sincos.argtypes = [vp, C.c_uint64, _f32p, _f32p, _f32p]
         lib.hitl_debug_relative_pose.argtypes = [vp, _f64p, C.c_uint32, _u32p, _u32p, _f32p]
         self.ctx = vp()
@@ -365,6 +367,14 @@ class HitlGpu:
 
     def debug_set_tiling(self, max_len=32, adaptive=True, target_parts=1):
         self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive), int(target_parts)))
+
+    def debug_set_tree_builder(self, host=False):
+        self._ck(self.lib.hitl_debug_set_tree_builder(self.ctx, int(host)))
+
+    def debug_tree_stats(self):
+        n = C.c_uint64()
+        self._ck(self.lib.hitl_debug_tree_stats(self.ctx, C.byref(n)))
+        return int(n.value)
 
     def debug_set_search_variant(self, variant=0, smem_carveout_pct=-1):
         self._ck(self.lib.hitl_debug_set_search_variant(self.ctx, int(variant), int(smem_carveout_pct)))

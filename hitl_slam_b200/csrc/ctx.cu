@@ -293,6 +293,12 @@ extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
 extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
   if (!ctx) return HITL_ERR_ARG;
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_build_kdtrees: call hitl_set_scans first");
+  if (ctx->tree_builder == 0) {
+    ctx->have_trees = false;
+    const int rc = build_kdtrees_device(ctx, &ctx->tree_exact_segments);
+    if (rc == HITL_OK) ctx->have_trees = true;
+    return rc;
+  }
   std::vector<hitl_kdnode> nodes(ctx->n_points);
   const uint32_t n = ctx->n_poses;
   if (ctx->h_pts.size() != 2 * ctx->n_points) {   // the builder runs on the host: fetch the resident clouds
@@ -315,6 +321,17 @@ extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
     });
   for (auto& x : th) x.join();
   return upload_trees(ctx, nodes.data());
+}
+
+extern "C" int hitl_debug_set_tree_builder(hitl_ctx* ctx, int host) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->tree_builder = host ? 1 : 0;
+  return HITL_OK;
+}
+extern "C" int hitl_debug_tree_stats(hitl_ctx* ctx, uint64_t* exact_segments) {
+  if (!ctx || !exact_segments) return HITL_ERR_ARG;
+  *exact_segments = ctx->tree_exact_segments;
+  return HITL_OK;
 }
 
 extern "C" int hitl_kdtree_build_host(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out) {

@@ -85,6 +85,8 @@ struct hitl_ctx {
 
   // ---- trees ----
   bool have_trees = false;
+  int tree_builder = 0;                  // 0: device (kdtree_gpu.cu), 1: host threads (kdtree_build.cpp)   (hitl_debug_set_tree_builder)
+  uint64_t tree_exact_segments = 0;      // segments of the last device build that needed the exact std::sort emulation (equal keys)
   hitl::DevBuf<float4> d_node_pm;        // px, py, bits(index | dim << 31), 0   (preorder, concatenated): one 16 B load per node visit
   hitl::DevBuf<float2> d_node_nn;        // nx, ny   (read only for nodes inside the query radius)
   hitl::DevBuf<hitl_kdnode> d_node_aos;  // staging for hitl_set_kdtrees / hitl_get_kdtrees (AoS <-> SoA on the device)
@@ -170,6 +172,8 @@ int upload_tiling(hitl_ctx* ctx);
 uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, uint32_t lo, uint32_t hi, uint64_t limit,
                            std::vector<uint32_t>* est);
 constexpr uint32_t kFullRange = 0xFFFFFFFFu;
+// device tree builder (kdtree_gpu.cu): all scans at once, reference-identical shape
+int build_kdtrees_device(hitl_ctx* ctx, uint64_t* n_exact_out);
 // host tree builder (kdtree_build.cpp)
 void build_flat_kdtree(const float* pts_xy, const float* nrm_xy, uint32_t n, hitl_kdnode* out);
 }  // namespace hitl

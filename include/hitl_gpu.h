@@ -221,6 +221,11 @@ int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
 /* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48);
  * smem_carveout_pct = preferred shared-memory carve-out of the unified L1 (percent, -1 = driver default). */
 int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int smem_carveout_pct);
+/* hitl_build_kdtrees builds on the device by default (all scans at once, reference-identical shape); host = 1 selects the
+ * threaded host builder instead (same trees; parity tests compare the two node for node).  hitl_debug_tree_stats: number of
+ * tree segments of the last device build that contained equal keys and were re-sorted with the exact std::sort emulation. */
+int hitl_debug_set_tree_builder(hitl_ctx* ctx, int host);
+int hitl_debug_tree_stats(hitl_ctx* ctx, uint64_t* exact_segments);
 int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out);
 int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src,
                              const uint32_t* dst, float* out6);

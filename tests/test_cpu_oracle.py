@@ -273,3 +273,43 @@ def test_shard_ranges_balance():
         assert r[0][0] == 0 and r[-1][1] == 1000 and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         loads = [int(off[b]) - int(off[a]) for a, b in r]
         assert max(loads) - min(loads) <= 2 * 800
+
+
+def test_stdsort_restatement_matches_std_sort(host):
+    """csrc/stdsort_exact.h restates libstdc++'s std::sort (introsort + final insertion sort + heap-sort fallback); the GPU tree
+    builder relies on it for segments with equal keys.  Compared with this image's std::sort — the one the host builder and
+    the compiled reference kdtree.cpp use — on tie-heavy, sorted, reversed and adversarial inputs."""
+    import ctypes as C
+    lib = host.lib
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+    lib.hitl_host_stdsort_mismatches.restype = C.c_uint64
+    lib.hitl_host_stdsort_mismatches.argtypes = [f32p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(0)
+    heap = C.c_uint32()
+    total_heap = 0
+
+    def check(k):
+        nonlocal total_heap
+        k = np.ascontiguousarray(k, np.float32)
+        assert lib.hitl_host_stdsort_mismatches(k, len(k), None, None, C.byref(heap)) == 0
+        total_heap += heap.value
+
+    for n in list(range(0, 40)) + [100, 257, 720, 1080, 2160, 65534]:
+        for rep in range(3):
+            check(rng.integers(0, max(2, n // (rep + 1) + 1), n))
+            check(rng.normal(size=n))
+            check(np.sort(rng.integers(0, 5, n)))
+            check(np.sort(rng.integers(0, 5, n))[::-1])
+        check(np.zeros(n))
+    for n in (128, 1000, 4096, 30000):          # median-of-3 killer (Musser): reaches the depth limit
+        k = n // 2
+        a = np.zeros(n)
+        for i in range(1, k + 1):
+            if i % 2 == 1:
+                a[i - 1] = i
+                if i < k:
+                    a[i] = k + i
+            a[k + i - 1] = 2 * i
+        check(a)
+        check(a // 3)
+    assert total_heap > 0

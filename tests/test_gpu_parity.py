@@ -90,6 +90,67 @@ def test_kd_queries_match_oracle(gpu, oracle, n):
             assert np.array_equal(cnt, ref)
 
 
+def _both_builders(gpu, off, pts, nrm):
+    gpu.set_scans(off, pts, nrm)
+    gpu.debug_set_tree_builder(host=False)
+    gpu.build_kdtrees()
+    dev, exact = gpu.get_kdtrees().copy(), gpu.debug_tree_stats()
+    gpu.debug_set_tree_builder(host=True)
+    gpu.build_kdtrees()
+    host = gpu.get_kdtrees().copy()
+    gpu.debug_set_tree_builder(host=False)
+    return dev, host, exact
+
+
+def test_device_tree_build_matches_host_builder(gpu, oracle, maps):
+    """The level-synchronous device builder (kdtree_gpu.cu) gives the host builder's trees node for node (the host builder
+    is pinned to the reference's kdtree.cpp in tests/test_cpu_oracle.py), on maps and on random scans of awkward sizes."""
+    for g in (maps("small"), maps("c1", normals="faithful")):
+        dev, host, _ = _both_builders(gpu, g["offsets"], g["pts"], g["nrm"])
+        assert dev.tobytes() == host.tobytes()
+    rng = np.random.default_rng(3)
+    sizes = [0, 1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 64, 100, 719, 720, 1081, 2160, 0, 4099]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    pts = (rng.normal(size=(off[-1], 2)) * 5).astype(np.float32)
+    nrm = rng.normal(size=(off[-1], 2)).astype(np.float32)
+    dev, host, _ = _both_builders(gpu, off, pts, nrm)
+    assert dev.tobytes() == host.tobytes()
+    S = oracle.scans(off, pts, nrm)
+    pn, idx, dim = S.flatten()
+    assert np.array_equal(dev["index"], idx) and np.array_equal(dev["dim"], dim) and np.array_equal(dev["px"], pn[:, 0])
+
+
+def test_device_tree_build_with_equal_coordinates(gpu, oracle):
+    """Equal keys: std::sort is not stable, the order (hence the tree) is whatever libstdc++'s introsort produces.  The
+    device builder re-sorts such segments with the step-for-step restatement (stdsort_exact.h)."""
+    rng = np.random.default_rng(11)
+    scans = []
+    scans.append(np.round(rng.normal(size=(1500, 2)) * 3, 1))                       # 0.1 lattice: many ties on both axes
+    scans.append(np.stack([np.repeat(np.arange(40), 25), np.tile(np.arange(25), 40)], 1).astype(np.float64))   # exact grid
+    dup = rng.normal(size=(300, 2)); scans.append(np.concatenate([dup, dup, dup[:77]]))                          # duplicated points
+    z = np.zeros((257, 2)); z[::2, 0] = -0.0; z[:, 1] = rng.integers(0, 3, 257); scans.append(z)                   # -0 / +0 and 3 values
+    scans.append(np.stack([np.linspace(-4, 4, 2000), np.zeros(2000)], 1))           # a wall on the x axis: y all equal
+    scans.append(np.round(rng.normal(size=(17, 2)), 0))
+    scans.append(np.ones((5000, 2)))                                                 # everything equal
+    k = 4096; mus = np.zeros(k)                                                      # median-of-3 killer: drives introsort into its heap-sort fallback
+    for i in range(1, k // 2 + 1):
+        if i % 2 == 1:
+            mus[i - 1] = i
+            if i < k // 2:
+                mus[i] = k // 2 + i
+        mus[k // 2 + i - 1] = 2 * i
+    scans.append(np.stack([mus // 3, np.zeros(k)], 1))
+    off = np.concatenate([[0], np.cumsum([len(x) for x in scans])]).astype(np.uint32)
+    pts = np.concatenate(scans).astype(np.float32)
+    nrm = rng.normal(size=pts.shape).astype(np.float32)
+    dev, host, exact = _both_builders(gpu, off, pts, nrm)
+    assert exact > 100
+    assert dev.tobytes() == host.tobytes()
+    S = oracle.scans(off, pts, nrm)
+    pn, idx, dim = S.flatten()
+    assert np.array_equal(dev["index"], idx) and np.array_equal(dev["dim"], dim)
+
+
 # ---- correspondence search -------------------------------------------------------------------------
 @pytest.mark.parametrize("name,normals", [("tiny", "compensated"), ("tiny", "faithful"), ("small", "compensated"), ("small", "faithful")])
 def test_find_stf_bit_exact(gpu, oracle, maps, name, normals):
