@@ -187,7 +187,8 @@ def generate(name="c1", n_poses=None, beams=None, normals="compensated", max_ran
     host = HostLib()
     out_dir = out_dir or os.environ.get("HITL_SYNTH_DIR", "/tmp/hitl_synth")
     os.makedirs(out_dir, exist_ok=True)
-    path = os.path.join(out_dir, "%s_%d_%d_%s.stfs.covars" % (name, N, P, normals))
+    # scratch file of the text round trip: unique per process (ranks of one box generate the same map side by side)
+    path = os.path.join(out_dir, "%s_%d_%d_%s%s.stfs.covars" % (name, N, P, normals, "" if keep_file else "_%d" % os.getpid()))
     host.save_stfs_covars(path, poses, cov, off, obs, nrm, map_name="synthetic_" + name, timestamp=0.0)
     g = host.load_pose_graph(path)
     g["path"] = path
