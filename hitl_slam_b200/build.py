@@ -25,6 +25,7 @@ GPU_SOURCES = [
     ("search.cu", ["--fmad=false"]),
     ("em.cu", ["--fmad=false"]),
     ("kdtree_gpu.cu", ["--fmad=false"]),
+    ("backprop.cu", ["--fmad=false"]),
     ("eval.cu", []),
     ("kdtree_build.cpp", []),
 ]

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
+    "hitl_normal_eq_device", "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
     "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
 
@@ -487,6 +487,9 @@ class HostLib:
             return
         vp = C.c_void_p
         lib.hitl_host_seg_fit_em.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p]
+        lib.hitl_host_app_exp_correct.argtypes = [C.c_int, _f32p, C.c_uint32, _f32p, C.c_uint32, _i32p, _f32p]
+        lib.hitl_host_backprop.argtypes = [vp, C.c_uint32, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, C.POINTER(C.c_float)]
+        lib.hitl_host_session_correct.argtypes = [vp, C.c_int, _f32p, vp, C.c_int, _i32p, _f64p, _f64p]
         lib.hitl_host_odometry_consts.argtypes = [_f32p, C.c_uint32, _f32p]
         lib.hitl_host_human_targets.argtypes = [_f32p, C.c_uint32, C.c_uint32, _i32p, _f32p, _f64p]
         lib.hitl_host_solver_selftest.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f64p]
@@ -578,6 +581,34 @@ class HostLib:
         return out
 
 
+def _hostlib_app_exp_correct(self, ctype, sel, poses_f32, corrected):
+    """AppExpCorrect::Run on explicit inputs: returns (poses [N,3] f32, C [3] f32 or None if no group was applied)."""
+    self._bind_mirror()
+    p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1).copy()
+    corr = np.ascontiguousarray(corrected, np.int32)
+    c3 = np.zeros(3, np.float32)
+    rc = self.lib.hitl_host_app_exp_correct(int(ctype), np.ascontiguousarray(sel, np.float32).reshape(-1), len(p) // 3, p, len(corr), corr, c3)
+    if rc < 0:
+        raise HitlError("hitl_host_app_exp_correct failed")
+    return p.reshape(-1, 3), (c3 if rc == 1 else None)
+
+
+def _hostlib_backprop(self, gpu, poses_f32, cov9, lo, hi, c3):
+    """Backprop::Run (pose update on the GPU): returns (poses [N,3] f32, cov [N,9] f32, device ms)."""
+    self._bind_mirror()
+    p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1).copy()
+    cov = np.ascontiguousarray(cov9, np.float32).reshape(-1).copy()
+    ms = C.c_float()
+    rc = self.lib.hitl_host_backprop(gpu.ctx, len(p) // 3, p, cov, int(lo), int(hi), np.ascontiguousarray(c3, np.float32), C.byref(ms))
+    if rc != 0:
+        raise HitlError("hitl_host_backprop failed: " + gpu.lib.hitl_last_error(gpu.ctx).decode())
+    return p.reshape(-1, 3), cov.reshape(-1, 9), ms.value
+
+
+HostLib.app_exp_correct = _hostlib_app_exp_correct
+HostLib.backprop = _hostlib_backprop
+
+
 class HostSession:
     """JointOpt + EMInput of the C++ host mirror on one GPU context (host_capi.cpp)."""
 
@@ -634,6 +665,19 @@ class HostSession:
         self.lib.hitl_host_session_em_poses(self.s, cor, anc)
         return dict(segs=sel.reshape(4, 2), corrected=cor[:info[0]].copy(), anchor=anc[:info[1]].copy(), backprop=(int(info[2]), int(info[3])),
                     rounds=(int(info[4]), int(info[5])))
+
+    def correct(self, correction_type, selected_points, cov=None, solve=True):
+        """One full human correction as HitLSLAM::Run wires it: EM -> explicit correction -> back-propagation -> constraints
+        (-> JointOpt::Run).  cov [N,9] f32 is updated in place when given."""
+        sel = np.ascontiguousarray(selected_points, np.float32).reshape(-1).copy()
+        info, ms, summ = np.zeros(8, np.int32), np.zeros(5), np.zeros(6)
+        if cov is not None:
+            assert cov.dtype == np.float32 and cov.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.hitl_host_session_correct(self.s, int(correction_type), sel, cov.ctypes.data if cov is not None else None, int(solve), info, ms, summ))
+        return dict(segs=sel.reshape(4, 2), n_corrected=int(info[0]), n_anchor=int(info[1]), backprop=(int(info[2]), int(info[3])), rounds=(int(info[4]), int(info[5])),
+                    n_constraints=int(info[6]), applied=bool(info[7]),
+                    ms=dict(em=ms[0], explicit=ms[1], backprop=ms[2], backprop_device=ms[3], joint_opt=ms[4]),
+                    initial_cost=summ[0], final_cost=summ[1], successful_steps=int(summ[2]), unsuccessful_steps=int(summ[3]))
 
     def add_constraints_from_em(self):
         n = C.c_uint32()

@@ -9,13 +9,16 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 #include <exception>
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include "correction_stages.h"
 #include "em_input.h"
 #include "hitl_host.h"
 #include "joint_optimization.h"
+#include "hitl_math.h"
 
 namespace hitl {
 
@@ -72,6 +75,7 @@ struct PowellF4 { template <typename T> bool operator()(const T* x1, const T* x4
   catch (...) { (s)->error = "unknown exception"; return -1; }
 
 extern "C" {
+static void fill_summary(const JointOpt& J, double out[6]);
 
 void* hitl_host_session_create(void* ctx) {
   if (!ctx) return nullptr;
@@ -185,6 +189,96 @@ int hitl_host_session_add_constraints(void* sp, uint32_t n, const int32_t* ids3,
     s->jopt.human_constraints_.push_back(hc);
   })
 }
+// ---- the two stages between EM and JointOpt (f3) -------------------------------------------------------------------
+// AppExpCorrect::Run on explicit inputs.  poses_xyt in/out; C3 = correction handed to Backprop; returns 1 if a group of
+// corrected poses was applied, 0 if none, -1 on error.
+int hitl_host_app_exp_correct(int correction_type, const float sel_xy[8], uint32_t n_poses, float* poses_xyt, uint32_t n_corrected, const int32_t* corrected,
+                              float C3[3]) {
+  try {
+    AppExpCorrect A;
+    A.correction_type_ = (CorrectionType)correction_type;
+    for (int i = 0; i < 4; ++i) A.selected_points_.push_back(Vector2f(sel_xy[2 * i], sel_xy[2 * i + 1]));
+    A.corrected_poses_.assign(corrected, corrected + n_corrected);
+    A.poses_.resize(n_poses);
+    for (uint32_t i = 0; i < n_poses; ++i) A.poses_[i] = Pose2Df(poses_xyt[3 * i + 2], poses_xyt[3 * i], poses_xyt[3 * i + 1]);
+    A.Run();
+    for (uint32_t i = 0; i < n_poses; ++i) { poses_xyt[3 * i] = A.poses_[i].translation.x; poses_xyt[3 * i + 1] = A.poses_[i].translation.y; poses_xyt[3 * i + 2] = A.poses_[i].angle; }
+    for (int i = 0; i < 3; ++i) C3[i] = A.correction_[i];
+    return A.applied_ ? 1 : 0;
+  } catch (...) { return -1; }
+}
+// Backprop::Run on explicit inputs (pose update on the GPU of `ctx`).  poses_xyt, cov9 in/out.
+int hitl_host_backprop(void* ctx, uint32_t n_poses, float* poses_xyt, float* cov9, int32_t lo, int32_t hi, const float C3[3], float* device_ms) {
+  try {
+    Backprop B(static_cast<hitl_ctx*>(ctx));
+    B.backprop_bounds_ = std::make_pair((int)lo, (int)hi);
+    B.correction_ = Vector3f{{C3[0], C3[1], C3[2]}};
+    B.poses_.resize(n_poses); B.covariances_.resize(n_poses);
+    for (uint32_t i = 0; i < n_poses; ++i) {
+      B.poses_[i] = Pose2Df(poses_xyt[3 * i + 2], poses_xyt[3 * i], poses_xyt[3 * i + 1]);
+      for (int k = 0; k < 9; ++k) B.covariances_[i][k] = cov9[9 * (size_t)i + k];
+    }
+    B.Run();
+    for (uint32_t i = 0; i < n_poses; ++i) {
+      poses_xyt[3 * i] = B.poses_[i].translation.x; poses_xyt[3 * i + 1] = B.poses_[i].translation.y; poses_xyt[3 * i + 2] = B.poses_[i].angle;
+      for (int k = 0; k < 9; ++k) cov9[9 * (size_t)i + k] = B.covariances_[i][k];
+    }
+    if (device_ms) *device_ms = B.last_device_ms_;
+    return 0;
+  } catch (...) { return -1; }
+}
+
+// One full human correction on the session's map, wired as HitLSLAM::Run (HitLSLAM.cpp:379-484): EMInput::Run (strokes refit,
+// corrected / anchor poses, bounds) -> AppExpCorrect::Run -> Backprop::Run -> angle wrap -> constraints appended ->
+// JointOpt::Run (unless solve = 0).  cov9: per-pose covariances, in/out (may be NULL: 1e-4 / 1e-5 diagonals).
+// info = {n_corrected, n_anchor, bound_lo, bound_hi, em_rounds_a, em_rounds_b, n_new_constraints, applied};
+// ms = {em, explicit correction, backprop (host + device), backprop device only, joint optimisation}.
+int hitl_host_session_correct(void* sp, int correction_type, float sel_xy[8], float* cov9, int solve, int32_t info[8], double ms[5], double summary[6]) {
+  Session* s = static_cast<Session*>(sp);
+  HOST_TRY(s, {
+    auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    for (int i = 0; i < 8; ++i) info[i] = 0;
+    for (int i = 0; i < 5; ++i) ms[i] = 0;
+    const double t0 = now();
+    EMInput& E = s->em;
+    E.correction_type_ = (CorrectionType)correction_type;
+    E.selected_points_.resize(4);
+    for (int i = 0; i < 4; ++i) E.selected_points_[i] = Vector2f(sel_xy[2 * i], sel_xy[2 * i + 1]);
+    E.Run();
+    for (int i = 0; i < 4; ++i) { sel_xy[2 * i] = E.selected_points_[i].x; sel_xy[2 * i + 1] = E.selected_points_[i].y; }
+    info[0] = (int32_t)E.corrected_poses_.size(); info[1] = (int32_t)E.anchor_poses_.size();
+    info[2] = E.backprop_bounds_.first; info[3] = E.backprop_bounds_.second; info[4] = E.em_rounds_[0]; info[5] = E.em_rounds_[1];
+    const double t1 = now();
+    ms[0] = t1 - t0;
+    if (!(E.backprop_bounds_.first >= 0 && E.backprop_bounds_.second >= 1)) return 0;      // HitLSLAM.cpp:413
+    AppExpCorrect A;
+    A.correction_type_ = E.correction_type_; A.selected_points_ = E.selected_points_;
+    A.corrected_poses_ = E.corrected_poses_; A.anchor_poses_ = E.anchor_poses_; A.poses_ = s->jopt.poses_;
+    A.Run();
+    info[6] = (int32_t)A.new_human_constraints_.size(); info[7] = A.applied_ ? 1 : 0;
+    s->jopt.human_constraints_.push_back(A.new_human_constraints_);
+    const double t2 = now();
+    ms[1] = t2 - t1;
+    Backprop B(s->ctx);
+    B.poses_ = A.poses_; B.correction_ = A.correction_; B.backprop_bounds_ = E.backprop_bounds_;
+    B.covariances_.resize(A.poses_.size());
+    for (size_t i = 0; i < B.covariances_.size(); ++i)
+      for (int k = 0; k < 9; ++k) B.covariances_[i][k] = cov9 ? cov9[9 * i + k] : ((k == 0 || k == 4) ? 1e-4f : (k == 8 ? 1e-5f : 0.f));
+    if (A.applied_) B.Run();
+    if (cov9) for (size_t i = 0; i < B.covariances_.size(); ++i) for (int k = 0; k < 9; ++k) cov9[9 * i + k] = B.covariances_[i][k];
+    for (size_t i = 0; i < B.poses_.size(); ++i) { const float a = B.poses_[i].angle; B.poses_[i].angle = atan2f(sinf_rn(a), cosf_rn(a)); }   // :443-447
+    s->jopt.poses_ = B.poses_;
+    s->em.world_clouds_resident_ = false;
+    const double t3 = now();
+    ms[2] = t3 - t2; ms[3] = B.last_device_ms_;
+    if (solve) {
+      s->jopt.Run();
+      if (summary) fill_summary(s->jopt, summary);
+    }
+    ms[4] = now() - t3;
+  })
+}
+
 int hitl_host_session_clear_constraints(void* sp) { static_cast<Session*>(sp)->jopt.human_constraints_.clear(); return 0; }
 
 // Solver knobs: which = 0 (SolveHumanConstraints) or 1 (PostHumanOptimization); negative values keep the default.

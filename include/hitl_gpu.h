@@ -204,6 +204,14 @@ int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, doub
 /* Device pointer + length (doubles) of the packed [H_diag | g | cost] buffer of the last hitl_normal_eq. */
 int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
 
+/* ---- COP-SLAM back-propagation (between EM and the joint optimisation) --------------------- */
+/* The pose update of Backprop::BackPropagateError (Backprop.cpp:170-199), with the host loops' float operation sequence per
+ * pose: for i in [lo, hi): rotate poses (i, hi] by rot_weights[i-lo] * theta about pose i (pose i's angle moves too), then
+ * with trans = destination - pose[hi]: poses (i, hi] += trans_weights[i-lo] * trans.  poses_xyt: n_poses float triples on the
+ * host, in/out; weights: hi - lo entries used.  ms_out (optional): device time of the kernel. */
+int hitl_backprop_poses(hitl_ctx* ctx, uint32_t n_poses, float* poses_xyt, uint32_t lo, uint32_t hi, const float* rot_weights,
+                        const float* trans_weights, float theta, const float* destination_xy, float* ms_out);
+
 /* ---- diagnostics ------------------------------------------------------------------------- */
 /* Device evaluation of the library's sinf/cosf (bit-identical to glibc 2.39's x86-64 FMA variant;
  * csrc/hitl_math.h) and of RelativePoseTransform (JointOptimization.cpp:296-305) for parity tests. */

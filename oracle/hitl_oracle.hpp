@@ -802,4 +802,147 @@ inline void world_transform(const float* poses_xyt, const std::vector<std::vecto
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Explicit correction + COP-SLAM back-propagation (the two host stages between EM and JointOpt) — "next" row f3.
+// Parity unpinned: restated from ApplyExplicitCorrection.cpp:150-181, 229-316, 318-445 and Backprop.cpp:98-210
+// (both translation units need Ceres/glog headers and cannot be compiled here).
+// ------------------------------------------------------------------------------------------
+struct Pose2Df { V2 translation; float angle; };                 // perception_2d.h:32-34
+struct CorrectionPair { int pose; float c[3]; };                 // ApplyExplicitCorrection.h: pair<int, Vector3f>
+enum CorrectionKind { kPoint = 1, kLineSegment = 2, kCorner = 3, kColinear = 4, kPerpendicular = 5, kParallel = 6 };   // human_constraints.h:8-17
+
+inline float scalar_cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }   // eigen_helper.h:25-29
+
+// CalculateExplicitCorrections (ApplyExplicitCorrection.cpp:318-356) with the four supported modes
+// (:150-181 line-to-line, :229-257 colinear, :259-293 perpendicular, :295-316 parallel).  sel = 4 points.
+inline void calculate_explicit_corrections(int type, const V2 sel[4], const std::vector<Pose2Df>& poses, const std::vector<int>& corrected,
+                                           std::vector<CorrectionPair>* out) {
+  V2 anchor_point, cmA;
+  float theta_f = 0.0f;
+  if (type == kLineSegment) {
+    cmA = (sel[1] + sel[0]) / 2.0f;
+    const V2 cmB = (sel[3] + sel[2]) / 2.0f;
+    const V2 A = normalized(sel[1] - sel[0]), B = normalized(sel[3] - sel[2]);
+    double theta = acosf(dot(A, B));                              // acos(float) -> acosf, widened
+    if (A.x * B.y - A.y * B.x < 0.0) theta = -theta;              // z of the 3-D cross product
+    theta_f = (float)theta;
+    anchor_point = cmB;
+  } else if (type == kColinear) {
+    cmA = 0.5f * (sel[1] + sel[0]);
+    const V2 cmB = 0.5f * (sel[3] + sel[2]);
+    const V2 A = normalized(sel[1] - sel[0]), B = normalized(sel[3] - sel[2]);
+    theta_f = (scalar_cross(A, B) >= 0.0) ? acosf(dot(A, B)) : -acosf(dot(A, B));
+    const float alpha = dot(cmA - cmB, B);
+    anchor_point = cmB + alpha * B;                               // new_cmA
+  } else if (type == kPerpendicular) {
+    cmA = (sel[1] + sel[0]) / 2.0f;
+    const V2 A = normalized(sel[1] - sel[0]), B = normalized(sel[3] - sel[2]);
+    double theta = 0.0;
+    if (A.x * B.y - A.y * B.x < 0.0) theta = -acosf(dot(A, B)); else theta = acosf(dot(A, B));
+    if (theta == M_PI / 2.0 || theta == -M_PI / 2.0) theta = 0.0;
+    else if (theta > 0.0) theta = -(-theta + M_PI / 2.0);
+    else theta = -(-theta - M_PI / 2.0);
+    theta_f = (float)theta;
+    anchor_point = cmA;
+  } else if (type == kParallel) {
+    cmA = 0.5f * (sel[1] + sel[0]);
+    const V2 A = normalized(sel[1] - sel[0]), B = normalized(sel[3] - sel[2]);
+    theta_f = (scalar_cross(A, B) >= 0.0) ? acosf(dot(A, B)) : -acosf(dot(A, B));
+    anchor_point = cmA;
+  } else {
+    return;                                                       // point / corner: "not currently supported"
+  }
+  const M2 R = rot2(theta_f);
+  for (size_t i = 0; i < corrected.size(); ++i) {
+    const V2 p0 = poses[corrected[i]].translation;
+    const V2 p1 = anchor_point + (R * (p0 - cmA));
+    const V2 T = p1 - p0;
+    CorrectionPair c; c.pose = corrected[i]; c.c[0] = T.x; c.c[1] = T.y; c.c[2] = theta_f;
+    out->push_back(c);
+  }
+}
+
+// AppExpCorrections (:417-445) = CalculateExplicitCorrections + FindContiguousGroups (:360-385) + ApplyExplicitCorrections
+// (:387-415) for group 0 only.  Returns the correction C handed to Backprop (first correction of the first group);
+// *applied = false when there was no group (C untouched).
+inline void app_exp_corrections(int type, const V2 sel[4], std::vector<Pose2Df>* poses_io, const std::vector<int>& corrected, float C[3], bool* applied) {
+  std::vector<Pose2Df>& poses = *poses_io;
+  std::vector<CorrectionPair> corrections;
+  calculate_explicit_corrections(type, sel, poses, corrected, &corrections);
+  std::vector<std::vector<CorrectionPair> > groups;
+  std::vector<CorrectionPair> one;
+  for (size_t i = 0; i + 1 <= poses.size(); ++i) {
+    bool in_group = false; size_t which = 0;
+    for (size_t j = 0; j < corrections.size(); ++j) if (corrections[j].pose == (int)i) { in_group = true; which = j; }
+    if (in_group) one.push_back(corrections[which]);
+    else if (!one.empty()) { groups.push_back(one); one.clear(); }
+  }
+  if (!one.empty()) groups.push_back(one);
+  *applied = !groups.empty();
+  if (groups.empty()) return;
+  const std::vector<CorrectionPair>& g0 = groups[0];
+  C[0] = g0[0].c[0]; C[1] = g0[0].c[1]; C[2] = g0[0].c[2];
+  for (size_t j = 0; j < g0.size(); ++j) {
+    poses[g0[j].pose].translation.x += g0[j].c[0];
+    poses[g0[j].pose].translation.y += g0[j].c[1];
+    poses[g0[j].pose].angle += g0[j].c[2];
+  }
+  const int last_pose = g0.back().pose;
+  const float* lc = g0.back().c;
+  for (size_t k = (size_t)last_pose + 1; k < poses.size(); ++k) {
+    poses[k].angle += lc[2];
+    const V2 ab = poses[k].translation - poses[last_pose].translation;
+    const V2 new_ab = rot2(lc[2]) * ab;
+    poses[k].translation = (poses[last_pose].translation + new_ab) + V2(lc[0], lc[1]);
+  }
+}
+
+// Backprop::BackPropagateError (Backprop.cpp:98-200) behind Run()'s bounds test (:202-210).  cov: 9 floats per pose, row-major.
+inline void backprop(std::vector<Pose2Df>* poses_io, std::vector<float>* cov_io, int min_poses, int max_poses, const float correction[3]) {
+  if (!(min_poses < max_poses)) return;
+  std::vector<Pose2Df>& poses = *poses_io;
+  std::vector<float>& cov = *cov_io;
+  const size_t n = cov.size() / 9;
+  const V2 destination = poses[max_poses].translation + V2(correction[0], correction[1]);
+  const float destination_rot_variance = 0.0001f, destination_trans_variance = 0.001f;
+  std::vector<float> rot_sigmas, trans_sigmas;
+  for (size_t i = 0; i < n; ++i) {
+    rot_sigmas.push_back(cov[9 * i + 8]);
+    trans_sigmas.push_back((float)((cov[9 * i + 0] + cov[9 * i + 4]) / 2.0));
+  }
+  std::vector<float> rot_weights, trans_weights;
+  float sum_of_rot_var = 0.0f, sum_of_trans_var = 0.0f;
+  for (int i = min_poses; i <= max_poses; ++i) { sum_of_rot_var += rot_sigmas[i]; sum_of_trans_var += trans_sigmas[i]; }
+  sum_of_rot_var += destination_rot_variance;
+  sum_of_trans_var += destination_trans_variance;
+  for (int i = min_poses; i <= max_poses; ++i) { rot_weights.push_back(rot_sigmas[i] / sum_of_rot_var); trans_weights.push_back(trans_sigmas[i] / sum_of_trans_var); }
+  const float rot_beta = 1 / (1 + (rot_sigmas[max_poses - 1] / destination_rot_variance));
+  const float trans_beta = 1 / (1 + (trans_sigmas[max_poses - 1] / destination_trans_variance));
+  for (int i = min_poses; i < max_poses; ++i) {
+    float* c = &cov[9 * (size_t)i];
+    c[0] *= trans_beta; c[1] *= trans_beta; c[3] *= trans_beta; c[4] *= trans_beta;
+    c[2] *= rot_beta; c[2] *= rot_beta;                           // (0,2) twice, (1,2) never: as in the reference (:166-169)
+    c[6] *= rot_beta; c[7] *= rot_beta;
+    c[8] *= rot_beta;
+  }
+  const float theta = correction[2];
+  for (int i = min_poses; i < max_poses; ++i) {
+    const float delta_theta = rot_weights[i - min_poses] * theta;
+    // Translation2Df(t) * Rotation2Df(d) * Translation2Df(-t): linear = R, translation = t + R * (-t)
+    Aff post; post.L = rot2(delta_theta);
+    post.t = poses[i].translation + (post.L * (-poses[i].translation));
+    poses[i].angle += delta_theta;
+    for (int k = i + 1; k <= max_poses; ++k) {
+      poses[k].angle += delta_theta;
+      poses[k].translation = post * poses[k].translation;
+    }
+  }
+  const V2 trans = destination - poses[max_poses].translation;
+  for (int i = min_poses; i < max_poses; ++i) {
+    const V2 delta_trans = trans_weights[i - min_poses] * trans;
+    for (int k = i + 1; k <= max_poses; ++k) poses[k].translation = poses[k].translation + delta_trans;
+  }
+}
+
 }  // namespace orc

@@ -275,6 +275,28 @@ void orc_pose_graph_get(void* p, float* poses, float* cov, uint32_t* off, float*
 }
 void orc_pose_graph_free(void* p) { delete static_cast<PoseGraph*>(p); }
 
+// ---- explicit correction + back-propagation (f3) -------------------------------------------------
+// poses: x, y, theta floats (in/out).  Returns 1 when a contiguous group was applied (C written), 0 otherwise.
+int orc_app_exp_corrections(int type, const float* sel8, float* poses_xyt, uint32_t n_poses, const int32_t* corrected, uint32_t n_corrected, float* C3) {
+  std::vector<Pose2Df> poses(n_poses);
+  for (uint32_t i = 0; i < n_poses; ++i) { poses[i].translation = V2(poses_xyt[3 * i], poses_xyt[3 * i + 1]); poses[i].angle = poses_xyt[3 * i + 2]; }
+  V2 sel[4];
+  for (int k = 0; k < 4; ++k) sel[k] = V2(sel8[2 * k], sel8[2 * k + 1]);
+  std::vector<int> corr(corrected, corrected + n_corrected);
+  bool applied = false;
+  app_exp_corrections(type, sel, &poses, corr, C3, &applied);
+  for (uint32_t i = 0; i < n_poses; ++i) { poses_xyt[3 * i] = poses[i].translation.x; poses_xyt[3 * i + 1] = poses[i].translation.y; poses_xyt[3 * i + 2] = poses[i].angle; }
+  return applied ? 1 : 0;
+}
+void orc_backprop(float* poses_xyt, float* cov9, uint32_t n_poses, int32_t lo, int32_t hi, const float* C3) {
+  std::vector<Pose2Df> poses(n_poses);
+  for (uint32_t i = 0; i < n_poses; ++i) { poses[i].translation = V2(poses_xyt[3 * i], poses_xyt[3 * i + 1]); poses[i].angle = poses_xyt[3 * i + 2]; }
+  std::vector<float> cov(cov9, cov9 + 9 * (size_t)n_poses);
+  backprop(&poses, &cov, lo, hi, C3);
+  for (uint32_t i = 0; i < n_poses; ++i) { poses_xyt[3 * i] = poses[i].translation.x; poses_xyt[3 * i + 1] = poses[i].translation.y; poses_xyt[3 * i + 2] = poses[i].angle; }
+  memcpy(cov9, cov.data(), 4 * cov.size());
+}
+
 float orc_sinf(float x) { return sinf(x); }
 float orc_cosf(float x) { return cosf(x); }
 double orc_angle_mod(double a) { return angle_mod_d(a); }

@@ -141,6 +141,24 @@ class Oracle:
         self.lib.orc_seg_fit(np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64), data, len(data) // 2, out)
         return out.reshape(2, 2)
 
+    def app_exp_corrections(self, ctype, sel, poses_f32, corrected):
+        """AppExpCorrect::AppExpCorrections: returns (new poses [N,3] f32, correction C [3] f32 or None when nothing was applied)."""
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1).copy()
+        corr = np.ascontiguousarray(corrected, np.int32)
+        c3 = np.zeros(3, np.float32)
+        self.lib.orc_app_exp_corrections.argtypes = [C.c_int, _f32p, _f32p, C.c_uint32, _i32p, C.c_uint32, _f32p]
+        ok = self.lib.orc_app_exp_corrections(int(ctype), np.ascontiguousarray(sel, np.float32).reshape(-1), p, len(p) // 3, corr, len(corr), c3)
+        return p.reshape(-1, 3), (c3 if ok else None)
+
+    def backprop(self, poses_f32, cov9, lo, hi, c3):
+        """Backprop::Run: returns (new poses [N,3] f32, new covariances [N,9] f32)."""
+        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1).copy()
+        cov = np.ascontiguousarray(cov9, np.float32).reshape(-1).copy()
+        self.lib.orc_backprop.argtypes = [_f32p, _f32p, C.c_uint32, C.c_int32, C.c_int32, _f32p]
+        self.lib.orc_backprop.restype = None
+        self.lib.orc_backprop(p, cov, len(p) // 3, int(lo), int(hi), np.ascontiguousarray(c3, np.float32))
+        return p.reshape(-1, 3), cov.reshape(-1, 9)
+
     def odometry_consts(self, poses_f32):
         p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
         n = len(p) // 3

@@ -152,6 +152,44 @@ def test_stfs_covars_io_threads_and_fast_parser(host, tmp_path, monkeypatch):
         assert np.array_equal(gb["pts"], g["pts"][:cutline - 2])
 
 
+def _same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+@pytest.mark.parametrize("ctype", [2, 4, 5, 6])
+def test_explicit_correction_bit_exact(host, oracle, ctype):
+    """AppExpCorrect (ApplyExplicitCorrection.cpp:150-181, 229-316, 360-445): corrected poses move rigidly about feature A,
+    later poses follow the last corrected pose, the first correction of the first contiguous group goes to Backprop."""
+    rng = np.random.default_rng(100 + ctype)
+    for trial in range(25):
+        n = int(rng.integers(5, 120))
+        poses = np.cumsum(rng.normal(size=(n, 3)) * [0.3, 0.3, 0.05], 0).astype(np.float32)
+        a0 = rng.normal(size=2) * 5
+        b0 = a0 + rng.normal(size=2) * 0.4
+        da, db = rng.normal(size=2), rng.normal(size=2)
+        if trial % 5 == 0:
+            db = np.array([-da[1], da[0]])                       # exactly perpendicular strokes
+        if trial % 7 == 0:
+            db = da.copy()                                       # parallel strokes
+        sel = np.array([a0, a0 + da, b0, b0 + db], np.float32)
+        k = int(rng.integers(1, max(2, n // 2)))
+        corrected = np.sort(rng.choice(n, k, replace=False))
+        if trial % 3 == 0:
+            corrected = np.arange(n // 3, n // 3 + k) % n        # one contiguous run
+        if trial % 11 == 0:
+            corrected = corrected[::-1]                          # unsorted list
+        got_p, got_c = host.app_exp_correct(ctype, sel, poses, corrected)
+        want_p, want_c = oracle.app_exp_corrections(ctype, sel, poses, corrected)
+        # bit-exact; exactly parallel strokes can give A.B = 1 + 1 ulp and acosf -> NaN in the reference arithmetic too (any NaN matches)
+        assert _same_bits(got_p, want_p), (ctype, trial)
+        assert _same_bits(got_c, want_c)
+    p, c = host.app_exp_correct(ctype, sel, poses, [])            # nothing to correct: poses untouched
+    assert c is None and np.array_equal(p, poses)
+    p, c = host.app_exp_correct(1, sel, poses, [1, 2])            # point correction: unsupported, as in the reference
+    assert c is None and np.array_equal(p, poses)
+
+
 def test_mirror_refuses_to_run_without_a_context(host):
     host._bind_mirror()
     assert not host.lib.hitl_host_session_create(None)     # no ctx, no session: there is no CPU implementation of the stages

@@ -285,3 +285,69 @@ def test_replayed_colinear_correction_end_to_end(session, host, oracle, maps, tm
     assert summ["final_cost"] <= summ["initial_cost"] + 1e-12
     p, _ = session.poses()
     assert np.abs(p - g["poses"]).max() <= 1e-3
+
+
+def _bits_equal(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+@pytest.mark.parametrize("n,lo,hi", [(12, 3, 4), (40, 0, 39), (300, 7, 250), (1500, 100, 1400), (5000, 0, 4999), (2600, 2599 - 1030, 2599)])
+def test_backprop_bit_exact(gpu, host, oracle, n, lo, hi):
+    """Backprop::BackPropagateError (Backprop.cpp:98-200): the O(L^2) pose update runs on the device (one CTA, systolic over
+    the poses) and gives every pose the host loops' float operation sequence: poses and covariances bit for bit."""
+    rng = np.random.default_rng(n + lo)
+    poses = np.cumsum(rng.normal(size=(n, 3)) * [0.25, 0.25, 0.03], 0).astype(np.float32)
+    cov = np.zeros((n, 9), np.float32)
+    cov[:, 0] = cov[:, 4] = 1e-4 * (1 + np.arange(n) / 100) * rng.uniform(0.5, 1.5, n)
+    cov[:, 8] = 1e-5 * (1 + np.arange(n) / 100)
+    cov[:, [1, 2, 3, 5, 6, 7]] = rng.normal(size=(n, 6)) * 1e-6
+    c3 = np.array([0.31, -0.22, 0.07], np.float32)
+    want_p, want_c = oracle.backprop(poses, cov, lo, hi, c3)
+    got_p, got_c, ms = host.backprop(gpu, poses, cov, lo, hi, c3)
+    assert _bits_equal(got_p, want_p) and _bits_equal(got_c, want_c)
+    assert np.abs(got_p[lo + 1:hi + 1] - poses[lo + 1:hi + 1]).max() > 1e-3         # something moved ...
+    assert np.array_equal(got_p[:lo], poses[:lo]) and np.array_equal(got_p[hi + 1:], poses[hi + 1:])   # ... only inside the bounds
+    # the last pose lands on the destination (that is what the weights are normalised for, up to the fused destination variance)
+    dest = poses[hi, :2] + c3[:2]
+    assert np.abs(got_p[hi, :2] - dest).max() < 0.5
+    # bounds that leave nothing to do
+    same_p, same_c, _ = host.backprop(gpu, poses, cov, hi, hi, c3)
+    assert np.array_equal(same_p, poses) and np.array_equal(same_c, cov)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_full_correction_chain_matches_oracle(session, gpu, oracle, maps, name):
+    """HitLSLAM::Run's wiring (HitLSLAM.cpp:379-484) up to the joint optimisation: EM -> explicit correction -> back-propagation ->
+    angle wrap, against the same chain of oracle stages.  The refit strokes differ by <= 1e-5 (two LM implementations), so the
+    corrected poses are compared at 1e-4; fed with the mirror's own strokes the two later stages are bit-exact (tests above)."""
+    from hitl_slam_b200 import synth
+    g = maps(name, **DRIFTY)
+    n = len(g["poses"])
+    session.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    session.world_transform(keep_host_copy=False)
+    strokes = synth.pick_strokes(g, min_sep=0.045)
+    cov = np.ascontiguousarray(g["cov"], np.float32).reshape(n, 9).copy() if "cov" in g else np.tile(np.array([1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-5], np.float32), (n, 1))
+    cov0 = cov.copy()
+    out = session.correct(4, strokes, cov=cov, solve=False)
+    assert out["applied"] and out["n_constraints"] == out["n_corrected"] * out["n_anchor"] > 0
+    got, _ = session.poses()
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    em = oracle.em_run(g["offsets"], S.world_transform(g["poses"]), strokes)
+    assert out["backprop"] == em["backprop"] and out["n_corrected"] == len(em["corrected"])
+    # oracle chain on the MIRROR's refit strokes: everything after EM must agree bit for bit
+    p1, c3 = oracle.app_exp_corrections(4, out["segs"], g["poses"], em["corrected"])
+    p2, cov2 = oracle.backprop(p1, cov0, em["backprop"][0], em["backprop"][1], c3)
+    wrapped = p2.copy()
+    wrapped[:, 2] = np.arctan2(np.sin(p2[:, 2].astype(np.float32)), np.cos(p2[:, 2].astype(np.float32)))
+    assert _bits_equal(got[:, :2], p2[:, :2]) and _bits_equal(cov, cov2)
+    assert np.abs(got[:, 2] - wrapped[:, 2]).max() <= 1e-6
+    # and on the oracle's own refit strokes within the LM tolerance
+    q1, d3 = oracle.app_exp_corrections(4, em["segs"], g["poses"], em["corrected"])
+    q2, _ = oracle.backprop(q1, cov0, em["backprop"][0], em["backprop"][1], d3)
+    assert np.abs(got[:, :2] - q2[:, :2]).max() <= 1e-4
+    # the correction did something: poses after the corrected range moved rigidly
+    assert np.abs(got - g["poses"]).max() > 1e-3
+    # the joint optimisation then starts from these poses with the new constraints
+    summ = session.joint_opt_run(post=False)
+    assert summ["termination"] in (0, 1) and summ["num_hc_residuals"] == 2 * out["n_constraints"]
