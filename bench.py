@@ -84,7 +84,7 @@ def workload(name, n_poses=None, beams=None):
             out["config"] = json.loads(str(z["config_json"]))
             return out
     g = synth.generate(name, n_poses=n_poses, beams=beams)
-    out = {k: g[k] for k in ("poses", "offsets", "pts", "nrm")}
+    out = {k: g[k] for k in ("poses", "offsets", "pts", "nrm", "cov")}
     os.makedirs(os.path.dirname(cache), exist_ok=True)
     np.savez(cache, config_json=np.array(json.dumps(g["config"])), **out)
     out["config"] = g["config"]
@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
+    ap.add_argument("--replay", type=int, default=0, help="BASELINE config 4: replay this many sequential corrections on --replay-workload and report per-correction latency")
+    ap.add_argument("--replay-workload", default="c4")
+    ap.add_argument("--replay-seconds", type=float, default=150.0, help="wall-clock budget of the replay leg (stroke picking included)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -366,6 +369,15 @@ def main():
         except Exception as e:            # the headline line must still print
             correction = {"error": str(e)[:200]}
 
+    replay = None
+    if rank == 0 and args.replay > 0:
+        try:
+            gr = g if args.replay_workload == args.workload else workload(args.replay_workload, synth.CONFIGS[args.replay_workload]["n_poses"], synth.CONFIGS[args.replay_workload]["beams"])
+            replay = correction_replay(gpu, gr, args.replay, budget_s=args.replay_seconds)
+            replay["workload"] = args.replay_workload
+        except Exception as e:
+            replay = {"error": str(e)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rebuild_fast_oracle_native()
@@ -377,7 +389,7 @@ def main():
                     "kdtree_build_device_s": t_build})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction, "correction_replay": replay,
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
                            "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
                            "per_rank_[ms_search,ms_find_stf,tiles,source_poses]": per_rank}}
@@ -429,6 +441,74 @@ def correction_latency(gpu, g, cpu=True, reps=5):
         out["cpu_ms"] = (time.perf_counter() - t0) * 1e3
         out["cpu_what"] = "oracle port, 1 thread as in the reference: world transform + EM (same strokes, %d rounds) + odometry block evaluation" % ref["rounds"]
     return out
+
+
+def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
+    """BASELINE config 4: a replay of sequential human corrections on one map, each drawn on the map AS IT IS after the
+    previous ones (strokes picked from the current poses, untimed).  Per correction, as HitLSLAM::Run wires it: world clouds ->
+    EM -> explicit correction -> COP-SLAM back-propagation -> constraint targets -> joint optimisation.  The latency of the
+    accelerated path excludes the host LM solve, which is reported beside it; every cpu_every-th correction
+    is also run through the single-threaded oracle chain on the same inputs."""
+    from hitl_slam_b200 import HostSession, synth
+    from oracle.pyoracle import Oracle
+    sess = HostSession(gpu)
+    sess.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    n = len(g["poses"])
+    cov = (np.ascontiguousarray(g["cov"], np.float32).reshape(n, 9).copy() if "cov" in g
+           else np.tile(np.array([1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-5], np.float32), (n, 1)))
+    orc = Oracle(fast=True)
+    S = orc.scans(g["offsets"], g["pts"], g["nrm"], build_trees=False)
+    cur = dict(g)
+    lat, solve, parts, cpu_ms, spans, blocks = [], [], [], [], [], []
+    start, t_begin = 0, time.perf_counter()
+    for c in range(n_corrections):
+        if time.perf_counter() - t_begin > budget_s:
+            break
+        cur["poses"] = sess.poses()[0]
+        try:
+            # the first corrections close real loop-closure gaps; once those are used up the replay keeps drawing on revisited
+            # walls wherever they are (a separation of ~0 exercises the same pipeline)
+            strokes, start = synth.pick_strokes(cur, min_sep=0.04 if c < 4 else 0.0, start=start, return_next=True)
+        except RuntimeError:
+            try:
+                strokes, start = synth.pick_strokes(cur, min_sep=0.0, start=start, return_next=True)
+            except RuntimeError:
+                break
+        if cpu_every and c % cpu_every == 0:
+            cov_c = cov.copy()
+            t0 = time.perf_counter()
+            world = S.world_transform(cur["poses"])
+            em = orc.em_run(g["offsets"], world, strokes)
+            if em["backprop"][0] >= 0 and em["backprop"][1] >= 1:
+                p1, c3 = orc.app_exp_corrections(4, em["segs"], cur["poses"], em["corrected"])
+                if c3 is not None:
+                    p1, cov_c = orc.backprop(p1, cov_c, em["backprop"][0], em["backprop"][1], c3)
+                orc.eval_odometry(orc.odometry_consts(p1), p1.astype(np.float64))
+            cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        sess.world_transform(keep_host_copy=False)
+        out = sess.correct(4, strokes, cov=cov, solve=True)
+        t1 = time.perf_counter()
+        total = (t1 - t0) * 1e3
+        lat.append(total - out["ms"]["joint_opt"])
+        solve.append(out["ms"]["joint_opt"])
+        parts.append([out["ms"]["em"], out["ms"]["explicit"], out["ms"]["backprop"], out["ms"]["backprop_device"]])
+        spans.append(out["backprop"][1] - out["backprop"][0] if out["applied"] else 0)
+        blocks.append(out["n_constraints"])
+    sess.close()
+    if not lat:
+        return {"error": "no usable stroke pair on this map"}
+    lat, solve, parts = np.array(lat), np.array(solve), np.array(parts)
+    return {"corrections": int(len(lat)), "unit": "ms per correction",
+            "latency_ms": {"median": float(np.median(lat)), "p90": float(np.percentile(lat, 90)), "max": float(lat.max()), "min": float(lat.min())},
+            "host_solve_ms": {"median": float(np.median(solve)), "max": float(solve.max())},
+            "parts_ms_median": {"em": float(np.median(parts[:, 0])), "explicit_correction": float(np.median(parts[:, 1])),
+                                "backprop": float(np.median(parts[:, 2])), "backprop_device": float(np.median(parts[:, 3]))},
+            "backprop_span_poses": {"median": float(np.median(spans)), "max": int(max(spans))}, "human_blocks_total": int(sum(blocks)),
+            "cpu_ms": {"median": float(np.median(cpu_ms)) if cpu_ms else None, "max": float(max(cpu_ms)) if cpu_ms else None, "samples": len(cpu_ms),
+                       "what": "oracle port, 1 thread as in the reference: world transform + EM + explicit correction + back-propagation + odometry block evaluation"},
+            "what": "world transform + EM + explicit correction + back-propagation (pose update on the GPU) + constraint targets; host LM solve listed separately",
+            "n_poses": int(n), "n_points": int(g["offsets"][-1])}
 
 
 def tensor_from_ptr(ptr, n_doubles, device_index):

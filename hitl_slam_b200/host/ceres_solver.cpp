@@ -229,6 +229,53 @@ bool pcg_solve(const BlockSparse& H, const std::vector<double>& lm_diag2, const 
   return true;   // best effort: the trust-region ratio test guards a poor step
 }
 
+// Direct solve of (H + diag(lm)) x = rhs when H is block TRIDIAGONAL in the order of the variable blocks — the shape of the
+// human-constraint problem (odometry chain + unary factors, JointOptimization.cpp:1064-1138): block Thomas elimination,
+// O(#blocks), exact up to rounding.  Returns false when H has any other coupling (caller falls back to PCG) or a pivot block
+// is not positive definite.
+bool tridiagonal_solve(const BlockSparse& H, const std::vector<double>& lm_diag2, const std::vector<double>& rhs, std::vector<double>* x, bool* applicable) {
+  const size_t m = H.diag.size();
+  std::vector<int> next(m, -1);
+  *applicable = true;
+  for (size_t p = 0; p < H.pairs.size(); ++p) {
+    const int a = H.pairs[p].first, b = H.pairs[p].second;
+    if (b != a + 1 || next[(size_t)a] >= 0) { *applicable = false; return false; }
+    next[(size_t)a] = (int)p;
+  }
+  std::vector<std::vector<double>> Sinv(m);
+  std::vector<double> y = rhs, S, W;
+  for (size_t a = 0; a < m; ++a) {
+    const int s = H.size[a], o = H.off[a];
+    S = H.diag[a];
+    for (int i = 0; i < s; ++i) S[(size_t)i * s + i] += lm_diag2[o + i];
+    if (a > 0 && next[a - 1] >= 0) {
+      const int sp = H.size[a - 1], op = H.off[a - 1];
+      const std::vector<double>& B = H.offd[(size_t)next[a - 1]];          // sp x s
+      const std::vector<double>& Pinv = Sinv[a - 1];                       // sp x sp
+      W.assign((size_t)s * sp, 0.0);                                       // W = B^T * Sinv_prev   (s x sp)
+      for (int i = 0; i < s; ++i) for (int j = 0; j < sp; ++j) { double t = 0; for (int k = 0; k < sp; ++k) t += B[(size_t)k * s + i] * Pinv[(size_t)k * sp + j]; W[(size_t)i * sp + j] = t; }
+      for (int i = 0; i < s; ++i) {
+        for (int j = 0; j < s; ++j) { double t = 0; for (int k = 0; k < sp; ++k) t += W[(size_t)i * sp + k] * B[(size_t)k * s + j]; S[(size_t)i * s + j] -= t; }
+        double t = 0; for (int k = 0; k < sp; ++k) t += W[(size_t)i * sp + k] * y[op + k];
+        y[o + i] -= t;
+      }
+    }
+    if (!small_inverse(S, s, &Sinv[a])) return false;
+  }
+  x->assign(H.n, 0.0);
+  for (size_t a = m; a-- > 0;) {
+    const int s = H.size[a], o = H.off[a];
+    std::vector<double> t(y.begin() + o, y.begin() + o + s);
+    if (a + 1 < m && next[a] >= 0) {
+      const int sn = H.size[a + 1], on = H.off[a + 1];
+      const std::vector<double>& B = H.offd[(size_t)next[a]];              // s x sn
+      for (int i = 0; i < s; ++i) { double u = 0; for (int k = 0; k < sn; ++k) u += B[(size_t)i * sn + k] * (*x)[on + k]; t[i] -= u; }
+    }
+    for (int i = 0; i < s; ++i) { double u = 0; for (int k = 0; k < s; ++k) u += Sinv[a][(size_t)i * s + k] * t[k]; (*x)[o + i] = u; }
+  }
+  return true;
+}
+
 }  // namespace
 
 bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector<double>* residuals, std::vector<double>* gradient, CRSMatrix* jacobian) {
@@ -393,7 +440,10 @@ void Solve(const Solver::Options& opt, Problem* problem, Solver::Summary* summar
       step = g;
       solved = dense_cholesky_solve(A, n, step);
     } else {
-      solved = pcg_solve(H, lm2, g, opt.cg_max_iterations, opt.cg_tolerance, &step);
+      bool chain = false;
+      solved = false;
+      if (opt.chain_direct) solved = tridiagonal_solve(H, lm2, g, &step, &chain);   // odometry chain + unary factors: direct, O(#poses)
+      if (!chain) solved = pcg_solve(H, lm2, g, opt.cg_max_iterations, opt.cg_tolerance, &step);
     }
     double model_change = 0;
     if (solved) {

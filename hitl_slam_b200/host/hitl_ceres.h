@@ -216,7 +216,7 @@ struct Solver {
           initial_trust_region_radius(1e4), max_trust_region_radius(1e16), min_trust_region_radius(1e-32), min_relative_decrease(1e-3),
           min_lm_diagonal(1e-6), max_lm_diagonal(1e32), jacobi_scaling(true), minimizer_progress_to_stdout(false),
           update_state_every_iteration(false), num_threads(1), num_linear_solver_threads(1), evaluation_callback(nullptr),
-          dense_limit(2400), cg_max_iterations(2000), cg_tolerance(1e-12) {}
+          dense_limit(2400), cg_max_iterations(2000), cg_tolerance(1e-12), chain_direct(true) {}
     MinimizerType minimizer_type;
     TrustRegionStrategyType trust_region_strategy_type;
     LinearSolverType linear_solver_type;
@@ -229,6 +229,7 @@ struct Solver {
     EvaluationCallback* evaluation_callback;   // Ceres 1.14 placement; Problem::Options is the 2.x placement
     // stand-in linear algebra (not Ceres options): dense Cholesky up to dense_limit parameters, PCG beyond
     int dense_limit, cg_max_iterations;
+    bool chain_direct;   // beyond dense_limit: block-tridiagonal systems (odometry chain + unary factors) are eliminated directly
     double cg_tolerance;
   };
   struct Summary {

@@ -60,6 +60,7 @@ int hitl_host_seg_fit_em(const double p1[2], const double p2[2], const double* d
 void hitl_host_odometry_consts(const float* poses_xyt, uint32_t n_poses, float* consts9);
 void hitl_host_human_targets(const float* poses_xyt, uint32_t n_poses, uint32_t n, const int32_t* ids3, const float* deltas4, double* targets4);
 int hitl_host_solver_selftest(double x[4], int max_iterations, int hold_x1, int force_cg, double out[4]);
+int hitl_host_solver_chain_selftest(double* x, int n, int mode, double out[4]);
 int hitl_host_load_log(const char* path, uint32_t cap_entries, uint32_t cap_points, int32_t* types, int32_t* undone, int32_t* npts, float* pts_xy,
                        uint32_t* n_entries, uint32_t* n_points);
 int hitl_host_save_log(const char* path, uint32_t n_entries, const int32_t* types, const int32_t* undone, const int32_t* npts, const float* pts_xy);

@@ -66,6 +66,8 @@ namespace {
 struct PowellF1 { template <typename T> bool operator()(const T* x1, const T* x2, T* r) const { r[0] = x1[0] + 10.0 * x2[0]; return true; } };
 struct PowellF2 { template <typename T> bool operator()(const T* x3, const T* x4, T* r) const { r[0] = ::sqrt(5.0) * (x3[0] - x4[0]); return true; } };
 struct PowellF3 { template <typename T> bool operator()(const T* x2, const T* x3, T* r) const { const T d = x2[0] - 2.0 * x3[0]; r[0] = d * d; return true; } };
+struct ChainRel { double dx, dy; template <typename T> bool operator()(const T* a, const T* b, T* r) const { r[0] = b[0] - a[0] - dx + 0.1 * sin(a[1]); r[1] = b[1] - a[1] - dy; return true; } };
+struct ChainPin { double tx, ty; template <typename T> bool operator()(const T* a, T* r) const { r[0] = 3.0 * (a[0] - tx); r[1] = 3.0 * (a[1] - ty) + 0.2 * (a[0] - tx); return true; } };
 struct PowellF4 { template <typename T> bool operator()(const T* x1, const T* x4, T* r) const { const T d = x1[0] - x4[0]; r[0] = ::sqrt(10.0) * d * d; return true; } };
 }  // namespace
 
@@ -412,6 +414,25 @@ int hitl_host_solver_selftest(double x[4], int max_iterations, int hold_x1, int 
   o.max_num_iterations = max_iterations;
   o.function_tolerance = 1e-20; o.gradient_tolerance = 1e-14; o.parameter_tolerance = 1e-14;
   if (force_cg) o.dense_limit = 0;
+  ceres::Solver::Summary s;
+  ceres::Solve(o, &problem, &s);
+  out[0] = s.initial_cost; out[1] = s.final_cost; out[2] = s.num_successful_steps + s.num_unsuccessful_steps; out[3] = (double)s.termination_type;
+  return 0;
+}
+
+// A pose-chain problem of the human-constraint shape — n blocks of 2 parameters, relative factors between neighbours,
+// unary factors on every 7th block, non-linear through a sine — solved with the dense path (mode 0), the chain-direct
+// path (mode 1: block-tridiagonal elimination) or PCG (mode 2).  x: 2 n values in/out.
+int hitl_host_solver_chain_selftest(double* x, int n, int mode, double out[4]) {
+  ceres::Problem problem;
+  for (int i = 0; i + 1 < n; ++i) problem.AddResidualBlock(new ceres::AutoDiffCostFunction<ChainRel, 2, 2, 2>(new ChainRel{0.3 + 0.01 * (i % 5), -0.1 + 0.02 * (i % 3)}), NULL, &x[2 * i], &x[2 * i + 2]);
+  for (int i = 3; i < n; i += 7) problem.AddResidualBlock(new ceres::AutoDiffCostFunction<ChainPin, 2, 2>(new ChainPin{0.31 * i, -0.07 * i}), NULL, &x[2 * i]);
+  problem.SetParameterBlockConstant(&x[0]);
+  ceres::Solver::Options o;
+  o.max_num_iterations = 200;
+  o.function_tolerance = 1e-18; o.gradient_tolerance = 1e-13; o.parameter_tolerance = 1e-14;
+  o.dense_limit = mode == 0 ? (1 << 30) : 0;
+  if (mode == 2) o.chain_direct = false;
   ceres::Solver::Summary s;
   ceres::Solve(o, &problem, &s);
   out[0] = s.initial_cost; out[1] = s.final_cost; out[2] = s.num_successful_steps + s.num_unsuccessful_steps; out[3] = (double)s.termination_type;

@@ -233,44 +233,67 @@ def _observers(w, pid, a, b, thr=0.03, min_obs=5):
     return ids[cnt > min_obs]
 
 
-def pick_strokes(g, min_sep=0.07, max_sep=0.6, window=2.0):
-    """Two strokes a human would draw on the displayed map to close a loop: the same physical wall as
-    it appears on a LATE visit (feature A, first stroke) and on an EARLY visit (feature B), picked where
-    odometry drift separates the two appearances by more than the EM pill and the poses observing the
-    two strokes are cleanly ordered in time.  Returns float32 [4, 2] (a0, a1, b0, b1) or raises if the
-    map has no usable revisit."""
-    cfg = g["config"]
+def _wall_windows(cfg, window):
+    """Every (wall y, x0, x1) window a stroke pair may be drawn on: the horizontal walls of every block."""
     cor, bw, bh = cfg["cor"], cfg["bw"], cfg["bh"]
-    w, pid = world_points(g)
+    out = []
     for j in range(cfg["by"]):
         for i in range(cfg["bx"]):
             for ywall in (cor + j * (bh + cor), cor + j * (bh + cor) + bh):
                 wx0, wx1 = cor + i * (bw + cor) + 0.1 * bw, cor + i * (bw + cor) + 0.9 * bw
                 for x0 in np.arange(wx0, wx1 - window + 1e-9, 0.5):
-                    x1 = x0 + window
-                    sel = (np.abs(w[:, 1] - ywall) < 0.3) & (w[:, 0] > x0) & (w[:, 0] < x1)
-                    ids = np.unique(pid[sel])
-                    if len(ids) < 12:
-                        continue
-                    passes = [p for p in np.split(ids, np.where(np.diff(ids) > 25)[0] + 1) if len(p) >= 6]
-                    fits = []
-                    for p in passes:
-                        m = sel & np.isin(pid, p)
-                        fits.append(np.polyfit(w[m, 0], w[m, 1], 1) if m.sum() >= 40 else None)
-                    for late in range(len(passes) - 1, 0, -1):
-                        for early in range(late):
-                            if fits[late] is None or fits[early] is None:
-                                continue
-                            (k1, c1), (k0, c0) = fits[late], fits[early]
-                            xm = 0.5 * (x0 + x1)
-                            sep = abs((k1 * xm + c1) - (k0 * xm + c0))
-                            if not (min_sep <= sep <= max_sep):
-                                continue
-                            A = np.array([[x0, k1 * x0 + c1], [x1, k1 * x1 + c1]])
-                            B = np.array([[x0, k0 * x0 + c0], [x1, k0 * x1 + c0]])
-                            fa, fb = _observers(w, pid, A[0], A[1]), _observers(w, pid, B[0], B[1])
-                            both = np.intersect1d(fa, fb)
-                            fa, fb = np.setdiff1d(fa, both), np.setdiff1d(fb, both)
-                            if len(fa) >= 3 and len(fb) >= 3 and fa.min() > fb.max() + 5:
-                                return np.concatenate([A, B]).astype(np.float32)
+                    out.append((ywall, float(x0), float(x0 + window)))
+    return out
+
+
+def pick_strokes(g, min_sep=0.07, max_sep=0.6, window=2.0, start=0, return_next=False):
+    """Two strokes a human would draw on the displayed map to close a loop: the same physical wall as
+    it appears on a LATE visit (feature A, first stroke) and on an EARLY visit (feature B), picked where
+    odometry drift separates the two appearances by more than the EM pill and the poses observing the
+    two strokes are cleanly ordered in time.  Returns float32 [4, 2] (a0, a1, b0, b1) or raises if the
+    map has no usable revisit.  `start` rotates the order in which the walls are tried (a replay of many
+    corrections draws on a different place each time); with return_next the index to continue from is returned too."""
+    cfg = g["config"]
+    w, pid = world_points(g)
+    wins = _wall_windows(cfg, window)
+    w_all, pid_all, band_of = w, pid, None
+    for q in range(len(wins)):
+        ywall, x0, x1 = wins[(start + q) % len(wins)]
+        if band_of != ywall:                                   # points near this wall, once per wall (the map has millions of points)
+            near = np.flatnonzero(np.abs(w_all[:, 1] - ywall) < 0.35)
+            w, pid, band_of = w_all[near], pid_all[near], ywall
+        sel = (np.abs(w[:, 1] - ywall) < 0.3) & (w[:, 0] > x0) & (w[:, 0] < x1)
+        ids = np.unique(pid[sel])
+        if len(ids) < 12:
+            continue
+        passes = [p for p in np.split(ids, np.where(np.diff(ids) > 25)[0] + 1) if len(p) >= 6]
+        inwin = np.flatnonzero((w[:, 0] > x0 - 0.05) & (w[:, 0] < x1 + 0.05))     # a stroke's pill lies inside the window
+        ww, wp = w[inwin], pid[inwin]
+        tried = 0
+        fits = []
+        for p in passes:
+            m = sel & np.isin(pid, p)
+            fits.append(np.polyfit(w[m, 0], w[m, 1], 1) if m.sum() >= 40 else None)
+        for late in range(len(passes) - 1, 0, -1):
+            if tried > 24:
+                break
+            for early in range(late):
+                if fits[late] is None or fits[early] is None:
+                    continue
+                (k1, c1), (k0, c0) = fits[late], fits[early]
+                xm = 0.5 * (x0 + x1)
+                sep = abs((k1 * xm + c1) - (k0 * xm + c0))
+                if not (min_sep <= sep <= max_sep):
+                    continue
+                A = np.array([[x0, k1 * x0 + c1], [x1, k1 * x1 + c1]])
+                B = np.array([[x0, k0 * x0 + c0], [x1, k0 * x1 + c0]])
+                tried += 1
+                if tried > 24:                                   # enough attempts on this window: move on
+                    break
+                fa, fb = _observers(ww, wp, A[0], A[1]), _observers(ww, wp, B[0], B[1])
+                both = np.intersect1d(fa, fb)
+                fa, fb = np.setdiff1d(fa, both), np.setdiff1d(fb, both)
+                if len(fa) >= 3 and len(fb) >= 3 and fa.min() > fb.max() + 5:
+                    out = np.concatenate([A, B]).astype(np.float32)
+                    return (out, (start + q + 1) % len(wins)) if return_next else out
     raise RuntimeError("no revisited wall with enough drift in this map")

@@ -39,6 +39,26 @@ def test_solver_powell_dense_cg_and_constant_block(host):
     assert np.abs(x[1:] - ref.x).max() < 1e-6
 
 
+def test_solver_chain_direct_matches_dense_and_cg(host):
+    """Beyond the dense limit the stand-in LM eliminates block-tridiagonal systems (the odometry chain + unary human factors)
+    directly; same minimiser as the dense path and as PCG."""
+    import ctypes as C
+    lib = host.lib
+    lib.hitl_host_solver_chain_selftest.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C"), C.c_int, C.c_int, np.ctypeslib.ndpointer(np.float64, flags="C")]
+    for n in (2, 3, 40, 400):
+        rng = np.random.default_rng(n)
+        x0 = np.cumsum(rng.normal(size=(n, 2)) * 0.3, 0).reshape(-1)
+        sols, costs = [], []
+        for mode in (0, 1, 2):
+            x, out = x0.copy(), np.zeros(4)
+            assert lib.hitl_host_solver_chain_selftest(x, n, mode, out) == 0
+            assert out[1] <= out[0] and out[3] in (0.0, 1.0)
+            sols.append(x); costs.append(out[1])
+        assert np.abs(sols[1] - sols[0]).max() <= 1e-7 and np.abs(sols[2] - sols[0]).max() <= 1e-5
+        assert abs(costs[1] - costs[0]) <= 1e-10 * max(1.0, costs[0])
+        assert np.array_equal(sols[1][:2], x0[:2])                # the constant block stays put
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_seg_fit_em_matches_oracle(host, oracle, seed):
     rng = np.random.default_rng(seed)
