@@ -459,7 +459,7 @@ def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
     orc = Oracle(fast=True)
     S = orc.scans(g["offsets"], g["pts"], g["nrm"], build_trees=False)
     cur = dict(g)
-    lat, solve, parts, cpu_ms, spans, blocks = [], [], [], [], [], []
+    lat, solve, parts, cpu_ms, spans, blocks, applied = [], [], [], [], [], [], []
     start, t_begin = 0, time.perf_counter()
     for c in range(n_corrections):
         if time.perf_counter() - t_begin > budget_s:
@@ -495,11 +495,17 @@ def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
         parts.append([out["ms"]["em"], out["ms"]["explicit"], out["ms"]["backprop"], out["ms"]["backprop_device"]])
         spans.append(out["backprop"][1] - out["backprop"][0] if out["applied"] else 0)
         blocks.append(out["n_constraints"])
+        applied.append(bool(out["applied"]))
     sess.close()
     if not lat:
         return {"error": "no usable stroke pair on this map"}
-    lat, solve, parts = np.array(lat), np.array(solve), np.array(parts)
-    return {"corrections": int(len(lat)), "unit": "ms per correction",
+    attempted = len(lat)
+    keep = np.array(applied, bool) if any(applied) else np.ones(len(lat), bool)
+    # statistics over the corrections that went all the way (EM found cleanly ordered observers of both strokes); the others stop
+    # after EM, as HitLSLAM::Run does when the back-propagation bounds are invalid (HitLSLAM.cpp:413)
+    lat, solve, parts = np.array(lat)[keep], np.array(solve)[keep], np.array(parts)[keep]
+    spans = [sp for sp, k in zip(spans, keep) if k]
+    return {"corrections": int(len(lat)), "attempted": int(attempted), "unit": "ms per correction",
             "latency_ms": {"median": float(np.median(lat)), "p90": float(np.percentile(lat, 90)), "max": float(lat.max()), "min": float(lat.min())},
             "host_solve_ms": {"median": float(np.median(solve)), "max": float(solve.max())},
             "parts_ms_median": {"em": float(np.median(parts[:, 0])), "explicit_correction": float(np.median(parts[:, 1])),
