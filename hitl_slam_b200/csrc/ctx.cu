@@ -150,7 +150,7 @@ extern "C" int hitl_create(hitl_ctx** out, int device) {
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 4; ++i) { cudaEventCreate(&ctx->ev[i]); cudaEventCreate(&ctx->evx[i]); }
   if (cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess) { hitl_destroy(ctx); cudaGetLastError(); return HITL_ERR_CUDA; }
   *out = ctx;
   return HITL_OK;
@@ -180,7 +180,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_p2l_pose.release(); ctx->d_p2l_pts.release(); ctx->d_p2l_n.release(); ctx->d_p2l_o.release(); ctx->d_p2l_v.release();
   ctx->d_r.release(); ctx->d_J.release(); ctx->d_neq.release(); ctx->d_hoff.release(); ctx->d_trig.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 4; ++i) { if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); if (ctx->evx[i]) cudaEventDestroy(ctx->evx[i]); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

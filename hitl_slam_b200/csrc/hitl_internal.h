@@ -48,6 +48,7 @@ struct hitl_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};   // extra phase marks of hitl_find_stf (HITL_STF_TIMING=1 prints them)
   std::string err;
   uint64_t launches = 0;
 

@@ -24,6 +24,7 @@
 //     merge the tiles of each pose into the reference's (i, j, k) order, apply the
 //     "> 10 matches per pair" rule and emit the CSR arrays.
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -745,15 +746,19 @@ __global__ void __launch_bounds__(128) stf_split_merge_kernel(const MergeParams 
 //   (host-launched scan over poses)
 //   pass 1 (fill):  per pose -> pair_i, pair_j, pair_off, k, idx at the scanned offsets
 // ------------------------------------------------------------------------------------------------
-constexpr int kOrderThreads = 128;
+constexpr int kOrderThreads = 512;   // the record sweeps are chains of dependent loads per thread: many threads, few iterations each
 constexpr uint32_t kDropped = 0xFFFFFFFFu;
+constexpr uint32_t kMaxTileRecords = 32 * 64;   // a tile holds <= 32 points x cap (<= 64) records
+constexpr uint32_t kOrderSlots = 1024;          // kept pairs of one source pose whose fill position lives in shared memory
+constexpr uint32_t kOrderTileBatch = 256;       // tile descriptors fetched at once
+constexpr uint32_t kOrderMaskWords = 6144;      // shared bitmap of the fast placement path (pairs x ceil(points / 32) words)
+constexpr uint32_t kSlotFlag = 0x80000000u;     // cntj[j] = kSlotFlag | slot (offsets inside a pose's segment stay below 2^31)
 
 struct OrderParams {
   const uint32_t* __restrict__ raw_j; const uint32_t* __restrict__ raw_k; const uint32_t* __restrict__ raw_idx;
   const uint32_t* __restrict__ tile_cnt; const uint32_t* __restrict__ tile_begin; const uint32_t* __restrict__ tile_slot; const uint32_t* __restrict__ off;
   uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
   uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
-  uint32_t* kept;                     // gridDim.x * n_poses: kept target poses of the pose being placed (pass 1)
   unsigned long long* pose_cnt;       // 2 per source pose of the shard: matches, pairs (pass 1: exclusive offsets)
   uint32_t* pair_i; uint32_t* pair_j; unsigned long long* pair_off; uint32_t* out_k; uint32_t* out_idx;
 };
@@ -792,23 +797,46 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned lo
 
 template <int PASS>
 __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderParams P) {
-  __shared__ unsigned long long sm[8];
+  __shared__ unsigned long long sm[kOrderThreads / 32 + 1];
   __shared__ uint32_t s_jlo, s_jhi;
   __shared__ unsigned long long s_off_m, s_off_p;
+  __shared__ uint32_t s_hcnt[kOrderTileBatch], s_hbase[kOrderTileBatch], s_htotal;   // tile descriptors of the pose (prefix of counts, record bases)
+  __shared__ uint32_t s_next[PASS == 1 ? kOrderSlots : 1];      // next free slot of the pose's first kOrderSlots kept pairs
+  __shared__ uint32_t s_tcnt[PASS == 1 ? kOrderTileBatch : 1], s_tbase[PASS == 1 ? kOrderTileBatch : 1];
+  __shared__ uint32_t s_mask[PASS == 1 ? kOrderMaskWords : 1];  // fast path: one bit row per kept pair over the pose's points
+  uint32_t* const s_j = s_mask;                                 // fallback path: the j column of the tile being placed (<= kMaxTileRecords)
+  __shared__ uint16_t s_pref[PASS == 1 ? kOrderMaskWords : 1];  // ... and the popcount prefix of each row word
+  __shared__ uint32_t s_total;
   uint32_t* const cntj = P.scratch + (size_t)blockIdx.x * P.n_poses;
-  uint32_t* const keptj = PASS == 1 ? P.kept + (size_t)blockIdx.x * P.n_poses : nullptr;
   for (uint32_t i = P.src_lo + blockIdx.x; i < P.src_hi; i += gridDim.x) {
     const uint32_t tb = P.tile_begin[i], te = P.tile_begin[i + 1];
     if (threadIdx.x == 0) { s_jlo = 0xFFFFFFFFu; s_jhi = 0; }
     __syncthreads();
-    // -- histogram over j (tile lists are sorted by j: first/last record bound the range) --
+    // -- histogram over j.  Tile descriptors are fetched in one sweep and the records are addressed by a flat index, so all
+    //    loads of a pose are independent of each other (no per-tile chain of dependent round trips). --
     uint32_t jlo = 0xFFFFFFFFu, jhi = 0;
-    for (uint32_t t = tb; t < te; ++t) {
-      const uint32_t c = P.tile_cnt[t], base = P.tile_slot[t] * (uint32_t)P.cap;
-      for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
-        const uint32_t j = P.raw_j[base + u];
+    const uint32_t ntile_h = te - tb;
+    if (ntile_h <= kOrderTileBatch) {
+      for (uint32_t q = threadIdx.x; q < ntile_h; q += kOrderThreads) { s_hcnt[q] = P.tile_cnt[tb + q]; s_hbase[q] = P.tile_slot[tb + q] * (uint32_t)P.cap; }
+      __syncthreads();
+      if (threadIdx.x == 0) { uint32_t acc = 0; for (uint32_t q = 0; q < ntile_h; ++q) { const uint32_t c = s_hcnt[q]; s_hcnt[q] = acc; acc += c; } s_htotal = acc; }
+      __syncthreads();
+      const uint32_t R = s_htotal;
+      for (uint32_t g = threadIdx.x; g < R; g += kOrderThreads) {
+        uint32_t lo = 0, hi = ntile_h;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_hcnt[mid] <= g) lo = mid; else hi = mid; }
+        const uint32_t j = P.raw_j[s_hbase[lo] + (g - s_hcnt[lo])];
         atomicAdd(&cntj[j], 1u);
         jlo = min(jlo, j); jhi = max(jhi, j);
+      }
+    } else {
+      for (uint32_t t = tb; t < te; ++t) {
+        const uint32_t c = P.tile_cnt[t], base = P.tile_slot[t] * (uint32_t)P.cap;
+        for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+          const uint32_t j = P.raw_j[base + u];
+          atomicAdd(&cntj[j], 1u);
+          jlo = min(jlo, j); jhi = max(jhi, j);
+        }
       }
     }
     if (jlo != 0xFFFFFFFFu) { atomicMin(&s_jlo, jlo); atomicMax(&s_jhi, jhi); }
@@ -820,52 +848,115 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
     if (jlo != 0xFFFFFFFFu) {
       // -- scan over j in [jlo, jhi]: kept-match prefix and kept-pair prefix --
       uint32_t run_m = 0, run_p = 0;
-      for (uint32_t j0 = jlo; j0 <= jhi; j0 += kOrderThreads) {
-        const uint32_t j = j0 + threadIdx.x;
-        const uint32_t c = j <= jhi ? cntj[j] : 0;
-        const uint32_t keep = c > P.min_corr ? c : 0;
+      for (uint32_t j0 = jlo; j0 <= jhi; j0 += 4 * kOrderThreads) {
+        uint32_t keep[4], lm = 0, lp = 0;
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t j = j0 + 4 * threadIdx.x + q;
+          const uint32_t c = j <= jhi ? cntj[j] : 0;
+          keep[q] = c > P.min_corr ? c : 0;
+          lm += keep[q]; lp += keep[q] ? 1u : 0u;
+        }
         unsigned long long tot2;
-        const unsigned long long ex2 = block_exclusive_scan64((unsigned long long)keep | ((unsigned long long)(keep ? 1u : 0u) << 40), &tot2, sm);
-        const uint32_t em = (uint32_t)(ex2 & 0xFFFFFFFFFFull), ep = (uint32_t)(ex2 >> 40);
+        const unsigned long long ex2 = block_exclusive_scan64((unsigned long long)lm | ((unsigned long long)lp << 40), &tot2, sm);
+        uint32_t em = (uint32_t)(ex2 & 0xFFFFFFFFFFull), ep = (uint32_t)(ex2 >> 40);
         const uint32_t tm = (uint32_t)(tot2 & 0xFFFFFFFFFFull), tp = (uint32_t)(tot2 >> 40);
-        if (PASS == 1 && j <= jhi) {
-          if (keep) {
-            const unsigned long long po = s_off_p + run_p + ep;
-            P.pair_i[po] = i; P.pair_j[po] = j; P.pair_off[po] = s_off_m + run_m + em;
-            cntj[j] = run_m + em;                 // start of this pair inside the pose's kept segment
-            keptj[run_p + ep] = j;
+        if (PASS == 1) {
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t j = j0 + 4 * threadIdx.x + q;
+            if (j > jhi) break;
+            if (keep[q]) {
+              const uint32_t slot = run_p + ep;       // index of pair (i, j) among the pose's kept pairs
+              const unsigned long long po = s_off_p + slot;
+              P.pair_i[po] = i; P.pair_j[po] = j; P.pair_off[po] = s_off_m + run_m + em;
+              // next free slot of the pair inside the pose's kept segment: in shared memory for the first kOrderSlots pairs
+              // (cntj[j] then names the slot), in cntj[j] itself beyond
+              if (slot < kOrderSlots) { s_next[slot] = run_m + em; cntj[j] = kSlotFlag | slot; }
+              else cntj[j] = run_m + em;
+              em += keep[q]; ep += 1;
+            } else {
+              cntj[j] = kDropped;
+            }
           }
         }
         run_m += tm; run_p += tp;
       }
       tot_m = run_m; tot_p = run_p;
       if (PASS == 1) {
-        __syncthreads();
-        // -- placement, one warp per kept target pose j: every tile list is sorted by (j, k) and tiles are
-        //    in ascending k order, so pair (i, j) is the concatenation over tiles of each tile's run of j.
-        //    Lanes bisect "their" tile for the run, a warp scan turns run lengths into offsets. --
-        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const uint32_t ntile = te - tb;
-        for (uint32_t e = wid; e < tot_p; e += kOrderThreads / 32) {
-          const uint32_t j = keptj[e];
-          unsigned long long dst = s_off_m + cntj[j];
-          for (uint32_t t0 = 0; t0 < ntile; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            uint32_t lb = 0, len = 0, base = 0;
-            if (t < ntile) {
-              const uint32_t c = P.tile_cnt[tb + t];
-              base = P.tile_slot[tb + t] * (uint32_t)P.cap;
-              uint32_t lo = 0, hi = c;                                   // lower_bound(j)
-              while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (P.raw_j[base + mid] < j) lo = mid + 1; else hi = mid; }
-              lb = lo;
-              while (lb + len < c && len < 32 && P.raw_j[base + lb + len] == j) ++len;   // a run holds each point at most once: <= 32 records
+        // -- placement, tile by tile: every tile list is sorted by (j, k) and the tiles of a pose come in ascending k
+        //    (units of a split tile: ascending target range), so pair (i, j) is the concatenation over tiles of each
+        //    tile's run of j.  A record's slot = the pair's next free slot + its rank inside the run (bisection of the
+        //    tile's j column in shared memory); the last record of a run then advances the pair's next free slot.
+        //    Tile descriptors are fetched once per pose, so the per-tile chain touches shared memory only. --
+        // Fast path (the usual case): the pose's kept pairs x ceil(points / 32) words fit the shared bitmap.  Within pair (i, j)
+        // the final order is ascending source point k and a point appears at most once, so a record's rank is the number of
+        // the pair's points below k: every record sets bit k of its pair's row, rows are prefix-popcounted, every record
+        // reads its rank back.  Three sweeps over the records with independent loads — no per-tile chain.
+        const uint32_t n_pts = P.off[i + 1] - P.off[i], W = (n_pts + 31) >> 5, ntile = te - tb;
+        const bool fast = tot_p <= kOrderSlots && (uint64_t)tot_p * W <= kOrderMaskWords && ntile <= kOrderTileBatch;
+        if (fast) {
+          __syncthreads();
+          for (uint32_t q = threadIdx.x; q < ntile; q += kOrderThreads) { s_tcnt[q] = P.tile_cnt[tb + q]; s_tbase[q] = P.tile_slot[tb + q] * (uint32_t)P.cap; }
+          for (uint32_t q = threadIdx.x; q < tot_p * W; q += kOrderThreads) s_mask[q] = 0;
+          __syncthreads();
+          if (threadIdx.x == 0) { uint32_t acc = 0; for (uint32_t q = 0; q < ntile; ++q) { const uint32_t c = s_tcnt[q]; s_tcnt[q] = acc; acc += c; } s_total = acc; }
+          __syncthreads();
+          const uint32_t R = s_total;
+          auto locate = [&](uint32_t g) -> uint32_t {                     // flat record index -> address in the raw arrays
+            uint32_t lo = 0, hi = ntile;                                   // last tile with prefix <= g
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_tcnt[mid] <= g) lo = mid; else hi = mid; }
+            return s_tbase[lo] + (g - s_tcnt[lo]);
+          };
+          for (uint32_t g = threadIdx.x; g < R; g += kOrderThreads) {
+            const uint32_t a = locate(g), v = cntj[P.raw_j[a]];
+            if (v == kDropped) continue;
+            const uint32_t k = P.raw_k[a];
+            atomicOr(&s_mask[(v & ~kSlotFlag) * W + (k >> 5)], 1u << (k & 31));
+          }
+          __syncthreads();
+          for (uint32_t e = threadIdx.x; e < tot_p; e += kOrderThreads) {
+            uint32_t acc = 0;
+            for (uint32_t w = 0; w < W; ++w) { s_pref[e * W + w] = (uint16_t)acc; acc += __popc(s_mask[e * W + w]); }
+          }
+          __syncthreads();
+          for (uint32_t g = threadIdx.x; g < R; g += kOrderThreads) {
+            const uint32_t a = locate(g), v = cntj[P.raw_j[a]];
+            if (v == kDropped) continue;
+            const uint32_t k = P.raw_k[a], e = v & ~kSlotFlag;
+            const uint32_t rank = s_pref[e * W + (k >> 5)] + __popc(s_mask[e * W + (k >> 5)] & ((1u << (k & 31)) - 1u));
+            const unsigned long long dst = s_off_m + s_next[e] + rank;
+            P.out_k[dst] = k; P.out_idx[dst] = P.raw_idx[a];
+          }
+        } else
+        for (uint32_t t0 = tb; t0 < te; t0 += kOrderTileBatch) {
+          const uint32_t nt = min(kOrderTileBatch, te - t0);
+          __syncthreads();
+          for (uint32_t q = threadIdx.x; q < nt; q += kOrderThreads) { s_tcnt[q] = P.tile_cnt[t0 + q]; s_tbase[q] = P.tile_slot[t0 + q] * (uint32_t)P.cap; }
+          __syncthreads();
+          for (uint32_t q = 0; q < nt; ++q) {
+            const uint32_t c = s_tcnt[q], base = s_tbase[q];
+            if (c == 0) continue;
+            __syncthreads();
+            for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) s_j[u] = P.raw_j[base + u];
+            __syncthreads();
+            for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+              const uint32_t j = s_j[u], v = cntj[j];
+              if (v == kDropped) continue;
+              uint32_t lo = 0, hi = u;                                   // first record of the run of j
+              while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_j[mid] < j) lo = mid + 1; else hi = mid; }
+              const uint32_t st = (v & kSlotFlag) ? s_next[v & ~kSlotFlag] : v;
+              const unsigned long long dst = s_off_m + st + (u - lo);
+              P.out_k[dst] = P.raw_k[base + u]; P.out_idx[dst] = P.raw_idx[base + u];
             }
-            uint32_t x = len;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
-            const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
-            const unsigned long long o0 = dst + (x - len);
-            for (uint32_t r = 0; r < len; ++r) { P.out_k[o0 + r] = P.raw_k[base + lb + r]; P.out_idx[o0 + r] = P.raw_idx[base + lb + r]; }
-            dst += total;
+            __syncthreads();
+            for (uint32_t u = threadIdx.x; u < c; u += kOrderThreads) {
+              const uint32_t j = s_j[u];
+              if (u + 1 != c && s_j[u + 1] == j) continue;               // only the last record of a run
+              const uint32_t v = cntj[j];
+              if (v == kDropped) continue;
+              uint32_t lo = 0, hi = u;
+              while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_j[mid] < j) lo = mid + 1; else hi = mid; }
+              if (v & kSlotFlag) s_next[v & ~kSlotFlag] += u - lo + 1; else cntj[j] = v + (u - lo + 1);
+            }
           }
         }
       }
@@ -1108,6 +1199,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   int rc = upload_poses_and_prep(ctx, pose_array, o->point_match_threshold);
   if (rc) return rc;
 
+  HITL_CUDA(cudaEventRecord(ctx->evx[0], ctx->stream));   // after pose upload + prep
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
@@ -1159,21 +1251,26 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     HITL_LAUNCH_CHECK("stf_split_merge_kernel");
   }
 
+  HITL_CUDA(cudaEventRecord(ctx->evx[1], ctx->stream));   // after the split merge
   OrderParams Q;
   Q.raw_j = ctx->d_raw_j.p; Q.raw_k = ctx->d_raw_k.p; Q.raw_idx = ctx->d_raw_idx.p; Q.tile_cnt = ctx->d_tile_cnt.p;
   Q.tile_begin = ctx->d_tile_begin.p; Q.tile_slot = ctx->d_tile_slot.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
   Q.min_corr = o->min_inter_pose_correspondence;
-  const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)ctx->sm_count * 8);
+  int order_per_sm = 0;
+  HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&order_per_sm, stf_order_kernel<1>, kOrderThreads, 0));
+  if (order_per_sm < 1) order_per_sm = 1;
+  const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)(ctx->sm_count * order_per_sm));   // one resident wave: a CTA keeps an n_poses-sized scratch
   HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
-  HITL_CUDA(ctx->d_srt_k.ensure((size_t)order_grid * n));   // reused as the kept-j lists
   HITL_CUDA(cudaMemsetAsync(ctx->d_srt_j.p, 0, sizeof(uint32_t) * (size_t)order_grid * n, ctx->stream));
-  Q.scratch = ctx->d_srt_j.p; Q.kept = ctx->d_srt_k.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
+  Q.scratch = ctx->d_srt_j.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
   Q.pair_i = ctx->d_pair_i.p; Q.pair_j = ctx->d_pair_j.p; Q.pair_off = (unsigned long long*)ctx->d_pair_off.p;
   Q.out_k = ctx->d_k.p; Q.out_idx = ctx->d_idx.p;
   stf_order_kernel<0><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<0>");
+  HITL_CUDA(cudaEventRecord(ctx->evx[2], ctx->stream));   // after order<0>
   pose_cnt_scan_kernel<<<1, 1024, 0, ctx->stream>>>((unsigned long long*)ctx->d_pose_cnt.p, hi - lo, (unsigned long long*)ctx->d_counters.p);
   HITL_LAUNCH_CHECK("pose_cnt_scan_kernel");
+  HITL_CUDA(cudaEventRecord(ctx->evx[3], ctx->stream));   // after the scan
   stf_order_kernel<1><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<1>");
   HITL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -1188,6 +1285,12 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_search, ctx->ev[1], ctx->ev[2]));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_total, ctx->ev[0], ctx->ev[3]));
+  if (getenv("HITL_STF_TIMING")) {
+    float a = 0, b = 0, c = 0, d = 0, e = 0, f = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->evx[0]); cudaEventElapsedTime(&b, ctx->evx[0], ctx->ev[1]); cudaEventElapsedTime(&c, ctx->ev[2], ctx->evx[1]);
+    cudaEventElapsedTime(&d, ctx->evx[1], ctx->evx[2]); cudaEventElapsedTime(&e, ctx->evx[2], ctx->evx[3]); cudaEventElapsedTime(&f, ctx->evx[3], ctx->ev[3]);
+    fprintf(stderr, "find_stf phases (ms): prep %.3f | schedule sort %.3f | search %.3f | split merge %.3f | order<0> %.3f | scan %.3f | order<1> %.3f\n", a, b, inf.ms_search, c, d, e, f);
+  }
   ctx->n_pairs = inf.n_pairs; ctx->n_matches = inf.n_matches; ctx->have_stf = true;
   inf.n_tiles = n_tiles; inf.n_tiles_next = n_tiles;
   if (info) *info = inf;
