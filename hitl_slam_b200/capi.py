@@ -488,6 +488,7 @@ class HostLib:
         vp = C.c_void_p
         lib.hitl_host_seg_fit_em.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p]
         lib.hitl_host_app_exp_correct.argtypes = [C.c_int, _f32p, C.c_uint32, _f32p, C.c_uint32, _i32p, _f32p]
+        lib.hitl_host_constraint_targets.argtypes = [C.c_int, _f32p, C.c_uint32, _f32p, C.c_uint32, _i32p, C.c_uint32, _i32p, _i32p, _f32p]
         lib.hitl_host_backprop.argtypes = [vp, C.c_uint32, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, C.POINTER(C.c_float)]
         lib.hitl_host_session_correct.argtypes = [vp, C.c_int, _f32p, vp, C.c_int, _i32p, _f64p, _f64p]
         lib.hitl_host_odometry_consts.argtypes = [_f32p, C.c_uint32, _f32p]
@@ -605,7 +606,21 @@ def _hostlib_backprop(self, gpu, poses_f32, cov9, lo, hi, c3):
     return p.reshape(-1, 3), cov.reshape(-1, 9), ms.value
 
 
+def _hostlib_constraint_targets(self, ctype, sel, poses_f32, corrected, anchor):
+    """AppExpCorrect::calculateConstraintTargets: (ids3 [B,3] i32 = type, constrained, anchor; deltas4 [B,4] f32), anchor-major."""
+    self._bind_mirror()
+    p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+    cor, anc = np.ascontiguousarray(corrected, np.int32), np.ascontiguousarray(anchor, np.int32)
+    nb = max(len(cor) * len(anc), 1)
+    ids, dl = np.zeros(3 * nb, np.int32), np.zeros(4 * nb, np.float32)
+    n = self.lib.hitl_host_constraint_targets(int(ctype), np.ascontiguousarray(sel, np.float32).reshape(-1), len(p) // 3, p, len(cor), cor, len(anc), anc, ids, dl)
+    if n < 0:
+        raise HitlError("hitl_host_constraint_targets failed")
+    return ids[:3 * n].reshape(-1, 3).copy(), dl[:4 * n].reshape(-1, 4).copy()
+
+
 HostLib.app_exp_correct = _hostlib_app_exp_correct
+HostLib.constraint_targets = _hostlib_constraint_targets
 HostLib.backprop = _hostlib_backprop
 
 

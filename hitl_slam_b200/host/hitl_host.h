@@ -44,6 +44,8 @@ int hitl_host_session_add_constraints_from_em(void* s, uint32_t* n_out);
 int hitl_host_session_add_constraints(void* s, uint32_t n, const int32_t* ids3, const float* deltas4);
 int hitl_host_session_clear_constraints(void* s);
 int hitl_host_app_exp_correct(int correction_type, const float sel_xy[8], uint32_t n_poses, float* poses_xyt, uint32_t n_corrected, const int32_t* corrected, float C3[3]);
+int hitl_host_constraint_targets(int correction_type, const float sel_xy[8], uint32_t n_poses, const float* poses_xyt, uint32_t n_corrected, const int32_t* corrected,
+                                 uint32_t n_anchor, const int32_t* anchor, int32_t* ids3, float* deltas4);
 int hitl_host_backprop(void* ctx, uint32_t n_poses, float* poses_xyt, float* cov9, int32_t lo, int32_t hi, const float C3[3], float* device_ms);
 int hitl_host_session_correct(void* s, int correction_type, float sel_xy[8], float* cov9, int solve, int32_t info[8], double ms[5], double summary[6]);
 int hitl_host_session_solver_options(void* s, int which, int max_iterations, double function_tolerance, double gradient_tolerance, double parameter_tolerance,

@@ -209,6 +209,27 @@ int hitl_host_app_exp_correct(int correction_type, const float sel_xy[8], uint32
     return A.applied_ ? 1 : 0;
   } catch (...) { return -1; }
 }
+// AppExpCorrect::calculateConstraintTargets (ApplyExplicitCorrection.cpp:447-487) on explicit inputs: one HumanConstraint per
+// (anchor, corrected) pair, anchor-major.  ids3 = (type, constrained, anchor), deltas4 = (parallel, perpendicular, angle, penalty dir).
+// Buffers hold n_anchor * n_corrected entries; returns that count, or -1 on error.
+int hitl_host_constraint_targets(int correction_type, const float sel_xy[8], uint32_t n_poses, const float* poses_xyt, uint32_t n_corrected, const int32_t* corrected,
+                                 uint32_t n_anchor, const int32_t* anchor, int32_t* ids3, float* deltas4) {
+  try {
+    std::vector<Pose2Df> poses(n_poses);
+    for (uint32_t i = 0; i < n_poses; ++i) poses[i] = Pose2Df(poses_xyt[3 * i + 2], poses_xyt[3 * i], poses_xyt[3 * i + 1]);
+    std::vector<Vector2f> sel;
+    for (int i = 0; i < 4; ++i) sel.push_back(Vector2f(sel_xy[2 * i], sel_xy[2 * i + 1]));
+    for (uint32_t i = 0; i < n_corrected; ++i) if (corrected[i] < 0 || (uint32_t)corrected[i] >= n_poses) return -1;
+    for (uint32_t i = 0; i < n_anchor; ++i) if (anchor[i] < 0 || (uint32_t)anchor[i] >= n_poses) return -1;
+    const std::vector<HumanConstraint> hc = CalculateConstraintTargets(poses, sel, (CorrectionType)correction_type, std::vector<int>(anchor, anchor + n_anchor),
+                                                                       std::vector<int>(corrected, corrected + n_corrected));
+    for (size_t b = 0; b < hc.size(); ++b) {
+      ids3[3 * b] = (int32_t)hc[b].constraint_type; ids3[3 * b + 1] = hc[b].constrained_pose_id; ids3[3 * b + 2] = hc[b].anchor_pose_id;
+      deltas4[4 * b] = hc[b].delta_parallel; deltas4[4 * b + 1] = hc[b].delta_perpendicular; deltas4[4 * b + 2] = hc[b].delta_angle; deltas4[4 * b + 3] = hc[b].relative_penalty_dir;
+    }
+    return (int)hc.size();
+  } catch (...) { return -1; }
+}
 // Backprop::Run on explicit inputs (pose update on the GPU of `ctx`).  poses_xyt, cov9 in/out.
 int hitl_host_backprop(void* ctx, uint32_t n_poses, float* poses_xyt, float* cov9, int32_t lo, int32_t hi, const float C3[3], float* device_ms) {
   try {

@@ -393,3 +393,247 @@ class RefFunctors:
         out = np.zeros(len(pts) // 2, np.float32)
         self.lib.ref_distance_to_line_segment(len(out), self._f32(p0), self._f32(p1), pts, out)
         return out
+
+
+class RefBackend:
+    """The reference's own back-end translation units (oracle/_ref/libhitl_ref.so: JointOptimization.cpp, EMinput.cpp,
+    ApplyExplicitCorrection.cpp, Backprop.cpp, HitLSLAM.cpp, kdtree.cpp compiled where they lie against oracle/shim3,
+    behind oracle/ref_hitl_capi.cpp), when built.  Pins the restated loops to the reference's own code."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref.so"))
+
+    def __init__(self):
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref.so"))
+        vp = C.c_void_p
+        lib.ref_jo_create.restype = vp
+        lib.ref_jo_create.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _f32p]
+        lib.ref_jo_destroy.argtypes = [vp]
+        lib.ref_jo_set_options.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_uint32, C.c_float, C.c_float]
+        lib.ref_min_cos.restype = C.c_float
+        lib.ref_min_cos.argtypes = [C.c_float]
+        lib.ref_jo_set_pose_array.argtypes = [vp, _f64p]
+        lib.ref_jo_get_pose_array.argtypes = [vp, _f64p]
+        lib.ref_jo_set_poses.argtypes = [vp, _f32p]
+        lib.ref_jo_world_clouds.argtypes = [vp, _f32p]
+        lib.ref_jo_relative_pose.argtypes = [vp, C.c_uint32, _u32p, _u32p, _f32p]
+        lib.ref_jo_find_stf.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p]
+        lib.ref_jo_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_void_p]
+        lib.ref_jo_find_vo.restype = C.c_uint64
+        lib.ref_jo_find_vo.argtypes = [vp, C.c_int, C.c_int]
+        lib.ref_jo_get_vo.argtypes = [vp, _u32p, _u32p, _u32p]
+        lib.ref_jo_kd_query.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
+        lib.ref_jo_set_human_constraints.argtypes = [vp, C.c_uint32, _u32p, _i32p, _f32p]
+        lib.ref_jo_eval_blocks.restype = C.c_int64
+        lib.ref_jo_eval_blocks.argtypes = [vp, C.c_int, _f64p, C.c_uint64, C.c_int, C.c_int, _f64p, _f64p, _i32p]
+        lib.ref_jo_run.argtypes = [vp, _f32p, _f64p]
+        lib.ref_em_run.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_int, _i32p, _i32p, _i32p]
+        lib.ref_em_observation_sets.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
+        lib.ref_em_dist_to_line_seg.restype = C.c_double
+        lib.ref_em_dist_to_line_seg.argtypes = [_f32p, _f32p, _f32p]
+        lib.ref_em_seg_fit.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p]
+        lib.ref_app_exp_run.restype = C.c_uint32
+        lib.ref_app_exp_run.argtypes = [C.c_int, _f32p, _f32p, C.c_uint32, _i32p, C.c_uint32, _i32p, C.c_uint32, _f32p, _i32p, _f32p]
+        lib.ref_backprop_run.argtypes = [_f32p, _f32p, C.c_uint32, C.c_int, C.c_int, _f32p]
+        lib.ref_session_create.restype = vp
+        lib.ref_session_create.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _f32p, _f32p]
+        lib.ref_session_destroy.argtypes = [vp]
+        lib.ref_session_replay.restype = C.c_uint32
+        lib.ref_session_replay.argtypes = [vp, C.c_int, _f32p]
+        lib.ref_session_get.argtypes = [vp, _f32p, _f32p, _f32p]
+        lib.ref_session_constraints.restype = C.c_uint32
+        lib.ref_session_constraints.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.ref_session_verify.restype = C.c_size_t
+        lib.ref_session_verify.argtypes = [vp, C.c_int, _f32p]
+
+    @staticmethod
+    def _f32(a):
+        return np.ascontiguousarray(a, np.float32).reshape(-1)
+
+    def min_cos(self, max_angle=None):
+        if max_angle is None:
+            max_angle = np.float32(np.deg2rad(25.0))
+        return float(self.lib.ref_min_cos(float(max_angle)))
+
+    def joint_opt(self, offsets, pts, nrm, poses_f32):
+        return RefJointOpt(self, offsets, pts, nrm, poses_f32)
+
+    def session(self, offsets, pts, nrm, poses_f32, cov9=None):
+        return RefSession(self, offsets, pts, nrm, poses_f32, cov9)
+
+    def em_run(self, offsets, world, segs, ctype=4):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        n = len(offsets) - 1
+        s = self._f32(segs).copy()
+        ret = np.zeros(4, np.int32)
+        cor, anc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.lib.ref_em_run(n, offsets, self._f32(world), s, int(ctype), ret, cor, anc)
+        return dict(segs=s.reshape(4, 2), corrected=cor[:ret[0]].copy(), anchor=anc[:ret[1]].copy(), backprop=(int(ret[2]), int(ret[3])))
+
+    def em_observation_sets(self, offsets, world, segs):
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        n, m = len(offsets) - 1, int(offsets[-1])
+        ns = np.zeros(2, np.uint32)
+        bufs = [(np.zeros(n, np.uint32), np.zeros(n + 1, np.uint64), np.zeros(max(m, 1), np.uint32)) for _ in range(2)]
+        self.lib.ref_em_observation_sets(n, offsets, self._f32(world), self._f32(segs), ns, bufs[0][0], bufs[0][1], bufs[0][2], bufs[1][0], bufs[1][1], bufs[1][2])
+        out = []
+        for f in range(2):
+            k = int(ns[f])
+            off = bufs[f][1][:k + 1].copy()
+            out.append((bufs[f][0][:k].copy(), off, bufs[f][2][:int(off[-1])].copy()))
+        return out
+
+    def dist_to_line_seg(self, p1, p2, p):
+        return float(self.lib.ref_em_dist_to_line_seg(self._f32(p1), self._f32(p2), self._f32(p)))
+
+    def seg_fit(self, p1, p2, data):
+        out = np.zeros(4, np.float32)
+        data = np.ascontiguousarray(data, np.float64).reshape(-1)
+        self.lib.ref_em_seg_fit(np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64), data, len(data) // 2, out)
+        return out.reshape(2, 2)
+
+    def app_exp_run(self, ctype, sel, poses_f32, corrected, anchor):
+        """AppExpCorrect::Run: (poses [N,3] f32, C [3] f32, hc_i [B,3] i32, hc_f [B,4] f32)."""
+        p = self._f32(poses_f32).copy()
+        cor, anc = np.ascontiguousarray(corrected, np.int32), np.ascontiguousarray(anchor, np.int32)
+        nb = max(len(cor) * len(anc), 1)
+        c3, hi, hf = np.zeros(3, np.float32), np.zeros(3 * nb, np.int32), np.zeros(4 * nb, np.float32)
+        n = self.lib.ref_app_exp_run(int(ctype), self._f32(sel), p, len(p) // 3, cor, len(cor), anc, len(anc), c3, hi, hf)
+        return p.reshape(-1, 3), c3, hi[:3 * n].reshape(-1, 3).copy(), hf[:4 * n].reshape(-1, 4).copy()
+
+    def backprop(self, poses_f32, cov9, lo, hi, c3):
+        p, cov = self._f32(poses_f32).copy(), self._f32(cov9).copy()
+        self.lib.ref_backprop_run(p, cov, len(p) // 3, int(lo), int(hi), self._f32(c3))
+        return p.reshape(-1, 3), cov.reshape(-1, 9)
+
+
+class RefJointOpt:
+    """The reference's JointOpt over one map (trees built by its own BuildKDTrees)."""
+
+    def __init__(self, ref, offsets, pts, nrm, poses_f32):
+        self.ref, self.lib = ref, ref.lib
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        self.n, self.m = len(self.offsets) - 1, int(self.offsets[-1])
+        self.h = self.lib.ref_jo_create(self.n, self.offsets, ref._f32(pts), ref._f32(nrm), ref._f32(poses_f32))
+        self.set_options()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_jo_destroy(self.h)
+            self.h = None
+
+    def set_options(self, thr=0.15, max_angle=None, cap=6, skip=1, laser_std=0.05, corr=1.0 / 40.0):
+        if max_angle is None:
+            max_angle = np.float32(np.deg2rad(25.0))
+        self.lib.ref_jo_set_options(self.h, thr, float(max_angle), cap, skip, laser_std, corr)
+
+    def set_pose_array(self, poses_f64):
+        self.lib.ref_jo_set_pose_array(self.h, np.ascontiguousarray(poses_f64, np.float64).reshape(-1))
+
+    def pose_array(self):
+        out = np.zeros(3 * self.n)
+        self.lib.ref_jo_get_pose_array(self.h, out)
+        return out.reshape(-1, 3)
+
+    def set_poses(self, poses_f32):
+        self.lib.ref_jo_set_poses(self.h, self.ref._f32(poses_f32))
+
+    def world_clouds(self):
+        out = np.zeros(2 * self.m, np.float32)
+        self.lib.ref_jo_world_clouds(self.h, out)
+        return out.reshape(-1, 2)
+
+    def relative_pose(self, src, dst):
+        src, dst = np.ascontiguousarray(src, np.uint32), np.ascontiguousarray(dst, np.uint32)
+        out = np.zeros(6 * len(src), np.float32)
+        self.lib.ref_jo_relative_pose(self.h, len(src), src, dst, out)
+        return out.reshape(-1, 6)
+
+    def find_stf(self, poses_f64=None, min_pose=0, max_pose=None, with_points=False):
+        if poses_f64 is not None:
+            self.set_pose_array(poses_f64)
+        if max_pose is None:
+            max_pose = self.n - 1
+        counts = np.zeros(2, np.uint64)
+        self.lib.ref_jo_find_stf(self.h, int(min_pose), int(max_pose), counts)
+        npairs, nm = int(counts[0]), int(counts[1])
+        pi, pj = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32)
+        off = np.zeros(npairs + 1, np.uint64)
+        k, idx = np.zeros(nm, np.uint32), np.zeros(nm, np.uint32)
+        xy = np.zeros(8 * nm, np.float32) if with_points else None
+        self.lib.ref_jo_get_stf(self.h, pi, pj, off, k, idx, xy.ctypes.data if with_points else None)
+        out = dict(pair_i=pi, pair_j=pj, pair_off=off, k=k, idx=idx)
+        if with_points:
+            out["xy8"] = xy.reshape(-1, 4, 2)
+        return out
+
+    def find_vo(self, poses_f64=None, min_pose=0, max_pose=None):
+        if poses_f64 is not None:
+            self.set_pose_array(poses_f64)
+        if max_pose is None:
+            max_pose = self.n - 1
+        n = int(self.lib.ref_jo_find_vo(self.h, int(min_pose), int(max_pose)))
+        sp, sk, tk = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.lib.ref_jo_get_vo(self.h, sp, sk, tk)
+        return sp, sk, tk
+
+    def kd_query(self, scan, q, thr, mode=0):
+        q = self.ref._f32(q)
+        n = len(q) // 2
+        d, i = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.ref_jo_kd_query(self.h, int(scan), n, q, thr, mode, d, i)
+        return d, i
+
+    def set_human_constraints(self, groups):
+        """groups: list of (hc_i [B,3] int32, hc_f [B,4] float32)."""
+        off = np.concatenate([[0], np.cumsum([len(g[0]) for g in groups])]).astype(np.uint32)
+        hi = np.concatenate([np.asarray(g[0], np.int32).reshape(-1, 3) for g in groups] or [np.zeros((0, 3), np.int32)])
+        hf = np.concatenate([np.asarray(g[1], np.float32).reshape(-1, 4) for g in groups] or [np.zeros((0, 4), np.float32)])
+        self.lib.ref_jo_set_human_constraints(self.h, len(groups), off, np.ascontiguousarray(hi).reshape(-1), np.ascontiguousarray(hf).reshape(-1))
+
+    def eval_blocks(self, which, poses_f64, cap):
+        """which: 0 odometry (r 3, J [2,3,3]), 1 human (r <= 3, J [nr,3]), 2 STF of the last find_stf (r 2, J [2,2,3])."""
+        rs, js = {0: (3, 18), 1: (3, 9), 2: (2, 12)}[which]
+        r, J, nr = np.zeros(rs * cap), np.zeros(js * cap), np.zeros(cap, np.int32)
+        n = int(self.lib.ref_jo_eval_blocks(self.h, which, np.ascontiguousarray(poses_f64, np.float64).reshape(-1), cap, rs, js, r, J, nr))
+        assert n >= 0, "eval_blocks: capacity too small"
+        return r[:rs * n].reshape(n, rs), J[:js * n].reshape(n, js), nr[:n]
+
+    def run(self):
+        p, pa = np.zeros(3 * self.n, np.float32), np.zeros(3 * self.n)
+        self.lib.ref_jo_run(self.h, p, pa)
+        return p.reshape(-1, 3), pa.reshape(-1, 3)
+
+
+class RefSession:
+    """The reference's HitLSLAM (init + replayLog): the whole correction chain on its own code."""
+
+    def __init__(self, ref, offsets, pts, nrm, poses_f32, cov9=None):
+        self.ref, self.lib = ref, ref.lib
+        self.offsets = np.ascontiguousarray(offsets, np.uint32)
+        self.n, self.m = len(self.offsets) - 1, int(self.offsets[-1])
+        cov = np.zeros(9 * self.n, np.float32) if cov9 is None else ref._f32(cov9)
+        self.h = self.lib.ref_session_create(self.n, self.offsets, ref._f32(pts), ref._f32(nrm), ref._f32(poses_f32), cov)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_session_destroy(self.h)
+            self.h = None
+
+    def verify(self, ctype, sel):
+        return int(self.lib.ref_session_verify(self.h, int(ctype), self.ref._f32(sel)))
+
+    def replay(self, ctype, sel):
+        return int(self.lib.ref_session_replay(self.h, int(ctype), self.ref._f32(sel)))
+
+    def state(self):
+        p, cov, w = np.zeros(3 * self.n, np.float32), np.zeros(9 * self.n, np.float32), np.zeros(2 * self.m, np.float32)
+        self.lib.ref_session_get(self.h, p, cov, w)
+        return p.reshape(-1, 3), cov.reshape(-1, 9), w.reshape(-1, 2)
+
+    def constraints(self, g):
+        n = int(self.lib.ref_session_constraints(self.h, g, None, None))
+        hi, hf = np.zeros(3 * max(n, 1), np.int32), np.zeros(4 * max(n, 1), np.float32)
+        self.lib.ref_session_constraints(self.h, g, hi.ctypes.data, hf.ctypes.data)
+        return hi[:3 * n].reshape(-1, 3), hf[:4 * n].reshape(-1, 4)

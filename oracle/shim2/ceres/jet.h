@@ -36,6 +36,12 @@ HITL_JET bool operator<=(const Jet<T, N>& f, const Jet<T, N>& g) { return f.a <=
 HITL_JET bool operator>=(const Jet<T, N>& f, const Jet<T, N>& g) { return f.a >= g.a; }
 HITL_JET bool operator==(const Jet<T, N>& f, const Jet<T, N>& g) { return f.a == g.a; }
 HITL_JET bool operator!=(const Jet<T, N>& f, const Jet<T, N>& g) { return f.a != g.a; }
+HITL_JET bool operator<(const Jet<T, N>& f, T s) { return f.a < s; }
+HITL_JET bool operator>(const Jet<T, N>& f, T s) { return f.a > s; }
+HITL_JET bool operator<=(const Jet<T, N>& f, T s) { return f.a <= s; }
+HITL_JET bool operator>=(const Jet<T, N>& f, T s) { return f.a >= s; }
+HITL_JET bool operator<(T s, const Jet<T, N>& f) { return s < f.a; }
+HITL_JET bool operator>(T s, const Jet<T, N>& f) { return s > f.a; }
 HITL_JET Jet<T, N> sqrt(const Jet<T, N>& f) { Jet<T, N> h; h.a = std::sqrt(f.a); const T t = T(1.0) / (T(2.0) * h.a); for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * t; return h; }
 HITL_JET Jet<T, N> sin(const Jet<T, N>& f) { Jet<T, N> h; h.a = std::sin(f.a); const T c = std::cos(f.a); for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i]; return h; }
 HITL_JET Jet<T, N> cos(const Jet<T, N>& f) { Jet<T, N> h; h.a = std::cos(f.a); const T s = -std::sin(f.a); for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i]; return h; }

@@ -1,0 +1,348 @@
+"""Pins the oracle restatement (and the host mirror's O(#poses) stages) to the REFERENCE's own back-end code:
+JointOptimization.cpp, EMinput.cpp, ApplyExplicitCorrection.cpp, Backprop.cpp, HitLSLAM.cpp and kdtree.cpp compiled
+where they lie against the stand-in headers of oracle/shim3 (oracle/_ref/libhitl_ref.so, built by oracle/Makefile when
+/root/reference is present; the prebuilt library travels to the GPU box).  Integer / index / float32 outputs are compared
+bit for bit; double residuals and Jacobians at 1e-12 (same Jet arithmetic, accumulation order inside a block may differ);
+anything that passes through a Levenberg-Marquardt solve at the tolerance written in the test (two LM implementations)."""
+import numpy as np
+import pytest
+
+from conftest import assert_same_stf, random_scans
+from oracle.pyoracle import RefBackend, default_min_cos
+
+pytestmark = pytest.mark.skipif(not RefBackend.available(), reason="oracle/_ref/libhitl_ref.so not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefBackend()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def close(a, b, tol=1e-12):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return b.size == 0
+    return np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0)
+
+
+DRIFTY = dict(drift_xy=0.012, drift_th=0.004)   # enough odometry drift for a visible loop-closure error on the small maps
+
+
+def jittered(g, seed, s_xy=0.02, s_th=0.01):
+    rng = np.random.default_rng(seed)
+    return g["poses"].astype(np.float64) + rng.normal(size=g["poses"].shape) * [s_xy, s_xy, s_th]
+
+
+# ---- a6 / a7 / a8: the search loops ---------------------------------------------------------------------------------
+def test_cosine_gate_constant(ref):
+    # cos(kMaxStfAngleError) as JointOptimization.cpp:564 forms it == the float the oracle / C ABI are given
+    assert ref.min_cos() == default_min_cos()
+
+
+@pytest.mark.parametrize("name,normals", [("tiny", "compensated"), ("tiny", "faithful"), ("small", "compensated")])
+def test_find_stf_is_the_references_own_loop(oracle, ref, maps, name, normals):
+    g = maps(name, normals=normals)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    for poses in (g["poses"].astype(np.float64), jittered(g, 1)):
+        want = J.find_stf(poses, with_points=True)
+        got = S.find_stf(poses)
+        assert len(want["k"]) > 1000
+        assert_same_stf(got, want)
+        # the point / normal copies every reference correspondence carries are the scan entries the indices name
+        off = g["offsets"].astype(np.int64)
+        bi = np.repeat(want["pair_i"].astype(np.int64), np.diff(want["pair_off"].astype(np.int64)))
+        bj = np.repeat(want["pair_j"].astype(np.int64), np.diff(want["pair_off"].astype(np.int64)))
+        xy = want["xy8"]
+        assert np.array_equal(xy[:, 0], g["pts"][off[bi] + want["k"]]) and np.array_equal(xy[:, 1], g["pts"][off[bj] + want["idx"]])
+        assert np.array_equal(xy[:, 2], g["nrm"][off[bi] + want["k"]]) and np.array_equal(xy[:, 3], g["nrm"][off[bj] + want["idx"]])
+
+
+@pytest.mark.parametrize("opts", [dict(cap=1), dict(cap=3, skip=2), dict(skip=5), dict(thr=0.05), dict(thr=0.4, cap=2), dict(max_angle=np.float32(0.1))])
+def test_find_stf_options(oracle, ref, maps, opts):
+    g = maps("tiny")
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    J.set_options(**opts)
+    poses = jittered(g, 2)
+    kw = {k: v for k, v in opts.items() if k in ("cap", "skip", "thr")}
+    if "max_angle" in opts:
+        kw["min_cos"] = ref.min_cos(opts["max_angle"])
+    assert_same_stf(S.find_stf(poses, **kw), J.find_stf(poses))
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 39), (5, 20), (10, 10), (12, 13), (0, 1000), (30, 39)])
+def test_find_stf_pose_ranges(oracle, ref, maps, lo, hi):
+    g = maps("tiny")
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    poses = g["poses"].astype(np.float64)
+    assert_same_stf(S.find_stf(poses, min_pose=lo, max_pose=hi), J.find_stf(poses, min_pose=lo, max_pose=hi))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_find_stf_random_ragged_scans_with_ties(oracle, ref, seed):
+    # random clouds (duplicated coordinates -> tie cases of the tree build, 1-point scans), overlapping poses.  No EMPTY scans here:
+    # the reference queries a default-constructed KDTree for them (JointOptimization.cpp:533-535), which reads uninitialised members;
+    # the oracle / CUDA path define that case as "no match" (tests/test_gpu_parity.py covers it against the oracle).
+    rng = np.random.default_rng(seed)
+    off, pts, nrm = random_scans(rng, 14, 1, 90)
+    poses32 = (rng.normal(size=(14, 3)) * [0.05, 0.05, 0.05]).astype(np.float32)
+    poses = poses32.astype(np.float64) + rng.normal(size=(14, 3)) * 1e-3
+    S = oracle.scans(off, pts, nrm)
+    J = ref.joint_opt(off, pts, nrm, poses32)
+    J.set_options(thr=0.3, cap=4)
+    got, want = S.find_stf(poses, thr=0.3, cap=4), J.find_stf(poses)
+    assert_same_stf(got, want)
+    J.set_options(thr=0.3, cap=64, max_angle=np.float32(3.0))
+    assert_same_stf(S.find_stf(poses, thr=0.3, cap=64, min_cos=ref.min_cos(np.float32(3.0))), J.find_stf(poses))
+
+
+def test_find_vo_is_the_references_own_loop(oracle, ref, maps):
+    g = maps("small")
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    for poses, lo, hi in ((g["poses"].astype(np.float64), 0, None), (jittered(g, 3), 0, None), (jittered(g, 4), 17, 90), (jittered(g, 4), 5, 5), (jittered(g, 4), 100, 5000)):
+        a, b = S.find_vo(poses, min_pose=lo, max_pose=hi), J.find_vo(poses, min_pose=lo, max_pose=hi)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert len(b[0]) > 0
+
+
+def test_relative_pose_transform_bits(ref, host, maps):
+    g = maps("small")
+    rng = np.random.default_rng(5)
+    poses = jittered(g, 5)
+    poses[3, 2] = 3.14159; poses[4, 2] = -3.14159; poses[5, 2] = 100.25; poses[6] = [1e3, -2e3, -7.5]
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    J.set_pose_array(poses)
+    src, dst = rng.integers(0, len(poses), 1500).astype(np.uint32), rng.integers(0, len(poses), 1500).astype(np.uint32)
+    src[:8], dst[:8] = [3, 4, 5, 6, 3, 5, 6, 0], [4, 3, 6, 5, 0, 3, 4, 6]
+    want = J.relative_pose(src, dst)
+    flat = poses.reshape(-1)
+    got = np.stack([host.relative_pose(flat, int(a), int(b)) for a, b in zip(src, dst)])
+    assert same_bits(got, want)
+
+
+def test_trees_answer_like_the_references(oracle, ref):
+    rng = np.random.default_rng(6)
+    off, pts, nrm = random_scans(rng, 6, 1, 300)
+    S = oracle.scans(off, pts, nrm)
+    J = ref.joint_opt(off, pts, nrm, np.zeros((6, 3), np.float32))
+    for scan in range(6):
+        q = (rng.normal(size=(500, 2)) * 2.0).astype(np.float32)
+        q[::3] = pts[off[scan]:off[scan + 1]][rng.integers(0, off[scan + 1] - off[scan], len(q[::3]))]    # exact hits (distance 0 -> early exit)
+        for mode in (0, 1):
+            for thr in (0.05, 0.5, 10.0):
+                d0, i0 = S.query(scan, q, thr, mode)
+                d1, i1 = J.kd_query(scan, q, thr, mode)
+                assert np.array_equal(i0, i1) and same_bits(d0, d1), (scan, mode, thr)
+
+
+# ---- f1: world-frame clouds -----------------------------------------------------------------------------------------
+def test_world_clouds_bits(oracle, ref, maps):
+    g = maps("small")
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    poses = g["poses"].copy()
+    poses[:, 2] += np.float32(0.37)
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], poses)
+    want = J.world_clouds()                                   # JointOpt::CopyTempLaserScans
+    assert same_bits(S.world_transform(poses), want)
+    sess = ref.session(g["offsets"], g["pts"], g["nrm"], poses)
+    assert same_bits(sess.state()[2], want)                   # HitLSLAM::transformPointCloudsToWorldFrame gives the same bits
+
+
+# ---- a15 - a19: the residual blocks the reference's Add*Constraints build -------------------------------------------
+def test_odometry_blocks_built_by_the_reference(oracle, ref, maps):
+    g = maps("small")
+    poses32 = g["poses"].copy()
+    poses32[7] = poses32[6]; poses32[7, 2] += np.float32(0.3)            # a pair that did not move: the heading-axes branch
+    poses32[20, 2] = np.float32(3.1); poses32[21, 2] = np.float32(-3.1)   # wrap-around of the measured rotation
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], poses32)
+    x = poses32.astype(np.float64) + np.random.default_rng(7).normal(size=poses32.shape) * 0.02
+    r1, J1, nr = J.eval_blocks(0, x, len(x))
+    r0, J0 = oracle.eval_odometry(oracle.odometry_consts(poses32), x)
+    assert len(r1) == len(x) - 1 and np.all(nr == 3)
+    assert close(r0, r1) and close(J0.reshape(len(r0), -1), J1)
+
+
+def test_human_blocks_built_by_the_reference(oracle, ref, maps):
+    g = maps("small")
+    n = len(g["poses"])
+    rng = np.random.default_rng(8)
+    m = 96
+    ids = np.stack([rng.choice([2, 4, 5, 6], m), rng.integers(0, n, m), rng.integers(0, n, m)], 1).astype(np.int32)
+    deltas = (rng.normal(size=(m, 4)) * 2).astype(np.float32)
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    J.set_human_constraints([(ids[:40], deltas[:40]), (ids[40:], deltas[40:])])
+    x = jittered(g, 9)
+    r1, J1, nr = J.eval_blocks(1, x, m)
+    blk_i, blk_d = oracle.human_blocks(g["poses"], ids, deltas)
+    r0, J0 = oracle.eval_human(blk_i, blk_d, x)
+    assert len(r1) == m
+    assert np.array_equal(nr, np.array([{2: 3, 4: 2, 5: 1, 6: 1}[t] for t in ids[:, 0]]))
+    for b in range(m):
+        k = nr[b]
+        assert close(r0[b, :k], r1[b, :k]) and close(J0[b, :k].reshape(-1), J1[b, :3 * k]), b
+
+
+def test_stf_blocks_built_by_the_reference(oracle, ref, maps):
+    g = maps("tiny")
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    poses = g["poses"].astype(np.float64)
+    corr = J.find_stf(poses)
+    x = jittered(g, 10)
+    r1, J1, nr = J.eval_blocks(2, x, len(corr["pair_i"]))     # AddSTFConstraints over point_point_glob_correspondences_
+    r0, J0 = S.eval_stf(x, corr)
+    assert len(r1) == len(corr["pair_i"]) and np.all(nr == 2)
+    assert close(r0, r1) and close(J0.reshape(len(r0), -1), J1)
+
+
+# ---- a9 - a14: EM ---------------------------------------------------------------------------------------------------
+def test_dist_to_line_seg_bits(oracle, ref):
+    rng = np.random.default_rng(11)
+    p1, p2, p = rng.normal(size=(3, 3000, 2)).astype(np.float32)
+    p2[:50] = p1[:50]                                         # zero-length stroke: 0/0 -> NaN compares false twice -> projection branch
+    p[50:100] = p1[50:100]
+    for k in list(range(100)) + list(range(100, 3000, 7)):
+        seg = np.array([p1[k], p2[k]], np.float32).reshape(-1)
+        want = ref.dist_to_line_seg(p1[k], p2[k], p[k])
+        got = oracle.lib.orc_dist_to_line_seg(seg, float(p[k, 0]), float(p[k, 1]))
+        assert (np.isnan(want) and np.isnan(got)) or want == got, k
+
+
+def test_observation_sets_are_the_references(oracle, ref, maps):
+    from hitl_slam_b200 import synth
+    g = maps("small", **DRIFTY)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    w = S.world_transform(g["poses"])
+    segs = synth.pick_strokes(g, min_sep=0.045)
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        s = segs + (rng.normal(size=segs.shape) * 0.01 * trial).astype(np.float32)
+        a, b = oracle.em_assign(g["offsets"], w, s), ref.em_observation_sets(g["offsets"], w, s)
+        for f in range(2):
+            assert all(np.array_equal(x, y) for x, y in zip(a[f], b[f])), (trial, f)
+        assert len(b[0][0]) > 0 and len(b[1][0]) > 0
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_em_run_is_the_references(oracle, ref, maps, name):
+    from hitl_slam_b200 import synth
+    g = maps(name, **DRIFTY)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    w = S.world_transform(g["poses"])
+    segs = synth.pick_strokes(g, min_sep=0.045)
+    for s in (segs, segs[[2, 3, 0, 1]]):                      # drawn late-visit first ("user was good") and the other way round (swapped by the reference)
+        a, b = oracle.em_run(g["offsets"], w, s), ref.em_run(g["offsets"], w, s)
+        assert np.abs(a["segs"] - b["segs"]).max() <= 1e-5    # endpoints pass through SegFitEM: two LM implementations
+        assert np.array_equal(a["corrected"], b["corrected"]) and np.array_equal(a["anchor"], b["anchor"])
+        assert a["backprop"] == b["backprop"] and b["backprop"][0] >= 0
+        assert len(b["corrected"]) > 0 and len(b["anchor"]) > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_seg_fit_em_is_the_references(oracle, ref, host, seed):
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0.02, 1.5)
+    n = int(rng.integers(8, 400))
+    t = rng.uniform(-0.2, 2.2, n)
+    data = np.stack([1 + t * np.cos(ang), 2 + t * np.sin(ang)], 1) + rng.normal(size=(n, 2)) * 0.01
+    p1 = np.array([1.0, 2.0]) + rng.normal(size=2) * 0.03
+    p2 = np.array([1 + 2 * np.cos(ang), 2 + 2 * np.sin(ang)]) + rng.normal(size=2) * 0.03
+    want = ref.seg_fit(p1, p2, data)                          # reference SegFitEM over the stand-in LM
+    assert np.abs(oracle.seg_fit(p1, p2, data) - want).max() <= 1e-5
+    assert np.abs(host.seg_fit_em(p1, p2, data) - want).max() <= 1e-5
+
+
+# ---- f3: explicit correction, constraint targets, back-propagation --------------------------------------------------
+@pytest.mark.parametrize("ctype", [2, 4, 5, 6])
+def test_explicit_correction_is_the_references(oracle, ref, host, ctype):
+    rng = np.random.default_rng(200 + ctype)
+    for trial in range(20):
+        n = int(rng.integers(8, 120))
+        poses = np.cumsum(rng.normal(size=(n, 3)) * [0.3, 0.3, 0.05], 0).astype(np.float32)
+        a0 = rng.normal(size=2) * 5
+        b0 = a0 + rng.normal(size=2) * 0.4
+        da, db = rng.normal(size=2), rng.normal(size=2)
+        if trial % 5 == 0:
+            db = np.array([-da[1], da[0]])
+        sel = np.array([a0, a0 + da, b0, b0 + db], np.float32)
+        k = int(rng.integers(1, max(2, n // 3)))
+        corrected = np.sort(rng.choice(np.arange(n // 2, n), min(k, n - n // 2), replace=False)).astype(np.int32)
+        if trial % 3 == 0:
+            corrected = (np.arange(n // 2, n // 2 + len(corrected))).astype(np.int32)
+        anchor = np.sort(rng.choice(np.arange(0, n // 2), int(rng.integers(1, max(2, n // 4))), replace=False)).astype(np.int32)
+        want_p, want_c, hc_i, hc_f = ref.app_exp_run(ctype, sel, poses, corrected, anchor)
+        got_p, got_c = oracle.app_exp_corrections(ctype, sel, poses, corrected)
+        assert same_bits(got_p, want_p) and same_bits(got_c, want_c), (ctype, trial)
+        hp, hcorr = host.app_exp_correct(ctype, sel, poses, corrected)
+        assert same_bits(hp, want_p) and same_bits(hcorr, want_c)
+        # calculateConstraintTargets: |anchor| x |corrected| constraints, anchor-major, deltas frozen from the CORRECTED poses
+        assert len(hc_i) == len(anchor) * len(corrected)
+        assert np.array_equal(hc_i[:, 0], np.full(len(hc_i), ctype)) and np.array_equal(hc_i[:, 2], np.repeat(anchor, len(corrected)))
+        assert np.array_equal(hc_i[:, 1], np.tile(corrected, len(anchor)))
+        ti, tf = host.constraint_targets(ctype, sel, want_p, corrected, anchor)
+        assert np.array_equal(ti, hc_i) and same_bits(tf, hc_f), (ctype, trial)
+
+
+def test_back_propagation_is_the_references(oracle, ref):
+    rng = np.random.default_rng(13)
+    for trial in range(12):
+        n = int(rng.integers(6, 400))
+        poses = np.cumsum(rng.normal(size=(n, 3)) * [0.3, 0.3, 0.05], 0).astype(np.float32)
+        cov = np.abs(rng.normal(size=(n, 9)) * 1e-3).astype(np.float32) + np.float32(1e-5)
+        lo = int(rng.integers(0, n - 3))
+        hi = int(rng.integers(lo + 2, n))
+        c3 = (rng.normal(size=3) * [0.3, 0.3, 0.1]).astype(np.float32)
+        want_p, want_c = ref.backprop(poses, cov, lo, hi, c3)
+        got_p, got_c = oracle.backprop(poses, cov, lo, hi, c3)
+        assert same_bits(got_p, want_p) and same_bits(got_c, want_c), trial
+
+
+# ---- a20 + the chain: one whole correction on the reference's HitLSLAM::replayLog ------------------------------------
+def test_whole_correction_chain_against_hitlslam(oracle, ref, host, maps):
+    """HitLSLAM::replayLog (verify -> EMInput -> AppExpCorrect -> Backprop -> angle wrap -> JointOpt::Run) on the reference's own
+    code vs the same chain composed from the oracle's restated stages.  Everything up to the solve is bit-exact except the
+    stroke endpoints that pass through SegFitEM (1e-5); the solved poses are compared at 1e-4 (different LM code, float poses)."""
+    from hitl_slam_b200 import synth
+    g = maps("small", **DRIFTY)
+    segs = synth.pick_strokes(g, min_sep=0.045)
+    cov = np.tile(np.array([1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-5], np.float32), (len(g["poses"]), 1))
+    sess = ref.session(g["offsets"], g["pts"], g["nrm"], g["poses"], cov)
+    assert sess.verify(4, segs) == 4
+    assert sess.replay(4, segs) == 1                           # one group of human constraints was added: the correction was applied
+    p_ref, cov_ref, w_ref = sess.state()
+    hc_i, hc_f = sess.constraints(0)
+
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    em = oracle.em_run(g["offsets"], S.world_transform(g["poses"]), segs)
+    em_ref = ref.em_run(g["offsets"], S.world_transform(g["poses"]), segs)
+    assert np.array_equal(em["corrected"], em_ref["corrected"]) and np.array_equal(em["anchor"], em_ref["anchor"]) and em["backprop"] == em_ref["backprop"]
+    # from here on feed both sides the reference's refit endpoints, so that the remaining stages can be compared bit for bit
+    p1, c3 = oracle.app_exp_corrections(4, em_ref["segs"], g["poses"], em["corrected"])
+    ti, tf = host.constraint_targets(4, em_ref["segs"], p1, em["corrected"], em["anchor"])
+    assert np.array_equal(ti, hc_i) and same_bits(tf, hc_f)
+    p2, cov2 = oracle.backprop(p1, cov, em["backprop"][0], em["backprop"][1], c3)
+    assert same_bits(cov2, cov_ref)
+    p2[:, 2] = np.arctan2(np.sin(p2[:, 2].astype(np.float64)), np.cos(p2[:, 2].astype(np.float64))).astype(np.float32)
+    # JointOpt::Run on those poses: the reference's own problem building + the stand-in LM, against scipy on the oracle's blocks
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], p2)
+    J.set_human_constraints([(hc_i, hc_f)])
+    p_solved, _ = J.run()
+    assert np.abs(p_solved - p_ref).max() <= 1e-4             # the session's final poses are this solve's
+    assert same_bits(S.world_transform(p_ref), w_ref)          # and its world clouds are their transform
+    # the solve moved the corrected poses onto the human constraints: cost of the human blocks at the solution is tiny
+    blk_i, blk_d = oracle.human_blocks(p2, hc_i, hc_f)
+    r_before, _ = oracle.eval_human(blk_i, blk_d, p2.astype(np.float64), want_jac=False)
+    r_after, _ = oracle.eval_human(blk_i, blk_d, p_ref.astype(np.float64), want_jac=False)
+    assert np.abs(r_after).max() <= max(np.abs(r_before).max(), 1e-3)
