@@ -401,11 +401,12 @@ class RefBackend:
     behind oracle/ref_hitl_capi.cpp), when built.  Pins the restated loops to the reference's own code."""
 
     @staticmethod
-    def available():
-        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref.so"))
+    def available(fast=False):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref_fast.so" if fast else "libhitl_ref.so"))
 
-    def __init__(self):
-        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref.so"))
+    def __init__(self, fast=False):
+        """fast=True loads the timing build (the reference's Release flags) instead of the parity build (-O2 -ffp-contract=off)."""
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref_fast.so" if fast else "libhitl_ref.so"))
         vp = C.c_void_p
         lib.ref_jo_create.restype = vp
         lib.ref_jo_create.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _f32p]
