@@ -44,34 +44,67 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons of this rank's GPU during the timed region.  In-process NVML (the library nvidia-smi reads; one
+    cheap query per sample, no child process per rank — eight nvidia-smi start-ups inside an 8-rank timed region perturb the launches
+    they are meant to observe); falls back to `nvidia-smi --query-gpu ... -lms` when the NVML binding is unavailable.  Started before
+    the warm-up; only samples taken between mark_begin() and stop() are reported."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.010):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.period = index, [], None, period_s
+        self.t_begin, self.halt, self.source = None, threading.Event(), None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.source = "nvml"
+            while not self.halt.is_set():
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.perf_counter(), sm, mx, [k for k, b in bits.items() if r & b]))
+                self.halt.wait(self.period)
+            return
+        except Exception:
+            pass
+        try:
+            self.source = "nvidia-smi"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                r = [x.strip() for x in line.split(",")]
+                if len(r) >= 8 and r[1].replace(".", "").isdigit() and r[2].replace(".", "").isdigit():
+                    self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                      [k for k, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]) if v.lower().startswith("active")]))
         except Exception:
             pass
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
     def stop(self):
+        t_end = time.perf_counter()
+        self.halt.set()
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [r for r in self.rows if self.t_begin is None or self.t_begin <= r[0] <= t_end] or self.rows[-1:]
+        sm = [r[1] for r in rows]
+        mx = [r[2] for r in rows]
+        reasons = set(k for r in rows for k in r[3])
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def workload(name, n_poses=None, beams=None):
@@ -310,6 +343,8 @@ def main():
             if os.environ.get("HITL_BENCH_DEBUG"):
                 sys.stderr.write("[rank %d] balance %d: [%d, %d) ms_search %.3f ms_total %.3f tiles %d -> %d\n" % (rank, p, lo, hi, info_b["ms_search"], info_b["ms_total"], info_b["n_tiles"], info_b["n_tiles_next"]))
             lo, hi = shard_ranges_by_work(est, world)[rank]
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                # before the warm-up: NVML start-up is not inside the timed region
     for w in range(args.warmup):
         info_w, _ = step()
         if os.environ.get("HITL_BENCH_DEBUG"):
@@ -317,9 +352,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    sampler.mark_begin()
     launches0 = gpu.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

@@ -969,8 +969,9 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
   }
 }
 
-// Exclusive scan over the per-pose (matches, pairs) counts; totals to counters[3], [4]. Single CTA.
-__global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, unsigned long long* counters) {
+// Exclusive scan over the per-pose (matches, pairs) counts; totals to counters[3], [4] and the terminating CSR offset
+// pair_off[n_pairs] = n_matches. Single CTA.
+__global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, unsigned long long* counters, unsigned long long* pair_off) {
   __shared__ unsigned long long sm_m[32], sm_p[32];
   __shared__ unsigned long long carry_m, carry_p;
   if (threadIdx.x == 0) { carry_m = 0; carry_p = 0; }
@@ -1001,7 +1002,7 @@ __global__ void pose_cnt_scan_kernel(unsigned long long* pose_cnt, uint32_t n, u
     if (threadIdx.x == 0) { carry_m += sm_m[nw - 1]; carry_p += sm_p[nw - 1]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { counters[3] = carry_p; counters[4] = carry_m; }
+  if (threadIdx.x == 0) { counters[3] = carry_p; counters[4] = carry_m; pair_off[carry_p] = carry_m; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1268,7 +1269,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   stf_order_kernel<0><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<0>");
   HITL_CUDA(cudaEventRecord(ctx->evx[2], ctx->stream));   // after order<0>
-  pose_cnt_scan_kernel<<<1, 1024, 0, ctx->stream>>>((unsigned long long*)ctx->d_pose_cnt.p, hi - lo, (unsigned long long*)ctx->d_counters.p);
+  pose_cnt_scan_kernel<<<1, 1024, 0, ctx->stream>>>((unsigned long long*)ctx->d_pose_cnt.p, hi - lo, (unsigned long long*)ctx->d_counters.p, (unsigned long long*)ctx->d_pair_off.p);
   HITL_LAUNCH_CHECK("pose_cnt_scan_kernel");
   HITL_CUDA(cudaEventRecord(ctx->evx[3], ctx->stream));   // after the scan
   stf_order_kernel<1><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
@@ -1280,9 +1281,6 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5]; inf.n_coarse_pass = ctx->h_pinned[9]; inf.n_in_radius = ctx->h_pinned[10];
   inf.sum_tile_cycles = ctx->h_pinned[7] << 6; inf.max_tile_cycles = ctx->h_pinned[8] << 6;
   const uint64_t work_sum = ctx->h_pinned[7];
-  // terminating offset of the CSR
-  HITL_CUDA(cudaMemcpyAsync((unsigned long long*)ctx->d_pair_off.p + inf.n_pairs, &ctx->h_pinned[4], sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_search, ctx->ev[1], ctx->ev[2]));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_total, ctx->ev[0], ctx->ev[3]));
   if (getenv("HITL_STF_TIMING")) {
