@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "hitl_host_alloc", "hitl_host_free",
     "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_kd_query",
     "hitl_find_stf", "hitl_get_stf", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
-    "hitl_world_transform", "hitl_set_world_clouds", "hitl_em_inliers", "hitl_em_assign",
+    "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
     "hitl_normal_eq_device", "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
@@ -105,6 +105,7 @@ class HitlGpu:
         lib.hitl_set_world_clouds.argtypes = [vp, _f32p]
         lib.hitl_em_inliers.argtypes = [vp, _f32p, C.c_double, C.c_uint64, vp, vp, vp, C.POINTER(C.c_uint64)]
         lib.hitl_em_assign.argtypes = [vp, _f32p, C.c_double, C.c_uint32, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
+        lib.hitl_verify_input.argtypes = [vp, C.c_uint32, _f32p, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.hitl_set_stf_blocks_from_search.argtypes = [vp, C.c_float, C.c_float]
         lib.hitl_set_stf_blocks.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_float, C.c_float]
         lib.hitl_set_odometry_blocks.argtypes = [vp, C.c_uint32, _f32p]
@@ -271,6 +272,13 @@ class HitlGpu:
         op, oi, xy = np.zeros(max(cap, 1), np.uint32), np.zeros(max(cap, 1), np.uint32), np.zeros(2 * max(cap, 1), np.float32)
         self._ck(self.lib.hitl_em_inliers(self.ctx, seg, thr, cap, op.ctypes.data, oi.ctypes.data, xy.ctypes.data, C.byref(n)))
         return op[:n.value].copy(), oi[:n.value].copy(), xy[:2 * n.value].reshape(-1, 2).copy()
+
+    def verify_input(self, sel, thr=0.05):
+        """HitLSLAM::verifyUserInput on the resident world clouds: (points_verified, seen bit mask)."""
+        sel = np.ascontiguousarray(sel, np.float32).reshape(-1)
+        v, m = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.hitl_verify_input(self.ctx, len(sel) // 2, sel, C.c_float(thr), C.byref(v), C.byref(m)))
+        return v.value, m.value
 
     def em_assign(self, segs, thr=0.03, min_obs=5):
         segs = np.ascontiguousarray(segs, np.float32).reshape(-1)
@@ -510,6 +518,7 @@ class HostLib:
         lib.hitl_host_session_add_constraints_from_em.argtypes = [vp, C.POINTER(C.c_uint32)]
         lib.hitl_host_session_add_constraints.argtypes = [vp, C.c_uint32, _i32p, _f32p]
         lib.hitl_host_session_clear_constraints.argtypes = [vp]
+        lib.hitl_host_session_verify_input.argtypes = [vp, _f32p, C.POINTER(C.c_uint32)]
         lib.hitl_host_session_solver_options.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         lib.hitl_host_session_joint_opt_run.argtypes = [vp, C.c_int, _f64p]
         lib.hitl_host_session_solve.argtypes = [vp, C.c_int, _f64p]
@@ -681,10 +690,19 @@ class HostSession:
         return dict(segs=sel.reshape(4, 2), corrected=cor[:info[0]].copy(), anchor=anc[:info[1]].copy(), backprop=(int(info[2]), int(info[3])),
                     rounds=(int(info[4]), int(info[5])))
 
-    def correct(self, correction_type, selected_points, cov=None, solve=True):
-        """One full human correction as HitLSLAM::Run wires it: EM -> explicit correction -> back-propagation -> constraints
-        (-> JointOpt::Run).  cov [N,9] f32 is updated in place when given."""
+    def verify_input(self, selected_points):
+        """HitLSLAM::verifyUserInput on the session's resident world clouds: number of verified points (4 = go on)."""
+        v = C.c_uint32()
+        self._ck(self.lib.hitl_host_session_verify_input(self.s, np.ascontiguousarray(selected_points, np.float32).reshape(-1), C.byref(v)))
+        return v.value
+
+    def correct(self, correction_type, selected_points, cov=None, solve=True, verify=False):
+        """One full human correction as HitLSLAM::Run wires it: (input verification ->) EM -> explicit correction -> back-propagation ->
+        constraints (-> JointOpt::Run).  cov [N,9] f32 is updated in place when given.  With verify=True an input that fails
+        verifyUserInput is dropped, as in HitLSLAM::replayLog."""
         sel = np.ascontiguousarray(selected_points, np.float32).reshape(-1).copy()
+        if verify and self.verify_input(sel) != 4:
+            return dict(segs=sel.reshape(4, 2), n_corrected=0, n_anchor=0, backprop=(0, 0), rounds=(0, 0), n_constraints=0, applied=False, verified=False, ms={})
         info, ms, summ = np.zeros(8, np.int32), np.zeros(5), np.zeros(6)
         if cov is not None:
             assert cov.dtype == np.float32 and cov.flags["C_CONTIGUOUS"]

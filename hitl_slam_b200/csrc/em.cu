@@ -225,9 +225,68 @@ __global__ void em_sets_gather_kernel(const uint32_t* __restrict__ obs_slots, co
   for (uint32_t k = lane; k < c; k += 32) obs_out[dst + k] = obs_slots[src + k];
 }
 
+// HitLSLAM::verifyUserInput (HitLSLAM.cpp:218-243): which of the selected points have ANY world-frame point closer than the
+// selection threshold ((w - s).norm() < thr, float).  The reference scans the clouds per selected point and stops at the first
+// hit; existence does not depend on the order, so this is one HBM stream over the resident clouds (8 B per point, two points
+// per 16 B load), flags OR-reduced per warp and merged with one atomicOr per warp that saw a hit.
+struct VerifySel { float x[8], y[8]; uint32_t n; float thr; };
+__global__ void __launch_bounds__(256) verify_input_kernel(const float2* __restrict__ world, uint64_t n_points, const VerifySel S, uint32_t* __restrict__ flags_out) {
+  uint32_t flags = 0;
+  const uint64_t n2 = n_points >> 1, stride = (uint64_t)gridDim.x * blockDim.x;
+  const float4* w4 = reinterpret_cast<const float4*>(world);
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += stride) {
+    const float4 v = __ldg(w4 + q);
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+      if (i < S.n) {
+        const float ax = fsub(v.x, S.x[i]), ay = fsub(v.y, S.y[i]), bx = fsub(v.z, S.x[i]), by = fsub(v.w, S.y[i]);
+        const float da = __fsqrt_rn(fadd(fmul(ax, ax), fmul(ay, ay))), db = __fsqrt_rn(fadd(fmul(bx, bx), fmul(by, by)));
+        if (da < S.thr || db < S.thr) flags |= 1u << i;
+      }
+    }
+  }
+  if ((n_points & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const float2 v = world[n_points - 1];
+    for (uint32_t i = 0; i < S.n; ++i) {
+      const float ax = fsub(v.x, S.x[i]), ay = fsub(v.y, S.y[i]);
+      if (__fsqrt_rn(fadd(fmul(ax, ax), fmul(ay, ay))) < S.thr) flags |= 1u << i;
+    }
+  }
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((threadIdx.x & 31) == 0 && flags) atomicOr(flags_out, flags);
+}
+
 }  // namespace hitl
 
 using namespace hitl;
+
+extern "C" int hitl_verify_input(hitl_ctx* ctx, uint32_t n_selected, const float* sel_xy, float threshold, uint32_t* points_verified, uint32_t* seen_mask) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!points_verified || (n_selected && !sel_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_verify_input: null argument");
+  if (n_selected > 8) return fail(ctx, HITL_ERR_ARG, "hitl_verify_input: at most 8 selected points");
+  if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_verify_input: world clouds not set (hitl_world_transform / hitl_set_world_clouds)");
+  VerifySel S; memset(&S, 0, sizeof(S));
+  S.n = n_selected; S.thr = threshold;
+  for (uint32_t i = 0; i < n_selected; ++i) { S.x[i] = sel_xy[2 * i]; S.y[i] = sel_xy[2 * i + 1]; }
+  HITL_CUDA(ctx->d_ticket.ensure(4));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(uint32_t), ctx->stream));
+  if (ctx->n_points && n_selected) {
+    const uint64_t pairs = (ctx->n_points + 1) / 2;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((pairs + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    verify_input_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_world.p, ctx->n_points, S, ctx->d_ticket.p);
+    HITL_LAUNCH_CHECK("verify_input_kernel");
+  }
+  uint32_t* h = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+  HITL_CUDA(cudaMemcpyAsync(h, ctx->d_ticket.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t mask = h[0];
+  uint32_t v = (uint32_t)__builtin_popcount(mask);
+  // degenerate strokes void the whole input (HitLSLAM.cpp:238-241; the reference reads selected points 0..3 there)
+  if (n_selected >= 4 && ((sel_xy[0] == sel_xy[2] && sel_xy[1] == sel_xy[3]) || (sel_xy[4] == sel_xy[6] && sel_xy[5] == sel_xy[7]))) v = 0;
+  *points_verified = v;
+  if (seen_mask) *seen_mask = mask;
+  return HITL_OK;
+}
 
 extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float* world_xy_out) {
   if (!ctx) return HITL_ERR_ARG;

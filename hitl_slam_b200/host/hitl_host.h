@@ -43,6 +43,7 @@ int hitl_host_session_em_poses(void* s, int32_t* corrected, int32_t* anchor);
 int hitl_host_session_add_constraints_from_em(void* s, uint32_t* n_out);
 int hitl_host_session_add_constraints(void* s, uint32_t n, const int32_t* ids3, const float* deltas4);
 int hitl_host_session_clear_constraints(void* s);
+int hitl_host_session_verify_input(void* s, const float sel_xy[8], uint32_t* points_verified);
 int hitl_host_app_exp_correct(int correction_type, const float sel_xy[8], uint32_t n_poses, float* poses_xyt, uint32_t n_corrected, const int32_t* corrected, float C3[3]);
 int hitl_host_constraint_targets(int correction_type, const float sel_xy[8], uint32_t n_poses, const float* poses_xyt, uint32_t n_corrected, const int32_t* corrected,
                                  uint32_t n_anchor, const int32_t* anchor, int32_t* ids3, float* deltas4);

@@ -302,6 +302,15 @@ int hitl_host_session_correct(void* sp, int correction_type, float sel_xy[8], fl
   })
 }
 
+// HitLSLAM::verifyUserInput (HitLSLAM.cpp:218-243) over the world clouds resident on the session's GPU context: replayLog / Run go on
+// only when every selected point was verified (:315, :383).
+int hitl_host_session_verify_input(void* sp, const float sel_xy[8], uint32_t* points_verified) {
+  Session* s = static_cast<Session*>(sp);
+  HOST_TRY(s, {
+    if (hitl_verify_input(s->ctx, 4, sel_xy, 0.05f, points_verified, nullptr) != HITL_OK) throw std::runtime_error(hitl_last_error(s->ctx));
+  })
+}
+
 int hitl_host_session_clear_constraints(void* sp) { static_cast<Session*>(sp)->jopt.human_constraints_.clear(); return 0; }
 
 // Solver knobs: which = 0 (SolveHumanConstraints) or 1 (PostHumanOptimization); negative values keep the default.

@@ -11,6 +11,7 @@
  *   hitl_find_stf / hitl_get_stf          JointOpt::FindSTFCorrespondences  JointOptimization.cpp:561-642
  *   hitl_find_vo / hitl_get_vo            JointOpt::FindVisualOdometryCorrespondences  JointOptimization.cpp:432-468
  *   hitl_world_transform                  HitLSLAM::transformPointCloudsToWorldFrame   human_in_the_loop_slam/HitLSLAM.cpp:245-254
+ *   hitl_verify_input                     HitLSLAM::verifyUserInput                    human_in_the_loop_slam/HitLSLAM.cpp:218-243
  *   hitl_em_inliers                       E-step of EMInput::AutomaticEndpointAdjustment  human_in_the_loop_slam/EMinput.cpp:207-218
  *   hitl_em_assign                        EMInput::EstablishObservationSets EMinput.cpp:281-323
  *   hitl_set_*_blocks / hitl_eval         AutoDiffCostFunction<...>::Evaluate of the blocks added by
@@ -144,6 +145,11 @@ int hitl_get_vo(hitl_ctx* ctx, uint32_t* source_pose, uint32_t* source_point, ui
  * Result stays resident for the EM calls; world_xy_out may be NULL. */
 int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float* world_xy_out);
 int hitl_set_world_clouds(hitl_ctx* ctx, const float* world_xy);
+
+/* Input verification over the resident world clouds: points_verified = number of selected points (<= 8, sel_xy = x, y per point)
+ * that have a world point with (w - s).norm() < threshold (the reference uses 0.05f), or 0 when either stroke of a 4-point input is
+ * degenerate (sel[0] == sel[1] or sel[2] == sel[3]).  seen_mask (may be NULL): bit i = selected point i was seen. */
+int hitl_verify_input(hitl_ctx* ctx, uint32_t n_selected, const float* sel_xy, float threshold, uint32_t* points_verified, uint32_t* seen_mask);
 
 /* E-step: every world point with DistanceToLineSegment(seg) < threshold, in (pose, index) order.
  * seg = {p0x, p0y, p1x, p1y}. out_* may be NULL (count only); cap = capacity of the out arrays. */

@@ -802,6 +802,23 @@ inline void world_transform(const float* poses_xyt, const std::vector<std::vecto
   }
 }
 
+// HitLSLAM.cpp:218-243 — verifyUserInput: how many selected points have a world point closer than 0.05 (float), scanned per
+// selected point with a break at the first hit; degenerate strokes (sel[0] == sel[1] or sel[2] == sel[3]) void the input.
+// seen_mask (optional): bit i = selected point i was seen.
+inline size_t verify_user_input(const std::vector<std::vector<V2> >& world, const V2* sel, size_t n_sel, uint32_t* seen_mask = nullptr,
+                                float local_select_thresh = 0.05f) {
+  size_t points_verified = 0;
+  uint32_t mask = 0;
+  for (size_t i = 0; i < n_sel; ++i) {
+    bool seen = false;
+    for (size_t j = 0; j < world.size() && !seen; ++j)
+      for (size_t k = 0; k < world[j].size(); ++k)
+        if (norm(world[j][k] - sel[i]) < local_select_thresh) { ++points_verified; seen = true; mask |= 1u << i; break; }
+  }
+  if (n_sel >= 4 && (!(sel[0] != sel[1]) || !(sel[2] != sel[3]))) points_verified = 0;
+  if (seen_mask) *seen_mask = mask;
+  return points_verified;
+}
 
 // ------------------------------------------------------------------------------------------
 // Explicit correction + COP-SLAM back-propagation (the two host stages between EM and JointOpt) — "next" row f3.

@@ -126,6 +126,12 @@ void orc_world_transform(void* p, const float* poses_xyt, float* out_xy) {
   size_t o = 0;
   for (size_t i = 0; i < w.size(); ++i) for (size_t j = 0; j < w[i].size(); ++j, ++o) { out_xy[2 * o] = w[i][j].x; out_xy[2 * o + 1] = w[i][j].y; }
 }
+uint64_t orc_verify_input(uint32_t n, const uint32_t* off, const float* world_xy, uint32_t n_sel, const float* sel_xy, float thr, uint32_t* seen_mask) {
+  std::vector<std::vector<V2> > w; fill(&w, n, off, world_xy);
+  std::vector<V2> sel(n_sel);
+  for (uint32_t i = 0; i < n_sel; ++i) sel[i] = V2(sel_xy[2 * i], sel_xy[2 * i + 1]);
+  return verify_user_input(w, sel.data(), n_sel, seen_mask, thr);
+}
 uint64_t orc_em_inliers(uint32_t n, const uint32_t* off, const float* world_xy, const float seg[4], double thr,
                         uint32_t* out_pose, uint32_t* out_idx, uint64_t cap) {
   std::vector<std::vector<V2> > w; fill(&w, n, off, world_xy);

@@ -50,6 +50,8 @@ class Oracle:
         lib.orc_find_vo.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, C.c_float, C.c_float]
         lib.orc_get_vo.argtypes = [C.c_void_p, _u32p, _u32p, _u32p]
         lib.orc_world_transform.argtypes = [C.c_void_p, _f32p, _f32p]
+        lib.orc_verify_input.restype = C.c_uint64
+        lib.orc_verify_input.argtypes = [C.c_uint32, _u32p, _f32p, C.c_uint32, _f32p, C.c_float, _u32p]
         lib.orc_em_inliers.restype = C.c_uint64
         lib.orc_em_inliers.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_double, _u32p, _u32p, C.c_uint64]
         lib.orc_em_assign.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_double, C.c_uint32, _u32p,
@@ -100,6 +102,14 @@ class Oracle:
         self.lib.orc_pose_graph_free(h)
         return dict(poses=poses.reshape(-1, 3), cov=cov.reshape(-1, 9), offsets=off, pts=pts.reshape(-1, 2),
                     nrm=nrm.reshape(-1, 2))
+
+    def verify_input(self, offsets, world, sel, thr=0.05):
+        """HitLSLAM::verifyUserInput: (points_verified, seen bit mask)."""
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        sel = np.ascontiguousarray(sel, np.float32).reshape(-1)
+        mask = np.zeros(1, np.uint32)
+        v = self.lib.orc_verify_input(len(offsets) - 1, offsets, np.ascontiguousarray(world, np.float32).reshape(-1), len(sel) // 2, sel, thr, mask)
+        return int(v), int(mask[0])
 
     def em_inliers(self, offsets, world, seg, thr=0.03):
         offsets = np.ascontiguousarray(offsets, np.uint32)

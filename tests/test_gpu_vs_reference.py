@@ -134,6 +134,39 @@ def test_observation_sets_equal_reference(gpu, ref, maps):
                 assert np.array_equal(a, b), (trial, f)
 
 
+def test_verify_input_equals_reference(gpu, ref, oracle, host, maps):
+    from hitl_slam_b200 import HostSession, synth
+    from test_oracle_ref_backend import _verify_cases
+    g = maps("small", **DRIFTY)
+    load_map(gpu, g)
+    world = gpu.world_transform(g["poses"])
+    sess = ref.session(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    strokes = synth.pick_strokes(g, min_sep=0.045)
+    for sel in _verify_cases(g, world, strokes):
+        got, mask = gpu.verify_input(sel)
+        assert got == sess.verify(4, sel), sel                    # HitLSLAM::verifyUserInput on the reference's own code
+        assert (got, mask) == oracle.verify_input(g["offsets"], world, sel)
+    # odd point counts and fewer than four selected points (the reference only ever passes four)
+    off, pts, nrm = random_scans(np.random.default_rng(5), 9, 1, 40, empty=(2,))
+    gpu.set_scans(off, pts, nrm)
+    gpu.build_kdtrees()
+    w = gpu.world_transform(np.zeros((9, 3), np.float32))
+    for k in (1, 2, 3, 8):
+        sel = np.concatenate([w[-1:], w[:1], w[3:4] + np.float32(10.0), w[5:6] + np.float32(0.01), w[-1:] + np.float32(0.2), w[1:4]])[:k]
+        assert gpu.verify_input(sel) == oracle.verify_input(off, w, sel)
+    # the session drops an unverified input like HitLSLAM::replayLog does
+    s = HostSession(gpu, host)
+    try:
+        s.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+        s.world_transform(keep_host_copy=False)
+        assert s.verify_input(strokes) == 4
+        bad = strokes.copy(); bad[0] = [999, 999]
+        out = s.correct(4, bad, solve=False, verify=True)
+        assert not out["applied"] and out["verified"] is False
+    finally:
+        s.close()
+
+
 def test_residual_blocks_equal_the_blocks_the_reference_builds(gpu, ref, host, maps):
     """GPU evaluation of odometry / human / STF blocks against AutoDiffCostFunction over the reference's own functors, in the blocks
     JointOpt::AddOdometryConstraints / AddHumanConstraints / AddSTFConstraints build (constants frozen by the reference code)."""

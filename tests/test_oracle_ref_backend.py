@@ -160,6 +160,33 @@ def test_world_clouds_bits(oracle, ref, maps):
     assert same_bits(sess.state()[2], want)                   # HitLSLAM::transformPointCloudsToWorldFrame gives the same bits
 
 
+def _verify_cases(g, world, strokes):
+    rng = np.random.default_rng(21)
+    far = np.array([[500, 500], [501, 500], [-300, 2], [-300, 3]], np.float32)
+    one_off = strokes.copy(); one_off[2] = [400, -400]
+    degenerate_a = strokes.copy(); degenerate_a[1] = degenerate_a[0]
+    degenerate_b = strokes.copy(); degenerate_b[3] = degenerate_b[2]
+    on_points = world[rng.integers(0, len(world), 4)].copy()
+    near = on_points + np.float32(0.03)                         # 0.042 m away: inside the 0.05 m selection radius
+    edge = on_points + np.array([0.05, 0.0], np.float32)        # right at the radius: decided by float rounding
+    return [strokes, far, one_off, degenerate_a, degenerate_b, on_points, near, edge]
+
+
+def test_verify_user_input_is_the_references(oracle, ref, maps):
+    from hitl_slam_b200 import synth
+    g = maps("small", **DRIFTY)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    world = S.world_transform(g["poses"])
+    sess = ref.session(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    seen = set()
+    for sel in _verify_cases(g, world, synth.pick_strokes(g, min_sep=0.045)):
+        want = sess.verify(4, sel)                                # HitLSLAM::verifyUserInput
+        got, _ = oracle.verify_input(g["offsets"], world, sel)
+        assert got == want, sel
+        seen.add(want)
+    assert {0, 4} <= seen
+
+
 # ---- a15 - a19: the residual blocks the reference's Add*Constraints build -------------------------------------------
 def test_odometry_blocks_built_by_the_reference(oracle, ref, maps):
     g = maps("small")
