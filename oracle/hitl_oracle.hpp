@@ -15,11 +15,19 @@
 //       pins PointToPointGlob, PoseConstraint, the four human-imposed functors, both point-to-line
 //       functors (values and auto-diff Jacobians, <= 1e-12) and DistanceToLineSegment (identical
 //       inlier sets) (tests/test_oracle_functors_ref.py).
-// Still "parity unpinned" (restated from the cited lines only, nothing of the reference runs beside
-// them): the FindSTFCorrespondences / FindVisualOdometryCorrespondences loops and
-// RelativePoseTransform (JointOptimization.cpp — needs Ceres/CImg/ROS headers), EMInput's
-// distToLineSeg / EstablishObservationSets / OrderAndFilterUserInput / SegFitEM (EMinput.cpp — Ceres),
-// and the problem-building constants of AddOdometryConstraints / AddHumanConstraints.
+//   * human_in_the_loop_slam/{JointOptimization,EMinput,ApplyExplicitCorrection,Backprop,HitLSLAM}.cpp + kdtree.cpp + helpers.cpp
+//     against oracle/shim3 (2-D Eigen subset incl. Affine2f / Translation2f, a Ceres API slice with a small dense LM, glog, CImg)
+//     behind oracle/ref_hitl_capi.cpp -> libhitl_ref.so
+//       pins, on the reference's OWN code: FindSTFCorrespondences / FindVisualOdometryCorrespondences / RelativePoseTransform /
+//       BuildKDTrees (index lists, transforms and query answers bit for bit), the residual blocks AddOdometryConstraints /
+//       AddHumanConstraints / AddSTFConstraints build (<= 1e-12), CopyTempLaserScans / transformPointCloudsToWorldFrame,
+//       verifyUserInput, EMInput::Run / EstablishObservationSets / distToLineSeg / SegFitEM, AppExpCorrect::Run (incl.
+//       calculateConstraintTargets), Backprop::Run and the whole HitLSLAM::replayLog chain
+//       (tests/test_oracle_ref_backend.py; the CUDA path against the same library: tests/test_gpu_vs_reference.py).
+// What stays restated-only is THIRD-PARTY arithmetic that is absent from /root/reference and from this image: Eigen 3's
+// evaluation order for the 2-D expressions used (the shims restate it a second time, so the pin is on the
+// reference's loops and constants, not on Eigen's internals), Ceres' Jet rules and trust-region loop (1.x documentation), and
+// libstdc++'s std::sort for equal keys (pinned against this image's libstdc++).
 //
 // Every function cites the reference lines it follows (paths relative to
 // /root/reference/HitL-SLAM/src/).  Float expressions follow Eigen 3's evaluation order as
@@ -822,8 +830,8 @@ inline size_t verify_user_input(const std::vector<std::vector<V2> >& world, cons
 
 // ------------------------------------------------------------------------------------------
 // Explicit correction + COP-SLAM back-propagation (the two host stages between EM and JointOpt) — "next" row f3.
-// Parity unpinned: restated from ApplyExplicitCorrection.cpp:150-181, 229-316, 318-445 and Backprop.cpp:98-210
-// (both translation units need Ceres/glog headers and cannot be compiled here).
+// Restated from ApplyExplicitCorrection.cpp:150-181, 229-316, 318-445 and Backprop.cpp:98-210; pinned bit for bit against those
+// translation units compiled where they lie (oracle/_ref/libhitl_ref.so, tests/test_oracle_ref_backend.py).
 // ------------------------------------------------------------------------------------------
 struct Pose2Df { V2 translation; float angle; };                 // perception_2d.h:32-34
 struct CorrectionPair { int pose; float c[3]; };                 // ApplyExplicitCorrection.h: pair<int, Vector3f>
