@@ -315,11 +315,12 @@ def main():
     gpu.set_odometry_blocks(odo)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     neq_dev = None
+    poses_pinned = gpu.pinned_copy(poses)          # the per-call pose upload (120 KB at c2) comes from page-locked memory: no staging copy in the driver
 
     def step():
-        info = gpu.find_stf(poses, src_lo=lo, src_hi=hi, fetch=False)
+        info = gpu.find_stf(poses_pinned, src_lo=lo, src_hi=hi, fetch=False)
         gpu.set_stf_blocks_from_search(STD_DEV, CORR)
-        ne = gpu.normal_eq(poses, fetch=False)
+        ne = gpu.normal_eq(poses_pinned, fetch=False)
         if world > 1:
             nonlocal neq_dev
             ptr, nd = gpu.normal_eq_device()
