@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_set_tiling",
+    "hitl_normal_eq_device", "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
     "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
 
@@ -117,6 +117,7 @@ class HitlGpu:
         lib.hitl_normal_eq.argtypes = [vp, _f64p, vp, vp, vp, vp, C.POINTER(C.c_float)]
         lib.hitl_normal_eq_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         lib.hitl_debug_tile_work.argtypes = [vp, C.c_uint32, _u32p, C.POINTER(C.c_uint32)]
+        lib.hitl_debug_tile_desc.argtypes = [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, _u32p]
         lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int, C.c_uint32]
         lib.hitl_debug_set_fine_occupancy.argtypes = [vp, C.c_int]
         lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int, C.c_int]
@@ -372,6 +373,12 @@ class HitlGpu:
         w = np.zeros(max(n.value, 1), np.uint32)
         self._ck(self.lib.hitl_debug_tile_work(self.ctx, n.value, w, C.byref(n)))
         return w[:n.value].astype(np.uint64) * 64
+
+    def debug_tile_desc(self):
+        n = len(self.debug_tile_work())
+        a = [np.zeros(max(n, 1), np.uint32) for _ in range(5)]
+        self._ck(self.lib.hitl_debug_tile_desc(self.ctx, n, *a))
+        return dict(scan=a[0][:n], k0=a[1][:n] & 0xFFFF, len=a[1][:n] >> 16, jlo=a[2][:n], jhi=a[3][:n], open=a[4][:n])
 
     def debug_set_tiling(self, max_len=32, adaptive=True, target_parts=1):
         self._ck(self.lib.hitl_debug_set_tiling(self.ctx, max_len, int(adaptive), int(target_parts)))

@@ -111,7 +111,7 @@ uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, c
       if (ctx->target_splitting && h_open[t - lo] > 0 && work > limit * parts) {
         const uint32_t ja = a, jb = std::min(b, last_pose);
         const uint32_t span = jb >= ja ? jb - ja + 1 : 0;
-        jparts = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(16, span / 64), (work + limit * parts - 1) / (limit * parts));
+        jparts = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(16, span / std::max(1u, ctx->min_target_span)), (work + limit * parts - 1) / (limit * parts));
         if (jparts < 1) jparts = 1;
       }
     }
@@ -149,6 +149,10 @@ extern "C" int hitl_create(hitl_ctx** out, int device) {
   hitl_ctx* ctx = new hitl_ctx();
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // scheduling knobs of the adaptive tiling (results never depend on them)
+  if (const char* v = getenv("HITL_SPLIT_LIMIT_DIV")) ctx->split_limit_div = (uint32_t)std::max(1, atoi(v));
+  if (const char* v = getenv("HITL_MIN_TARGET_SPAN")) ctx->min_target_span = (uint32_t)std::max(1, atoi(v));
+  if (const char* v = getenv("HITL_SPLIT_ROUNDS")) ctx->max_split_rounds = (uint32_t)std::max(0, atoi(v));
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) { cudaEventCreate(&ctx->ev[i]); cudaEventCreate(&ctx->evx[i]); }
   if (cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess) { hitl_destroy(ctx); cudaGetLastError(); return HITL_ERR_CUDA; }

@@ -1298,10 +1298,10 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   if (ctx->adaptive_tiling && n_tiles > 1 && !o->disable_culling) {
     const uint64_t slots = (uint64_t)ctx->sm_count * 64;
     const uint64_t fair = work_sum / slots + 1;                              // cycles/64 per resident warp if perfectly packed
-    const uint64_t limit = std::max<uint64_t>(fair / 2, 4096);               // never split tiles cheaper than ~0.13 ms
+    const uint64_t limit = std::max<uint64_t>(fair / std::max(1u, ctx->split_limit_div), 4096);   // never split tiles cheaper than ~0.13 ms
     const uint64_t h_max = ctx->h_pinned[8];                                 // heaviest tile of this call
     if (ctx->split_lo != lo || ctx->split_hi != hi) { ctx->split_lo = lo; ctx->split_hi = hi; ctx->split_rounds = 0; }
-    if (h_max > 2 * limit && ctx->split_rounds < 4) {
+    if (h_max > 2 * limit && ctx->split_rounds < ctx->max_split_rounds) {
       ++ctx->split_rounds;
       std::vector<uint32_t> h_work(n_tiles), h_open(n_tiles), est;
       HITL_CUDA(cudaMemcpy(h_work.data(), ctx->d_tile_work.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
@@ -1393,6 +1393,23 @@ extern "C" int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_
   const uint32_t n = std::min(cap, ctx->n_tiles);
   if (n && work_out) HITL_CUDA(cudaMemcpyAsync(work_out, ctx->d_tile_work.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+// Tile descriptors of the current tiling (host tables) and the "open points" count the last search measured per tile.
+extern "C" int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan, uint32_t* k0_len, uint32_t* jlo, uint32_t* jhi, uint32_t* open) {
+  if (!ctx) return HITL_ERR_ARG;
+  const uint32_t n = std::min<uint32_t>(cap, (uint32_t)ctx->h_tile_scan.size());
+  for (uint32_t t = 0; t < n; ++t) {
+    if (scan) scan[t] = ctx->h_tile_scan[t];
+    if (k0_len) k0_len[t] = ctx->h_tile_kl[t];
+    if (jlo) jlo[t] = ctx->h_tile_jlo[t];
+    if (jhi) jhi[t] = ctx->h_tile_jhi[t];
+  }
+  if (open && n && ctx->d_tile_open.p) {
+    HITL_CUDA(cudaMemcpyAsync(open, ctx->d_tile_open.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   return HITL_OK;
 }
 

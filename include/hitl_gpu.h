@@ -224,6 +224,9 @@ int hitl_backprop_poses(hitl_ctx* ctx, uint32_t n_poses, float* poses_xyt, uint3
 /* SM cycles / 64 the last hitl_find_stf spent on each 32-point tile (tiles outside the searched range keep
  * stale values); profiling aid for the tile scheduler. */
 int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32_t* n_tiles_out);
+/* Descriptors of the current tiles: source scan, first point | length << 16, target range [jlo, jhi] (0 .. 0xFFFFFFFF = all),
+ * and the number of points the last search left below the cap at the end of the tile's range. Any pointer may be NULL. */
+int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan, uint32_t* k0_len, uint32_t* jlo, uint32_t* jhi, uint32_t* open_points);
 /* Re-cuts every scan into tiles of at most max_len (1..32) points and sets the automatic splitting of heavy tiles:
  * adaptive 0 = off, 1 = along the points and along the target axis, 2 = along the points only.  target_parts > 1
  * additionally cuts EVERY tile into that many consecutive target ranges that are searched concurrently and merged
