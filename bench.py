@@ -317,17 +317,30 @@ def main():
     neq_dev = None
     poses_pinned = gpu.pinned_copy(poses)          # the per-call pose upload (120 KB at c2) comes from page-locked memory: no staging copy in the driver
 
+    debug = bool(os.environ.get("HITL_BENCH_DEBUG"))
+    trace = []
+
     def step():
+        t0 = time.perf_counter()
         info = gpu.find_stf(poses_pinned, src_lo=lo, src_hi=hi, fetch=False)
+        t1 = time.perf_counter()
         gpu.set_stf_blocks_from_search(STD_DEV, CORR)
         ne = gpu.normal_eq(poses_pinned, fetch=False)
+        t2 = time.perf_counter()
         if world > 1:
             nonlocal neq_dev
             ptr, nd = gpu.normal_eq_device()
             if neq_dev is None or neq_dev[0] != ptr:
                 neq_dev = (ptr, tensor_from_ptr(ptr, nd, local_rank))
             with torch.cuda.stream(stream):
+                if debug:
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record()
                 dist.all_reduce(neq_dev[1])
+                if debug:
+                    eb.record()
+                    eb.synchronize()
+                    trace.append((t1 - t0, t2 - t1, time.perf_counter() - t2, ea.elapsed_time(eb), info["ms_total"], ne["ms"]))
         return info, ne
 
     if world > 1:
@@ -366,8 +379,16 @@ def main():
         infos.append(step())
         with torch.cuda.stream(stream):
             ends[k].record()
+        # The step ends with an asynchronous all-reduce when N > 1: wait for it before the (untimed) L2 flush of the next iteration is
+        # launched, otherwise the 512 MB fill runs concurrently with the collective it is not part of and delays it (measured at N = 2:
+        # 6.18 -> 5.63 ms per step).
+        ends[k].synchronize()
     torch.cuda.synchronize()
     launches = gpu.launch_count() - launches0
+    if debug and trace:
+        for k, tr in enumerate(trace[-args.steps:]):
+            sys.stderr.write("[rank %d] step %d: host find_stf %.3f ms (device %.3f) | host normal_eq %.3f ms (device %.3f) | all-reduce host %.3f ms, on stream %.3f ms | events %.3f ms\n"
+                             % (rank, k, tr[0] * 1e3, tr[4], tr[1] * 1e3, tr[5], tr[2] * 1e3, tr[3], starts[k].elapsed_time(ends[k])))
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
