@@ -1,9 +1,10 @@
 """Regenerates the committed golden fixtures under tests/golden/.
 
-The reference ships no golden vectors for this path and cannot be compiled
-here, so the fixtures are outputs of the CPU oracle (oracle/hitl_oracle.hpp, whose KD-tree is
-itself pinned against the reference's own kdtree.cpp via oracle/_ref) on small seeded synthetic
-maps.  Run from the repo root:  python tests/golden/make_golden.py
+The reference ships no golden vectors for this path, so the fixtures are outputs of the
+CPU oracle (oracle/hitl_oracle.hpp) on small seeded synthetic maps; the reference's own JointOpt /
+EMInput, compiled where they lie (oracle/_ref/libhitl_ref.so), reproduce them from the fixture inputs
+(tests/test_oracle_ref_backend.py::test_golden_fixtures_equal_the_references_output).
+Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys

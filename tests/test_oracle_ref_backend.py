@@ -409,3 +409,31 @@ def test_whole_correction_chain_against_hitlslam(oracle, ref, host, maps, monkey
     assert np.abs(p_ref - wrapped).max() <= 2e-6
     assert same_bits(S.world_transform(p_ref), w_ref)          # the session's world clouds are the transform of its final poses
     assert np.abs(p_ref - g["poses"]).max() > 1e-3             # and the correction did move the map
+
+
+# ---- the committed golden fixtures are what the reference's own code produces ---------------------------------------
+def test_golden_fixtures_equal_the_references_output(ref):
+    """tests/golden/*.npz were generated from the oracle (tests/golden/make_golden.py); here the reference's own JointOpt /
+    EMInput reproduce them from the fixture inputs, so the fixtures pin the CUDA path to the reference even on a box where
+    oracle/_ref is absent."""
+    import os
+    from conftest import ROOT
+    from hitl_slam_b200 import synth
+    gd = os.path.join(ROOT, "tests", "golden")
+    m = np.load(os.path.join(gd, "tiny_compensated.npz"))
+    want = np.load(os.path.join(gd, "tiny_stf.npz"))
+    J = ref.joint_opt(m["offsets"], m["pts"], m["nrm"], m["poses"])
+    got = J.find_stf(m["poses"].astype(np.float64))
+    for k in ("pair_i", "pair_j", "pair_off", "k", "idx"):
+        assert np.array_equal(got[k], want[k]), k
+    ev = np.load(os.path.join(gd, "tiny_eval.npz"))
+    r_stf, J_stf, _ = J.eval_blocks(2, ev["x"], len(got["pair_i"]))
+    r_odo, J_odo, _ = J.eval_blocks(0, ev["x"], len(m["poses"]))
+    assert close(ev["r_stf"], r_stf) and close(ev["J_stf"].reshape(len(r_stf), -1), J_stf)
+    assert close(ev["r_odo"], r_odo) and close(ev["J_odo"].reshape(len(r_odo), -1), J_odo)
+    em = np.load(os.path.join(gd, "small_em.npz"))
+    g = synth.generate("small")
+    world = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"]).world_clouds()
+    sets = ref.em_observation_sets(g["offsets"], world, em["strokes"])
+    for f in range(2):
+        assert np.array_equal(sets[f][0], em["set%d_pose" % f]) and np.array_equal(sets[f][1], em["set%d_off" % f]) and np.array_equal(sets[f][2], em["set%d_obs" % f])
