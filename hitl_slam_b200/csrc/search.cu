@@ -1301,8 +1301,12 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     const uint64_t limit = std::max<uint64_t>(fair / std::max(1u, ctx->split_limit_div), 4096);   // never split tiles cheaper than ~0.13 ms
     const uint64_t h_max = ctx->h_pinned[8];                                 // heaviest tile of this call
     if (ctx->split_lo != lo || ctx->split_hi != hi) { ctx->split_lo = lo; ctx->split_hi = hi; ctx->split_rounds = 0; }
-    if (h_max > 2 * limit && ctx->split_rounds < ctx->max_split_rounds) {
-      ++ctx->split_rounds;
+    // Re-tiling is a SETUP cost (milliseconds of host work): it may only follow the first max_split_rounds CALLS on a source range.
+    // Counting calls, not splits, matters: a heaviest tile that hovers around the threshold would otherwise keep re-tiling now and
+    // then for ever (seen on one rank of an 8-rank run: 5-10 ms of host time inside steady-state steps).
+    const bool may_split = ctx->split_rounds < ctx->max_split_rounds;
+    if (may_split) ++ctx->split_rounds;
+    if (may_split && h_max > 2 * limit) {
       std::vector<uint32_t> h_work(n_tiles), h_open(n_tiles), est;
       HITL_CUDA(cudaMemcpy(h_work.data(), ctx->d_tile_work.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
       HITL_CUDA(cudaMemcpy(h_open.data(), ctx->d_tile_open.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
