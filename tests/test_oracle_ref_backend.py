@@ -411,6 +411,54 @@ def test_whole_correction_chain_against_hitlslam(oracle, ref, host, maps, monkey
     assert np.abs(p_ref - g["poses"]).max() > 1e-3             # and the correction did move the map
 
 
+def test_sequential_corrections_against_hitlslam(oracle, ref, host, maps, monkeypatch):
+    """BASELINE config 4 in miniature: several corrections replayed one after the other on the reference's HitLSLAM session, each drawn
+    on the map as the previous ones left it and each adding a group of human constraints that the next joint optimisation keeps.  After
+    every correction the oracle chain (fed with the reference's refit endpoints) reproduces the constraint targets and covariances bit
+    for bit and an independent minimiser over ALL constraint groups so far reproduces the session's poses (1e-5)."""
+    from hitl_slam_b200 import synth
+    monkeypatch.setenv("HITL_SHIM_LM_TIGHT", "1")
+    g = maps("c1", **DRIFTY)
+    n = len(g["poses"])
+    cov = np.tile(np.array([1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-5], np.float32), (n, 1))
+    sess = ref.session(g["offsets"], g["pts"], g["nrm"], g["poses"], cov)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    cur, start, groups, applied = dict(g), 0, [], 0
+    for c in range(3):
+        try:
+            segs, start = synth.pick_strokes(cur, min_sep=0.045 if c == 0 else 0.01, start=start, return_next=True)
+        except RuntimeError:
+            break                                              # the remaining walls have no visible gap any more
+        world = S.world_transform(cur["poses"])
+        assert same_bits(world, sess.state()[2])               # the session's displayed clouds are the transform of its poses
+        em = oracle.em_run(g["offsets"], world, segs)
+        em_ref = ref.em_run(g["offsets"], world, segs)
+        assert np.array_equal(em["corrected"], em_ref["corrected"]) and np.array_equal(em["anchor"], em_ref["anchor"]) and em["backprop"] == em_ref["backprop"]
+        n_groups = sess.replay(4, segs)
+        if not (em_ref["backprop"][0] >= 0 and em_ref["backprop"][1] >= 1):
+            assert n_groups == len(groups)                     # rejected input (overlapping selections): nothing changes (HitLSLAM.cpp:332)
+            continue
+        assert n_groups == len(groups) + 1
+        p_ref, cov_ref, _ = sess.state()
+        hc_i, hc_f = sess.constraints(len(groups))
+        p1, c3 = oracle.app_exp_corrections(4, em_ref["segs"], cur["poses"], em["corrected"])
+        ti, tf = host.constraint_targets(4, em_ref["segs"], p1, em["corrected"], em["anchor"])
+        assert np.array_equal(ti, hc_i) and same_bits(tf, hc_f), c
+        p2, cov2 = oracle.backprop(p1, cov, em["backprop"][0], em["backprop"][1], c3)
+        assert same_bits(cov2, cov_ref), c
+        p2[:, 2] = np.arctan2(np.sin(p2[:, 2]), np.cos(p2[:, 2]))
+        groups.append((hc_i, hc_f))
+        all_i, all_f = np.concatenate([x[0] for x in groups]), np.concatenate([x[1] for x in groups])
+        want, _ = _scipy_minimiser(oracle, p2, all_i, all_f)   # every group so far constrains the solve (JointOptimization.cpp:973-975)
+        wrapped = want.copy()
+        wrapped[:, 2] -= 2 * np.pi * np.rint(wrapped[:, 2] / (2 * np.pi))
+        assert np.abs(p_ref - wrapped).max() <= 1e-5, c        # 500-pose chain, two solvers, float32 storage of the result
+        cur = dict(cur); cur["poses"] = p_ref
+        cov = cov_ref
+        applied += 1
+    assert applied >= 2
+
+
 # ---- the committed golden fixtures are what the reference's own code produces ---------------------------------------
 def test_golden_fixtures_equal_the_references_output(ref):
     """tests/golden/*.npz were generated from the oracle (tests/golden/make_golden.py); here the reference's own JointOpt /
