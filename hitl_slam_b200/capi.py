@@ -474,9 +474,17 @@ class HostLib:
         self.lib.hitl_host_relative_pose(np.ascontiguousarray(poses, np.float64).reshape(-1), src, dst, out)
         return out
 
-    def load_pose_graph(self, path):
+    def load_pose_graph(self, path, cache=None):
+        """cache: None = parse the text file; True = through path + ".hitlcache"; a string = through that cache file.
+        With a cache the result carries from_cache (bool)."""
         n, m = C.c_uint64(), C.c_uint64()
-        h = self.lib.hitl_host_load_pose_graph(path.encode(), C.byref(n), C.byref(m))
+        hit = C.c_int(0)
+        if cache is None:
+            h = self.lib.hitl_host_load_pose_graph(path.encode(), C.byref(n), C.byref(m))
+        else:
+            self.lib.hitl_host_load_pose_graph_cached.restype = C.c_void_p
+            self.lib.hitl_host_load_pose_graph_cached.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+            h = self.lib.hitl_host_load_pose_graph_cached(path.encode(), None if cache is True else str(cache).encode(), C.byref(n), C.byref(m), C.byref(hit))
         if not h:
             raise IOError("cannot read pose graph " + path)
         poses, cov = np.zeros(3 * n.value, np.float32), np.zeros(9 * n.value, np.float32)
@@ -484,7 +492,10 @@ class HostLib:
         pts, nrm = np.zeros(2 * m.value, np.float32), np.zeros(2 * m.value, np.float32)
         self.lib.hitl_host_pose_graph_get(h, poses, cov, off, pts, nrm)
         self.lib.hitl_host_pose_graph_free(h)
-        return dict(poses=poses.reshape(-1, 3), cov=cov.reshape(-1, 9), offsets=off, pts=pts.reshape(-1, 2), nrm=nrm.reshape(-1, 2))
+        out = dict(poses=poses.reshape(-1, 3), cov=cov.reshape(-1, 9), offsets=off, pts=pts.reshape(-1, 2), nrm=nrm.reshape(-1, 2))
+        if cache is not None:
+            out["from_cache"] = bool(hit.value)
+        return out
 
     def save_stfs_covars(self, path, poses, cov, offsets, obs_world, nrm_world, map_name="synthetic", timestamp=0.0):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1)

@@ -7,6 +7,8 @@ extern "C" {
 #endif
 // .stfs.covars (loadPoseGraph, HitLSLAM_main.cpp:192-300 / SaveStfsandCovars, vector_mapping_main.cpp:1855-1928)
 void* hitl_host_load_pose_graph(const char* path, uint64_t* n_poses, uint64_t* n_points);
+// the same through a binary cache of the parsed graph (default cache_path: path + ".hitlcache"; stale caches are detected and rewritten)
+void* hitl_host_load_pose_graph_cached(const char* path, const char* cache_path, uint64_t* n_poses, uint64_t* n_points, int* from_cache);
 void hitl_host_pose_graph_get(void* h, float* poses, float* cov, uint32_t* off, float* pts, float* nrm);
 void hitl_host_pose_graph_free(void* h);
 int hitl_host_save_stfs_covars(const char* path, const char* map_name, double timestamp, uint32_t n_poses, const float* poses_xyt,

@@ -210,6 +210,87 @@ void hitl_host_pose_graph_get(void* h, float* poses, float* cov, uint32_t* off, 
 }
 void hitl_host_pose_graph_free(void* h) { delete static_cast<Graph*>(h); }
 
+// ---- binary cache of a parsed pose graph ------------------------------------------------------------
+// Parsing is the dominant wall-clock term outside the kernels at c3 / c5 sizes (one text line per point: 21.6 M - 216 M lines).
+// The cache stores the PARSED graph (robot-frame clouds, poses, covariances, offsets: exactly what hitl_host_load_pose_graph
+// returns) next to a fingerprint of the text file (size, mtime in ns, FNV-1a of the first and last 64 KB); a cache whose
+// fingerprint does not match the text file is ignored and rewritten.  Layout: 64-byte header, then poses | cov | off | pts | nrm.
+namespace {
+struct CacheHeader {
+  char magic[8];                  // "HITLPG01"
+  uint64_t text_size, text_mtime_ns, text_hash, n_poses, n_points;
+  double timestamp;
+  uint64_t reserved;
+};
+static_assert(sizeof(CacheHeader) == 64, "cache header layout");
+}  // namespace
+}  // extern "C" (helpers below are C++)
+#include <sys/stat.h>
+namespace {
+bool text_fingerprint(const char* path, uint64_t* size, uint64_t* mtime_ns, uint64_t* hash) {
+  struct stat st;
+  if (stat(path, &st) != 0) return false;
+  *size = (uint64_t)st.st_size;
+  *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  uint64_t h = 1469598103934665603ull;
+  std::vector<unsigned char> buf(65536);
+  auto mix = [&](size_t n) { for (size_t i = 0; i < n; ++i) { h ^= buf[i]; h *= 1099511628211ull; } };
+  size_t n = fread(buf.data(), 1, buf.size(), f);
+  mix(n);
+  if (*size > 2 * buf.size()) { fseek(f, -(long)buf.size(), SEEK_END); n = fread(buf.data(), 1, buf.size(), f); mix(n); }
+  fclose(f);
+  *hash = h;
+  return true;
+}
+bool read_all(FILE* f, void* dst, size_t bytes) { return bytes == 0 || fread(dst, 1, bytes, f) == bytes; }
+bool write_all(FILE* f, const void* src, size_t bytes) { return bytes == 0 || fwrite(src, 1, bytes, f) == bytes; }
+}  // namespace
+extern "C" {
+
+// Loads `path` through its cache `cache_path` (NULL: path + ".hitlcache").  *from_cache (may be NULL) tells which way it went.
+// A missing / stale / truncated cache falls back to the text parser and is rewritten (best effort: a read-only directory only
+// costs the cache).  Returns the same handle type as hitl_host_load_pose_graph.
+void* hitl_host_load_pose_graph_cached(const char* path, const char* cache_path, uint64_t* n_poses, uint64_t* n_points, int* from_cache) {
+  if (from_cache) *from_cache = 0;
+  if (!path || !n_poses || !n_points) return NULL;
+  const std::string cp = cache_path ? std::string(cache_path) : std::string(path) + ".hitlcache";
+  uint64_t size = 0, mtime = 0, hash = 0;
+  if (!text_fingerprint(path, &size, &mtime, &hash)) return NULL;
+  if (FILE* f = fopen(cp.c_str(), "rb")) {
+    CacheHeader h;
+    Graph* g = new Graph();
+    bool ok = read_all(f, &h, sizeof(h)) && memcmp(h.magic, "HITLPG01", 8) == 0 && h.text_size == size && h.text_mtime_ns == mtime && h.text_hash == hash &&
+              h.n_poses < (1ull << 32) && h.n_points < (1ull << 32);
+    if (ok) {
+      g->poses.resize(3 * h.n_poses); g->cov.resize(9 * h.n_poses); g->off.resize(h.n_poses + 1); g->pts.resize(2 * h.n_points); g->nrm.resize(2 * h.n_points);
+      g->timestamp = h.timestamp;
+      ok = read_all(f, g->poses.data(), 4 * g->poses.size()) && read_all(f, g->cov.data(), 4 * g->cov.size()) && read_all(f, g->off.data(), 4 * g->off.size()) &&
+           read_all(f, g->pts.data(), 4 * g->pts.size()) && read_all(f, g->nrm.data(), 4 * g->nrm.size());
+      // structural check: offsets start at 0, never decrease and end at n_points
+      ok = ok && g->off[0] == 0 && g->off[h.n_poses] == h.n_points;
+      for (uint64_t i = 0; ok && i < h.n_poses; ++i) ok = g->off[i] <= g->off[i + 1];
+    }
+    fclose(f);
+    if (ok) { *n_poses = h.n_poses; *n_points = h.n_points; if (from_cache) *from_cache = 1; return g; }
+    delete g;
+  }
+  Graph* g = static_cast<Graph*>(hitl_host_load_pose_graph(path, n_poses, n_points));
+  if (!g) return NULL;
+  const std::string tmp = cp + ".tmp";
+  if (FILE* f = fopen(tmp.c_str(), "wb")) {
+    CacheHeader h; memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "HITLPG01", 8);
+    h.text_size = size; h.text_mtime_ns = mtime; h.text_hash = hash; h.n_poses = *n_poses; h.n_points = *n_points; h.timestamp = g->timestamp;
+    const bool ok = write_all(f, &h, sizeof(h)) && write_all(f, g->poses.data(), 4 * g->poses.size()) && write_all(f, g->cov.data(), 4 * g->cov.size()) &&
+                    write_all(f, g->off.data(), 4 * g->off.size()) && write_all(f, g->pts.data(), 4 * g->pts.size()) && write_all(f, g->nrm.data(), 4 * g->nrm.size());
+    const bool closed = fclose(f) == 0;
+    if (ok && closed) rename(tmp.c_str(), cp.c_str()); else remove(tmp.c_str());
+  }
+  return g;
+}
+
 // One line per point; obs/normals are WORLD frame as the format requires (README.md:119-137).
 int hitl_host_save_stfs_covars(const char* path, const char* map_name, double timestamp, uint32_t n_poses, const float* poses_xyt, const float* cov9,
                                const uint32_t* off, const float* obs_world_xy, const float* nrm_world_xy) {

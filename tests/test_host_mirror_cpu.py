@@ -172,6 +172,56 @@ def test_stfs_covars_io_threads_and_fast_parser(host, tmp_path, monkeypatch):
         assert np.array_equal(gb["pts"], g["pts"][:cutline - 2])
 
 
+def test_pose_graph_binary_cache(host, tmp_path):
+    """a binary cache of the parsed scans beside the .stfs.covars text file.  A cache hit returns exactly what the text
+    parser returns; a cache that no longer matches the text file (content, size or mtime changed, truncated, foreign bytes) is ignored
+    and rewritten."""
+    import os
+    rng = np.random.default_rng(17)
+    n = 120
+    poses = (rng.normal(size=(n, 3)) * 10).astype(np.float32)
+    cov = np.abs(rng.normal(size=(n, 9)) * 1e-4).astype(np.float32)
+    cnt = rng.integers(1, 200, n)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
+    obs = (rng.normal(size=(off[-1], 2)) * 25).astype(np.float32)
+    nrm = rng.normal(size=(off[-1], 2)).astype(np.float32)
+    path = str(tmp_path / "map.stfs.covars")
+    host.save_stfs_covars(path, poses, cov, off, obs, nrm, map_name="cache", timestamp=3.25)
+    want = host.load_pose_graph(path)
+
+    def same(a, b):
+        return all(np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in ("poses", "cov", "offsets", "pts", "nrm"))
+
+    first = host.load_pose_graph(path, cache=True)
+    assert not first["from_cache"] and same(first, want) and os.path.exists(path + ".hitlcache")
+    second = host.load_pose_graph(path, cache=True)
+    assert second["from_cache"] and same(second, want)
+    # explicit cache location
+    other = str(tmp_path / "elsewhere.bin")
+    assert not host.load_pose_graph(path, cache=other)["from_cache"] and host.load_pose_graph(path, cache=other)["from_cache"]
+    # truncated cache: falls back to the text and repairs the cache
+    blob = open(path + ".hitlcache", "rb").read()
+    open(path + ".hitlcache", "wb").write(blob[:len(blob) // 2])
+    third = host.load_pose_graph(path, cache=True)
+    assert not third["from_cache"] and same(third, want)
+    assert host.load_pose_graph(path, cache=True)["from_cache"]
+    # foreign bytes
+    open(path + ".hitlcache", "wb").write(b"not a cache at all" * 10)
+    assert not host.load_pose_graph(path, cache=True)["from_cache"]
+    # the text changes (one more scan): the old cache must not be served
+    poses2 = np.concatenate([poses, poses[-1:] + np.float32(1.0)])
+    cov2 = np.concatenate([cov, cov[-1:]])
+    off2 = np.concatenate([off, [off[-1] + 7]]).astype(np.uint32)
+    obs2 = np.concatenate([obs, (rng.normal(size=(7, 2)) * 5).astype(np.float32)])
+    nrm2 = np.concatenate([nrm, rng.normal(size=(7, 2)).astype(np.float32)])
+    host.save_stfs_covars(path, poses2, cov2, off2, obs2, nrm2, map_name="cache", timestamp=3.25)
+    fresh = host.load_pose_graph(path, cache=True)
+    assert not fresh["from_cache"] and len(fresh["poses"]) == n + 1 and same(fresh, host.load_pose_graph(path))
+    assert host.load_pose_graph(path, cache=True)["from_cache"]
+    with pytest.raises(IOError):
+        host.load_pose_graph(str(tmp_path / "missing.stfs.covars"), cache=True)
+
+
 def _same_bits(a, b):
     a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
     return a.shape == b.shape and bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
