@@ -439,6 +439,9 @@ class RefBackend:
         lib.ref_jo_eval_blocks.restype = C.c_int64
         lib.ref_jo_eval_blocks.argtypes = [vp, C.c_int, _f64p, C.c_uint64, C.c_int, C.c_int, _f64p, _f64p, _i32p]
         lib.ref_jo_run.argtypes = [vp, _f32p, _f64p]
+        lib.ref_jo_post_human_optimization.restype = C.c_int
+        lib.ref_jo_post_human_optimization.argtypes = [vp, _f64p, _u64p]
+        lib.ref_jo_get_gradient.argtypes = [vp, _f64p]
         lib.ref_em_run.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_int, _i32p, _i32p, _i32p]
         lib.ref_em_observation_sets.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
         lib.ref_em_dist_to_line_seg.restype = C.c_double
@@ -616,6 +619,16 @@ class RefJointOpt:
         self.lib.ref_jo_run(self.h, p, pa)
         return p.reshape(-1, 3), pa.reshape(-1, 3)
 
+    def post_human_optimization(self, poses_f64=None):
+        """JointOpt::PostHumanOptimization on the reference's own CPU code (search + STF blocks + solve + Problem::Evaluate)."""
+        if poses_f64 is not None:
+            self.set_pose_array(poses_f64)
+        out, counts = np.zeros(3 * self.n), np.zeros(4, np.uint64)
+        t = int(self.lib.ref_jo_post_human_optimization(self.h, out, counts))
+        grad = np.zeros(int(counts[3]))
+        self.lib.ref_jo_get_gradient(self.h, grad)
+        return dict(termination=t, pose_array=out.reshape(-1, 3), n_blocks=int(counts[0]), n_matches=int(counts[1]), n_vo=int(counts[2]), gradient=grad)
+
 
 class RefSession:
     """The reference's HitLSLAM (init + replayLog): the whole correction chain on its own code."""
@@ -648,3 +661,49 @@ class RefSession:
         hi, hf = np.zeros(3 * max(n, 1), np.int32), np.zeros(4 * max(n, 1), np.float32)
         self.lib.ref_session_constraints(self.h, g, hi.ctypes.data, hf.ctypes.data)
         return hi[:3 * n].reshape(-1, 3), hf[:4 * n].reshape(-1, 4)
+
+
+class RefDropin:
+    """The reference's JointOpt with BuildKDTrees / FindSTFCorrespondences / FindVisualOdometryCorrespondences re-bound to the product's
+    C ABI (oracle/_ref/libhitl_ref_dropin.so, oracle/ref_dropin_capi.cpp): the drop-in demonstration.  Needs a hitl_ctx (a B200)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref_dropin.so"))
+
+    def __init__(self):
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref_dropin.so"))
+        vp = C.c_void_p
+        lib.dropin_create.restype = vp
+        lib.dropin_create.argtypes = [vp, C.c_uint32, _u32p, _f32p, _f32p, _f32p, C.c_char_p, C.c_size_t]
+        lib.dropin_destroy.argtypes = [vp]
+        lib.dropin_set_options.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_uint32, C.c_float, C.c_float]
+        lib.dropin_set_pose_array.argtypes = [vp, _f64p]
+        lib.dropin_post_human_optimization.restype = C.c_int
+        lib.dropin_post_human_optimization.argtypes = [vp, _f64p, _u64p, C.c_char_p, C.c_size_t]
+        lib.dropin_get_gradient.argtypes = [vp, _f64p]
+
+    def create(self, ctx, offsets, pts, nrm, poses_f32):
+        """ctx: the c_void_p of a live hitl_ctx (HitlGpu.ctx) or None.  Raises RuntimeError with the library's message on failure."""
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        err = C.create_string_buffer(512)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32).reshape(-1)   # noqa: E731
+        h = self.lib.dropin_create(ctx, len(offsets) - 1, offsets, f32(pts), f32(nrm), f32(poses_f32), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode() or "dropin_create failed")
+        self.lib.dropin_set_options(h, 0.15, float(np.float32(np.deg2rad(25.0))), 6, 1, 0.05, 1.0 / 40.0)
+        return h
+
+    def destroy(self, h):
+        self.lib.dropin_destroy(h)
+
+    def post_human_optimization(self, h, n_poses, poses_f64=None):
+        if poses_f64 is not None:
+            self.lib.dropin_set_pose_array(h, np.ascontiguousarray(poses_f64, np.float64).reshape(-1))
+        out, counts, err = np.zeros(3 * n_poses), np.zeros(4, np.uint64), C.create_string_buffer(512)
+        t = self.lib.dropin_post_human_optimization(h, out, counts, err, 512)
+        if t < 0:
+            raise RuntimeError(err.value.decode())
+        grad = np.zeros(int(counts[3]))
+        self.lib.dropin_get_gradient(h, grad)
+        return dict(termination=t, pose_array=out.reshape(-1, 3), n_blocks=int(counts[0]), n_matches=int(counts[1]), n_vo=int(counts[2]), gradient=grad)

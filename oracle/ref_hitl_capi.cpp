@@ -236,6 +236,24 @@ void ref_jo_run(void* hp, float* poses_xyt_out, double* pose_array_out) {
   if (pose_array_out) std::copy(h->jo.pose_array_.begin(), h->jo.pose_array_.end(), pose_array_out);
 }
 
+// JointOpt::PostHumanOptimization (:1156-1256) on the reference's own CPU code: FindVisualOdometryCorrespondences, FindSTFCorrespondences,
+// AddSTFConstraints, Solve (stand-in LM), Problem::Evaluate.  counts = {STF blocks, STF matches, consecutive-pose correspondences, gradient entries}.
+int ref_jo_post_human_optimization(void* hp, double* pose_array_out, uint64_t counts[4]) {
+  Quiet q;
+  JointOpt& jo = ((RefJointOpt*)hp)->jo;
+  jo.point_point_correspondences_.clear();
+  const int t = (int)jo.PostHumanOptimization(0, (int)jo.pose_array_.size() / 3 - 1);
+  std::copy(jo.pose_array_.begin(), jo.pose_array_.end(), pose_array_out);
+  uint64_t m = 0;
+  for (size_t b = 0; b < jo.point_point_glob_correspondences_.size(); ++b) m += jo.point_point_glob_correspondences_[b].points0_indices.size();
+  counts[0] = jo.point_point_glob_correspondences_.size(); counts[1] = m; counts[2] = jo.point_point_correspondences_.size(); counts[3] = jo.gradients_.size();
+  return t;
+}
+void ref_jo_get_gradient(void* hp, double* out) {
+  JointOpt& jo = ((RefJointOpt*)hp)->jo;
+  std::copy(jo.gradients_.begin(), jo.gradients_.end(), out);
+}
+
 // ---- EMInput -----------------------------------------------------------------------------------
 // EMInput::Run on world-frame clouds. ret = {n_corrected, n_anchor, backprop first, backprop second}
 void ref_em_run(uint32_t n, const uint32_t* off, const float* world_xy, float segs[8], int type, int32_t* ret, int32_t* corrected, int32_t* anchor) {

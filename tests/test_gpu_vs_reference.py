@@ -4,6 +4,8 @@ and kdtree.cpp compiled from /root/reference where they lie (stand-in Eigen/Cere
 library travels to the GPU box; nothing here reads /root/reference.  Correspondence sets, observation sets, world clouds, trees'
 answers and the back-propagated poses: bit-exact.  Residuals / Jacobians: <= 1e-9 relative (FP64), <= 1e-5 (FP32 mode).
 Solved poses: tolerance written in the test."""
+import os
+
 import numpy as np
 import pytest
 
@@ -246,3 +248,26 @@ def test_whole_correction_equals_HitLSLAM_replayLog(gpu, ref, host, maps, name, 
     assert np.abs(cov - cov_ref).max() <= 1e-6 * np.abs(cov_ref).max()     # covariances: same recurrences, endpoints differ by <= 1e-5
     assert np.abs(got - p_ref).max() <= 5e-5
     assert np.abs(gpu.world_transform(got) - w_ref).max() <= 5e-4
+
+
+@pytest.mark.skipif(not os.environ.get("HITL_DROPIN_TEST"), reason="drop-in demonstration: written after the round's GPU budget ended, not yet validated on a GPU (set HITL_DROPIN_TEST=1)")
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_reference_jointopt_with_the_hot_path_bound_to_the_c_abi(gpu, ref, maps, name):
+    """The reference's own JointOpt::PostHumanOptimization with BuildKDTrees / FindSTFCorrespondences / FindVisualOdometryCorrespondences
+    re-bound to the C ABI (oracle/_ref/libhitl_ref_dropin.so) against the same function of the unmodified CPU library: same blocks, same
+    consecutive-pose matches, bit-identical optimised poses and gradient (everything after the search is the same code on the same inputs)."""
+    from oracle.pyoracle import RefDropin
+    if not RefDropin.available():
+        pytest.skip("oracle/_ref/libhitl_ref_dropin.so not built")
+    g = maps(name)
+    n = len(g["poses"])
+    want = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"]).post_human_optimization()
+    d = RefDropin()
+    h = d.create(gpu.ctx, g["offsets"], g["pts"], g["nrm"], g["poses"])
+    try:
+        got = d.post_human_optimization(h, n)
+    finally:
+        d.destroy(h)
+    assert (got["n_blocks"], got["n_matches"], got["n_vo"]) == (want["n_blocks"], want["n_matches"], want["n_vo"])
+    assert got["termination"] == want["termination"]
+    assert np.array_equal(got["pose_array"], want["pose_array"]) and np.array_equal(got["gradient"], want["gradient"])

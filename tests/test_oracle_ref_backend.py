@@ -485,3 +485,28 @@ def test_golden_fixtures_equal_the_references_output(ref):
     sets = ref.em_observation_sets(g["offsets"], world, em["strokes"])
     for f in range(2):
         assert np.array_equal(sets[f][0], em["set%d_pose" % f]) and np.array_equal(sets[f][1], em["set%d_off" % f]) and np.array_equal(sets[f][2], em["set%d_obs" % f])
+
+
+# ---- drop-in demonstration: the reference's JointOpt bound to the product's C ABI -----------------------------------
+def test_dropin_library_routes_the_hot_path_into_the_c_abi(maps):
+    """oracle/_ref/libhitl_ref_dropin.so = the reference's JointOptimization.cpp with BuildKDTrees / FindSTFCorrespondences /
+    FindVisualOdometryCorrespondences weakened and re-defined as C-ABI calls (oracle/ref_dropin_capi.cpp).  Without a GPU context the
+    replaced BuildKDTrees must be the one that runs — and fail cleanly in hitl_set_scans, not fall back to the CPU trees."""
+    from oracle.pyoracle import RefDropin
+    if not RefDropin.available():
+        pytest.skip("oracle/_ref/libhitl_ref_dropin.so not built")
+    g = maps("tiny")
+    with pytest.raises(RuntimeError, match="hitl_set_scans"):
+        RefDropin().create(None, g["offsets"], g["pts"], g["nrm"], g["poses"])
+
+
+def test_reference_post_human_optimization_runs_on_the_cpu_library(ref, maps):
+    """The CPU side of the drop-in comparison (tests/test_gpu_vs_reference.py): PostHumanOptimization of the reference's own code."""
+    g = maps("tiny")
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    r = J.post_human_optimization()
+    want = J.find_stf(g["poses"].astype(np.float64))             # the search ran at the initial poses
+    assert r["n_blocks"] == len(want["pair_i"]) and r["n_matches"] == len(want["k"]) and r["n_vo"] > 0
+    assert len(r["gradient"]) == 3 * len(g["poses"]) and np.all(np.isfinite(r["pose_array"]))
+    assert np.array_equal(r["pose_array"][0], g["poses"][0].astype(np.float64))      # pose 0 is held constant (:1197)
+    assert np.abs(r["pose_array"] - g["poses"]).max() > 1e-4     # the solve moved the others
