@@ -554,7 +554,46 @@ def correction_latency(gpu, g, cpu=True, reps=5):
         orc.eval_odometry(consts, g["poses"].astype(np.float64))
         out["cpu_ms"] = (time.perf_counter() - t0) * 1e3
         out["cpu_what"] = "oracle port, 1 thread as in the reference: world transform + EM (same strokes, %d rounds) + odometry block evaluation" % ref["rounds"]
+        try:
+            out["cpu_reference"] = ref_correction_cpu(g, strokes)
+        except Exception as e:               # a baseline leg must never take the headline line down
+            out["cpu_reference"] = {"error": str(e)[:200]}
     return out
+
+
+def ref_correction_cpu(g, strokes):
+    """The same correction on the REFERENCE's own code (oracle/_ref/libhitl_ref_fast.so), one thread as the reference runs it, solve excluded
+    like the GPU figure: world clouds (JointOpt::CopyTempLaserScans) + EMInput::Run (E-steps, M-steps, observation sets, ordering; the call
+    includes one whole-cloud copy, as HitLSLAM.cpp:400 makes one) + AppExpCorrect::Run + Backprop::Run + the odometry and human blocks that
+    AddOdometryConstraints / AddHumanConstraints build, evaluated once through AutoDiffCostFunction.  Session set-up (cloud copies into
+    JointOpt, BuildKDTrees) is not timed.  Returns None when the library is absent."""
+    from oracle.pyoracle import RefBackend
+    if not RefBackend.available(fast=True):
+        return None
+    ref = RefBackend(fast=True)
+    n = len(g["poses"])
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    cov = np.tile(np.array([1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-5], np.float32), (n, 1))
+    t0 = time.perf_counter()
+    world = J.world_clouds()
+    t1 = time.perf_counter()
+    em = ref.em_run(g["offsets"], world, strokes)
+    t2 = time.perf_counter()
+    applied = em["backprop"][0] >= 0 and em["backprop"][1] >= 1
+    n_hc = 0
+    if applied:
+        p1, c3, hc_i, hc_f = ref.app_exp_run(4, em["segs"], g["poses"], em["corrected"], em["anchor"])
+        p2, _ = ref.backprop(p1, cov, em["backprop"][0], em["backprop"][1], c3)
+        J.set_poses(p2)
+        J.set_human_constraints([(hc_i, hc_f)])
+        n_hc = len(hc_i)
+    x = J.pose_array()
+    J.eval_blocks(0, x, n)
+    if n_hc:
+        J.eval_blocks(1, x, n_hc)
+    t3 = time.perf_counter()
+    return {"ms": (t3 - t0) * 1e3, "ms_world": (t1 - t0) * 1e3, "ms_em": (t2 - t1) * 1e3, "ms_correct_backprop_blocks": (t3 - t2) * 1e3, "human_blocks": int(n_hc),
+            "what": "reference's own code, 1 thread: CopyTempLaserScans + EMInput::Run + AppExpCorrect::Run + Backprop::Run + odometry/human blocks built and evaluated once (no solve)"}
 
 
 def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
