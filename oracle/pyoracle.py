@@ -442,6 +442,8 @@ class RefBackend:
         lib.ref_jo_post_human_optimization.restype = C.c_int
         lib.ref_jo_post_human_optimization.argtypes = [vp, _f64p, _u64p]
         lib.ref_jo_get_gradient.argtypes = [vp, _f64p]
+        lib.ref_jo_evaluate_stf_problem.restype = C.c_int64
+        lib.ref_jo_evaluate_stf_problem.argtypes = [vp, _f64p, _f64p, _f64p, C.c_uint64, _f64p]
         lib.ref_em_run.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, C.c_int, _i32p, _i32p, _i32p]
         lib.ref_em_observation_sets.argtypes = [C.c_uint32, _u32p, _f32p, _f32p, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
         lib.ref_em_dist_to_line_seg.restype = C.c_double
@@ -619,6 +621,14 @@ class RefJointOpt:
         self.lib.ref_jo_run(self.h, p, pa)
         return p.reshape(-1, 3), pa.reshape(-1, 3)
 
+    def evaluate_stf_problem(self, poses_f64, cap):
+        """FindSTFCorrespondences + AddSTFConstraints + Problem::Evaluate on the reference's own code: (cost, residuals [B, 2], gradient [N, 3])."""
+        x = np.ascontiguousarray(poses_f64, np.float64).reshape(-1)
+        cost, res, grad = np.zeros(1), np.zeros(2 * cap), np.zeros(len(x))
+        nb = int(self.lib.ref_jo_evaluate_stf_problem(self.h, x, cost, res, 2 * cap, grad))
+        assert nb >= 0, "evaluate_stf_problem: capacity too small"
+        return float(cost[0]), res[:2 * nb].reshape(-1, 2), grad.reshape(-1, 3)
+
     def post_human_optimization(self, poses_f64=None):
         """JointOpt::PostHumanOptimization on the reference's own CPU code (search + STF blocks + solve + Problem::Evaluate)."""
         if poses_f64 is not None:
@@ -668,12 +678,17 @@ class RefDropin:
     C ABI (oracle/_ref/libhitl_ref_dropin.so, oracle/ref_dropin_capi.cpp): the drop-in demonstration.  Needs a hitl_ctx (a B200)."""
 
     @staticmethod
-    def available():
-        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref_dropin.so"))
+    def available(blocks=False):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhitl_ref_dropin_blocks.so" if blocks else "libhitl_ref_dropin.so"))
 
-    def __init__(self):
-        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref_dropin.so"))
+    def __init__(self, blocks=False):
+        """blocks=True: the library that also replaces AddSTFConstraints with GPU-backed cost blocks (one batched hitl_eval per point)."""
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libhitl_ref_dropin_blocks.so" if blocks else "libhitl_ref_dropin.so"))
         vp = C.c_void_p
+        lib.dropin_evaluate_stf_problem.restype = C.c_int64
+        lib.dropin_evaluate_stf_problem.argtypes = [vp, _f64p, _f64p, _f64p, C.c_uint64, _f64p, C.c_char_p, C.c_size_t]
+        lib.dropin_has_gpu_blocks.restype = C.c_int
+        lib.dropin_last_batches.restype = C.c_uint64
         lib.dropin_create.restype = vp
         lib.dropin_create.argtypes = [vp, C.c_uint32, _u32p, _f32p, _f32p, _f32p, C.c_char_p, C.c_size_t]
         lib.dropin_destroy.argtypes = [vp]
@@ -696,6 +711,15 @@ class RefDropin:
 
     def destroy(self, h):
         self.lib.dropin_destroy(h)
+
+    def evaluate_stf_problem(self, h, poses_f64, cap):
+        """Search + AddSTFConstraints + Problem::Evaluate at poses_f64: (cost, residuals [B, 2], gradient [N, 3])."""
+        x = np.ascontiguousarray(poses_f64, np.float64).reshape(-1)
+        cost, res, grad, err = np.zeros(1), np.zeros(2 * cap), np.zeros(len(x)), C.create_string_buffer(512)
+        nb = int(self.lib.dropin_evaluate_stf_problem(h, x, cost, res, 2 * cap, grad, err, 512))
+        if nb < 0:
+            raise RuntimeError(err.value.decode())
+        return float(cost[0]), res[:2 * nb].reshape(-1, 2), grad.reshape(-1, 3)
 
     def post_human_optimization(self, h, n_poses, poses_f64=None):
         if poses_f64 is not None:

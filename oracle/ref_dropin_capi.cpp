@@ -17,6 +17,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -114,6 +115,65 @@ void JointOpt::FindVisualOdometryCorrespondences(int min_poses, int max_poses) {
   }
 }
 
+#ifdef DROPIN_GPU_BLOCKS
+// ---- fourth replaced member (libhitl_ref_dropin_blocks.so only): the STF cost blocks ----------------------------------------
+// JointOpt::AddSTFConstraints (:539-559) registers one AutoDiffCostFunction<PointToPointGlobConstraint, 2, 3, 3> per kept pair.  Here
+// the same AddResidualBlock calls are made with GPU-backed SizedCostFunction<2, 3, 3> objects: ONE batched hitl_eval per evaluation
+// point fills a staging buffer, every block's Evaluate copies its slice (the shape SURVEY.md 8b describes).  Without an
+// EvaluationCallback in the Ceres API slice of shim3 the batch is triggered by the first Evaluate that sees a changed pose array.
+namespace {
+struct GpuBatch {
+  hitl_ctx* ctx;
+  const std::vector<double>* pose_array;
+  std::vector<double> at, r, J;       // evaluation point of the cached batch, residuals (2 per block), Jacobians (12 per block)
+  uint64_t n_blocks;
+  uint64_t n_batches;
+  void Refresh() {
+    if (at.size() == pose_array->size() && memcmp(at.data(), pose_array->data(), sizeof(double) * at.size()) == 0) return;
+    at = *pose_array;
+    check(hitl_eval(ctx, at.data(), /*precision FP64*/ 0, r.data(), J.data(), NULL), "hitl_eval");
+    ++n_batches;
+  }
+};
+uint64_t g_last_batches = 0;
+class GpuStfBlock : public ceres::SizedCostFunction<2, 3, 3> {
+ public:
+  GpuStfBlock(const std::shared_ptr<GpuBatch>& batch, uint64_t block) : batch_(batch), block_(block) {}
+  ~GpuStfBlock() override { g_last_batches = batch_->n_batches; }
+  bool Evaluate(double const* const* /*parameters: slices of the pose array the batch already saw*/, double* residuals, double** jacobians) const override {
+    try { batch_->Refresh(); } catch (const std::exception&) { return false; }
+    residuals[0] = batch_->r[2 * block_]; residuals[1] = batch_->r[2 * block_ + 1];
+    if (jacobians) {
+      const double* Jb = &batch_->J[12 * block_];          // [2x3 wrt pose_index0 | 2x3 wrt pose_index1], row-major
+      if (jacobians[0]) memcpy(jacobians[0], Jb, 6 * sizeof(double));
+      if (jacobians[1]) memcpy(jacobians[1], Jb + 6, 6 * sizeof(double));
+    }
+    return true;
+  }
+ private:
+  std::shared_ptr<GpuBatch> batch_;
+  uint64_t block_;
+};
+}  // namespace
+
+void JointOpt::AddSTFConstraints(ceres::Problem* problem) {
+  // the blocks are the kept pairs of the last hitl_find_stf on this context, in the order FindSTFCorrespondences listed them
+  check(hitl_set_odometry_blocks(g_ctx, 0, NULL), "hitl_set_odometry_blocks");
+  check(hitl_set_human_blocks(g_ctx, 0, NULL, NULL), "hitl_set_human_blocks");
+  check(hitl_set_stf_blocks_from_search(g_ctx, localization_options_.kLaserStdDev, localization_options_.kPointPointCorrelationFactor), "hitl_set_stf_blocks_from_search");
+  hitl_eval_layout L;
+  check(hitl_eval_layout_get(g_ctx, &L), "hitl_eval_layout_get");
+  if (L.n_stf != point_point_glob_correspondences_.size()) throw std::runtime_error("AddSTFConstraints: block count differs from the search result");
+  std::shared_ptr<GpuBatch> batch(new GpuBatch());
+  batch->ctx = g_ctx; batch->pose_array = &pose_array_; batch->n_blocks = L.n_stf; batch->n_batches = 0;
+  batch->r.assign(L.n_residuals + 1, 0.0); batch->J.assign(L.n_jacobian + 1, 0.0);
+  for (size_t b = 0; b < point_point_glob_correspondences_.size(); ++b) {
+    const vector_localization::VectorMapping::PointToPointGlobCorrespondence& c = point_point_glob_correspondences_[b];
+    problem->AddResidualBlock(new GpuStfBlock(batch, b), NULL, &(pose_array_[3 * c.pose_index0]), &(pose_array_[3 * c.pose_index1]));
+  }
+}
+#endif  // DROPIN_GPU_BLOCKS
+
 // ---- harness ----------------------------------------------------------------------------------------------------------
 namespace {
 struct Dropin {
@@ -184,6 +244,51 @@ int dropin_post_human_optimization(void* p, double* pose_array_out, uint64_t cou
     if (err && err_cap) snprintf(err, err_cap, "%s", e.what());
     return -1;
   }
+}
+// Builds the STF problem at `pose_array` (search + AddSTFConstraints, whichever definitions this library links) and evaluates it once
+// through Problem::Evaluate: cost, residuals (2 per block) and the gradient over all poses.  Returns the number of blocks, -1 on error.
+int64_t dropin_evaluate_stf_problem(void* p, const double* pose_array, double* cost, double* residuals, uint64_t res_cap, double* gradient, char* err, size_t err_cap) {
+  Quiet q;
+  Dropin* d = static_cast<Dropin*>(p);
+  try {
+    std::copy(pose_array, pose_array + d->jo.pose_array_.size(), d->jo.pose_array_.begin());
+    d->jo.FindSTFCorrespondences(0, d->jo.pose_array_.size() / 3 - 1);
+    ceres::Problem problem;
+    d->jo.AddSTFConstraints(&problem);
+    problem.SetParameterBlockConstant(&d->jo.pose_array_[0]);
+    std::vector<double> res, grad;
+    ceres::CRSMatrix jac;
+    problem.Evaluate(ceres::Problem::EvaluateOptions(), cost, &res, &grad, &jac);
+    if (res.size() > res_cap) throw std::runtime_error("dropin_evaluate_stf_problem: residual buffer too small");
+    std::copy(res.begin(), res.end(), residuals);
+    // Problem::Evaluate orders the gradient by parameter block in insertion order: scatter it back to pose order
+    std::fill(gradient, gradient + d->jo.pose_array_.size(), 0.0);
+    const std::vector<double*>& order = problem.parameter_blocks();
+    for (size_t i = 0; i < order.size(); ++i) {
+      const size_t pose = (size_t)(order[i] - &d->jo.pose_array_[0]) / 3;
+      for (int e = 0; e < 3; ++e) gradient[3 * pose + e] = grad[3 * i + e];
+    }
+    return (int64_t)problem.NumResidualBlocks();
+  } catch (const std::exception& e) {
+    if (err && err_cap) snprintf(err, err_cap, "%s", e.what());
+    return -1;
+  }
+}
+// 1 when this library also replaces AddSTFConstraints with GPU-backed cost blocks
+int dropin_has_gpu_blocks(void) {
+#ifdef DROPIN_GPU_BLOCKS
+  return 1;
+#else
+  return 0;
+#endif
+}
+// batched hitl_eval calls made by the cost blocks of the last destroyed Problem (GPU-block library only)
+uint64_t dropin_last_batches(void) {
+#ifdef DROPIN_GPU_BLOCKS
+  return g_last_batches;
+#else
+  return 0;
+#endif
 }
 void dropin_get_gradient(void* p, double* out) {
   JointOpt& jo = static_cast<Dropin*>(p)->jo;

@@ -249,6 +249,28 @@ int ref_jo_post_human_optimization(void* hp, double* pose_array_out, uint64_t co
   counts[0] = jo.point_point_glob_correspondences_.size(); counts[1] = m; counts[2] = jo.point_point_correspondences_.size(); counts[3] = jo.gradients_.size();
   return t;
 }
+// The CPU counterpart of dropin_evaluate_stf_problem: FindSTFCorrespondences + AddSTFConstraints + Problem::Evaluate, all reference code.
+int64_t ref_jo_evaluate_stf_problem(void* hp, const double* pose_array, double* cost, double* residuals, uint64_t res_cap, double* gradient) {
+  Quiet q;
+  JointOpt& jo = ((RefJointOpt*)hp)->jo;
+  std::copy(pose_array, pose_array + jo.pose_array_.size(), jo.pose_array_.begin());
+  jo.FindSTFCorrespondences(0, jo.pose_array_.size() / 3 - 1);
+  ceres::Problem problem;
+  jo.AddSTFConstraints(&problem);
+  problem.SetParameterBlockConstant(&jo.pose_array_[0]);
+  std::vector<double> res, grad;
+  ceres::CRSMatrix jac;
+  problem.Evaluate(ceres::Problem::EvaluateOptions(), cost, &res, &grad, &jac);
+  if (res.size() > res_cap) return -1;
+  std::copy(res.begin(), res.end(), residuals);
+  std::fill(gradient, gradient + jo.pose_array_.size(), 0.0);
+  const std::vector<double*>& order = problem.parameter_blocks();
+  for (size_t i = 0; i < order.size(); ++i) {
+    const size_t pose = (size_t)(order[i] - &jo.pose_array_[0]) / 3;
+    for (int e = 0; e < 3; ++e) gradient[3 * pose + e] = grad[3 * i + e];
+  }
+  return (int64_t)problem.NumResidualBlocks();
+}
 void ref_jo_get_gradient(void* hp, double* out) {
   JointOpt& jo = ((RefJointOpt*)hp)->jo;
   std::copy(jo.gradients_.begin(), jo.gradients_.end(), out);

@@ -510,3 +510,26 @@ def test_reference_post_human_optimization_runs_on_the_cpu_library(ref, maps):
     assert len(r["gradient"]) == 3 * len(g["poses"]) and np.all(np.isfinite(r["pose_array"]))
     assert np.array_equal(r["pose_array"][0], g["poses"][0].astype(np.float64))      # pose 0 is held constant (:1197)
     assert np.abs(r["pose_array"] - g["poses"]).max() > 1e-4     # the solve moved the others
+
+
+def test_reference_stf_problem_evaluation_matches_the_oracle(oracle, ref, maps):
+    """Problem::Evaluate of the STF problem the reference builds (cost, residuals, gradient over poses) against the oracle's blocks: the CPU
+    side of the cost-block drop-in comparison."""
+    g = maps("tiny")
+    x = jittered(g, 31)
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    cost, res, grad = J.evaluate_stf_problem(x, 4096)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    corr = S.find_stf(x)
+    r, Jb = S.eval_stf(x, corr)
+    assert close(res, r) and abs(cost - 0.5 * (r ** 2).sum()) <= 1e-12 * cost
+    want = np.zeros_like(x)
+    for b in range(len(r)):
+        i, j = int(corr["pair_i"][b]), int(corr["pair_j"][b])
+        want[i] += Jb[b, 0].T @ r[b]
+        want[j] += Jb[b, 1].T @ r[b]
+    want[0] = 0.0                                              # pose 0 is constant (:1197)
+    assert close(grad, want, 1e-10)
+    from oracle.pyoracle import RefDropin
+    if RefDropin.available(blocks=True):
+        assert RefDropin(blocks=True).lib.dropin_has_gpu_blocks() == 1 and RefDropin().lib.dropin_has_gpu_blocks() == 0
