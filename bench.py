@@ -442,13 +442,24 @@ def main():
     o_stf = (gpu.pinned(npair + 1, np.uint32), gpu.pinned(npair + 1, np.uint32), gpu.pinned(npair + 2, np.uint64), gpu.pinned(nmatch + 1, np.uint32), gpu.pinned(nmatch + 1, np.uint32))
     n_res, n_jac = 3 * len(odo) + 2 * npair, 18 * len(odo) + 12 * npair
     o_ev = (gpu.pinned(n_res + 1, np.float64), gpu.pinned(n_jac + 1, np.float64))
-    h2d = h_pts.nbytes + h_nrm.nbytes + h_nodes.nbytes + h_off.nbytes + h_poses.nbytes * 2 + h_odo.nbytes
+    # Opt-in (HITL_E2E_COMPACT=1, not the default until it has been validated on a GPU): the compact boundary formats — trees as one u32
+    # per node (the points are already uploaded with the scans) and 16-bit point indices in the correspondence lists.
+    compact = bool(os.environ.get("HITL_E2E_COMPACT"))
+    if compact:
+        h_compact = gpu.pinned_copy((nodes["index"].astype(np.uint32) & 0x7FFFFFFF) | (nodes["dim"].astype(np.uint32) << 31))
+        o_stf16 = (o_stf[0], o_stf[1], o_stf[2], gpu.pinned(nmatch + 1, np.uint16), gpu.pinned(nmatch + 1, np.uint16))
+    h2d = h_pts.nbytes + h_nrm.nbytes + (h_compact.nbytes if compact else h_nodes.nbytes) + h_off.nbytes + h_poses.nbytes * 2 + h_odo.nbytes
     d2h = 0
 
     def e2e_step():
         gpu.set_scans(h_off, h_pts, h_nrm)
-        gpu.set_kdtrees(h_nodes)
-        out = gpu.find_stf(h_poses, src_lo=lo, src_hi=hi, fetch=True, out=o_stf)
+        if compact:
+            gpu.set_kdtrees_compact(h_compact)
+            info_c = gpu.find_stf(h_poses, src_lo=lo, src_hi=hi, fetch=False)
+            out = gpu.get_stf16(info_c["n_pairs"], info_c["n_matches"], out=o_stf16)
+        else:
+            gpu.set_kdtrees(h_nodes)
+            out = gpu.find_stf(h_poses, src_lo=lo, src_hi=hi, fetch=True, out=o_stf)
         gpu.set_odometry_blocks(h_odo)
         gpu.set_stf_blocks_from_search(STD_DEV, CORR)
         ev = gpu.eval(h_poses, fetch=True, out=o_ev)
@@ -468,7 +479,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": evals / float(te.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
-           "timing": "host wall clock around the synchronous C-ABI calls (every call ends with a stream sync), pinned host buffers, max over ranks"}
+           "timing": "host wall clock around the synchronous C-ABI calls (every call ends with a stream sync), pinned host buffers, max over ranks",
+           "formats": "compact (u32 tree nodes, u16 point indices)" if compact else "hitl_kdnode trees (24 B/node), u32 point indices"}
 
     # ---- correction latency (second half of the BASELINE metric): one human correction on this map ----
     correction = None

@@ -25,8 +25,8 @@ KDNODE = np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), (
 ABI_SYMBOLS = [
     "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count",
     "hitl_host_alloc", "hitl_host_free",
-    "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_kd_query",
-    "hitl_find_stf", "hitl_get_stf", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
+    "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_set_kdtrees_compact", "hitl_get_kdtrees_compact", "hitl_kd_query",
+    "hitl_find_stf", "hitl_get_stf", "hitl_get_stf16", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
@@ -105,6 +105,9 @@ class HitlGpu:
         lib.hitl_set_world_clouds.argtypes = [vp, _f32p]
         lib.hitl_em_inliers.argtypes = [vp, _f32p, C.c_double, C.c_uint64, vp, vp, vp, C.POINTER(C.c_uint64)]
         lib.hitl_em_assign.argtypes = [vp, _f32p, C.c_double, C.c_uint32, _u32p, _u32p, _u64p, _u32p, _u32p, _u64p, _u32p]
+        lib.hitl_set_kdtrees_compact.argtypes = [vp, C.c_void_p]
+        lib.hitl_get_kdtrees_compact.argtypes = [vp, C.c_void_p]
+        lib.hitl_get_stf16.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hitl_verify_input.argtypes = [vp, C.c_uint32, _f32p, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.hitl_set_stf_blocks_from_search.argtypes = [vp, C.c_float, C.c_float]
         lib.hitl_set_stf_blocks.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_float, C.c_float]
@@ -188,6 +191,23 @@ class HitlGpu:
     def set_kdtrees(self, nodes):
         nodes = np.ascontiguousarray(nodes, KDNODE)
         self._ck(self.lib.hitl_set_kdtrees(self.ctx, nodes.ctypes.data))
+
+    def set_kdtrees_compact(self, index_dim):
+        """Trees as one u32 per node (index | dim << 31, preorder): the points and normals are taken from the resident scans."""
+        self._ck(self.lib.hitl_set_kdtrees_compact(self.ctx, np.ascontiguousarray(index_dim, np.uint32).ctypes.data_as(C.c_void_p)))
+
+    def get_kdtrees_compact(self, out=None):
+        out = np.zeros(max(self.n_points, 1), np.uint32) if out is None else out
+        self._ck(self.lib.hitl_get_kdtrees_compact(self.ctx, out.ctypes.data_as(C.c_void_p)))
+        return out[:self.n_points]
+
+    def get_stf16(self, n_pairs, n_matches, out=None):
+        """hitl_get_stf with 16-bit point indices; out = (pair_i u32, pair_j u32, pair_off u64, k u16, idx u16) buffers or None."""
+        if out is None:
+            out = (np.zeros(n_pairs + 1, np.uint32), np.zeros(n_pairs + 1, np.uint32), np.zeros(n_pairs + 2, np.uint64), np.zeros(n_matches + 1, np.uint16), np.zeros(n_matches + 1, np.uint16))
+        vp = C.c_void_p
+        self._ck(self.lib.hitl_get_stf16(self.ctx, out[0].ctypes.data_as(vp), out[1].ctypes.data_as(vp), out[2].ctypes.data_as(vp), out[3].ctypes.data_as(vp), out[4].ctypes.data_as(vp)))
+        return dict(pair_i=out[0][:n_pairs], pair_j=out[1][:n_pairs], pair_off=out[2][:n_pairs + 1], k=out[3][:n_matches], idx=out[4][:n_matches])
 
     def get_kdtrees(self):
         nodes = np.zeros(max(self.n_points, 1), KDNODE)

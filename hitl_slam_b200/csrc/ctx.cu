@@ -359,6 +359,66 @@ extern "C" int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* out) {
   return HITL_OK;
 }
 
+// ---- compact tree format: 4 B per node instead of 24 ----------------------------------------------
+// A flattened tree is a permutation of its scan's points plus one split bit per node; the points and normals are already resident
+// (hitl_set_scans), so (index | dim << 31) per node in preorder is the whole tree: 14 MB instead of 86 MB across PCIe at c2.
+namespace hitl {
+__global__ void expand_nodes_kernel(const uint32_t* __restrict__ compact, const float2* __restrict__ pts, const float2* __restrict__ nrm,
+                                    const uint32_t* __restrict__ off, uint32_t n_poses, uint64_t m, float4* __restrict__ pm, float2* __restrict__ nn,
+                                    uint32_t* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t w = compact[i], index = w & 0x7FFFFFFFu;
+  uint32_t lo = 0, hi = n_poses;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+  const uint32_t base = off[lo], n = off[lo + 1] - base;
+  if (index >= n) { atomicOr(bad, 1u); return; }
+  const float2 p = pts[base + index];
+  pm[i] = make_float4(p.x, p.y, __uint_as_float(w), 0.0f);
+  nn[i] = nrm[base + index];
+}
+__global__ void compact_nodes_kernel(const float4* __restrict__ pm, uint64_t m, uint32_t* __restrict__ compact) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) compact[i] = __float_as_uint(pm[i].z);
+}
+}  // namespace hitl
+
+extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_kdtrees_compact: call hitl_set_scans first");
+  const size_t m = ctx->n_points;
+  if (!index_dim && m) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees_compact: null nodes");
+  HITL_CUDA(ctx->d_node_pm.ensure(m)); HITL_CUDA(ctx->d_node_nn.ensure(m));
+  ctx->have_trees = false;
+  if (m) {
+    HITL_CUDA(ctx->d_tile_keys.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(4));      // d_tile_keys: u32 scratch, rewritten by every search
+    HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_keys.p, index_dim, 4 * m, cudaMemcpyHostToDevice, ctx->stream));
+    expand_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tile_keys.p, ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, ctx->n_poses, m,
+                                                                              ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_ticket.p);
+    HITL_LAUNCH_CHECK("expand_nodes_kernel");
+    HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_ticket.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*(const uint32_t*)ctx->h_pinned) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees_compact: node index out of range");
+  }
+  ctx->have_trees = true;
+  return HITL_OK;
+}
+
+extern "C" int hitl_get_kdtrees_compact(hitl_ctx* ctx, uint32_t* index_dim_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_get_kdtrees_compact: trees not built");
+  const size_t m = ctx->n_points;
+  if (!m) return HITL_OK;
+  if (!index_dim_out) return fail(ctx, HITL_ERR_ARG, "hitl_get_kdtrees_compact: null output");
+  HITL_CUDA(ctx->d_tile_keys.ensure(m));
+  compact_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pm.p, m, ctx->d_tile_keys.p);
+  HITL_LAUNCH_CHECK("compact_nodes_kernel");
+  HITL_CUDA(cudaMemcpyAsync(index_dim_out, ctx->d_tile_keys.p, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
 // ---- diagnostics ---------------------------------------------------------------------------------
 namespace hitl {
 __global__ void debug_sincos_kernel(const float* __restrict__ x, uint64_t n, float* __restrict__ s, float* __restrict__ c) {

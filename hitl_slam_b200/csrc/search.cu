@@ -1381,6 +1381,39 @@ extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, u
   return HITL_OK;
 }
 
+// Point indices as 16-bit values (scans hold at most 65534 points, hitl_set_scans): half the bytes of the two largest result arrays.
+namespace hitl {
+__global__ void pack_u16_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint64_t n, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b) {
+  // one thread packs two consecutive entries of each array into one 32-bit word
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, i = 2 * w;
+  if (i >= n) return;
+  const uint32_t a0 = a[i], b0 = b[i], a1 = i + 1 < n ? a[i + 1] : 0u, b1 = i + 1 < n ? b[i + 1] : 0u;
+  out_a[w] = (a0 & 0xFFFFu) | (a1 << 16);
+  out_b[w] = (b0 & 0xFFFFu) | (b1 << 16);
+}
+}  // namespace hitl
+extern "C" int hitl_get_stf16(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint16_t* k, uint16_t* idx) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf16: no search result");
+  const uint64_t np = ctx->n_pairs, nm = ctx->n_matches;
+  if (pair_off && np == 0) pair_off[0] = 0;
+  if (np) {
+    if (pair_i) HITL_CUDA(cudaMemcpyAsync(pair_i, ctx->d_pair_i.p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_j) HITL_CUDA(cudaMemcpyAsync(pair_j, ctx->d_pair_j.p, 4 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_off) HITL_CUDA(cudaMemcpyAsync(pair_off, ctx->d_pair_off.p, 8 * (np + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (nm && (k || idx)) {
+    // staging: the raw record columns are free once the search has been ordered (d_raw_k / d_raw_idx hold >= n_matches words)
+    const uint64_t words = (nm + 1) / 2;
+    pack_u16_kernel<<<(uint32_t)((words + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_k.p, ctx->d_idx.p, nm, ctx->d_raw_k.p, ctx->d_raw_idx.p);
+    HITL_LAUNCH_CHECK("pack_u16_kernel");
+    if (k) HITL_CUDA(cudaMemcpyAsync(k, ctx->d_raw_k.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idx) HITL_CUDA(cudaMemcpyAsync(idx, ctx->d_raw_idx.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
 extern "C" int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose) {
   if (!ctx) return HITL_ERR_ARG;
   if (!ctx->have_stf || !ctx->d_pose_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf_work: no search result");

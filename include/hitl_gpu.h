@@ -81,6 +81,10 @@ int hitl_build_kdtrees(hitl_ctx* ctx);
 /* Or adopt trees built elsewhere (same layout, concatenated by scan_offsets). */
 int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes);
 int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* nodes_out);
+/* Compact form of the same trees: one 32-bit word per node in preorder, index | dim << 31.  The node's point and normal are the
+ * scan's entries at `index`, which hitl_set_scans already made resident, so this is the whole tree at 4 B per node (24 B in hitl_kdnode). */
+int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim);
+int hitl_get_kdtrees_compact(hitl_ctx* ctx, uint32_t* index_dim_out);
 
 /* The same builder for one scan without a context (pure host code; used by tests and by callers
  * that want to inspect a tree).  out must hold n nodes. */
@@ -129,6 +133,8 @@ int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t min_pose, ui
 /* CSR copy-out in the reference's order (pose_index0 asc, pose_index1 asc, points0 index asc):
  * pair_i/pair_j [n_pairs], pair_off [n_pairs+1], k/idx [n_matches]. */
 int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx);
+/* The same with 16-bit point indices (a scan holds at most 65534 points): half the bytes of the two largest arrays across PCIe. */
+int hitl_get_stf16(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint16_t* k, uint16_t* idx);
 
 /* Load-balancing feedback: SM cycles the last hitl_find_stf spent on each source pose (0 outside the
  * searched source range).  work_per_pose holds n_poses entries.  Multi-GPU callers sum these over the
