@@ -76,7 +76,8 @@ typedef struct {
 } hitl_kdnode;
 
 /* Build every scan's tree with the reference's algorithm (max-variance split, std::sort,
- * median n/2) and make it resident.  v1 builds on the host side of the library. */
+ * median n/2) and make it resident.  Built on the device, all scans at once, with the reference's exact
+ * tree shape (equal keys included); hitl_debug_set_tree_builder(ctx, 1) selects the threaded host builder. */
 int hitl_build_kdtrees(hitl_ctx* ctx);
 /* Or adopt trees built elsewhere (same layout, concatenated by scan_offsets). */
 int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes);
