@@ -90,7 +90,6 @@ def test_kd_queries_match_oracle(gpu, oracle, n):
             assert np.array_equal(cnt, ref)
 
 
-@pytest.mark.skipif(not os.environ.get("HITL_COMPACT_TEST"), reason="compact boundary formats: written after the round's GPU budget ended, not yet validated on a GPU (set HITL_COMPACT_TEST=1)")
 def test_compact_tree_and_index_formats(gpu, oracle, maps):
     """hitl_set/get_kdtrees_compact (index | dim << 31 per node) reproduce the 24-byte node form bit for bit, a search over trees uploaded in the
     compact form returns the same lists, and hitl_get_stf16 returns the same indices in 16 bits."""

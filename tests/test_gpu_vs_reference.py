@@ -250,7 +250,6 @@ def test_whole_correction_equals_HitLSLAM_replayLog(gpu, ref, host, maps, name, 
     assert np.abs(gpu.world_transform(got) - w_ref).max() <= 5e-4
 
 
-@pytest.mark.skipif(not os.environ.get("HITL_DROPIN_TEST"), reason="drop-in demonstration: written after the round's GPU budget ended, not yet validated on a GPU (set HITL_DROPIN_TEST=1)")
 @pytest.mark.parametrize("name", ["tiny", "small"])
 def test_reference_jointopt_with_the_hot_path_bound_to_the_c_abi(gpu, ref, maps, name):
     """The reference's own JointOpt::PostHumanOptimization with BuildKDTrees / FindSTFCorrespondences / FindVisualOdometryCorrespondences
@@ -273,7 +272,6 @@ def test_reference_jointopt_with_the_hot_path_bound_to_the_c_abi(gpu, ref, maps,
     assert np.array_equal(got["pose_array"], want["pose_array"]) and np.array_equal(got["gradient"], want["gradient"])
 
 
-@pytest.mark.skipif(not os.environ.get("HITL_DROPIN_TEST"), reason="drop-in demonstration: written after the round's GPU budget ended, not yet validated on a GPU (set HITL_DROPIN_TEST=1)")
 def test_reference_jointopt_with_gpu_cost_blocks(gpu, ref, maps):
     """The north-star claim, literally: the reference's own JointOpt builds its STF problem with GPU-backed cost blocks (AddSTFConstraints
     re-bound, one batched hitl_eval per evaluation point behind SizedCostFunction<2,3,3>::Evaluate) and evaluates / solves it through the
