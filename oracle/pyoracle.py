@@ -272,6 +272,24 @@ class OracleScans:
         self.lib.orc_get_stf(self.h, pi, pj, off, k, idx)
         return dict(pair_i=pi, pair_j=pj, pair_off=off, k=k, idx=idx, n_queries=int(counts[2]))
 
+    def check_chunks(self, result, poses, chunks, **opts):
+        """Checker for searches too large to repeat on the CPU as a whole: for every [lo, hi) source-pose chunk, run the oracle's
+        FindSTFCorrespondences over those sources against ALL targets and compare bit for bit with the rows of `result` (a CSR in
+        the reference's (i, j, k) order, e.g. hitl_get_stf of a full-map or shard search) whose source pose lies in the chunk.
+        Returns the list of (lo, hi, ok, n_pairs, n_matches)."""
+        pi = np.asarray(result["pair_i"]); pj = np.asarray(result["pair_j"]); off = np.asarray(result["pair_off"]).astype(np.int64)
+        rk = np.asarray(result["k"]); ridx = np.asarray(result["idx"])
+        out = []
+        for lo, hi in chunks:
+            want = self.find_stf(poses, src_lo=lo, src_hi=hi, **opts)
+            a, b = np.searchsorted(pi, lo, side="left"), np.searchsorted(pi, hi, side="left")
+            m0, m1 = int(off[a]), int(off[b])
+            ok = (np.array_equal(pi[a:b], want["pair_i"]) and np.array_equal(pj[a:b], want["pair_j"])
+                  and np.array_equal(off[a:b + 1] - m0, want["pair_off"].astype(np.int64))
+                  and np.array_equal(rk[m0:m1], want["k"]) and np.array_equal(ridx[m0:m1], want["idx"]))
+            out.append((int(lo), int(hi), bool(ok), int(b - a), int(m1 - m0)))
+        return out
+
     def find_vo(self, poses, min_pose=0, max_pose=None, thr=0.15, min_cos=None):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
         if max_pose is None:
@@ -430,6 +448,7 @@ class RefBackend:
         lib.ref_jo_world_clouds.argtypes = [vp, _f32p]
         lib.ref_jo_relative_pose.argtypes = [vp, C.c_uint32, _u32p, _u32p, _f32p]
         lib.ref_jo_find_stf.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p]
+        lib.ref_jo_restrict_sources.argtypes = [vp, C.c_uint32, _u32p]
         lib.ref_jo_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p, C.c_void_p]
         lib.ref_jo_find_vo.restype = C.c_uint64
         lib.ref_jo_find_vo.argtypes = [vp, C.c_int, C.c_int]
@@ -565,6 +584,12 @@ class RefJointOpt:
         out = np.zeros(6 * len(src), np.float32)
         self.lib.ref_jo_relative_pose(self.h, len(src), src, dst, out)
         return out.reshape(-1, 6)
+
+    def restrict_sources(self, keep=None):
+        """Timing samples of a full map: the reference's own FindSTFCorrespondences then searches only the kept SOURCE poses, against all
+        targets (ref_jo_restrict_sources parks the other poses' point_clouds_g_ entries; None restores them)."""
+        ids = np.ascontiguousarray(keep if keep is not None else [], np.uint32)
+        self.lib.ref_jo_restrict_sources(self.h, len(ids), ids)
 
     def find_stf(self, poses_f64=None, min_pose=0, max_pose=None, with_points=False):
         if poses_f64 is not None:

@@ -64,6 +64,7 @@ struct RefJointOpt {
   JointOpt jo;
   cimg_library::CImg<float> info;
   std::vector<ceres::Problem::Block> recorded;
+  std::vector<std::vector<vector2f> > parked_sources;   // point_clouds_g_ entries parked by ref_jo_restrict_sources
 };
 
 }  // namespace
@@ -135,6 +136,24 @@ void ref_jo_relative_pose(void* hp, uint32_t n_pairs, const uint32_t* src, const
     out6[6 * p + 0] = T.linear()(0, 0); out6[6 * p + 1] = T.linear()(0, 1); out6[6 * p + 2] = T.linear()(1, 0); out6[6 * p + 3] = T.linear()(1, 1);
     out6[6 * p + 4] = T.translation()(0); out6[6 * p + 5] = T.translation()(1);
   }
+}
+// Bounded SAMPLE of the full-map search for timing: JointOpt::FindSTFCorrespondences takes the SOURCE point count of pose i from
+// point_clouds_g_[i].size() (:577, :593) and everything about the TARGETS from kdtrees_[j] / robot_frame_point_clouds_[j], so
+// parking the point_clouds_g_ entry of every pose outside `keep` makes the reference's own, unmodified loop search exactly the
+// kept source poses against ALL target poses of the full map (each source pose is independent: private cap counters, :577).
+// keep == NULL or n_keep == 0 restores every pose.
+void ref_jo_restrict_sources(void* hp, uint32_t n_keep, const uint32_t* keep) {
+  RefJointOpt* h = (RefJointOpt*)hp;
+  JointOpt& jo = h->jo;
+  const size_t n = jo.point_clouds_g_.size();
+  if (h->parked_sources.size() != n) h->parked_sources.assign(n, std::vector<vector2f>());
+  for (size_t i = 0; i < n; ++i)
+    if (jo.point_clouds_g_[i].empty() && !h->parked_sources[i].empty()) jo.point_clouds_g_[i].swap(h->parked_sources[i]);   // restore
+  if (!keep || n_keep == 0) return;
+  std::vector<char> kept(n, 0);
+  for (uint32_t q = 0; q < n_keep; ++q) if (keep[q] < n) kept[keep[q]] = 1;
+  for (size_t i = 0; i < n; ++i)
+    if (!kept[i]) jo.point_clouds_g_[i].swap(h->parked_sources[i]);
 }
 // counts[0] = kept pose pairs, counts[1] = matches in them
 void ref_jo_find_stf(void* hp, uint64_t min_pose, uint64_t max_pose, uint64_t* counts) {

@@ -597,3 +597,51 @@ def test_error_paths(gpu):
     with pytest.raises(HitlError):
         fresh.set_human_blocks(np.array([[3, 0]], np.int32), np.zeros((1, 4)))   # corner type unsupported, as in the reference
     fresh.close()
+
+
+# ---- the benchmarked workloads themselves (BASELINE configs 2 and 3 at full size) -------------------------
+def _spread_chunks(n, n_chunks, width):
+    """Source-pose chunks spread over the trajectory, the first and the LAST poses included (late poses see every earlier lap: heaviest tiles)."""
+    return [(int(lo), int(lo) + width) for lo in np.linspace(0, n - width, n_chunks).astype(np.int64)]
+
+
+@pytest.mark.parametrize("name,n_chunks", [("c2", 10), ("c3", 5)])
+def test_find_stf_full_size_matches_oracle_on_chunks(gpu, oracle, maps, name, n_chunks):
+    """c2 (5 000 x 720) and c3 (20 000 x 1080) exactly as bench.py runs them.  The whole map is too large for the oracle, so the oracle
+    searches 16-pose source chunks against ALL targets and the rows of the GPU result whose source lies in the chunk must be identical
+    (pairs, offsets, k, idx).  The GPU search is compared after >= 4 warm-up calls, i.e. with adaptive re-tiling, target-axis splits of
+    heavy tiles and heaviest-first tickets live — the machinery that only engages at scale — first over the whole map (world = 1), then
+    on the first / a middle / the last source shard of an 8-way cut (world = 8), each with its own warm-up."""
+    from hitl_slam_b200.sharding import shard_ranges
+    g = maps(name)
+    load_map(gpu, g)
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    tiles0 = None
+    for _ in range(4):
+        info = gpu.find_stf(poses, fetch=False)
+        tiles0 = tiles0 or info["n_tiles"]
+    res = gpu.find_stf(poses)
+    assert res["n_tiles"] >= tiles0
+    checks = S.check_chunks(res, poses, _spread_chunks(n, n_chunks, 16))
+    assert all(c[2] for c in checks), checks
+    assert sum(c[4] for c in checks) > 1000
+    # size-independent properties over the WHOLE result: pairs sorted by (i, j), > 10 matches per pair, <= cap matches per source point
+    counts = np.diff(res["pair_off"].astype(np.int64))
+    assert (counts > 10).all()
+    assert (np.diff(res["pair_i"].astype(np.int64) * (1 << 32) + res["pair_j"]) > 0).all()
+    per_point = np.bincount(g["offsets"].astype(np.int64)[res["pair_i"]].repeat(counts) + res["k"], minlength=int(g["offsets"][-1]))
+    assert per_point.max() <= 6
+    shards = shard_ranges(g["offsets"], 8)
+    for r in (0, 3, 7):
+        lo, hi = shards[r]
+        for _ in range(4):
+            gpu.find_stf(poses, src_lo=lo, src_hi=hi, fetch=False)
+        part = gpu.find_stf(poses, src_lo=lo, src_hi=hi)
+        assert len(part["pair_i"]) and part["pair_i"].min() >= lo and part["pair_i"].max() < hi
+        checks = S.check_chunks(part, poses, [(hi - 16, hi)])
+        assert all(c[2] for c in checks), (r, checks)
+    if name == "c3":
+        from conftest import _MAPS
+        _MAPS.pop(("c3", ()), None)                      # 0.7 GB of host arrays: not kept for the rest of the session
