@@ -163,58 +163,79 @@ def cpu_sample(g, seconds=15.0, threads=None):
             "search_Mq_per_s": queries / t_search / 1e6 if t_search else 0.0, "eval_Mm_per_s": matches / t_eval / 1e6 if t_eval else 0.0, "seconds": t_used}
 
 
-def ref_sample(g, seconds=15.0):
-    """The REFERENCE's own CPU path timed on the host cores (oracle/_ref/libhitl_ref_fast.so = JointOptimization.cpp + kdtree.cpp
-    compiled where they lie with the reference's Release flags; prebuilt, it travels to the GPU box): JointOpt::BuildKDTrees once
-    (not timed), then JointOpt::FindSTFCorrespondences over the whole pose range — OpenMP over source poses as the reference runs it
-    (JointOptimization.cpp:575) — and the evaluation of the blocks AddSTFConstraints builds through AutoDiffCostFunction on ONE
-    thread (the reference leaves Ceres at one thread, :154-155).  Bounded sample: the same map sub-sampled to every s-th pose, s
-    chosen from a calibration pass so that the timed pass takes about `seconds`.  Executed-query counts (cap-skipped queries
-    excluded, as the metric defines them) come from the oracle port on the same sub-map (the reference does not count them; the
-    parity builds of both produce identical lists, tests/test_oracle_ref_backend.py)."""
-    from oracle.pyoracle import Oracle, RefBackend
+REF_SAMPLE_UNIT = 1.1e9      # poses x points per unit of source stride: c2 (5 000 x 3.58 M) -> every 16th source pose, ~2 s of reference search on 16 threads
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU legs (reference arm, cpu_baseline) run on every host
+    thread this process may use, and say how many.  Must run before the first OpenMP library is loaded."""
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
+    return host_threads()
+
+
+class RefSampler:
+    """The REFERENCE's own CPU path on the FULL map (oracle/_ref/libhitl_ref_fast.so = JointOptimization.cpp + kdtree.cpp compiled where
+    they lie with the reference's Release flags; prebuilt, it travels to the GPU box).  Set-up, untimed: JointOpt over all poses,
+    JointOpt::BuildKDTrees.  One step, timed: JointOpt::FindSTFCorrespondences over the whole pose range — OpenMP over source poses as the
+    reference runs it (JointOptimization.cpp:575) — for a FIXED sample of source poses (every s-th pose, s from the map size alone, so
+    the sample is the same in every run and at every N) against ALL target poses, then the evaluation of the blocks AddSTFConstraints
+    builds through AutoDiffCostFunction on ONE thread (the reference leaves Ceres at one thread, :154-155).  The unmodified loop is
+    restricted to the sample through its own data (RefJointOpt.restrict_sources; every source pose is independent of the others).
+    Executed-query counts (cap-skipped queries excluded, as the metric defines them) come from the oracle port on the same sample
+    (the reference does not count them; both produce identical lists, tests/test_oracle_ref_backend.py)."""
+
+    def __init__(self, g):
+        from oracle.pyoracle import Oracle, RefBackend
+        self.ref = RefBackend(fast=True)
+        orc = Oracle(fast=True)
+        self.cores = orc.num_threads()
+        n = len(g["poses"])
+        self.n, self.n_points = n, int(g["offsets"][-1])
+        self.stride = max(1, int(round(n * float(self.n_points) / REF_SAMPLE_UNIT)))
+        self.phase = self.stride // 2
+        self.ids = np.arange(self.phase, n, self.stride)
+        self.poses = g["poses"].astype(np.float64)
+        self.J = self.ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+        self.J.restrict_sources(self.ids)
+        port = orc.scans(g["offsets"], g["pts"], g["nrm"]).find_stf(self.poses, src_lo=self.phase, src_stride=self.stride)
+        self.queries, self.port_matches = int(port["n_queries"]), int(len(port["k"]))
+
+    def step(self):
+        t0 = time.perf_counter()
+        corr = self.J.find_stf(self.poses)
+        t1 = time.perf_counter()
+        self.J.eval_blocks(2, self.poses, max(len(corr["pair_i"]), 1))
+        t2 = time.perf_counter()
+        matches, t_search, t_eval = int(len(corr["k"])), t1 - t0, t2 - t1
+        t_used = t_search + t_eval
+        return {"value": (self.queries + matches) / t_used / 1e6, "unit": UNIT, "cores": self.cores, "kind": "reference",
+                "sample": "every %d-th source pose of the full map (%d of %d poses, fixed) against all %d target poses: JointOpt::FindSTFCorrespondences "
+                          "(%d executed queries, %d matches, %d blocks) in %.2f s on %d OpenMP threads + AutoDiffCostFunction evaluation of the blocks in %.2f s on 1 thread; "
+                          "reference sources compiled with -O3 -march=x86-64-v3 -fopenmp -DNDEBUG (FMA contraction on, as -march=native gives the reference); "
+                          "the port's timing build finds %d matches on the same sample"
+                          % (self.stride, len(self.ids), self.n, self.n, self.queries, matches, len(corr["pair_i"]), t_search, self.cores, t_eval, self.port_matches),
+                "search_Mq_per_s": self.queries / t_search / 1e6 if t_search else 0.0, "eval_Mm_per_s": matches / t_eval / 1e6 if t_eval else 0.0, "seconds": t_used,
+                "source_stride": self.stride, "source_poses": int(len(self.ids))}
+
+
+def ref_sample(g, steps=3):
+    """cpu_baseline of the own arm: the mean of `steps` RefSampler steps (None when oracle/_ref was not built)."""
+    from oracle.pyoracle import RefBackend
     if not RefBackend.available(fast=True):
         return None
-    ref = RefBackend(fast=True)
-    orc = Oracle(fast=True)
-    n = len(g["poses"])
-    off = g["offsets"].astype(np.int64)
-
-    def submap(stride):
-        ids = np.arange(0, n, stride)
-        sizes = (off[ids + 1] - off[ids])
-        o = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
-        sel = np.concatenate([np.arange(off[i], off[i + 1]) for i in ids])
-        return ids, o, np.ascontiguousarray(g["pts"][sel], np.float32), np.ascontiguousarray(g["nrm"][sel], np.float32), np.ascontiguousarray(g["poses"][ids], np.float32)
-
-    def run(stride):
-        ids, o, pts, nrm, poses32 = submap(stride)
-        J = ref.joint_opt(o, pts, nrm, poses32)
-        poses = poses32.astype(np.float64)
-        t0 = time.perf_counter()
-        corr = J.find_stf(poses)
-        t1 = time.perf_counter()
-        J.eval_blocks(2, poses, max(len(corr["pair_i"]), 1))
-        t2 = time.perf_counter()
-        return ids, o, pts, nrm, poses, corr, t1 - t0, t2 - t1
-
-    n_cal = min(n, 250)
-    s_cal = max(1, n // n_cal)
-    *_, t_cal_s, t_cal_e = run(s_cal)
-    n_cal = len(range(0, n, s_cal))
-    n_target = int(min(n, max(n_cal, n_cal * np.sqrt(seconds / max(t_cal_s + t_cal_e, 1e-3)))))
-    stride = max(1, n // n_target)
-    ids, o, pts, nrm, poses, corr, t_search, t_eval = run(stride)
-    port = orc.scans(o, pts, nrm).find_stf(poses)
-    queries, matches = int(port["n_queries"]), int(len(corr["k"]))
-    t_used = t_search + t_eval
-    return {"value": (queries + matches) / t_used / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "reference",
-            "sample": "every %d-th pose of the map (%d of %d poses, %d points): JointOpt::FindSTFCorrespondences over all %d x %d ordered pairs "
-                      "(%d executed queries, %d matches, %d blocks) in %.1f s on %d OpenMP threads + AutoDiffCostFunction evaluation of the blocks in %.2f s on 1 thread; "
-                      "reference sources compiled with -O3 -march=x86-64-v3 -fopenmp -DNDEBUG (FMA contraction on, as -march=native gives the reference); "
-                      "the port's timing build finds %d matches on the same sub-map"
-                      % (stride, len(ids), n, int(o[-1]), len(ids), len(ids) - 1, queries, matches, len(corr["pair_i"]), t_search, orc.num_threads(), t_eval, len(port["k"])),
-            "search_Mq_per_s": queries / t_search / 1e6 if t_search else 0.0, "eval_Mm_per_s": matches / t_eval / 1e6 if t_eval else 0.0, "seconds": t_used}
+    smp = RefSampler(g)
+    rs = [smp.step() for _ in range(steps + 1)][1:]
+    out = dict(rs[-1])
+    out["value"] = float(np.mean([r["value"] for r in rs]))
+    out["seconds"] = float(np.sum([r["seconds"] for r in rs]))
+    return out
 
 
 def rebuild_fast_oracle_native():
@@ -226,32 +247,55 @@ def rebuild_fast_oracle_native():
         pass
 
 
+def load_workload_detached(name, n_poses, beams):
+    """The reference arm maps none of the repo's product libraries: the synthetic map comes from the .npz cache, and when the cache is
+    missing a CHILD process generates it (the generator runs through libhitl_host.so's .stfs.covars writer / loader)."""
+    cache = os.path.join(os.environ.get("HITL_SYNTH_DIR", "/tmp/hitl_synth"), "%s_%s_%s.npz" % (name, n_poses, beams))
+    if not os.path.exists(cache):
+        subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import bench; bench.workload(%r, %r, %r)" % (ROOT, name, n_poses, beams)],
+                       check=True, stdout=subprocess.DEVNULL)
+    z = np.load(cache)
+    out = {k: z[k] for k in z.files if k != "config_json"}
+    out["config"] = json.loads(str(z["config_json"]))
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     rebuild_fast_oracle_native()
-    g = workload(args.workload, args.poses, args.beams)
-    per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    g = load_workload_detached(args.workload, args.poses, args.beams)
+    from oracle.pyoracle import RefBackend
+    if RefBackend.available(fast=True):
+        smp = RefSampler(g)
+        step = smp.step
+    else:                                            # oracle/_ref absent (built only where /root/reference exists): the oracle port
+        per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+        step = lambda: cpu_sample(g, seconds=per_step)
     vals = []
     for it in range(args.warmup + args.steps):
-        r = ref_sample(g, seconds=per_step) or cpu_sample(g, seconds=per_step)   # the reference's own code when it was compiled here, else the port
+        r = step()
         if it >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
     last = vals[-1]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.mean([x.get("seconds", per_step) for x in vals])) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / f64 residuals",
-            "data": "synthetic", "config": config_of(args, g),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "ms_per_step": float(np.mean([x["seconds"] for x in vals])) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals",
+            "data": "synthetic", "config": config_of(args, g, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
+                             "value_min": float(np.min([x["value"] for x in vals])), "value_max": float(np.max([x["value"] for x in vals]))},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def config_of(args, g):
+def config_of(args, g, world=1):
+    """Identical in both arms (the driver compares them)."""
     return {"workload": "%s: synthetic corridor-lattice map, %d poses x %d beams (%d points) in .stfs.covars format, thr 0.15 m, 25 deg, cap 6, skip 1"
                         % (args.workload, len(g["poses"]), args.beams or 0, int(g["offsets"][-1])),
             "n_poses": int(len(g["poses"])), "n_points": int(g["offsets"][-1]),
-            "l2": "scans + trees + record buffers exceed the 126 MB L2; a 512 MB buffer is also written between timed steps"}
+            "l2": "scans + trees + record buffers exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
+            "parallelism": ("source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 all-reduce of packed J^TJ/J^Tr per step" % world
+                            if world > 1 else "single GPU")}
 
 
 def main():
@@ -268,6 +312,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check of the benchmarked search against the oracle")
     ap.add_argument("--replay", type=int, default=0, help="BASELINE config 4: replay this many sequential corrections on --replay-workload and report per-correction latency")
     ap.add_argument("--replay-workload", default="c4")
     ap.add_argument("--replay-seconds", type=float, default=150.0, help="wall-clock budget of the replay leg (stroke picking included)")
@@ -275,6 +320,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" or world == 1:
+        use_all_host_threads()                         # the CPU legs say how many threads they used (`cores`)
     from hitl_slam_b200 import synth
     if args.beams is None:
         args.beams = synth.CONFIGS[args.workload]["beams"]
@@ -413,23 +460,35 @@ def main():
     evals = queries + matches
     value = evals / (ms_per_step * 1e-3) / 1e6
 
+    # ---- parity of the benchmarked workload itself (outside every timed region; the oracle is the checker, never the thing measured) ----
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(gpu, g, poses, lo, hi, world)
+            if world > 1:
+                pc = torch.tensor([float(parity["chunks"]), float(parity["ok"])], dtype=torch.float64, device="cuda")
+                dist.all_reduce(pc)
+                parity["chunks"], parity["ok"] = int(pc[0].item()), int(pc[1].item())
+            parity["all_ok"] = parity["chunks"] == parity["ok"]
+        except Exception as e:
+            parity = {"error": str(e)[:200]}
+            if world > 1:
+                dist.all_reduce(torch.zeros(2, dtype=torch.float64, device="cuda"))
+
     # ---- roofline of the dominant kernel (this rank's launch) ----
     peak, peak_src = load_peaks()
     ms_search = float(np.mean([i[0]["ms_search"] for i in infos]))
     my_q, my_m = infos[-1][0]["n_queries"], infos[-1][0]["n_raw_matches"]
-    alg_bytes = 40.0 * my_q + 8.0 * my_m
-    achieved = alg_bytes / (ms_search * 1e-3) / 1e9
-    traffic = None
-    try:                                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["stf_search_kernel"]
-        if args.workload == "c2" and world == 1:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    roofline = search_roofline(args, world, gpu, ms_search, ms_per_step, my_q, my_m, clocks, peak, peak_src)
+    try:
+        ms_ev = gpu.last_kernel_ms("eval_stf_kernel")
+        ev_bytes = 32.0 * infos[-1][0]["n_matches"] + 160.0 * infos[-1][0]["n_pairs"]
+        roofline["kernels"]["eval_stf_kernel"] = {
+            "bound": "hbm", "achieved": ev_bytes / (ms_ev * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": ev_bytes / (ms_ev * 1e-3) / 1e9 / peak, "ms_kernel": ms_ev,
+            "algorithmic_bytes": ev_bytes, "traffic": counter_of("eval_stf_kernel", "dram_bytes", args, world),
+            "note": "32 B gathered per correspondence + 160 B per block (SURVEY.md 8d); normal-equation mode of this rank's blocks, last timed step"}
     except Exception:
         pass
-    roofline = {"kernel": "stf_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "ms_kernel": ms_search, "share_of_step": ms_search / ms_per_step,
-                "note": "algorithmic bytes = 40 B per query + 8 B per match (pair-tile model, SURVEY.md 8d); the kernel proves most queries empty "
-                        "with AABB tests and reuses one source tile across all targets, so it can exceed the stream model"}
 
     # ---- e2e through the C ABI with HOST buffers (page-locked, from hitl_host_alloc) ----
     # One step = what a caller holding the map on the host pays: scans + trees + poses H2D, the search,
@@ -490,6 +549,17 @@ def main():
         except Exception as e:            # the headline line must still print
             correction = {"error": str(e)[:200]}
 
+    if rank == 0 and correction and "error" not in correction:
+        try:
+            ms_em = gpu.last_kernel_ms("em_inliers_kernel")
+            em_bytes = 8.0 * float(g["offsets"][-1])
+            roofline["kernels"]["em_inliers_kernel"] = {
+                "bound": "hbm", "achieved": em_bytes / (ms_em * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": em_bytes / (ms_em * 1e-3) / 1e9 / peak, "ms_kernel": ms_em,
+                "algorithmic_bytes": em_bytes, "traffic": counter_of("em_inliers_kernel", "dram_bytes", args, world),
+                "note": "8 B per world-frame point per E-step (SURVEY.md 8d); last E-step of the correction leg; launch-latency sized at this map (28.6 MB)"}
+        except Exception:
+            pass
+
     replay = None
     if rank == 0 and args.replay > 0:
         try:
@@ -503,26 +573,81 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         rebuild_fast_oracle_native()
         port = cpu_sample(g, seconds=args.cpu_seconds)
-        cpu = ref_sample(g, seconds=args.cpu_seconds)
+        cpu = ref_sample(g)
         if cpu is None:
             cpu = port
         else:
             cpu["port"] = port            # the oracle port on a full-map sample, timed beside the reference's own code
 
     if rank == 0:
-        cfg = config_of(args, g)
-        cfg.update({"parallelism": "source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 all-reduce of packed J^TJ/J^Tr per step" % world if world > 1 else "single GPU",
-                    "kdtree_build_device_s": t_build})
+        cfg = config_of(args, g, world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "correction_latency": correction, "correction_replay": replay,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_checked": parity, "cpu_baseline": cpu, "correction_latency": correction, "correction_replay": replay,
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
-                           "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
+                           "kdtree_build_device_s": t_build, "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
                            "per_rank_[ms_search,ms_find_stf,tiles,source_poses]": per_rank}}
         print(json.dumps(line))
     gpu.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def counter_of(kernel, key, args, world):
+    """Per-launch hardware counters of the committed `ncu --set full` capture (profiles/ncu_counters.json: workload c2, one GPU, this
+    code).  They describe ONE launch on c2 at N = 1; other workloads / shard sizes get None rather than a number that is not theirs."""
+    if args.workload != "c2" or world != 1 or args.poses != 5000 or args.beams != 720:
+        return None
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))[kernel]
+        if key == "dram_bytes":
+            return c["dram_bytes_read"] + c["dram_bytes_write"]
+        return c.get(key)
+    except Exception:
+        return None
+
+
+def search_roofline(args, world, gpu, ms_search, ms_per_step, n_queries, n_raw_matches, clocks, hbm_peak, peak_src):
+    """stf_search_kernel is ISSUE-bound (divergent tree walks): its physical roofline is the warp-instruction issue rate
+    of the chip, 4 schedulers x SMs x SM clock.  achieved = warp-instructions of one launch (smsp__inst_executed.sum of the committed
+    ncu capture of this code on this workload) / the kernel's duration measured live with CUDA events.  The HBM figures stay beside it:
+    `traffic` / `frac_measured_traffic` are the DRAM bytes the launch really moved, and `hbm_stream_model` is SURVEY.md 8d's pair-tile
+    stream model (40 B per reference-semantics query + 8 B per match), which is NOT a physical fraction: the kernel proves > 98 % of
+    those queries empty with exact bitmap tests and streams nothing for them, so the model exceeds 1."""
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = gpu.sm_count() * 4 * sm_mhz * 1e6 / 1e9                     # G warp-instructions / s
+    inst = counter_of("stf_search_kernel", "inst_executed", args, world)
+    traffic = counter_of("stf_search_kernel", "dram_bytes", args, world)
+    achieved = inst / (ms_search * 1e-3) / 1e9 if inst else None
+    alg_bytes = 40.0 * n_queries + 8.0 * n_raw_matches
+    model = alg_bytes / (ms_search * 1e-3) / 1e9
+    return {"kernel": "stf_search_kernel", "bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "G warp-inst/s",
+            "frac": achieved / issue_peak if achieved else None,
+            "traffic": traffic, "frac_measured_traffic": traffic / (ms_search * 1e-3) / 1e9 / hbm_peak if traffic else None,
+            "issue_active": counter_of("stf_search_kernel", "issue_active_pct", args, world), "threads_per_inst": counter_of("stf_search_kernel", "threads_per_inst", args, world),
+            "warp_instructions": inst, "ms_kernel": ms_search, "share_of_step": ms_search / ms_per_step,
+            "peak_source": "issue: %d SMs x 4 schedulers x %.0f MHz (SM clock sampled during the timed region); HBM: %s" % (gpu.sm_count(), sm_mhz, peak_src),
+            "hbm_stream_model": {"achieved": model, "peak": hbm_peak, "unit": "GB/s", "frac": model / hbm_peak, "algorithmic_bytes": alg_bytes, "physical": False,
+                                 "note": "40 B per reference-semantics query + 8 B per match (SURVEY.md 8d pair-tile model); exceeds 1 because exact culling "
+                                         "proves most counted queries empty without streaming their scans - not evidence of bandwidth"},
+            "kernels": {}}
+
+
+def parity_check(gpu, g, poses, lo, hi, world):
+    """The search the bench just timed (same context, same adaptive tiling, same source shard) fetched once more and compared bit for bit
+    with the CPU oracle's FindSTFCorrespondences on a few source-pose chunks of this rank's shard against ALL targets — the last poses of
+    the shard included, where tiles are heaviest.  One rank: 4 chunks of 16 poses on all host threads; N ranks: one 4-pose chunk per rank
+    (torchrun leaves each rank one OpenMP thread)."""
+    from oracle.pyoracle import Oracle
+    S = Oracle().scans(g["offsets"], g["pts"], g["nrm"])
+    res = gpu.find_stf(poses, src_lo=lo, src_hi=hi)
+    width = 16 if world == 1 else 4
+    width = min(width, hi - lo)
+    starts = sorted(set([hi - width] if world > 1 else [int(x) for x in np.linspace(lo, hi - width, 4)]))
+    t0 = time.perf_counter()
+    checks = S.check_chunks(res, poses, [(a, a + width) for a in starts])
+    return {"chunks": len(checks), "ok": int(sum(1 for c in checks if c[2])), "source_chunks": [[c[0], c[1]] for c in checks], "matches_compared": int(sum(c[4] for c in checks)),
+            "against": "oracle FindSTFCorrespondences (parity build) on these source poses vs all targets: pair_i, pair_j, pair_off, k, idx bit for bit", "seconds": time.perf_counter() - t0}
 
 
 def correction_latency(gpu, g, cpu=True, reps=5):

@@ -23,7 +23,7 @@ KDNODE = np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), (
 
 # every symbol include/hitl_gpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
-    "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count",
+    "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count", "hitl_last_kernel_ms",
     "hitl_host_alloc", "hitl_host_free",
     "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_set_kdtrees_compact", "hitl_get_kdtrees_compact", "hitl_kd_query",
     "hitl_find_stf", "hitl_get_stf", "hitl_get_stf16", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
@@ -88,6 +88,7 @@ class HitlGpu:
         lib.hitl_launch_count.restype = C.c_uint64
         lib.hitl_launch_count.argtypes = [vp]
         lib.hitl_sm_count.argtypes = [vp]
+        lib.hitl_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
         lib.hitl_host_alloc.restype = vp
         lib.hitl_host_alloc.argtypes = [C.c_size_t]
         lib.hitl_host_free.argtypes = [vp]
@@ -173,6 +174,13 @@ class HitlGpu:
             raise HitlError("status %d: %s" % (rc, self.lib.hitl_last_error(self.ctx).decode()))
 
     # ---- scans / trees ----
+    def _poses(self, poses, dtype=np.float64, what="poses"):
+        """The C ABI takes the pose array without a length and reads 3 * n_poses values: a short array is an error here, not a host over-read."""
+        p = np.ascontiguousarray(poses, dtype).reshape(-1)
+        if p.size != 3 * self.n_poses:
+            raise HitlError("%s: expected %d values (3 per pose of the resident map), got %d" % (what, 3 * self.n_poses, p.size))
+        return p
+
     def set_scans(self, offsets, pts, nrm):
         offsets = np.ascontiguousarray(offsets, np.uint32)
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
@@ -180,6 +188,8 @@ class HitlGpu:
         self.offsets = offsets
         self.n_poses = len(offsets) - 1
         self.n_points = int(offsets[-1]) if len(offsets) else 0
+        if len(pts) != 2 * self.n_points or len(nrm) != 2 * self.n_points:
+            raise HitlError("set_scans: clouds must hold 2 floats per point (%d points per the offsets)" % self.n_points)
         if len(pts) == 0:
             pts = np.zeros(2, np.float32)
             nrm = np.zeros(2, np.float32)
@@ -190,11 +200,16 @@ class HitlGpu:
 
     def set_kdtrees(self, nodes):
         nodes = np.ascontiguousarray(nodes, KDNODE)
+        if nodes.size != self.n_points:
+            raise HitlError("set_kdtrees: expected %d nodes (one per point), got %d" % (self.n_points, nodes.size))
         self._ck(self.lib.hitl_set_kdtrees(self.ctx, nodes.ctypes.data))
 
     def set_kdtrees_compact(self, index_dim):
         """Trees as one u32 per node (index | dim << 31, preorder): the points and normals are taken from the resident scans."""
-        self._ck(self.lib.hitl_set_kdtrees_compact(self.ctx, np.ascontiguousarray(index_dim, np.uint32).ctypes.data_as(C.c_void_p)))
+        index_dim = np.ascontiguousarray(index_dim, np.uint32)
+        if index_dim.size != self.n_points:
+            raise HitlError("set_kdtrees_compact: expected %d nodes (one per point), got %d" % (self.n_points, index_dim.size))
+        self._ck(self.lib.hitl_set_kdtrees_compact(self.ctx, index_dim.ctypes.data_as(C.c_void_p)))
 
     def get_kdtrees_compact(self, out=None):
         out = np.zeros(max(self.n_points, 1), np.uint32) if out is None else out
@@ -227,7 +242,7 @@ class HitlGpu:
         return StfOpts(thr, default_min_cos() if min_cos is None else min_cos, cap, skip, min_corr, disable_culling)
 
     def find_stf(self, poses, min_pose=0, max_pose=None, src_lo=0, src_hi=0xFFFFFFFF, opts=None, fetch=True, out=None):
-        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        poses = self._poses(poses, what="find_stf")
         if max_pose is None:
             max_pose = max(self.n_poses - 1, 0)
         opts = opts or self.stf_opts()
@@ -261,7 +276,7 @@ class HitlGpu:
         return w[:self.n_poses]
 
     def find_vo(self, poses, min_pose=0, max_pose=None, opts=None):
-        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        poses = self._poses(poses, what="find_vo")
         if max_pose is None:
             max_pose = self.n_poses - 1
         opts = opts or self.stf_opts()
@@ -274,7 +289,7 @@ class HitlGpu:
 
     # ---- world / EM ----
     def world_transform(self, poses_f32, fetch=True):
-        p = np.ascontiguousarray(poses_f32, np.float32).reshape(-1)
+        p = self._poses(poses_f32, np.float32, "world_transform")
         out = np.zeros(2 * max(self.n_points, 1), np.float32) if fetch else None
         self._ck(self.lib.hitl_world_transform(self.ctx, p, out.ctypes.data if fetch else None))
         return out[:2 * self.n_points].reshape(-1, 2) if fetch else None
@@ -353,7 +368,7 @@ class HitlGpu:
 
     def eval(self, poses, precision=0, want_jac=True, fetch=True, out=None):
         """out = (r, J) preallocated float64 arrays (e.g. pinned) at least as large as the layout."""
-        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        poses = self._poses(poses, what="eval")
         L = self.layout()
         if out is not None:
             if len(out[0]) < L.n_residuals or (want_jac and len(out[1]) < L.n_jacobian):
@@ -370,7 +385,7 @@ class HitlGpu:
         return out
 
     def normal_eq(self, poses, fetch=True):
-        poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
+        poses = self._poses(poses, what="normal_eq")
         n = self.n_poses
         L = self.layout()
         nbin = L.n_odometry + L.n_stf
@@ -429,6 +444,14 @@ class HitlGpu:
         out = np.zeros(6 * len(src), np.float32)
         self._ck(self.lib.hitl_debug_relative_pose(self.ctx, poses, len(src), src, dst, out))
         return out.reshape(-1, 6)
+
+    KERNELS = {"stf_search_kernel": 0, "eval_stf_kernel": 1, "em_inliers_kernel": 2, "em_assign_kernel": 3, "world_transform_kernel": 4, "em_fit_kernel": 5}
+
+    def last_kernel_ms(self, name):
+        """Duration of the last launch of one named kernel (CUDA events on the library's stream)."""
+        ms = C.c_float()
+        self._ck(self.lib.hitl_last_kernel_ms(self.ctx, self.KERNELS[name], C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return self.lib.hitl_launch_count(self.ctx)

@@ -155,6 +155,7 @@ extern "C" int hitl_create(hitl_ctx** out, int device) {
   if (const char* v = getenv("HITL_SPLIT_ROUNDS")) ctx->max_split_rounds = (uint32_t)std::max(0, atoi(v));
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) { cudaEventCreate(&ctx->ev[i]); cudaEventCreate(&ctx->evx[i]); }
+  for (int k = 0; k < HITL_K_COUNT; ++k) { cudaEventCreate(&ctx->kev[k][0]); cudaEventCreate(&ctx->kev[k][1]); }
   if (cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(uint64_t)) != cudaSuccess) { hitl_destroy(ctx); cudaGetLastError(); return HITL_ERR_CUDA; }
   *out = ctx;
   return HITL_OK;
@@ -167,7 +168,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
-  ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release();
+  ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release(); ctx->d_node_compact.release(); ctx->d_pack_k.release(); ctx->d_pack_idx.release();
   ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
@@ -185,6 +186,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_r.release(); ctx->d_J.release(); ctx->d_neq.release(); ctx->d_hoff.release(); ctx->d_trig.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < 4; ++i) { if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); if (ctx->evx[i]) cudaEventDestroy(ctx->evx[i]); }
+  for (int k = 0; k < HITL_K_COUNT; ++k) for (int q = 0; q < 2; ++q) if (ctx->kev[k][q]) cudaEventDestroy(ctx->kev[k][q]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -193,6 +195,14 @@ extern "C" const char* hitl_last_error(const hitl_ctx* ctx) { return ctx ? ctx->
 extern "C" void* hitl_stream(hitl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t hitl_launch_count(const hitl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int hitl_sm_count(const hitl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int hitl_last_kernel_ms(hitl_ctx* ctx, int which, float* ms) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (which < 0 || which >= HITL_K_COUNT || !ms) return fail(ctx, HITL_ERR_ARG, "hitl_last_kernel_ms: bad argument");
+  if (!ctx->kev_set[which]) return fail(ctx, HITL_ERR_STATE, "hitl_last_kernel_ms: that kernel has not been launched yet");
+  HITL_CUDA(cudaEventSynchronize(ctx->kev[which][1]));
+  HITL_CUDA(cudaEventElapsedTime(ms, ctx->kev[which][0], ctx->kev[which][1]));
+  return HITL_OK;
+}
 
 // Page-locked host buffers for the caller's pose / scan / result arrays: DMA at PCIe rate and truly
 // asynchronous copies.  Plain malloc'd buffers work everywhere too (staged by the driver).
@@ -207,23 +217,30 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   if (!ctx) return HITL_ERR_ARG;
   if (!off && n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null offsets");
   HITL_CUDA(cudaSetDevice(ctx->device));
-  ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false;
-  // Same scan partition as before (a re-upload of the same map): tiling and schedule hints stay valid.
-  const bool same_partition = ctx->n_poses == n_poses && n_poses > 0 && ctx->h_off.size() == (size_t)n_poses + 1 &&
-                              memcmp(ctx->h_off.data(), off, sizeof(uint32_t) * ((size_t)n_poses + 1)) == 0 && !ctx->h_tile_scan.empty();
-  ctx->n_poses = n_poses;
-  ctx->h_off.assign(n_poses + 1, 0);
+  // Validate everything into locals first: a rejected call leaves the context exactly as it was.
   uint32_t max_scan = 0;
-  for (uint32_t i = 0; i <= n_poses && n_poses; ++i) {
-    ctx->h_off[i] = off[i];
-    if (i && off[i] < off[i - 1]) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: offsets must be non-decreasing");
-    if (i) max_scan = std::max(max_scan, off[i] - off[i - 1]);
+  for (uint32_t i = 1; i <= n_poses; ++i) {
+    if (off[i] < off[i - 1]) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: offsets must be non-decreasing");
+    max_scan = std::max(max_scan, off[i] - off[i - 1]);
   }
   if (n_poses && off[0] != 0) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: offsets must start at 0");
   if (max_scan > 65534) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: scans larger than 65534 points are not supported");
+  const uint64_t n_points = n_poses ? off[n_poses] : 0;
+  if (n_points && (!pts_xy || !nrm_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null clouds");
+  // Same scan partition as before (a re-upload of the same map): tiling and schedule hints stay valid.
+  const bool same_partition = ctx->n_poses == n_poses && n_poses > 0 && ctx->h_off.size() == (size_t)n_poses + 1 &&
+                              memcmp(ctx->h_off.data(), off, sizeof(uint32_t) * ((size_t)n_poses + 1)) == 0 && !ctx->h_tile_scan.empty();
+  // ---- commit ----
+  ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false;
+  // Residual blocks registered for the previous map carry pose / point indices that were range-checked against IT: they must be
+  // registered again (hitl_eval / hitl_normal_eq would otherwise index the new, possibly smaller, map with stale indices).
+  ctx->nb_odo = ctx->nb_human = ctx->nb_stf = ctx->nb_p2lg = ctx->nb_p2l = 0; ctx->stf_from_search = false;
+  ctx->n_pairs = ctx->n_matches = 0; ctx->n_vo = 0;
+  ctx->n_poses = n_poses;
+  ctx->h_off.assign(n_poses + 1, 0);
+  for (uint32_t i = 0; i <= n_poses && n_poses; ++i) ctx->h_off[i] = off[i];
   ctx->max_scan = max_scan;
-  ctx->n_points = n_poses ? off[n_poses] : 0;
-  if (ctx->n_points && (!pts_xy || !nrm_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null clouds");
+  ctx->n_points = n_points;
   ctx->h_pts.clear(); ctx->h_nrm.clear();   // host copies are fetched lazily by hitl_build_kdtrees
   HITL_CUDA(ctx->d_off.ensure(n_poses + 1));
   HITL_CUDA(ctx->d_pts.ensure(ctx->n_points)); HITL_CUDA(ctx->d_nrm.ensure(ctx->n_points));
@@ -391,10 +408,10 @@ extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim
   HITL_CUDA(ctx->d_node_pm.ensure(m)); HITL_CUDA(ctx->d_node_nn.ensure(m));
   ctx->have_trees = false;
   if (m) {
-    HITL_CUDA(ctx->d_tile_keys.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(4));      // d_tile_keys: u32 scratch, rewritten by every search
+    HITL_CUDA(ctx->d_node_compact.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(4));
     HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_tile_keys.p, index_dim, 4 * m, cudaMemcpyHostToDevice, ctx->stream));
-    expand_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tile_keys.p, ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, ctx->n_poses, m,
+    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_compact.p, index_dim, 4 * m, cudaMemcpyHostToDevice, ctx->stream));
+    expand_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_compact.p, ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, ctx->n_poses, m,
                                                                               ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_ticket.p);
     HITL_LAUNCH_CHECK("expand_nodes_kernel");
     HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_ticket.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -411,10 +428,10 @@ extern "C" int hitl_get_kdtrees_compact(hitl_ctx* ctx, uint32_t* index_dim_out) 
   const size_t m = ctx->n_points;
   if (!m) return HITL_OK;
   if (!index_dim_out) return fail(ctx, HITL_ERR_ARG, "hitl_get_kdtrees_compact: null output");
-  HITL_CUDA(ctx->d_tile_keys.ensure(m));
-  compact_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pm.p, m, ctx->d_tile_keys.p);
+  HITL_CUDA(ctx->d_node_compact.ensure(m));
+  compact_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pm.p, m, ctx->d_node_compact.p);
   HITL_LAUNCH_CHECK("compact_nodes_kernel");
-  HITL_CUDA(cudaMemcpyAsync(index_dim_out, ctx->d_tile_keys.p, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(index_dim_out, ctx->d_node_compact.p, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }
@@ -441,7 +458,7 @@ extern "C" int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, floa
   if (!ctx) return HITL_ERR_ARG;
   if (n == 0) return HITL_OK;
   if (!x || !sin_out || !cos_out) return fail(ctx, HITL_ERR_ARG, "hitl_debug_sincos: null argument");
-  DevBuf<float> dx, ds, dc;
+  TmpBuf<float> dx, ds, dc;
   HITL_CUDA(dx.ensure(n)); HITL_CUDA(ds.ensure(n)); HITL_CUDA(dc.ensure(n));
   HITL_CUDA(cudaMemcpyAsync(dx.p, x, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   debug_sincos_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.p, n, ds.p, dc.p);
@@ -449,7 +466,6 @@ extern "C" int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, floa
   HITL_CUDA(cudaMemcpyAsync(sin_out, ds.p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(cos_out, dc.p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  dx.release(); ds.release(); dc.release();
   return HITL_OK;
 }
 
@@ -457,7 +473,9 @@ extern "C" int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array,
   if (!ctx) return HITL_ERR_ARG;
   if (n_pairs == 0) return HITL_OK;
   if (!pose_array || !src || !dst || !out6 || ctx->n_poses == 0) return fail(ctx, HITL_ERR_ARG, "hitl_debug_relative_pose: bad argument");
-  DevBuf<double> dp; DevBuf<uint32_t> da, db; DevBuf<float> dout;
+  for (uint32_t q = 0; q < n_pairs; ++q)
+    if (src[q] >= ctx->n_poses || dst[q] >= ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_debug_relative_pose: pose index out of range");
+  TmpBuf<double> dp; TmpBuf<uint32_t> da, db; TmpBuf<float> dout;
   HITL_CUDA(dp.ensure(3 * (size_t)ctx->n_poses)); HITL_CUDA(da.ensure(n_pairs)); HITL_CUDA(db.ensure(n_pairs)); HITL_CUDA(dout.ensure(6 * (size_t)n_pairs));
   HITL_CUDA(cudaMemcpyAsync(dp.p, pose_array, 24 * (size_t)ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(da.p, src, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -466,6 +484,5 @@ extern "C" int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array,
   HITL_LAUNCH_CHECK("debug_relative_pose_kernel");
   HITL_CUDA(cudaMemcpyAsync(out6, dout.p, 24 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  dp.release(); da.release(); db.release(); dout.release();
   return HITL_OK;
 }

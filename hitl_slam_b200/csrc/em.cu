@@ -296,8 +296,10 @@ extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float
   if (ctx->n_poses) {
     HITL_CUDA(cudaMemcpyAsync(ctx->d_poses_f.p, poses_xyt, 12 * (size_t)ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
+    HITL_KERNEL_BEGIN(HITL_K_WORLD_TRANSFORM);
     world_transform_kernel<<<((size_t)ctx->n_poses * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>(ctx->d_pts.p, ctx->d_off.p, ctx->d_poses_f.p,
                                                                                                           ctx->n_poses, ctx->d_world.p);
+    HITL_KERNEL_END(HITL_K_WORLD_TRANSFORM);
     HITL_LAUNCH_CHECK("world_transform_kernel");
   }
   if (world_xy_out && ctx->n_points) HITL_CUDA(cudaMemcpyAsync(world_xy_out, ctx->d_world.p, 8 * ctx->n_points, cudaMemcpyDeviceToHost, ctx->stream));
@@ -347,11 +349,13 @@ extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double thresho
   HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
   Seg s; make_seg(seg, &s);
   const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
+  HITL_KERNEL_BEGIN(HITL_K_EM_INLIERS);
   em_inliers_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, threshold,
                                                           (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap,
                                                           want ? ctx->d_em_pose.p : nullptr, want ? ctx->d_em_idx.p : nullptr,
                                                           (want && out_xy) ? ctx->d_em_xy.p : nullptr,
                                                           (unsigned long long*)ctx->d_scan_state.p + n_chunks);
+  HITL_KERNEL_END(HITL_K_EM_INLIERS);
   HITL_LAUNCH_CHECK("em_inliers_kernel");
   HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_scan_state.p + n_chunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -387,8 +391,10 @@ extern "C" int hitl_em_assign(hitl_ctx* ctx, const float segs[8], double thresho
   Seg2 sa, sb; make_seg2(segs, &sa); make_seg2(segs + 4, &sb);
   const int threads = 256;
   const uint32_t grid = (uint32_t)(((size_t)n * 32 + threads - 1) / threads);
+  HITL_KERNEL_BEGIN(HITL_K_EM_ASSIGN);
   em_assign_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, n, sa, sb, threshold, slots[0].p, slots[1].p, ctx->d_em_cnt[0].p,
                                                       ctx->d_em_cnt[1].p);
+  HITL_KERNEL_END(HITL_K_EM_ASSIGN);
   HITL_LAUNCH_CHECK("em_assign_kernel");
   uint32_t* set_pose[2] = {set_pose0, set_pose1}; uint64_t* set_off[2] = {set_off0, set_off1}; uint32_t* obs[2] = {obs0, obs1};
   for (int f = 0; f < 2; ++f) {

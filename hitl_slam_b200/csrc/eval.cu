@@ -423,6 +423,8 @@ extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
   if (!ctx) return HITL_ERR_ARG;
   if (n_blocks && (!blk_pose || !blk_off || !pts_xy || !ln_xy || !lo || !valid)) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: null argument");
   for (uint32_t b = 0; b < n_blocks; ++b) if (blk_pose[b] >= ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: pose out of range");
+  if (n_blocks && blk_off[0] != 0) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: blk_off must start at 0");
+  for (uint32_t b = 0; b < n_blocks; ++b) if (blk_off[b + 1] < blk_off[b]) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: blk_off must be non-decreasing");
   const uint64_t m = n_blocks ? blk_off[n_blocks] : 0;
   HITL_CUDA(ctx->d_p2lg_pose.ensure(n_blocks)); HITL_CUDA(ctx->d_p2lg_off.ensure(n_blocks + 1)); HITL_CUDA(ctx->d_p2lg_pts.ensure(m));
   HITL_CUDA(ctx->d_p2lg_n.ensure(m)); HITL_CUDA(ctx->d_p2lg_o.ensure(m)); HITL_CUDA(ctx->d_p2lg_v.ensure(m));
@@ -483,10 +485,12 @@ static int launch_all(hitl_ctx* ctx, double* d_r, double* d_J, const NeqOut& neq
     HITL_CUDA(ctx->d_trig.ensure(2 * (size_t)ctx->n_poses));
     pose_trig_kernel<<<(ctx->n_poses + 255) / 256, 256, 0, ctx->stream>>>(pose, ctx->n_poses, ctx->d_trig.p);
     HITL_LAUNCH_CHECK("pose_trig_kernel");
+    HITL_KERNEL_BEGIN(HITL_K_EVAL_STF);
     eval_stf_kernel<T><<<(uint32_t)((nb * 32 + kStfThreads - 1) / kStfThreads), kStfThreads, 0, ctx->stream>>>(
         ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, fs ? ctx->d_pair_i.p : ctx->d_blk_i.p, fs ? ctx->d_pair_j.p : ctx->d_blk_j.p,
         (const unsigned long long*)(fs ? ctx->d_pair_off.p : ctx->d_blk_off.p), fs ? ctx->d_k.p : ctx->d_blk_k.p, fs ? ctx->d_idx.p : ctx->d_blk_idx.p, ctx->d_trig.p, nb,
         ctx->stf_std, ctx->stf_corr, d_r ? d_r + ro : nullptr, d_J ? d_J + jo : nullptr, neq, want_neq, (size_t)ctx->nb_odo);
+    HITL_KERNEL_END(HITL_K_EVAL_STF);
     HITL_LAUNCH_CHECK("eval_stf_kernel");
   }
   ro += 2 * ctx->nb_stf; jo += 12 * ctx->nb_stf;

@@ -40,6 +40,13 @@ template <typename T> struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// A DevBuf local to one call: freed on every exit path (the HITL_CUDA early returns included).
+template <typename T> struct TmpBuf : DevBuf<T> {
+  TmpBuf() {}
+  ~TmpBuf() { this->release(); }
+  TmpBuf(const TmpBuf&) = delete;
+  TmpBuf& operator=(const TmpBuf&) = delete;
+};
 
 }  // namespace hitl
 
@@ -49,6 +56,8 @@ struct hitl_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};   // extra phase marks of hitl_find_stf (HITL_STF_TIMING=1 prints them)
+  cudaEvent_t kev[HITL_K_COUNT][2] = {};                       // begin / end of the last launch of the kernels hitl_last_kernel_ms names
+  bool kev_set[HITL_K_COUNT] = {};
   std::string err;
   uint64_t launches = 0;
 
@@ -95,6 +104,8 @@ struct hitl_ctx {
   hitl::DevBuf<float4> d_node_pm;        // px, py, bits(index | dim << 31), 0   (preorder, concatenated): one 16 B load per node visit
   hitl::DevBuf<float2> d_node_nn;        // nx, ny   (read only for nodes inside the query radius)
   hitl::DevBuf<hitl_kdnode> d_node_aos;  // staging for hitl_set_kdtrees / hitl_get_kdtrees (AoS <-> SoA on the device)
+  hitl::DevBuf<uint32_t> d_node_compact; // staging for hitl_set_kdtrees_compact / hitl_get_kdtrees_compact (index | dim << 31 per node)
+  hitl::DevBuf<uint32_t> d_pack_k, d_pack_idx;   // staging for hitl_get_stf16 (two 16-bit indices per word)
 
   // ---- per-call pose tables ----
   hitl::DevBuf<double> d_pose;           // x, y, theta
@@ -165,6 +176,9 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
     cudaError_t e__ = (call);                                        \
     if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, #call); \
   } while (0)
+// Event pair around one named kernel launch (hitl_last_kernel_ms)
+#define HITL_KERNEL_BEGIN(which) do { if (ctx->kev[which][0]) cudaEventRecord(ctx->kev[which][0], ctx->stream); } while (0)
+#define HITL_KERNEL_END(which) do { if (ctx->kev[which][1]) { cudaEventRecord(ctx->kev[which][1], ctx->stream); ctx->kev_set[which] = true; } } while (0)
 #define HITL_LAUNCH_CHECK(name)                                      \
   do {                                                               \
     ctx->launches++;                                                 \

@@ -1066,7 +1066,7 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_kd_query: trees not built");
   if (scan >= ctx->n_poses || mode < 0 || mode > 2 || (nq && (!q_xy || !index_out))) return fail(ctx, HITL_ERR_ARG, "hitl_kd_query: bad argument");
   if (nq == 0) return HITL_OK;
-  DevBuf<float2> dq; DevBuf<float> dd; DevBuf<int32_t> di;
+  TmpBuf<float2> dq; TmpBuf<float> dd; TmpBuf<int32_t> di;
   HITL_CUDA(dq.ensure(nq)); HITL_CUDA(dd.ensure(nq)); HITL_CUDA(di.ensure(nq));
   HITL_CUDA(cudaMemcpyAsync(dq.p, q_xy, sizeof(float2) * nq, cudaMemcpyHostToDevice, ctx->stream));
   const uint32_t toff = ctx->h_off[scan], tn = ctx->h_off[scan + 1] - toff;
@@ -1078,7 +1078,6 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
   if (dist_out && mode != 2) HITL_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(float) * nq, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(index_out, di.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  dq.release(); dd.release(); di.release();
   return HITL_OK;
 }
 
@@ -1191,7 +1190,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(ctx->d_pose_cnt.ensure(2 * (size_t)n + 2));
   HITL_CUDA(ctx->d_pose_work.ensure(n));
   HITL_CUDA(ctx->d_k.ensure(rec_cap)); HITL_CUDA(ctx->d_idx.ensure(rec_cap));
-  const size_t pair_cap = rec_cap / (o->min_inter_pose_correspondence + 1) + 1;
+  const size_t pair_cap = rec_cap / ((size_t)o->min_inter_pose_correspondence + 1) + 1;   // + 1 in 64 bits: UINT32_MAX must not wrap to a zero divisor
   HITL_CUDA(ctx->d_pair_i.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_j.ensure(pair_cap)); HITL_CUDA(ctx->d_pair_off.ensure(pair_cap + 1));
 
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1238,7 +1237,9 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSearchThreads, 0));
     if (per_sm < 1) per_sm = 1;
     const uint32_t grid = std::min<uint32_t>((n_tiles + wpb - 1) / wpb, (uint32_t)(ctx->sm_count * per_sm));
+    HITL_KERNEL_BEGIN(HITL_K_STF_SEARCH);
     kernel<<<grid, kSearchThreads, 0, ctx->stream>>>(P);
+    HITL_KERNEL_END(HITL_K_STF_SEARCH);
     HITL_LAUNCH_CHECK("stf_search_kernel");
   }
   HITL_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1403,12 +1404,12 @@ extern "C" int hitl_get_stf16(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j,
     if (pair_off) HITL_CUDA(cudaMemcpyAsync(pair_off, ctx->d_pair_off.p, 8 * (np + 1), cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (nm && (k || idx)) {
-    // staging: the raw record columns are free once the search has been ordered (d_raw_k / d_raw_idx hold >= n_matches words)
     const uint64_t words = (nm + 1) / 2;
-    pack_u16_kernel<<<(uint32_t)((words + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_k.p, ctx->d_idx.p, nm, ctx->d_raw_k.p, ctx->d_raw_idx.p);
+    HITL_CUDA(ctx->d_pack_k.ensure(words)); HITL_CUDA(ctx->d_pack_idx.ensure(words));   // dedicated staging (no aliasing of search scratch)
+    pack_u16_kernel<<<(uint32_t)((words + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_k.p, ctx->d_idx.p, nm, ctx->d_pack_k.p, ctx->d_pack_idx.p);
     HITL_LAUNCH_CHECK("pack_u16_kernel");
-    if (k) HITL_CUDA(cudaMemcpyAsync(k, ctx->d_raw_k.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
-    if (idx) HITL_CUDA(cudaMemcpyAsync(idx, ctx->d_raw_idx.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (k) HITL_CUDA(cudaMemcpyAsync(k, ctx->d_pack_k.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idx) HITL_CUDA(cudaMemcpyAsync(idx, ctx->d_pack_idx.p, 2 * nm, cudaMemcpyDeviceToHost, ctx->stream));
   }
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;

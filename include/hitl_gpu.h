@@ -56,6 +56,10 @@ void* hitl_stream(hitl_ctx* ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t hitl_launch_count(const hitl_ctx* ctx);
 int hitl_sm_count(const hitl_ctx* ctx);
+/* Duration (ms, CUDA events on the context's stream) of the LAST launch of one named kernel, for roofline accounting in bench.py:
+ * the call that launched it has returned, i.e. the stream is idle.  HITL_ERR_STATE if that kernel has not run yet. */
+enum { HITL_K_STF_SEARCH = 0, HITL_K_EVAL_STF = 1, HITL_K_EM_INLIERS = 2, HITL_K_EM_ASSIGN = 3, HITL_K_WORLD_TRANSFORM = 4, HITL_K_EM_FIT = 5, HITL_K_COUNT = 6 };
+int hitl_last_kernel_ms(hitl_ctx* ctx, int which, float* ms);
 /* Page-locked host memory for the caller's buffers (optional: any host pointer is accepted by every
  * call; pinned ones move at PCIe rate).  NULL on failure. */
 void* hitl_host_alloc(size_t bytes);

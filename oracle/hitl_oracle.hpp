@@ -280,21 +280,25 @@ inline Aff relative_pose_transform(const double* pose_array, unsigned source, un
 
 // JointOptimization.cpp:561-642. Returns kept pairs in (i asc, j asc) order; *n_queries
 // counts the KD queries the reference executes (not skipped by the per-point cap).
-// src_lo/src_hi restrict the SOURCE pose range (for shard tests); targets always span
+// src_lo/src_hi restrict the SOURCE pose range (for shard tests) and src_stride keeps every
+// src_stride-th pose of it (timing samples spread over the trajectory); targets always span
 // [min_poses, poses_end).
 inline void find_stf(const ScanSet& S, const double* pose_array, size_t min_poses, size_t max_poses,
                      const StfOptions& o, std::vector<GlobCorrespondence>* out, uint64_t* n_queries,
-                     size_t src_lo = 0, size_t src_hi = (size_t)-1) {
+                     size_t src_lo = 0, size_t src_hi = (size_t)-1, size_t src_stride = 1) {
   const size_t poses_end = std::min(max_poses + 1, S.points.size());
+  if (src_stride == 0) src_stride = 1;
   out->clear();
   if (poses_end <= min_poses) { if (n_queries) *n_queries = 0; return; }
   const size_t lo = std::max(min_poses, src_lo), hi = std::min(poses_end, src_hi);
-  std::vector<std::vector<GlobCorrespondence> > per_pose(hi > lo ? hi - lo : 0);
+  const size_t n_src = hi > lo ? (hi - lo + src_stride - 1) / src_stride : 0;
+  std::vector<std::vector<GlobCorrespondence> > per_pose(n_src);
   uint64_t queries = 0;
 #if defined(_OPENMP)
 #pragma omp parallel for schedule(static) reduction(+ : queries)
 #endif
-  for (size_t i = lo; i < hi; ++i) {
+  for (size_t q = 0; q < n_src; ++q) {
+    const size_t i = lo + q * src_stride;
     std::vector<int> count(S.points[i].size(), 0);
     for (size_t j = min_poses; j < poses_end; ++j) {
       if (i == j) continue;
@@ -316,7 +320,7 @@ inline void find_stf(const ScanSet& S, const double* pose_array, size_t min_pose
           ++count[k];
         }
       }
-      if (c.points0_indices.size() > o.kMinInterPoseCorrespondence) per_pose[i - lo].push_back(c);
+      if (c.points0_indices.size() > o.kMinInterPoseCorrespondence) per_pose[q].push_back(c);
     }
   }
   for (size_t i = 0; i < per_pose.size(); ++i) out->insert(out->end(), per_pose[i].begin(), per_pose[i].end());

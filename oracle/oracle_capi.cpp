@@ -97,6 +97,17 @@ void orc_find_stf(void* p, const double* poses, uint64_t min_pose, uint64_t max_
   for (size_t i = 0; i < h->stf.size(); ++i) m += h->stf[i].points0_indices.size();
   counts[0] = h->stf.size(); counts[1] = m; counts[2] = h->n_queries;
 }
+// The same with every src_stride-th source pose of [src_lo, src_hi) only (timing samples).
+void orc_find_stf_strided(void* p, const double* poses, uint64_t min_pose, uint64_t max_pose, float thr, float min_cos,
+                          int cap, uint32_t skip, uint32_t min_corr, uint64_t src_lo, uint64_t src_hi, uint64_t src_stride, uint64_t* counts) {
+  Handle* h = static_cast<Handle*>(p);
+  StfOptions o; o.kPointMatchThreshold = thr; o.min_cosine_angle = min_cos; o.kMaxCorrespondencesPerPoint = cap;
+  o.num_skip_readings = skip; o.kMinInterPoseCorrespondence = min_corr;
+  find_stf(h->S, poses, min_pose, max_pose, o, &h->stf, &h->n_queries, src_lo, src_hi, src_stride);
+  uint64_t m = 0;
+  for (size_t i = 0; i < h->stf.size(); ++i) m += h->stf[i].points0_indices.size();
+  counts[0] = h->stf.size(); counts[1] = m; counts[2] = h->n_queries;
+}
 void orc_get_stf(void* p, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx) {
   Handle* h = static_cast<Handle*>(p);
   uint64_t o = 0;

@@ -45,6 +45,8 @@ class Oracle:
         lib.orc_relative_pose.argtypes = [_f64p, C.c_uint32, C.c_uint32, _f32p]
         lib.orc_find_stf.argtypes = [C.c_void_p, _f64p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int,
                                      C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _u64p]
+        lib.orc_find_stf_strided.argtypes = [C.c_void_p, _f64p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int,
+                                             C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, _u64p]
         lib.orc_get_stf.argtypes = [C.c_void_p, _u32p, _u32p, _u64p, _u32p, _u32p]
         lib.orc_find_vo.restype = C.c_uint64
         lib.orc_find_vo.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -255,7 +257,7 @@ class OracleScans:
         return idx[:n].copy()
 
     def find_stf(self, poses, min_pose=0, max_pose=None, thr=0.15, min_cos=None, cap=6, skip=1, min_corr=10,
-                 src_lo=0, src_hi=None):
+                 src_lo=0, src_hi=None, src_stride=1):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1)
         if max_pose is None:
             max_pose = self.n - 1
@@ -264,7 +266,10 @@ class OracleScans:
         if src_hi is None:
             src_hi = 2 ** 62
         counts = np.zeros(3, np.uint64)
-        self.lib.orc_find_stf(self.h, poses, min_pose, max_pose, thr, min_cos, cap, skip, min_corr, src_lo, src_hi, counts)
+        if src_stride != 1:
+            self.lib.orc_find_stf_strided(self.h, poses, min_pose, max_pose, thr, min_cos, cap, skip, min_corr, src_lo, src_hi, src_stride, counts)
+        else:
+            self.lib.orc_find_stf(self.h, poses, min_pose, max_pose, thr, min_cos, cap, skip, min_corr, src_lo, src_hi, counts)
         npairs, nm = int(counts[0]), int(counts[1])
         pi, pj = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32)
         off = np.zeros(npairs + 1, np.uint64)

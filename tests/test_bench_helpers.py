@@ -23,9 +23,20 @@ def test_reference_sample_times_the_references_own_loop(bench, maps):
     if not RefBackend.available(fast=True):
         pytest.skip("oracle/_ref/libhitl_ref_fast.so not built")
     g = maps("small")
-    r = bench.ref_sample(g, seconds=0.5)
+    r = bench.ref_sample(g, steps=1)
     assert r["kind"] == "reference" and r["unit"] == bench.UNIT and r["cores"] >= 1 and r["value"] > 0
     assert "JointOpt::FindSTFCorrespondences" in r["sample"] and r["seconds"] > 0
+    # the sample is FIXED by the map size alone (same in every run, at every N) and covers the full map's targets
+    a, b = bench.RefSampler(g), bench.RefSampler(g)
+    assert a.stride == b.stride == 1 and np.array_equal(a.ids, b.ids) and a.queries == b.queries > 0
+    big = {"poses": np.zeros((5000, 3), np.float32), "offsets": np.arange(5001, dtype=np.uint64) * 715}
+    assert max(1, int(round(5000 * float(big["offsets"][-1]) / bench.REF_SAMPLE_UNIT))) == 16
+
+
+def test_cpu_legs_use_every_host_thread_even_under_torchrun(bench, monkeypatch):
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")                 # what torch.distributed.run exports to its workers
+    n = bench.use_all_host_threads()
+    assert n == bench.host_threads() >= 1 and os.environ["OMP_NUM_THREADS"] == str(n)
 
 
 def test_port_sample_and_reference_arm_line(bench, maps, tmp_path):
@@ -43,6 +54,15 @@ def test_port_sample_and_reference_arm_line(bench, maps, tmp_path):
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"] and d["config"]["n_poses"] == 120
+    assert d["cpu_baseline"]["cores"] == bench.host_threads() and d["scaling"] == "strong" and d["config"]["parallelism"] == "single GPU"
+    # torchrun's OMP_NUM_THREADS=1 must not reach the reference arm, and rank 0 of an N-rank launch reports the same sample
+    env8 = dict(env, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="8", LOCAL_RANK="0")
+    out8 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8", "--workload", "c2", "--poses", "120", "--beams", "90", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=env8, timeout=600)
+    assert out8.returncode == 0, out8.stderr[-2000:]
+    d8 = json.loads([l for l in out8.stdout.splitlines() if l.strip()][0])
+    assert d8["cpu_baseline"]["cores"] == bench.host_threads() and d8["n_gpus"] == 8
+    assert d8["cpu_baseline"]["sample"].split(" in ")[0] == d["cpu_baseline"]["sample"].split(" in ")[0]      # same fixed sample, same counts
 
 
 def test_reference_arm_other_ranks_exit_quietly(tmp_path):

@@ -588,7 +588,9 @@ def test_error_paths(gpu):
     from hitl_slam_b200 import HitlError, HitlGpu
     fresh = HitlGpu(0)
     with pytest.raises(HitlError):
-        fresh.find_stf(np.zeros(3))                      # scans not set
+        fresh.find_stf(np.zeros(0))                      # scans not set (library state check)
+    with pytest.raises(HitlError):
+        fresh.find_stf(np.zeros(3))                      # wrapper: 3 values for a map of 0 poses
     with pytest.raises(HitlError):
         fresh.em_inliers(np.zeros(4, np.float32))        # world clouds not set
     fresh.set_scans(np.array([0, 2], np.uint32), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32))
@@ -596,6 +598,27 @@ def test_error_paths(gpu):
         fresh.set_scans(np.array([0, 3, 2], np.uint32), np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32))
     with pytest.raises(HitlError):
         fresh.set_human_blocks(np.array([[3, 0]], np.int32), np.zeros((1, 4)))   # corner type unsupported, as in the reference
+    # a rejected hitl_set_scans leaves the context as it was (validation precedes every state change) ...
+    fresh.set_odometry_blocks(np.zeros((0, 9), np.float32))
+    assert fresh.lib.hitl_set_scans(fresh.ctx, 2, np.array([0, 3, 2], np.uint32), np.zeros(6, np.float32), np.zeros(6, np.float32)) != 0
+    fresh.n_poses, fresh.n_points = 1, 2
+    fresh.build_kdtrees()
+    assert fresh.find_stf(np.zeros(3))["n_pairs"] == 0
+    with pytest.raises(HitlError):
+        fresh.find_stf(np.zeros(6))                      # pose array of another map
+    # ... and a successful one drops the residual blocks registered for the previous map (their indices were checked against it)
+    fresh.set_scans(np.array([0, 2, 4, 6], np.uint32), np.zeros((6, 2), np.float32), np.zeros((6, 2), np.float32))
+    fresh.set_odometry_blocks(np.zeros((2, 9), np.float32) + 1)
+    assert fresh.layout().n_odometry == 2
+    fresh.set_scans(np.array([0, 2], np.uint32), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32))
+    assert fresh.layout().n_odometry == 0
+    with pytest.raises(HitlError):
+        fresh.set_p2l_glob_blocks(np.zeros(2, np.uint32), np.array([0, 3, 2], np.uint64), np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32),
+                                  np.zeros(3, np.float32), np.ones(3, np.uint8), 0.05, 0.025)   # blk_off not monotone
+    with pytest.raises(HitlError):
+        fresh.debug_relative_pose(np.zeros(3), [0], [5])                                        # pose index out of range
+    fresh.build_kdtrees()
+    assert fresh.find_stf(np.zeros(3), opts=fresh.stf_opts(min_corr=0xFFFFFFFF))["n_pairs"] == 0   # min_corr + 1 must not wrap to a zero divisor
     fresh.close()
 
 

@@ -533,3 +533,34 @@ def test_reference_stf_problem_evaluation_matches_the_oracle(oracle, ref, maps):
     from oracle.pyoracle import RefDropin
     if RefDropin.available(blocks=True):
         assert RefDropin(blocks=True).lib.dropin_has_gpu_blocks() == 1 and RefDropin().lib.dropin_has_gpu_blocks() == 0
+
+
+def test_source_samples_of_a_full_map(oracle, ref, maps):
+    """bench.py's reference arm times the reference's own FindSTFCorrespondences on a SAMPLE of source poses against all targets of the full
+    map (RefJointOpt.restrict_sources parks the other poses' point_clouds_g_ entries; the loop itself is untouched).  The sampled search
+    must return exactly the rows of the full search whose source pose is in the sample, and the oracle's strided search (which supplies
+    the executed-query count) must agree with both."""
+    g = maps("small")
+    n = len(g["poses"])
+    poses = g["poses"].astype(np.float64)
+    J = ref.joint_opt(g["offsets"], g["pts"], g["nrm"], g["poses"])
+    full = J.find_stf(poses)
+    full = {k: np.array(v) for k, v in full.items()}
+    S = oracle.scans(g["offsets"], g["pts"], g["nrm"])
+    for stride, phase in ((7, 0), (16, 5), (1, 0)):
+        ids = np.arange(phase, n, stride)
+        J.restrict_sources(ids)
+        part = J.find_stf(poses)
+        keep = np.isin(full["pair_i"], ids)
+        assert np.array_equal(part["pair_i"], full["pair_i"][keep]) and np.array_equal(part["pair_j"], full["pair_j"][keep])
+        cnt = np.diff(full["pair_off"].astype(np.int64))
+        rows = np.repeat(keep, cnt)
+        assert np.array_equal(part["k"], full["k"][rows]) and np.array_equal(part["idx"], full["idx"][rows])
+        port = S.find_stf(poses, src_lo=phase, src_stride=stride)
+        assert_same_stf(port, part)
+        per_pose = [S.find_stf(poses, src_lo=int(i), src_hi=int(i) + 1)["n_queries"] for i in ids[:5]]
+        assert port["n_queries"] >= sum(per_pose)
+    J.restrict_sources(None)
+    assert_same_stf(J.find_stf(poses), full)
+    whole = S.find_stf(poses)
+    assert sum(S.find_stf(poses, src_lo=p, src_stride=4)["n_queries"] for p in range(4)) == whole["n_queries"]
