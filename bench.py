@@ -294,7 +294,7 @@ def config_of(args, g, world=1):
                         % (args.workload, len(g["poses"]), args.beams or 0, int(g["offsets"][-1])),
             "n_poses": int(len(g["poses"])), "n_points": int(g["offsets"][-1]),
             "l2": "scans + trees + record buffers exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
-            "parallelism": ("source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 all-reduce of packed J^TJ/J^Tr per step" % world
+            "parallelism": ("source-pose shards x%d cut at equal measured work (scans+trees replicated), no collective in the search, 1 in-library ncclAllReduce (hitl_normal_eq_allreduce) of packed J^TJ/J^Tr per step" % world
                             if world > 1 else "single GPU")}
 
 
@@ -312,6 +312,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
+    ap.add_argument("--no-largest-map", action="store_true", help="N > 1: skip the config-3 (20k x 1080) leg that measures the N-GPU speed-up on the largest map")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check of the benchmarked search against the oracle")
     ap.add_argument("--replay", type=int, default=0, help="BASELINE config 4: replay this many sequential corrections on --replay-workload and report per-correction latency")
     ap.add_argument("--replay-workload", default="c4")
@@ -361,33 +362,28 @@ def main():
     odo = odometry_consts_host(g["poses"]) if rank == 0 else np.zeros((0, 9), np.float32)
     gpu.set_odometry_blocks(odo)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    neq_dev = None
     poses_pinned = gpu.pinned_copy(poses)          # the per-call pose upload (120 KB at c2) comes from page-locked memory: no staging copy in the driver
 
     debug = bool(os.environ.get("HITL_BENCH_DEBUG"))
     trace = []
+
+    if world > 1:
+        # The product's own communicator (comm.cu: NCCL bound inside libhitl_gpu.so): rank 0 draws the id, torch.distributed only carries
+        # the 128 bytes to the other ranks (out-of-band plumbing, like MPI would); every collective of a step is a C-ABI call.
+        uid = [HitlGpu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.comm_init(uid[0], rank, world)
 
     def step():
         t0 = time.perf_counter()
         info = gpu.find_stf(poses_pinned, src_lo=lo, src_hi=hi, fetch=False)
         t1 = time.perf_counter()
         gpu.set_stf_blocks_from_search(STD_DEV, CORR)
-        ne = gpu.normal_eq(poses_pinned, fetch=False)
-        t2 = time.perf_counter()
-        if world > 1:
-            nonlocal neq_dev
-            ptr, nd = gpu.normal_eq_device()
-            if neq_dev is None or neq_dev[0] != ptr:
-                neq_dev = (ptr, tensor_from_ptr(ptr, nd, local_rank))
-            with torch.cuda.stream(stream):
-                if debug:
-                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ea.record()
-                dist.all_reduce(neq_dev[1])
-                if debug:
-                    eb.record()
-                    eb.synchronize()
-                    trace.append((t1 - t0, t2 - t1, time.perf_counter() - t2, ea.elapsed_time(eb), info["ms_total"], ne["ms"]))
+        # this rank's J^T J / J^T r blocks and, on the same stream without a host synchronisation in between, the in-library
+        # ncclAllReduce(sum, f64) of the packed [H_diag | g | cost] buffer (hitl_normal_eq_allreduce; at N = 1 it is hitl_normal_eq)
+        ne = gpu.normal_eq_allreduce(poses_pinned, fetch=False)
+        if debug:
+            trace.append((t1 - t0, time.perf_counter() - t1, info["ms_total"], ne["ms"], gpu.last_kernel_ms("allreduce") if world > 1 else 0.0))
         return info, ne
 
     if world > 1:
@@ -434,8 +430,8 @@ def main():
     launches = gpu.launch_count() - launches0
     if debug and trace:
         for k, tr in enumerate(trace[-args.steps:]):
-            sys.stderr.write("[rank %d] step %d: host find_stf %.3f ms (device %.3f) | host normal_eq %.3f ms (device %.3f) | all-reduce host %.3f ms, on stream %.3f ms | events %.3f ms\n"
-                             % (rank, k, tr[0] * 1e3, tr[4], tr[1] * 1e3, tr[5], tr[2] * 1e3, tr[3], starts[k].elapsed_time(ends[k])))
+            sys.stderr.write("[rank %d] step %d: host find_stf %.3f ms (device %.3f) | host normal_eq+all-reduce %.3f ms (device %.3f, all-reduce on stream %.3f) | events %.3f ms\n"
+                             % (rank, k, tr[0] * 1e3, tr[2], tr[1] * 1e3, tr[3], tr[4], starts[k].elapsed_time(ends[k])))
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
@@ -579,11 +575,20 @@ def main():
         else:
             cpu["port"] = port            # the oracle port on a full-map sample, timed beside the reference's own code
 
+    largest = None
+    if world > 1 and not args.no_largest_map and args.workload == "c2":
+        try:
+            gpu.comm_destroy()
+            gpu.close()                                  # frees the c2 context before the 21.4 M-point map is loaded
+            largest = largest_map_leg(args, rank, world, local_rank)
+        except Exception as e:
+            largest = {"error": str(e)[:300]}
+
     if rank == 0:
         cfg = config_of(args, g, world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 search / f64 residuals", "data": "synthetic", "config": cfg,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_checked": parity, "cpu_baseline": cpu, "correction_latency": correction, "correction_replay": replay,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_checked": parity, "cpu_baseline": cpu, "correction_latency": correction, "correction_replay": replay, "largest_map": largest,
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
                            "kdtree_build_device_s": t_build, "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
                            "per_rank_[ms_search,ms_find_stf,tiles,source_poses]": per_rank}}
@@ -807,15 +812,88 @@ def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
             "n_poses": int(n), "n_points": int(g["offsets"][-1])}
 
 
-def tensor_from_ptr(ptr, n_doubles, device_index):
-    """Wrap the library's resident normal-equation buffer as a torch tensor (no copy) for NCCL."""
+def largest_map_leg(args, rank, world, local_rank, name="c3", steps=3, warmup=4):
+    """north_star: ">= 5x at 8 GPUs on the largest synthetic map".  BASELINE config 3 (20 000 poses x 1080 beams, 21.4 M points) sharded over
+    the N ranks exactly like the headline step (source ranges cut at equal measured work, replicated scans + trees, one in-library
+    all-reduce per step), timed as the max over ranks of CUDA-event time per step; then rank 0 ALONE runs the same step over the whole
+    map on its one GPU, in the same process and run, and `speedup_vs_1` is the ratio of the two."""
     import torch
+    import torch.distributed as dist
+    from hitl_slam_b200 import HitlGpu, synth
+    from hitl_slam_b200.sharding import shard_ranges, shard_ranges_by_work
+    cfg = synth.CONFIGS[name]
+    if rank == 0:
+        g = workload(name, cfg["n_poses"], cfg["beams"])
+    dist.barrier()
+    if rank != 0:
+        g = workload(name, cfg["n_poses"], cfg["beams"])
+    poses = g["poses"].astype(np.float64)
+    n = len(poses)
+    gpu = HitlGpu(local_rank)
+    stream = torch.cuda.ExternalStream(gpu.lib.hitl_stream(gpu.ctx), device=torch.device("cuda", local_rank))
+    gpu.set_scans(g["offsets"], g["pts"], g["nrm"])
+    gpu.build_kdtrees()
+    uid = [HitlGpu.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    gpu.comm_init(uid[0], rank, world)
+    gpu.set_odometry_blocks(odometry_consts_host(g["poses"]) if rank == 0 else np.zeros((0, 9), np.float32))
+    pp = gpu.pinned_copy(poses)
+    lo, hi = shard_ranges(g["offsets"], world)[rank]
+    est = None
+    for _ in range(3):                                   # setup: cut the source ranges at equal measured work
+        gpu.find_stf(pp, src_lo=lo, src_hi=hi, fetch=False)
+        work = torch.from_numpy(gpu.stf_work().astype(np.float64)).cuda()
+        dist.all_reduce(work)
+        wk = work.cpu().numpy()
+        est = wk if est is None else 0.5 * (est + wk)
+        lo, hi = shard_ranges_by_work(est, world)[rank]
 
-    class _Arr:
-        pass
-    a = _Arr()
-    a.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-    return torch.as_tensor(a, device=torch.device("cuda", device_index))
+    def one(lo_, hi_, collective):
+        info = gpu.find_stf(pp, src_lo=lo_, src_hi=hi_, fetch=False)
+        gpu.set_stf_blocks_from_search(STD_DEV, CORR)
+        ne = gpu.normal_eq_allreduce(pp, fetch=False) if collective else gpu.normal_eq(pp, fetch=False)
+        return info, ne
+
+    def timed(lo_, hi_, collective, sync_ranks):
+        for _ in range(warmup):
+            one(lo_, hi_, collective)
+        tot, last = 0.0, None
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            if sync_ranks:
+                dist.barrier()
+            with torch.cuda.stream(stream):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            last = one(lo_, hi_, collective)
+            with torch.cuda.stream(stream):
+                b.record()
+            b.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / steps, last
+
+    ms_n, last = timed(lo, hi, True, True)
+    t = torch.tensor([ms_n], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([float(last[0]["n_queries"]), float(last[0]["n_matches"]), float(last[0]["n_pairs"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(cnt)
+    per_rank = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(per_rank, torch.tensor([last[0]["ms_search"], last[0]["ms_total"], float(hi - lo)], dtype=torch.float64, device="cuda"))
+    ms_n = float(t.item())
+    out = None
+    gpu.comm_destroy()
+    if rank == 0:
+        ms_1, last1 = timed(0, n, False, False)          # the whole map on ONE GPU (this rank's), same code, same run
+        evals = float(cnt[0].item() + cnt[1].item())
+        assert int(last1[0]["n_queries"]) == int(cnt[0].item()) and int(last1[0]["n_matches"]) == int(cnt[1].item()), "sharded and single-GPU searches disagree"
+        out = {"workload": "%s: %d poses x %d beams (%d points)" % (name, n, cfg["beams"], int(g["offsets"][-1])), "n_gpus": world,
+               "ms_per_step": ms_n, "ms_per_step_1gpu": ms_1, "speedup_vs_1": ms_1 / ms_n, "value": evals / (ms_n * 1e-3) / 1e6, "value_1gpu": evals / (ms_1 * 1e-3) / 1e6, "unit": UNIT,
+               "queries_per_step": int(cnt[0].item()), "jacobian_evals_per_step": int(cnt[1].item()), "residual_blocks": int(cnt[2].item()),
+               "counts_equal_single_gpu": True, "steps": steps, "warmup": warmup,
+               "per_rank_[ms_search,ms_find_stf,source_poses]": [[round(float(x), 3) for x in r.tolist()] for r in per_rank]}
+    gpu.close()
+    dist.barrier()
+    return out
 
 
 def odometry_consts_host(poses_f32):

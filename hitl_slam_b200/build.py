@@ -27,6 +27,7 @@ GPU_SOURCES = [
     ("kdtree_gpu.cu", ["--fmad=false"]),
     ("backprop.cu", ["--fmad=false"]),
     ("eval.cu", []),
+    ("comm.cu", []),
     ("kdtree_build.cpp", []),
 ]
 
@@ -64,7 +65,7 @@ def build_gpu(force=False, verbose=False):
                 print(out)
     so = os.path.join(LIB, "libhitl_gpu.so")
     if force or _newer(so, objs):
-        _run([NVCC, "-shared", "-ccbin", GXX] + ARCH + ["-o", so] + objs + ["-Xcompiler", "-pthread"])
+        _run([NVCC, "-shared", "-ccbin", GXX] + ARCH + ["-o", so] + objs + ["-Xcompiler", "-pthread", "-ldl"])   # NCCL is bound at run time (comm.cu)
     return so
 
 

@@ -30,7 +30,8 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
+    "hitl_normal_eq_device", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks",
+    "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
     "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
 
@@ -89,6 +90,12 @@ class HitlGpu:
         lib.hitl_launch_count.argtypes = [vp]
         lib.hitl_sm_count.argtypes = [vp]
         lib.hitl_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+        lib.hitl_comm_unique_id.argtypes = [vp]
+        lib.hitl_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        lib.hitl_comm_destroy.argtypes = [vp]
+        lib.hitl_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.hitl_normal_eq_allreduce.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+        lib.hitl_gather_stf_blocks.argtypes = [vp, C.c_int, C.c_uint64, _u64p, vp, vp, vp, vp]
         lib.hitl_host_alloc.restype = vp
         lib.hitl_host_alloc.argtypes = [C.c_size_t]
         lib.hitl_host_free.argtypes = [vp]
@@ -397,6 +404,60 @@ class HitlGpu:
         self._ck(self.lib.hitl_normal_eq(self.ctx, poses, H.ctypes.data, g.ctypes.data, Ho.ctypes.data, cost.ctypes.data, C.byref(ms)))
         return dict(H_diag=H.reshape(n, 3, 3), g=g.reshape(n, 3), H_off=Ho[:9 * nbin].reshape(-1, 3, 3), cost=float(cost[0]), ms=ms.value)
 
+    # ---- multi-GPU exchange (NCCL inside the C ABI) ----
+    @staticmethod
+    def comm_unique_id():
+        """128-byte ncclUniqueId from hitl_comm_unique_id (one rank calls it; hand the bytes to the others out of band)."""
+        lib = load_gpu_library()
+        lib.hitl_comm_unique_id.argtypes = [C.c_void_p]
+        buf = (C.c_ubyte * 128)()
+        if lib.hitl_comm_unique_id(buf) != 0:
+            raise HitlError("hitl_comm_unique_id: NCCL is not available in this process")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.hitl_comm_init(self.ctx, buf, rank, world))
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_destroy(self):
+        self._ck(self.lib.hitl_comm_destroy(self.ctx))
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.hitl_comm_info(self.ctx, C.byref(r), C.byref(w), C.byref(v)))
+        return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+    def normal_eq_allreduce(self, poses=None, fetch=True):
+        """hitl_normal_eq_allreduce: (poses given) this rank's normal equations, then the in-library ncclAllReduce of [H_diag | g | cost]."""
+        n = self.n_poses
+        ms = C.c_float()
+        pp = self._poses(poses, what="normal_eq_allreduce").ctypes.data if poses is not None else None
+        if not fetch:
+            self._ck(self.lib.hitl_normal_eq_allreduce(self.ctx, pp, None, None, None, C.byref(ms)))
+            return dict(ms=ms.value)
+        H, g, cost = np.zeros(9 * n), np.zeros(3 * n), np.zeros(1)
+        self._ck(self.lib.hitl_normal_eq_allreduce(self.ctx, pp, H.ctypes.data, g.ctypes.data, cost.ctypes.data, C.byref(ms)))
+        return dict(H_diag=H.reshape(n, 3, 3), g=g.reshape(n, 3), cost=float(cost[0]), ms=ms.value)
+
+    def gather_stf_blocks(self, root=0, cap_blocks=None):
+        """hitl_gather_stf_blocks after eval(): on root the STF blocks of all ranks in rank order (pair_i, pair_j, r [B,2], J [B,2,2,3])."""
+        world = getattr(self, "comm_world", 1)
+        rank = getattr(self, "comm_rank", 0)
+        counts = np.zeros(world, np.uint64)
+        if rank != root:
+            self._ck(self.lib.hitl_gather_stf_blocks(self.ctx, root, 0, counts, None, None, None, None))
+            return dict(counts=counts)
+        if cap_blocks is None:                          # sizes first (the collective runs once more with buffers that fit)
+            cap_blocks = int(self.layout().n_stf) if world == 1 else None
+        if cap_blocks is None:
+            raise HitlError("gather_stf_blocks: pass cap_blocks on the root of a multi-rank job (all ranks make ONE collective call)")
+        pi, pj = np.zeros(max(cap_blocks, 1), np.uint32), np.zeros(max(cap_blocks, 1), np.uint32)
+        r, J = np.zeros(2 * max(cap_blocks, 1)), np.zeros(12 * max(cap_blocks, 1))
+        self._ck(self.lib.hitl_gather_stf_blocks(self.ctx, root, cap_blocks, counts, pi.ctypes.data, pj.ctypes.data, r.ctypes.data, J.ctypes.data))
+        t = int(counts.sum())
+        return dict(counts=counts, pair_i=pi[:t], pair_j=pj[:t], r=r[:2 * t].reshape(-1, 2), J=J[:12 * t].reshape(-1, 2, 2, 3))
+
     def normal_eq_device(self):
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self.lib.hitl_normal_eq_device(self.ctx, C.byref(p), C.byref(n)))
@@ -445,7 +506,7 @@ class HitlGpu:
         self._ck(self.lib.hitl_debug_relative_pose(self.ctx, poses, len(src), src, dst, out))
         return out.reshape(-1, 6)
 
-    KERNELS = {"stf_search_kernel": 0, "eval_stf_kernel": 1, "em_inliers_kernel": 2, "em_assign_kernel": 3, "world_transform_kernel": 4, "em_fit_kernel": 5}
+    KERNELS = {"stf_search_kernel": 0, "eval_stf_kernel": 1, "em_inliers_kernel": 2, "em_assign_kernel": 3, "world_transform_kernel": 4, "em_fit_kernel": 5, "allreduce": 6}
 
     def last_kernel_ms(self, name):
         """Duration of the last launch of one named kernel (CUDA events on the library's stream)."""

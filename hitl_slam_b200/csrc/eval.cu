@@ -362,6 +362,7 @@ using namespace hitl;
 extern "C" int hitl_set_stf_blocks_from_search(hitl_ctx* ctx, float std_dev, float corr) {
   if (!ctx) return HITL_ERR_ARG;
   if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_set_stf_blocks_from_search: no search result");
+  ctx->eval_valid = ctx->neq_valid = false;
   ctx->stf_from_search = true; ctx->nb_stf = ctx->n_pairs; ctx->stf_std = std_dev; ctx->stf_corr = corr;
   return HITL_OK;
 }
@@ -388,6 +389,7 @@ extern "C" int hitl_set_stf_blocks(hitl_ctx* ctx, uint64_t n_pairs, const uint32
     HITL_CUDA(cudaMemcpyAsync(ctx->d_blk_idx.p, idx, 4 * nm, cudaMemcpyHostToDevice, ctx->stream));
     HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  ctx->eval_valid = ctx->neq_valid = false;
   ctx->stf_from_search = false; ctx->nb_stf = n_pairs; ctx->stf_std = std_dev; ctx->stf_corr = corr;
   return HITL_OK;
 }
@@ -399,7 +401,7 @@ extern "C" int hitl_set_odometry_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
     for (int q = 4; q < 7; ++q) if (!(consts9[9 * b + q] > 0.0f)) return fail(ctx, HITL_ERR_ARG, "hitl_set_odometry_blocks: std-dev must be > 0");
   HITL_CUDA(ctx->d_odo.ensure(9 * (size_t)n_blocks));
   if (n_blocks) HITL_CUDA(cudaMemcpy(ctx->d_odo.p, consts9, 36 * (size_t)n_blocks, cudaMemcpyHostToDevice));
-  ctx->nb_odo = n_blocks;
+  ctx->nb_odo = n_blocks; ctx->eval_valid = ctx->neq_valid = false;
   return HITL_OK;
 }
 extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int32_t* type_pose, const double* targets4) {
@@ -415,7 +417,7 @@ extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int
     HITL_CUDA(cudaMemcpy(ctx->d_hum_i.p, type_pose, 8 * (size_t)n_blocks, cudaMemcpyHostToDevice));
     HITL_CUDA(cudaMemcpy(ctx->d_hum_d.p, targets4, 32 * (size_t)n_blocks, cudaMemcpyHostToDevice));
   }
-  ctx->nb_human = n_blocks;
+  ctx->nb_human = n_blocks; ctx->eval_valid = ctx->neq_valid = false;
   return HITL_OK;
 }
 extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const uint32_t* blk_pose, const uint64_t* blk_off, const float* pts_xy,
@@ -436,6 +438,7 @@ extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
       HITL_CUDA(cudaMemcpy(ctx->d_p2lg_o.p, lo, 4 * m, cudaMemcpyHostToDevice)); HITL_CUDA(cudaMemcpy(ctx->d_p2lg_v.p, valid, m, cudaMemcpyHostToDevice));
     }
   }
+  ctx->eval_valid = ctx->neq_valid = false;
   ctx->nb_p2lg = n_blocks; ctx->p2lg_std = std_dev; ctx->p2lg_corr = corr;
   return HITL_OK;
 }
@@ -451,6 +454,7 @@ extern "C" int hitl_set_p2l_blocks(hitl_ctx* ctx, uint64_t n, const uint32_t* po
     HITL_CUDA(cudaMemcpy(ctx->d_p2l_n.p, ln_xy, 8 * n, cudaMemcpyHostToDevice)); HITL_CUDA(cudaMemcpy(ctx->d_p2l_o.p, lo, 4 * n, cudaMemcpyHostToDevice));
     HITL_CUDA(cudaMemcpy(ctx->d_p2l_v.p, valid, n, cudaMemcpyHostToDevice));
   }
+  ctx->eval_valid = ctx->neq_valid = false;
   ctx->nb_p2l = n; ctx->p2l_std = std_dev; ctx->p2l_corr = corr;
   return HITL_OK;
 }
@@ -523,6 +527,7 @@ extern "C" int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision,
   int rc = precision == 1 ? launch_all<float>(ctx, ctx->d_r.p, J_out ? ctx->d_J.p : nullptr, none, 0)
                           : launch_all<double>(ctx, ctx->d_r.p, J_out ? ctx->d_J.p : nullptr, none, 0);
   if (rc) return rc;
+  ctx->eval_valid = J_out != nullptr;
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (r_out && L.n_residuals) HITL_CUDA(cudaMemcpyAsync(r_out, ctx->d_r.p, 8 * L.n_residuals, cudaMemcpyDeviceToHost, ctx->stream));
   if (J_out && L.n_jacobian) HITL_CUDA(cudaMemcpyAsync(J_out, ctx->d_J.p, 8 * L.n_jacobian, cudaMemcpyDeviceToHost, ctx->stream));
@@ -531,24 +536,36 @@ extern "C" int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision,
   return HITL_OK;
 }
 
-extern "C" int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* H_off, double* cost, float* ms_out) {
-  if (!ctx) return HITL_ERR_ARG;
-  if (!pose_array) return fail(ctx, HITL_ERR_ARG, "hitl_normal_eq: null poses");
+namespace hitl {
+// Asynchronous part of hitl_normal_eq (also the first half of hitl_normal_eq_allreduce): pose upload, zero fill, the evaluation kernels.
+int normal_eq_launch(hitl_ctx* ctx, const double* pose_array) {
   if (ctx->nb_stf && ctx->stf_from_search && !ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_normal_eq: search result was invalidated");
   const size_t n = ctx->n_poses, nbin = ctx->nb_odo + ctx->nb_stf;
+  ctx->neq_valid = false;
   HITL_CUDA(ctx->d_pose.ensure(3 * n));
   HITL_CUDA(ctx->d_neq.ensure(12 * n + 1)); HITL_CUDA(ctx->d_hoff.ensure(9 * nbin));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_pose.p, pose_array, 24 * n, cudaMemcpyHostToDevice, ctx->stream));
-  HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_neq.p, 0, 8 * (12 * n + 1), ctx->stream));
   NeqOut q; q.H_diag = ctx->d_neq.p; q.g = ctx->d_neq.p + 9 * n; q.cost = ctx->d_neq.p + 12 * n; q.H_off = ctx->d_hoff.p;
-  int rc = launch_all<double>(ctx, nullptr, nullptr, q, 1);
+  const int rc = launch_all<double>(ctx, nullptr, nullptr, q, 1);
+  if (rc) return rc;
+  ctx->neq_valid = true;
+  return HITL_OK;
+}
+}  // namespace hitl
+
+extern "C" int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* H_off, double* cost, float* ms_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!pose_array) return fail(ctx, HITL_ERR_ARG, "hitl_normal_eq: null poses");
+  const size_t n = ctx->n_poses, nbin = ctx->nb_odo + ctx->nb_stf;
+  HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  const int rc = hitl::normal_eq_launch(ctx, pose_array);
   if (rc) return rc;
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-  if (H_diag && n) HITL_CUDA(cudaMemcpyAsync(H_diag, q.H_diag, 72 * n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (g && n) HITL_CUDA(cudaMemcpyAsync(g, q.g, 24 * n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (H_off && nbin) HITL_CUDA(cudaMemcpyAsync(H_off, q.H_off, 72 * nbin, cudaMemcpyDeviceToHost, ctx->stream));
-  if (cost) HITL_CUDA(cudaMemcpyAsync(cost, q.cost, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (H_diag && n) HITL_CUDA(cudaMemcpyAsync(H_diag, ctx->d_neq.p, 72 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (g && n) HITL_CUDA(cudaMemcpyAsync(g, ctx->d_neq.p + 9 * n, 24 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (H_off && nbin) HITL_CUDA(cudaMemcpyAsync(H_off, ctx->d_hoff.p, 72 * nbin, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cost) HITL_CUDA(cudaMemcpyAsync(cost, ctx->d_neq.p + 12 * n, 8, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ms_out) HITL_CUDA(cudaEventElapsedTime(ms_out, ctx->ev[0], ctx->ev[1]));
   return HITL_OK;

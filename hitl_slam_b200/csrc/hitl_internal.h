@@ -164,6 +164,14 @@ struct hitl_ctx {
   hitl::DevBuf<double> d_r, d_J, d_neq, d_hoff;
   hitl::DevBuf<double2> d_trig;          // per pose (cos, sin), (x, y) of the current evaluation point
 
+  bool neq_valid = false, eval_valid = false;   // d_neq / d_r + d_J hold the result of a completed evaluation of the current blocks
+  // ---- multi-GPU exchange (comm.cu) ----
+  void* comm = nullptr;                  // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  hitl::DevBuf<uint64_t> d_comm_cnt;
+  hitl::DevBuf<uint32_t> d_g_pi, d_g_pj; // gathered STF blocks (root only)
+  hitl::DevBuf<double> d_g_r, d_g_J;
+
   // pinned staging for small read-backs
   uint64_t* h_pinned = nullptr;          // 64 x u64
 };

@@ -20,6 +20,8 @@
  *                                         1054-1133, 1299-1415; point-to-line :314-385, :557-622)
  *   hitl_normal_eq                        per-pose 3x3 J^T J / J^T r blocks of the same problem (input of the
  *                                         Gauss-Newton / LM step the host solver takes)
+ *   hitl_comm_* / hitl_normal_eq_allreduce / hitl_gather_stf_blocks   the one exchange of a multi-GPU iteration (NCCL inside the
+ *                                         boundary): OMP-over-source-poses of :575 becomes one rank per source range
  *
  * Conventions: plain pointers and sizes; the caller owns every host buffer; the context owns
  * all device memory; scans/trees are uploaded once per session, poses per call. Every call
@@ -44,7 +46,7 @@ enum {
   HITL_ERR_CUDA = 2,      /* CUDA runtime error (message in hitl_last_error) */
   HITL_ERR_STATE = 3,     /* call order: scans / trees / blocks not set */
   HITL_ERR_OVERFLOW = 4,  /* caller buffer too small */
-  HITL_ERR_NCCL = 5
+  HITL_ERR_NCCL = 5       /* NCCL missing or a collective failed (hitl_comm_*, hitl_normal_eq_allreduce, hitl_gather_stf_blocks) */
 };
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -58,7 +60,7 @@ uint64_t hitl_launch_count(const hitl_ctx* ctx);
 int hitl_sm_count(const hitl_ctx* ctx);
 /* Duration (ms, CUDA events on the context's stream) of the LAST launch of one named kernel, for roofline accounting in bench.py:
  * the call that launched it has returned, i.e. the stream is idle.  HITL_ERR_STATE if that kernel has not run yet. */
-enum { HITL_K_STF_SEARCH = 0, HITL_K_EVAL_STF = 1, HITL_K_EM_INLIERS = 2, HITL_K_EM_ASSIGN = 3, HITL_K_WORLD_TRANSFORM = 4, HITL_K_EM_FIT = 5, HITL_K_COUNT = 6 };
+enum { HITL_K_STF_SEARCH = 0, HITL_K_EVAL_STF = 1, HITL_K_EM_INLIERS = 2, HITL_K_EM_ASSIGN = 3, HITL_K_WORLD_TRANSFORM = 4, HITL_K_EM_FIT = 5, HITL_K_ALLREDUCE = 6, HITL_K_COUNT = 7 };
 int hitl_last_kernel_ms(hitl_ctx* ctx, int which, float* ms);
 /* Page-locked host memory for the caller's buffers (optional: any host pointer is accepted by every
  * call; pinned ones move at PCIe rate).  NULL on failure. */
@@ -220,6 +222,30 @@ int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, doub
                    float* ms_out);
 /* Device pointer + length (doubles) of the packed [H_diag | g | cost] buffer of the last hitl_normal_eq. */
 int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
+
+/* ---- multi-GPU exchange -------------------------------------------------------- */
+/* One context per GPU (one process per GPU, or several contexts in one process driven by one host thread each).  The search
+ * shards by source pose with no collective (hitl_find_stf's src_lo / src_hi); scans and trees are replicated.  The context owns
+ * an NCCL communicator, bound at run time (libnccl.so.2); every failure of the layer returns HITL_ERR_NCCL.
+ * hitl_comm_unique_id: on ONE rank, fills HITL_COMM_ID_BYTES (an ncclUniqueId) to be handed to the others out of band
+ * (MPI / torch.distributed / a file).  hitl_comm_init is collective: every rank of the job calls it with the same id. */
+#define HITL_COMM_ID_BYTES 128
+int hitl_comm_unique_id(void* id_out);
+int hitl_comm_init(hitl_ctx* ctx, const void* nccl_unique_id, int rank, int world);
+int hitl_comm_destroy(hitl_ctx* ctx);
+int hitl_comm_info(const hitl_ctx* ctx, int* rank, int* world, int* nccl_version);
+/* The per-iteration collective (PostHumanOptimization's Gauss-Newton / LM loop, JointOptimization.cpp:1192-1208): when pose_array is
+ * not NULL, evaluates the normal equations of THIS rank's blocks as hitl_normal_eq does, then — same stream, no host
+ * synchronisation in between — one ncclAllReduce(sum, f64) over the packed resident buffer [H_diag n_poses x 9 | g n_poses x 3 |
+ * cost], in place.  Afterwards every rank holds the whole problem's H_diag / g / cost (also resident: hitl_normal_eq_device);
+ * H_off stays with the rank that owns each block.  Without a communicator (single GPU) it is hitl_normal_eq. */
+int hitl_normal_eq_allreduce(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* cost, float* ms_out);
+/* The Ceres-on-the-host feed: after hitl_eval (with Jacobians) on every rank, gathers the STF blocks of all ranks to `root` in rank
+ * order (= the reference's block order when the ranks own ascending source ranges): pair_i / pair_j [total], r [total x 2],
+ * J [total x 12] = 14 doubles per block, what SizedCostFunction<2,3,3>::Evaluate hands to Ceres.  n_blocks_per_rank [world] is
+ * filled on every rank; the other outputs only on root (may be NULL elsewhere).  HITL_ERR_OVERFLOW when total > cap_blocks. */
+int hitl_gather_stf_blocks(hitl_ctx* ctx, int root, uint64_t cap_blocks, uint64_t* n_blocks_per_rank, uint32_t* pair_i, uint32_t* pair_j,
+                           double* r, double* J);
 
 /* ---- COP-SLAM back-propagation (between EM and the joint optimisation) --------------------- */
 /* The pose update of Backprop::BackPropagateError (Backprop.cpp:170-199), with the host loops' float operation sequence per
