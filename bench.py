@@ -35,6 +35,29 @@ UNIT = "M evals/s"
 STD_DEV, CORR = 0.05, 1.0 / 40.0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries print there too (NCCL's version banner comes from whichever communicator
+    a process creates first), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -285,7 +308,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
                              "value_min": float(np.min([x["value"] for x in vals])), "value_max": float(np.max([x["value"] for x in vals]))},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def config_of(args, g, world=1):
@@ -318,6 +341,7 @@ def main():
     ap.add_argument("--replay-workload", default="c4")
     ap.add_argument("--replay-seconds", type=float, default=150.0, help="wall-clock budget of the replay leg (stroke picking included)")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -592,7 +616,7 @@ def main():
                 "detail": {"queries_per_step": queries, "jacobian_evals_per_step": matches, "residual_blocks": pairs, "tree_walks_per_step": trav, "tile_pairs_per_step": int(infos[-1][0]["n_tile_pairs"]),
                            "kdtree_build_device_s": t_build, "ms_find_stf": float(np.mean([i[0]["ms_total"] for i in infos])), "ms_normal_eq": float(np.mean([i[1]["ms"] for i in infos])),
                            "per_rank_[ms_search,ms_find_stf,tiles,source_poses]": per_rank}}
-        print(json.dumps(line))
+        emit_line(line)
     gpu.close()
     if world > 1:
         dist.destroy_process_group()

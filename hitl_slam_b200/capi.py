@@ -68,6 +68,30 @@ def load_gpu_library():
     return C.CDLL(path)
 
 
+def preload_nccl():
+    """comm.cu binds NCCL at run time by soname (libnccl.so.2).  In a Python process that also imports torch, both must share ONE copy:
+    glibc resolves a soname to whichever copy is already loaded, and torch's libtorch_cuda.so needs symbols of its own bundled NCCL
+    (site-packages/nvidia/nccl), which an older system libnccl lacks.  So the pip-bundled copy is loaded first when it exists; a C++ host
+    without Python simply gets the system library.  HITL_NCCL_LIBRARY overrides the choice."""
+    path = os.environ.get("HITL_NCCL_LIBRARY")
+    if not path:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    path = cand
+                    break
+        except Exception:
+            path = None
+    if path:
+        try:
+            C.CDLL(path, mode=C.RTLD_GLOBAL)
+        except OSError:
+            pass
+
+
 def default_min_cos():
     """cos(deg2rad(25)) stored to a float (config/non_markov_localization.cfg:48; JointOptimization.cpp:564)."""
     ang = np.float32(np.deg2rad(25.0))
@@ -408,6 +432,7 @@ class HitlGpu:
     @staticmethod
     def comm_unique_id():
         """128-byte ncclUniqueId from hitl_comm_unique_id (one rank calls it; hand the bytes to the others out of band)."""
+        preload_nccl()
         lib = load_gpu_library()
         lib.hitl_comm_unique_id.argtypes = [C.c_void_p]
         buf = (C.c_ubyte * 128)()
@@ -416,6 +441,7 @@ class HitlGpu:
         return bytes(buf)
 
     def comm_init(self, unique_id, rank, world):
+        preload_nccl()
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
         self._ck(self.lib.hitl_comm_init(self.ctx, buf, rank, world))
         self.comm_rank, self.comm_world = rank, world

@@ -13,6 +13,7 @@
 // else the system one), so libhitl_gpu.so itself has no link-time dependency and single-GPU users never touch it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -40,7 +41,9 @@ NcclApi g_nccl;
 std::once_flag g_nccl_once;
 
 void load_nccl() {
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy this process already holds (e.g. torch's)
+  void* h = nullptr;
+  if (const char* path = getenv("HITL_NCCL_LIBRARY")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);    // the copy this process already holds (e.g. torch's: ONE copy per process)
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
   if (!h) return;
