@@ -689,14 +689,17 @@ def correction_latency(gpu, g, cpu=True, reps=5):
     strokes = synth.pick_strokes(g)
     sess = HostSession(gpu)
     sess.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
-    lat, solve, em = [], [], None
+    lat, solve, parts, em = [], [], [], None
     for it in range(reps + 1):
         sess.clear_constraints()
         sess.set_poses(g["poses"])
         t0 = time.perf_counter()
         sess.world_transform(keep_host_copy=False)
+        ta = time.perf_counter()
         em = sess.em_run(4, strokes)
+        tb = time.perf_counter()
         nc = sess.add_constraints_from_em()
+        tc = time.perf_counter()
         sess.evaluate_block(0, with_stf=False)
         t1 = time.perf_counter()
         summ = sess.joint_opt_run(post=False)
@@ -704,8 +707,11 @@ def correction_latency(gpu, g, cpu=True, reps=5):
         if it:                              # first pass warms allocations
             lat.append((t1 - t0) * 1e3)
             solve.append((t2 - t1) * 1e3)
+            parts.append([(ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, (t1 - tc) * 1e3])
+    pm = np.median(np.array(parts), axis=0)
     out = {"ms": float(np.median(lat)), "ms_min": float(np.min(lat)), "ms_with_host_solve": float(np.median(lat) + np.median(solve)), "unit": "ms per correction",
-           "what": "world transform + EM (E-steps/assignment on GPU, M-step/ordering on host) + constraint targets + build & one batched evaluation of all odometry+human blocks",
+           "parts_ms": {"world_transform": float(pm[0]), "em_run": float(pm[1]), "constraint_targets": float(pm[2]), "build_and_evaluate_blocks": float(pm[3])},
+           "what": "world transform + EM (E-step AND M-step on the GPU: hitl_em_refit; observation sets on the GPU, ordering on the host) + constraint targets + build & one batched evaluation of all odometry+human blocks",
            "em_rounds": list(em["rounds"]), "corrected_poses": int(len(em["corrected"])), "anchor_poses": int(len(em["anchor"])), "human_blocks": int(nc),
            "solver_steps": int(summ["successful_steps"] + summ["unsuccessful_steps"]), "n_points": int(g["offsets"][-1])}
     sess.close()

@@ -25,9 +25,9 @@ KDNODE = np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), (
 ABI_SYMBOLS = [
     "hitl_create", "hitl_destroy", "hitl_last_error", "hitl_stream", "hitl_launch_count", "hitl_sm_count", "hitl_last_kernel_ms",
     "hitl_host_alloc", "hitl_host_free",
-    "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_set_kdtrees_compact", "hitl_get_kdtrees_compact", "hitl_kd_query",
+    "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_set_kdtrees_compact", "hitl_get_kdtrees_compact", "hitl_kd_query", "hitl_kd_neighbors",
     "hitl_find_stf", "hitl_get_stf", "hitl_get_stf16", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
-    "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_assign",
+    "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_refit", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
     "hitl_normal_eq_device", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks",
@@ -46,6 +46,11 @@ class StfInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
                 ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float),
                 ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("sum_tile_cycles", C.c_uint64), ("max_tile_cycles", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
+
+
+class EmFitInfo(C.Structure):
+    _fields_ = [("theta", C.c_double), ("initial_cost", C.c_double), ("final_cost", C.c_double), ("n_inliers", C.c_uint64),
+                ("iterations", C.c_int32), ("evaluations", C.c_int32), ("termination", C.c_int32), ("ms", C.c_float)]
 
 
 class EvalLayout(C.Structure):
@@ -128,6 +133,8 @@ class HitlGpu:
         lib.hitl_set_kdtrees.argtypes = [vp, vp]
         lib.hitl_get_kdtrees.argtypes = [vp, vp]
         lib.hitl_kd_query.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
+        lib.hitl_kd_neighbors.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_uint32, vp, _u32p]
+        lib.hitl_em_refit.argtypes = [vp, _f32p, C.c_double, C.c_int32, _f32p, C.POINTER(EmFitInfo)]
         lib.hitl_find_stf.argtypes = [vp, _f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(StfOpts), C.POINTER(StfInfo)]
         lib.hitl_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p]
         lib.hitl_get_stf_work.argtypes = [vp, _u64p]
@@ -267,6 +274,14 @@ class HitlGpu:
         self._ck(self.lib.hitl_kd_query(self.ctx, scan, n, q if n else np.zeros(2, np.float32), thr, mode, d, i))
         return d[:n], i[:n]
 
+    def kd_neighbors(self, scan, q, thr, cap=64):
+        """FindNeighborPoints: (lists of point indices in the reference's push order, truncated to cap; total counts)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1)
+        n = len(q) // 2
+        idx, cnt = np.full((max(n, 1), max(cap, 1)), -1, np.int32), np.zeros(max(n, 1), np.uint32)
+        self._ck(self.lib.hitl_kd_neighbors(self.ctx, scan, n, q if n else np.zeros(2, np.float32), thr, cap, idx.ctypes.data if cap else None, cnt))
+        return [idx[k, :min(int(cnt[k]), cap)].copy() for k in range(n)], cnt[:n]
+
     # ---- search ----
     @staticmethod
     def stf_opts(thr=0.15, min_cos=None, cap=6, skip=1, min_corr=10, disable_culling=0):
@@ -339,6 +354,13 @@ class HitlGpu:
         op, oi, xy = np.zeros(max(cap, 1), np.uint32), np.zeros(max(cap, 1), np.uint32), np.zeros(2 * max(cap, 1), np.float32)
         self._ck(self.lib.hitl_em_inliers(self.ctx, seg, thr, cap, op.ctypes.data, oi.ctypes.data, xy.ctypes.data, C.byref(n)))
         return op[:n.value].copy(), oi[:n.value].copy(), xy[:2 * n.value].reshape(-1, 2).copy()
+
+    def em_refit(self, seg, thr=0.03, max_iterations=25):
+        """One EM round on the device (hitl_em_refit): E-step + SegFitEM's LM.  Returns (refit segment [4] f32, info dict)."""
+        seg = np.ascontiguousarray(seg, np.float32).reshape(-1)
+        out, info = np.zeros(4, np.float32), EmFitInfo()
+        self._ck(self.lib.hitl_em_refit(self.ctx, seg, thr, max_iterations, out, C.byref(info)))
+        return out, {k: getattr(info, k) for k, _ in EmFitInfo._fields_}
 
     def verify_input(self, sel, thr=0.05):
         """HitLSLAM::verifyUserInput on the resident world clouds: (points_verified, seen bit mask)."""
@@ -677,6 +699,18 @@ class HostLib:
         lib.hitl_host_session_evaluate_block.argtypes = [vp, C.c_int, C.c_uint64, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _f64p, _f64p, _f64p, C.POINTER(C.c_uint64)]
         lib._mirror_bound = True
 
+    def seg_fit_em_theta(self, p1, p2, data):
+        """The host M-step (FitSegmentAngle on the host LM): (endpoints [2,2] f32, theta, LM iterations)."""
+        self._bind_mirror()
+        self.lib.hitl_host_seg_fit_em_theta.argtypes = [_f64p, _f64p, _f64p, C.c_int, _f32p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        data = np.ascontiguousarray(data, np.float64).reshape(-1)
+        out, th, it = np.zeros(4, np.float32), C.c_double(), C.c_int()
+        rc = self.lib.hitl_host_seg_fit_em_theta(np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64), data if len(data) else np.zeros(2), len(data) // 2, out,
+                                                 C.byref(th), C.byref(it))
+        if rc != 0:
+            raise HitlError("hitl_host_seg_fit_em_theta failed")
+        return out.reshape(2, 2), th.value, it.value
+
     def seg_fit_em(self, p1, p2, data):
         """EMInput::SegFitEM of the C++ mirror (host only)."""
         self._bind_mirror()
@@ -828,6 +862,11 @@ class HostSession:
 
     def world_transform(self, keep_host_copy=False):
         self._ck(self.lib.hitl_host_session_world_transform(self.s, int(keep_host_copy)))
+
+    def set_device_m_step(self, on=True):
+        """Where EMInput's M-step runs: device (hitl_em_refit, default) or the host LM (the checker)."""
+        self.lib.hitl_host_session_set_device_m_step.argtypes = [C.c_void_p, C.c_int]
+        self.lib.hitl_host_session_set_device_m_step(self.s, int(bool(on)))
 
     def em_run(self, correction_type, selected_points):
         sel = np.ascontiguousarray(selected_points, np.float32).reshape(-1).copy()

@@ -9,6 +9,8 @@
 // Both are HBM streams: 8 B read per point, a few bytes written per inlier.  Compiled with
 // --fmad=false; float expressions follow Eigen's evaluation order so flags are bit-exact.
 #include <float.h>
+#include <string.h>
+#include <algorithm>
 #include "hitl_internal.h"
 #include "hitl_math.h"
 
@@ -140,6 +142,153 @@ __global__ void __launch_bounds__(kEmThreads) em_inliers_kernel(const float2* __
       }
     }
     __syncthreads();   // s_chunk / s_warp reuse
+  }
+}
+
+// ---- K2c: M-step on the device — SegFitEM's one-parameter Levenberg-Marquardt over the resident inliers ----------------
+// EMinput.cpp:107-191: the stroke keeps its midpoint and length; the only unknown is its direction angle theta, fitted to the
+// E-step inliers by least squares on the point-to-segment distance (segDistResidualEM, three cases on the projection
+// parameter t) with Ceres' LM at its defaults (<= 25 iterations, theta_0 = acos(|dx| / length)).  The whole loop runs in ONE
+// cooperative launch: every evaluation is a grid-wide reduction of sum r^2, sum r dr/dtheta, sum (dr/dtheta)^2 in a fixed
+// order (per-thread strided sums -> shuffle tree -> per-CTA partials -> one grid barrier -> every CTA adds the partials in
+// CTA order), and every CTA runs the same scalar trust-region logic on the same sums, so no CTA waits for a host round trip
+// or for a designated leader.  The control flow restates host/ceres_solver.cpp::Solve for one scalar parameter (Jacobi
+// scaling from the first Jacobian, (H + clamp(H)/radius) step, model_change / rho acceptance, radius update
+// radius / max(1/3, 1 - (2 rho - 1)^3), halving 2, 4, 8 ... on rejection, function / gradient / parameter tolerances).
+// The derivative is analytic where the reference differentiates a Jet: same value up to rounding (test: theta within 1e-9).
+struct FitSums { double rr, jr, jj; };
+struct FitResult { double theta, cost0, cost; unsigned long long n; int iterations, evaluations, termination; float seg[4]; };
+constexpr int kFitThreads = 256;
+constexpr int kFitMaxBlocks = 64;
+
+__device__ __forceinline__ void seg_angle_residual(double px, double py, double cmx, double cmy, double len, double ax, double ay, double* r, double* dr) {
+  // e1 = cm + len a, e2 = cm - len a, d = e2 - e1; t = (p - e1).d / d.d
+  const double e1x = cmx + len * ax, e1y = cmy + len * ay, e2x = cmx - len * ax, e2y = cmy - len * ay;
+  const double dx = e2x - e1x, dy = e2y - e1y;
+  const double t = ((px - e1x) * dx + (py - e1y) * dy) / (dx * dx + dy * dy);
+  const double apx = -ay, apy = ax;                       // da / dtheta of the unit direction
+  double wx, wy, k;                                       // r = |w|, dr/dtheta = k (w . a') / r
+  if (t < 0.0) { wx = px - e1x; wy = py - e1y; k = -len; }
+  else if (t > 1.0) { wx = px - e2x; wy = py - e2y; k = len; }
+  else { wx = px - (e1x + t * dx); wy = py - (e1y + t * dy); k = -len * (1.0 - 2.0 * t); }
+  const double rr = sqrt(wx * wx + wy * wy);
+  *r = rr;
+  *dr = rr > 0.0 ? k * (wx * apx + wy * apy) / rr : 0.0;
+}
+
+__global__ void __launch_bounds__(kFitThreads) em_fit_kernel(const float2* __restrict__ xy, const unsigned long long* __restrict__ n_ptr, double p1x, double p1y,
+                                                             double p2x, double p2y, int max_iterations, double* partial /* 2 x gridDim.x x 3 */,
+                                                             unsigned int* barrier /* 2 words, zero on entry */, FitResult* out) {
+  __shared__ double s_red[3][kFitThreads / 32];
+  __shared__ FitSums s_tot;
+  const unsigned long long n = *n_ptr;
+  const double cmx = (p1x + p2x) / 2.0, cmy = (p1y + p2y) / 2.0;
+  const double hy = sqrt((p1x - p2x) * (p1x - p2x) + (p1y - p2y) * (p1y - p2y));
+  const double len = hy / 2.0;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, G = gridDim.x;
+  uint32_t n_eval = 0, barrier_goal = 0;
+
+  // grid barrier (all CTAs are co-resident: the launch is cooperative and G <= #SMs): arrival counter, monotone goal
+  auto grid_sync = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      barrier_goal += G;
+      __threadfence();
+      atomicAdd(barrier, 1u);
+      while (atomicAdd(barrier, 0u) < barrier_goal) { }
+      __threadfence();
+    }
+    __syncthreads();
+  };
+  auto evaluate = [&](double theta) -> FitSums {
+    double ax = cos(theta), ay = sin(theta);
+    const double inv = sqrt(ax * ax + ay * ay);             // alpha.normalize()
+    ax /= inv; ay /= inv;
+    double rr = 0.0, jr = 0.0, jj = 0.0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * kFitThreads + threadIdx.x; i < n; i += (unsigned long long)G * kFitThreads) {
+      const float2 p = xy[i];
+      double r, dr;
+      seg_angle_residual((double)p.x, (double)p.y, cmx, cmy, len, ax, ay, &r, &dr);
+      rr += r * r; jr += dr * r; jj += dr * dr;
+    }
+    for (int o = 16; o; o >>= 1) { rr += __shfl_xor_sync(0xffffffffu, rr, o); jr += __shfl_xor_sync(0xffffffffu, jr, o); jj += __shfl_xor_sync(0xffffffffu, jj, o); }
+    if (lane == 0) { s_red[0][w] = rr; s_red[1][w] = jr; s_red[2][w] = jj; }
+    __syncthreads();
+    double* mine = partial + ((size_t)(n_eval & 1u) * G + blockIdx.x) * 3;
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int q = 0; q < kFitThreads / 32; ++q) { a += s_red[0][q]; b += s_red[1][q]; c += s_red[2][q]; }
+      mine[0] = a; mine[1] = b; mine[2] = c;
+    }
+    grid_sync();
+    if (threadIdx.x == 0) {
+      const volatile double* all = partial + (size_t)(n_eval & 1u) * G * 3;
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (uint32_t q = 0; q < G; ++q) { a += all[3 * q]; b += all[3 * q + 1]; c += all[3 * q + 2]; }
+      s_tot.rr = a; s_tot.jr = b; s_tot.jj = c;
+    }
+    __syncthreads();
+    const FitSums t = s_tot;
+    ++n_eval;
+    __syncthreads();
+    return t;
+  };
+
+  double x = acos(fabs(p1x - p2x) / hy);                    // in [0, pi/2]: the sign of the slope is dropped, as in the reference
+  int iterations = 0, termination = 0;                      // 0 no convergence (iteration cap), 1 convergence
+  double cost0 = 0.0, cost = 0.0;
+  if (n > 0) {
+    const double kFtol = 1e-6, kGtol = 1e-10, kPtol = 1e-8, kMinRel = 1e-3, kMinDiag = 1e-6, kMaxDiag = 1e32, kMinRadius = 1e-32, kMaxRadius = 1e16;
+    FitSums S = evaluate(x);
+    cost0 = cost = 0.5 * S.rr;
+    const double scale = 1.0 / (1.0 + sqrt(S.jj));
+    double g = S.jr * scale, H = S.jj * scale * scale;
+    if (fabs(g / scale) <= kGtol) termination = 1;
+    double radius = 1e4, decrease = 2.0;
+    for (int iter = 1; iter <= max_iterations && termination == 0; ++iter) {
+      iterations = iter;
+      const double lm2 = fmin(fmax(H, kMinDiag), kMaxDiag) / radius;
+      const double A = H + lm2;
+      bool solved = A > 0.0;
+      double step = 0.0, model_change = 0.0;
+      if (solved) {
+        const double d = sqrt(A);
+        step = -((g / d) / d);
+        model_change -= step * (g + 0.5 * (H * step));
+      }
+      if (!solved || !(model_change > 0.0)) {
+        radius /= decrease; decrease *= 2.0;
+        if (radius < kMinRadius) termination = 1;
+        continue;
+      }
+      const double dx = step * scale, x_new = x + dx;
+      if (sqrt(dx * dx) <= kPtol * (sqrt(x * x) + kPtol)) { termination = 1; break; }
+      const FitSums Sn = evaluate(x_new);
+      const double new_cost = 0.5 * Sn.rr, cost_change = cost - new_cost, rho = cost_change / model_change;
+      if (rho > kMinRel) {
+        x = x_new;
+        const double old_cost = cost;
+        cost = new_cost;
+        g = Sn.jr * scale; H = Sn.jj * scale * scale;
+        if (fabs(cost_change) <= kFtol * old_cost) { termination = 1; break; }
+        if (fabs(g / scale) <= kGtol) { termination = 1; break; }
+        const double t = 2.0 * rho - 1.0;
+        radius = fmin(kMaxRadius, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        decrease = 2.0;
+      } else {
+        radius /= decrease; decrease *= 2.0;
+        if (radius < kMinRadius) termination = 1;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double ax = cos(x), ay = sin(x);
+    const double l2 = sqrt(ax * ax + ay * ay);
+    ax /= l2; ay /= l2;
+    FitResult R;
+    R.theta = x; R.cost0 = cost0; R.cost = cost; R.n = n; R.iterations = iterations; R.evaluations = (int)n_eval; R.termination = termination;
+    R.seg[0] = (float)(cmx + len * ax); R.seg[1] = (float)(cmy + len * ay); R.seg[2] = (float)(cmx - len * ax); R.seg[3] = (float)(cmy - len * ay);
+    *out = R;
   }
 }
 
@@ -369,6 +518,59 @@ extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double thresho
     HITL_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n > cap) return fail(ctx, HITL_ERR_OVERFLOW, "hitl_em_inliers: more inliers than cap");
   }
+  return HITL_OK;
+}
+
+extern "C" int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4], hitl_em_fit_info* info) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_refit: world clouds not set");
+  if (!seg_in || !seg_out || max_iterations < 0) return fail(ctx, HITL_ERR_ARG, "hitl_em_refit: bad argument");
+  hitl_em_fit_info inf; memset(&inf, 0, sizeof(inf));
+  for (int q = 0; q < 4; ++q) seg_out[q] = seg_in[q];
+  if (ctx->n_points == 0) { if (info) *info = inf; return HITL_OK; }
+  // E-step: the inliers' coordinates stay resident, in (pose, index) order (every point may be an inlier: the list cannot overflow)
+  const uint64_t dcap = ctx->n_points;
+  const uint32_t n_chunks = (uint32_t)((ctx->n_points + kEmChunk - 1) / kEmChunk);
+  HITL_CUDA(ctx->d_scan_state.ensure(n_chunks + 1)); HITL_CUDA(ctx->d_ticket.ensure(4));
+  HITL_CUDA(ctx->d_em_pose.ensure(dcap)); HITL_CUDA(ctx->d_em_idx.ensure(dcap)); HITL_CUDA(ctx->d_em_xy.ensure(dcap));
+  const int fit_blocks = std::min(kFitMaxBlocks, ctx->sm_count);
+  HITL_CUDA(ctx->d_fit_partial.ensure(2 * (size_t)kFitMaxBlocks * 3)); HITL_CUDA(ctx->d_fit_out.ensure(sizeof(FitResult)));
+  HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_scan_state.p, 0, 8 * (size_t)(n_chunks + 1), ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 16, ctx->stream));                      // word 0: E-step ticket, words 2-3: the fit's grid barrier
+  Seg s; make_seg(seg_in, &s);
+  const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
+  HITL_KERNEL_BEGIN(HITL_K_EM_INLIERS);
+  em_inliers_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, inlier_threshold,
+                                                          (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap, ctx->d_em_pose.p, ctx->d_em_idx.p,
+                                                          ctx->d_em_xy.p, (unsigned long long*)ctx->d_scan_state.p + n_chunks);
+  HITL_KERNEL_END(HITL_K_EM_INLIERS);
+  HITL_LAUNCH_CHECK("em_inliers_kernel");
+  // M-step: the whole LM loop in one cooperative launch (co-resident CTAs, software grid barrier)
+  const float2* d_xy = ctx->d_em_xy.p;
+  const unsigned long long* d_n = (const unsigned long long*)ctx->d_scan_state.p + n_chunks;
+  double p1x = seg_in[0], p1y = seg_in[1], p2x = seg_in[2], p2y = seg_in[3];
+  int iters = max_iterations;
+  double* d_partial = ctx->d_fit_partial.p;
+  unsigned int* d_barrier = ctx->d_ticket.p + 2;
+  FitResult* d_out = reinterpret_cast<FitResult*>(ctx->d_fit_out.p);
+  void* args[] = {(void*)&d_xy, (void*)&d_n, (void*)&p1x, (void*)&p1y, (void*)&p2x, (void*)&p2y, (void*)&iters, (void*)&d_partial, (void*)&d_barrier, (void*)&d_out};
+  HITL_KERNEL_BEGIN(HITL_K_EM_FIT);
+  HITL_CUDA(cudaLaunchCooperativeKernel((const void*)em_fit_kernel, dim3(fit_blocks), dim3(kFitThreads), args, 0, ctx->stream));
+  HITL_KERNEL_END(HITL_K_EM_FIT);
+  HITL_LAUNCH_CHECK("em_fit_kernel");
+  HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  FitResult* h = reinterpret_cast<FitResult*>(ctx->h_pinned);
+  HITL_CUDA(cudaMemcpyAsync(h, d_out, sizeof(FitResult), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  inf.theta = h->theta; inf.initial_cost = h->cost0; inf.final_cost = h->cost; inf.n_inliers = h->n; inf.iterations = h->iterations;
+  inf.evaluations = h->evaluations; inf.termination = h->termination;
+  HITL_CUDA(cudaEventElapsedTime(&inf.ms, ctx->ev[0], ctx->ev[1]));
+  if (h->n) for (int q = 0; q < 4; ++q) seg_out[q] = h->seg[q];
+  else {       // no inliers: the reference skips the solve and rebuilds the stroke from theta_0 (EMinput.cpp:178-190)
+    for (int q = 0; q < 4; ++q) seg_out[q] = h->seg[q];
+  }
+  if (info) *info = inf;
   return HITL_OK;
 }
 

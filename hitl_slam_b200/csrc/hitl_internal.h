@@ -145,6 +145,8 @@ struct hitl_ctx {
   hitl::DevBuf<float2> d_em_xy;
   hitl::DevBuf<uint64_t> d_scan_state;   // decoupled look-back tile states
   hitl::DevBuf<uint32_t> d_ticket;
+  hitl::DevBuf<double> d_fit_partial;    // per-CTA partial sums of the device M-step (two buffers)
+  hitl::DevBuf<uint8_t> d_fit_out;       // FitResult of the last hitl_em_refit
 
   // ---- residual blocks ----
   uint64_t nb_odo = 0, nb_human = 0, nb_stf = 0, nb_p2lg = 0, nb_p2l = 0;

@@ -185,6 +185,38 @@ __device__ uint32_t neighbor_count(const TreeRef t, uint32_t n_nodes, float qx, 
   return count;
 }
 
+// FindNeighborPoints with its result list: the point indices of the nodes within thr, in the reference's push order (node, then the
+// left subtree, then the right subtree — kdtree.cpp:204-217).  Each query owns `cap` output slots; the count is always complete.
+__global__ void kd_neighbors_kernel(const float4* pm, uint32_t tree_off, uint32_t n_nodes, uint32_t nq, const float2* q, float thr, uint32_t cap,
+                                    int32_t* __restrict__ index_out, uint32_t* __restrict__ count_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  uint32_t count = 0;
+  if (n_nodes) {
+    const float4* t = pm + tree_off;
+    const float2 p = q[i];
+    uint32_t stack_pos[34], stack_n[34];
+    int sp = 1;
+    stack_pos[0] = 0; stack_n[0] = n_nodes;
+    while (sp) {
+      --sp;
+      const uint32_t pos = stack_pos[sp], n = stack_n[sp];
+      const float4 nd = __ldg(t + pos);
+      const int dim = (int)(node_meta(nd) >> 31);
+      const float ex = fsub(nd.x, p.x), ey = fsub(nd.y, p.y);
+      if (sqrtf(fadd(fmul(ex, ex), fmul(ey, ey))) < thr) {
+        if (count < cap) index_out[(size_t)i * cap + count] = (int32_t)(node_meta(nd) & 0x7FFFFFFFu);
+        ++count;
+      }
+      const float s = dim ? fsub(p.y, nd.y) : fsub(p.x, nd.x);
+      const uint32_t nl = n >> 1, nr = n - 1 - nl;
+      if (s > -thr && nr) { stack_pos[sp] = pos + 1 + nl; stack_n[sp] = nr; ++sp; }   // popped after the left subtree
+      if (s < thr && nl) { stack_pos[sp] = pos + 1; stack_n[sp] = nl; ++sp; }
+    }
+  }
+  count_out[i] = count;
+}
+
 __global__ void kd_query_kernel(const float4* pm, const float2* nn, uint32_t tree_off, uint32_t n_nodes, uint32_t nq,
                                 const float2* q, float thr, int mode, float* dist, int32_t* index) {
   extern __shared__ uint2 smem_stack[];
@@ -1077,6 +1109,25 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
   HITL_LAUNCH_CHECK("kd_query_kernel");
   if (dist_out && mode != 2) HITL_CUDA(cudaMemcpyAsync(dist_out, dd.p, sizeof(float) * nq, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(index_out, di.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HITL_OK;
+}
+
+extern "C" int hitl_kd_neighbors(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const float* q_xy, float threshold, uint32_t cap, int32_t* index_out,
+                                 uint32_t* count_out) {
+  if (!ctx) return HITL_ERR_ARG;
+  if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_kd_neighbors: trees not built");
+  if (scan >= ctx->n_poses || (nq && (!q_xy || !count_out || (cap && !index_out)))) return fail(ctx, HITL_ERR_ARG, "hitl_kd_neighbors: bad argument");
+  if (nq == 0) return HITL_OK;
+  TmpBuf<float2> dq; TmpBuf<int32_t> di; TmpBuf<uint32_t> dc;
+  HITL_CUDA(dq.ensure(nq)); HITL_CUDA(di.ensure((size_t)nq * cap)); HITL_CUDA(dc.ensure(nq));
+  HITL_CUDA(cudaMemcpyAsync(dq.p, q_xy, sizeof(float2) * nq, cudaMemcpyHostToDevice, ctx->stream));
+  if (cap) HITL_CUDA(cudaMemsetAsync(di.p, 0xFF, sizeof(int32_t) * (size_t)nq * cap, ctx->stream));   // unused slots read -1
+  const uint32_t toff = ctx->h_off[scan], tn = ctx->h_off[scan + 1] - toff;
+  kd_neighbors_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_node_pm.p, toff, tn, nq, dq.p, threshold, cap, di.p, dc.p);
+  HITL_LAUNCH_CHECK("kd_neighbors_kernel");
+  if (cap) HITL_CUDA(cudaMemcpyAsync(index_out, di.p, sizeof(int32_t) * (size_t)nq * cap, cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(count_out, dc.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
 }

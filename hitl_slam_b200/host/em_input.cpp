@@ -68,7 +68,7 @@ std::vector<Vector2f> EMInput::SegFitEM(double* p1, double* p2, double* cm, doub
 }
 
 // The M-step proper: pure host code, no device state.
-std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const double* data, int size) {
+std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const double* data, int size, double* theta_out, int* iterations_out) {
   const double icm[2] = {(p1[0] + p2[0]) / 2.0, (p1[1] + p2[1]) / 2.0};
   const double hy = sqrt(pow(p1[0] - p2[0], 2) + pow(p1[1] - p2[1], 2));
   const double ad = fabs(p1[0] - p2[0]);
@@ -83,6 +83,8 @@ std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const 
   options.minimizer_progress_to_stdout = false;
   ceres::Solver::Summary summary;
   if (size > 0) ceres::Solve(options, &problem, &summary);
+  if (theta_out) *theta_out = theta[0];
+  if (iterations_out) *iterations_out = summary.num_successful_steps + summary.num_unsuccessful_steps;
   double ax = cos(theta[0]), ay = sin(theta[0]);
   const double len = sqrt(ax * ax + ay * ay);
   ax /= len; ay /= len;
@@ -104,6 +106,21 @@ void EMInput::AutomaticEndpointAdjustment() {
     while ((adjustment1 > thresh || adjustment2 > thresh) && em_rounds_[k] < max_em_rounds_) {
       // E-step on the device: every world point within 3 cm of the stroke, in (pose, index) order.
       const float seg[4] = {selected_points_[2 * k].x, selected_points_[2 * k].y, selected_points_[2 * k + 1].x, selected_points_[2 * k + 1].y};
+      if (device_m_step_) {
+        // ... and the M-step too: SegFitEM's LM runs on the resident inliers (hitl_em_refit); only the refit stroke comes back.
+        float out[4];
+        hitl_em_fit_info fi;
+        check(hitl_em_refit(ctx_, seg, 0.03, 25, out, &fi), "hitl_em_refit");
+        em_inliers_[k] = fi.n_inliers;
+        last_theta_[k] = fi.theta;
+        const std::vector<Vector2f> fit = {Vector2f(out[0], out[1]), Vector2f(out[2], out[3])};
+        adjustment1 = norm(selected_points_[2 * k] - fit[0]);
+        adjustment2 = norm(selected_points_[2 * k + 1] - fit[1]);
+        selected_points_[2 * k] = fit[0];
+        selected_points_[2 * k + 1] = fit[1];
+        ++em_rounds_[k];
+        continue;
+      }
       uint64_t n = 0;
       if (in_pose.empty()) { in_pose.resize(1 << 16); in_idx.resize(1 << 16); xy.resize(2 << 16); }
       int rc = hitl_em_inliers(ctx_, seg, 0.03, in_pose.size(), in_pose.data(), in_idx.data(), xy.data(), &n);
@@ -130,7 +147,11 @@ void EMInput::AutomaticEndpointAdjustment() {
   }
 }
 
-std::pair<PoseObservations, PoseObservations> EMInput::EstablishObservationSets() {
+std::pair<PoseObservations, PoseObservations> EMInput::EstablishObservationSets() { return ObservationSets(true); }
+
+// with_indices = false returns the observing POSES only (empty index vectors): all that OrderAndFilterUserInput and
+// SetCorrectionRelations read (EMinput.cpp:253-267, 325-455 use `.first` of every entry), without copying the index lists back.
+std::pair<PoseObservations, PoseObservations> EMInput::ObservationSets(bool with_indices) {
   if (!world_clouds_resident_) UploadWorldClouds();
   const size_t n = local_version_point_clouds_.size();
   size_t total = 0;
@@ -140,14 +161,15 @@ std::pair<PoseObservations, PoseObservations> EMInput::EstablishObservationSets(
   uint32_t n_sets[2] = {0, 0};
   std::vector<uint32_t> set_pose[2], obs[2];
   std::vector<uint64_t> set_off[2];
-  for (int f = 0; f < 2; ++f) { set_pose[f].resize(std::max<size_t>(n, 1)); set_off[f].resize(n + 1); obs[f].resize(std::max<size_t>(total, 1)); }
-  check(hitl_em_assign(ctx_, segs, 0.03, 5, n_sets, set_pose[0].data(), set_off[0].data(), obs[0].data(), set_pose[1].data(), set_off[1].data(), obs[1].data()),
+  for (int f = 0; f < 2; ++f) { set_pose[f].resize(std::max<size_t>(n, 1)); if (with_indices) { set_off[f].resize(n + 1); obs[f].resize(std::max<size_t>(total, 1)); } }
+  check(hitl_em_assign(ctx_, segs, 0.03, 5, n_sets, set_pose[0].data(), with_indices ? set_off[0].data() : nullptr, with_indices ? obs[0].data() : nullptr,
+                       set_pose[1].data(), with_indices ? set_off[1].data() : nullptr, with_indices ? obs[1].data() : nullptr),
         "hitl_em_assign");
   std::pair<PoseObservations, PoseObservations> out;
   PoseObservations* dst[2] = {&out.first, &out.second};
   for (int f = 0; f < 2; ++f)
     for (uint32_t s = 0; s < n_sets[f]; ++s)
-      dst[f]->push_back(std::make_pair((int)set_pose[f][s], std::vector<int>(obs[f].begin() + set_off[f][s], obs[f].begin() + set_off[f][s + 1])));
+      dst[f]->push_back(std::make_pair((int)set_pose[f][s], with_indices ? std::vector<int>(obs[f].begin() + set_off[f][s], obs[f].begin() + set_off[f][s + 1]) : std::vector<int>()));
   return out;
 }
 
@@ -162,7 +184,7 @@ void EMInput::SetCorrectionRelations(const PoseObservations& first_poses_obs, co
 // back-propagation bounds.  (-1, -1) signals an unusable selection, as in the reference.
 void EMInput::OrderAndFilterUserInput() {
   if (selected_points_.size() != 4) throw std::invalid_argument("OrderAndFilterUserInput: 4 selected points expected");
-  const std::pair<PoseObservations, PoseObservations> sets = EstablishObservationSets();
+  const std::pair<PoseObservations, PoseObservations> sets = ObservationSets(fetch_observation_indices_);
   std::vector<int> first, second;
   for (const auto& p : sets.first) first.push_back(p.first);
   for (const auto& p : sets.second) second.push_back(p.first);

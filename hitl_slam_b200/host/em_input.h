@@ -24,7 +24,7 @@ typedef std::vector<std::pair<int, std::vector<int>>> PoseObservations;
 
 // SegFitEM's computation (EMinput.cpp:152-191): refit the direction of the segment p1-p2 about its
 // fixed midpoint and length to the inliers data[2*size]; returns the two new endpoints.
-std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const double* data, int size);
+std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const double* data, int size, double* theta_out = nullptr, int* iterations_out = nullptr);
 
 class EMInput {
  public:
@@ -45,6 +45,12 @@ class EMInput {
   // true: the context already holds the world clouds of the current scans (hitl_world_transform /
   // hitl_set_world_clouds) and local_version_point_clouds_ is not uploaded again.
   bool world_clouds_resident_ = false;
+  // M-step placement: true (default) = hitl_em_refit, E-step + SegFitEM's LM in one device call per round (nothing but 64 bytes crosses
+  // PCIe); false = inliers copied back and FitSegmentAngle on the host LM (the checker: tests compare the two to 1e-9 in theta).
+  bool device_m_step_ = true;
+  // OrderAndFilterUserInput reads only the observing poses; true also copies every pose's index list back (EstablishObservationSets always does)
+  bool fetch_observation_indices_ = false;
+  double last_theta_[2] = {0, 0};    // fitted direction angle of each stroke's last M-step
   int max_em_rounds_ = 1000;         // guard for the reference's unbounded while loop (:200)
   int em_rounds_[2] = {0, 0};        // E/M rounds each stroke took
   uint64_t em_inliers_[2] = {0, 0};  // inliers of the last E-step of each stroke
@@ -55,6 +61,7 @@ class EMInput {
   void AutomaticEndpointAdjustment();
   std::vector<Vector2f> SegFitEM(double* p1, double* p2, double* cm, double* data, int size);
   std::pair<PoseObservations, PoseObservations> EstablishObservationSets();
+  std::pair<PoseObservations, PoseObservations> ObservationSets(bool with_indices);
   void OrderAndFilterUserInput();
   void SetCorrectionRelations(const PoseObservations& first_poses_obs, const PoseObservations& second_poses_obs);
 

@@ -407,6 +407,15 @@ int hitl_host_session_evaluate_block(void* sp, int with_stf, uint64_t block, con
 }
 
 // ---- device-free pieces (CPU tests) ---------------------------------------------------------------------
+int hitl_host_seg_fit_em_theta(const double p1[2], const double p2[2], const double* data, int size, float out4[4], double* theta, int* iterations) {
+  try {
+    const std::vector<Vector2f> fit = FitSegmentAngle(p1, p2, data, size, theta, iterations);
+    out4[0] = fit[0].x; out4[1] = fit[0].y; out4[2] = fit[1].x; out4[3] = fit[1].y;
+    return 0;
+  } catch (...) { return -1; }
+}
+// Selects where EMInput's M-step runs in this session: 1 = device (hitl_em_refit, default), 0 = host LM (the checker).
+int hitl_host_session_set_device_m_step(void* sp, int on) { static_cast<Session*>(sp)->em.device_m_step_ = on != 0; return 0; }
 int hitl_host_seg_fit_em(const double p1[2], const double p2[2], const double* data, int size, float out4[4]) {
   try {
     const std::vector<Vector2f> fit = FitSegmentAngle(p1, p2, data, size);

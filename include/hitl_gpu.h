@@ -7,12 +7,13 @@
  *                                         KDTree<float,2>::BuildKDTree      perception_tools/kdtree.cpp:37-139
  *   hitl_kd_query                         KDTree::FindNearestPointNormal    perception_tools/kdtree.cpp:141-197
  *                                         KDTree::FindNearestPoint          perception_tools/kdtree.cpp:220-273
- *                                         KDTree::FindNeighborPoints        perception_tools/kdtree.cpp:199-218 (count only)
+ *   hitl_kd_neighbors                     KDTree::FindNeighborPoints        perception_tools/kdtree.cpp:199-218 (the node list, in push order)
  *   hitl_find_stf / hitl_get_stf          JointOpt::FindSTFCorrespondences  JointOptimization.cpp:561-642
  *   hitl_find_vo / hitl_get_vo            JointOpt::FindVisualOdometryCorrespondences  JointOptimization.cpp:432-468
  *   hitl_world_transform                  HitLSLAM::transformPointCloudsToWorldFrame   human_in_the_loop_slam/HitLSLAM.cpp:245-254
  *   hitl_verify_input                     HitLSLAM::verifyUserInput                    human_in_the_loop_slam/HitLSLAM.cpp:218-243
  *   hitl_em_inliers                       E-step of EMInput::AutomaticEndpointAdjustment  human_in_the_loop_slam/EMinput.cpp:207-218
+ *   hitl_em_refit                         one E-step + M-step round: the above + EMInput::SegFitEM / segDistResidualEM  EMinput.cpp:107-191
  *   hitl_em_assign                        EMInput::EstablishObservationSets EMinput.cpp:281-323
  *   hitl_set_*_blocks / hitl_eval         AutoDiffCostFunction<...>::Evaluate of the blocks added by
  *                                         AddSTFConstraints :539-559, AddOdometryConstraints :736-825,
@@ -103,6 +104,12 @@ int hitl_kdtree_build_host(const float* pts_xy, const float* nrm_xy, uint32_t n,
 int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t n_queries, const float* q_xy, float threshold, int mode,
                   float* dist_out, int32_t* index_out);
 
+/* KDTree::FindNeighborPoints (kdtree.cpp:199-218) with its result list: for every query, count_out = number of nodes with
+ * |node - q| < threshold and index_out[q * cap ...] = the scan point indices of the first `cap` of them in the reference's push order
+ * (node, left subtree, right subtree); unused slots are -1.  cap = 0 counts only (index_out may be NULL). */
+int hitl_kd_neighbors(hitl_ctx* ctx, uint32_t scan, uint32_t n_queries, const float* q_xy, float threshold, uint32_t cap,
+                      int32_t* index_out, uint32_t* count_out);
+
 /* ---- scan-to-scan correspondence search ------------------------------------------------ */
 typedef struct {
   float point_match_threshold;          /* kPointMatchThreshold, config 0.15 */
@@ -168,6 +175,21 @@ int hitl_verify_input(hitl_ctx* ctx, uint32_t n_selected, const float* sel_xy, f
  * seg = {p0x, p0y, p1x, p1y}. out_* may be NULL (count only); cap = capacity of the out arrays. */
 int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double threshold, uint64_t cap, uint32_t* out_pose,
                     uint32_t* out_idx, float* out_xy, uint64_t* n_out);
+
+/* One EM round of EMInput::AutomaticEndpointAdjustment entirely on the device (EMinput.cpp:195-250): the E-step above (inliers of
+ * seg_in within inlier_threshold stay resident) and the M-step, SegFitEM's one-parameter Levenberg-Marquardt fit of the stroke's
+ * direction to those inliers (EMinput.cpp:107-191: fixed midpoint and length, theta_0 = acos(|dx| / length), Ceres defaults,
+ * <= max_iterations iterations; the reference passes 25), as ONE cooperative kernel whose every evaluation is a grid-wide
+ * deterministic reduction.  seg_out = the refit endpoints as the reference rounds them to float.  Nothing but the 64-byte
+ * result crosses PCIe. */
+typedef struct {
+  double theta, initial_cost, final_cost;
+  uint64_t n_inliers;
+  int32_t iterations, evaluations, termination; /* termination: 1 = a Ceres convergence test fired, 0 = iteration cap */
+  float ms;                                     /* device time of E-step + M-step */
+} hitl_em_fit_info;
+int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4],
+                  hitl_em_fit_info* info);
 
 /* Observation sets of both strokes: segs = {a0, a1, b0, b1} as 8 floats.  A pose is kept for a
  * stroke when MORE than min_obs of its points are within threshold (reference: 5).

@@ -86,8 +86,16 @@ def test_kd_queries_match_oracle(gpu, oracle, n):
                 assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)), (scan, mode, thr)
         if m:
             _, cnt = gpu.kd_query(scan, q[:200], 0.3, 2)
-            ref = np.array([len(S.radius(scan, q[k, 0], q[k, 1], 0.3)) for k in range(200)])
+            want = [S.radius(scan, q[k, 0], q[k, 1], 0.3) for k in range(200)]
+            ref = np.array([len(w) for w in want])
             assert np.array_equal(cnt, ref)
+            # FindNeighborPoints' node LIST (kdtree.cpp:199-218): same nodes in the reference's push order; truncation keeps the head
+            lists, cnt2 = gpu.kd_neighbors(scan, q[:200], 0.3, cap=int(ref.max()) + 1)
+            assert np.array_equal(cnt2, ref)
+            for k in range(200):
+                assert np.array_equal(lists[k], np.asarray(want[k], np.int32)), (scan, k)
+            short, cnt3 = gpu.kd_neighbors(scan, q[:50], 0.3, cap=2)
+            assert np.array_equal(cnt3, ref[:50]) and all(np.array_equal(short[k], np.asarray(want[k][:2], np.int32)) for k in range(50))
 
 
 def test_compact_tree_and_index_formats(gpu, oracle, maps):

@@ -262,6 +262,40 @@ def test_em_input_run_matches_oracle(session, gpu, oracle, maps, name):
     assert np.array_equal(again["segs"], got["segs"]) and np.array_equal(again["corrected"], got["corrected"])
 
 
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_device_m_step_matches_the_host_lm(session, gpu, host, maps, name):
+    """hitl_em_refit (E-step + SegFitEM's LM in one cooperative kernel) against the host M-step on the SAME inliers: the fitted angle within
+    1e-9, the same number of LM iterations, the float endpoints equal up to the last place; then EMInput::Run with the M-step on the device
+    against the M-step on the host LM: same rounds, same pose lists, endpoints within 1e-6."""
+    from hitl_slam_b200 import synth
+    g = maps(name, **DRIFTY)
+    session.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    session.world_transform(keep_host_copy=False)
+    strokes = synth.pick_strokes(g, min_sep=0.045)
+    rng = np.random.default_rng(7)
+    for case in (strokes, strokes + rng.normal(size=(4, 2)).astype(np.float32) * 0.01, strokes[::-1].copy()):
+        for seg in (case[:2], case[2:]):
+            _, _, xy = gpu.em_inliers(seg.reshape(-1))
+            want_seg, want_theta, want_it = host.seg_fit_em_theta(seg[0].astype(np.float64), seg[1].astype(np.float64), xy.astype(np.float64).reshape(-1))
+            got_seg, info = gpu.em_refit(seg.reshape(-1))
+            assert info["n_inliers"] == len(xy) > 0
+            assert abs(info["theta"] - want_theta) <= 1e-9, (info, want_theta)
+            assert info["iterations"] == want_it and info["final_cost"] <= info["initial_cost"] * (1 + 1e-12)
+            assert np.abs(got_seg.reshape(2, 2) - want_seg).max() <= 2e-6
+            again, info2 = gpu.em_refit(seg.reshape(-1))              # deterministic reductions: bit-identical on a second run
+            assert np.array_equal(again, got_seg) and info2["theta"] == info["theta"]
+    none_seg, none = gpu.em_refit(np.array([500, 500, 501, 500.5], np.float32))   # no inlier: the stroke is rebuilt from theta_0, as in the reference
+    w0, t0, _ = host.seg_fit_em_theta(np.array([500.0, 500.0]), np.array([501.0, 500.5]), np.zeros(0))
+    assert none["n_inliers"] == 0 and none["iterations"] == 0 and abs(none["theta"] - t0) <= 1e-15 and np.abs(none_seg.reshape(2, 2) - w0).max() <= 1e-4
+    session.set_device_m_step(False)
+    want = session.em_run(4, strokes)
+    session.set_device_m_step(True)
+    got = session.em_run(4, strokes)
+    assert got["rounds"] == want["rounds"] and got["backprop"] == want["backprop"]
+    assert np.array_equal(got["corrected"], want["corrected"]) and np.array_equal(got["anchor"], want["anchor"])
+    assert np.abs(got["segs"] - want["segs"]).max() <= 1e-6
+
+
 def test_replayed_colinear_correction_end_to_end(session, host, oracle, maps, tmp_path):
     """BASELINE config 1: one colinear constraint replayed from a session log through EM -> constraint
     targets -> JointOpt::Run; the optimised poses satisfy the constraint and stay near odometry."""
