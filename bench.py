@@ -337,7 +337,8 @@ def main():
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
     ap.add_argument("--no-largest-map", action="store_true", help="N > 1: skip the config-3 (20k x 1080) leg that measures the N-GPU speed-up on the largest map")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check of the benchmarked search against the oracle")
-    ap.add_argument("--replay", type=int, default=0, help="BASELINE config 4: replay this many sequential corrections on --replay-workload and report per-correction latency")
+    ap.add_argument("--replay", type=int, default=-1, help="BASELINE config 4: replay this many sequential corrections on --replay-workload and report per-correction latency "
+                                                          "(default: 10 at N = 1 on the default workload, else 0)")
     ap.add_argument("--replay-workload", default="c4")
     ap.add_argument("--replay-seconds", type=float, default=150.0, help="wall-clock budget of the replay leg (stroke picking included)")
     args = ap.parse_args()
@@ -355,6 +356,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.replay < 0:
+        args.replay = 10 if (world == 1 and args.workload == "c2" and args.poses == synth.CONFIGS["c2"]["n_poses"] and not args.no_correction) else 0
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries exactly one JSON line
     import torch
@@ -584,7 +587,7 @@ def main():
     if rank == 0 and args.replay > 0:
         try:
             gr = g if args.replay_workload == args.workload else workload(args.replay_workload, synth.CONFIGS[args.replay_workload]["n_poses"], synth.CONFIGS[args.replay_workload]["beams"])
-            replay = correction_replay(gpu, gr, args.replay, budget_s=args.replay_seconds)
+            replay = correction_replay(gpu, gr, args.replay, budget_s=args.replay_seconds if args.replay > 10 else min(args.replay_seconds, 80.0))
             replay["workload"] = args.replay_workload
         except Exception as e:
             replay = {"error": str(e)[:300]}
@@ -786,19 +789,31 @@ def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
     cur = dict(g)
     lat, solve, parts, cpu_ms, spans, blocks, applied = [], [], [], [], [], [], []
     start, t_begin = 0, time.perf_counter()
+    dry_runs = 0
     for c in range(n_corrections):
         if time.perf_counter() - t_begin > budget_s:
             break
         cur["poses"] = sess.poses()[0]
-        try:
-            # the first corrections close real loop-closure gaps; once those are used up the replay keeps drawing on revisited
-            # walls wherever they are (a separation of ~0 exercises the same pipeline)
-            strokes, start = synth.pick_strokes(cur, min_sep=0.04 if c < 4 else 0.0, start=start, return_next=True)
-        except RuntimeError:
+        # Untimed: the "human" draws two strokes on a revisited wall of the map AS IT IS NOW.  A real user draws strokes the tool accepts;
+        # here every candidate pair is first put through the same EM (dry run, it changes no session state) and is drawn again elsewhere
+        # when EM finds the observers of the two strokes interleaved in time (HitLSLAM::Run would stop after EM, HitLSLAM.cpp:413).
+        # The first corrections close real loop-closure gaps; later ones also accept walls with little separation left.
+        strokes = None
+        sess.world_transform(keep_host_copy=False)
+        for attempt in range(8):
             try:
-                strokes, start = synth.pick_strokes(cur, min_sep=0.0, start=start, return_next=True)
+                cand, start = synth.pick_strokes(cur, min_sep=(0.04 if c < 4 else 0.015) if attempt < 5 else 0.0, start=start, return_next=True)
             except RuntimeError:
+                if attempt >= 5:
+                    break
+                continue
+            dry = sess.em_run(4, cand)
+            dry_runs += 1
+            strokes = cand
+            if dry["backprop"][0] >= 0 and dry["backprop"][1] >= 1:
                 break
+        if strokes is None:
+            break
         if cpu_every and c % cpu_every == 0:
             cov_c = cov.copy()
             t0 = time.perf_counter()
@@ -830,7 +845,7 @@ def correction_replay(gpu, g, n_corrections, cpu_every=10, budget_s=150.0):
     # after EM, as HitLSLAM::Run does when the back-propagation bounds are invalid (HitLSLAM.cpp:413)
     lat, solve, parts = np.array(lat)[keep], np.array(solve)[keep], np.array(parts)[keep]
     spans = [sp for sp, k in zip(spans, keep) if k]
-    return {"corrections": int(len(lat)), "attempted": int(attempted), "unit": "ms per correction",
+    return {"corrections": int(len(lat)), "attempted": int(attempted), "applied_fraction": float(len(lat)) / max(attempted, 1), "stroke_dry_runs": int(dry_runs), "unit": "ms per correction",
             "latency_ms": {"median": float(np.median(lat)), "p90": float(np.percentile(lat, 90)), "max": float(lat.max()), "min": float(lat.min())},
             "host_solve_ms": {"median": float(np.median(solve)), "max": float(solve.max())},
             "parts_ms_median": {"em": float(np.median(parts[:, 0])), "explicit_correction": float(np.median(parts[:, 1])),

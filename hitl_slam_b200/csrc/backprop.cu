@@ -88,8 +88,8 @@ extern "C" int hitl_backprop_poses(hitl_ctx* ctx, uint32_t n_poses, float* poses
   if (!poses_xyt || !rot_weights || !trans_weights || !destination_xy) return fail(ctx, HITL_ERR_ARG, "hitl_backprop_poses: null argument");
   if (hi >= n_poses || lo >= hi) return fail(ctx, HITL_ERR_ARG, "hitl_backprop_poses: need lo < hi < n_poses");
   const uint32_t L = hi - lo + 1;
-  DevBuf<float> d_poses, d_rw, d_tw; DevBuf<float2> d_cs;
-  struct Free { DevBuf<float>*a, *b, *c; DevBuf<float2>* d; ~Free() { a->release(); b->release(); c->release(); d->release(); } } fr{&d_poses, &d_rw, &d_tw, &d_cs};
+  // context-owned scratch, grown on demand: a correction must not pay four cudaMalloc / cudaFree round trips
+  DevBuf<float>& d_poses = ctx->d_bp_poses; DevBuf<float>& d_rw = ctx->d_bp_rw; DevBuf<float>& d_tw = ctx->d_bp_tw; DevBuf<float2>& d_cs = ctx->d_bp_cs;
   HITL_CUDA(d_poses.ensure(3 * (size_t)n_poses)); HITL_CUDA(d_rw.ensure(L)); HITL_CUDA(d_tw.ensure(L)); HITL_CUDA(d_cs.ensure(L));
   HITL_CUDA(cudaMemcpyAsync(d_poses.p, poses_xyt, 12 * (size_t)n_poses, cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(d_rw.p, rot_weights, 4 * (size_t)(L - 1), cudaMemcpyHostToDevice, ctx->stream));

@@ -180,7 +180,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_world.release(); ctx->d_poses_f.release(); ctx->d_em_pose.release(); ctx->d_em_idx.release(); ctx->d_em_xy.release();
   for (int f = 0; f < 2; ++f) { ctx->d_em_obs[f].release(); ctx->d_em_cnt[f].release(); ctx->d_em_setpose[f].release(); ctx->d_em_setoff[f].release(); ctx->d_em_slots[f].release(); }
   ctx->d_em_slotof.release();
-  ctx->d_scan_state.release(); ctx->d_ticket.release(); ctx->d_fit_partial.release(); ctx->d_fit_out.release();
+  ctx->d_scan_state.release(); ctx->d_ticket.release(); ctx->d_fit_partial.release(); ctx->d_fit_out.release(); ctx->d_bp_poses.release(); ctx->d_bp_rw.release(); ctx->d_bp_tw.release(); ctx->d_bp_cs.release();
   ctx->d_odo.release(); ctx->d_hum_i.release(); ctx->d_hum_d.release();
   ctx->d_blk_i.release(); ctx->d_blk_j.release(); ctx->d_blk_k.release(); ctx->d_blk_idx.release(); ctx->d_blk_off.release();
   ctx->d_p2lg_pose.release(); ctx->d_p2lg_off.release(); ctx->d_p2lg_pts.release(); ctx->d_p2lg_n.release(); ctx->d_p2lg_o.release(); ctx->d_p2lg_v.release();

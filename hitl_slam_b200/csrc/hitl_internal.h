@@ -145,6 +145,8 @@ struct hitl_ctx {
   hitl::DevBuf<float2> d_em_xy;
   hitl::DevBuf<uint64_t> d_scan_state;   // decoupled look-back tile states
   hitl::DevBuf<uint32_t> d_ticket;
+  hitl::DevBuf<float> d_bp_poses, d_bp_rw, d_bp_tw;   // scratch of hitl_backprop_poses
+  hitl::DevBuf<float2> d_bp_cs;
   hitl::DevBuf<double> d_fit_partial;    // per-CTA partial sums of the device M-step (two buffers)
   hitl::DevBuf<uint8_t> d_fit_out;       // FitResult of the last hitl_em_refit
 

@@ -15,19 +15,32 @@ GpuBlockEvaluator::GpuBlockEvaluator(hitl_ctx* ctx, const double* pose_array, si
   memset(r_off_, 0, sizeof(r_off_)); memset(j_off_, 0, sizeof(j_off_));
 }
 
-bool GpuBlockEvaluator::Refresh() {
+GpuBlockEvaluator::~GpuBlockEvaluator() {
+  if (r_) hitl_host_free(r_);
+  if (J_) hitl_host_free(J_);
+}
+
+bool GpuBlockEvaluator::resolve_layout() {
   if (hitl_eval_layout_get(ctx_, &layout_) != HITL_OK) { ok_ = false; error_ = "hitl_eval_layout_get failed"; return false; }
   const uint64_t counts[kNumKinds] = {layout_.n_odometry, layout_.n_human, layout_.n_stf, layout_.n_p2l_glob, layout_.n_p2l};
   uint64_t ro = 0, jo = 0;
   for (int k = 0; k < kNumKinds; ++k) { r_off_[k] = ro; j_off_[k] = jo; ro += counts[k] * kResPerBlock[k]; jo += counts[k] * kJacPerBlock[k]; }
-  r_.assign(layout_.n_residuals ? layout_.n_residuals : 1, 0.0);
-  J_.assign(layout_.n_jacobian ? layout_.n_jacobian : 1, 0.0);
-  valid_ = false; ok_ = true;
+  auto grow = [](double** p, size_t* cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) hitl_host_free(*p);
+    const size_t want = need + need / 4 + 64;
+    *p = static_cast<double*>(hitl_host_alloc(want * sizeof(double)));
+    *cap = *p ? want : 0;
+    return *p != nullptr;
+  };
+  if (!grow(&r_, &r_cap_, layout_.n_residuals + 1) || !grow(&J_, &J_cap_, layout_.n_jacobian + 1)) { ok_ = false; error_ = "hitl_host_alloc failed"; return false; }
+  dirty_ = false; ok_ = true;
   return true;
 }
 
 bool GpuBlockEvaluator::run_batch(bool want_jac) {
-  const int rc = hitl_eval(ctx_, pose_array_, precision_, r_.data(), want_jac ? J_.data() : nullptr, &last_ms_);
+  if (dirty_ && !resolve_layout()) { valid_ = false; return false; }
+  const int rc = hitl_eval(ctx_, pose_array_, precision_, r_, want_jac ? J_ : nullptr, &last_ms_);
   ++batches_;
   if (rc != HITL_OK) { ok_ = false; valid_ = false; error_ = hitl_last_error(ctx_); return false; }
   snapshot_.assign(pose_array_, pose_array_ + 3 * n_poses_);
@@ -62,10 +75,10 @@ bool GpuBlockEvaluator::Fetch(Kind kind, uint64_t block, int pose0, const double
     }
   }
   if (!ok_) return false;
-  const double* r = &r_[r_off_[kind] + block * kResPerBlock[kind]];
+  const double* r = r_ + r_off_[kind] + block * kResPerBlock[kind];
   for (int q = 0; q < nres; ++q) residuals[q] = r[q];
   if (want_jac) {
-    const double* J = &J_[j_off_[kind] + block * kJacPerBlock[kind]];
+    const double* J = J_ + j_off_[kind] + block * kJacPerBlock[kind];
     const int half = kJacPerBlock[kind] / 2;   // binary kinds: [rows x 3 wrt pose0 | rows x 3 wrt pose1]
     if (jac0) memcpy(jac0, J, sizeof(double) * 3 * nres);
     if (jac1) memcpy(jac1, J + half, sizeof(double) * 3 * nres);

@@ -33,9 +33,14 @@ class GpuBlockEvaluator : public ceres::EvaluationCallback {
  public:
   enum Kind { kOdometry = 0, kHuman = 1, kStf = 2, kPointToLineGlob = 3, kPointToLine = 4, kNumKinds = 5 };
   GpuBlockEvaluator(hitl_ctx* ctx, const double* pose_array, size_t n_poses, int precision = 0);
-  // Re-reads the block layout from the context; call after the hitl_set_*_blocks registrations.
-  bool Refresh();
-  void Rebind(const double* pose_array, size_t n_poses) { pose_array_ = pose_array; n_poses_ = n_poses; valid_ = false; }
+  ~GpuBlockEvaluator();
+  GpuBlockEvaluator(const GpuBlockEvaluator&) = delete;
+  GpuBlockEvaluator& operator=(const GpuBlockEvaluator&) = delete;
+  // Call after every hitl_set_*_blocks registration: the block layout is re-read from the context before the next batch
+  // (lazily — a problem is built from several registrations and evaluated once).
+  bool Refresh() { dirty_ = true; valid_ = false; return true; }
+  void Rebind(const double* pose_array, size_t n_poses) { pose_array_ = pose_array; n_poses_ = n_poses; valid_ = false; dirty_ = true; }
+  void Rebind(const double* pose_array, size_t n_poses, int precision) { Rebind(pose_array, n_poses); precision_ = precision; ok_ = true; error_.clear(); }
   void PrepareForEvaluation(bool evaluate_jacobians, bool new_evaluation_point) override;
 
   // Slice accessors used by the cost functions. Return false when the batch failed.
@@ -48,6 +53,7 @@ class GpuBlockEvaluator : public ceres::EvaluationCallback {
 
  private:
   bool run_batch(bool want_jac);
+  bool resolve_layout();
   bool matches(int pose, const double* x) const;
   hitl_ctx* ctx_;
   const double* pose_array_;
@@ -55,8 +61,12 @@ class GpuBlockEvaluator : public ceres::EvaluationCallback {
   int precision_;
   hitl_eval_layout layout_;
   uint64_t r_off_[kNumKinds], j_off_[kNumKinds];
-  std::vector<double> r_, J_, snapshot_;
-  bool valid_ = false, have_jac_ = false, ok_ = true;
+  // staging of one batch: page-locked (hitl_host_alloc), so hitl_eval's read-back runs at PCIe rate without a driver staging copy;
+  // grown on demand, never zero-filled (every block's slice is written by the batch)
+  double* r_ = nullptr; double* J_ = nullptr;
+  size_t r_cap_ = 0, J_cap_ = 0;
+  std::vector<double> snapshot_;
+  bool valid_ = false, have_jac_ = false, ok_ = true, dirty_ = true;
   std::string error_;
   uint64_t batches_ = 0;
   float last_ms_ = 0.f;

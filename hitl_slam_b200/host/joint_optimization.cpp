@@ -208,7 +208,9 @@ ceres::Problem::Options JointOpt::BeginProblem() {
   check(hitl_set_stf_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.05f, 0.025f), "hitl_set_stf_blocks(0)");
   check(hitl_set_p2l_glob_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_glob_blocks(0)");
   check(hitl_set_p2l_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_blocks(0)");
-  evaluator_.reset(new GpuBlockEvaluator(ctx_, pose_array_.data(), poses_.size(), precision_));
+  // one evaluator per JointOpt, re-bound per problem: its page-locked staging buffers survive from one problem to the next
+  if (!evaluator_) evaluator_.reset(new GpuBlockEvaluator(ctx_, pose_array_.data(), poses_.size(), precision_));
+  else evaluator_->Rebind(pose_array_.data(), poses_.size(), precision_);
   ceres::Problem::Options po;
   po.evaluation_callback = evaluator_.get();
   return po;
