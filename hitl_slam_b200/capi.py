@@ -45,7 +45,8 @@ class StfOpts(C.Structure):
 class StfInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_raw_matches", C.c_uint64),
                 ("n_queries", C.c_uint64), ("n_traversals", C.c_uint64), ("n_tile_pairs", C.c_uint64), ("ms_search", C.c_float), ("ms_total", C.c_float),
-                ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("sum_tile_cycles", C.c_uint64), ("max_tile_cycles", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32)]
+                ("n_coarse_pass", C.c_uint64), ("n_in_radius", C.c_uint64), ("sum_tile_cycles", C.c_uint64), ("max_tile_cycles", C.c_uint64), ("n_tiles", C.c_uint32), ("n_tiles_next", C.c_uint32),
+                ("n_gate_fail", C.c_uint64), ("n_over_cap", C.c_uint64), ("n_dir_culled", C.c_uint64)]
 
 
 class EmFitInfo(C.Structure):
@@ -296,7 +297,7 @@ class HitlGpu:
         self._ck(self.lib.hitl_find_stf(self.ctx, poses, min_pose, max_pose, src_lo, src_hi, C.byref(opts), C.byref(info)))
         res = dict(n_pairs=info.n_pairs, n_matches=info.n_matches, n_raw_matches=info.n_raw_matches, n_queries=info.n_queries,
                    n_traversals=info.n_traversals, n_tile_pairs=info.n_tile_pairs, n_coarse_pass=info.n_coarse_pass, n_in_radius=info.n_in_radius, sum_tile_cycles=info.sum_tile_cycles, max_tile_cycles=info.max_tile_cycles, ms_search=info.ms_search, ms_total=info.ms_total,
-                   n_tiles=info.n_tiles, n_tiles_next=info.n_tiles_next)
+                   n_tiles=info.n_tiles, n_tiles_next=info.n_tiles_next, n_gate_fail=info.n_gate_fail, n_over_cap=info.n_over_cap, n_dir_culled=info.n_dir_culled)
         if fetch:
             res.update(self.get_stf(info.n_pairs, info.n_matches, out))
         return res

@@ -171,7 +171,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
   ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release(); ctx->d_node_compact.release(); ctx->d_pack_k.release(); ctx->d_pack_idx.release();
-  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
   ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();
@@ -303,6 +303,7 @@ static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
     if (*(const uint32_t*)ctx->h_pinned) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
   }
   ctx->have_trees = true;
+  ctx->grid_valid = false;      // the direction masks are built from the node normals
   return HITL_OK;
 }
 
@@ -319,7 +320,7 @@ extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
   if (ctx->tree_builder == 0) {
     ctx->have_trees = false;
     const int rc = build_kdtrees_device(ctx, &ctx->tree_exact_segments);
-    if (rc == HITL_OK) ctx->have_trees = true;
+    if (rc == HITL_OK) { ctx->have_trees = true; ctx->grid_valid = false; }
     return rc;
   }
   std::vector<hitl_kdnode> nodes(ctx->n_points);
@@ -421,6 +422,7 @@ extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim
     if (*(const uint32_t*)ctx->h_pinned) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees_compact: node index out of range");
   }
   ctx->have_trees = true;
+  ctx->grid_valid = false;
   return HITL_OK;
 }
 

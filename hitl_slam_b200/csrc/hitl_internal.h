@@ -18,7 +18,8 @@ struct __align__(16) PoseRec {
   float gx0, gy0, ginv;           // occupancy grid of the scan: origin and 1 / cell size (cell >= thr)
   uint32_t gdim;                  // nx | ny << 16  (0 = empty scan)
   uint32_t goff;                  // first word of the scan's bitmap
-  float c, s;                     // cos / sin of the pose angle
+  float theta;                    // (float) pose angle: the direction filter works in float angles with a margin (search.cu)
+  float nmax;                     // largest |normal| among the scan's nodes (1 for unit normals): bounds |nb| in the angle gate
   uint32_t foff;                  // first word of the scan's FINE bitmap (kFineCells x kFineCells cells per coarse cell), kNoFine = none
 };
 constexpr uint32_t kNoFine = 0xFFFFFFFFu;
@@ -117,6 +118,9 @@ struct hitl_ctx {
   hitl::DevBuf<hitl::GridRec> d_grid;
   hitl::DevBuf<uint32_t> d_occ;
   hitl::DevBuf<uint32_t> d_occ_fine;     // second level: cell = thr / 4, consulted only for points that pass the coarse level
+  hitl::DevBuf<uint32_t> d_occ_dir;      // per coarse cell: 16 direction bins of the NODE normals near it (two cells per word); angle-gate prefilter
+  hitl::DevBuf<float> d_nmax;            // per scan: largest node-normal length
+  int dir_occupancy = 1;                 // direction prefilter on (hitl_debug_set_fine_occupancy bit 1 clears it)
   bool grid_valid = false;
   int fine_occupancy = 1;                // second-level bitmaps on (hitl_debug_set_fine_occupancy)
   float grid_thr = 0.f;

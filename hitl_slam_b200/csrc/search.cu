@@ -24,6 +24,7 @@
 //     merge the tiles of each pose into the reference's (i, j, k) order, apply the
 //     "> 10 matches per pair" rule and emit the CSR arrays.
 #include <float.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -262,14 +263,14 @@ __device__ __forceinline__ float cull_margin(float a, float b, float c, float d)
 }
 
 __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* __restrict__ aabb,
-                                 const uint32_t* __restrict__ off, const GridRec* __restrict__ grid, uint32_t n_poses,
+                                 const uint32_t* __restrict__ off, const GridRec* __restrict__ grid, const float* __restrict__ nmax, uint32_t n_poses,
                                  PoseRec* __restrict__ rec, float4* __restrict__ src, float4* __restrict__ wbox) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_poses) return;
   const Aff2 a = pose_affine(pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]);
   const Aff2 inv = affine_inverse(a);
   PoseRec r;
-  r.c = a.m00; r.s = a.m10;
+  r.theta = (float)pose[3 * i + 2]; r.nmax = nmax[i];
   r.i00 = inv.m00; r.i01 = inv.m01; r.i10 = inv.m10; r.i11 = inv.m11; r.itx = inv.tx; r.ity = inv.ty;
   const float4 b = aabb[i];
   r.off = off[i]; r.n = off[i + 1] - off[i];
@@ -370,6 +371,67 @@ __global__ void occupancy_fine_build_kernel(const float2* __restrict__ pts, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Direction occupancy: the angle gate's prefilter.  43 % of the tree walks of a dense map end with an in-radius node whose
+// normal fails `nb . R n > min_cos` (points near corners and wall ends see, in most overlapping scans, only the OTHER wall):
+// executed queries without a match, each a full walk.  Per coarse cell of scan j (same 3 x 3 dilation as the coarse bitmap, so
+// the cell of a query covers every node within thr of it) a 16-bit mask records which of 16 direction bins (22.5 degrees)
+// hold the normal of some NODE near the cell.  The gate can only pass for nodes whose normal lies within
+// alpha = acos(min_cos / (|nb| |R n|)) of the rotated source normal; if no bin that intersects that window (widened by a float
+// margin) is set, every in-radius node fails the gate, the query cannot produce a match whatever node the walk would return,
+// and skipping the walk is exact (the query still counts as executed: that accounting does not depend on walks).
+// Angles here are plain floats with kDirMargin of slack; inputs whose float angles could exceed the slack (|theta| > 256 rad,
+// zero / non-finite normals) simply bypass the filter.
+// ------------------------------------------------------------------------------------------------
+constexpr float kDirBinsPerRad = 16.0f / 6.28318530717958647692f;
+constexpr float kDirMargin = 4e-3f;                 // rad: dominates atan2f / float-angle rounding (< 1e-4 for |theta| <= 256)
+constexpr float kDirMaxTheta = 256.0f;
+// bins [floor(u_lo), floor(u_hi)] of a window in bin units, as a 16-bit mask
+__device__ __forceinline__ uint32_t dir_window_mask(float u_lo, float u_hi) {
+  const int lo = (int)floorf(u_lo), hi = (int)floorf(u_hi);
+  const int cnt = hi - lo + 1;
+  if (cnt >= 16) return 0xFFFFu;
+  const uint32_t m = (1u << cnt) - 1u, sh = (uint32_t)lo & 15u;
+  const uint32_t r = m << sh;
+  return (r | (r >> 16)) & 0xFFFFu;
+}
+
+// one thread per node: marks its direction bin(s) in the 3 x 3 coarse cells around the node's cell; per-scan max |normal|
+__global__ void occupancy_dir_build_kernel(const float4* __restrict__ node_pm, const float2* __restrict__ node_nn, const uint32_t* __restrict__ off,
+                                           uint32_t n_poses, uint64_t n_nodes, const GridRec* __restrict__ grid, uint32_t* __restrict__ occ_dir,
+                                           float* __restrict__ nmax) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes) return;
+  uint32_t lo = 0, hi = n_poses;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+  const uint32_t i = lo;
+  const GridRec g = grid[i];
+  const float4 nd = node_pm[t];
+  const float2 nv = node_nn[t];
+  const float len = sqrtf(nv.x * nv.x + nv.y * nv.y);
+  if (len > 0.0f) atomicMax(reinterpret_cast<int*>(nmax + i), __float_as_int(len));   // positive floats order like ints (NaN / inf: see below)
+  uint32_t bins;
+  if (!(len > 0.0f) || !(len < 1e30f)) {
+    // zero normal: the dot product is 0, the gate passes only for min_cos < 0 (the filter is off then); non-finite or huge: every bin
+    bins = (len > 0.0f || len != len) ? 0xFFFFu : 0u;
+    if (len != len || len >= 1e30f) atomicMax(reinterpret_cast<int*>(nmax + i), __float_as_int(1e30f));
+  } else {
+    const float u = atan2f(nv.y, nv.x) * kDirBinsPerRad;      // (-8, 8]
+    bins = dir_window_mask(u - kDirMargin * kDirBinsPerRad, u + kDirMargin * kDirBinsPerRad);
+  }
+  if (bins == 0) return;
+  uint32_t cx, cy;
+  if (!grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, nd.x, nd.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  const uint32_t nx = g.gdim & 0xFFFFu, ny = g.gdim >> 16;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = (int)cx + dx, y = (int)cy + dy;
+      if (x < 0 || y < 0 || x >= (int)nx || y >= (int)ny) continue;
+      const uint64_t cell = (uint64_t)g.goff * 32 + (uint32_t)y * nx + (uint32_t)x;   // cells of scan i start at bit goff * 32 of the coarse bitmap
+      atomicOr(occ_dir + (cell >> 1), bins << (16 * (cell & 1)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: the search.  Persistent warps; each warp pulls 32-point source tiles from a global counter.
 //
 // Per tile, the ascending target loop is split in two decoupled stages so that the expensive part
@@ -390,12 +452,13 @@ struct SearchParams {
   const float2* __restrict__ pts; const float2* __restrict__ nrm;
   const float4* __restrict__ node_pm; const float2* __restrict__ node_nn;
   const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
-  const uint32_t* __restrict__ occ; const uint32_t* __restrict__ occ_fine;
+  const uint32_t* __restrict__ occ; const uint32_t* __restrict__ occ_fine; const uint32_t* __restrict__ occ_dir;   // occ_dir = null: direction prefilter off
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
   const uint2* __restrict__ tile_j; const uint32_t* __restrict__ tile_slot;   // target range of the unit, record slot
   uint32_t tile_lo, tile_hi;          // tiles of the source shard
   uint32_t jmin, jmax;                // inclusive target range
   float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
+  float dir_alpha_unit;               // acos(min_cos / 1.0006): half-width of the angle gate for unit normals (host-computed)
   uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
   unsigned long long* __restrict__ counters;   // [6] = tile ticket
   unsigned long long* __restrict__ pose_work;  // SM cycles spent on the tiles of each source pose (load-balancing feedback)
@@ -409,9 +472,11 @@ constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kSearchMinBlocks = 16;   // 48 warps / SM: the walk is latency-bound, more resident warps hide the node loads
 constexpr uint32_t kQueueCap = 64;
 constexpr uint32_t kNotCapped = 0xFFFFFFFFu;
+constexpr uint32_t kSparseMaxPoints = 24;   // coarse stage: lane-per-candidate loop over the active points when at most this many points are below the cap
 
 struct __align__(16) WarpShared {
   uint4 rec[16][3];        // per candidate of the current half block of 16 target poses: T_ij, scan size, occupancy grid descriptor
+  uint32_t cj[64];         // stage 1: compacted candidate targets (passed the world-box test), ascending j, <= 63 waiting
   uint32_t queue[kQueueCap];   // stage A: items that passed the coarse occupancy level; item = owner lane | j << 5
   uint32_t wq[kQueueCap];      // stage B: items that also passed the fine level
   uint32_t cnt[32];        // matches per lane's point
@@ -425,7 +490,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   uint2 stack[34];                                             // walk entries (local memory, 8 B each, at most 2 per tree level)
   unsigned long long n_trav = 0, n_cand = 0;
-  uint32_t n_coarse = 0, n_inrad = 0;                          // per-thread diagnostics (flushed per kernel)
+  uint32_t n_coarse = 0, n_inrad = 0, n_gatefail = 0, n_overcap = 0, n_dirskip = 0;   // per-thread diagnostics (flushed per kernel)
 
   for (;;) {
     uint32_t tile = 0;
@@ -444,6 +509,11 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
     float2 p = make_float2(0.f, 0.f), nv = make_float2(0.f, 0.f);
     if (valid) { p = P.pts[i_off + k]; nv = P.nrm[i_off + k]; }
     const double theta_i = P.pose[3 * i + 2];
+    // direction prefilter: this lane's normal as (angle in bin units, length); usable only for finite non-zero normals and moderate pose angles
+    const float nlen = sqrtf(nv.x * nv.x + nv.y * nv.y);
+    const float thf_i = (float)theta_i;
+    const bool dir_ok = P.occ_dir != nullptr && valid && nlen > 0.0f && nlen < 1e30f && fabsf(thf_i) <= kDirMaxTheta;
+    const float nang = dir_ok ? atan2f(nv.y, nv.x) : 0.0f;
     const float4 si = P.src[i];
     Aff2 src; src.m00 = si.x; src.m01 = -si.y; src.m10 = si.y; src.m11 = si.x; src.tx = si.z; src.ty = si.w;
 
@@ -475,6 +545,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       const uint32_t it = item ? W.queue[lane] : 0u;
       const uint32_t o = it & 31u, j = it >> 5;
       const float opx = __shfl_sync(0xffffffffu, p.x, o), opy = __shfl_sync(0xffffffffu, p.y, o);
+      const float o_nang = __shfl_sync(0xffffffffu, nang, o), o_nlen = __shfl_sync(0xffffffffu, nlen, o);
+      const bool o_dir = __shfl_sync(0xffffffffu, (int)dir_ok, o) != 0;
       bool pass = false; float qx = 0.f, qy = 0.f;
       if (item && W.cnt[o] < (uint32_t)P.cap) {
         ++n_coarse;
@@ -489,6 +561,22 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
           if (pass) {
             const uint64_t bit = (uint64_t)cy * ((rj.gdim & 0xFFFFu) * kFineCells) + cx;
             pass = (__ldg(P.occ_fine + rj.foff + (bit >> 5)) >> (bit & 31)) & 1u;
+          }
+        }
+        if (pass && o_dir && !P.no_cull && fabsf(rj.theta) <= kDirMaxTheta) {
+          // Angle gate prefilter (see "Direction occupancy" above).  The gate rotates the source normal by (float)(theta_j - theta_i)
+          // (JointOptimization.cpp:604-606); in float angles that is o_nang + (theta_j - theta_i) up to < 1e-4 rad.
+          const float bound = fmul(fmul(rj.nmax, o_nlen), 1.0002f);        // >= |nb| |R n| for every node of scan j
+          const float ca = P.min_cos / bound;
+          if (ca < 1.0f) {                                                    // else no node can pass at all; leave that to the walk
+            const float alpha = (bound <= 1.0005f ? P.dir_alpha_unit : acosf(fmaxf(ca, 0.0f))) + kDirMargin;
+            const float u = (o_nang + (rj.theta - thf_i)) * kDirBinsPerRad, a16 = alpha * kDirBinsPerRad;
+            uint32_t ccx, ccy;
+            if (grid_cell(rj.gx0, rj.gy0, rj.ginv, rj.gdim, qx, qy, &ccx, &ccy)) {
+              const uint64_t cell = (uint64_t)rj.goff * 32 + ccy * (rj.gdim & 0xFFFFu) + ccx;
+              const uint32_t have = (__ldg(P.occ_dir + (cell >> 1)) >> (16 * (cell & 1))) & 0xFFFFu;
+              if ((have & dir_window_mask(u - a16, u + a16)) == 0) { pass = false; ++n_dirskip; }
+            }
           }
         }
       }
@@ -538,6 +626,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
           const float2 nb = __ldg(t.nn + bpos);
           ok = fadd(fmul(nb.x, rnx), fmul(nb.y, rny)) > P.min_cos;
           tgt = node_meta(__ldg(t.pm + bpos)) & 0x7FFFFFFFu;
+          n_gatefail += ok ? 0u : 1u;
         }
       }
       // commit in queue order: an item counts only while its owner is below the cap
@@ -545,6 +634,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
       const uint32_t earlier = __popc(same & okmask & lt);
       const bool commit = ok && (cnt_o + earlier < (uint32_t)P.cap);
+      n_overcap += (ok && !commit) ? 1u : 0u;
       const uint32_t cm = __ballot_sync(0xffffffffu, commit);
       if (commit) {
         const uint32_t dst = out_base + wcount + __popc(cm & lt);
@@ -567,29 +657,27 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
 
     if (jlo <= jhi && __any_sync(0xffffffffu, active)) {
       bool all_done = false;
-      for (uint32_t jb = jlo & ~31u; jb <= jhi && !all_done; jb += 32) {
-        // ---- stage 1: candidates of this block of 32 target poses ----
-        const uint32_t jl = jb + lane;
-        bool hit = jl >= jlo && jl <= jhi && jl != i;
-        if (hit && !P.no_cull) {
-          const float4 wb = __ldg(P.wbox + jl);
-          hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
-        }
-        const uint32_t cand = __ballot_sync(0xffffffffu, hit);
-        if (cand == 0) continue;
-        n_cand += __popc(cand);
+      uint32_t nc = 0;                                          // candidates waiting in W.cj (ascending j)
+
+      // ---- stage 1b: the next m <= 32 candidates (one per lane / slot), coarse occupancy level, queueing, walks ----
+      // Candidates come compacted: whatever the density of overlapping targets along the trajectory, every pass over this
+      // stage works on a full set of 32 (the tail of a tile excepted).
+      auto process = [&](uint32_t m) {
+        const uint32_t slots = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+        const bool have = lane < m;
+        const uint32_t jl = have ? W.cj[lane] : 0u;
         const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
-        uint32_t need = 0, todo = cand;
-        if (!P.no_cull && __popc(act_mask) * 5u < __popc(cand) * 9u) {
-          // ---- stage 1, sparse form: few points of the tile are still below the cap (stragglers keep a tile alive
-          // through all the targets), so the loop runs over the active POINTS with one candidate target per lane:
-          // each lane keeps its own T_ij and tests the owner's point against its own target's coarse bitmap. ----
+        uint32_t need = 0, todo = slots;
+        if (!P.no_cull && __popc(act_mask) <= (int)kSparseMaxPoints) {
+          // sparse form: few points of the tile are still below the cap (stragglers keep a tile alive through all its
+          // targets), so the loop runs over the active POINTS with one candidate target per lane: each lane keeps its own
+          // T_ij and tests the owner's point against its own target's coarse bitmap.
           Aff2 T; uint32_t goff = 0, gdim = 0; float gx0 = 0.f, gy0 = 0.f, ginv = 0.f;
           bool live = false;
-          if (hit) {
+          if (have) {
             const PoseRec rj = P.rec[jl];
             Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
-            T = affine_mul(inv, src);
+            T = affine_mul(inv, src);                             // T_ij = target^-1 * source (JointOptimization.cpp:304)
             goff = rj.goff; gdim = rj.gdim; gx0 = rj.gx0; gy0 = rj.gy0; ginv = rj.ginv;
             live = rj.n != 0;
           }
@@ -607,66 +695,92 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
                 in = (__ldg(P.occ + goff + (bit >> 5)) >> (bit & 31)) & 1u;
               }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, in);     // bit c = target jb + c passes for owner o
-            if (lane == o) need = m;
+            const uint32_t mm = __ballot_sync(0xffffffffu, in);   // bit c = candidate slot c passes for owner o
+            if (lane == o) need = mm;
           }
           todo = __reduce_or_sync(0xffffffffu, need);
         } else {
-        // dense form: the candidates' T_ij and grid descriptors are staged in shared memory, 16 targets at a time
-        for (uint32_t half = 0; half < 2; ++half) {
-          const uint32_t hm = cand & (0xFFFFu << (16 * half));
-          if (hm == 0) continue;
-          if (hit && (lane >> 4) == half) {
-            // this lane's candidate: T_ij = target^-1 * source once per (tile, j)
-            const PoseRec rj = P.rec[jl];
-            Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
-            const Aff2 T = affine_mul(inv, src);
-            uint4* const r = W.rec[lane & 15];
-            r[0] = make_uint4(__float_as_uint(T.m00), __float_as_uint(T.m01), __float_as_uint(T.m10), __float_as_uint(T.m11));
-            r[1] = make_uint4(__float_as_uint(T.tx), __float_as_uint(T.ty), rj.n, rj.goff);
-            r[2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
-          }
-          __syncwarp();
-          for (uint32_t cm = hm; cm; cm &= cm - 1) {
-            const uint32_t c = __ffs(cm) - 1;
-            const uint4 r0 = W.rec[c & 15][0], r1 = W.rec[c & 15][1];
-            bool in = active && r1.z != 0;                        // r1.z = n
-            if (in && !P.no_cull) {
-              Aff2 T; T.m00 = __uint_as_float(r0.x); T.m01 = __uint_as_float(r0.y); T.m10 = __uint_as_float(r0.z); T.m11 = __uint_as_float(r0.w);
-              T.tx = __uint_as_float(r1.x); T.ty = __uint_as_float(r1.y);
-              float qx, qy;
-              affine_apply(T, p.x, p.y, &qx, &qy);
-              const uint4 r2 = W.rec[c & 15][2];
-              uint32_t cx, cy;
-              in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
-              if (in) {
-                const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
-                in = (__ldg(P.occ + r1.w + (bit >> 5)) >> (bit & 31)) & 1u;
-              }
+          // dense form: the candidates' T_ij and grid descriptors are staged in shared memory, 16 at a time, and every lane
+          // tests its own point against each
+          for (uint32_t half = 0; half < 2; ++half) {
+            const uint32_t hm = slots & (0xFFFFu << (16 * half));
+            if (hm == 0) continue;
+            if (have && (lane >> 4) == half) {
+              const PoseRec rj = P.rec[jl];
+              Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+              const Aff2 T = affine_mul(inv, src);
+              uint4* const r = W.rec[lane & 15];
+              r[0] = make_uint4(__float_as_uint(T.m00), __float_as_uint(T.m01), __float_as_uint(T.m10), __float_as_uint(T.m11));
+              r[1] = make_uint4(__float_as_uint(T.tx), __float_as_uint(T.ty), rj.n, rj.goff);
+              r[2] = make_uint4(__float_as_uint(rj.gx0), __float_as_uint(rj.gy0), __float_as_uint(rj.ginv), rj.gdim);
             }
-            need |= (uint32_t)in << c;
+            __syncwarp();
+            for (uint32_t cm = hm; cm; cm &= cm - 1) {
+              const uint32_t c = __ffs(cm) - 1;
+              const uint4 r0 = W.rec[c & 15][0], r1 = W.rec[c & 15][1];
+              bool in = active && r1.z != 0;                        // r1.z = n
+              if (in && !P.no_cull) {
+                Aff2 T; T.m00 = __uint_as_float(r0.x); T.m01 = __uint_as_float(r0.y); T.m10 = __uint_as_float(r0.z); T.m11 = __uint_as_float(r0.w);
+                T.tx = __uint_as_float(r1.x); T.ty = __uint_as_float(r1.y);
+                float qx, qy;
+                affine_apply(T, p.x, p.y, &qx, &qy);
+                const uint4 r2 = W.rec[c & 15][2];
+                uint32_t cx, cy;
+                in = grid_cell(__uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), r2.w, qx, qy, &cx, &cy);
+                if (in) {
+                  const uint32_t bit = cy * (r2.w & 0xFFFFu) + cx;
+                  in = (__ldg(P.occ + r1.w + (bit >> 5)) >> (bit & 31)) & 1u;
+                }
+              }
+              need |= (uint32_t)in << c;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-        }
         }
         // ---- stage 2: queue (j, lane) items in order; walk whenever a full batch is available ----
-        for (uint32_t cm = todo; cm; cm &= cm - 1) {
+        for (uint32_t cm = todo & slots; cm && !all_done; cm &= cm - 1) {
           const uint32_t c = __ffs(cm) - 1;
           const bool want = ((need >> c) & 1u) && active;
-          const uint32_t m = __ballot_sync(0xffffffffu, want);
-          if (m == 0) continue;
-          if (want) W.queue[qn + __popc(m & lt)] = lane | ((jb + c) << 5);
-          qn += __popc(m);
+          const uint32_t mm = __ballot_sync(0xffffffffu, want);
+          if (mm == 0) continue;
+          if (want) W.queue[qn + __popc(mm & lt)] = lane | (W.cj[c] << 5);
+          qn += __popc(mm);
           __syncwarp();
           if (qn >= 32) {
             filter(32);
             if (qw >= 32) {
               drain(32);
-              if (!__any_sync(0xffffffffu, active)) { all_done = true; break; }
+              if (!__any_sync(0xffffffffu, active)) all_done = true;
             }
           }
         }
+        // drop the consumed candidates
+        const uint32_t rest = nc - m;
+        uint32_t keep = 0;
+        if (lane < rest) keep = W.cj[m + lane];
+        __syncwarp();
+        if (lane < rest) W.cj[lane] = keep;
+        nc = rest;
+        __syncwarp();
+      };
+
+      for (uint32_t jb = jlo & ~31u; jb <= jhi && !all_done; jb += 32) {
+        // ---- stage 1a: world-box test, one target pose per lane; survivors are appended to the candidate list ----
+        const uint32_t jl = jb + lane;
+        bool hit = jl >= jlo && jl <= jhi && jl != i;
+        if (hit && !P.no_cull) {
+          const float4 wb = __ldg(P.wbox + jl);
+          hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
+        }
+        const uint32_t cand = __ballot_sync(0xffffffffu, hit);
+        if (cand == 0) continue;
+        n_cand += __popc(cand);
+        if (hit) W.cj[nc + __popc(cand & lt)] = jl;
+        nc += __popc(cand);
+        __syncwarp();
+        if (nc >= 32) process(32);
       }
+      if (nc && !all_done) process(nc);
       while ((qn || qw) && !all_done) {
         if (qn && qw < 32) { filter(qn < 32 ? qn : 32); if ((qn && qw < 32) || qw == 0) continue; }
         drain(qw < 32 ? qw : 32);
@@ -695,12 +809,16 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
     }
     __syncwarp();
   }
-  unsigned long long n_co = n_coarse, n_ir = n_inrad;
+  unsigned long long n_co = n_coarse, n_ir = n_inrad, n_gf = n_gatefail, n_oc = n_overcap, n_ds = n_dirskip;
   for (int o = 16; o; o >>= 1) {
     n_trav += __shfl_xor_sync(0xffffffffu, n_trav, o);
     n_co += __shfl_xor_sync(0xffffffffu, n_co, o); n_ir += __shfl_xor_sync(0xffffffffu, n_ir, o);
+    n_gf += __shfl_xor_sync(0xffffffffu, n_gf, o); n_oc += __shfl_xor_sync(0xffffffffu, n_oc, o); n_ds += __shfl_xor_sync(0xffffffffu, n_ds, o);
   }
-  if (lane == 0) { atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); atomicAdd(P.counters + 9, n_co); atomicAdd(P.counters + 10, n_ir); }
+  if (lane == 0) {
+    atomicAdd(P.counters + 1, n_trav); atomicAdd(P.counters + 5, n_cand); atomicAdd(P.counters + 9, n_co); atomicAdd(P.counters + 10, n_ir);
+    atomicAdd(P.counters + 11, n_gf); atomicAdd(P.counters + 12, n_oc); atomicAdd(P.counters + 13, n_ds);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1184,6 +1302,17 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
       HITL_LAUNCH_CHECK("occupancy_fine_build_kernel");
     }
   }
+  // direction masks of the node normals (two 16-bit cells per word) and the per-scan bound on |normal|
+  HITL_CUDA(ctx->d_nmax.ensure(n));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_nmax.p, 0, 4 * (size_t)(n ? n : 1), ctx->stream));
+  if (ctx->dir_occupancy && ctx->n_points) {
+    const uint64_t cells = words * 32;
+    HITL_CUDA(ctx->d_occ_dir.ensure((cells + 1) / 2));
+    HITL_CUDA(cudaMemsetAsync(ctx->d_occ_dir.p, 0, 4 * ((cells + 1) / 2), ctx->stream));
+    occupancy_dir_build_kernel<<<(uint32_t)((ctx->n_points + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_off.p, n, ctx->n_points,
+                                                                                                 ctx->d_grid.p, ctx->d_occ_dir.p, ctx->d_nmax.p);
+    HITL_LAUNCH_CHECK("occupancy_dir_build_kernel");
+  }
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tab is a local
   ctx->grid_valid = true; ctx->grid_thr = thr;
   return HITL_OK;
@@ -1196,7 +1325,7 @@ int upload_poses_and_prep(hitl_ctx* ctx, const double* pose_array, float thr) {
   HITL_CUDA(ctx->d_rec.ensure(ctx->n_poses)); HITL_CUDA(ctx->d_src.ensure(ctx->n_poses));
   HITL_CUDA(ctx->d_wbox.ensure(ctx->n_poses));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_pose.p, pose_array, sizeof(double) * 3 * ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
-  pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->d_grid.p, ctx->n_poses,
+  pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->d_grid.p, ctx->d_nmax.p, ctx->n_poses,
                                                                         ctx->d_rec.p, ctx->d_src.p, ctx->d_wbox.p);
   HITL_LAUNCH_CHECK("pose_prep_kernel");
   return HITL_OK;
@@ -1254,6 +1383,8 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaEventRecord(ctx->evx[0], ctx->stream));   // after pose upload + prep
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
+  P.occ_dir = (ctx->dir_occupancy && o->min_cosine_angle > 0.0f && o->min_cosine_angle < 1.0f) ? ctx->d_occ_dir.p : nullptr;
+  P.dir_alpha_unit = acosf(std::min(1.0f, std::max(0.0f, o->min_cosine_angle / 1.0006f)));
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
   P.tile_j = ctx->d_tile_j.p; P.tile_slot = ctx->d_tile_slot.p;
   P.tile_lo = ctx->h_tile_begin[lo]; P.tile_hi = ctx->h_tile_begin[hi];
@@ -1333,6 +1464,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   inf.n_queries = ctx->h_pinned[0]; inf.n_traversals = ctx->h_pinned[1]; inf.n_raw_matches = ctx->h_pinned[2];
   inf.n_pairs = ctx->h_pinned[3]; inf.n_matches = ctx->h_pinned[4]; inf.n_tile_pairs = ctx->h_pinned[5]; inf.n_coarse_pass = ctx->h_pinned[9]; inf.n_in_radius = ctx->h_pinned[10];
   inf.sum_tile_cycles = ctx->h_pinned[7] << 6; inf.max_tile_cycles = ctx->h_pinned[8] << 6;
+  inf.n_gate_fail = ctx->h_pinned[11]; inf.n_over_cap = ctx->h_pinned[12]; inf.n_dir_culled = ctx->h_pinned[13];
   const uint64_t work_sum = ctx->h_pinned[7];
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_search, ctx->ev[1], ctx->ev[2]));
   HITL_CUDA(cudaEventElapsedTime(&inf.ms_total, ctx->ev[0], ctx->ev[3]));
@@ -1412,7 +1544,9 @@ extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int sme
 
 extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {
   if (!ctx) return HITL_ERR_ARG;
-  if (ctx->fine_occupancy != (on ? 1 : 0)) { ctx->fine_occupancy = on ? 1 : 0; ctx->grid_valid = false; }
+  // bit 0: fine level, bit 1 set: direction prefilter OFF (on = 1 keeps both culls, on = 0 drops the fine level only, on = 2 / 3 drop the prefilter)
+  const int fine = on & 1, dir = (on & 2) ? 0 : 1;
+  if (ctx->fine_occupancy != fine || ctx->dir_occupancy != dir) { ctx->fine_occupancy = fine; ctx->dir_occupancy = dir; ctx->grid_valid = false; }
   return HITL_OK;
 }
 

@@ -135,6 +135,9 @@ typedef struct {
   uint64_t max_tile_cycles; /* ... and of the single most expensive tile: the kernel's critical path (a tile is a sequential loop) */
   uint32_t n_tiles;       /* work units (runs of <= 32 source points) the search kernel scheduled in this call */
   uint32_t n_tiles_next;  /* ... and after the adaptive split of heavy tiles that this call's measurements triggered */
+  uint64_t n_gate_fail;   /* walks that found an in-radius node whose normal failed the angle gate (an executed query without a match) */
+  uint64_t n_over_cap;    /* walks that matched but whose point had filled its cap earlier in the same batch (speculative, dropped) */
+  uint64_t n_dir_culled;  /* queries whose walk was skipped because no node normal near them can pass the angle gate (exact prefilter) */
 } hitl_stf_info;
 
 /* Correspondences between source poses [src_lo, src_hi) ∩ [min_pose, max_pose] and all target
@@ -291,8 +294,9 @@ int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan, uint32_t* 
  * additionally cuts EVERY tile into that many consecutive target ranges that are searched concurrently and merged
  * under the per-point cap.  The tiling is a scheduling choice; parity tests use this to prove it. */
 int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_t target_parts);
-/* Switches the second (fine, cell = threshold / 4) level of the occupancy cull on or off; the bitmaps are rebuilt by the
- * next search.  Culling is result-preserving; parity tests compare both settings and disable_culling = 1. */
+/* Switches the second (fine, cell = threshold / 4) level of the occupancy cull (bit 0 of `on`) and the angle-gate direction
+ * prefilter (bit 1 SET switches it OFF: on = 1 is the default, everything on; 0 = no fine level; 3 = no prefilter; 2 = neither);
+ * the bitmaps are rebuilt by the next search.  Culling is result-preserving; parity tests compare the settings and disable_culling = 1. */
 int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
 /* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48);
  * smem_carveout_pct = preferred shared-memory carve-out of the unified L1 (percent, -1 = driver default). */

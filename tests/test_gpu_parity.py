@@ -391,6 +391,13 @@ def test_find_stf_culling_is_result_preserving_at_scale(gpu, maps):
     gpu.debug_set_fine_occupancy(True)
     assert_same_stf(a, c)
     assert a["n_queries"] == c["n_queries"] and a["n_traversals"] < c["n_traversals"] < b["n_traversals"]
+    # the angle-gate direction prefilter only removes walks whose result would fail the normal gate
+    gpu.debug_set_fine_occupancy(3)
+    d = gpu.find_stf(poses)
+    gpu.debug_set_fine_occupancy(True)
+    assert_same_stf(a, d)
+    assert a["n_queries"] == d["n_queries"] and d["n_dir_culled"] == 0 and a["n_dir_culled"] > 0
+    assert a["n_traversals"] + a["n_dir_culled"] >= d["n_traversals"] * 0.98 and a["n_gate_fail"] < d["n_gate_fail"]
     counts = np.diff(a["pair_off"].astype(np.int64))
     assert (counts > 10).all()
     # per source point at most `cap` matches over all pairs
