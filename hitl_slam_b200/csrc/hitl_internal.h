@@ -24,6 +24,7 @@ struct __align__(16) PoseRec {
 };
 constexpr uint32_t kNoFine = 0xFFFFFFFFu;
 constexpr int kFineCells = 4;     // fine cell = coarse cell / 4  (power of two: the fine 1/cell is exact)
+constexpr int kMipCells = 4;      // mip cell = 4 x 4 coarse cells
 // Per-scan occupancy grid descriptor (host-built from the scan AABBs for a given threshold).
 struct GridRec { float gx0, gy0, ginv; uint32_t gdim, goff, foff; };
 static_assert(sizeof(PoseRec) == 64, "PoseRec must be 64 bytes");
@@ -118,6 +119,9 @@ struct hitl_ctx {
   hitl::DevBuf<hitl::GridRec> d_grid;
   hitl::DevBuf<uint32_t> d_occ;
   hitl::DevBuf<uint32_t> d_occ_fine;     // second level: cell = thr / 4, consulted only for points that pass the coarse level
+  hitl::DevBuf<uint32_t> d_occ_mip;      // coarse bitmap reduced kMipCells x kMipCells (tile-box vs scan cull, one lane per target pose)
+  hitl::DevBuf<uint32_t> d_moff;         // per scan: first word of its mip bitmap
+  int mip_occupancy = 1;                 // (hitl_debug_set_fine_occupancy bit 2 set clears it)
   hitl::DevBuf<uint32_t> d_occ_dir;      // per coarse cell: 16 direction bins of the NODE normals near it (two cells per word); angle-gate prefilter
   hitl::DevBuf<float> d_nmax;            // per scan: largest node-normal length
   int dir_occupancy = 1;                 // direction prefilter on (hitl_debug_set_fine_occupancy bit 1 clears it)

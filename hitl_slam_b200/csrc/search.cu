@@ -324,7 +324,7 @@ __device__ __forceinline__ bool fine_cell(const float gx0, const float gy0, cons
 
 __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ off, const uint32_t* __restrict__ tile_scan,
                                        const uint32_t* __restrict__ tile_k0, uint32_t n_tiles, const GridRec* __restrict__ grid,
-                                       uint32_t* __restrict__ occ) {
+                                       uint32_t* __restrict__ occ, uint32_t* __restrict__ occ_mip, const uint32_t* __restrict__ moff) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   const uint32_t i = tile_scan[tile], kl = tile_k0[tile], k = (kl & 0xFFFFu) + lane;
@@ -340,6 +340,10 @@ __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uin
       if (x < 0 || y < 0 || x >= (int)nx || y >= (int)ny) continue;
       const uint32_t bit = (uint32_t)y * nx + (uint32_t)x;
       atomicOr(occ + g.goff + (bit >> 5), 1u << (bit & 31));
+      if (occ_mip) {                                            // the same mark one level up: mip cell = kMipCells x kMipCells coarse cells
+        const uint32_t mnx = (nx + kMipCells - 1) / kMipCells, mbit = ((uint32_t)y / kMipCells) * mnx + (uint32_t)x / kMipCells;
+        atomicOr(occ_mip + moff[i] + (mbit >> 5), 1u << (mbit & 31));
+      }
     }
 }
 
@@ -458,6 +462,7 @@ struct SearchParams {
   uint32_t tile_lo, tile_hi;          // tiles of the source shard
   uint32_t jmin, jmax;                // inclusive target range
   float thr, min_cos; int cap; uint32_t skip; uint32_t no_cull;
+  const uint32_t* __restrict__ occ_mip; const uint32_t* __restrict__ moff;   // occ_mip = null: tile-box cull off
   float dir_alpha_unit;               // acos(min_cos / 1.0006): half-width of the angle gate for unit normals (host-computed)
   uint32_t* __restrict__ raw_j; uint32_t* __restrict__ raw_k; uint32_t* __restrict__ raw_idx; uint32_t* __restrict__ tile_cnt;
   unsigned long long* __restrict__ counters;   // [6] = tile ticket
@@ -482,6 +487,44 @@ struct __align__(16) WarpShared {
   uint32_t cnt[32];        // matches per lane's point
   uint32_t exec_last[32];  // j that filled the cap (kNotCapped otherwise)
 };
+
+// Tile-box vs target-scan cull (stage 1a, one lane per target pose j).  Every point of the tile lies in the robot-frame box
+// [rx0, rx1] x [ry0, ry1] of source scan i; T_ij maps that box to a parallelogram whose axis-aligned hull in frame j (the four
+// transformed corners, widened by a margin that dominates the float rounding of T_ij * p) contains every T_ij * p the later
+// stages compute.  The coarse cell of any such point therefore lies in the hull's cell range (the cell formula is monotone in
+// the coordinate), so if NO coarse cell of scan j in that range is marked — tested one level up, on the kMipCells x kMipCells
+// reduction of the coarse bitmap — every per-point coarse test of this (tile, j) pair would fail: skipping the pair is exact.
+__device__ __forceinline__ bool tile_box_may_touch(const SearchParams& P, uint32_t j, const Aff2& src, float rx0, float ry0, float rx1, float ry1) {
+  const PoseRec rj = P.rec[j];
+  if (rj.n == 0) return false;                                  // empty scan: no point can have a neighbour (the coarse stage drops it too)
+  Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
+  const Aff2 T = affine_mul(inv, src);
+  float x0, y0, x1, y1, x2, y2, x3, y3;
+  affine_apply(T, rx0, ry0, &x0, &y0); affine_apply(T, rx1, ry0, &x1, &y1);
+  affine_apply(T, rx0, ry1, &x2, &y2); affine_apply(T, rx1, ry1, &x3, &y3);
+  float lox = fminf(fminf(x0, x1), fminf(x2, x3)), hix = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+  float loy = fminf(fminf(y0, y1), fminf(y2, y3)), hiy = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
+  const float m = cull_margin(lox, loy, hix, hiy);
+  lox -= m; loy -= m; hix += m; hiy += m;
+  // cell range with the cell formula of grid_cell_dims (same instruction sequence: monotone in the coordinate)
+  const float nxf = (float)(rj.gdim & 0xFFFFu), nyf = (float)(rj.gdim >> 16);
+  const float fx0 = fmul(fsub(lox, rj.gx0), rj.ginv), fx1 = fmul(fsub(hix, rj.gx0), rj.ginv);
+  const float fy0 = fmul(fsub(loy, rj.gy0), rj.ginv), fy1 = fmul(fsub(hiy, rj.gy0), rj.ginv);
+  if (!(fx1 >= 0.0f && fy1 >= 0.0f && fx0 < nxf && fy0 < nyf)) return false;   // the hull misses the grid: every point test fails (NaN: conservative below)
+  if (!(fx0 == fx0 && fx1 == fx1 && fy0 == fy0 && fy1 == fy1)) return true;
+  const uint32_t cx0 = (uint32_t)fmaxf(fx0, 0.0f), cy0 = (uint32_t)fmaxf(fy0, 0.0f);
+  const uint32_t cx1 = (uint32_t)fminf(fx1, nxf - 1.0f), cy1 = (uint32_t)fminf(fy1, nyf - 1.0f);
+  const uint32_t mx0 = cx0 / kMipCells, mx1 = cx1 / kMipCells, my0 = cy0 / kMipCells, my1 = cy1 / kMipCells;
+  if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 48u) return true;      // an oversized tile (its points straddle a depth jump): not worth the scan
+  const uint32_t mnx = ((rj.gdim & 0xFFFFu) + kMipCells - 1) / kMipCells;
+  const uint32_t* __restrict__ mip = P.occ_mip + __ldg(P.moff + j);
+  for (uint32_t my = my0; my <= my1; ++my)
+    for (uint32_t mx = mx0; mx <= mx1; ++mx) {
+      const uint32_t bit = my * mnx + mx;
+      if ((__ldg(mip + (bit >> 5)) >> (bit & 31)) & 1u) return true;
+    }
+  return false;
+}
 
 template <int MINB>
 __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const SearchParams P) {
@@ -527,6 +570,13 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
     {
       const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
       bx0 -= m; by0 -= m; bx1 += m; by1 += m;
+    }
+    // robot-frame box of the tile's points (tile-box vs target-scan cull, stage 1a)
+    float rx0 = FLT_MAX, ry0 = FLT_MAX, rx1 = -FLT_MAX, ry1 = -FLT_MAX;
+    if (valid) { rx0 = rx1 = p.x; ry0 = ry1 = p.y; }
+    for (int o = 16; o; o >>= 1) {
+      rx0 = fminf(rx0, __shfl_xor_sync(0xffffffffu, rx0, o)); ry0 = fminf(ry0, __shfl_xor_sync(0xffffffffu, ry0, o));
+      rx1 = fmaxf(rx1, __shfl_xor_sync(0xffffffffu, rx1, o)); ry1 = fmaxf(ry1, __shfl_xor_sync(0xffffffffu, ry1, o));
     }
     const uint32_t out_base = P.tile_slot[tile] * (uint32_t)P.cap;   // this unit's private record region
     const uint2 tj = P.tile_j[tile];
@@ -771,6 +821,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
         if (hit && !P.no_cull) {
           const float4 wb = __ldg(P.wbox + jl);
           hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
+          if (hit && P.occ_mip) hit = tile_box_may_touch(P, jl, src, rx0, ry0, rx1, ry1);
         }
         const uint32_t cand = __ballot_sync(0xffffffffu, hit);
         if (cand == 0) continue;
@@ -1286,6 +1337,17 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
     tab[i].foff = (fine && fine_words[i]) ? (uint32_t)fwords : kNoFine;
     if (fine) fwords += fine_words[i];
   }
+  // mip level: the coarse bitmap reduced kMipCells x kMipCells
+  std::vector<uint32_t> moff(n ? n : 1, 0);
+  uint64_t mwords = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    moff[i] = (uint32_t)mwords;
+    const uint32_t nx = tab[i].gdim & 0xFFFFu, ny = tab[i].gdim >> 16;
+    mwords += ((uint64_t)((nx + kMipCells - 1) / kMipCells) * ((ny + kMipCells - 1) / kMipCells) + 31) / 32;
+  }
+  HITL_CUDA(ctx->d_occ_mip.ensure(mwords)); HITL_CUDA(ctx->d_moff.ensure(n));
+  if (n) HITL_CUDA(cudaMemcpyAsync(ctx->d_moff.p, moff.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_occ_mip.p, 0, 4 * (mwords ? mwords : 1), ctx->stream));
   HITL_CUDA(ctx->d_grid.ensure(n)); HITL_CUDA(ctx->d_occ.ensure(words)); HITL_CUDA(ctx->d_occ_fine.ensure(fwords));
   if (n) HITL_CUDA(cudaMemcpyAsync(ctx->d_grid.p, tab.data(), sizeof(GridRec) * n, cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_occ.p, 0, 4 * (words ? words : 1), ctx->stream));
@@ -1294,7 +1356,7 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
     const int threads = 128;
     const uint32_t blocks = (uint32_t)(((size_t)ctx->n_tiles * 32 + threads - 1) / threads);
     occupancy_build_kernel<<<blocks, threads, 0, ctx->stream>>>(
-        ctx->d_pts.p, ctx->d_off.p, ctx->d_tile_scan.p, ctx->d_tile_k0.p, ctx->n_tiles, ctx->d_grid.p, ctx->d_occ.p);
+        ctx->d_pts.p, ctx->d_off.p, ctx->d_tile_scan.p, ctx->d_tile_k0.p, ctx->n_tiles, ctx->d_grid.p, ctx->d_occ.p, ctx->d_occ_mip.p, ctx->d_moff.p);
     HITL_LAUNCH_CHECK("occupancy_build_kernel");
     if (fine && fwords) {
       occupancy_fine_build_kernel<<<blocks, threads, 0, ctx->stream>>>(
@@ -1384,6 +1446,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
   P.occ_dir = (ctx->dir_occupancy && o->min_cosine_angle > 0.0f && o->min_cosine_angle < 1.0f) ? ctx->d_occ_dir.p : nullptr;
+  P.occ_mip = ctx->mip_occupancy ? ctx->d_occ_mip.p : nullptr; P.moff = ctx->d_moff.p;
   P.dir_alpha_unit = acosf(std::min(1.0f, std::max(0.0f, o->min_cosine_angle / 1.0006f)));
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
   P.tile_j = ctx->d_tile_j.p; P.tile_slot = ctx->d_tile_slot.p;
@@ -1546,6 +1609,7 @@ extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {
   if (!ctx) return HITL_ERR_ARG;
   // bit 0: fine level, bit 1 set: direction prefilter OFF (on = 1 keeps both culls, on = 0 drops the fine level only, on = 2 / 3 drop the prefilter)
   const int fine = on & 1, dir = (on & 2) ? 0 : 1;
+  ctx->mip_occupancy = (on & 4) ? 0 : 1;                       // bit 2 set: tile-box cull OFF (no rebuild needed: the kernel just ignores the level)
   if (ctx->fine_occupancy != fine || ctx->dir_occupancy != dir) { ctx->fine_occupancy = fine; ctx->dir_occupancy = dir; ctx->grid_valid = false; }
   return HITL_OK;
 }

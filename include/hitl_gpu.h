@@ -295,7 +295,8 @@ int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan, uint32_t* 
  * under the per-point cap.  The tiling is a scheduling choice; parity tests use this to prove it. */
 int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_t target_parts);
 /* Switches the second (fine, cell = threshold / 4) level of the occupancy cull (bit 0 of `on`) and the angle-gate direction
- * prefilter (bit 1 SET switches it OFF: on = 1 is the default, everything on; 0 = no fine level; 3 = no prefilter; 2 = neither);
+ * prefilter (bit 1 SET switches it OFF: on = 1 is the default, everything on; 0 = no fine level; 3 = no prefilter; 2 = neither;
+ * bit 2 SET additionally switches the tile-box vs scan cull off, e.g. 5);
  * the bitmaps are rebuilt by the next search.  Culling is result-preserving; parity tests compare the settings and disable_culling = 1. */
 int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
 /* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48);

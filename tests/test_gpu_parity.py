@@ -398,6 +398,12 @@ def test_find_stf_culling_is_result_preserving_at_scale(gpu, maps):
     assert_same_stf(a, d)
     assert a["n_queries"] == d["n_queries"] and d["n_dir_culled"] == 0 and a["n_dir_culled"] > 0
     assert a["n_traversals"] + a["n_dir_culled"] >= d["n_traversals"] * 0.98 and a["n_gate_fail"] < d["n_gate_fail"]
+    # the tile-box vs scan cull (mip level of the coarse bitmap) only removes (tile, target) pairs whose every per-point test would fail
+    gpu.debug_set_fine_occupancy(5)
+    e = gpu.find_stf(poses)
+    gpu.debug_set_fine_occupancy(True)
+    assert_same_stf(a, e)
+    assert a["n_queries"] == e["n_queries"] and a["n_tile_pairs"] < e["n_tile_pairs"] and a["n_coarse_pass"] <= e["n_coarse_pass"]
     counts = np.diff(a["pair_off"].astype(np.int64))
     assert (counts > 10).all()
     # per source point at most `cap` matches over all pairs
