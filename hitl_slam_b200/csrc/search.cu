@@ -26,6 +26,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -326,13 +327,15 @@ __global__ void occupancy_build_kernel(const float2* __restrict__ pts, const uin
                                        const uint32_t* __restrict__ tile_k0, uint32_t n_tiles, const GridRec* __restrict__ grid,
                                        uint32_t* __restrict__ occ, uint32_t* __restrict__ occ_mip, const uint32_t* __restrict__ moff) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (tile >= n_tiles) return;
+  if (tile >= n_tiles) return;                                  // warp-uniform
   const uint32_t i = tile_scan[tile], kl = tile_k0[tile], k = (kl & 0xFFFFu) + lane;
-  if (lane >= (kl >> 16) || k >= off[i + 1] - off[i]) return;
   const GridRec g = grid[i];
-  const float2 p = pts[off[i] + k];
-  uint32_t cx, cy;
-  if (!grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  uint32_t cx = 0, cy = 0;
+  bool ok = lane < (kl >> 16) && k < off[i + 1] - off[i];
+  if (ok) { const float2 p = pts[off[i] + k]; ok = grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy); }   // false cannot happen: the grid covers the AABB
+  // consecutive beams fall into the same cell (cell 15 cm, beam spacing millimetres): one lane per distinct cell does the marking
+  const uint32_t same = __match_any_sync(0xffffffffu, ok ? (cy << 16 | cx) : (0xFFFF0000u | lane));
+  if (!ok || (uint32_t)(__ffs(same) - 1) != lane) return;
   const uint32_t nx = g.gdim & 0xFFFFu, ny = g.gdim >> 16;
   for (int dy = -1; dy <= 1; ++dy)
     for (int dx = -1; dx <= 1; ++dx) {
@@ -351,14 +354,16 @@ __global__ void occupancy_fine_build_kernel(const float2* __restrict__ pts, cons
                                             const uint32_t* __restrict__ tile_k0, uint32_t n_tiles, const GridRec* __restrict__ grid,
                                             uint32_t* __restrict__ occ) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (tile >= n_tiles) return;
+  if (tile >= n_tiles) return;                                  // warp-uniform
   const uint32_t i = tile_scan[tile], kl = tile_k0[tile], k = (kl & 0xFFFFu) + lane;
-  if (lane >= (kl >> 16) || k >= off[i + 1] - off[i]) return;
   const GridRec g = grid[i];
-  if (g.foff == kNoFine) return;
-  const float2 p = pts[off[i] + k];
-  uint32_t cx, cy;
-  if (!fine_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  if (g.foff == kNoFine) return;                                // warp-uniform (one scan per tile)
+  uint32_t cx = 0, cy = 0;
+  bool ok = lane < (kl >> 16) && k < off[i + 1] - off[i];
+  if (ok) { const float2 p = pts[off[i] + k]; ok = fine_cell(g.gx0, g.gy0, g.ginv, g.gdim, p.x, p.y, &cx, &cy); }   // false cannot happen: the grid covers the AABB
+  const unsigned long long key = ok ? ((unsigned long long)cy << 32 | cx) : (0xFFFFFFFF00000000ull | lane);
+  const uint32_t same = __match_any_sync(0xffffffffu, key);     // one lane per distinct fine cell
+  if (!ok || (uint32_t)(__ffs(same) - 1) != lane) return;
   const int nx = (int)((g.gdim & 0xFFFFu) * kFineCells), ny = (int)((g.gdim >> 16) * kFineCells);
   for (int dy = -kFineCells; dy <= kFineCells; ++dy) {
     const int y = (int)cy + dy;
@@ -412,19 +417,27 @@ __global__ void occupancy_dir_build_kernel(const float4* __restrict__ node_pm, c
   const float4 nd = node_pm[t];
   const float2 nv = node_nn[t];
   const float len = sqrtf(nv.x * nv.x + nv.y * nv.y);
-  if (len > 0.0f) atomicMax(reinterpret_cast<int*>(nmax + i), __float_as_int(len));   // positive floats order like ints (NaN / inf: see below)
   uint32_t bins;
+  float bound = len;                                            // this node's contribution to the scan's bound on |normal|
   if (!(len > 0.0f) || !(len < 1e30f)) {
     // zero normal: the dot product is 0, the gate passes only for min_cos < 0 (the filter is off then); non-finite or huge: every bin
     bins = (len > 0.0f || len != len) ? 0xFFFFu : 0u;
-    if (len != len || len >= 1e30f) atomicMax(reinterpret_cast<int*>(nmax + i), __float_as_int(1e30f));
+    bound = (len != len || len >= 1e30f) ? 1e30f : 0.0f;
   } else {
     const float u = atan2f(nv.y, nv.x) * kDirBinsPerRad;      // (-8, 8]
     bins = dir_window_mask(u - kDirMargin * kDirBinsPerRad, u + kDirMargin * kDirBinsPerRad);
   }
-  if (bins == 0) return;
-  uint32_t cx, cy;
-  if (!grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, nd.x, nd.y, &cx, &cy)) return;   // cannot happen: the grid covers the AABB
+  uint32_t cx = 0, cy = 0;
+  const bool ok = bins != 0 && grid_cell(g.gx0, g.gy0, g.ginv, g.gdim, nd.x, nd.y, &cx, &cy);   // false for bins != 0 cannot happen: the grid covers the AABB
+  // one atomic per (scan, cell) and per scan in this warp: lanes of the same group OR their bins / take the max bound
+  const uint32_t act = __activemask();
+  const uint32_t scan_grp = __match_any_sync(act, i);
+  const int gmax = __reduce_max_sync(scan_grp, __float_as_int(bound));        // non-negative floats order like ints
+  if ((uint32_t)(__ffs(scan_grp) - 1) == (threadIdx.x & 31u) && gmax > 0) atomicMax(reinterpret_cast<int*>(nmax + i), gmax);
+  const unsigned long long key = ok ? ((unsigned long long)i << 32 | cy << 16 | cx) : (0xFFFFFFFF00000000ull | (threadIdx.x & 31u));
+  const uint32_t same = __match_any_sync(act, key);
+  bins = __reduce_or_sync(same, bins);
+  if (!ok || (uint32_t)(__ffs(same) - 1) != (threadIdx.x & 31u)) return;
   const uint32_t nx = g.gdim & 0xFFFFu, ny = g.gdim >> 16;
   for (int dy = -1; dy <= 1; ++dy)
     for (int dx = -1; dx <= 1; ++dx) {
@@ -1305,6 +1318,7 @@ namespace hitl {
 // (Re)build the per-scan occupancy bitmaps for threshold thr (cached until the scans or thr change).
 int ensure_occupancy(hitl_ctx* ctx, float thr) {
   if (ctx->grid_valid && ctx->grid_thr == thr) return HITL_OK;
+  struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
   const uint32_t n = ctx->n_poses;
   std::vector<GridRec> tab(n);
   std::vector<uint64_t> fine_words(n, 0);
@@ -1376,6 +1390,10 @@ int ensure_occupancy(hitl_ctx* ctx, float thr) {
     HITL_LAUNCH_CHECK("occupancy_dir_build_kernel");
   }
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));   // tab is a local
+  if (getenv("HITL_STF_TIMING")) {
+    struct timespec ts1; clock_gettime(CLOCK_MONOTONIC, &ts1);
+    fprintf(stderr, "occupancy rebuild (coarse + mip + fine + direction levels): %.3f ms host wall\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+  }
   ctx->grid_valid = true; ctx->grid_thr = thr;
   return HITL_OK;
 }
