@@ -248,11 +248,19 @@ class RefSampler:
                 "source_stride": self.stride, "source_poses": int(len(self.ids))}
 
 
+def reference_footprint_gb(g):
+    """Host memory the reference's JointOpt needs for a map: info_mat_ (n_poses^2 floats, JointOptimization.cpp:1313) + ~120 B per KD node."""
+    n, m = float(len(g["poses"])), float(g["offsets"][-1])
+    return (4.0 * n * n + 120.0 * m) / 1e9
+
+
 def ref_sample(g, steps=3):
     """cpu_baseline of the own arm: the mean of `steps` RefSampler steps (None when oracle/_ref was not built)."""
     from oracle.pyoracle import RefBackend
     if not RefBackend.available(fast=True):
         return None
+    if reference_footprint_gb(g) > 24.0:
+        return None                                  # the reference allocates an N x N float image (info_mat_) and one heap node per point: not runnable at this size
     smp = RefSampler(g)
     rs = [smp.step() for _ in range(steps + 1)][1:]
     out = dict(rs[-1])
@@ -289,7 +297,7 @@ def run_reference(args, rank, world):
     rebuild_fast_oracle_native()
     g = load_workload_detached(args.workload, args.poses, args.beams)
     from oracle.pyoracle import RefBackend
-    if RefBackend.available(fast=True):
+    if RefBackend.available(fast=True) and reference_footprint_gb(g) <= 24.0:
         smp = RefSampler(g)
         step = smp.step
     else:                                            # oracle/_ref absent (built only where /root/reference exists): the oracle port

@@ -172,7 +172,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
   ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release(); ctx->d_node_compact.release(); ctx->d_pack_k.release(); ctx->d_pack_idx.release();
-  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_occ_mip.release(); ctx->d_moff.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_gbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_occ_mip.release(); ctx->d_moff.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
   ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();

@@ -113,6 +113,7 @@ struct hitl_ctx {
   hitl::DevBuf<double> d_pose;           // x, y, theta
   hitl::DevBuf<hitl::PoseRec> d_rec;
   hitl::DevBuf<float4> d_wbox;           // world-frame AABB per scan, inflated (pair cull)
+  hitl::DevBuf<float4> d_gbox;           // union of d_wbox over every 32 consecutive poses (first level of the target sweep)
   hitl::DevBuf<float4> d_src;            // source-side transform per pose: cos, sin, tx, ty
   // occupancy bitmaps (exact "no point of scan j within thr of q" test), rebuilt when thr or the scans change
   std::vector<float> h_aabb;             // 4 per scan

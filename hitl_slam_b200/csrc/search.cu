@@ -292,6 +292,19 @@ __global__ void pose_prep_kernel(const double* __restrict__ pose, const float4* 
   src[i] = make_float4(a.m00, a.m10, a.tx, a.ty);
 }
 
+// Union of the (inflated) world boxes of every 32 consecutive poses: the first level of the target sweep.
+__global__ void pose_group_box_kernel(const float4* __restrict__ wbox, uint32_t n_poses, float4* __restrict__ gbox) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g * 32 >= n_poses) return;
+  const uint32_t j = g * 32 + lane;
+  float4 b = j < n_poses ? wbox[j] : make_float4(FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (int o = 16; o; o >>= 1) {
+    b.x = fminf(b.x, __shfl_xor_sync(0xffffffffu, b.x, o)); b.y = fminf(b.y, __shfl_xor_sync(0xffffffffu, b.y, o));
+    b.z = fmaxf(b.z, __shfl_xor_sync(0xffffffffu, b.z, o)); b.w = fmaxf(b.w, __shfl_xor_sync(0xffffffffu, b.w, o));
+  }
+  if (lane == 0) gbox[g] = b;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Occupancy bitmaps: scan j's grid has cell size >= thr * (1 + 2^-9) and every point marks the
 // 3x3 block of cells around its own cell.  A query q with an unmarked (or out-of-grid) cell has
@@ -469,6 +482,7 @@ struct SearchParams {
   const float2* __restrict__ pts; const float2* __restrict__ nrm;
   const float4* __restrict__ node_pm; const float2* __restrict__ node_nn;
   const PoseRec* __restrict__ rec; const float4* __restrict__ src; const float4* __restrict__ wbox; const double* __restrict__ pose;
+  const float4* __restrict__ gbox; uint32_t n_groups;   // union of the world boxes of every 32 consecutive poses
   const uint32_t* __restrict__ occ; const uint32_t* __restrict__ occ_fine; const uint32_t* __restrict__ occ_dir;   // occ_dir = null: direction prefilter off
   const uint32_t* __restrict__ tile_scan; const uint32_t* __restrict__ tile_k0;
   const uint2* __restrict__ tile_j; const uint32_t* __restrict__ tile_slot;   // target range of the unit, record slot
@@ -827,7 +841,24 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
         __syncwarp();
       };
 
+      // ---- stage 1a': GROUPS of 32 consecutive target poses, one group per lane: the union of their world boxes (consecutive
+      // poses of a trajectory are neighbours in space) against the tile box.  Only blocks of groups that overlap are looked at
+      // pose by pose, so the sweep over the targets costs N / 1024 steps plus the overlapping part, not N / 32 (100 k-pose maps). ----
+      uint32_t gmask = 0, gbase = 0xFFFFFFFFu;
       for (uint32_t jb = jlo & ~31u; jb <= jhi && !all_done; jb += 32) {
+        if (!P.no_cull) {
+          const uint32_t grp = jb >> 5;
+          if ((grp >> 5) != gbase) {
+            gbase = grp >> 5;
+            const uint32_t gl = (gbase << 5) + lane;
+            bool ghit = false;
+            if (gl < P.n_groups) { const float4 gb = __ldg(P.gbox + gl); ghit = !(gb.x > bx1 || gb.z < bx0 || gb.y > by1 || gb.w < by0); }
+            gmask = __ballot_sync(0xffffffffu, ghit);
+          }
+          const uint32_t rest = gmask >> (grp & 31u);
+          if (rest == 0) { jb = (((gbase + 1) << 10)) - 32; continue; }     // no overlapping group left in this span of 1024 poses
+          if (!(rest & 1u)) { jb += ((__ffs(rest) - 1) << 5) - 32; continue; }   // jump to the next overlapping group
+        }
         // ---- stage 1a: world-box test, one target pose per lane; survivors are appended to the candidate list ----
         const uint32_t jl = jb + lane;
         bool hit = jl >= jlo && jl <= jhi && jl != i;
@@ -1408,6 +1439,12 @@ int upload_poses_and_prep(hitl_ctx* ctx, const double* pose_array, float thr) {
   pose_prep_kernel<<<(ctx->n_poses + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pose.p, ctx->d_aabb.p, ctx->d_off.p, ctx->d_grid.p, ctx->d_nmax.p, ctx->n_poses,
                                                                         ctx->d_rec.p, ctx->d_src.p, ctx->d_wbox.p);
   HITL_LAUNCH_CHECK("pose_prep_kernel");
+  const uint32_t n_groups = (ctx->n_poses + 31) / 32;
+  HITL_CUDA(ctx->d_gbox.ensure(n_groups));
+  if (n_groups) {
+    pose_group_box_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_wbox.p, ctx->n_poses, ctx->d_gbox.p);
+    HITL_LAUNCH_CHECK("pose_group_box_kernel");
+  }
   return HITL_OK;
 }
 int launch_scan_aabb(hitl_ctx* ctx) {
@@ -1464,6 +1501,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   SearchParams P;
   P.pts = ctx->d_pts.p; P.nrm = ctx->d_nrm.p; P.node_pm = ctx->d_node_pm.p; P.node_nn = ctx->d_node_nn.p;
   P.occ_dir = (ctx->dir_occupancy && o->min_cosine_angle > 0.0f && o->min_cosine_angle < 1.0f) ? ctx->d_occ_dir.p : nullptr;
+  P.gbox = ctx->d_gbox.p; P.n_groups = (n + 31) / 32;
   P.occ_mip = ctx->mip_occupancy ? ctx->d_occ_mip.p : nullptr; P.moff = ctx->d_moff.p;
   P.dir_alpha_unit = acosf(std::min(1.0f, std::max(0.0f, o->min_cosine_angle / 1.0006f)));
   P.rec = ctx->d_rec.p; P.src = ctx->d_src.p; P.occ = ctx->d_occ.p; P.occ_fine = ctx->d_occ_fine.p; P.wbox = ctx->d_wbox.p; P.pose = ctx->d_pose.p; P.tile_scan = ctx->d_tile_scan.p; P.tile_k0 = ctx->d_tile_k0.p;
