@@ -87,8 +87,8 @@ int build_tiling(hitl_ctx* ctx, uint32_t max_len) {
 // the target poses, so a few points that never reach the cap keep it alive through all of them — along the TARGET
 // axis into up to 16 consecutive ranges (never below 64 target poses) that different warps search concurrently
 // (stf_split_merge_kernel re-applies the per-point cap across the ranges).  Returns the number of tiles that were split.
-uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, uint32_t lo, uint32_t hi, uint64_t limit,
-                           std::vector<uint32_t>* est) {
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, const std::vector<uint32_t>& h_end, uint32_t lo,
+                           uint32_t hi, uint64_t limit, std::vector<uint32_t>* est) {
   std::vector<uint32_t> scan, kl, jlo, jhi;
   const size_t cap0 = ctx->h_tile_scan.size() + 1024;
   est->clear(); est->reserve(cap0);
@@ -103,13 +103,16 @@ uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, c
     const bool measured = t >= lo && t < hi;
     const uint64_t work = measured ? h_work[t - lo] : 0;
     uint32_t parts = 1, jparts = 1;
+    uint32_t swept_end = std::min(b, last_pose);
     if (work > limit) {
       const bool is_unit = a != 0 || b != kFullRange;                       // units of a group keep their points (the group must stay aligned)
       if (!is_unit) while (parts < 8 && len / (parts * 2) >= 4 && work > limit * parts) parts *= 2;
-      // only tiles that some point kept alive to the end of the target range: a tile whose points all reach the cap
-      // would redo its whole matching phase in every range
-      if (ctx->target_splitting && h_open[t - lo] > 0 && work > limit * parts) {
-        const uint32_t ja = a, jb = std::min(b, last_pose);
+      // The part of the target range the tile really swept: to its end when some point stayed below the cap, else up to the target
+      // where its last point was capped (h_end).  Every range restarts the cap state, so a range redoes the (cheap) matching of the
+      // points that cap early; the long tail that a few slow points cause is what gets divided.
+      if (h_open[t - lo] == 0 && h_end[t - lo] > a) swept_end = std::min(swept_end, h_end[t - lo] - 1);
+      if (ctx->target_splitting && work > limit * parts) {
+        const uint32_t ja = a, jb = swept_end;
         const uint32_t span = jb >= ja ? jb - ja + 1 : 0;
         jparts = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(16, span / std::max(1u, ctx->min_target_span)), (work + limit * parts - 1) / (limit * parts));
         if (jparts < 1) jparts = 1;
@@ -120,7 +123,7 @@ uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, c
     const uint32_t w = (uint32_t)(work / (parts * jparts));   // children inherit an equal share of the measured work
     for (uint32_t p0 = 0; p0 < len; p0 += step) {
       if (jparts == 1) { scan.push_back(i); kl.push_back((k0 + p0) | (std::min(step, len - p0) << 16)); jlo.push_back(a); jhi.push_back(b); est->push_back(w); continue; }
-      const uint32_t ja = a, jb = std::min(b, last_pose), span = jb - ja + 1;
+      const uint32_t ja = a, jb = swept_end, span = jb - ja + 1;    // the ranges divide the swept part; the last one keeps the original end
       for (uint32_t q = 0; q < jparts; ++q) {
         const uint32_t qa = ja + (uint32_t)((uint64_t)span * q / jparts), qb = ja + (uint32_t)((uint64_t)span * (q + 1) / jparts) - 1;
         scan.push_back(i); kl.push_back((k0 + p0) | (std::min(step, len - p0) << 16));
@@ -172,7 +175,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
   ctx->d_node_pm.release(); ctx->d_node_nn.release(); ctx->d_node_aos.release(); ctx->d_node_compact.release(); ctx->d_pack_k.release(); ctx->d_pack_idx.release();
-  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_gbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_occ_mip.release(); ctx->d_moff.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release();
+  ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_gbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_occ_mip.release(); ctx->d_moff.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release(); ctx->d_tile_end.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
   ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();

@@ -96,7 +96,7 @@ struct hitl_ctx {
   int search_carveout = -1;              // preferred shared-memory carve-out in percent (-1: driver default)
   int search_variant = 0;                // 0: 16 CTAs/SM (32 regs), 1: 12 CTAs/SM (40 regs), 2: 10 CTAs/SM (hitl_debug_set_search_variant)
   // scheduling hint of the search: tiles sorted by the cycles the previous call spent on them
-  hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys, d_tile_open;
+  hitl::DevBuf<uint32_t> d_tile_work, d_tile_order, d_tile_iota, d_tile_keys, d_tile_open, d_tile_end;
   hitl::DevBuf<uint8_t> d_sort_tmp;
 
   // ---- trees ----
@@ -209,8 +209,8 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
 
 int build_tiling(hitl_ctx* ctx, uint32_t max_len);
 int upload_tiling(hitl_ctx* ctx);
-uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, uint32_t lo, uint32_t hi, uint64_t limit,
-                           std::vector<uint32_t>* est);
+uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, const std::vector<uint32_t>& h_end, uint32_t lo,
+                           uint32_t hi, uint64_t limit, std::vector<uint32_t>* est);
 constexpr uint32_t kFullRange = 0xFFFFFFFFu;
 // device tree builder (kdtree_gpu.cu): all scans at once, reference-identical shape
 int build_kdtrees_device(hitl_ctx* ctx, uint64_t* n_exact_out);

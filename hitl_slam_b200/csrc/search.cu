@@ -497,6 +497,7 @@ struct SearchParams {
   const uint32_t* __restrict__ tile_order;     // tiles of the shard, most expensive first (from the previous call), or null
   uint32_t* __restrict__ tile_work;            // cycles / 64 per tile of this call
   uint32_t* __restrict__ tile_open;            // points of the tile that ended below the cap (they kept it alive through all its targets)
+  uint32_t* __restrict__ tile_end;             // first target pose the tile did NOT need to look at any more (all its points were capped before it)
 };
 
 constexpr int kSearchThreads = 128;
@@ -732,6 +733,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       __syncwarp();
     };
 
+    uint32_t j_reached = jlo;                                   // sweep position when the tile ended (scheduling feedback only)
     if (jlo <= jhi && __any_sync(0xffffffffu, active)) {
       bool all_done = false;
       uint32_t nc = 0;                                          // candidates waiting in W.cj (ascending j)
@@ -846,6 +848,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       // pose by pose, so the sweep over the targets costs N / 1024 steps plus the overlapping part, not N / 32 (100 k-pose maps). ----
       uint32_t gmask = 0, gbase = 0xFFFFFFFFu;
       for (uint32_t jb = jlo & ~31u; jb <= jhi && !all_done; jb += 32) {
+        j_reached = jb + 32;
         if (!P.no_cull) {
           const uint32_t grp = jb >> 5;
           if ((grp >> 5) != gbase) {
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       }
     }
     const uint32_t open_pts = __popc(__ballot_sync(0xffffffffu, valid && W.cnt[lane] < (uint32_t)P.cap));
-    if (lane == 0) { P.tile_cnt[tile] = wcount; P.tile_open[tile] = open_pts; }
+    if (lane == 0) { P.tile_cnt[tile] = wcount; P.tile_open[tile] = open_pts; P.tile_end[tile] = j_reached; }
     // queries the reference semantics execute for this point: every j != i in range up to and
     // including the one that filled the cap (JointOptimization.cpp:597-600)
     unsigned long long exec = 0;
@@ -1513,8 +1516,8 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   P.counters = (unsigned long long*)ctx->d_counters.p;
   P.pose_work = (unsigned long long*)ctx->d_pose_work.p;
   P.tile_work = ctx->d_tile_work.p;
-  HITL_CUDA(ctx->d_tile_open.ensure(ctx->n_tiles));
-  P.tile_open = ctx->d_tile_open.p;
+  HITL_CUDA(ctx->d_tile_open.ensure(ctx->n_tiles)); HITL_CUDA(ctx->d_tile_end.ensure(ctx->n_tiles));
+  P.tile_open = ctx->d_tile_open.p; P.tile_end = ctx->d_tile_end.p;
   P.tile_order = nullptr;
   const uint32_t n_tiles = P.tile_hi - P.tile_lo;
   const uint32_t wpb = kSearchThreads / 32;
@@ -1611,10 +1614,11 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
     const bool may_split = ctx->split_rounds < ctx->max_split_rounds;
     if (may_split) ++ctx->split_rounds;
     if (may_split && h_max > 2 * limit) {
-      std::vector<uint32_t> h_work(n_tiles), h_open(n_tiles), est;
+      std::vector<uint32_t> h_work(n_tiles), h_open(n_tiles), h_end(n_tiles), est;
       HITL_CUDA(cudaMemcpy(h_work.data(), ctx->d_tile_work.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
       HITL_CUDA(cudaMemcpy(h_open.data(), ctx->d_tile_open.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
-      if (split_heavy_tiles(ctx, h_work, h_open, P.tile_lo, P.tile_hi, limit, &est)) {
+      HITL_CUDA(cudaMemcpy(h_end.data(), ctx->d_tile_end.p + P.tile_lo, 4 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+      if (split_heavy_tiles(ctx, h_work, h_open, h_end, P.tile_lo, P.tile_hi, limit, &est)) {
         rc = upload_tiling(ctx);
         if (rc) return rc;
         const uint32_t new_lo = ctx->h_tile_begin[lo], new_hi = ctx->h_tile_begin[hi], nn = new_hi - new_lo;
