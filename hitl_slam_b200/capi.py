@@ -746,6 +746,14 @@ class HostLib:
         self.lib.hitl_host_solver_selftest(x, max_iterations, int(hold_x1), int(force_cg), out)
         return x, dict(initial_cost=out[0], final_cost=out[1], iterations=int(out[2]), termination=int(out[3]))
 
+    def evaluate_selftest(self, x0, hold_x1=False):
+        """Problem::Evaluate of Powell's function: (gradient, (rows, cols, nnz) of the CRS Jacobian, cost)."""
+        self._bind_mirror()
+        self.lib.hitl_host_evaluate_selftest.argtypes = [_f64p, C.c_int, _f64p, _u64p, C.POINTER(C.c_double)]
+        g, dims, cost = np.zeros(4), np.zeros(3, np.uint64), C.c_double()
+        n = self.lib.hitl_host_evaluate_selftest(np.ascontiguousarray(x0, np.float64), int(hold_x1), g, dims, C.byref(cost))
+        return g[:max(n, 0)], tuple(int(v) for v in dims), cost.value
+
     def save_log(self, path, entries):
         """entries: list of (type, undone, [[x, y], ...]) in the reference's session-log format."""
         self._bind_mirror()
@@ -863,6 +871,19 @@ class HostSession:
 
     def world_transform(self, keep_host_copy=False):
         self._ck(self.lib.hitl_host_session_world_transform(self.s, int(keep_host_copy)))
+
+    def use_shard_contexts(self, extra_gpus):
+        """JointOpt::UseShardContexts: HitlGpu objects on OTHER devices that share the search and the STF blocks (call set_map afterwards)."""
+        self._extra = list(extra_gpus)                    # keep them alive
+        arr = (C.c_void_p * max(len(self._extra), 1))(*[g.ctx for g in self._extra])
+        self.lib.hitl_host_session_use_shard_contexts.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        self._ck(self.lib.hitl_host_session_use_shard_contexts(self.s, len(self._extra), arr))
+
+    def shard_info(self):
+        out, n = np.zeros(3 * 64, np.uint64), C.c_uint32()
+        self.lib.hitl_host_session_shard_info.argtypes = [C.c_void_p, C.c_uint32, _u64p, C.POINTER(C.c_uint32)]
+        self.lib.hitl_host_session_shard_info(self.s, 64, out, C.byref(n))
+        return [tuple(int(x) for x in out[3 * r:3 * r + 3]) for r in range(n.value)]
 
     def set_device_m_step(self, on=True):
         """Where EMInput's M-step runs: device (hitl_em_refit, default) or the host LM (the checker)."""

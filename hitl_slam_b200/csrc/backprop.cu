@@ -85,6 +85,7 @@ using namespace hitl;
 extern "C" int hitl_backprop_poses(hitl_ctx* ctx, uint32_t n_poses, float* poses_xyt, uint32_t lo, uint32_t hi, const float* rot_weights,
                                    const float* trans_weights, float theta, const float* destination_xy, float* ms_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!poses_xyt || !rot_weights || !trans_weights || !destination_xy) return fail(ctx, HITL_ERR_ARG, "hitl_backprop_poses: null argument");
   if (hi >= n_poses || lo >= hi) return fail(ctx, HITL_ERR_ARG, "hitl_backprop_poses: need lo < hi < n_poses");
   const uint32_t L = hi - lo + 1;

@@ -83,6 +83,7 @@ extern "C" int hitl_comm_unique_id(void* id_out) {
 
 extern "C" int hitl_comm_init(hitl_ctx* ctx, const void* nccl_unique_id, int rank, int world) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!nccl_unique_id || world < 1 || rank < 0 || rank >= world) return fail(ctx, HITL_ERR_ARG, "hitl_comm_init: bad argument");
   if (!nccl_ready()) return fail(ctx, HITL_ERR_NCCL, "hitl_comm_init: libnccl.so.2 not found (no NCCL in this process and none on the library path)");
   if (ctx->comm) return fail(ctx, HITL_ERR_STATE, "hitl_comm_init: this context already has a communicator (hitl_comm_destroy first)");
@@ -97,6 +98,7 @@ extern "C" int hitl_comm_init(hitl_ctx* ctx, const void* nccl_unique_id, int ran
 
 extern "C" int hitl_comm_destroy(hitl_ctx* ctx) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->comm) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -119,6 +121,7 @@ namespace hitl { int normal_eq_launch(hitl_ctx* ctx, const double* pose_array); 
 
 extern "C" int hitl_normal_eq_allreduce(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* cost, float* ms_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   const size_t n = ctx->n_poses;
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (pose_array) {                                   // evaluate this rank's blocks first, same stream, no synchronisation in between
@@ -145,6 +148,7 @@ extern "C" int hitl_normal_eq_allreduce(hitl_ctx* ctx, const double* pose_array,
 extern "C" int hitl_gather_stf_blocks(hitl_ctx* ctx, int root, uint64_t cap_blocks, uint64_t* n_blocks_per_rank, uint32_t* pair_i, uint32_t* pair_j,
                                       double* r, double* J) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   const int world = ctx->comm ? ctx->comm_world : 1, rank = ctx->comm ? ctx->comm_rank : 0;
   if (root < 0 || root >= world) return fail(ctx, HITL_ERR_ARG, "hitl_gather_stf_blocks: root out of range");
   if (!ctx->eval_valid) return fail(ctx, HITL_ERR_STATE, "hitl_gather_stf_blocks: call hitl_eval (with Jacobians) first: r and J of this rank's blocks must be resident");

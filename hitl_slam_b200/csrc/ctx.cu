@@ -203,6 +203,7 @@ extern "C" uint64_t hitl_launch_count(const hitl_ctx* ctx) { return ctx ? ctx->l
 extern "C" int hitl_sm_count(const hitl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" int hitl_last_kernel_ms(hitl_ctx* ctx, int which, float* ms) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (which < 0 || which >= HITL_K_COUNT || !ms) return fail(ctx, HITL_ERR_ARG, "hitl_last_kernel_ms: bad argument");
   if (!ctx->kev_set[which]) return fail(ctx, HITL_ERR_STATE, "hitl_last_kernel_ms: that kernel has not been launched yet");
   HITL_CUDA(cudaEventSynchronize(ctx->kev[which][1]));
@@ -221,6 +222,7 @@ extern "C" void hitl_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* off, const float* pts_xy, const float* nrm_xy) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!off && n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_scans: null offsets");
   HITL_CUDA(cudaSetDevice(ctx->device));
   // Validate everything into locals first: a rejected call leaves the context exactly as it was.
@@ -313,6 +315,7 @@ static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
 
 extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_kdtrees: call hitl_set_scans first");
   if (!nodes && ctx->n_points) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: null nodes");
   return upload_trees(ctx, nodes);
@@ -320,6 +323,7 @@ extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
 
 extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_build_kdtrees: call hitl_set_scans first");
   if (ctx->tree_builder == 0) {
     ctx->have_trees = false;
@@ -353,6 +357,7 @@ extern "C" int hitl_build_kdtrees(hitl_ctx* ctx) {
 
 extern "C" int hitl_debug_set_tree_builder(hitl_ctx* ctx, int host) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   ctx->tree_builder = host ? 1 : 0;
   return HITL_OK;
 }
@@ -371,6 +376,7 @@ extern "C" int hitl_kdtree_build_host(const float* pts_xy, const float* nrm_xy, 
 
 extern "C" int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_get_kdtrees: trees not built");
   const size_t m = ctx->n_points;
   if (!m) return HITL_OK;
@@ -409,6 +415,7 @@ __global__ void compact_nodes_kernel(const float4* __restrict__ pm, uint64_t m, 
 
 extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_kdtrees_compact: call hitl_set_scans first");
   const size_t m = ctx->n_points;
   if (!index_dim && m) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees_compact: null nodes");
@@ -432,6 +439,7 @@ extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim
 
 extern "C" int hitl_get_kdtrees_compact(hitl_ctx* ctx, uint32_t* index_dim_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_get_kdtrees_compact: trees not built");
   const size_t m = ctx->n_points;
   if (!m) return HITL_OK;
@@ -464,6 +472,7 @@ __global__ void debug_relative_pose_kernel(const double* __restrict__ pose, uint
 
 extern "C" int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, float* sin_out, float* cos_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n == 0) return HITL_OK;
   if (!x || !sin_out || !cos_out) return fail(ctx, HITL_ERR_ARG, "hitl_debug_sincos: null argument");
   TmpBuf<float> dx, ds, dc;
@@ -479,6 +488,7 @@ extern "C" int hitl_debug_sincos(hitl_ctx* ctx, uint64_t n, const float* x, floa
 
 extern "C" int hitl_debug_relative_pose(hitl_ctx* ctx, const double* pose_array, uint32_t n_pairs, const uint32_t* src, const uint32_t* dst, float* out6) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n_pairs == 0) return HITL_OK;
   if (!pose_array || !src || !dst || !out6 || ctx->n_poses == 0) return fail(ctx, HITL_ERR_ARG, "hitl_debug_relative_pose: bad argument");
   for (uint32_t q = 0; q < n_pairs; ++q)

@@ -411,6 +411,7 @@ using namespace hitl;
 
 extern "C" int hitl_verify_input(hitl_ctx* ctx, uint32_t n_selected, const float* sel_xy, float threshold, uint32_t* points_verified, uint32_t* seen_mask) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!points_verified || (n_selected && !sel_xy)) return fail(ctx, HITL_ERR_ARG, "hitl_verify_input: null argument");
   if (n_selected > 8) return fail(ctx, HITL_ERR_ARG, "hitl_verify_input: at most 8 selected points");
   if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_verify_input: world clouds not set (hitl_world_transform / hitl_set_world_clouds)");
@@ -439,6 +440,7 @@ extern "C" int hitl_verify_input(hitl_ctx* ctx, uint32_t n_selected, const float
 
 extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float* world_xy_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_world_transform: scans not set");
   if (!poses_xyt && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_world_transform: null poses");
   HITL_CUDA(ctx->d_world.ensure(ctx->n_points)); HITL_CUDA(ctx->d_poses_f.ensure(3 * (size_t)ctx->n_poses));
@@ -459,6 +461,7 @@ extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float
 
 extern "C" int hitl_set_world_clouds(hitl_ctx* ctx, const float* world_xy) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_world_clouds: scans not set");
   if (!world_xy && ctx->n_points) return fail(ctx, HITL_ERR_ARG, "hitl_set_world_clouds: null clouds");
   HITL_CUDA(ctx->d_world.ensure(ctx->n_points));
@@ -485,6 +488,7 @@ static void make_seg2(const float s[4], Seg2* o) {
 extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double threshold, uint64_t cap, uint32_t* out_pose, uint32_t* out_idx,
                                float* out_xy, uint64_t* n_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_inliers: world clouds not set");
   if (!seg || !n_out) return fail(ctx, HITL_ERR_ARG, "hitl_em_inliers: null argument");
   *n_out = 0;
@@ -523,6 +527,7 @@ extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double thresho
 
 extern "C" int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4], hitl_em_fit_info* info) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_refit: world clouds not set");
   if (!seg_in || !seg_out || max_iterations < 0) return fail(ctx, HITL_ERR_ARG, "hitl_em_refit: bad argument");
   hitl_em_fit_info inf; memset(&inf, 0, sizeof(inf));
@@ -577,6 +582,7 @@ extern "C" int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier
 extern "C" int hitl_em_assign(hitl_ctx* ctx, const float segs[8], double threshold, uint32_t min_obs, uint32_t n_sets[2], uint32_t* set_pose0,
                               uint64_t* set_off0, uint32_t* obs0, uint32_t* set_pose1, uint64_t* set_off1, uint32_t* obs1) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_assign: world clouds not set");
   if (!segs || !n_sets) return fail(ctx, HITL_ERR_ARG, "hitl_em_assign: null argument");
   n_sets[0] = n_sets[1] = 0;

@@ -361,6 +361,7 @@ using namespace hitl;
 // ---- block registration ------------------------------------------------------------------------
 extern "C" int hitl_set_stf_blocks_from_search(hitl_ctx* ctx, float std_dev, float corr) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_set_stf_blocks_from_search: no search result");
   ctx->eval_valid = ctx->neq_valid = false;
   ctx->stf_from_search = true; ctx->nb_stf = ctx->n_pairs; ctx->stf_std = std_dev; ctx->stf_corr = corr;
@@ -369,6 +370,7 @@ extern "C" int hitl_set_stf_blocks_from_search(hitl_ctx* ctx, float std_dev, flo
 extern "C" int hitl_set_stf_blocks(hitl_ctx* ctx, uint64_t n_pairs, const uint32_t* pair_i, const uint32_t* pair_j, const uint64_t* pair_off,
                                    const uint32_t* k, const uint32_t* idx, float std_dev, float corr) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_set_stf_blocks: scans not set");
   if (n_pairs && (!pair_i || !pair_j || !pair_off || !k || !idx)) return fail(ctx, HITL_ERR_ARG, "hitl_set_stf_blocks: null argument");
   const uint64_t nm = n_pairs ? pair_off[n_pairs] : 0;
@@ -395,6 +397,7 @@ extern "C" int hitl_set_stf_blocks(hitl_ctx* ctx, uint64_t n_pairs, const uint32
 }
 extern "C" int hitl_set_odometry_blocks(hitl_ctx* ctx, uint32_t n_blocks, const float* consts9) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n_blocks && !consts9) return fail(ctx, HITL_ERR_ARG, "hitl_set_odometry_blocks: null argument");
   if (n_blocks && n_blocks + 1 > ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_odometry_blocks: more blocks than pose pairs");
   for (uint32_t b = 0; b < n_blocks; ++b)
@@ -406,6 +409,7 @@ extern "C" int hitl_set_odometry_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
 }
 extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int32_t* type_pose, const double* targets4) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n_blocks && (!type_pose || !targets4)) return fail(ctx, HITL_ERR_ARG, "hitl_set_human_blocks: null argument");
   for (uint32_t b = 0; b < n_blocks; ++b) {
     const int t = type_pose[2 * b];
@@ -423,6 +427,7 @@ extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int
 extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const uint32_t* blk_pose, const uint64_t* blk_off, const float* pts_xy,
                                         const float* ln_xy, const float* lo, const uint8_t* valid, float std_dev, float corr) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n_blocks && (!blk_pose || !blk_off || !pts_xy || !ln_xy || !lo || !valid)) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: null argument");
   for (uint32_t b = 0; b < n_blocks; ++b) if (blk_pose[b] >= ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: pose out of range");
   if (n_blocks && blk_off[0] != 0) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_glob_blocks: blk_off must start at 0");
@@ -445,6 +450,7 @@ extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
 extern "C" int hitl_set_p2l_blocks(hitl_ctx* ctx, uint64_t n, const uint32_t* pose_idx, const float* pts_xy, const float* ln_xy, const float* lo,
                                    const uint8_t* valid, float std_dev, float corr) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (n && (!pose_idx || !pts_xy || !ln_xy || !lo || !valid)) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_blocks: null argument");
   for (uint64_t b = 0; b < n; ++b) if (pose_idx[b] >= ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_set_p2l_blocks: pose out of range");
   HITL_CUDA(ctx->d_p2l_pose.ensure(n)); HITL_CUDA(ctx->d_p2l_pts.ensure(n)); HITL_CUDA(ctx->d_p2l_n.ensure(n)); HITL_CUDA(ctx->d_p2l_o.ensure(n));
@@ -516,6 +522,7 @@ static int launch_all(hitl_ctx* ctx, double* d_r, double* d_J, const NeqOut& neq
 
 extern "C" int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision, double* r_out, double* J_out, float* ms_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!pose_array) return fail(ctx, HITL_ERR_ARG, "hitl_eval: null poses");
   if (ctx->nb_stf && ctx->stf_from_search && !ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_eval: search result was invalidated");
   hitl_eval_layout L; hitl_eval_layout_get(ctx, &L);
@@ -556,6 +563,7 @@ int normal_eq_launch(hitl_ctx* ctx, const double* pose_array) {
 
 extern "C" int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* H_off, double* cost, float* ms_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!pose_array) return fail(ctx, HITL_ERR_ARG, "hitl_normal_eq: null poses");
   const size_t n = ctx->n_poses, nbin = ctx->nb_odo + ctx->nb_stf;
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));

@@ -200,6 +200,13 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
 // Event pair around one named kernel launch (hitl_last_kernel_ms)
 #define HITL_KERNEL_BEGIN(which) do { if (ctx->kev[which][0]) cudaEventRecord(ctx->kev[which][0], ctx->stream); } while (0)
 #define HITL_KERNEL_END(which) do { if (ctx->kev[which][1]) { cudaEventRecord(ctx->kev[which][1], ctx->stream); ctx->kev_set[which] = true; } } while (0)
+// Every ABI entry makes its context's device current first: several contexts (one per GPU) may live in one process, driven by
+// different host threads, and a kernel launch goes to whatever device the calling thread last selected.
+#define HITL_DEVICE(ctx)                                                       \
+  do {                                                                         \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                            \
+    if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, "cudaSetDevice"); \
+  } while (0)
 #define HITL_LAUNCH_CHECK(name)                                      \
   do {                                                               \
     ctx->launches++;                                                 \

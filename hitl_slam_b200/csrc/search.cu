@@ -1311,6 +1311,7 @@ static uint32_t stack_levels(uint32_t max_scan) {
 extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const float* q_xy, float threshold, int mode,
                              float* dist_out, int32_t* index_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_kd_query: trees not built");
   if (scan >= ctx->n_poses || mode < 0 || mode > 2 || (nq && (!q_xy || !index_out))) return fail(ctx, HITL_ERR_ARG, "hitl_kd_query: bad argument");
   if (nq == 0) return HITL_OK;
@@ -1332,6 +1333,7 @@ extern "C" int hitl_kd_query(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const fl
 extern "C" int hitl_kd_neighbors(hitl_ctx* ctx, uint32_t scan, uint32_t nq, const float* q_xy, float threshold, uint32_t cap, int32_t* index_out,
                                  uint32_t* count_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_kd_neighbors: trees not built");
   if (scan >= ctx->n_poses || (nq && (!q_xy || !count_out || (cap && !index_out)))) return fail(ctx, HITL_ERR_ARG, "hitl_kd_neighbors: bad argument");
   if (nq == 0) return HITL_OK;
@@ -1464,6 +1466,7 @@ int launch_scan_aabb(hitl_ctx* ctx) {
 extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t min_pose, uint32_t max_pose, uint32_t src_lo,
                              uint32_t src_hi, const hitl_stf_opts* o, hitl_stf_info* info) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!pose_array || !o) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: null argument");
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_find_stf: scans/trees not set");
   if (o->num_skip_readings == 0) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: num_skip_readings must be >= 1");
@@ -1634,6 +1637,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
 
 extern "C" int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_t target_parts) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_debug_set_tiling: scans not set");
   ctx->adaptive_tiling = adaptive != 0;
   ctx->target_splitting = adaptive == 1;
@@ -1667,6 +1671,7 @@ extern "C" int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int sme
 
 extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   // bit 0: fine level, bit 1 set: direction prefilter OFF (on = 1 keeps both culls, on = 0 drops the fine level only, on = 2 / 3 drop the prefilter)
   const int fine = on & 1, dir = (on & 2) ? 0 : 1;
   ctx->mip_occupancy = (on & 4) ? 0 : 1;                       // bit 2 set: tile-box cull OFF (no rebuild needed: the kernel just ignores the level)
@@ -1676,6 +1681,7 @@ extern "C" int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on) {
 
 extern "C" int hitl_get_stf(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint32_t* k, uint32_t* idx) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf: no search result");
   const uint64_t np = ctx->n_pairs, nm = ctx->n_matches;
   if (pair_off && np == 0) pair_off[0] = 0;
@@ -1705,6 +1711,7 @@ __global__ void pack_u16_kernel(const uint32_t* __restrict__ a, const uint32_t* 
 }  // namespace hitl
 extern "C" int hitl_get_stf16(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j, uint64_t* pair_off, uint16_t* k, uint16_t* idx) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf16: no search result");
   const uint64_t np = ctx->n_pairs, nm = ctx->n_matches;
   if (pair_off && np == 0) pair_off[0] = 0;
@@ -1727,6 +1734,7 @@ extern "C" int hitl_get_stf16(hitl_ctx* ctx, uint32_t* pair_i, uint32_t* pair_j,
 
 extern "C" int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_stf || !ctx->d_pose_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_get_stf_work: no search result");
   if (!work_per_pose && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_get_stf_work: null output");
   if (ctx->n_poses) HITL_CUDA(cudaMemcpyAsync(work_per_pose, ctx->d_pose_work.p, 8 * (size_t)ctx->n_poses, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1736,6 +1744,7 @@ extern "C" int hitl_get_stf_work(hitl_ctx* ctx, uint64_t* work_per_pose) {
 
 extern "C" int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_out, uint32_t* n_tiles_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!ctx->have_stf || !ctx->d_tile_work.p) return fail(ctx, HITL_ERR_STATE, "hitl_debug_tile_work: no search result");
   if (n_tiles_out) *n_tiles_out = ctx->n_tiles;
   const uint32_t n = std::min(cap, ctx->n_tiles);
@@ -1747,6 +1756,7 @@ extern "C" int hitl_debug_tile_work(hitl_ctx* ctx, uint32_t cap, uint32_t* work_
 // Tile descriptors of the current tiling (host tables) and the "open points" count the last search measured per tile.
 extern "C" int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan, uint32_t* k0_len, uint32_t* jlo, uint32_t* jhi, uint32_t* open) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   const uint32_t n = std::min<uint32_t>(cap, (uint32_t)ctx->h_tile_scan.size());
   for (uint32_t t = 0; t < n; ++t) {
     if (scan) scan[t] = ctx->h_tile_scan[t];
@@ -1764,6 +1774,7 @@ extern "C" int hitl_debug_tile_desc(hitl_ctx* ctx, uint32_t cap, uint32_t* scan,
 extern "C" int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min_pose, int32_t max_pose, const hitl_stf_opts* o,
                             uint64_t* n_out) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (!pose_array || !o || min_pose < 0) return fail(ctx, HITL_ERR_ARG, "hitl_find_vo: bad argument");
   if (!ctx->have_trees) return fail(ctx, HITL_ERR_STATE, "hitl_find_vo: scans/trees not set");
   ctx->n_vo = 0;
@@ -1801,6 +1812,7 @@ extern "C" int hitl_find_vo(hitl_ctx* ctx, const double* pose_array, int32_t min
 
 extern "C" int hitl_get_vo(hitl_ctx* ctx, uint32_t* source_pose, uint32_t* source_point, uint32_t* target_point) {
   if (!ctx) return HITL_ERR_ARG;
+  HITL_DEVICE(ctx);
   if (ctx->n_vo == 0) return HITL_OK;
   if (source_pose) HITL_CUDA(cudaMemcpy(source_pose, ctx->d_vo_sp.p, 4 * ctx->n_vo, cudaMemcpyDeviceToHost));
   if (source_point) HITL_CUDA(cudaMemcpy(source_point, ctx->d_vo_sk.p, 4 * ctx->n_vo, cudaMemcpyDeviceToHost));

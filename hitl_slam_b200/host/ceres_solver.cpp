@@ -285,13 +285,15 @@ bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector
   if (cost) *cost = half_sq_norm(L.r);
   if (residuals) *residuals = L.r;
   if (!want_jac) return true;
-  // column layout: requested blocks (default: all, in insertion order) that are not constant
+  // column layout: requested blocks (default: all, in insertion order).  Constant blocks keep their columns, as in Ceres
+  // (ProblemEvaluateTest.ConstantParameterBlock): their gradient entries and Jacobian columns stay zero, so a consumer that indexes
+  // by 3 * pose sees the same offsets whether or not pose 0 is held constant.
   std::vector<int> order;
   if (options.parameter_blocks.empty()) { for (int i = 0; i < (int)blocks_.size(); ++i) order.push_back(i); }
   else for (double* v : options.parameter_blocks) { auto it = index_.find(v); if (it == index_.end()) return false; order.push_back(it->second); }
   std::vector<int> col(blocks_.size(), -1);
   int n = 0;
-  for (int b : order) if (!blocks_[b].constant) { col[b] = n; n += blocks_[b].size; }
+  for (int b : order) { col[b] = n; n += blocks_[b].size; }
   if (gradient) gradient->assign(n, 0.0);
   struct Entry { int c; double v; };
   std::vector<std::vector<Entry>> rows(jacobian ? num_residuals_ : 0);
@@ -301,7 +303,7 @@ bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector
     for (size_t s = 0; s < rb.blocks.size(); ++s) {
       const size_t jo = L.jac_off[L.slot0[b] + s];
       const int pb = rb.blocks[s];
-      if (jo == (size_t)-1 || col[pb] < 0) continue;
+      if (jo == (size_t)-1 || col[pb] < 0 || blocks_[pb].constant) continue;
       const int sz = blocks_[pb].size;
       for (int q = 0; q < nr; ++q)
         for (int c = 0; c < sz; ++c) {

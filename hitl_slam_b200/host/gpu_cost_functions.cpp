@@ -2,6 +2,7 @@
 #include "gpu_cost_functions.h"
 
 #include <string.h>
+#include <thread>
 
 namespace hitl {
 
@@ -25,6 +26,19 @@ bool GpuBlockEvaluator::resolve_layout() {
   const uint64_t counts[kNumKinds] = {layout_.n_odometry, layout_.n_human, layout_.n_stf, layout_.n_p2l_glob, layout_.n_p2l};
   uint64_t ro = 0, jo = 0;
   for (int k = 0; k < kNumKinds; ++k) { r_off_[k] = ro; j_off_[k] = jo; ro += counts[k] * kResPerBlock[k]; jo += counts[k] * kJacPerBlock[k]; }
+  // extra contexts carry STF blocks only; their slices follow the first context's, shard after shard
+  shard_r_off_.assign(shards_.size(), 0); shard_j_off_.assign(shards_.size(), 0);
+  uint64_t r_end = layout_.n_residuals, j_end = layout_.n_jacobian;
+  if (!shards_.empty() && (layout_.n_p2l_glob || layout_.n_p2l)) { ok_ = false; error_ = "sharded evaluation does not support point-to-line blocks"; return false; }
+  for (size_t q = 0; q < shards_.size(); ++q) {
+    hitl_eval_layout lq;
+    if (hitl_eval_layout_get(shards_[q], &lq) != HITL_OK) { ok_ = false; error_ = "hitl_eval_layout_get failed on a shard"; return false; }
+    if (lq.n_odometry || lq.n_human || lq.n_p2l_glob || lq.n_p2l) { ok_ = false; error_ = "a shard context holds blocks other than STF blocks"; return false; }
+    shard_r_off_[q] = r_end; shard_j_off_[q] = j_end;
+    r_end += lq.n_residuals; j_end += lq.n_jacobian;
+    layout_.n_stf += lq.n_stf;
+  }
+  layout_.n_residuals = r_end; layout_.n_jacobian = j_end;
   auto grow = [](double** p, size_t* cap, size_t need) {
     if (need <= *cap) return true;
     if (*p) hitl_host_free(*p);
@@ -40,9 +54,17 @@ bool GpuBlockEvaluator::resolve_layout() {
 
 bool GpuBlockEvaluator::run_batch(bool want_jac) {
   if (dirty_ && !resolve_layout()) { valid_ = false; return false; }
+  // one hitl_eval per context, the extra contexts on their own host threads (every ABI call selects its context's device)
+  std::vector<int> rcs(shards_.size(), HITL_OK);
+  std::vector<std::thread> workers;
+  for (size_t q = 0; q < shards_.size(); ++q)
+    workers.emplace_back([&, q]() { float ms = 0.f; rcs[q] = hitl_eval(shards_[q], pose_array_, precision_, r_ + shard_r_off_[q], want_jac ? J_ + shard_j_off_[q] : nullptr, &ms); });
   const int rc = hitl_eval(ctx_, pose_array_, precision_, r_, want_jac ? J_ : nullptr, &last_ms_);
+  for (std::thread& w : workers) w.join();
   ++batches_;
   if (rc != HITL_OK) { ok_ = false; valid_ = false; error_ = hitl_last_error(ctx_); return false; }
+  for (size_t q = 0; q < shards_.size(); ++q)
+    if (rcs[q] != HITL_OK) { ok_ = false; valid_ = false; error_ = std::string("shard: ") + hitl_last_error(shards_[q]); return false; }
   snapshot_.assign(pose_array_, pose_array_ + 3 * n_poses_);
   valid_ = true; have_jac_ = want_jac; ok_ = true;
   return true;

@@ -39,6 +39,11 @@ class GpuBlockEvaluator : public ceres::EvaluationCallback {
   // Call after every hitl_set_*_blocks registration: the block layout is re-read from the context before the next batch
   // (lazily — a problem is built from several registrations and evaluated once).
   bool Refresh() { dirty_ = true; valid_ = false; return true; }
+  // Multi-GPU: contexts on other devices that hold the STF blocks of the other source shards (and nothing else).  Block order of the
+  // staging buffers stays [odometry | human | stf of ctx | stf of shard 1 | stf of shard 2 ...] — the reference's AddResidualBlock order
+  // when the shards are ascending source ranges.  One batch = one hitl_eval per context, each on its own host thread, each
+  // reading its slice back into the shared page-locked staging.
+  void SetShardContexts(const std::vector<hitl_ctx*>& extra) { shards_ = extra; dirty_ = true; valid_ = false; }
   void Rebind(const double* pose_array, size_t n_poses) { pose_array_ = pose_array; n_poses_ = n_poses; valid_ = false; dirty_ = true; }
   void Rebind(const double* pose_array, size_t n_poses, int precision) { Rebind(pose_array, n_poses); precision_ = precision; ok_ = true; error_.clear(); }
   void PrepareForEvaluation(bool evaluate_jacobians, bool new_evaluation_point) override;
@@ -59,6 +64,8 @@ class GpuBlockEvaluator : public ceres::EvaluationCallback {
   const double* pose_array_;
   size_t n_poses_;
   int precision_;
+  std::vector<hitl_ctx*> shards_;                 // extra contexts (ranks 1 ..)
+  std::vector<uint64_t> shard_r_off_, shard_j_off_;   // where each extra context's residuals / Jacobians start in the staging buffers
   hitl_eval_layout layout_;
   uint64_t r_off_[kNumKinds], j_off_[kNumKinds];
   // staging of one batch: page-locked (hitl_host_alloc), so hitl_eval's read-back runs at PCIe rate without a driver staging copy;

@@ -355,6 +355,24 @@ int hitl_host_session_solve(void* sp, int mode, double summary[6]) {
 }
 int hitl_host_session_copy_params(void* sp) { static_cast<Session*>(sp)->jopt.CopyParams(); return 0; }
 
+// Multi-GPU in one process: extra contexts (other devices) that share the search and the STF blocks with the session's context
+// (JointOpt::UseShardContexts).  n_extra = 0 goes back to one context.  The map must be set again afterwards.
+int hitl_host_session_use_shard_contexts(void* sp, uint32_t n_extra, void** extra_ctx) {
+  Session* s = static_cast<Session*>(sp);
+  HOST_TRY(s, {
+    std::vector<hitl_ctx*> v;
+    for (uint32_t q = 0; q < n_extra; ++q) v.push_back(static_cast<hitl_ctx*>(extra_ctx[q]));
+    s->jopt.UseShardContexts(v);
+  })
+}
+// Source-pose range and STF block count of every context in the last FindSTFCorrespondences: out = {lo, hi, blocks} per context.
+int hitl_host_session_shard_info(void* sp, uint32_t cap, uint64_t* out3, uint32_t* n_contexts) {
+  Session* s = static_cast<Session*>(sp);
+  const JointOpt& J = s->jopt;
+  if (n_contexts) *n_contexts = (uint32_t)J.NumContexts();
+  for (size_t r = 0; r < J.shard_ranges_.size() && r < cap; ++r) { out3[3 * r] = J.shard_ranges_[r].first; out3[3 * r + 1] = J.shard_ranges_[r].second; out3[3 * r + 2] = r < J.shard_blocks_.size() ? J.shard_blocks_[r] : 0; }
+  return 0;
+}
 // FindSTFCorrespondences through the mirror; counts = {n_pairs, n_matches, n_queries}.
 int hitl_host_session_find_stf(void* sp, uint64_t min_pose, uint64_t max_pose, uint64_t counts[3]) {
   Session* s = static_cast<Session*>(sp);
@@ -457,6 +475,25 @@ int hitl_host_solver_selftest(double x[4], int max_iterations, int hold_x1, int 
   ceres::Solve(o, &problem, &s);
   out[0] = s.initial_cost; out[1] = s.final_cost; out[2] = s.num_successful_steps + s.num_unsuccessful_steps; out[3] = (double)s.termination_type;
   return 0;
+}
+
+// Problem::Evaluate on Powell's function with x1 optionally constant: gradient (as many entries as the problem has parameters — constant
+// blocks keep zero entries, as in Ceres) and the CRS Jacobian's dimensions {rows, cols, non-zeros}.  Returns the gradient length.
+int hitl_host_evaluate_selftest(const double x_in[4], int hold_x1, double grad_out[4], uint64_t dims[3], double* cost) {
+  double x[4] = {x_in[0], x_in[1], x_in[2], x_in[3]};
+  ceres::Problem problem;
+  problem.AddResidualBlock(new ceres::AutoDiffCostFunction<PowellF1, 1, 1, 1>(new PowellF1), NULL, &x[0], &x[1]);
+  problem.AddResidualBlock(new ceres::AutoDiffCostFunction<PowellF2, 1, 1, 1>(new PowellF2), NULL, &x[2], &x[3]);
+  problem.AddResidualBlock(new ceres::AutoDiffCostFunction<PowellF3, 1, 1, 1>(new PowellF3), NULL, &x[1], &x[2]);
+  problem.AddResidualBlock(new ceres::AutoDiffCostFunction<PowellF4, 1, 1, 1>(new PowellF4), NULL, &x[0], &x[3]);
+  if (hold_x1) problem.SetParameterBlockConstant(&x[0]);
+  std::vector<double> residuals, gradient;
+  ceres::CRSMatrix jac;
+  ceres::Problem::EvaluateOptions eo;
+  if (!problem.Evaluate(eo, cost, &residuals, &gradient, &jac)) return -1;
+  for (size_t i = 0; i < gradient.size() && i < 4; ++i) grad_out[i] = gradient[i];
+  dims[0] = jac.num_rows; dims[1] = jac.num_cols; dims[2] = jac.values.size();
+  return (int)gradient.size();
 }
 
 // A pose-chain problem of the human-constraint shape — n blocks of 2 parameters, relative factors between neighbours,

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <stdexcept>
+#include <thread>
 
 namespace hitl {
 
@@ -81,6 +82,30 @@ void JointOpt::check(int rc, const char* where) {
   throw std::runtime_error(last_error_);
 }
 
+void JointOpt::UseShardContexts(const std::vector<hitl_ctx*>& extra) {
+  for (hitl_ctx* c : extra) if (!c || c == ctx_) throw std::invalid_argument("UseShardContexts: null or duplicate context");
+  shard_ctx_ = extra;
+  kdtrees_built_ = false;
+  if (evaluator_) evaluator_->SetShardContexts(shard_ctx_);
+}
+
+// Runs fn(rank, ctx) for every context, the extra ones on their own host threads; rethrows the first failure.
+template <typename F>
+static void for_each_context(hitl_ctx* first, const std::vector<hitl_ctx*>& extra, F fn) {
+  std::vector<std::string> errors(extra.size());
+  std::vector<std::thread> workers;
+  for (size_t q = 0; q < extra.size(); ++q)
+    workers.emplace_back([&, q]() { try { fn(q + 1, extra[q]); } catch (const std::exception& e) { errors[q] = e.what(); if (errors[q].empty()) errors[q] = "error"; } });
+  std::string mine;
+  try { fn(0, first); } catch (const std::exception& e) { mine = e.what(); if (mine.empty()) mine = "error"; }
+  for (std::thread& w : workers) w.join();
+  if (!mine.empty()) throw std::runtime_error(mine);
+  for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error("shard context: " + e);
+}
+static void check_ctx(hitl_ctx* c, int rc, const char* where) {
+  if (rc != HITL_OK) throw std::runtime_error(std::string(where) + ": " + hitl_last_error(c));
+}
+
 void JointOpt::ClearPoses() {
   poses_.clear(); robot_frame_point_clouds_.clear(); robot_frame_normal_clouds_.clear(); covariances_.clear();
   pose_array_.clear(); kdtrees_built_ = false;
@@ -140,8 +165,13 @@ void JointOpt::BuildKDTrees() {
       pts[2 * o] = robot_frame_point_clouds_[i][k].x; pts[2 * o + 1] = robot_frame_point_clouds_[i][k].y;
       nrm[2 * o] = robot_frame_normal_clouds_[i][k].x; nrm[2 * o + 1] = robot_frame_normal_clouds_[i][k].y;
     }
-  check(hitl_set_scans(ctx_, (uint32_t)n, off.data(), pts.data(), nrm.data()), "hitl_set_scans");
-  check(hitl_build_kdtrees(ctx_), "hitl_build_kdtrees");
+  // scans + trees are replicated on every context (the search shards by SOURCE pose; every shard needs all targets)
+  try {
+    for_each_context(ctx_, shard_ctx_, [&](size_t, hitl_ctx* c) {
+      check_ctx(c, hitl_set_scans(c, (uint32_t)n, off.data(), pts.data(), nrm.data()), "hitl_set_scans");
+      check_ctx(c, hitl_build_kdtrees(c), "hitl_build_kdtrees");
+    });
+  } catch (const std::exception& e) { last_error_ = e.what(); throw; }
   kdtrees_built_ = true;
 }
 
@@ -163,13 +193,59 @@ void JointOpt::FindSTFCorrespondences(size_t min_poses, size_t max_poses) {
   S = StfCorrespondenceSet();
   const hitl_stf_opts o = search_options();
   const uint32_t lo = (uint32_t)std::min<size_t>(min_poses, 0xFFFFFFFFu), hi = (uint32_t)std::min<size_t>(max_poses, 0xFFFFFFFEu);
-  check(hitl_find_stf(ctx_, pose_array_.data(), lo, hi, 0, 0xFFFFFFFFu, &o, &last_search_info_), "hitl_find_stf");
-  const uint64_t np = last_search_info_.n_pairs, nm = last_search_info_.n_matches;
-  S.pair_i.resize(np); S.pair_j.resize(np); S.pair_off.assign(np + 1, 0); S.k.resize(nm); S.idx.resize(nm);
-  S.n_queries = last_search_info_.n_queries;
   uint32_t dummy = 0;
-  check(hitl_get_stf(ctx_, np ? S.pair_i.data() : &dummy, np ? S.pair_j.data() : &dummy, S.pair_off.data(), nm ? S.k.data() : &dummy, nm ? S.idx.data() : &dummy),
-        "hitl_get_stf");
+  if (shard_ctx_.empty()) {
+    check(hitl_find_stf(ctx_, pose_array_.data(), lo, hi, 0, 0xFFFFFFFFu, &o, &last_search_info_), "hitl_find_stf");
+    const uint64_t np = last_search_info_.n_pairs, nm = last_search_info_.n_matches;
+    S.pair_i.resize(np); S.pair_j.resize(np); S.pair_off.assign(np + 1, 0); S.k.resize(nm); S.idx.resize(nm);
+    S.n_queries = last_search_info_.n_queries;
+    check(hitl_get_stf(ctx_, np ? S.pair_i.data() : &dummy, np ? S.pair_j.data() : &dummy, S.pair_off.data(), nm ? S.k.data() : &dummy, nm ? S.idx.data() : &dummy),
+          "hitl_get_stf");
+    shard_ranges_.assign(1, std::make_pair(0u, (uint32_t)poses_.size())); shard_blocks_.assign(1, np);
+    return;
+  }
+  // One contiguous source-pose range per context, balanced by point count; every range is searched against ALL targets on its own GPU
+  // and the per-range lists concatenate to the reference's (i, j, k) order.
+  const size_t R = 1 + shard_ctx_.size(), n = poses_.size();
+  std::vector<uint64_t> cum(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) cum[i + 1] = cum[i] + robot_frame_point_clouds_[i].size();
+  shard_ranges_.assign(R, std::make_pair(0u, 0u));
+  uint32_t prev = 0;
+  for (size_t r = 0; r < R; ++r) {
+    uint32_t end = (uint32_t)n;
+    if (r + 1 < R) { const uint64_t target = cum[n] * (r + 1) / R; end = (uint32_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()); end = std::max(prev, std::min<uint32_t>(end, (uint32_t)n)); }
+    shard_ranges_[r] = std::make_pair(prev, end);
+    prev = end;
+  }
+  std::vector<StfCorrespondenceSet> part(R);
+  std::vector<hitl_stf_info> infos(R);
+  try {
+    for_each_context(ctx_, shard_ctx_, [&](size_t r, hitl_ctx* c) {
+      memset(&infos[r], 0, sizeof(hitl_stf_info));
+      check_ctx(c, hitl_find_stf(c, pose_array_.data(), lo, hi, shard_ranges_[r].first, shard_ranges_[r].second, &o, &infos[r]), "hitl_find_stf");
+      StfCorrespondenceSet& P = part[r];
+      const uint64_t np = infos[r].n_pairs, nm = infos[r].n_matches;
+      uint32_t dmy = 0;
+      P.pair_i.resize(np); P.pair_j.resize(np); P.pair_off.assign(np + 1, 0); P.k.resize(nm); P.idx.resize(nm);
+      check_ctx(c, hitl_get_stf(c, np ? P.pair_i.data() : &dmy, np ? P.pair_j.data() : &dmy, P.pair_off.data(), nm ? P.k.data() : &dmy, nm ? P.idx.data() : &dmy), "hitl_get_stf");
+    });
+  } catch (const std::exception& e) { last_error_ = e.what(); throw; }
+  memset(&last_search_info_, 0, sizeof(last_search_info_));
+  shard_blocks_.assign(R, 0);
+  S.pair_off.assign(1, 0);
+  for (size_t r = 0; r < R; ++r) {
+    const StfCorrespondenceSet& P = part[r];
+    const uint64_t base = S.k.size();
+    S.pair_i.insert(S.pair_i.end(), P.pair_i.begin(), P.pair_i.end()); S.pair_j.insert(S.pair_j.end(), P.pair_j.begin(), P.pair_j.end());
+    for (size_t b = 1; b < P.pair_off.size(); ++b) S.pair_off.push_back(base + P.pair_off[b]);
+    S.k.insert(S.k.end(), P.k.begin(), P.k.end()); S.idx.insert(S.idx.end(), P.idx.begin(), P.idx.end());
+    shard_blocks_[r] = infos[r].n_pairs;
+    last_search_info_.n_pairs += infos[r].n_pairs; last_search_info_.n_matches += infos[r].n_matches; last_search_info_.n_raw_matches += infos[r].n_raw_matches;
+    last_search_info_.n_queries += infos[r].n_queries; last_search_info_.n_traversals += infos[r].n_traversals; last_search_info_.n_tile_pairs += infos[r].n_tile_pairs;
+    last_search_info_.ms_search = std::max(last_search_info_.ms_search, infos[r].ms_search); last_search_info_.ms_total = std::max(last_search_info_.ms_total, infos[r].ms_total);
+  }
+  S.n_queries = last_search_info_.n_queries;
+  (void)dummy;
 }
 
 PointToPointGlobCorrespondence JointOpt::GlobCorrespondence(size_t b) const {
@@ -208,9 +284,16 @@ ceres::Problem::Options JointOpt::BeginProblem() {
   check(hitl_set_stf_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.05f, 0.025f), "hitl_set_stf_blocks(0)");
   check(hitl_set_p2l_glob_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_glob_blocks(0)");
   check(hitl_set_p2l_blocks(ctx_, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_blocks(0)");
+  for (hitl_ctx* c : shard_ctx_) {                  // the extra contexts only ever hold STF blocks
+    check_ctx(c, hitl_set_odometry_blocks(c, 0, z9), "hitl_set_odometry_blocks(0)"); check_ctx(c, hitl_set_human_blocks(c, 0, zi, zd), "hitl_set_human_blocks(0)");
+    check_ctx(c, hitl_set_stf_blocks(c, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.05f, 0.025f), "hitl_set_stf_blocks(0)");
+    check_ctx(c, hitl_set_p2l_glob_blocks(c, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_glob_blocks(0)");
+    check_ctx(c, hitl_set_p2l_blocks(c, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f), "hitl_set_p2l_blocks(0)");
+  }
   // one evaluator per JointOpt, re-bound per problem: its page-locked staging buffers survive from one problem to the next
   if (!evaluator_) evaluator_.reset(new GpuBlockEvaluator(ctx_, pose_array_.data(), poses_.size(), precision_));
   else evaluator_->Rebind(pose_array_.data(), poses_.size(), precision_);
+  evaluator_->SetShardContexts(shard_ctx_);
   ceres::Problem::Options po;
   po.evaluation_callback = evaluator_.get();
   return po;
@@ -220,6 +303,8 @@ void JointOpt::AddSTFConstraints(ceres::Problem* problem) {
   const StfCorrespondenceSet& S = point_point_glob_correspondences_;
   // The blocks are the kept pairs of the search that is still resident on the device; nothing is re-uploaded.
   check(hitl_set_stf_blocks_from_search(ctx_, localization_options_.kLaserStdDev, localization_options_.kPointPointCorrelationFactor), "hitl_set_stf_blocks_from_search");
+  for (hitl_ctx* c : shard_ctx_)                    // every context registers the pairs ITS search found; block b of the concatenated list lives on the context that found it
+    check_ctx(c, hitl_set_stf_blocks_from_search(c, localization_options_.kLaserStdDev, localization_options_.kPointPointCorrelationFactor), "hitl_set_stf_blocks_from_search");
   evaluator_->Refresh();
   for (size_t b = 0; b < S.size(); ++b)
     problem->AddResidualBlock(new GpuPointToPointGlobConstraint(evaluator_.get(), b, (int)S.pair_i[b], (int)S.pair_j[b]), NULL, &pose_array_[3 * (size_t)S.pair_i[b]],

@@ -19,6 +19,7 @@
 #include <array>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/hitl_gpu.h"
 #include "gpu_cost_functions.h"
@@ -35,6 +36,15 @@ class JointOpt {
 
   void Run();
   void ClearPoses();
+  // Multi-GPU, one process: contexts on OTHER devices (created with hitl_create(&c, device)) that share the search and the STF blocks
+  // with the constructor's context.  BuildKDTrees replicates scans + trees on every context; FindSTFCorrespondences gives each context a
+  // contiguous source-pose range balanced by point count (OMP-over-i of the reference, :575, becomes one GPU per range) and
+  // concatenates the per-range lists, which is the reference's block order; every evaluation point costs one hitl_eval per context,
+  // concurrently.  Results are identical to the single-context stage (tests/test_gpu_multi.py).  Call before BuildKDTrees.
+  void UseShardContexts(const std::vector<hitl_ctx*>& extra);
+  size_t NumContexts() const { return 1 + shard_ctx_.size(); }
+  std::vector<std::pair<uint32_t, uint32_t>> shard_ranges_;   // source-pose range [lo, hi) of every context in the last search
+  std::vector<uint64_t> shard_blocks_;                         // kept pairs (= STF blocks) each context found
   std::vector<float> GetCeresCost() const { return ceres_cost_; }
 
   // ---- public state of the reference class (JointOptimization.h:64-89) ----
@@ -87,6 +97,7 @@ class JointOpt {
   void check(int rc, const char* where);
   hitl_stf_opts search_options() const;
   hitl_ctx* ctx_;
+  std::vector<hitl_ctx*> shard_ctx_;                           // extra contexts (ranks 1 ..)
   std::unique_ptr<GpuBlockEvaluator> evaluator_;
   std::vector<float> ceres_cost_;
 };

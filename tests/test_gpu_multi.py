@@ -132,3 +132,49 @@ def test_two_rank_exchange(gpu, host, maps):
     assert outs[0]["n_local"] + outs[1]["n_local"] == len(found["pair_i"]) and min(outs[0]["n_local"], outs[1]["n_local"]) > 0
     assert np.array_equal(outs[0]["pair_i"], found["pair_i"]) and np.array_equal(outs[0]["pair_j"], found["pair_j"])
     assert np.array_equal(outs[0]["r"], ev["r_stf"]) and np.array_equal(outs[0]["J"].reshape(ev["J_stf"].shape), ev["J_stf"])
+
+
+def test_sharded_jointopt_in_one_process(gpu, host, maps):
+    """The C++ drop-in on two GPUs, one process: hitl::JointOpt with a second context (JointOpt::UseShardContexts).  Scans + trees are
+    replicated, each context searches its own source range, the concatenated list and every GPU-backed cost block (evaluated through
+    CostFunction::Evaluate, blocks of both shards) equal the single-context stage's; the post-HitL solve ends at the same poses."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from hitl_slam_b200 import HitlGpu, HostSession
+    g = maps("small")
+    x = _jitter(g, 11)
+    one = HostSession(gpu, host)
+    one.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    want = one.find_stf()
+    nb = want["n_pairs"]
+    n_odo = len(g["poses"]) - 1
+    picks = [n_odo + b for b in (0, 1, nb // 2 - 1, nb // 2, nb // 2 + 1, nb - 2, nb - 1)]
+    want_blocks = [one.evaluate_block(b, with_stf=True, pose_array=x) for b in picks]
+    one.solver_options(1, max_iterations=8)
+    one.set_poses(g["poses"])
+    one.find_stf()
+    s1 = one.solve(1)
+    p1 = one.poses()[1].copy()
+    one.close()
+    second = HitlGpu(1)
+    two = HostSession(gpu, host)
+    two.use_shard_contexts([second])
+    two.set_map(g["poses"], g["offsets"], g["pts"], g["nrm"])
+    got = two.find_stf()
+    info = two.shard_info()
+    assert len(info) == 2 and info[0][0] == 0 and info[0][1] == info[1][0] and info[1][1] == len(g["poses"]) and info[0][2] + info[1][2] == nb and min(info[0][2], info[1][2]) > 0
+    for k in ("pair_i", "pair_j", "pair_off", "k", "idx"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["n_queries"] == want["n_queries"]
+    for b, (r0, j0, j1, tot) in zip(picks, want_blocks):
+        r, a, c, tot2 = two.evaluate_block(b, with_stf=True, pose_array=x)
+        assert tot2 == tot and np.array_equal(r, r0) and np.array_equal(a, j0) and np.array_equal(c, j1), b
+    two.solver_options(1, max_iterations=8)
+    two.set_poses(g["poses"])
+    two.find_stf()
+    s2 = two.solve(1)
+    assert s2["termination"] == s1["termination"] and abs(s2["final_cost"] - s1["final_cost"]) <= 1e-9 * max(s1["final_cost"], 1e-30)
+    assert np.abs(two.poses()[1] - p1).max() <= 1e-9
+    two.close()
+    second.close()

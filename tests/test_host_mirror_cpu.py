@@ -39,6 +39,21 @@ def test_solver_powell_dense_cg_and_constant_block(host):
     assert np.abs(x[1:] - ref.x).max() < 1e-6
 
 
+def test_problem_evaluate_keeps_constant_blocks_as_zero_columns(host):
+    """Ceres' Problem::Evaluate (ProblemEvaluateTest.ConstantParameterBlock): a constant block keeps its gradient entries and Jacobian
+    columns, filled with zeros — the reference's consumers index gradients_ / ceres_jacobian_ by 3 * pose with pose 0 held constant."""
+    x0 = np.array([3.0, -1.0, 0.5, 1.0])
+    r = np.array([x0[0] + 10 * x0[1], np.sqrt(5) * (x0[2] - x0[3]), (x0[1] - 2 * x0[2]) ** 2, np.sqrt(10) * (x0[0] - x0[3]) ** 2])
+    J = np.array([[1, 10, 0, 0], [0, 0, np.sqrt(5), -np.sqrt(5)], [0, 2 * (x0[1] - 2 * x0[2]), -4 * (x0[1] - 2 * x0[2]), 0],
+                  [2 * np.sqrt(10) * (x0[0] - x0[3]), 0, 0, -2 * np.sqrt(10) * (x0[0] - x0[3])]])
+    g, dims, cost = host.evaluate_selftest(x0)
+    assert len(g) == 4 and dims == (4, 4, 8) and cost == pytest.approx(0.5 * (r ** 2).sum()) and np.allclose(g, J.T @ r, rtol=1e-12)
+    g, dims, cost = host.evaluate_selftest(x0, hold_x1=True)
+    want = J.T @ r
+    want[0] = 0.0
+    assert len(g) == 4 and dims[:2] == (4, 4) and dims[2] == 6 and g[0] == 0.0 and np.allclose(g, want, rtol=1e-12)
+
+
 def test_solver_chain_direct_matches_dense_and_cg(host):
     """Beyond the dense limit the stand-in LM eliminates block-tridiagonal systems (the odometry chain + unary human factors)
     directly; same minimiser as the dense path and as PCG."""

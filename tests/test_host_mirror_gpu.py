@@ -219,9 +219,10 @@ def test_post_human_optimization_final_poses(session, oracle, maps):
         assert abs(summ["final_cost"] - want_cost) <= 1e-7 * want_cost
         assert np.abs(got - want).max() <= 1e-7               # optimised poses, FP64 mode (north_star: <= 1e-9 relative on ~10 m coordinates)
     grad, dims = session.gradient()                            # Problem::Evaluate at the solution (JointOptimization.cpp:1252)
-    assert len(grad) == 3 * (n - 1) and dims[0] == 2 * nb and dims[1] == 3 * (n - 1)
+    # constant blocks keep their (zero) columns, as in Ceres: the gradient has 3 entries per pose and pose 0's are zero
+    assert len(grad) == 3 * n and dims[0] == 2 * nb and dims[1] == 3 * n and np.all(grad[:3] == 0.0)
     J = fun(got, True).toarray()
-    assert np.abs(grad - J.T @ fun(got, False)).max() <= 1e-9 * max(1.0, np.abs(grad).max())
+    assert np.abs(grad[3:] - J.T @ fun(got, False)).max() <= 1e-9 * max(1.0, np.abs(grad).max())
 
 
 def test_fp32_mode_reaches_the_same_poses_within_1e5(session, maps):
