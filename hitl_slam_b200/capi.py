@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_refit", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks",
+    "hitl_normal_eq_device", "hitl_set_deterministic", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks",
     "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
     "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
@@ -506,6 +506,10 @@ class HitlGpu:
         self._ck(self.lib.hitl_gather_stf_blocks(self.ctx, root, cap_blocks, counts, pi.ctypes.data, pj.ctypes.data, r.ctypes.data, J.ctypes.data))
         t = int(counts.sum())
         return dict(counts=counts, pair_i=pi[:t], pair_j=pj[:t], r=r[:2 * t].reshape(-1, 2), J=J[:12 * t].reshape(-1, 2, 2, 3))
+
+    def set_deterministic(self, on=True):
+        self.lib.hitl_set_deterministic.argtypes = [C.c_void_p, C.c_int]
+        self._ck(self.lib.hitl_set_deterministic(self.ctx, int(bool(on))))
 
     def normal_eq_device(self):
         p, n = C.c_void_p(), C.c_uint64()

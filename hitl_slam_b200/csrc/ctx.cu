@@ -170,7 +170,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   hitl_comm_destroy(ctx);
-  ctx->d_comm_cnt.release(); ctx->d_g_pi.release(); ctx->d_g_pj.release(); ctx->d_g_r.release(); ctx->d_g_J.release();
+  ctx->d_inc_key.release(); ctx->d_inc_ref.release(); ctx->d_inc_off.release(); ctx->d_cost_partial.release(); ctx->d_comm_cnt.release(); ctx->d_g_pi.release(); ctx->d_g_pj.release(); ctx->d_g_r.release(); ctx->d_g_J.release();
   ctx->d_off.release(); ctx->d_pts.release(); ctx->d_nrm.release(); ctx->d_aabb.release();
   ctx->d_tile_scan.release(); ctx->d_tile_k0.release(); ctx->d_tile_begin.release();
   ctx->d_tile_work.release(); ctx->d_tile_order.release(); ctx->d_tile_iota.release(); ctx->d_tile_keys.release(); ctx->d_sort_tmp.release();
@@ -243,7 +243,7 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   // Residual blocks registered for the previous map carry pose / point indices that were range-checked against IT: they must be
   // registered again (hitl_eval / hitl_normal_eq would otherwise index the new, possibly smaller, map with stale indices).
   ctx->nb_odo = ctx->nb_human = ctx->nb_stf = ctx->nb_p2lg = ctx->nb_p2l = 0; ctx->stf_from_search = false;
-  ctx->n_pairs = ctx->n_matches = 0; ctx->n_vo = 0; ctx->eval_valid = ctx->neq_valid = false;
+  ctx->n_pairs = ctx->n_matches = 0; ctx->n_vo = 0; ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   ctx->n_poses = n_poses;
   ctx->h_off.assign(n_poses + 1, 0);
   for (uint32_t i = 0; i <= n_poses && n_poses; ++i) ctx->h_off[i] = off[i];

@@ -12,6 +12,7 @@
 // to rounding (<= 1e-9 relative in FP64 is the contract; FP32 mode <= 1e-5), ~85 flop per
 // correspondence instead of ~7x that, so the STF kernel stays bound by its 32 B/correspondence
 // gather.  Jacobian layout = Ceres': row-major [residual][param] per parameter block.
+#include <cub/device/device_radix_sort.cuh>
 #include "hitl_internal.h"
 
 namespace hitl {
@@ -363,7 +364,7 @@ extern "C" int hitl_set_stf_blocks_from_search(hitl_ctx* ctx, float std_dev, flo
   if (!ctx) return HITL_ERR_ARG;
   HITL_DEVICE(ctx);
   if (!ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_set_stf_blocks_from_search: no search result");
-  ctx->eval_valid = ctx->neq_valid = false;
+  ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   ctx->stf_from_search = true; ctx->nb_stf = ctx->n_pairs; ctx->stf_std = std_dev; ctx->stf_corr = corr;
   return HITL_OK;
 }
@@ -391,7 +392,7 @@ extern "C" int hitl_set_stf_blocks(hitl_ctx* ctx, uint64_t n_pairs, const uint32
     HITL_CUDA(cudaMemcpyAsync(ctx->d_blk_idx.p, idx, 4 * nm, cudaMemcpyHostToDevice, ctx->stream));
     HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  ctx->eval_valid = ctx->neq_valid = false;
+  ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   ctx->stf_from_search = false; ctx->nb_stf = n_pairs; ctx->stf_std = std_dev; ctx->stf_corr = corr;
   return HITL_OK;
 }
@@ -404,7 +405,7 @@ extern "C" int hitl_set_odometry_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
     for (int q = 4; q < 7; ++q) if (!(consts9[9 * b + q] > 0.0f)) return fail(ctx, HITL_ERR_ARG, "hitl_set_odometry_blocks: std-dev must be > 0");
   HITL_CUDA(ctx->d_odo.ensure(9 * (size_t)n_blocks));
   if (n_blocks) HITL_CUDA(cudaMemcpy(ctx->d_odo.p, consts9, 36 * (size_t)n_blocks, cudaMemcpyHostToDevice));
-  ctx->nb_odo = n_blocks; ctx->eval_valid = ctx->neq_valid = false;
+  ctx->nb_odo = n_blocks; ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   return HITL_OK;
 }
 extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int32_t* type_pose, const double* targets4) {
@@ -421,7 +422,7 @@ extern "C" int hitl_set_human_blocks(hitl_ctx* ctx, uint32_t n_blocks, const int
     HITL_CUDA(cudaMemcpy(ctx->d_hum_i.p, type_pose, 8 * (size_t)n_blocks, cudaMemcpyHostToDevice));
     HITL_CUDA(cudaMemcpy(ctx->d_hum_d.p, targets4, 32 * (size_t)n_blocks, cudaMemcpyHostToDevice));
   }
-  ctx->nb_human = n_blocks; ctx->eval_valid = ctx->neq_valid = false;
+  ctx->nb_human = n_blocks; ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   return HITL_OK;
 }
 extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const uint32_t* blk_pose, const uint64_t* blk_off, const float* pts_xy,
@@ -443,7 +444,7 @@ extern "C" int hitl_set_p2l_glob_blocks(hitl_ctx* ctx, uint32_t n_blocks, const 
       HITL_CUDA(cudaMemcpy(ctx->d_p2lg_o.p, lo, 4 * m, cudaMemcpyHostToDevice)); HITL_CUDA(cudaMemcpy(ctx->d_p2lg_v.p, valid, m, cudaMemcpyHostToDevice));
     }
   }
-  ctx->eval_valid = ctx->neq_valid = false;
+  ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   ctx->nb_p2lg = n_blocks; ctx->p2lg_std = std_dev; ctx->p2lg_corr = corr;
   return HITL_OK;
 }
@@ -460,7 +461,7 @@ extern "C" int hitl_set_p2l_blocks(hitl_ctx* ctx, uint64_t n, const uint32_t* po
     HITL_CUDA(cudaMemcpy(ctx->d_p2l_n.p, ln_xy, 8 * n, cudaMemcpyHostToDevice)); HITL_CUDA(cudaMemcpy(ctx->d_p2l_o.p, lo, 4 * n, cudaMemcpyHostToDevice));
     HITL_CUDA(cudaMemcpy(ctx->d_p2l_v.p, valid, n, cudaMemcpyHostToDevice));
   }
-  ctx->eval_valid = ctx->neq_valid = false;
+  ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   ctx->nb_p2l = n; ctx->p2l_std = std_dev; ctx->p2l_corr = corr;
   return HITL_OK;
 }
@@ -544,6 +545,139 @@ extern "C" int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision,
 }
 
 namespace hitl {
+// ---- deterministic normal equations (hitl_set_deterministic) ------------------------------------------------------------------
+// The default path adds every block's J^T J / J^T r into the per-pose buffers with FP64 atomics: correct to rounding, but the order
+// of the additions — hence the last bits — varies from run to run.  The deterministic path evaluates r and J per block (each block is
+// a fixed-order reduction already), then GATHERS: an incidence list per pose, built once per block registration by a stable radix
+// sort of (pose, block reference) pairs generated in the canonical block order [odometry | human | stf | p2l_glob | p2l], and one
+// warp per pose in which lane e < 9 owns H entry e and lanes 9..11 own g, each walking the pose's list in order.  The cost is a
+// two-level sum of fixed shape.  Same inputs, same bits, on every run and for every launch geometry of the other kernels.
+constexpr uint64_t kRefKindShift = 60, kRefSideBit = 1ull << 59;
+__global__ void incidence_fill_kernel(uint64_t n_odo, uint64_t n_hum, uint64_t n_stf, uint64_t n_p2lg, uint64_t n_p2l, const int32_t* __restrict__ hum_i,
+                                      const uint32_t* __restrict__ stf_i, const uint32_t* __restrict__ stf_j, const uint32_t* __restrict__ p2lg_pose,
+                                      const uint32_t* __restrict__ p2l_pose, uint32_t* __restrict__ keys, uint64_t* __restrict__ refs) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t a = 2 * n_odo, b = a + n_hum, c = b + 2 * n_stf, d = c + n_p2lg, e = d + n_p2l;
+  if (t >= e) return;
+  if (t < a) { const uint64_t blk = t >> 1, side = t & 1; keys[t] = (uint32_t)(blk + side); refs[t] = (0ull << kRefKindShift) | (side ? kRefSideBit : 0) | blk; }
+  else if (t < b) { const uint64_t blk = t - a; keys[t] = (uint32_t)hum_i[2 * blk + 1]; refs[t] = (1ull << kRefKindShift) | blk; }
+  else if (t < c) { const uint64_t u = t - b, blk = u >> 1, side = u & 1; keys[t] = side ? stf_j[blk] : stf_i[blk]; refs[t] = (2ull << kRefKindShift) | (side ? kRefSideBit : 0) | blk; }
+  else if (t < d) { const uint64_t blk = t - c; keys[t] = p2lg_pose[blk]; refs[t] = (3ull << kRefKindShift) | blk; }
+  else { const uint64_t blk = t - d; keys[t] = p2l_pose[blk]; refs[t] = (4ull << kRefKindShift) | blk; }
+}
+__global__ void incidence_offsets_kernel(const uint32_t* __restrict__ sorted_keys, uint64_t n_inc, uint32_t n_poses, uint64_t* __restrict__ inc_off) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n_poses) return;
+  uint64_t lo = 0, hi = n_inc;                                      // first incidence with key >= p
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < p) lo = mid + 1; else hi = mid; }
+  inc_off[p] = lo;
+}
+struct GatherLayout { uint64_t r_off[5], j_off[5]; };
+__global__ void neq_gather_kernel(const uint64_t* __restrict__ inc_off, const uint64_t* __restrict__ refs, uint32_t n_poses, const double* __restrict__ r,
+                                  const double* __restrict__ J, GatherLayout L, double* __restrict__ H_diag, double* __restrict__ g) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, e = threadIdx.x & 31;
+  if (p >= n_poses || e >= 12) return;
+  const int kRes[5] = {3, 3, 2, 1, 1}, kJac[5] = {18, 9, 12, 3, 3};
+  double acc = 0.0;
+  for (uint64_t q = inc_off[p]; q < inc_off[p + 1]; ++q) {
+    const uint64_t ref = refs[q];
+    const int kind = (int)(ref >> kRefKindShift), side = (ref & kRefSideBit) ? 1 : 0;
+    const uint64_t blk = ref & (kRefSideBit - 1);
+    const int nr = kRes[kind];
+    const double* Js = J + L.j_off[kind] + blk * kJac[kind] + side * 3 * nr;      // [rows x 3] wrt this pose
+    const double* rs = r + L.r_off[kind] + blk * nr;
+    double v = 0.0;
+    if (e < 9) { const int a = e / 3, b = e % 3; for (int row = 0; row < nr; ++row) v += Js[3 * row + a] * Js[3 * row + b]; }
+    else { const int c = e - 9; for (int row = 0; row < nr; ++row) v += Js[3 * row + c] * rs[row]; }
+    acc += v;
+  }
+  if (e < 9) H_diag[9 * (size_t)p + e] = acc; else g[3 * (size_t)p + (e - 9)] = acc;
+}
+// H_off of the binary blocks (odometry, then stf): J_a^T J_b, 9 entries per block, from the per-block Jacobians
+__global__ void neq_hoff_kernel(uint64_t n_odo, uint64_t n_stf, const double* __restrict__ J, GatherLayout L, double* __restrict__ H_off) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = t / 9; const int e = (int)(t % 9);
+  if (b >= n_odo + n_stf) return;
+  const bool odo = b < n_odo;
+  const int nr = odo ? 3 : 2;
+  const double* Jb = odo ? J + L.j_off[0] + b * 18 : J + L.j_off[2] + (b - n_odo) * 12;
+  const int a3 = e / 3, b3 = e % 3;
+  double h = 0.0;
+  for (int row = 0; row < nr; ++row) h += Jb[3 * row + a3] * Jb[3 * nr + 3 * row + b3];
+  H_off[9 * b + e] = h;
+}
+constexpr int kCostBlocks = 256, kCostThreads = 256;
+__global__ void __launch_bounds__(kCostThreads) neq_cost_partial_kernel(const double* __restrict__ r, uint64_t n, double* __restrict__ partial) {
+  __shared__ double sm[kCostThreads];
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kCostThreads + threadIdx.x; i < n; i += (uint64_t)kCostBlocks * kCostThreads) acc += r[i] * r[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kCostThreads / 2; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+__global__ void neq_cost_final_kernel(const double* __restrict__ partial, double* __restrict__ cost) {
+  double acc = 0.0;
+  for (int q = 0; q < kCostBlocks; ++q) acc += partial[q];
+  *cost = 0.5 * acc;
+}
+
+static int ensure_incidence(hitl_ctx* ctx) {
+  if (ctx->inc_valid) return HITL_OK;
+  const uint64_t n_inc = 2 * ctx->nb_odo + ctx->nb_human + 2 * ctx->nb_stf + ctx->nb_p2lg + ctx->nb_p2l;
+  if (n_inc >= 0x7FFFFFFFull) return fail(ctx, HITL_ERR_ARG, "deterministic normal equations: too many block incidences");
+  ctx->n_inc = n_inc;
+  HITL_CUDA(ctx->d_inc_key.ensure(2 * n_inc)); HITL_CUDA(ctx->d_inc_ref.ensure(2 * n_inc)); HITL_CUDA(ctx->d_inc_off.ensure((size_t)ctx->n_poses + 2));
+  if (n_inc) {
+    const bool fs = ctx->stf_from_search;
+    incidence_fill_kernel<<<(uint32_t)((n_inc + 255) / 256), 256, 0, ctx->stream>>>(ctx->nb_odo, ctx->nb_human, ctx->nb_stf, ctx->nb_p2lg, ctx->nb_p2l, ctx->d_hum_i.p,
+                                                                                    fs ? ctx->d_pair_i.p : ctx->d_blk_i.p, fs ? ctx->d_pair_j.p : ctx->d_blk_j.p,
+                                                                                    ctx->d_p2lg_pose.p, ctx->d_p2l_pose.p, ctx->d_inc_key.p, ctx->d_inc_ref.p);
+    HITL_LAUNCH_CHECK("incidence_fill_kernel");
+    size_t tmp = 0;
+    HITL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_inc_key.p, ctx->d_inc_key.p + n_inc, ctx->d_inc_ref.p, ctx->d_inc_ref.p + n_inc, (int)n_inc, 0, 32, ctx->stream));
+    HITL_CUDA(ctx->d_sort_tmp.ensure(tmp));
+    HITL_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, ctx->d_inc_key.p, ctx->d_inc_key.p + n_inc, ctx->d_inc_ref.p, ctx->d_inc_ref.p + n_inc, (int)n_inc, 0, 32, ctx->stream));
+    ctx->launches += 1;
+  }
+  incidence_offsets_kernel<<<(ctx->n_poses + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_inc_key.p + n_inc, n_inc, ctx->n_poses, ctx->d_inc_off.p);
+  HITL_LAUNCH_CHECK("incidence_offsets_kernel");
+  ctx->inc_valid = true;
+  return HITL_OK;
+}
+
+static int normal_eq_launch_deterministic(hitl_ctx* ctx) {
+  const size_t n = ctx->n_poses;
+  hitl_eval_layout L; hitl_eval_layout_get(ctx, &L);
+  HITL_CUDA(ctx->d_r.ensure(L.n_residuals)); HITL_CUDA(ctx->d_J.ensure(L.n_jacobian)); HITL_CUDA(ctx->d_cost_partial.ensure(kCostBlocks));
+  int rc = ensure_incidence(ctx);
+  if (rc) return rc;
+  NeqOut none; none.H_diag = none.g = none.H_off = none.cost = nullptr;
+  rc = launch_all<double>(ctx, ctx->d_r.p, ctx->d_J.p, none, 0);
+  if (rc) return rc;
+  ctx->eval_valid = true;                            // r and J of every block are resident as after hitl_eval
+  GatherLayout G;
+  const uint64_t counts[5] = {ctx->nb_odo, ctx->nb_human, ctx->nb_stf, ctx->nb_p2lg, ctx->nb_p2l};
+  const int kRes[5] = {3, 3, 2, 1, 1}, kJac[5] = {18, 9, 12, 3, 3};
+  uint64_t ro = 0, jo = 0;
+  for (int k = 0; k < 5; ++k) { G.r_off[k] = ro; G.j_off[k] = jo; ro += counts[k] * kRes[k]; jo += counts[k] * kJac[k]; }
+  if (n) {
+    neq_gather_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_inc_off.p, ctx->d_inc_ref.p + ctx->n_inc, (uint32_t)n, ctx->d_r.p, ctx->d_J.p, G, ctx->d_neq.p,
+                                                                                ctx->d_neq.p + 9 * n);
+    HITL_LAUNCH_CHECK("neq_gather_kernel");
+  }
+  const uint64_t nbin = ctx->nb_odo + ctx->nb_stf;
+  if (nbin) {
+    neq_hoff_kernel<<<(uint32_t)((nbin * 9 + 255) / 256), 256, 0, ctx->stream>>>(ctx->nb_odo, ctx->nb_stf, ctx->d_J.p, G, ctx->d_hoff.p);
+    HITL_LAUNCH_CHECK("neq_hoff_kernel");
+  }
+  neq_cost_partial_kernel<<<kCostBlocks, kCostThreads, 0, ctx->stream>>>(ctx->d_r.p, L.n_residuals, ctx->d_cost_partial.p);
+  HITL_LAUNCH_CHECK("neq_cost_partial_kernel");
+  neq_cost_final_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_cost_partial.p, ctx->d_neq.p + 12 * n);
+  HITL_LAUNCH_CHECK("neq_cost_final_kernel");
+  return HITL_OK;
+}
+
 // Asynchronous part of hitl_normal_eq (also the first half of hitl_normal_eq_allreduce): pose upload, zero fill, the evaluation kernels.
 int normal_eq_launch(hitl_ctx* ctx, const double* pose_array) {
   if (ctx->nb_stf && ctx->stf_from_search && !ctx->have_stf) return fail(ctx, HITL_ERR_STATE, "hitl_normal_eq: search result was invalidated");
@@ -552,6 +686,12 @@ int normal_eq_launch(hitl_ctx* ctx, const double* pose_array) {
   HITL_CUDA(ctx->d_pose.ensure(3 * n));
   HITL_CUDA(ctx->d_neq.ensure(12 * n + 1)); HITL_CUDA(ctx->d_hoff.ensure(9 * nbin));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_pose.p, pose_array, 24 * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->deterministic) {
+    const int rcd = normal_eq_launch_deterministic(ctx);
+    if (rcd) return rcd;
+    ctx->neq_valid = true;
+    return HITL_OK;
+  }
   HITL_CUDA(cudaMemsetAsync(ctx->d_neq.p, 0, 8 * (12 * n + 1), ctx->stream));
   NeqOut q; q.H_diag = ctx->d_neq.p; q.g = ctx->d_neq.p + 9 * n; q.cost = ctx->d_neq.p + 12 * n; q.H_off = ctx->d_hoff.p;
   const int rc = launch_all<double>(ctx, nullptr, nullptr, q, 1);
@@ -576,6 +716,13 @@ extern "C" int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H
   if (cost) HITL_CUDA(cudaMemcpyAsync(cost, ctx->d_neq.p + 12 * n, 8, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ms_out) HITL_CUDA(cudaEventElapsedTime(ms_out, ctx->ev[0], ctx->ev[1]));
+  return HITL_OK;
+}
+
+extern "C" int hitl_set_deterministic(hitl_ctx* ctx, int on) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->deterministic = on ? 1 : 0;
+  ctx->neq_valid = false;
   return HITL_OK;
 }
 

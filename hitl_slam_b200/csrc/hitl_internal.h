@@ -177,6 +177,13 @@ struct hitl_ctx {
   hitl::DevBuf<double> d_r, d_J, d_neq, d_hoff;
   hitl::DevBuf<double2> d_trig;          // per pose (cos, sin), (x, y) of the current evaluation point
 
+  int deterministic = 0;                 // hitl_set_deterministic: normal equations by per-pose gather instead of FP64 atomics
+  bool inc_valid = false;                // per-pose incidence lists match the registered blocks
+  uint64_t n_inc = 0;
+  hitl::DevBuf<uint32_t> d_inc_key;      // [unsorted | sorted] pose of every (block, side)
+  hitl::DevBuf<uint64_t> d_inc_ref;      // [unsorted | sorted] block reference: kind << 60 | side << 59 | block
+  hitl::DevBuf<uint64_t> d_inc_off;      // per pose: first incidence
+  hitl::DevBuf<double> d_cost_partial;
   bool neq_valid = false, eval_valid = false;   // d_neq / d_r + d_J hold the result of a completed evaluation of the current blocks
   // ---- multi-GPU exchange (comm.cu) ----
   void* comm = nullptr;                  // ncclComm_t

@@ -1473,7 +1473,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   if (o->max_correspondences_per_point > 64) return fail(ctx, HITL_ERR_ARG, "hitl_find_stf: max_correspondences_per_point > 64 unsupported");
   hitl_stf_info inf; memset(&inf, 0, sizeof(inf));
   ctx->have_stf = false; ctx->n_pairs = ctx->n_matches = 0;
-  if (ctx->stf_from_search) ctx->eval_valid = ctx->neq_valid = false;
+  if (ctx->stf_from_search) ctx->eval_valid = ctx->neq_valid = false; ctx->inc_valid = false;
   // poses_end = min(max_poses + 1, n)  (JointOptimization.cpp:566-567)
   const uint32_t n = ctx->n_poses;
   const uint64_t poses_end = std::min<uint64_t>((uint64_t)max_pose + 1, n);

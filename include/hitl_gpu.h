@@ -245,6 +245,11 @@ int hitl_eval(hitl_ctx* ctx, const double* pose_array, int precision, double* r_
  * (hitl_normal_eq_device) for a device-side all-reduce. */
 int hitl_normal_eq(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* H_off, double* cost,
                    float* ms_out);
+/* on = 1: hitl_normal_eq / hitl_normal_eq_allreduce become run-to-run reproducible to the last bit on one context: instead of FP64
+ * atomics, every pose GATHERS the J^T J / J^T r of its blocks in a fixed order (per-pose incidence lists, rebuilt when blocks are
+ * registered) and the cost is a fixed-shape sum.  Slightly slower (per-block r and J are written and read back once); r and J of every
+ * block are resident afterwards as after hitl_eval.  Default 0. */
+int hitl_set_deterministic(hitl_ctx* ctx, int on);
 /* Device pointer + length (doubles) of the packed [H_diag | g | cost] buffer of the last hitl_normal_eq. */
 int hitl_normal_eq_device(hitl_ctx* ctx, void** dev_ptr, uint64_t* n_doubles);
 

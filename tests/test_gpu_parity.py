@@ -602,6 +602,28 @@ def test_normal_equations_match_oracle_jacobians(gpu, oracle, maps):
     assert abs(out["cost"] - cost) <= REL64 * cost
     ptr, nd = gpu.normal_eq_device()
     assert ptr and nd == 12 * n + 1
+    # deterministic mode (hitl_set_deterministic): per-pose gather instead of FP64 atomics — the same blocks to rounding, and the SAME BITS
+    # on every run, also after the blocks were registered again and with other work in between
+    gpu.set_deterministic(True)
+    try:
+        d1 = gpu.normal_eq(x)
+        assert rel_err(d1["H_diag"], H) <= REL64 and rel_err(d1["g"], gvec) <= REL64 and rel_err(d1["H_off"], np.array(Hoff)) <= REL64
+        assert abs(d1["cost"] - cost) <= REL64 * cost
+        assert rel_err(d1["H_diag"], out["H_diag"]) <= 1e-12 and rel_err(d1["g"], out["g"]) <= 1e-12
+        gpu.eval(x + 0.5)
+        d2 = gpu.normal_eq(x)
+        gpu.set_odometry_blocks(consts)
+        gpu.set_human_blocks(blk_i, blk_d)
+        gpu.set_stf_blocks_from_search()
+        d3 = gpu.normal_eq(x)
+        for other in (d2, d3):
+            for key in ("H_diag", "g", "H_off"):
+                assert np.array_equal(other[key], d1[key]), key
+            assert other["cost"] == d1["cost"]
+        ga = gpu.gather_stf_blocks(0)                            # r and J of every block are resident after the deterministic pass
+        assert np.array_equal(ga["r"], gpu.eval(x)["r_stf"])
+    finally:
+        gpu.set_deterministic(False)
 
 
 # ---- error behaviour ------------------------------------------------------------------------------------
