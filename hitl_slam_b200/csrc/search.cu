@@ -522,35 +522,36 @@ struct __align__(16) WarpShared {
 // stages compute.  The coarse cell of any such point therefore lies in the hull's cell range (the cell formula is monotone in
 // the coordinate), so if NO coarse cell of scan j in that range is marked — tested one level up, on the kMipCells x kMipCells
 // reduction of the coarse bitmap — every per-point coarse test of this (tile, j) pair would fail: skipping the pair is exact.
-__device__ __forceinline__ bool tile_box_may_touch(const SearchParams& P, uint32_t j, const Aff2& src, float rx0, float ry0, float rx1, float ry1) {
+__device__ __forceinline__ bool tile_box_may_touch(const SearchParams& P, uint32_t j, const Aff2& src, float bcx, float bcy, float bhx, float bhy) {
   const PoseRec rj = P.rec[j];
   if (rj.n == 0) return false;                                  // empty scan: no point can have a neighbour (the coarse stage drops it too)
   Aff2 inv; inv.m00 = rj.i00; inv.m01 = rj.i01; inv.m10 = rj.i10; inv.m11 = rj.i11; inv.tx = rj.itx; inv.ty = rj.ity;
   const Aff2 T = affine_mul(inv, src);
-  float x0, y0, x1, y1, x2, y2, x3, y3;
-  affine_apply(T, rx0, ry0, &x0, &y0); affine_apply(T, rx1, ry0, &x1, &y1);
-  affine_apply(T, rx0, ry1, &x2, &y2); affine_apply(T, rx1, ry1, &x3, &y3);
-  float lox = fminf(fminf(x0, x1), fminf(x2, x3)), hix = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
-  float loy = fminf(fminf(y0, y1), fminf(y2, y3)), hiy = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
-  const float m = cull_margin(lox, loy, hix, hiy);
-  lox -= m; loy -= m; hix += m; hiy += m;
+  // hull of the transformed box: centre +- |L| * half extents (the box is given by its centre (bcx, bcy) and half extents (bhx, bhy))
+  float cx, cy;
+  affine_apply(T, bcx, bcy, &cx, &cy);
+  const float ex = fadd(fmul(fabsf(T.m00), bhx), fmul(fabsf(T.m01), bhy)), ey = fadd(fmul(fabsf(T.m10), bhx), fmul(fabsf(T.m11), bhy));
+  const float m = cull_margin(fabsf(cx) + ex, fabsf(cy) + ey, 0.0f, 0.0f);
+  const float lox = cx - ex - m, hix = cx + ex + m, loy = cy - ey - m, hiy = cy + ey + m;
   // cell range with the cell formula of grid_cell_dims (same instruction sequence: monotone in the coordinate)
   const float nxf = (float)(rj.gdim & 0xFFFFu), nyf = (float)(rj.gdim >> 16);
   const float fx0 = fmul(fsub(lox, rj.gx0), rj.ginv), fx1 = fmul(fsub(hix, rj.gx0), rj.ginv);
   const float fy0 = fmul(fsub(loy, rj.gy0), rj.ginv), fy1 = fmul(fsub(hiy, rj.gy0), rj.ginv);
-  if (!(fx1 >= 0.0f && fy1 >= 0.0f && fx0 < nxf && fy0 < nyf)) return false;   // the hull misses the grid: every point test fails (NaN: conservative below)
-  if (!(fx0 == fx0 && fx1 == fx1 && fy0 == fy0 && fy1 == fy1)) return true;
+  if (!(fx1 >= 0.0f && fy1 >= 0.0f && fx0 < nxf && fy0 < nyf)) return !(fx0 == fx0 && fx1 == fx1 && fy0 == fy0 && fy1 == fy1);   // the hull misses the grid: every point test fails (NaN: keep the pair)
   const uint32_t cx0 = (uint32_t)fmaxf(fx0, 0.0f), cy0 = (uint32_t)fmaxf(fy0, 0.0f);
   const uint32_t cx1 = (uint32_t)fminf(fx1, nxf - 1.0f), cy1 = (uint32_t)fminf(fy1, nyf - 1.0f);
   const uint32_t mx0 = cx0 / kMipCells, mx1 = cx1 / kMipCells, my0 = cy0 / kMipCells, my1 = cy1 / kMipCells;
-  if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 48u) return true;      // an oversized tile (its points straddle a depth jump): not worth the scan
+  if (mx1 - mx0 >= 32u || my1 - my0 >= 12u) return true;         // an oversized tile (its points straddle a depth jump): not worth the scan
   const uint32_t mnx = ((rj.gdim & 0xFFFFu) + kMipCells - 1) / kMipCells;
   const uint32_t* __restrict__ mip = P.occ_mip + __ldg(P.moff + j);
-  for (uint32_t my = my0; my <= my1; ++my)
-    for (uint32_t mx = mx0; mx <= mx1; ++mx) {
-      const uint32_t bit = my * mnx + mx;
-      if ((__ldg(mip + (bit >> 5)) >> (bit & 31)) & 1u) return true;
-    }
+  // one mip row at a time: its cells are consecutive bits, a span of <= 32 of them lies in at most two words
+  const uint32_t span = (mx1 - mx0 == 31u) ? 0xFFFFFFFFu : ((1u << (mx1 - mx0 + 1)) - 1u);
+  for (uint32_t my = my0; my <= my1; ++my) {
+    const uint32_t b0 = my * mnx + mx0, w0 = b0 >> 5, sh = b0 & 31u;
+    uint32_t bits = __ldg(mip + w0) >> sh;
+    if (sh && ((b0 + (mx1 - mx0)) >> 5) != w0) bits |= __ldg(mip + w0 + 1) << (32u - sh);
+    if (bits & span) return true;
+  }
   return false;
 }
 
@@ -599,13 +600,16 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
       const float m = P.thr + cull_margin(bx0, by0, bx1, by1);
       bx0 -= m; by0 -= m; bx1 += m; by1 += m;
     }
-    // robot-frame box of the tile's points (tile-box vs target-scan cull, stage 1a)
+    // robot-frame box of the tile's points as centre + half extents (tile-box vs target-scan cull, stage 1a)
     float rx0 = FLT_MAX, ry0 = FLT_MAX, rx1 = -FLT_MAX, ry1 = -FLT_MAX;
     if (valid) { rx0 = rx1 = p.x; ry0 = ry1 = p.y; }
     for (int o = 16; o; o >>= 1) {
       rx0 = fminf(rx0, __shfl_xor_sync(0xffffffffu, rx0, o)); ry0 = fminf(ry0, __shfl_xor_sync(0xffffffffu, ry0, o));
       rx1 = fmaxf(rx1, __shfl_xor_sync(0xffffffffu, rx1, o)); ry1 = fmaxf(ry1, __shfl_xor_sync(0xffffffffu, ry1, o));
     }
+    // the half extents are rounded UP so that centre +- extent contains [rx0, rx1] x [ry0, ry1] whatever the rounding of the centre
+    const float bcx = 0.5f * (rx0 + rx1), bcy = 0.5f * (ry0 + ry1);
+    const float bhx = fmaxf(bcx - rx0, rx1 - bcx) * 1.000001f + 1e-6f, bhy = fmaxf(bcy - ry0, ry1 - bcy) * 1.000001f + 1e-6f;
     const uint32_t out_base = P.tile_slot[tile] * (uint32_t)P.cap;   // this unit's private record region
     const uint2 tj = P.tile_j[tile];
     const bool is_unit = tj.x != 0 || tj.y != kFullRange;        // one of several target ranges of a split tile
@@ -868,7 +872,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) stf_search_kernel(const 
         if (hit && !P.no_cull) {
           const float4 wb = __ldg(P.wbox + jl);
           hit = !(wb.x > bx1 || wb.z < bx0 || wb.y > by1 || wb.w < by0);
-          if (hit && P.occ_mip) hit = tile_box_may_touch(P, jl, src, rx0, ry0, rx1, ry1);
+          if (hit && P.occ_mip) hit = tile_box_may_touch(P, jl, src, bcx, bcy, bhx, bhy);
         }
         const uint32_t cand = __ballot_sync(0xffffffffu, hit);
         if (cand == 0) continue;
