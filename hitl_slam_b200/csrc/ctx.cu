@@ -155,6 +155,7 @@ extern "C" int hitl_create(hitl_ctx** out, int device) {
   // scheduling knobs of the adaptive tiling (results never depend on them)
   if (const char* v = getenv("HITL_SPLIT_LIMIT_DIV")) ctx->split_limit_div = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("HITL_MIN_TARGET_SPAN")) ctx->min_target_span = (uint32_t)std::max(1, atoi(v));
+  if (const char* v = getenv("HITL_ORDER_TWO_PASS")) ctx->order_two_pass = atoi(v) ? 1 : 0;
   if (const char* v = getenv("HITL_SEARCH_VARIANT")) ctx->search_variant = std::min(2, std::max(0, atoi(v)));   // occupancy / register trade-off (profiling)
   if (const char* v = getenv("HITL_SPLIT_ROUNDS")) ctx->max_split_rounds = (uint32_t)std::max(0, atoi(v));
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
@@ -178,7 +179,7 @@ extern "C" void hitl_destroy(hitl_ctx* ctx) {
   ctx->d_pose.release(); ctx->d_rec.release(); ctx->d_wbox.release(); ctx->d_gbox.release(); ctx->d_src.release(); ctx->d_grid.release(); ctx->d_occ.release(); ctx->d_occ_fine.release(); ctx->d_occ_dir.release(); ctx->d_nmax.release(); ctx->d_occ_mip.release(); ctx->d_moff.release(); ctx->d_tile_j.release(); ctx->d_tile_slot.release(); ctx->d_groups.release(); ctx->d_tile_open.release(); ctx->d_tile_end.release();
   ctx->d_raw_j.release(); ctx->d_raw_k.release(); ctx->d_raw_idx.release(); ctx->d_tile_cnt.release();
   ctx->d_srt_j.release(); ctx->d_srt_k.release(); ctx->d_srt_idx.release(); ctx->d_srt_flag.release();
-  ctx->d_pose_cnt.release(); ctx->d_counters.release(); ctx->d_pose_work.release();
+  ctx->d_pose_cnt.release(); ctx->d_order_state.release(); ctx->d_counters.release(); ctx->d_pose_work.release();
   ctx->d_pair_i.release(); ctx->d_pair_j.release(); ctx->d_k.release(); ctx->d_idx.release(); ctx->d_pair_off.release();
   ctx->d_vo_sp.release(); ctx->d_vo_sk.release(); ctx->d_vo_tk.release();
   ctx->d_world.release(); ctx->d_poses_f.release(); ctx->d_em_pose.release(); ctx->d_em_idx.release(); ctx->d_em_xy.release();

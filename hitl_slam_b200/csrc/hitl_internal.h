@@ -134,6 +134,8 @@ struct hitl_ctx {
   hitl::DevBuf<uint32_t> d_raw_j, d_raw_k, d_raw_idx, d_tile_cnt;   // per-tile raw records
   hitl::DevBuf<uint32_t> d_srt_j, d_srt_k, d_srt_idx;               // per-pose sorted staging
   hitl::DevBuf<uint8_t> d_srt_flag;                                 // bit0 keep, bit1 first-of-pair
+  hitl::DevBuf<uint64_t> d_order_state;  // look-back states of the single-pass ordering kernel (4 words per source pose)
+  int order_two_pass = 0;                // HITL_ORDER_TWO_PASS=1: the older count / scan / place sequence (A/B check)
   hitl::DevBuf<uint64_t> d_pose_cnt;     // per pose: kept matches, kept pairs (2 per pose) then scanned
   hitl::DevBuf<uint64_t> d_pose_work;    // SM cycles per source pose of the last search (shard balancing)
   hitl::DevBuf<uint64_t> d_counters;     // [0] n_queries [1] n_traversals [2] raw matches [3] pairs [4] matches

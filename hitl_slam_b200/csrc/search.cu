@@ -1012,6 +1012,10 @@ struct OrderParams {
   uint32_t src_lo, src_hi, n_poses; int cap; uint32_t min_corr;
   uint32_t* scratch;                  // gridDim.x * n_poses, zero on entry and on exit
   unsigned long long* pose_cnt;       // 2 per source pose of the shard: matches, pairs (pass 1: exclusive offsets)
+  // single-pass variant (PASS == 2): poses are handed out by ticket in ascending order; the (matches, pairs) offsets of a pose come from a
+  // decoupled look-back over the states its predecessors publish: 4 words per pose = {aggregate matches | flag, aggregate pairs,
+  // inclusive-prefix matches | flag, inclusive-prefix pairs}, zero on entry
+  unsigned long long* state; unsigned long long* ticket; unsigned long long* counters;
   uint32_t* pair_i; uint32_t* pair_j; unsigned long long* pair_off; uint32_t* out_k; uint32_t* out_idx;
 };
 
@@ -1053,14 +1057,24 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
   __shared__ uint32_t s_jlo, s_jhi;
   __shared__ unsigned long long s_off_m, s_off_p;
   __shared__ uint32_t s_hcnt[kOrderTileBatch], s_hbase[kOrderTileBatch], s_htotal;   // tile descriptors of the pose (prefix of counts, record bases)
-  __shared__ uint32_t s_next[PASS == 1 ? kOrderSlots : 1];      // next free slot of the pose's first kOrderSlots kept pairs
-  __shared__ uint32_t s_tcnt[PASS == 1 ? kOrderTileBatch : 1], s_tbase[PASS == 1 ? kOrderTileBatch : 1];
-  __shared__ uint32_t s_mask[PASS == 1 ? kOrderMaskWords : 1];  // fast path: one bit row per kept pair over the pose's points
+  __shared__ uint32_t s_next[PASS >= 1 ? kOrderSlots : 1];      // next free slot of the pose's first kOrderSlots kept pairs
+  __shared__ uint32_t s_tcnt[PASS >= 1 ? kOrderTileBatch : 1], s_tbase[PASS >= 1 ? kOrderTileBatch : 1];
+  __shared__ uint32_t s_mask[PASS >= 1 ? kOrderMaskWords : 1];  // fast path: one bit row per kept pair over the pose's points
   uint32_t* const s_j = s_mask;                                 // fallback path: the j column of the tile being placed (<= kMaxTileRecords)
-  __shared__ uint16_t s_pref[PASS == 1 ? kOrderMaskWords : 1];  // ... and the popcount prefix of each row word
+  __shared__ uint16_t s_pref[PASS >= 1 ? kOrderMaskWords : 1];  // ... and the popcount prefix of each row word
   __shared__ uint32_t s_total;
   uint32_t* const cntj = P.scratch + (size_t)blockIdx.x * P.n_poses;
-  for (uint32_t i = P.src_lo + blockIdx.x; i < P.src_hi; i += gridDim.x) {
+  __shared__ uint32_t s_ticket;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t i;
+    if (PASS == 2) {                                            // ascending tickets: a pose only ever waits for poses that are already being processed
+      if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(P.ticket, 1ull);
+      __syncthreads();
+      i = P.src_lo + s_ticket;
+    } else {
+      i = P.src_lo + blockIdx.x + it * gridDim.x;
+    }
+    if (i >= P.src_hi) break;
     const uint32_t tb = P.tile_begin[i], te = P.tile_begin[i + 1];
     if (threadIdx.x == 0) { s_jlo = 0xFFFFFFFFu; s_jhi = 0; }
     __syncthreads();
@@ -1097,6 +1111,56 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
     unsigned long long tot_m = 0, tot_p = 0;
     if (PASS == 1 && threadIdx.x == 0) { s_off_m = P.pose_cnt[2 * (i - P.src_lo)]; s_off_p = P.pose_cnt[2 * (i - P.src_lo) + 1]; }
     __syncthreads();
+    if (PASS == 2) {
+      // -- totals of this pose (the counting scan), then its offsets by decoupled look-back over the preceding poses --
+      uint32_t run_m = 0, run_p = 0;
+      if (jlo != 0xFFFFFFFFu)
+        for (uint32_t j0 = jlo; j0 <= jhi; j0 += 4 * kOrderThreads) {
+          uint32_t lm = 0, lp = 0;
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t j = j0 + 4 * threadIdx.x + q;
+            const uint32_t c = j <= jhi ? cntj[j] : 0;
+            if (c > P.min_corr) { lm += c; lp += 1u; }
+          }
+          unsigned long long tot2;
+          block_exclusive_scan64((unsigned long long)lm | ((unsigned long long)lp << 40), &tot2, sm);
+          run_m += (uint32_t)(tot2 & 0xFFFFFFFFFFull); run_p += (uint32_t)(tot2 >> 40);
+        }
+      if (threadIdx.x < 32) {
+        constexpr unsigned long long kFlag = 1ull << 63;
+        const uint32_t lane = threadIdx.x, q = i - P.src_lo;
+        unsigned long long* const st = P.state;
+        if (lane == 0) { st[4 * (size_t)q + 1] = run_p; __threadfence(); atomicExch(&st[4 * (size_t)q], kFlag | run_m); }
+        unsigned long long pm = 0, pp = 0;
+        long long base = (long long)q - 1;
+        bool done = q == 0;
+        while (!done) {
+          const long long c = base - lane;
+          unsigned long long vm = 0, vp = 0;
+          bool is_prefix = c < 0;                                 // before the first pose: an empty inclusive prefix
+          if (c >= 0) {
+            for (;;) {
+              const unsigned long long v2 = atomicAdd(&st[4 * (size_t)c + 2], 0ull);
+              if (v2 & kFlag) { __threadfence(); vp = *(volatile unsigned long long*)&st[4 * (size_t)c + 3]; vm = v2 & ~kFlag; is_prefix = true; break; }
+              const unsigned long long v0 = atomicAdd(&st[4 * (size_t)c], 0ull);
+              if (v0 & kFlag) { __threadfence(); vp = *(volatile unsigned long long*)&st[4 * (size_t)c + 1]; vm = v0 & ~kFlag; break; }
+            }
+          }
+          const uint32_t pre = __ballot_sync(0xffffffffu, is_prefix);
+          const uint32_t first = pre ? (uint32_t)(__ffs(pre) - 1) : 31u;       // nearest predecessor that already knows its inclusive prefix
+          if (lane > first) { vm = 0; vp = 0; }
+          for (int o = 16; o; o >>= 1) { vm += __shfl_xor_sync(0xffffffffu, vm, o); vp += __shfl_xor_sync(0xffffffffu, vp, o); }
+          pm += vm; pp += vp;
+          if (pre) done = true; else base -= 32;
+        }
+        if (lane == 0) {
+          st[4 * (size_t)q + 3] = pp + run_p; __threadfence(); atomicExch(&st[4 * (size_t)q + 2], kFlag | (pm + run_m));
+          s_off_m = pm; s_off_p = pp;
+          if (i + 1 == P.src_hi) { P.counters[3] = pp + run_p; P.counters[4] = pm + run_m; P.pair_off[pp + run_p] = pm + run_m; }
+        }
+      }
+      __syncthreads();
+    }
     if (jlo != 0xFFFFFFFFu) {
       // -- scan over j in [jlo, jhi]: kept-match prefix and kept-pair prefix --
       uint32_t run_m = 0, run_p = 0;
@@ -1112,7 +1176,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
         const unsigned long long ex2 = block_exclusive_scan64((unsigned long long)lm | ((unsigned long long)lp << 40), &tot2, sm);
         uint32_t em = (uint32_t)(ex2 & 0xFFFFFFFFFFull), ep = (uint32_t)(ex2 >> 40);
         const uint32_t tm = (uint32_t)(tot2 & 0xFFFFFFFFFFull), tp = (uint32_t)(tot2 >> 40);
-        if (PASS == 1) {
+        if (PASS >= 1) {
           for (int q = 0; q < 4; ++q) {
             const uint32_t j = j0 + 4 * threadIdx.x + q;
             if (j > jhi) break;
@@ -1133,7 +1197,7 @@ __global__ void __launch_bounds__(kOrderThreads) stf_order_kernel(const OrderPar
         run_m += tm; run_p += tp;
       }
       tot_m = run_m; tot_p = run_p;
-      if (PASS == 1) {
+      if (PASS >= 1) {
         // -- placement, tile by tile: every tile list is sorted by (j, k) and the tiles of a pose come in ascending k
         //    (units of a split tile: ascending target range), so pair (i, j) is the concatenation over tiles of each
         //    tile's run of j.  A record's slot = the pair's next free slot + its rank inside the run (bisection of the
@@ -1571,7 +1635,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   Q.tile_begin = ctx->d_tile_begin.p; Q.tile_slot = ctx->d_tile_slot.p; Q.off = ctx->d_off.p; Q.src_lo = lo; Q.src_hi = hi; Q.n_poses = n; Q.cap = cap;
   Q.min_corr = o->min_inter_pose_correspondence;
   int order_per_sm = 0;
-  HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&order_per_sm, stf_order_kernel<1>, kOrderThreads, 0));
+  HITL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&order_per_sm, ctx->order_two_pass ? stf_order_kernel<1> : stf_order_kernel<2>, kOrderThreads, 0));
   if (order_per_sm < 1) order_per_sm = 1;
   const uint32_t order_grid = std::min<uint32_t>(hi - lo, (uint32_t)(ctx->sm_count * order_per_sm));   // one resident wave: a CTA keeps an n_poses-sized scratch
   HITL_CUDA(ctx->d_srt_j.ensure((size_t)order_grid * n));   // reused as the j-indexed scratch
@@ -1579,6 +1643,16 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   Q.scratch = ctx->d_srt_j.p; Q.pose_cnt = (unsigned long long*)ctx->d_pose_cnt.p;
   Q.pair_i = ctx->d_pair_i.p; Q.pair_j = ctx->d_pair_j.p; Q.pair_off = (unsigned long long*)ctx->d_pair_off.p;
   Q.out_k = ctx->d_k.p; Q.out_idx = ctx->d_idx.p;
+  if (!ctx->order_two_pass) {
+    // single pass: count, look back for the pose's offsets, place (one resident wave of CTAs, poses by ascending ticket)
+    HITL_CUDA(ctx->d_order_state.ensure(4 * (size_t)(hi - lo)));
+    HITL_CUDA(cudaMemsetAsync(ctx->d_order_state.p, 0, 32 * (size_t)(hi - lo), ctx->stream));
+    Q.state = (unsigned long long*)ctx->d_order_state.p; Q.ticket = (unsigned long long*)ctx->d_counters.p + 14; Q.counters = (unsigned long long*)ctx->d_counters.p;
+    HITL_CUDA(cudaEventRecord(ctx->evx[2], ctx->stream));
+    HITL_CUDA(cudaEventRecord(ctx->evx[3], ctx->stream));
+    stf_order_kernel<2><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
+    HITL_LAUNCH_CHECK("stf_order_kernel<2>");
+  } else {
   stf_order_kernel<0><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<0>");
   HITL_CUDA(cudaEventRecord(ctx->evx[2], ctx->stream));   // after order<0>
@@ -1587,6 +1661,7 @@ extern "C" int hitl_find_stf(hitl_ctx* ctx, const double* pose_array, uint32_t m
   HITL_CUDA(cudaEventRecord(ctx->evx[3], ctx->stream));   // after the scan
   stf_order_kernel<1><<<order_grid, kOrderThreads, 0, ctx->stream>>>(Q);
   HITL_LAUNCH_CHECK("stf_order_kernel<1>");
+  }
   HITL_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
   HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.p, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
