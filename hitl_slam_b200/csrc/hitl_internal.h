@@ -89,7 +89,7 @@ struct hitl_ctx {
   uint32_t split_rounds = 0, split_lo = 0, split_hi = 0;         // calls that were allowed to re-tile for the source range [split_lo, split_hi)
   int adaptive_tiling = 1;
   // split policy of the adaptive tiling (scheduling only; env HITL_SPLIT_LIMIT_DIV / HITL_MIN_TARGET_SPAN / HITL_SPLIT_ROUNDS override)
-  uint32_t split_limit_div = 2;          // a tile heavier than 2 x (fair share / split_limit_div) is split
+  uint32_t split_limit_div = 1;          // a tile heavier than 2 x (fair share / split_limit_div) is split (1: measured best on 1/8 shards of c2, profiles/diag_shard.py)
   uint32_t min_target_span = 64;         // target-axis ranges never get narrower than this many poses
   uint32_t max_split_rounds = 3;         // only the first max_split_rounds calls on a source range may re-tile (setup; W >= 3 warm-up steps cover it)
   int target_splitting = 1;              // heavy tiles may also be cut along the target axis (hitl_debug_set_tiling)

@@ -22,7 +22,7 @@ for lo, hi in ((0, n // 8), (3 * n // 8, n // 2), (7 * n // 8, n), (0, n)):
         hist.append(round(r["ms_search"], 3))
     print("range", lo, hi, "ms_search per call", hist, "ms_total", round(r["ms_total"], 3), "tiles", r["n_tiles"],
           "packed_ms", round(r["sum_tile_cycles"] / slots / 1.965e6, 3), "max_tile_ms", round(r["max_tile_cycles"] / 1.965e6, 3))
-    w = gpu.debug_tile_work().astype(np.float64) / 1.965e6 * 64
+    w = gpu.debug_tile_work().astype(np.float64) / 1.965e6
     d = gpu.debug_tile_desc()
     top = np.argsort(-w)[:6]
     for t in top:
