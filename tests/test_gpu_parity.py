@@ -357,6 +357,38 @@ def test_find_stf_ragged_and_empty_scans(gpu, oracle):
     assert len(S.find_stf(poses, min_corr=0, min_cos=-2.0)["k"]) > 0
 
 
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_angle_gate_prefilter_with_arbitrary_normals(gpu, oracle, seed):
+    """The direction prefilter must stay exact when normals are not unit vectors (the reference's loader leaves them un-normalised),
+    zero, tiny, huge, pointing anywhere, with pose angles of many turns, for tight and loose gates: same lists as the oracle and as the
+    search without any culling; poses beyond the filter's float-angle range (|theta| > 256 rad) simply bypass it."""
+    rng = np.random.default_rng(seed)
+    off, pts, nrm = random_scans(rng, 48, 20, 260, empty=(5,))
+    pts = (pts * 0.4).astype(np.float32)
+    m = len(nrm)
+    mag = np.exp(rng.uniform(np.log(0.05), np.log(40.0), m)).astype(np.float32)
+    mag[rng.random(m) < 0.05] = 0.0                                  # zero normals: the dot product is 0, never a match for min_cos > 0
+    mag[rng.random(m) < 0.03] = 1e-30
+    mag[rng.random(m) < 0.02] = 3e18
+    nrm = (nrm * mag[:, None]).astype(np.float32)
+    poses = np.stack([np.linspace(0, 2.5, 48), rng.normal(size=48) * 0.1, rng.uniform(-40.0, 40.0, 48)], 1)
+    if seed == 23:
+        poses[::5, 2] += 300.0                                       # beyond kDirMaxTheta: those pairs bypass the prefilter
+    gpu.set_scans(off, pts, nrm)
+    gpu.build_kdtrees()
+    S = oracle.scans(off, pts, nrm)
+    culled = 0
+    for opts in (dict(min_corr=0), dict(min_corr=0, min_cos=0.999, thr=0.3), dict(min_corr=1, min_cos=0.2, thr=0.25, cap=3), dict(min_corr=0, min_cos=1e-6)):
+        ref = S.find_stf(poses, **opts)
+        out = gpu.find_stf(poses, opts=gpu.stf_opts(**opts))
+        raw = gpu.find_stf(poses, opts=gpu.stf_opts(disable_culling=1, **opts))
+        assert_same_stf(out, ref)
+        assert_same_stf(raw, ref)
+        assert out["n_queries"] == ref["n_queries"] == raw["n_queries"]
+        culled += out["n_dir_culled"]
+    assert culled > 0
+
+
 def test_find_stf_empty_problem(gpu):
     gpu.set_scans(np.zeros(1, np.uint32), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
     gpu.build_kdtrees()
