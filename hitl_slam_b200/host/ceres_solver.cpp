@@ -39,21 +39,30 @@ int Problem::block_index(double* values, int size) {
 
 void Problem::AddParameterBlock(double* values, int size) { block_index(values, size); }
 
-ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss, const std::vector<double*>& blocks) {
-  (void)loss;   // the hot path passes NULL (JointOptimization.cpp:555, 820, 999, 1019, 1034, 1048)
-  ResidualBlock rb; rb.cost = cost; rb.residual_offset = num_residuals_;
+ResidualBlockId Problem::add_block(CostFunction* cost, double* const* blocks, size_t n) {
+  if (residuals_.empty()) { residuals_.reserve(1024); owned_.reserve(1024); blocks_.reserve(1024); index_.reserve(1024); }
+  residuals_.emplace_back();
+  ResidualBlock& rb = residuals_.back();
+  rb.cost = cost; rb.residual_offset = num_residuals_;
   const std::vector<int32_t>& sizes = cost->parameter_block_sizes();
-  for (size_t i = 0; i < blocks.size(); ++i) rb.blocks.push_back(block_index(blocks[i], sizes[i]));
+  for (size_t i = 0; i < n; ++i) rb.blocks.push_back(block_index(blocks[i], sizes[i]));
   num_residuals_ += cost->num_residuals();
-  residuals_.push_back(rb);
   owned_.push_back(cost);
   return (ResidualBlockId)residuals_.size() - 1;
 }
+ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss, const std::vector<double*>& blocks) {
+  (void)loss;   // the hot path passes NULL (JointOptimization.cpp:555, 820, 999, 1019, 1034, 1048)
+  return add_block(cost, blocks.data(), blocks.size());
+}
 ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0) {
-  return AddResidualBlock(cost, loss, std::vector<double*>{x0});
+  (void)loss;
+  double* b[1] = {x0};
+  return add_block(cost, b, 1);
 }
 ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss, double* x0, double* x1) {
-  return AddResidualBlock(cost, loss, std::vector<double*>{x0, x1});
+  (void)loss;
+  double* b[2] = {x0, x1};
+  return add_block(cost, b, 2);
 }
 void Problem::SetParameterBlockConstant(double* values) {
   auto it = index_.find(values);

@@ -41,20 +41,26 @@ class LossFunction { public: virtual ~LossFunction() {} };   // the path passes 
 // ---- cost functions --------------------------------------------------------------------------
 class CostFunction {
  public:
-  CostFunction() : num_residuals_(0) {}
+  CostFunction() : sizes_(&parameter_block_sizes_), num_residuals_(0) {}
   virtual ~CostFunction() {}
+  CostFunction(const CostFunction&) = delete;
+  CostFunction& operator=(const CostFunction&) = delete;
   // jacobians[i] is row-major [num_residuals x parameter_block_sizes()[i]]; jacobians or any
   // jacobians[i] may be NULL.
   virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const = 0;
-  const std::vector<int32_t>& parameter_block_sizes() const { return parameter_block_sizes_; }
+  const std::vector<int32_t>& parameter_block_sizes() const { return *sizes_; }
   int num_residuals() const { return num_residuals_; }
 
  protected:
-  std::vector<int32_t>* mutable_parameter_block_sizes() { return &parameter_block_sizes_; }
+  std::vector<int32_t>* mutable_parameter_block_sizes() { sizes_ = &parameter_block_sizes_; return &parameter_block_sizes_; }
   void set_num_residuals(int n) { num_residuals_ = n; }
+  // Sized cost functions share one size list per type: a problem of thousands of blocks (one object per residual block, as the
+  // reference builds it) then costs one allocation per block, not two.
+  void share_parameter_block_sizes(const std::vector<int32_t>* shared) { sizes_ = shared; }
 
  private:
   std::vector<int32_t> parameter_block_sizes_;
+  const std::vector<int32_t>* sizes_;
   int num_residuals_;
 };
 
@@ -62,8 +68,9 @@ template <int kNumResiduals, int... Ns>
 class SizedCostFunction : public CostFunction {
  public:
   SizedCostFunction() {
+    static const std::vector<int32_t> kSizes{Ns...};
     set_num_residuals(kNumResiduals);
-    *mutable_parameter_block_sizes() = std::vector<int32_t>{Ns...};
+    share_parameter_block_sizes(&kSizes);
   }
 };
 
@@ -192,13 +199,27 @@ class Problem {
 
   // -- used by Solve --
   struct ParameterBlock { double* values; int size; bool constant; };
-  struct ResidualBlock { CostFunction* cost; std::vector<int> blocks; int residual_offset; };
+  // parameter blocks of one residual block: the hot path has one or two (inline storage), anything longer spills to the heap
+  class BlockList {
+   public:
+    BlockList() : n_(0) {}
+    size_t size() const { return n_; }
+    int operator[](size_t i) const { return i < kInline ? inl_[i] : more_[i - kInline]; }
+    void push_back(int v) { if (n_ < kInline) inl_[n_] = v; else more_.push_back(v); ++n_; }
+   private:
+    static const size_t kInline = 2;
+    size_t n_;
+    int inl_[kInline];
+    std::vector<int> more_;
+  };
+  struct ResidualBlock { CostFunction* cost; BlockList blocks; int residual_offset; };
   const std::vector<ParameterBlock>& parameter_blocks() const { return blocks_; }
   const std::vector<ResidualBlock>& residual_blocks() const { return residuals_; }
   const Options& options() const { return options_; }
 
  private:
   int block_index(double* values, int size);
+  ResidualBlockId add_block(CostFunction* cost, double* const* blocks, size_t n);
   Options options_;
   std::vector<ParameterBlock> blocks_;
   std::unordered_map<double*, int> index_;
