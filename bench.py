@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--poses", type=int, default=None)
     ap.add_argument("--beams", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--balance-passes", type=int, default=4, help="multi-GPU setup: searches used to cut the source ranges at equal measured work")
+    ap.add_argument("--balance-passes", type=int, default=8, help="multi-GPU setup: searches used to cut the source ranges at equal measured work")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-correction", action="store_true", help="skip the correction-latency leg")
