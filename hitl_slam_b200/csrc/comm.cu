@@ -177,25 +177,28 @@ extern "C" int hitl_gather_stf_blocks(hitl_ctx* ctx, int root, uint64_t cap_bloc
   }
   if (world > 1) {
     HITL_NCCL(g_nccl.GroupStart());
+    ncclResult_t first_error = ncclSuccess;           // the group is always closed; the first failure inside it is reported afterwards
+    auto note = [&](ncclResult_t r) { if (r != ncclSuccess && first_error == ncclSuccess) first_error = r; };
     if (rank == root) {
       uint64_t o = 0;
       for (int q = 0; q < world; ++q) {
         const uint64_t c = counts[q];
         if (q != root && c) {
-          g_nccl.Recv(ctx->d_g_pi.p + o, c, ncclUint32, q, (ncclComm_t)ctx->comm, ctx->stream);
-          g_nccl.Recv(ctx->d_g_pj.p + o, c, ncclUint32, q, (ncclComm_t)ctx->comm, ctx->stream);
-          g_nccl.Recv(ctx->d_g_r.p + 2 * o, 2 * c, ncclDouble, q, (ncclComm_t)ctx->comm, ctx->stream);
-          g_nccl.Recv(ctx->d_g_J.p + 12 * o, 12 * c, ncclDouble, q, (ncclComm_t)ctx->comm, ctx->stream);
+          note(g_nccl.Recv(ctx->d_g_pi.p + o, c, ncclUint32, q, (ncclComm_t)ctx->comm, ctx->stream));
+          note(g_nccl.Recv(ctx->d_g_pj.p + o, c, ncclUint32, q, (ncclComm_t)ctx->comm, ctx->stream));
+          note(g_nccl.Recv(ctx->d_g_r.p + 2 * o, 2 * c, ncclDouble, q, (ncclComm_t)ctx->comm, ctx->stream));
+          note(g_nccl.Recv(ctx->d_g_J.p + 12 * o, 12 * c, ncclDouble, q, (ncclComm_t)ctx->comm, ctx->stream));
         }
         o += c;
       }
     } else if (mine) {
-      g_nccl.Send(d_pi, mine, ncclUint32, root, (ncclComm_t)ctx->comm, ctx->stream);
-      g_nccl.Send(d_pj, mine, ncclUint32, root, (ncclComm_t)ctx->comm, ctx->stream);
-      g_nccl.Send(d_r, 2 * mine, ncclDouble, root, (ncclComm_t)ctx->comm, ctx->stream);
-      g_nccl.Send(d_J, 12 * mine, ncclDouble, root, (ncclComm_t)ctx->comm, ctx->stream);
+      note(g_nccl.Send(d_pi, mine, ncclUint32, root, (ncclComm_t)ctx->comm, ctx->stream));
+      note(g_nccl.Send(d_pj, mine, ncclUint32, root, (ncclComm_t)ctx->comm, ctx->stream));
+      note(g_nccl.Send(d_r, 2 * mine, ncclDouble, root, (ncclComm_t)ctx->comm, ctx->stream));
+      note(g_nccl.Send(d_J, 12 * mine, ncclDouble, root, (ncclComm_t)ctx->comm, ctx->stream));
     }
     HITL_NCCL(g_nccl.GroupEnd());
+    if (first_error != ncclSuccess) return nccl_fail(ctx, first_error, "ncclSend / ncclRecv inside hitl_gather_stf_blocks");
     ctx->launches++;
   }
   if (rank == root) {

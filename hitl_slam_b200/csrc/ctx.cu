@@ -274,14 +274,21 @@ namespace hitl {
 // AoS hitl_kdnode (24 B) -> the resident SoA layout {float4 p|n, int32 index|dim<<31}; validates
 // index / dim against the owning scan on the way (one thread per node, scan found by bisection).
 __global__ void split_nodes_kernel(const hitl_kdnode* __restrict__ nodes, const uint32_t* __restrict__ off, uint32_t n_poses, uint64_t m,
-                                   float4* __restrict__ pm, float2* __restrict__ nn, uint32_t* __restrict__ bad) {
+                                   const float2* __restrict__ pts, const float2* __restrict__ nrm, float4* __restrict__ pm, float2* __restrict__ nn,
+                                   uint32_t* __restrict__ bad) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const hitl_kdnode nd = nodes[i];
   uint32_t lo = 0, hi = n_poses;
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
   const uint32_t n = off[lo + 1] - off[lo];
-  if (nd.index < 0 || (uint32_t)nd.index >= n || (nd.dim != 0 && nd.dim != 1)) atomicOr(bad, 1u);
+  if (nd.index < 0 || (uint32_t)nd.index >= n || (nd.dim != 0 && nd.dim != 1)) { atomicOr(bad, 1u); return; }
+  // a node IS a point of its scan (KDNodeValue = {point, normal, index}, kdtree.h:26-40): the occupancy levels of the search are built
+  // from the resident scans, so a tree whose node differs from the point it names would make the culls inexact — refuse it
+  const float2 p = pts[off[lo] + nd.index], v = nrm[off[lo] + nd.index];
+  if (__float_as_uint(p.x) != __float_as_uint(nd.px) || __float_as_uint(p.y) != __float_as_uint(nd.py) || __float_as_uint(v.x) != __float_as_uint(nd.nx) ||
+      __float_as_uint(v.y) != __float_as_uint(nd.ny))
+    atomicOr(bad, 2u);
   pm[i] = make_float4(nd.px, nd.py, __uint_as_float(((uint32_t)nd.index & 0x7FFFFFFFu) | (nd.dim ? 0x80000000u : 0u)), 0.0f);
   nn[i] = make_float2(nd.nx, nd.ny);
 }
@@ -302,12 +309,14 @@ static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
     HITL_CUDA(ctx->d_node_aos.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(1));
     HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
     HITL_CUDA(cudaMemcpyAsync(ctx->d_node_aos.p, nodes, sizeof(hitl_kdnode) * m, cudaMemcpyHostToDevice, ctx->stream));
-    split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_node_pm.p,
-                                                                            ctx->d_node_nn.p, ctx->d_ticket.p);
+    split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_pts.p, ctx->d_nrm.p,
+                                                                            ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_ticket.p);
     HITL_LAUNCH_CHECK("split_nodes_kernel");
     HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_ticket.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*(const uint32_t*)ctx->h_pinned) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
+    const uint32_t badbits = *(const uint32_t*)ctx->h_pinned;
+    if (badbits & 1u) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: node index/dim out of range");
+    if (badbits & 2u) return fail(ctx, HITL_ERR_ARG, "hitl_set_kdtrees: a node's point / normal differs from the scan point it names (trees must be trees of the uploaded scans)");
   }
   ctx->have_trees = true;
   ctx->grid_valid = false;      // the direction masks are built from the node normals

@@ -86,7 +86,8 @@ typedef struct {
  * median n/2) and make it resident.  Built on the device, all scans at once, with the reference's exact
  * tree shape (equal keys included); hitl_debug_set_tree_builder(ctx, 1) selects the threaded host builder. */
 int hitl_build_kdtrees(hitl_ctx* ctx);
-/* Or adopt trees built elsewhere (same layout, concatenated by scan_offsets). */
+/* Or adopt trees built elsewhere (same layout, concatenated by scan_offsets).  Every node must carry exactly the point and normal of
+ * the scan entry its `index` names (bit for bit — a KD-tree of a scan holds that scan's points); HITL_ERR_ARG otherwise. */
 int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes);
 int hitl_get_kdtrees(hitl_ctx* ctx, hitl_kdnode* nodes_out);
 /* Compact form of the same trees: one 32-bit word per node in preorder, index | dim << 31.  The node's point and normal are the

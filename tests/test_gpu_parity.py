@@ -122,6 +122,12 @@ def test_compact_tree_and_index_formats(gpu, oracle, maps):
     bad = comp.copy(); bad[5] = 0x7FFFFFF0
     with pytest.raises(Exception):
         gpu.set_kdtrees_compact(bad)
+    moved = nodes.copy(); moved["px"][7] += np.float32(0.25)          # a node that is not the scan point it names: refused (the culls are built from the scans)
+    with pytest.raises(Exception):
+        gpu.set_kdtrees(moved)
+    turned = nodes.copy(); turned["nx"][9] = -turned["nx"][9] - np.float32(1.0)
+    with pytest.raises(Exception):
+        gpu.set_kdtrees(turned)
     load_map(gpu, g)                                     # leave the shared context in a sane state
 
 
