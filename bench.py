@@ -538,7 +538,8 @@ def main():
     if compact:
         h_compact = gpu.pinned_copy((nodes["index"].astype(np.uint32) & 0x7FFFFFFF) | (nodes["dim"].astype(np.uint32) << 31))
         o_stf16 = (o_stf[0], o_stf[1], o_stf[2], gpu.pinned(nmatch + 1, np.uint16), gpu.pinned(nmatch + 1, np.uint16))
-    h2d = h_pts.nbytes + h_nrm.nbytes + (h_compact.nbytes if compact else h_nodes.nbytes) + h_off.nbytes + h_poses.nbytes * 2 + h_odo.nbytes
+    map_bytes = h_pts.nbytes + h_nrm.nbytes + (h_compact.nbytes if compact else h_nodes.nbytes)
+    h2d = (map_bytes + world - 1) // world + h_off.nbytes + h_poses.nbytes * 2 + h_odo.nbytes      # per rank: 1 / world of the map crosses ITS PCIe link
     d2h = 0
 
     e2e_parts = []
@@ -546,12 +547,13 @@ def main():
     def e2e_step(upload_map=True):
         t = [time.perf_counter()]
         if upload_map:
-            gpu.set_scans(h_off, h_pts, h_nrm)
+            # N > 1: every rank holds the map on its host; each uploads 1/N of it and the slices are all-gathered over NVLink (hitl_set_*_sharded)
+            (gpu.set_scans_sharded if world > 1 else gpu.set_scans)(h_off, h_pts, h_nrm)
             t.append(time.perf_counter())
             if compact:
-                gpu.set_kdtrees_compact(h_compact)
+                (gpu.set_kdtrees_compact_sharded if world > 1 else gpu.set_kdtrees_compact)(h_compact)
             else:
-                gpu.set_kdtrees(h_nodes)
+                (gpu.set_kdtrees_sharded if world > 1 else gpu.set_kdtrees)(h_nodes)
         else:
             t.append(t[0])
         t.append(time.perf_counter())
@@ -600,6 +602,8 @@ def main():
            "map_resident": {"value": evals / float(tr.item()) / 1e6, "ms_per_step": float(tr.item()) * 1e3, "h2d_bytes_per_step": int(h_poses.nbytes * 2 + h_odo.nbytes), "d2h_bytes_per_step": int(d2h),
                             "what": "the same step when scans + trees are already resident (uploaded once per session): poses up, correspondences + residuals + Jacobians down"},
            "timing": "host wall clock around the synchronous C-ABI calls (every call ends with a stream sync), pinned host buffers, max over ranks",
+           "upload": ("sharded: each rank uploads 1/%d of scans + trees, ncclAllGather over NVLink in place (hitl_set_scans_sharded / hitl_set_kdtrees_compact_sharded); "
+                      "h2d_bytes_per_step is per rank" % world) if world > 1 else "whole map over one PCIe link",
            "formats": "compact (u32 tree nodes, u16 point indices)" if compact else "hitl_kdnode trees (24 B/node), u32 point indices"}
 
     # ---- correction latency (second half of the BASELINE metric): one human correction on this map ----

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_refit", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
-    "hitl_normal_eq_device", "hitl_set_deterministic", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks",
+    "hitl_normal_eq_device", "hitl_set_deterministic", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks", "hitl_set_scans_sharded", "hitl_set_kdtrees_sharded", "hitl_set_kdtrees_compact_sharded",
     "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
     "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
@@ -220,7 +220,7 @@ class HitlGpu:
             raise HitlError("%s: expected %d values (3 per pose of the resident map), got %d" % (what, 3 * self.n_poses, p.size))
         return p
 
-    def set_scans(self, offsets, pts, nrm):
+    def set_scans(self, offsets, pts, nrm, _fn="hitl_set_scans"):
         offsets = np.ascontiguousarray(offsets, np.uint32)
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1)
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1)
@@ -232,7 +232,27 @@ class HitlGpu:
         if len(pts) == 0:
             pts = np.zeros(2, np.float32)
             nrm = np.zeros(2, np.float32)
-        self._ck(self.lib.hitl_set_scans(self.ctx, self.n_poses, offsets, pts, nrm))
+        fn = getattr(self.lib, _fn)
+        fn.argtypes = self.lib.hitl_set_scans.argtypes
+        self._ck(fn(self.ctx, self.n_poses, offsets, pts, nrm))
+
+    def set_scans_sharded(self, offsets, pts, nrm):
+        """hitl_set_scans_sharded: collective; every rank passes the same arrays and uploads 1/world of them."""
+        self.set_scans(offsets, pts, nrm, _fn="hitl_set_scans_sharded")
+
+    def set_kdtrees_compact_sharded(self, index_dim):
+        index_dim = np.ascontiguousarray(index_dim, np.uint32)
+        if index_dim.size != self.n_points:
+            raise HitlError("set_kdtrees_compact_sharded: expected %d nodes (one per point), got %d" % (self.n_points, index_dim.size))
+        self.lib.hitl_set_kdtrees_compact_sharded.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.hitl_set_kdtrees_compact_sharded(self.ctx, index_dim.ctypes.data_as(C.c_void_p)))
+
+    def set_kdtrees_sharded(self, nodes):
+        nodes = np.ascontiguousarray(nodes, KDNODE)
+        if nodes.size != self.n_points:
+            raise HitlError("set_kdtrees_sharded: expected %d nodes (one per point), got %d" % (self.n_points, nodes.size))
+        self.lib.hitl_set_kdtrees_sharded.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.hitl_set_kdtrees_sharded(self.ctx, nodes.ctypes.data))
 
     def build_kdtrees(self):
         self._ck(self.lib.hitl_build_kdtrees(self.ctx))

@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 #include "hitl_internal.h"
@@ -72,6 +73,30 @@ int nccl_fail(hitl_ctx* ctx, ncclResult_t r, const char* where) {
 }  // namespace
 
 static_assert(sizeof(ncclUniqueId) == HITL_COMM_ID_BYTES, "hitl_gpu.h: HITL_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
+
+namespace hitl {
+static size_t upload_slice(const hitl_ctx* ctx, size_t bytes) {
+  const size_t w = (size_t)ctx->comm_world;
+  return (((bytes + w - 1) / w) + 15) & ~(size_t)15;             // equal slices, 16-byte aligned
+}
+size_t replicated_upload_capacity(const hitl_ctx* ctx, size_t bytes) {
+  if (!ctx->upload_sharded || !ctx->comm || ctx->comm_world <= 1) return bytes;
+  return upload_slice(ctx, bytes) * (size_t)ctx->comm_world;
+}
+int replicated_upload(hitl_ctx* ctx, void* dev, const void* host, size_t bytes) {
+  if (bytes == 0) return HITL_OK;
+  if (!ctx->upload_sharded || !ctx->comm || ctx->comm_world <= 1) {
+    HITL_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HITL_OK;
+  }
+  const size_t slice = upload_slice(ctx, bytes), lo = slice * (size_t)ctx->comm_rank;
+  if (lo < bytes)
+    HITL_CUDA(cudaMemcpyAsync(static_cast<char*>(dev) + lo, static_cast<const char*>(host) + lo, std::min(slice, bytes - lo), cudaMemcpyHostToDevice, ctx->stream));
+  HITL_NCCL(g_nccl.AllGather(static_cast<char*>(dev) + lo, dev, slice, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));   // in place: every rank's slice sits at its own offset
+  ctx->launches++;
+  return HITL_OK;
+}
+}  // namespace hitl
 
 extern "C" int hitl_comm_unique_id(void* id_out) {
   if (!id_out || !nccl_ready()) return HITL_ERR_NCCL;

@@ -252,11 +252,14 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   ctx->n_points = n_points;
   ctx->h_pts.clear(); ctx->h_nrm.clear();   // host copies are fetched lazily by hitl_build_kdtrees
   HITL_CUDA(ctx->d_off.ensure(n_poses + 1));
-  HITL_CUDA(ctx->d_pts.ensure(ctx->n_points)); HITL_CUDA(ctx->d_nrm.ensure(ctx->n_points));
+  const size_t cloud_elems = (replicated_upload_capacity(ctx, 8 * ctx->n_points) + 7) / 8;      // padded to world equal slices when the upload is sharded
+  HITL_CUDA(ctx->d_pts.ensure(cloud_elems)); HITL_CUDA(ctx->d_nrm.ensure(cloud_elems));
   HITL_CUDA(cudaMemcpyAsync(ctx->d_off.p, ctx->h_off.data(), 4 * (size_t)(n_poses + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (ctx->n_points) {
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_pts.p, pts_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_nrm.p, nrm_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
+    int urc = replicated_upload(ctx, ctx->d_pts.p, pts_xy, 8 * ctx->n_points);
+    if (urc) return urc;
+    urc = replicated_upload(ctx, ctx->d_nrm.p, nrm_xy, 8 * ctx->n_points);
+    if (urc) return urc;
   }
   // tiles: up to 32 consecutive points of one scan (the unit of work of the search; heavy tiles are split later)
   int rc = same_partition ? HITL_OK : hitl::build_tiling(ctx, 32);
@@ -268,6 +271,32 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   if (n_poses) HITL_CUDA(cudaMemcpyAsync(ctx->h_aabb.data(), ctx->d_aabb.p, 16 * (size_t)n_poses, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   return HITL_OK;
+}
+
+// The same uploads for a multi-GPU job whose ranks all hold the map on their hosts (comm.cu: hitl_comm_init first): every rank passes the
+// SAME arrays, each moves only its 1/world slice across PCIe, the slices travel over NVLink (ncclAllGather, in place).  Collective.
+extern "C" int hitl_set_scans_sharded(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* off, const float* pts_xy, const float* nrm_xy) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->upload_sharded = true;
+  const int rc = hitl_set_scans(ctx, n_poses, off, pts_xy, nrm_xy);
+  ctx->upload_sharded = false;
+  return rc;
+}
+extern "C" int hitl_set_kdtrees(hitl_ctx* ctx, const hitl_kdnode* nodes);
+extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim);
+extern "C" int hitl_set_kdtrees_sharded(hitl_ctx* ctx, const hitl_kdnode* nodes) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->upload_sharded = true;
+  const int rc = hitl_set_kdtrees(ctx, nodes);
+  ctx->upload_sharded = false;
+  return rc;
+}
+extern "C" int hitl_set_kdtrees_compact_sharded(hitl_ctx* ctx, const uint32_t* index_dim) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->upload_sharded = true;
+  const int rc = hitl_set_kdtrees_compact(ctx, index_dim);
+  ctx->upload_sharded = false;
+  return rc;
 }
 
 namespace hitl {
@@ -306,9 +335,9 @@ static int upload_trees(hitl_ctx* ctx, const hitl_kdnode* nodes) {
   HITL_CUDA(ctx->d_node_pm.ensure(m)); HITL_CUDA(ctx->d_node_nn.ensure(m));
   ctx->have_trees = false;
   if (m) {
-    HITL_CUDA(ctx->d_node_aos.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(1));
+    HITL_CUDA(ctx->d_node_aos.ensure((replicated_upload_capacity(ctx, sizeof(hitl_kdnode) * m) + sizeof(hitl_kdnode) - 1) / sizeof(hitl_kdnode))); HITL_CUDA(ctx->d_ticket.ensure(1));
     HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_aos.p, nodes, sizeof(hitl_kdnode) * m, cudaMemcpyHostToDevice, ctx->stream));
+    { const int urc = replicated_upload(ctx, ctx->d_node_aos.p, nodes, sizeof(hitl_kdnode) * m); if (urc) return urc; }
     split_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_aos.p, ctx->d_off.p, ctx->n_poses, m, ctx->d_pts.p, ctx->d_nrm.p,
                                                                             ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_ticket.p);
     HITL_LAUNCH_CHECK("split_nodes_kernel");
@@ -432,9 +461,9 @@ extern "C" int hitl_set_kdtrees_compact(hitl_ctx* ctx, const uint32_t* index_dim
   HITL_CUDA(ctx->d_node_pm.ensure(m)); HITL_CUDA(ctx->d_node_nn.ensure(m));
   ctx->have_trees = false;
   if (m) {
-    HITL_CUDA(ctx->d_node_compact.ensure(m)); HITL_CUDA(ctx->d_ticket.ensure(4));
+    HITL_CUDA(ctx->d_node_compact.ensure((replicated_upload_capacity(ctx, 4 * m) + 3) / 4)); HITL_CUDA(ctx->d_ticket.ensure(4));
     HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
-    HITL_CUDA(cudaMemcpyAsync(ctx->d_node_compact.p, index_dim, 4 * m, cudaMemcpyHostToDevice, ctx->stream));
+    { const int urc = replicated_upload(ctx, ctx->d_node_compact.p, index_dim, 4 * m); if (urc) return urc; }
     expand_nodes_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_node_compact.p, ctx->d_pts.p, ctx->d_nrm.p, ctx->d_off.p, ctx->n_poses, m,
                                                                               ctx->d_node_pm.p, ctx->d_node_nn.p, ctx->d_ticket.p);
     HITL_LAUNCH_CHECK("expand_nodes_kernel");

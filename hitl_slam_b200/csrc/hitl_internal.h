@@ -188,6 +188,7 @@ struct hitl_ctx {
   hitl::DevBuf<double> d_cost_partial;
   bool neq_valid = false, eval_valid = false;   // d_neq / d_r + d_J hold the result of a completed evaluation of the current blocks
   // ---- multi-GPU exchange (comm.cu) ----
+  bool upload_sharded = false;           // hitl_set_scans_sharded / hitl_set_kdtrees*_sharded: the next uploads move 1/world over PCIe each
   void* comm = nullptr;                  // ncclComm_t
   int comm_rank = 0, comm_world = 1;
   hitl::DevBuf<uint64_t> d_comm_cnt;
@@ -223,6 +224,11 @@ int cuda_fail(hitl_ctx* c, cudaError_t e, const char* where);
     if (e__ != cudaSuccess) return hitl::cuda_fail(ctx, e__, name);  \
   } while (0)
 
+// Upload of a buffer that every rank of the job holds identically on its host (comm.cu): with a communicator and ctx->upload_sharded
+// set, this rank copies only its 1/world slice across PCIe and the slices are exchanged in place with ncclAllGather over NVLink;
+// otherwise a plain cudaMemcpyAsync.  `capacity_bytes` of the device buffer must be >= replicated_upload_capacity(ctx, bytes).
+size_t replicated_upload_capacity(const hitl_ctx* ctx, size_t bytes);
+int replicated_upload(hitl_ctx* ctx, void* dev, const void* host, size_t bytes);
 int build_tiling(hitl_ctx* ctx, uint32_t max_len);
 int upload_tiling(hitl_ctx* ctx);
 uint32_t split_heavy_tiles(hitl_ctx* ctx, const std::vector<uint32_t>& h_work, const std::vector<uint32_t>& h_open, const std::vector<uint32_t>& h_end, uint32_t lo,

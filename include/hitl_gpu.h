@@ -270,6 +270,12 @@ int hitl_comm_info(const hitl_ctx* ctx, int* rank, int* world, int* nccl_version
  * synchronisation in between — one ncclAllReduce(sum, f64) over the packed resident buffer [H_diag n_poses x 9 | g n_poses x 3 |
  * cost], in place.  Afterwards every rank holds the whole problem's H_diag / g / cost (also resident: hitl_normal_eq_device);
  * H_off stays with the rank that owns each block.  Without a communicator (single GPU) it is hitl_normal_eq. */
+/* Uploads for a job whose ranks all hold the same map on their hosts: identical arguments on every rank (collective); each rank moves
+ * only its 1/world slice across PCIe and the slices are exchanged over NVLink (ncclAllGather, in place).  Without a communicator they
+ * are the plain calls. */
+int hitl_set_scans_sharded(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* scan_offsets, const float* pts_xy, const float* nrm_xy);
+int hitl_set_kdtrees_sharded(hitl_ctx* ctx, const hitl_kdnode* nodes);
+int hitl_set_kdtrees_compact_sharded(hitl_ctx* ctx, const uint32_t* index_dim);
 int hitl_normal_eq_allreduce(hitl_ctx* ctx, const double* pose_array, double* H_diag, double* g, double* cost, float* ms_out);
 /* The Ceres-on-the-host feed: after hitl_eval (with Jacobians) on every rank, gathers the STF blocks of all ranks to `root` in rank
  * order (= the reference's block order when the ranks own ascending source ranges): pair_i / pair_j [total], r [total x 2],

@@ -71,8 +71,16 @@ def _rank_main(rank, world, uid, conn, name):
         from hitl_slam_b200.sharding import shard_ranges
         g = synth.generate(name)
         gpu = HitlGpu(rank)
-        _load(gpu, g)
         gpu.comm_init(uid, rank, world)
+        # sharded uploads: every rank passes the same host arrays, each moves 1/world over PCIe, the slices are all-gathered over NVLink
+        gpu.set_scans_sharded(g["offsets"], g["pts"], g["nrm"])
+        gpu.build_kdtrees()
+        comp, nodes = gpu.get_kdtrees_compact().copy(), gpu.get_kdtrees().copy()
+        gpu.set_scans_sharded(g["offsets"], g["pts"], g["nrm"])
+        gpu.set_kdtrees_compact_sharded(comp)
+        assert np.array_equal(gpu.get_kdtrees(), nodes), "sharded compact tree upload"
+        gpu.set_kdtrees_sharded(nodes)
+        assert np.array_equal(gpu.get_kdtrees(), nodes), "sharded tree upload"
         poses, x = g["poses"].astype(np.float64), _jitter(g, 5)
         lo, hi = shard_ranges(g["offsets"], world)[rank]
         part = gpu.find_stf(poses, src_lo=lo, src_hi=hi)
