@@ -15,39 +15,60 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 
 namespace hitl {
 namespace ceres {
 
 // ---- Problem ---------------------------------------------------------------------------------------
 Problem::~Problem() {
-  if (options_.cost_function_ownership == TAKE_OWNERSHIP) {
-    std::sort(owned_.begin(), owned_.end());
-    owned_.erase(std::unique(owned_.begin(), owned_.end()), owned_.end());
-    for (CostFunction* c : owned_) delete c;
+  if (options_.cost_function_ownership == TAKE_OWNERSHIP)
+    for (const ResidualBlock& rb : residuals_)
+      if (--rb.cost->problem_uses_ == 0) delete rb.cost;
+}
+
+int Problem::find_block(double* values) const {
+  if (!ascending_) {
+    auto it = index_.find(values);
+    return it == index_.end() ? -1 : it->second;
   }
+  if (blocks_.empty()) return -1;
+  if (blocks_.back().values == values) return (int)blocks_.size() - 1;     // a chain's block i starts where block i-1 ended
+  const std::less<double*> before;
+  auto it = std::lower_bound(blocks_.begin(), blocks_.end(), values, [&](const ParameterBlock& b, double* v) { return before(b.values, v); });
+  return (it != blocks_.end() && it->values == values) ? (int)(it - blocks_.begin()) : -1;
 }
 
 int Problem::block_index(double* values, int size) {
-  auto it = index_.find(values);
-  if (it != index_.end()) return it->second;
+  const int found = find_block(values);
+  if (found >= 0) return found;
+  if (ascending_ && !blocks_.empty() && !std::less<double*>()(blocks_.back().values, values)) {
+    ascending_ = false;
+    index_.reserve(2 * blocks_.size() + 16);
+    for (size_t b = 0; b < blocks_.size(); ++b) index_[blocks_[b].values] = (int)b;
+  }
   ParameterBlock b; b.values = values; b.size = size; b.constant = false;
   blocks_.push_back(b);
-  index_[values] = (int)blocks_.size() - 1;
+  if (!ascending_) index_[values] = (int)blocks_.size() - 1;
   return (int)blocks_.size() - 1;
 }
 
 void Problem::AddParameterBlock(double* values, int size) { block_index(values, size); }
 
 ResidualBlockId Problem::add_block(CostFunction* cost, double* const* blocks, size_t n) {
-  if (residuals_.empty()) { residuals_.reserve(1024); owned_.reserve(1024); blocks_.reserve(1024); index_.reserve(1024); }
+  if (residuals_.empty()) { residuals_.reserve(1024); blocks_.reserve(1024); }
   residuals_.emplace_back();
   ResidualBlock& rb = residuals_.back();
   rb.cost = cost; rb.residual_offset = num_residuals_;
   const std::vector<int32_t>& sizes = cost->parameter_block_sizes();
-  for (size_t i = 0; i < n; ++i) rb.blocks.push_back(block_index(blocks[i], sizes[i]));
+  rb.blocks.n_ = (uint32_t)n;
+  if (n > Problem::BlockList::kInline) { spill_.emplace_back(new int[n - Problem::BlockList::kInline]); rb.blocks.more_ = spill_.back().get(); }
+  for (size_t i = 0; i < n; ++i) {
+    const int b = block_index(blocks[i], sizes[i]);
+    if (i < Problem::BlockList::kInline) rb.blocks.inl_[i] = b; else rb.blocks.more_[i - Problem::BlockList::kInline] = b;
+  }
   num_residuals_ += cost->num_residuals();
-  owned_.push_back(cost);
+  ++cost->problem_uses_;
   return (ResidualBlockId)residuals_.size() - 1;
 }
 ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss, const std::vector<double*>& blocks) {
@@ -65,12 +86,12 @@ ResidualBlockId Problem::AddResidualBlock(CostFunction* cost, LossFunction* loss
   return add_block(cost, b, 2);
 }
 void Problem::SetParameterBlockConstant(double* values) {
-  auto it = index_.find(values);
-  if (it != index_.end()) blocks_[it->second].constant = true;
+  const int b = find_block(values);
+  if (b >= 0) blocks_[b].constant = true;
 }
 void Problem::SetParameterBlockVariable(double* values) {
-  auto it = index_.find(values);
-  if (it != index_.end()) blocks_[it->second].constant = false;
+  const int b = find_block(values);
+  if (b >= 0) blocks_[b].constant = false;
 }
 int Problem::NumParameters() const {
   int n = 0;
@@ -299,7 +320,7 @@ bool Problem::Evaluate(const EvaluateOptions& options, double* cost, std::vector
   // by 3 * pose sees the same offsets whether or not pose 0 is held constant.
   std::vector<int> order;
   if (options.parameter_blocks.empty()) { for (int i = 0; i < (int)blocks_.size(); ++i) order.push_back(i); }
-  else for (double* v : options.parameter_blocks) { auto it = index_.find(v); if (it == index_.end()) return false; order.push_back(it->second); }
+  else for (double* v : options.parameter_blocks) { const int b = find_block(v); if (b < 0) return false; order.push_back(b); }
   std::vector<int> col(blocks_.size(), -1);
   int n = 0;
   for (int b : order) { col[b] = n; n += blocks_[b].size; }

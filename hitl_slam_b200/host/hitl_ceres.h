@@ -59,9 +59,11 @@ class CostFunction {
   void share_parameter_block_sizes(const std::vector<int32_t>* shared) { sizes_ = shared; }
 
  private:
+  friend class Problem;
   std::vector<int32_t> parameter_block_sizes_;
   const std::vector<int32_t>* sizes_;
   int num_residuals_;
+  int problem_uses_ = 0;   // residual blocks of the owning Problem that use this object: a shared cost function is deleted once
 };
 
 template <int kNumResiduals, int... Ns>
@@ -199,18 +201,19 @@ class Problem {
 
   // -- used by Solve --
   struct ParameterBlock { double* values; int size; bool constant; };
-  // parameter blocks of one residual block: the hot path has one or two (inline storage), anything longer spills to the heap
+  // parameter blocks of one residual block: the hot path has one or two (inline storage); a longer list keeps its tail in storage
+  // the Problem owns, so that a ResidualBlock stays trivially copyable and the block vector grows by plain copies
   class BlockList {
    public:
-    BlockList() : n_(0) {}
+    BlockList() : n_(0), more_(nullptr) {}
     size_t size() const { return n_; }
     int operator[](size_t i) const { return i < kInline ? inl_[i] : more_[i - kInline]; }
-    void push_back(int v) { if (n_ < kInline) inl_[n_] = v; else more_.push_back(v); ++n_; }
    private:
+    friend class Problem;
     static const size_t kInline = 2;
-    size_t n_;
+    uint32_t n_;
     int inl_[kInline];
-    std::vector<int> more_;
+    int* more_;
   };
   struct ResidualBlock { CostFunction* cost; BlockList blocks; int residual_offset; };
   const std::vector<ParameterBlock>& parameter_blocks() const { return blocks_; }
@@ -219,12 +222,17 @@ class Problem {
 
  private:
   int block_index(double* values, int size);
+  int find_block(double* values) const;   // -1 when the pointer is not a parameter block of this problem
   ResidualBlockId add_block(CostFunction* cost, double* const* blocks, size_t n);
   Options options_;
   std::vector<ParameterBlock> blocks_;
+  // Pointer -> block index.  While the blocks arrive in ascending address order (the hot path walks one contiguous pose array:
+  // JointOptimization.cpp:817-821, 994-1049) blocks_ itself is the index (append / bisection, no allocation per block); the first
+  // out-of-order pointer switches to the hash map for the rest of the problem's life.
+  bool ascending_ = true;
   std::unordered_map<double*, int> index_;
   std::vector<ResidualBlock> residuals_;
-  std::vector<CostFunction*> owned_;
+  std::vector<std::unique_ptr<int[]>> spill_;   // tails of the block lists longer than BlockList::kInline
   int num_residuals_ = 0;
 };
 

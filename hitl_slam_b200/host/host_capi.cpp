@@ -496,6 +496,47 @@ int hitl_host_evaluate_selftest(const double x_in[4], int hold_x1, double grad_o
   return (int)gradient.size();
 }
 
+// Problem bookkeeping that the pose-chain hot path never exercises: parameter blocks added in DESCENDING address order (the pointer
+// index leaves its append-only form), one cost function shared by two residual blocks (deleted once), a residual block over three
+// parameter blocks (block list beyond its inline storage), SetParameterBlockConstant on a block found through each index form.
+// out = {cost, #parameter blocks, #residuals, gradient entry of the constant block, live cost functions after the problem died}.
+namespace {
+int g_live_sum3 = 0;
+struct Sum3 : ceres::CostFunction {        // r = a + 2 b + 3 c - 1 over three scalar blocks
+  Sum3() { ++g_live_sum3; set_num_residuals(1); for (int q = 0; q < 3; ++q) mutable_parameter_block_sizes()->push_back(1); }
+  ~Sum3() override { --g_live_sum3; }
+  bool Evaluate(double const* const* p, double* r, double** J) const override {
+    r[0] = p[0][0] + 2.0 * p[1][0] + 3.0 * p[2][0] - 1.0;
+    if (J) for (int q = 0; q < 3; ++q) if (J[q]) J[q][0] = q + 1.0;
+    return true;
+  }
+};
+}  // namespace
+int hitl_host_problem_selftest(double out[5]) {
+  double x[6] = {0.5, -1.0, 2.0, 0.25, 4.0, -3.0};
+  g_live_sum3 = 0;
+  {
+    ceres::Problem problem;
+    Sum3* shared = new Sum3;
+    problem.AddResidualBlock(shared, NULL, std::vector<double*>{&x[1], &x[2], &x[3]});      // ascending so far
+    problem.SetParameterBlockConstant(&x[2]);                                                   // found by bisection
+    problem.AddResidualBlock(shared, NULL, std::vector<double*>{&x[5], &x[4], &x[0]});      // x4 and x0 arrive out of order
+    problem.AddResidualBlock(new Sum3, NULL, std::vector<double*>{&x[0], &x[2], &x[5]});
+    problem.SetParameterBlockConstant(&x[0]);                                                   // found through the hash map
+    problem.SetParameterBlockVariable(&x[2]);
+    std::vector<double> residuals, gradient;
+    double cost = 0;
+    ceres::Problem::EvaluateOptions eo;
+    if (!problem.Evaluate(eo, &cost, &residuals, &gradient, NULL)) return -1;
+    out[0] = cost; out[1] = problem.NumParameterBlocks(); out[2] = problem.NumResiduals();
+    // blocks in insertion order: x1 x2 x3 x5 x4 x0 -> the constant x0 is the last gradient entry
+    out[3] = gradient.size() == 6 ? gradient[5] : -1.0;
+    if (g_live_sum3 != 2) return -2;
+  }
+  out[4] = g_live_sum3;
+  return 0;
+}
+
 // A pose-chain problem of the human-constraint shape — n blocks of 2 parameters, relative factors between neighbours,
 // unary factors on every 7th block, non-linear through a sine — solved with the dense path (mode 0), the chain-direct
 // path (mode 1: block-tridiagonal elimination) or PCG (mode 2).  x: 2 n values in/out.

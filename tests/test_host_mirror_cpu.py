@@ -54,6 +54,21 @@ def test_problem_evaluate_keeps_constant_blocks_as_zero_columns(host):
     assert len(g) == 4 and dims[:2] == (4, 4) and dims[2] == 6 and g[0] == 0.0 and np.allclose(g, want, rtol=1e-12)
 
 
+def test_problem_bookkeeping_off_the_chain_shape(host):
+    """The stand-in Problem indexes parameter blocks by bisection while they arrive in ascending address order (the pose chain) and
+    by hash map afterwards; cost functions shared between residual blocks are deleted once; block lists longer than two spill."""
+    import ctypes as C
+    lib = host.lib
+    lib.hitl_host_problem_selftest.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C")]
+    lib.hitl_host_problem_selftest.restype = C.c_int
+    out = np.zeros(5)
+    assert lib.hitl_host_problem_selftest(out) == 0
+    r = np.array([2.75, 5.5, -5.5])
+    assert out[0] == pytest.approx(0.5 * (r ** 2).sum(), rel=1e-15) and out[1] == 6 and out[2] == 3
+    assert out[3] == 0.0        # the constant block keeps a zero gradient entry
+    assert out[4] == 0          # both cost functions died with the problem, the shared one once
+
+
 def test_solver_chain_direct_matches_dense_and_cg(host):
     """Beyond the dense limit the stand-in LM eliminates block-tridiagonal systems (the odometry chain + unary human factors)
     directly; same minimiser as the dense path and as PCG."""
