@@ -27,12 +27,12 @@ ABI_SYMBOLS = [
     "hitl_host_alloc", "hitl_host_free",
     "hitl_set_scans", "hitl_build_kdtrees", "hitl_set_kdtrees", "hitl_get_kdtrees", "hitl_set_kdtrees_compact", "hitl_get_kdtrees_compact", "hitl_kd_query", "hitl_kd_neighbors",
     "hitl_find_stf", "hitl_get_stf", "hitl_get_stf16", "hitl_get_stf_work", "hitl_find_vo", "hitl_get_vo",
-    "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_refit", "hitl_em_assign",
+    "hitl_world_transform", "hitl_set_world_clouds", "hitl_verify_input", "hitl_em_inliers", "hitl_em_refit", "hitl_em_refit_chain", "hitl_em_assign",
     "hitl_set_stf_blocks_from_search", "hitl_set_stf_blocks", "hitl_set_odometry_blocks", "hitl_set_human_blocks",
     "hitl_set_p2l_glob_blocks", "hitl_set_p2l_blocks", "hitl_eval_layout_get", "hitl_eval", "hitl_normal_eq",
     "hitl_normal_eq_device", "hitl_set_deterministic", "hitl_comm_unique_id", "hitl_comm_init", "hitl_comm_destroy", "hitl_comm_info", "hitl_normal_eq_allreduce", "hitl_gather_stf_blocks", "hitl_set_scans_sharded", "hitl_set_kdtrees_sharded", "hitl_set_kdtrees_compact_sharded",
     "hitl_backprop_poses", "hitl_kdtree_build_host", "hitl_debug_sincos", "hitl_debug_relative_pose", "hitl_debug_tile_work", "hitl_debug_tile_desc", "hitl_debug_set_tiling",
-    "hitl_debug_set_fine_occupancy", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
+    "hitl_debug_set_fine_occupancy", "hitl_debug_set_em_cull", "hitl_debug_set_search_variant", "hitl_debug_set_tree_builder", "hitl_debug_tree_stats",
 ]
 
 
@@ -136,6 +136,7 @@ class HitlGpu:
         lib.hitl_kd_query.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_int, _f32p, _i32p]
         lib.hitl_kd_neighbors.argtypes = [vp, C.c_uint32, C.c_uint32, _f32p, C.c_float, C.c_uint32, vp, _u32p]
         lib.hitl_em_refit.argtypes = [vp, _f32p, C.c_double, C.c_int32, _f32p, C.POINTER(EmFitInfo)]
+        lib.hitl_em_refit_chain.argtypes = [vp, C.c_uint32, _f32p, C.c_double, C.c_int32, C.c_uint32, _f32p, C.POINTER(EmFitInfo)]
         lib.hitl_find_stf.argtypes = [vp, _f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(StfOpts), C.POINTER(StfInfo)]
         lib.hitl_get_stf.argtypes = [vp, _u32p, _u32p, _u64p, _u32p, _u32p]
         lib.hitl_get_stf_work.argtypes = [vp, _u64p]
@@ -163,6 +164,7 @@ class HitlGpu:
         lib.hitl_debug_tile_desc.argtypes = [vp, C.c_uint32, _u32p, _u32p, _u32p, _u32p, _u32p]
         lib.hitl_debug_set_tiling.argtypes = [vp, C.c_uint32, C.c_int, C.c_uint32]
         lib.hitl_debug_set_fine_occupancy.argtypes = [vp, C.c_int]
+        lib.hitl_debug_set_em_cull.argtypes = [vp, C.c_int]
         lib.hitl_debug_set_search_variant.argtypes = [vp, C.c_int, C.c_int]
         lib.hitl_debug_set_tree_builder.argtypes = [vp, C.c_int]
         lib.hitl_debug_tree_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -382,6 +384,19 @@ class HitlGpu:
         out, info = np.zeros(4, np.float32), EmFitInfo()
         self._ck(self.lib.hitl_em_refit(self.ctx, seg, thr, max_iterations, out, C.byref(info)))
         return out, {k: getattr(info, k) for k, _ in EmFitInfo._fields_}
+
+    def em_refit_chain(self, segs, rounds=2, thr=0.03, max_iterations=25):
+        """`rounds` EM rounds of 1 or 2 strokes with one host wait (hitl_em_refit_chain).  segs: [n_strokes, 4].
+        Returns (segments [rounds, n_strokes, 4] f32, infos [rounds][n_strokes] dicts)."""
+        segs = np.ascontiguousarray(segs, np.float32).reshape(-1, 4)
+        ns = len(segs)
+        out, infos = np.zeros(4 * ns * rounds, np.float32), (EmFitInfo * (ns * rounds))()
+        self._ck(self.lib.hitl_em_refit_chain(self.ctx, ns, segs.reshape(-1), thr, max_iterations, rounds, out, infos))
+        return out.reshape(rounds, ns, 4), [[{k: getattr(infos[r * ns + q], k) for k, _ in EmFitInfo._fields_} for q in range(ns)] for r in range(rounds)]
+
+    def debug_set_em_cull(self, on=True):
+        """E-step chunk cull on / off (result-preserving)."""
+        self._ck(self.lib.hitl_debug_set_em_cull(self.ctx, int(bool(on))))
 
     def verify_input(self, sel, thr=0.05):
         """HitLSLAM::verifyUserInput on the resident world clouds: (points_verified, seen bit mask)."""
@@ -913,6 +928,11 @@ class HostSession:
         """Where EMInput's M-step runs: device (hitl_em_refit, default) or the host LM (the checker)."""
         self.lib.hitl_host_session_set_device_m_step.argtypes = [C.c_void_p, C.c_int]
         self.lib.hitl_host_session_set_device_m_step(self.s, int(bool(on)))
+
+    def set_em_chain_rounds(self, rounds=2):
+        """Device M-step: EM rounds of both strokes enqueued per host wait (hitl_em_refit_chain); 1 = a wait per round."""
+        self.lib.hitl_host_session_set_em_chain_rounds.argtypes = [C.c_void_p, C.c_int]
+        self.lib.hitl_host_session_set_em_chain_rounds(self.s, int(rounds))
 
     def em_run(self, correction_type, selected_points):
         sel = np.ascontiguousarray(selected_points, np.float32).reshape(-1).copy()

@@ -156,6 +156,7 @@ extern "C" int hitl_create(hitl_ctx** out, int device) {
   if (const char* v = getenv("HITL_SPLIT_LIMIT_DIV")) ctx->split_limit_div = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("HITL_MIN_TARGET_SPAN")) ctx->min_target_span = (uint32_t)std::max(1, atoi(v));
   if (const char* v = getenv("HITL_ORDER_TWO_PASS")) ctx->order_two_pass = atoi(v) ? 1 : 0;
+  if (const char* v = getenv("HITL_EM_CULL")) ctx->em_cull = atoi(v) != 0;
   if (const char* v = getenv("HITL_SEARCH_VARIANT")) ctx->search_variant = std::min(2, std::max(0, atoi(v)));   // occupancy / register trade-off (profiling)
   if (const char* v = getenv("HITL_SPLIT_ROUNDS")) ctx->max_split_rounds = (uint32_t)std::max(0, atoi(v));
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; cudaGetLastError(); return HITL_ERR_CUDA; }
@@ -240,7 +241,7 @@ extern "C" int hitl_set_scans(hitl_ctx* ctx, uint32_t n_poses, const uint32_t* o
   const bool same_partition = ctx->n_poses == n_poses && n_poses > 0 && ctx->h_off.size() == (size_t)n_poses + 1 &&
                               memcmp(ctx->h_off.data(), off, sizeof(uint32_t) * ((size_t)n_poses + 1)) == 0 && !ctx->h_tile_scan.empty();
   // ---- commit ----
-  ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false;
+  ctx->have_trees = false; ctx->have_stf = false; ctx->have_world = false; ctx->em_boxes_valid = false;
   // Residual blocks registered for the previous map carry pose / point indices that were range-checked against IT: they must be
   // registered again (hitl_eval / hitl_normal_eq would otherwise index the new, possibly smaller, map with stale indices).
   ctx->nb_odo = ctx->nb_human = ctx->nb_stf = ctx->nb_p2lg = ctx->nb_p2l = 0; ctx->stf_from_search = false;

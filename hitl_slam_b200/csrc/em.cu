@@ -64,21 +64,98 @@ constexpr int kEmChunk = kEmThreads * kEmPerThread;   // 2048 points per CTA ste
 // chunk state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = value
 constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStMask = 3ull << 62;
 
+// Stroke of a chained round (hitl_em_refit_chain): the four floats the previous round's fit left on the device.  Same operations,
+// same order and same roundings as the host's make_seg (no contraction on either side), so a chained round sees the bits a host
+// round trip would have produced.
+__device__ __forceinline__ Seg seg_from_device(const float* __restrict__ s) {
+  Seg o;
+  o.p0x = s[0]; o.p0y = s[1]; o.p1x = s[2]; o.p1y = s[3];
+  const float dx = fsub(s[2], s[0]), dy = fsub(s[3], s[1]);
+  const float z = dot2(dx, dx, dy, dy);
+  if (z > 0.0f) { const float n = __fsqrt_rn(z); o.dirx = __fdiv_rn(dx, n); o.diry = __fdiv_rn(dy, n); }
+  else { o.dirx = dx; o.diry = dy; }
+  return o;
+}
+
+// The E-step's reach around a stroke, as a box: distance_to_line_segment() measures from p0 for t < 0, from p1 for t > 1 (t in
+// METRES along the unit direction — the reference's quirk, kept) and from the carrier line in between, so every point closer than
+// thr lies within thr of p0, of p1 or of the piece p0 .. p0 + 1 m * dir.  A chunk whose points' bounding box misses this box
+// (inflated by thr and a float-rounding margin far above the few ulps the distance evaluation can lose) has no inlier.
+// ok = false (degenerate or non-finite stroke: with dir = 0 EVERY point is at distance 0) disables the cull.
+struct ReachBox { float x0, y0, x1, y1; bool ok; };
+__device__ __forceinline__ ReachBox stroke_reach(const Seg& s, double thr) {
+  ReachBox b;
+  const float qx = s.p0x + s.dirx, qy = s.p0y + s.diry;
+  const float len2 = s.dirx * s.dirx + s.diry * s.diry;
+  const float lox = fminf(fminf(s.p0x, s.p1x), qx), hix = fmaxf(fmaxf(s.p0x, s.p1x), qx);
+  const float loy = fminf(fminf(s.p0y, s.p1y), qy), hiy = fmaxf(fmaxf(s.p0y, s.p1y), qy);
+  const float big = fmaxf(fmaxf(fabsf(lox), fabsf(hix)), fmaxf(fabsf(loy), fabsf(hiy)));
+  const float m = (float)thr + 1e-3f + 1e-5f * big;
+  b.x0 = lox - m; b.y0 = loy - m; b.x1 = hix + m; b.y1 = hiy + m;
+  b.ok = len2 > 0.5f && len2 < 2.0f && thr >= 0.0 && thr < 1e6 && isfinite(b.x0) && isfinite(b.y0) && isfinite(b.x1) && isfinite(b.y1);
+  return b;
+}
+
+// Chunk look-back of the ordered compaction, by the 32 lanes of warp 0 together: publishes this chunk's count, returns (on every
+// lane) the number of inliers before the chunk.  All chunks of a wave publish their aggregate at about the same moment, so a
+// single thread walking back one predecessor per L2 round trip needs ~sqrt(2 * chunk) trips before it meets an inclusive prefix;
+// the warp inspects 32 predecessors per trip.  Chunks are taken by ticket, so every predecessor is already running: no deadlock.
+__device__ __forceinline__ unsigned long long em_chunk_prefix(unsigned long long* state, uint32_t chunk, uint32_t block_total, uint32_t lane) {
+  if (chunk == 0) {
+    if (lane == 0) atomicExch(&state[0], kStPre | block_total);
+    return 0;
+  }
+  if (lane == 0) atomicExch(&state[chunk], kStAgg | block_total);
+  unsigned long long prefix = 0;
+  for (int64_t hi = (int64_t)chunk - 1;; hi -= 32) {
+    const int64_t c = hi - (int64_t)lane;
+    unsigned long long v = kStPre;                                       // before chunk 0: an empty inclusive prefix
+    if (c >= 0) do { v = atomicAdd(&state[c], 0ull); } while ((v & kStMask) == 0);
+    const uint32_t pre = __ballot_sync(0xffffffffu, (v & kStMask) == kStPre);
+    const uint32_t first = pre ? (uint32_t)(__ffs(pre) - 1) : 31u;       // nearest predecessor that already knows its inclusive prefix
+    unsigned long long val = lane <= first ? (v & ~kStMask) : 0ull;
+    for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    prefix += val;
+    if (pre) break;
+  }
+  if (lane == 0) atomicExch(&state[chunk], kStPre | (prefix + block_total));
+  return prefix;
+}
+
+// box_mode: 0 = plain pass; 1 = plain pass that also records every chunk's bounding box in `boxes`; 2 = chunks whose recorded box
+// misses the stroke's reach are counted as empty without being read (the boxes belong to the resident world clouds).
+template <int box_mode>
 __global__ void __launch_bounds__(kEmThreads) em_inliers_kernel(const float2* __restrict__ world, const uint32_t* __restrict__ off,
-                                                                uint32_t n_poses, uint64_t n_points, Seg seg, double thr,
-                                                                unsigned long long* state, uint32_t* ticket, uint64_t cap,
+                                                                uint32_t n_poses, uint64_t n_points, Seg seg_arg, const float* __restrict__ seg_dev,
+                                                                double thr, unsigned long long* state, uint32_t* ticket, uint64_t cap,
                                                                 uint32_t* __restrict__ out_pose, uint32_t* __restrict__ out_idx,
-                                                                float2* __restrict__ out_xy, unsigned long long* total) {
+                                                                float2* __restrict__ out_xy, unsigned long long* total, float4* boxes) {
   __shared__ uint32_t s_chunk;
   __shared__ uint32_t s_warp[kEmThreads / 32];
+  __shared__ float s_box[4][kEmThreads / 32];
   __shared__ unsigned long long s_prefix;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t n_chunks = (uint32_t)((n_points + kEmChunk - 1) / kEmChunk);
+  const Seg seg = seg_dev ? seg_from_device(seg_dev) : seg_arg;
+  ReachBox reach;
+  reach.ok = false;
+  if (box_mode == 2) reach = stroke_reach(seg, thr);
   for (;;) {
     if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t chunk = s_chunk;
     if (chunk >= n_chunks) return;
+    if (reach.ok) {
+      const float4 b = boxes[chunk];                       // (min x, min y, max x, max y) of the chunk's points
+      if (b.x > reach.x1 || b.z < reach.x0 || b.y > reach.y1 || b.w < reach.y0) {
+        if (w == 0) {
+          const unsigned long long prefix = em_chunk_prefix(state, chunk, 0u, lane);
+          if (lane == 0 && chunk == n_chunks - 1) *total = prefix;
+        }
+        __syncthreads();   // s_chunk reuse
+        continue;
+      }
+    }
     // thread owns 8 consecutive points: keeps (pose, idx) order inside the thread, lanes ascending
     const uint64_t base = (uint64_t)chunk * kEmChunk + (uint64_t)threadIdx.x * kEmPerThread;
     float2 p[kEmPerThread];
@@ -101,27 +178,34 @@ __global__ void __launch_bounds__(kEmThreads) em_inliers_kernel(const float2* __
     uint32_t x = cnt;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
     if (lane == 31) s_warp[w] = x;
+    if (box_mode == 1) {
+      // bounding box of the chunk's real points (the tail padding is excluded; fminf / fmaxf drop NaNs, which are never inliers)
+      float bx0 = FLT_MAX, by0 = FLT_MAX, bx1 = -FLT_MAX, by1 = -FLT_MAX;
+#pragma unroll
+      for (int q = 0; q < kEmPerThread; ++q)
+        if (base + q < n_points) { bx0 = fminf(bx0, p[q].x); by0 = fminf(by0, p[q].y); bx1 = fmaxf(bx1, p[q].x); by1 = fmaxf(by1, p[q].y); }
+      for (int o = 16; o; o >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+      }
+      if (lane == 0) { s_box[0][w] = bx0; s_box[1][w] = by0; s_box[2][w] = bx1; s_box[3][w] = by1; }
+    }
     __syncthreads();
     uint32_t wbase = 0, block_total = 0;
     for (int q = 0; q < kEmThreads / 32; ++q) { const uint32_t v = s_warp[q]; if (q < (int)w) wbase += v; block_total += v; }
     const uint32_t excl = wbase + x - cnt;
     // publish aggregate, look back for the exclusive prefix of this chunk
-    if (threadIdx.x == 0) {
-      unsigned long long prefix = 0;
-      if (chunk == 0) {
-        atomicExch(&state[0], kStPre | block_total);
-      } else {
-        atomicExch(&state[chunk], kStAgg | block_total);
-        for (int64_t c = (int64_t)chunk - 1; c >= 0; --c) {
-          unsigned long long v;
-          do { v = atomicAdd(&state[c], 0ull); } while ((v & kStMask) == 0);
-          prefix += v & ~kStMask;
-          if ((v & kStMask) == kStPre) break;
+    if (w == 0) {
+      const unsigned long long prefix = em_chunk_prefix(state, chunk, block_total, lane);
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (chunk == n_chunks - 1) *total = prefix + block_total;
+        if (box_mode == 1) {
+          float4 b = make_float4(s_box[0][0], s_box[1][0], s_box[2][0], s_box[3][0]);
+          for (int q = 1; q < kEmThreads / 32; ++q) { b.x = fminf(b.x, s_box[0][q]); b.y = fminf(b.y, s_box[1][q]); b.z = fmaxf(b.z, s_box[2][q]); b.w = fmaxf(b.w, s_box[3][q]); }
+          boxes[chunk] = b;
         }
-        atomicExch(&state[chunk], kStPre | (prefix + block_total));
       }
-      s_prefix = prefix;
-      if (chunk == n_chunks - 1) *total = prefix + block_total;
     }
     __syncthreads();
     unsigned long long o = s_prefix + excl;
@@ -177,15 +261,22 @@ __device__ __forceinline__ void seg_angle_residual(double px, double py, double 
 }
 
 __global__ void __launch_bounds__(kFitThreads) em_fit_kernel(const float2* __restrict__ xy, const unsigned long long* __restrict__ n_ptr, double p1x, double p1y,
-                                                             double p2x, double p2y, int max_iterations, double* partial /* 2 x gridDim.x x 3 */,
+                                                             double p2x, double p2y, const float* __restrict__ seg_dev /* chained round: the stroke, else NULL */,
+                                                             int max_iterations, double* partial /* 2 x gridDim.x x 3 */,
                                                              unsigned int* barrier /* 2 words, zero on entry */, FitResult* out) {
   __shared__ double s_red[3][kFitThreads / 32];
   __shared__ FitSums s_tot;
+  if (seg_dev) { p1x = (double)seg_dev[0]; p1y = (double)seg_dev[1]; p2x = (double)seg_dev[2]; p2y = (double)seg_dev[3]; }
   const unsigned long long n = *n_ptr;
   const double cmx = (p1x + p2x) / 2.0, cmy = (p1y + p2y) / 2.0;
   const double hy = sqrt((p1x - p2x) * (p1x - p2x) + (p1y - p2y) * (p1y - p2y));
   const double len = hy / 2.0;
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, G = gridDim.x;
+  // CTAs that take part: one per 1024 inliers (4 per thread), at most the grid.  A stroke on one wall collects a few thousand
+  // points; with every CTA of the grid at the barrier and in the partial sums, each evaluation would pay for 64 arrivals.
+  // The rest leave before touching the barrier; n is the same on every CTA, so all agree.
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t G = (uint32_t)min((unsigned long long)gridDim.x, max(1ull, (n + 1023ull) / 1024ull));
+  if (blockIdx.x >= G) return;
   uint32_t n_eval = 0, barrier_goal = 0;
 
   // grid barrier (all CTAs are co-resident: the launch is cooperative and G <= #SMs): arrival counter, monotone goal
@@ -195,7 +286,7 @@ __global__ void __launch_bounds__(kFitThreads) em_fit_kernel(const float2* __res
       barrier_goal += G;
       __threadfence();
       atomicAdd(barrier, 1u);
-      while (atomicAdd(barrier, 0u) < barrier_goal) { }
+      while (*(volatile unsigned int*)barrier < barrier_goal) { }
       __threadfence();
     }
     __syncthreads();
@@ -221,11 +312,13 @@ __global__ void __launch_bounds__(kFitThreads) em_fit_kernel(const float2* __res
       mine[0] = a; mine[1] = b; mine[2] = c;
     }
     grid_sync();
-    if (threadIdx.x == 0) {
+    if (w == 0) {
+      // the same fixed order on every CTA: lane q adds the partials q, q + 32, ..., then one butterfly
       const volatile double* all = partial + (size_t)(n_eval & 1u) * G * 3;
       double a = 0.0, b = 0.0, c = 0.0;
-      for (uint32_t q = 0; q < G; ++q) { a += all[3 * q]; b += all[3 * q + 1]; c += all[3 * q + 2]; }
-      s_tot.rr = a; s_tot.jr = b; s_tot.jj = c;
+      for (uint32_t q = lane; q < G; q += 32) { a += all[3 * q]; b += all[3 * q + 1]; c += all[3 * q + 2]; }
+      for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+      if (lane == 0) { s_tot.rr = a; s_tot.jr = b; s_tot.jj = c; }
     }
     __syncthreads();
     const FitSums t = s_tot;
@@ -444,6 +537,7 @@ extern "C" int hitl_world_transform(hitl_ctx* ctx, const float* poses_xyt, float
   if (ctx->h_off.empty()) return fail(ctx, HITL_ERR_STATE, "hitl_world_transform: scans not set");
   if (!poses_xyt && ctx->n_poses) return fail(ctx, HITL_ERR_ARG, "hitl_world_transform: null poses");
   HITL_CUDA(ctx->d_world.ensure(ctx->n_points)); HITL_CUDA(ctx->d_poses_f.ensure(3 * (size_t)ctx->n_poses));
+  ctx->em_boxes_valid = false;
   if (ctx->n_poses) {
     HITL_CUDA(cudaMemcpyAsync(ctx->d_poses_f.p, poses_xyt, 12 * (size_t)ctx->n_poses, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
@@ -467,7 +561,7 @@ extern "C" int hitl_set_world_clouds(hitl_ctx* ctx, const float* world_xy) {
   HITL_CUDA(ctx->d_world.ensure(ctx->n_points));
   if (ctx->n_points) HITL_CUDA(cudaMemcpyAsync(ctx->d_world.p, world_xy, 8 * ctx->n_points, cudaMemcpyHostToDevice, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->have_world = true;
+  ctx->have_world = true; ctx->em_boxes_valid = false;
   return HITL_OK;
 }
 
@@ -485,6 +579,26 @@ static void make_seg2(const float s[4], Seg2* o) {
   o->dd = o->dx * o->dx + o->dy * o->dy;
 }
 
+// One E-step launch on the context's stream.  `state`: n_chunks look-back words followed by the inlier total, `ticket`: one word;
+// both zero when the kernel starts.  seg_dev != NULL: the stroke is read from the device (a chained round), `s` is ignored.
+// The first E-step after the world clouds changed also records the chunks' bounding boxes; the later ones skip the chunks
+// out of the stroke's reach.
+static int launch_em_inliers(hitl_ctx* ctx, const Seg& s, const float* seg_dev, double thr, unsigned long long* state, uint32_t* ticket, uint64_t dcap,
+                             uint32_t* out_pose, uint32_t* out_idx, float2* out_xy) {
+  const uint32_t n_chunks = (uint32_t)((ctx->n_points + kEmChunk - 1) / kEmChunk);
+  int mode = 0;
+  if (ctx->em_cull) { HITL_CUDA(ctx->d_em_box.ensure(n_chunks)); mode = ctx->em_boxes_valid ? 2 : 1; }
+  const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
+  auto kernel = mode == 2 ? em_inliers_kernel<2> : mode == 1 ? em_inliers_kernel<1> : em_inliers_kernel<0>;
+  HITL_KERNEL_BEGIN(HITL_K_EM_INLIERS);
+  kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, seg_dev, thr, state, ticket, dcap, out_pose, out_idx,
+                                               out_xy, state + n_chunks, ctx->d_em_box.p);
+  HITL_KERNEL_END(HITL_K_EM_INLIERS);
+  HITL_LAUNCH_CHECK("em_inliers_kernel");
+  if (mode == 1) ctx->em_boxes_valid = true;
+  return HITL_OK;
+}
+
 extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double threshold, uint64_t cap, uint32_t* out_pose, uint32_t* out_idx,
                                float* out_xy, uint64_t* n_out) {
   if (!ctx) return HITL_ERR_ARG;
@@ -496,20 +610,14 @@ extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double thresho
   const bool want = out_pose && out_idx && cap;
   const uint64_t dcap = want ? std::min<uint64_t>(cap, ctx->n_points) : 0;
   const uint32_t n_chunks = (uint32_t)((ctx->n_points + kEmChunk - 1) / kEmChunk);
-  HITL_CUDA(ctx->d_scan_state.ensure(n_chunks + 1)); HITL_CUDA(ctx->d_ticket.ensure(1));
+  HITL_CUDA(ctx->d_scan_state.ensure(n_chunks + 1)); HITL_CUDA(ctx->d_ticket.ensure(4));
   if (want) { HITL_CUDA(ctx->d_em_pose.ensure(dcap)); HITL_CUDA(ctx->d_em_idx.ensure(dcap)); if (out_xy) HITL_CUDA(ctx->d_em_xy.ensure(dcap)); }
   HITL_CUDA(cudaMemsetAsync(ctx->d_scan_state.p, 0, 8 * (size_t)(n_chunks + 1), ctx->stream));
   HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 4, ctx->stream));
   Seg s; make_seg(seg, &s);
-  const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
-  HITL_KERNEL_BEGIN(HITL_K_EM_INLIERS);
-  em_inliers_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, threshold,
-                                                          (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap,
-                                                          want ? ctx->d_em_pose.p : nullptr, want ? ctx->d_em_idx.p : nullptr,
-                                                          (want && out_xy) ? ctx->d_em_xy.p : nullptr,
-                                                          (unsigned long long*)ctx->d_scan_state.p + n_chunks);
-  HITL_KERNEL_END(HITL_K_EM_INLIERS);
-  HITL_LAUNCH_CHECK("em_inliers_kernel");
+  if (int rc = launch_em_inliers(ctx, s, nullptr, threshold, (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap, want ? ctx->d_em_pose.p : nullptr,
+                                 want ? ctx->d_em_idx.p : nullptr, (want && out_xy) ? ctx->d_em_xy.p : nullptr))
+    return rc;
   HITL_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_scan_state.p + n_chunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
   const uint64_t n = ctx->h_pinned[0];
@@ -525,57 +633,88 @@ extern "C" int hitl_em_inliers(hitl_ctx* ctx, const float seg[4], double thresho
   return HITL_OK;
 }
 
-extern "C" int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4], hitl_em_fit_info* info) {
+// EM rounds chained on the device.  For every stroke, round r's E-step reads the stroke that round r-1's fit left in device memory
+// (round 0 reads the caller's), and its M-step refits it; all n_strokes x rounds (E-step, M-step) pairs are enqueued back to back
+// and the host waits ONCE, for all the results.  Each round is exactly the round hitl_em_refit would run on the previous round's
+// output, so a caller that applies its convergence rule to the returned sequence and ignores the rounds past convergence gets
+// the bits of the one-call-per-round loop (EMinput.cpp:107-147) without a host round trip per round.
+constexpr uint32_t kChainMaxStrokes = 2, kChainMaxRounds = 4;
+static_assert(sizeof(FitResult) == 64, "FitResult slots are copied back as 64-byte records");
+extern "C" int hitl_em_refit_chain(hitl_ctx* ctx, uint32_t n_strokes, const float* segs_in, double inlier_threshold, int32_t max_iterations, uint32_t rounds,
+                                   float* segs_out, hitl_em_fit_info* info) {
   if (!ctx) return HITL_ERR_ARG;
   HITL_DEVICE(ctx);
   if (!ctx->have_world) return fail(ctx, HITL_ERR_STATE, "hitl_em_refit: world clouds not set");
-  if (!seg_in || !seg_out || max_iterations < 0) return fail(ctx, HITL_ERR_ARG, "hitl_em_refit: bad argument");
-  hitl_em_fit_info inf; memset(&inf, 0, sizeof(inf));
-  for (int q = 0; q < 4; ++q) seg_out[q] = seg_in[q];
-  if (ctx->n_points == 0) { if (info) *info = inf; return HITL_OK; }
-  // E-step: the inliers' coordinates stay resident, in (pose, index) order (every point may be an inlier: the list cannot overflow)
+  if (!segs_in || !segs_out || max_iterations < 0 || n_strokes < 1 || n_strokes > kChainMaxStrokes || rounds < 1 || rounds > kChainMaxRounds)
+    return fail(ctx, HITL_ERR_ARG, "hitl_em_refit: bad argument");
+  const uint32_t L = n_strokes * rounds;                       // launches pairs; slot of (stroke s, round r) = r * n_strokes + s
+  for (uint32_t r = 0; r < rounds; ++r)
+    for (uint32_t q = 0; q < 4 * n_strokes; ++q) segs_out[4 * n_strokes * r + q] = segs_in[q];
+  if (info) memset(info, 0, sizeof(hitl_em_fit_info) * L);
+  if (ctx->n_points == 0) return HITL_OK;
+  // the inliers' coordinates stay resident, in (pose, index) order (every point may be an inlier: the list cannot overflow)
   const uint64_t dcap = ctx->n_points;
   const uint32_t n_chunks = (uint32_t)((ctx->n_points + kEmChunk - 1) / kEmChunk);
-  HITL_CUDA(ctx->d_scan_state.ensure(n_chunks + 1)); HITL_CUDA(ctx->d_ticket.ensure(4));
+  const size_t state_words = (size_t)n_chunks + 1;
+  HITL_CUDA(ctx->d_scan_state.ensure(state_words * L)); HITL_CUDA(ctx->d_ticket.ensure(4 * (size_t)L));
   HITL_CUDA(ctx->d_em_pose.ensure(dcap)); HITL_CUDA(ctx->d_em_idx.ensure(dcap)); HITL_CUDA(ctx->d_em_xy.ensure(dcap));
   const int fit_blocks = std::min(kFitMaxBlocks, ctx->sm_count);
-  HITL_CUDA(ctx->d_fit_partial.ensure(2 * (size_t)kFitMaxBlocks * 3)); HITL_CUDA(ctx->d_fit_out.ensure(sizeof(FitResult)));
+  HITL_CUDA(ctx->d_fit_partial.ensure(2 * (size_t)kFitMaxBlocks * 3)); HITL_CUDA(ctx->d_fit_out.ensure(sizeof(FitResult) * (size_t)L));
   HITL_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  HITL_CUDA(cudaMemsetAsync(ctx->d_scan_state.p, 0, 8 * (size_t)(n_chunks + 1), ctx->stream));
-  HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 16, ctx->stream));                      // word 0: E-step ticket, words 2-3: the fit's grid barrier
-  Seg s; make_seg(seg_in, &s);
-  const uint32_t grid = std::min<uint32_t>(n_chunks, (uint32_t)ctx->sm_count * 8);
-  HITL_KERNEL_BEGIN(HITL_K_EM_INLIERS);
-  em_inliers_kernel<<<grid, kEmThreads, 0, ctx->stream>>>(ctx->d_world.p, ctx->d_off.p, ctx->n_poses, ctx->n_points, s, inlier_threshold,
-                                                          (unsigned long long*)ctx->d_scan_state.p, ctx->d_ticket.p, dcap, ctx->d_em_pose.p, ctx->d_em_idx.p,
-                                                          ctx->d_em_xy.p, (unsigned long long*)ctx->d_scan_state.p + n_chunks);
-  HITL_KERNEL_END(HITL_K_EM_INLIERS);
-  HITL_LAUNCH_CHECK("em_inliers_kernel");
-  // M-step: the whole LM loop in one cooperative launch (co-resident CTAs, software grid barrier)
-  const float2* d_xy = ctx->d_em_xy.p;
-  const unsigned long long* d_n = (const unsigned long long*)ctx->d_scan_state.p + n_chunks;
-  double p1x = seg_in[0], p1y = seg_in[1], p2x = seg_in[2], p2y = seg_in[3];
-  int iters = max_iterations;
-  double* d_partial = ctx->d_fit_partial.p;
-  unsigned int* d_barrier = ctx->d_ticket.p + 2;
-  FitResult* d_out = reinterpret_cast<FitResult*>(ctx->d_fit_out.p);
-  void* args[] = {(void*)&d_xy, (void*)&d_n, (void*)&p1x, (void*)&p1y, (void*)&p2x, (void*)&p2y, (void*)&iters, (void*)&d_partial, (void*)&d_barrier, (void*)&d_out};
-  HITL_KERNEL_BEGIN(HITL_K_EM_FIT);
-  HITL_CUDA(cudaLaunchCooperativeKernel((const void*)em_fit_kernel, dim3(fit_blocks), dim3(kFitThreads), args, 0, ctx->stream));
-  HITL_KERNEL_END(HITL_K_EM_FIT);
-  HITL_LAUNCH_CHECK("em_fit_kernel");
+  HITL_CUDA(cudaMemsetAsync(ctx->d_scan_state.p, 0, 8 * state_words * L, ctx->stream));
+  HITL_CUDA(cudaMemsetAsync(ctx->d_ticket.p, 0, 16 * (size_t)L, ctx->stream));      // per launch pair: word 0 E-step ticket, words 2-3 the fit's grid barrier
+  FitResult* d_res = reinterpret_cast<FitResult*>(ctx->d_fit_out.p);
+  for (uint32_t sk = 0; sk < n_strokes; ++sk)
+    for (uint32_t r = 0; r < rounds; ++r) {
+      const uint32_t slot = r * n_strokes + sk;
+      unsigned long long* state = (unsigned long long*)ctx->d_scan_state.p + state_words * slot;
+      uint32_t* ticket = ctx->d_ticket.p + 4 * (size_t)slot;
+      const float* seg_dev = r ? d_res[slot - n_strokes].seg : nullptr;
+      Seg s; make_seg(segs_in + 4 * sk, &s);
+      if (int rc = launch_em_inliers(ctx, s, seg_dev, inlier_threshold, state, ticket, dcap, ctx->d_em_pose.p, ctx->d_em_idx.p, ctx->d_em_xy.p)) return rc;
+      // M-step: the whole LM loop in one cooperative launch (co-resident CTAs, software grid barrier)
+      const float2* d_xy = ctx->d_em_xy.p;
+      const unsigned long long* d_n = state + n_chunks;
+      double p1x = segs_in[4 * sk], p1y = segs_in[4 * sk + 1], p2x = segs_in[4 * sk + 2], p2y = segs_in[4 * sk + 3];
+      int iters = max_iterations;
+      double* d_partial = ctx->d_fit_partial.p;
+      unsigned int* d_barrier = ticket + 2;
+      FitResult* d_out = d_res + slot;
+      void* args[] = {(void*)&d_xy, (void*)&d_n, (void*)&p1x, (void*)&p1y, (void*)&p2x, (void*)&p2y, (void*)&seg_dev, (void*)&iters, (void*)&d_partial,
+                      (void*)&d_barrier, (void*)&d_out};
+      HITL_KERNEL_BEGIN(HITL_K_EM_FIT);
+      HITL_CUDA(cudaLaunchCooperativeKernel((const void*)em_fit_kernel, dim3(fit_blocks), dim3(kFitThreads), args, 0, ctx->stream));
+      HITL_KERNEL_END(HITL_K_EM_FIT);
+      HITL_LAUNCH_CHECK("em_fit_kernel");
+    }
   HITL_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  static_assert(sizeof(FitResult) * kChainMaxStrokes * kChainMaxRounds <= 64 * sizeof(uint64_t), "h_pinned holds every FitResult of a chain");
   FitResult* h = reinterpret_cast<FitResult*>(ctx->h_pinned);
-  HITL_CUDA(cudaMemcpyAsync(h, d_out, sizeof(FitResult), cudaMemcpyDeviceToHost, ctx->stream));
+  HITL_CUDA(cudaMemcpyAsync(h, d_res, sizeof(FitResult) * (size_t)L, cudaMemcpyDeviceToHost, ctx->stream));
   HITL_CUDA(cudaStreamSynchronize(ctx->stream));
-  inf.theta = h->theta; inf.initial_cost = h->cost0; inf.final_cost = h->cost; inf.n_inliers = h->n; inf.iterations = h->iterations;
-  inf.evaluations = h->evaluations; inf.termination = h->termination;
-  HITL_CUDA(cudaEventElapsedTime(&inf.ms, ctx->ev[0], ctx->ev[1]));
-  if (h->n) for (int q = 0; q < 4; ++q) seg_out[q] = h->seg[q];
-  else {       // no inliers: the reference skips the solve and rebuilds the stroke from theta_0 (EMinput.cpp:178-190)
-    for (int q = 0; q < 4; ++q) seg_out[q] = h->seg[q];
+  float ms = 0.f;
+  HITL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  for (uint32_t slot = 0; slot < L; ++slot) {
+    // no inliers: the fit kernel skips the solve and rebuilds the stroke from theta_0, as the reference does (EMinput.cpp:178-190)
+    for (int q = 0; q < 4; ++q) segs_out[4 * slot + q] = h[slot].seg[q];
+    if (info) {
+      hitl_em_fit_info& inf = info[slot];
+      inf.theta = h[slot].theta; inf.initial_cost = h[slot].cost0; inf.final_cost = h[slot].cost; inf.n_inliers = h[slot].n; inf.iterations = h[slot].iterations;
+      inf.evaluations = h[slot].evaluations; inf.termination = h[slot].termination;
+      inf.ms = ms;                                            // device time of the whole chain, the same in every record
+    }
   }
-  if (info) *info = inf;
+  return HITL_OK;
+}
+
+extern "C" int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4], hitl_em_fit_info* info) {
+  return hitl_em_refit_chain(ctx, 1, seg_in, inlier_threshold, max_iterations, 1, seg_out, info);
+}
+
+extern "C" int hitl_debug_set_em_cull(hitl_ctx* ctx, int on) {
+  if (!ctx) return HITL_ERR_ARG;
+  ctx->em_cull = on != 0;
+  ctx->em_boxes_valid = false;
   return HITL_OK;
 }
 
@@ -609,6 +748,7 @@ extern "C" int hitl_em_assign(hitl_ctx* ctx, const float segs[8], double thresho
     em_sets_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_em_cnt[f].p, n, min_obs, ctx->d_em_setpose[f].p, (unsigned long long*)ctx->d_em_setoff[f].p,
                                                      slot_of_pose.p, (unsigned long long*)ctx->d_counters.p + 2 * f);
     HITL_LAUNCH_CHECK("em_sets_scan_kernel");
+    if (!obs[f]) continue;                 // the caller reads the observing poses only: the index lists are not assembled
     em_sets_gather_kernel<<<grid, threads, 0, ctx->stream>>>(slots[f].p, ctx->d_off.p, ctx->d_em_cnt[f].p, slot_of_pose.p,
                                                             (unsigned long long*)ctx->d_em_setoff[f].p, n, ctx->d_em_obs[f].p);
     HITL_LAUNCH_CHECK("em_sets_gather_kernel");

@@ -159,7 +159,10 @@ struct hitl_ctx {
   hitl::DevBuf<float> d_bp_poses, d_bp_rw, d_bp_tw;   // scratch of hitl_backprop_poses
   hitl::DevBuf<float2> d_bp_cs;
   hitl::DevBuf<double> d_fit_partial;    // per-CTA partial sums of the device M-step (two buffers)
-  hitl::DevBuf<uint8_t> d_fit_out;       // FitResult of the last hitl_em_refit
+  hitl::DevBuf<uint8_t> d_fit_out;       // FitResults of the last hitl_em_refit / hitl_em_refit_chain (one per launch)
+  hitl::DevBuf<float4> d_em_box;         // bounding box of every E-step chunk of the resident world clouds
+  bool em_boxes_valid = false;           // recorded by the first E-step after the world clouds changed, used by the later ones
+  bool em_cull = true;                   // hitl_debug_set_em_cull / HITL_EM_CULL=0: every E-step reads every chunk
 
   // ---- residual blocks ----
   uint64_t nb_odo = 0, nb_human = 0, nb_stf = 0, nb_p2lg = 0, nb_p2l = 0;

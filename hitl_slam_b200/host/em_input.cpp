@@ -96,6 +96,44 @@ std::vector<Vector2f> FitSegmentAngle(const double* p1, const double* p2, const 
 
 void EMInput::AutomaticEndpointAdjustment() {
   if (!world_clouds_resident_) UploadWorldClouds();
+  if (device_m_step_) {
+    // E-step AND M-step on the device (SegFitEM's LM runs on the resident inliers), the rounds of both strokes chained: the strokes
+    // are independent (each round reads its own stroke and the fixed world clouds), so their loops run side by side and the host
+    // waits once per device_chain_rounds_ rounds.  Each stroke's rounds are consumed in order under the reference's loop condition.
+    const double thresh = 0.05;
+    const size_t ns = std::min<size_t>(selected_points_.size() / 2, 2);
+    bool active[2] = {false, false};
+    for (size_t k = 0; k < ns; ++k) { em_rounds_[k] = 0; active[k] = max_em_rounds_ > 0; }
+    for (;;) {
+      uint32_t idx[2], na = 0;
+      int rounds = std::max(1, std::min(device_chain_rounds_, 4));
+      for (size_t k = 0; k < ns; ++k)
+        if (active[k]) { idx[na++] = (uint32_t)k; rounds = std::min(rounds, max_em_rounds_ - em_rounds_[k]); }
+      if (na == 0) break;
+      float in[8], out[4 * 2 * 4];
+      hitl_em_fit_info fi[2 * 4];
+      for (uint32_t a = 0; a < na; ++a) {
+        in[4 * a] = selected_points_[2 * idx[a]].x; in[4 * a + 1] = selected_points_[2 * idx[a]].y;
+        in[4 * a + 2] = selected_points_[2 * idx[a] + 1].x; in[4 * a + 3] = selected_points_[2 * idx[a] + 1].y;
+      }
+      check(hitl_em_refit_chain(ctx_, na, in, 0.03, 25, (uint32_t)rounds, out, fi), "hitl_em_refit_chain");
+      for (uint32_t a = 0; a < na; ++a) {
+        const size_t k = idx[a];
+        for (int r = 0; r < rounds && active[k]; ++r) {
+          const size_t slot = (size_t)r * na + a;
+          const Vector2f fit0(out[4 * slot], out[4 * slot + 1]), fit1(out[4 * slot + 2], out[4 * slot + 3]);
+          const double adjustment1 = norm(selected_points_[2 * k] - fit0), adjustment2 = norm(selected_points_[2 * k + 1] - fit1);
+          selected_points_[2 * k] = fit0;
+          selected_points_[2 * k + 1] = fit1;
+          em_inliers_[k] = fi[slot].n_inliers;
+          last_theta_[k] = fi[slot].theta;
+          ++em_rounds_[k];
+          active[k] = (adjustment1 > thresh || adjustment2 > thresh) && em_rounds_[k] < max_em_rounds_;
+        }
+      }
+    }
+    return;
+  }
   std::vector<float> xy;
   std::vector<uint32_t> in_pose, in_idx;
   std::vector<double> data;
@@ -106,21 +144,6 @@ void EMInput::AutomaticEndpointAdjustment() {
     while ((adjustment1 > thresh || adjustment2 > thresh) && em_rounds_[k] < max_em_rounds_) {
       // E-step on the device: every world point within 3 cm of the stroke, in (pose, index) order.
       const float seg[4] = {selected_points_[2 * k].x, selected_points_[2 * k].y, selected_points_[2 * k + 1].x, selected_points_[2 * k + 1].y};
-      if (device_m_step_) {
-        // ... and the M-step too: SegFitEM's LM runs on the resident inliers (hitl_em_refit); only the refit stroke comes back.
-        float out[4];
-        hitl_em_fit_info fi;
-        check(hitl_em_refit(ctx_, seg, 0.03, 25, out, &fi), "hitl_em_refit");
-        em_inliers_[k] = fi.n_inliers;
-        last_theta_[k] = fi.theta;
-        const std::vector<Vector2f> fit = {Vector2f(out[0], out[1]), Vector2f(out[2], out[3])};
-        adjustment1 = norm(selected_points_[2 * k] - fit[0]);
-        adjustment2 = norm(selected_points_[2 * k + 1] - fit[1]);
-        selected_points_[2 * k] = fit[0];
-        selected_points_[2 * k + 1] = fit[1];
-        ++em_rounds_[k];
-        continue;
-      }
       uint64_t n = 0;
       if (in_pose.empty()) { in_pose.resize(1 << 16); in_idx.resize(1 << 16); xy.resize(2 << 16); }
       int rc = hitl_em_inliers(ctx_, seg, 0.03, in_pose.size(), in_pose.data(), in_idx.data(), xy.data(), &n);

@@ -48,6 +48,9 @@ class EMInput {
   // M-step placement: true (default) = hitl_em_refit, E-step + SegFitEM's LM in one device call per round (nothing but 64 bytes crosses
   // PCIe); false = inliers copied back and FitSegmentAngle on the host LM (the checker: tests compare the two to 1e-9 in theta).
   bool device_m_step_ = true;
+  // Device M-step only: rounds enqueued per host wait (hitl_em_refit_chain, both strokes together).  The stopping rule is applied to
+  // the returned sequence, so a stroke that converges early simply ignores the extra rounds; 1 = one wait per round.
+  int device_chain_rounds_ = 2;
   // OrderAndFilterUserInput reads only the observing poses; true also copies every pose's index list back (EstablishObservationSets always does)
   bool fetch_observation_indices_ = false;
   double last_theta_[2] = {0, 0};    // fitted direction angle of each stroke's last M-step

@@ -434,6 +434,8 @@ int hitl_host_seg_fit_em_theta(const double p1[2], const double p2[2], const dou
 }
 // Selects where EMInput's M-step runs in this session: 1 = device (hitl_em_refit, default), 0 = host LM (the checker).
 int hitl_host_session_set_device_m_step(void* sp, int on) { static_cast<Session*>(sp)->em.device_m_step_ = on != 0; return 0; }
+// Device M-step: EM rounds enqueued per host wait (1..4; hitl_em_refit_chain).  1 = one wait per round and stroke pair.
+int hitl_host_session_set_em_chain_rounds(void* sp, int rounds) { static_cast<Session*>(sp)->em.device_chain_rounds_ = rounds < 1 ? 1 : (rounds > 4 ? 4 : rounds); return 0; }
 int hitl_host_seg_fit_em(const double p1[2], const double p2[2], const double* data, int size, float out4[4]) {
   try {
     const std::vector<Vector2f> fit = FitSegmentAngle(p1, p2, data, size);

@@ -14,6 +14,7 @@
  *   hitl_verify_input                     HitLSLAM::verifyUserInput                    human_in_the_loop_slam/HitLSLAM.cpp:218-243
  *   hitl_em_inliers                       E-step of EMInput::AutomaticEndpointAdjustment  human_in_the_loop_slam/EMinput.cpp:207-218
  *   hitl_em_refit                         one E-step + M-step round: the above + EMInput::SegFitEM / segDistResidualEM  EMinput.cpp:107-191
+ *   hitl_em_refit_chain                   the rounds of both strokes chained on the device  EMInput::AutomaticEndpointAdjustment EMinput.cpp:195-250
  *   hitl_em_assign                        EMInput::EstablishObservationSets EMinput.cpp:281-323
  *   hitl_set_*_blocks / hitl_eval         AutoDiffCostFunction<...>::Evaluate of the blocks added by
  *                                         AddSTFConstraints :539-559, AddOdometryConstraints :736-825,
@@ -194,6 +195,16 @@ typedef struct {
 } hitl_em_fit_info;
 int hitl_em_refit(hitl_ctx* ctx, const float seg_in[4], double inlier_threshold, int32_t max_iterations, float seg_out[4],
                   hitl_em_fit_info* info);
+/* `rounds` (1..4) EM rounds of `n_strokes` (1..2) independent strokes with ONE host wait: round r of a stroke runs hitl_em_refit's
+ * E-step + M-step on the stroke that round r-1 left in device memory (round 0: segs_in[4 * s ..]).  Results are indexed
+ * slot = r * n_strokes + s: segs_out[4 * slot ..], info[slot] (info may be NULL; info[].ms = device time of the whole chain).
+ * The loop of EMInput::AutomaticEndpointAdjustment (EMinput.cpp:195-250) stops a stroke once both endpoints moved <= 0.05 m;
+ * a caller applies that rule to the returned sequence and ignores the rounds past convergence — every round it keeps is bit for
+ * bit the round a one-call-per-round loop would have produced.  hitl_em_refit is the (1 stroke, 1 round) case.
+ * E-steps after the first on the same world clouds skip, unread, the 2048-point chunks whose bounding box lies out of the
+ * stroke's reach (exact: such a chunk has no inlier). */
+int hitl_em_refit_chain(hitl_ctx* ctx, uint32_t n_strokes, const float* segs_in, double inlier_threshold, int32_t max_iterations,
+                        uint32_t rounds, float* segs_out, hitl_em_fit_info* info);
 
 /* Observation sets of both strokes: segs = {a0, a1, b0, b1} as 8 floats.  A pose is kept for a
  * stroke when MORE than min_obs of its points are within threshold (reference: 5).
@@ -311,6 +322,8 @@ int hitl_debug_set_tiling(hitl_ctx* ctx, uint32_t max_len, int adaptive, uint32_
  * bit 2 SET additionally switches the tile-box vs scan cull off, e.g. 5);
  * the bitmaps are rebuilt by the next search.  Culling is result-preserving; parity tests compare the settings and disable_culling = 1. */
 int hitl_debug_set_fine_occupancy(hitl_ctx* ctx, int on);
+/* E-step chunk cull (see hitl_em_refit_chain): on = 0 makes every E-step read every chunk.  Result-preserving; parity tests compare. */
+int hitl_debug_set_em_cull(hitl_ctx* ctx, int on);
 /* Occupancy / register trade-off of the search kernel: 0 = 16 CTAs per SM (32 registers), 1 = 12 (40), 2 = 10 (48);
  * smem_carveout_pct = preferred shared-memory carve-out of the unified L1 (percent, -1 = driver default). */
 int hitl_debug_set_search_variant(hitl_ctx* ctx, int variant, int smem_carveout_pct);

@@ -506,6 +506,85 @@ def test_em_inliers_and_assign_bit_exact(gpu, oracle, maps, name):
         assert np.array_equal(gp, gold["inl_pose"]) and np.array_equal(gi, gold["inl_idx"])
 
 
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_em_chunk_cull_is_result_preserving(gpu, oracle, maps, name):
+    """E-steps after the first one on the same world clouds skip the 2048-point chunks whose bounding box is out of the stroke's
+    reach.  The reach follows the reference's distance function, quirk included (the projection parameter is compared with 1.0 in
+    METRES: a stroke shorter than 1 m collects the carrier line's points up to 1 m from its first endpoint, a longer one loses the
+    points past 1 m unless they are near the far endpoint).  Oracle inliers == culled == unculled, for short / long / far strokes."""
+    from hitl_slam_b200 import synth
+    g = maps(name)
+    load_map(gpu, g)
+    world = gpu.world_transform(g["poses"])
+    a, b = synth.make_strokes(g)[:2]
+    d = (b - a) / max(float(np.linalg.norm(b - a)), 1e-6)
+    rng = np.random.default_rng(11)
+    segs = [np.concatenate([a, a + 0.25 * d]), np.concatenate([a, a + 0.999 * d]), np.concatenate([a, a + 1.001 * d]), np.concatenate([a, a + 4.0 * d]),
+            np.concatenate([a + 4.0 * d, a]), np.concatenate([a, a - 0.5 * d]), np.array([1e4, 1e4, 1e4 + 1, 1e4], np.float32),
+            np.array([np.nan, 0, 1, 1], np.float32), np.concatenate([a, a])]
+    lo, hi = world.min(axis=0), world.max(axis=0)
+    for _ in range(12):
+        p = lo + rng.random(2) * (hi - lo)
+        segs.append(np.concatenate([p, p + rng.normal(size=2) * rng.choice([0.2, 1.0, 5.0])]))
+    for thr in (0.03, 0.4):
+        for seg in segs:
+            seg = np.asarray(seg, np.float32)
+            op, oi = oracle.em_inliers(g["offsets"], world, seg, thr=thr)
+            gpu.debug_set_em_cull(True)
+            gpu.em_inliers(seg, thr=thr, fetch=False)                      # (re)records the chunk boxes
+            cp, ci, cxy = gpu.em_inliers(seg, thr=thr)                     # culled pass
+            gpu.debug_set_em_cull(False)
+            up, ui, uxy = gpu.em_inliers(seg, thr=thr)
+            assert np.array_equal(op, up) and np.array_equal(oi, ui), seg
+            assert np.array_equal(cp, up) and np.array_equal(ci, ui) and np.array_equal(cxy, uxy), seg
+    gpu.debug_set_em_cull(True)
+    # new world clouds invalidate the boxes: the same strokes on shifted clouds
+    shifted = world + np.float32(3.0)
+    gpu.set_world_clouds(shifted)
+    for seg in segs[:6]:
+        seg = np.asarray(seg, np.float32)
+        op, oi = oracle.em_inliers(g["offsets"], shifted, seg + np.float32(3.0))
+        for _ in range(2):
+            cp, ci, _ = gpu.em_inliers(seg + np.float32(3.0))
+            assert np.array_equal(op, cp) and np.array_equal(oi, ci)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_em_rounds_chained_on_the_device_equal_one_call_per_round(gpu, maps, name):
+    """hitl_em_refit_chain: round r of a stroke reads the stroke round r-1 left in device memory.  Every returned round is bit for
+    bit what hitl_em_refit returns when the host feeds the previous result back — for one stroke and for two side by side."""
+    from hitl_slam_b200 import synth
+    g = maps(name, drift_xy=0.012, drift_th=0.004)
+    load_map(gpu, g)
+    gpu.world_transform(g["poses"])
+    strokes = synth.pick_strokes(g, min_sep=0.045).astype(np.float32).reshape(2, 4)
+    rng = np.random.default_rng(5)
+    for case in (strokes, strokes + rng.normal(size=(2, 4)).astype(np.float32) * 0.02, np.array([[500, 500, 501, 500.5], strokes[0]], np.float32)):
+        want, winfo = [], []
+        for seg in case:                                            # the one-call-per-round loop, 4 rounds regardless of convergence
+            cur, rows, infos = seg.copy(), [], []
+            for _ in range(4):
+                cur, info = gpu.em_refit(cur)
+                rows.append(cur.copy()); infos.append(info)
+            want.append(rows); winfo.append(infos)
+        for cull in (True, False):
+            gpu.debug_set_em_cull(cull)
+            for rounds in (1, 2, 4):
+                segs, infos = gpu.em_refit_chain(case, rounds=rounds)
+                for r in range(rounds):
+                    for q in range(2):
+                        assert np.array_equal(segs[r, q].view(np.uint32), want[q][r].view(np.uint32)), (cull, rounds, r, q)
+                        for key in ("theta", "initial_cost", "final_cost", "n_inliers", "iterations", "evaluations", "termination"):
+                            assert infos[r][q][key] == winfo[q][r][key], (key, cull, rounds, r, q)
+            one, _ = gpu.em_refit_chain(case[1:], rounds=3)              # a single stroke
+            assert all(np.array_equal(one[r, 0], want[1][r]) for r in range(3))
+        gpu.debug_set_em_cull(True)
+    with pytest.raises(Exception):
+        gpu.em_refit_chain(case, rounds=5)
+    with pytest.raises(Exception):
+        gpu.em_refit_chain(np.zeros((3, 4), np.float32), rounds=1)
+
+
 def test_em_with_empty_scans(gpu, oracle):
     rng = np.random.default_rng(4)
     off, pts, nrm = random_scans(rng, 40, 1, 90, empty=(0, 3, 4, 39))

@@ -295,6 +295,13 @@ def test_device_m_step_matches_the_host_lm(session, gpu, host, maps, name):
     assert got["rounds"] == want["rounds"] and got["backprop"] == want["backprop"]
     assert np.array_equal(got["corrected"], want["corrected"]) and np.array_equal(got["anchor"], want["anchor"])
     assert np.abs(got["segs"] - want["segs"]).max() <= 1e-6
+    # rounds chained on the device (both strokes, several rounds per host wait): the same bits as one wait per round
+    for rounds in (1, 4):
+        session.set_em_chain_rounds(rounds)
+        other = session.em_run(4, strokes)
+        assert np.array_equal(other["segs"].view(np.uint32), got["segs"].view(np.uint32)) and other["rounds"] == got["rounds"]
+        assert np.array_equal(other["corrected"], got["corrected"]) and np.array_equal(other["anchor"], got["anchor"])
+    session.set_em_chain_rounds(2)
 
 
 def test_replayed_colinear_correction_end_to_end(session, host, oracle, maps, tmp_path):
