@@ -568,8 +568,10 @@ def main():
         e2e_parts.append([(b - a) * 1e3 for a, b in zip(t[:-1], t[1:])])
         return out["pair_i"].nbytes * 2 + out["pair_off"].nbytes + out["k"].nbytes * 2 + ev["r_stf"].nbytes + ev["J_stf"].nbytes + ev["r_odometry"].nbytes + ev["J_odometry"].nbytes
 
-    if e2e_steps:
-        e2e_step()                                 # warm-up (first-touch of the result buffers)
+    e2e_warmup = max(1, min(args.warmup, 5)) if e2e_steps else 0
+    for _ in range(e2e_warmup):
+        e2e_step()                                 # warm-up: first touch of the result buffers; the first calls on a freshly uploaded map may re-tile
+    e2e_parts = e2e_parts[-1:]                     # parts[0] = last warm-up step, parts[1:] = the timed steps
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -597,7 +599,8 @@ def main():
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
     pm = np.median(np.array(e2e_parts[1:1 + e2e_steps]), axis=0) if e2e_steps else np.zeros(5)
     e2e = {"value": evals / float(te.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
+           "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps, "warmup": e2e_warmup,
+           "steps_ms": [float(sum(p)) for p in e2e_parts[1:1 + e2e_steps]],
            "parts_ms": {"set_scans": float(pm[0]), "set_kdtrees": float(pm[1]), "find_stf": float(pm[2]), "get_stf": float(pm[3]), "blocks_eval_fetch": float(pm[4])},
            "map_resident": {"value": evals / float(tr.item()) / 1e6, "ms_per_step": float(tr.item()) * 1e3, "h2d_bytes_per_step": int(h_poses.nbytes * 2 + h_odo.nbytes), "d2h_bytes_per_step": int(d2h),
                             "what": "the same step when scans + trees are already resident (uploaded once per session): poses up, correspondences + residuals + Jacobians down"},

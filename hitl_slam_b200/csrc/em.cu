@@ -305,6 +305,20 @@ __global__ void __launch_bounds__(kFitThreads) em_fit_kernel(const float2* __res
     for (int o = 16; o; o >>= 1) { rr += __shfl_xor_sync(0xffffffffu, rr, o); jr += __shfl_xor_sync(0xffffffffu, jr, o); jj += __shfl_xor_sync(0xffffffffu, jj, o); }
     if (lane == 0) { s_red[0][w] = rr; s_red[1][w] = jr; s_red[2][w] = jj; }
     __syncthreads();
+    if (G == 1) {
+      // one CTA holds every inlier (<= 1024 of them, the usual stroke): its own sums are the totals.  No trip through global memory
+      // and no grid barrier — four dependent L2 round trips per evaluation otherwise; same additions in the same order.
+      if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int q = 0; q < kFitThreads / 32; ++q) { a += s_red[0][q]; b += s_red[1][q]; c += s_red[2][q]; }
+        s_tot.rr = a; s_tot.jr = b; s_tot.jj = c;
+      }
+      __syncthreads();
+      const FitSums t1 = s_tot;
+      ++n_eval;
+      __syncthreads();
+      return t1;
+    }
     double* mine = partial + ((size_t)(n_eval & 1u) * G + blockIdx.x) * 3;
     if (threadIdx.x == 0) {
       double a = 0.0, b = 0.0, c = 0.0;

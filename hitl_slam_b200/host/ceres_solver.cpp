@@ -56,7 +56,9 @@ int Problem::block_index(double* values, int size) {
 void Problem::AddParameterBlock(double* values, int size) { block_index(values, size); }
 
 ResidualBlockId Problem::add_block(CostFunction* cost, double* const* blocks, size_t n) {
-  if (residuals_.empty()) { residuals_.reserve(1024); blocks_.reserve(1024); }
+  // One generous reservation instead of growth by doubling: the pose-chain problems of a correction have a few thousand blocks, and
+  // re-growing (allocate, copy, free of ever larger arrays) cost more than the blocks themselves.  Untouched pages cost nothing.
+  if (residuals_.empty()) { residuals_.reserve(8192); blocks_.reserve(8192); }
   residuals_.emplace_back();
   ResidualBlock& rb = residuals_.back();
   rb.cost = cost; rb.residual_offset = num_residuals_;

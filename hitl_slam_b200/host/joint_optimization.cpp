@@ -313,7 +313,8 @@ void JointOpt::AddSTFConstraints(ceres::Problem* problem) {
 
 void JointOpt::AddOdometryConstraints(ceres::Problem* problem) {
   const size_t nb = poses_.size() > 0 ? poses_.size() - 1 : 0;
-  std::vector<float> consts(9 * std::max<size_t>(nb, 1));
+  std::vector<float>& consts = odometry_consts_;      // scratch kept between problems: no 180 KB allocation per build
+  consts.resize(9 * std::max<size_t>(nb, 1));
   for (size_t i = 1; i < poses_.size(); ++i) OdometryBlockConstants(poses_[i - 1], poses_[i], &consts[9 * (i - 1)]);
   check(hitl_set_odometry_blocks(ctx_, (uint32_t)nb, consts.data()), "hitl_set_odometry_blocks");
   evaluator_->Refresh();

@@ -99,6 +99,7 @@ class JointOpt {
   hitl_ctx* ctx_;
   std::vector<hitl_ctx*> shard_ctx_;                           // extra contexts (ranks 1 ..)
   std::unique_ptr<GpuBlockEvaluator> evaluator_;
+  std::vector<float> odometry_consts_;                         // AddOdometryConstraints' upload staging, kept between problems
   std::vector<float> ceres_cost_;
 };
 
